@@ -1,0 +1,187 @@
+"""Seedable synthetic MINLP instance generators and the
+child-batch generator of BASELINE config C3.
+
+These produce *structured models*: every function k (k=0 objective, k=1..m rows) is
+
+    F_k(x) = c_k + a_k.x + 1/2 x'Q_k x + sum_t phi_t(x[S_t])
+
+stored as a python dict of numpy arrays (see `StructuredModel`).  The same dict feeds
+the product (through `bnlp_problem_from_tape`) and the CPU oracle, and can be written
+as an AMPL `.nl` file (`bonmin_b200.nlwrite`).  This module is input generation only:
+no solver arithmetic lives here.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+INF = 1e19  # Bonmin's infinity: min(|nlp_lower_bound_inf|,|nlp_upper_bound_inf|), BonOsiTMINLPInterface.cpp:3002-3005
+
+# variable types as in Bonmin::TMINLP::VariableType (BonTMINLP.hpp:192-196)
+CONTINUOUS, BINARY, INTEGER = 0, 1, 2
+
+
+def pack_lower(Q: np.ndarray) -> np.ndarray:
+    """Row-major packed lower triangle (r>=c) of a symmetric matrix."""
+    n = Q.shape[0]
+    il = np.tril_indices(n)
+    return np.ascontiguousarray(Q[il])
+
+
+def unpack_lower(p: np.ndarray, n: int) -> np.ndarray:
+    Q = np.zeros((n, n))
+    il = np.tril_indices(n)
+    Q[il] = p
+    Q = Q + Q.T - np.diag(np.diag(Q))
+    return Q
+
+
+class StructuredModel(dict):
+    """dict with keys:
+    n, m                       ints
+    xl, xu (n) gl, gu (m)      bounds (|.|>=1e19 = infinite)
+    vtype (n) int32            0 continuous, 1 binary, 2 integer
+    x0 (n)                     starting point
+    c (m+1)                    constants, index 0 = objective
+    A (m+1, n)                 dense linear coefficients (converted to CSR at the C-ABI)
+    qd_fn (nqd) int32          function index of each dense quadratic block
+    qd (nqd, n(n+1)/2)         packed lower triangles, convention 1/2 x'Qx
+    qs_fn,qs_i,qs_j (nqs) int32, qs_v (nqs)   sparse quadratic triplets, i>=j, Q_ij=Q_ji=v
+    terms                      list of (fn, vars[int], prog[(op, iarg, darg)]) general nonlinear element terms
+    name
+    """
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:  # pragma: no cover
+            raise AttributeError(k) from e
+
+
+def _empty_sparse(model):
+    model.setdefault("qs_fn", np.zeros(0, np.int32))
+    model.setdefault("qs_i", np.zeros(0, np.int32))
+    model.setdefault("qs_j", np.zeros(0, np.int32))
+    model.setdefault("qs_v", np.zeros(0))
+    model.setdefault("terms", [])
+    return model
+
+
+def syn_miqcp(n: int, n_int: int, m_q: int, m_l: int, seed: int) -> StructuredModel:
+    """SYN-MIQCP(n, n_int, m_q, m_l, seed) of SURVEY.md Appendix B (C2/C3)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    m = m_q + m_l
+    xl = np.where(np.arange(n) < n_int, 0.0, -10.0)
+    xu = np.full(n, 10.0)
+    vtype = np.where(np.arange(n) < n_int, INTEGER, CONTINUOUS).astype(np.int32)
+    x0 = np.empty(n)
+    x0[:n_int] = rng.integers(2, 9, size=n_int)
+    x0[n_int:] = rng.uniform(-5, 5, size=n - n_int)
+    B0 = rng.standard_normal((n, n)) / np.sqrt(n)
+    Q0 = B0.T @ B0 + 0.1 * np.eye(n)
+    xhat = x0 + 3.0 * rng.standard_normal(n)
+    c0 = -Q0 @ xhat
+    A = np.zeros((m + 1, n))
+    c = np.zeros(m + 1)
+    gl = np.full(m, -INF)
+    gu = np.zeros(m)
+    A[0] = c0
+    qd = [pack_lower(Q0)]
+    qd_fn = [0]
+    for i in range(1, m_q + 1):
+        Bi = rng.standard_normal((8, n)) / np.sqrt(8.0)
+        Qi = Bi.T @ Bi
+        ai = rng.standard_normal(n)
+        q0 = 0.5 * x0 @ Qi @ x0 + ai @ x0
+        bi = q0 + 0.05 * (1 + abs(q0)) * rng.uniform(0.5, 1.5)
+        A[i] = ai
+        gu[i - 1] = bi
+        qd.append(pack_lower(Qi))
+        qd_fn.append(i)
+    for i in range(m_q + 1, m + 1):
+        li = rng.standard_normal(n)
+        li[rng.random(n) < 0.9] = 0.0
+        di = li @ x0 + rng.uniform(0.5, 1.5)
+        A[i] = li
+        gu[i - 1] = di
+    return _empty_sparse(StructuredModel(
+        n=n, m=m, xl=xl, xu=xu, gl=gl, gu=gu, vtype=vtype, x0=x0, c=c, A=A,
+        qd_fn=np.array(qd_fn, np.int32), qd=np.array(qd),
+        name=f"SYN-MIQCP(n={n},n_int={n_int},m_q={m_q},m_l={m_l},seed={seed})"))
+
+
+def config_c2() -> StructuredModel:
+    return syn_miqcp(100, 50, 20, 20, 20261019)
+
+
+def config_c3() -> StructuredModel:
+    return syn_miqcp(200, 100, 40, 40, 20261020)
+
+
+def c3_children(model: StructuredModel, xstar: np.ndarray, B: int, first: int = 0):
+    """Child-batch generator for C3: child k = root bounds +
+    d_k ~ U{0..20} random prior integer branchings + final branch on j = k mod n_int
+    (down if k even else up) at floor/ceil of the root optimum x*.
+    Returns XL, XU of shape (B, n).  Children may be infeasible (intended)."""
+    n = model.n
+    ints = np.flatnonzero(model.vtype != CONTINUOUS)
+    n_int = len(ints)
+    XL = np.tile(model.xl, (B, 1))
+    XU = np.tile(model.xu, (B, 1))
+    for b in range(B):
+        k = first + b
+        r = np.random.Generator(np.random.PCG64(7 + k))
+        d = int(r.integers(0, 21))
+        if d:
+            for jj in r.choice(n_int, d, replace=False):
+                j = ints[jj]
+                up = r.random() < 0.5
+                if abs(xstar[j] - round(xstar[j])) <= 1e-6:
+                    continue
+                if up:
+                    XL[b, j] = max(XL[b, j], np.ceil(xstar[j]))
+                else:
+                    XU[b, j] = min(XU[b, j], np.floor(xstar[j]))
+        j = ints[k % n_int]
+        if k % 2 == 0:
+            XU[b, j] = min(XU[b, j], np.floor(xstar[j]))
+        else:
+            XL[b, j] = max(XL[b, j], np.ceil(xstar[j]))
+    return XL, XU
+
+
+def strong_branching_children(model, xl, xu, xsol, cand):
+    """2K children of one B-BB node (BonChooseVariable.cpp:807-905): for each candidate
+    column j: down child xu_j := floor(x_j), up child xl_j := ceil(x_j).
+    Order: [cand0 down, cand0 up, cand1 down, ...]."""
+    K = len(cand)
+    XL = np.tile(xl, (2 * K, 1))
+    XU = np.tile(xu, (2 * K, 1))
+    for i, j in enumerate(cand):
+        XU[2 * i, j] = np.floor(xsol[j])
+        XL[2 * i + 1, j] = np.ceil(xsol[j])
+    return XL, XU
+
+
+def mytoy() -> StructuredModel:
+    """The model of the reference's only fixture (examples/amplExamples/toy.mod:5-14,
+    variable order of test/mytoy.nl:10: y1, y2, x, z), written out structurally:
+      min -y1 - y2 - x
+      (y1-1/2)^2 + (y2-1/2)^2 <= 1/4 ;  x - y1 <= 0 ;  x + y2 + z <= 2."""
+    n, m = 4, 3
+    A = np.zeros((m + 1, n))
+    c = np.zeros(m + 1)
+    A[0, :3] = -1.0
+    # row 1: y1^2 - y1 + y2^2 - y2 + 1/2
+    A[1, 0] = A[1, 1] = -1.0
+    c[1] = 0.5
+    A[2, 0], A[2, 2] = -1.0, 1.0
+    A[3, 1] = A[3, 2] = A[3, 3] = 1.0
+    return _empty_sparse(StructuredModel(
+        n=n, m=m, xl=np.zeros(n), xu=np.array([INF, INF, 1.0, 5.0]),
+        gl=np.full(m, -INF), gu=np.array([0.25, 0.0, 2.0]),
+        vtype=np.array([CONTINUOUS, CONTINUOUS, BINARY, INTEGER], np.int32),
+        x0=np.zeros(n), c=c, A=A,
+        qd_fn=np.zeros(0, np.int32), qd=np.zeros((0, n * (n + 1) // 2)),
+        qs_fn=np.array([1, 1], np.int32), qs_i=np.array([0, 1], np.int32),
+        qs_j=np.array([0, 1], np.int32), qs_v=np.array([2.0, 2.0]),
+        name="mytoy"))

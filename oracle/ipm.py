@@ -1,0 +1,86 @@
+"""ctypes front end of oracle/ipm_oracle.cpp (TEST INFRASTRUCTURE ONLY).
+
+`solve_batch(model, XL, XU, x0)` solves B child relaxations of a StructuredModel
+(bonmin_b200.instances) on host threads and returns the TMINLP2TNLP result fields
+(src/Interfaces/BonTMINLP2TNLP.cpp:474-509)."""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", _HERE, "libipm_oracle.so"])
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "libipm_oracle.so")
+        if not os.path.exists(path):
+            build()
+        _LIB = ctypes.CDLL(path)
+    return _LIB
+
+
+def dense_arrays(model):
+    """StructuredModel -> (c, A, qidx, Qfull) with every quadratic part densified."""
+    n, m = model.n, model.m
+    qidx = np.full(m + 1, -1, np.int32)
+    mats = []
+    il = np.tril_indices(n)
+    for k, fn in enumerate(model.qd_fn):
+        Q = np.zeros((n, n))
+        Q[il] = model.qd[k]
+        Q = Q + Q.T - np.diag(np.diag(Q))
+        qidx[fn] = len(mats)
+        mats.append(Q)
+    for fn, i, j, v in zip(model.qs_fn, model.qs_i, model.qs_j, model.qs_v):
+        if qidx[fn] < 0:
+            qidx[fn] = len(mats)
+            mats.append(np.zeros((n, n)))
+        Q = mats[qidx[fn]]
+        Q[i, j] += v
+        if i != j:
+            Q[j, i] += v
+    Q = np.ascontiguousarray(np.array(mats)) if mats else np.zeros((0, n, n))
+    return (np.ascontiguousarray(model.c, dtype=np.float64), np.ascontiguousarray(model.A, dtype=np.float64),
+            qidx, Q)
+
+
+def _p(a, t=ctypes.c_double):
+    return a.ctypes.data_as(ctypes.POINTER(t))
+
+
+def solve_batch(model, XL, XU, x0, threads=1, max_iter=0, dense=None):
+    if model.get("terms"):
+        raise NotImplementedError("oracle IPM: general nonlinear terms are not restated yet")
+    n, m = model.n, model.m
+    XL = np.ascontiguousarray(np.atleast_2d(XL), dtype=np.float64)
+    XU = np.ascontiguousarray(np.atleast_2d(XU), dtype=np.float64)
+    B = XL.shape[0]
+    x0 = np.ascontiguousarray(x0, dtype=np.float64)
+    per_child = int(x0.ndim == 2)
+    c, A, qidx, Q = dense if dense is not None else dense_arrays(model)
+    xl = np.ascontiguousarray(model.xl, dtype=np.float64)
+    xu = np.ascontiguousarray(model.xu, dtype=np.float64)
+    gl = np.ascontiguousarray(model.gl, dtype=np.float64)
+    gu = np.ascontiguousarray(model.gu, dtype=np.float64)
+    OBJ = np.zeros(B)
+    STATUS = np.zeros(B, np.int32)
+    ITERS = np.zeros(B, np.int32)
+    P1 = np.zeros(B, np.int32)
+    X = np.zeros((B, n))
+    G = np.zeros((B, max(m, 1)))[:, :m].copy() if m else np.zeros((B, 0))
+    D = np.zeros((B, 2 * n + m))
+    ci = ctypes.c_int
+    lib().oracle_solve_batch(ci(n), ci(m), _p(xl), _p(xu), _p(gl), _p(gu), _p(c), _p(A), _p(qidx, ci), _p(Q),
+                             ci(B), _p(XL), _p(XU), _p(x0), ci(per_child), ci(threads), ci(max_iter),
+                             _p(OBJ), _p(STATUS, ci), _p(ITERS, ci), _p(X), _p(G), _p(D), _p(P1, ci))
+    return dict(obj=OBJ, status=STATUS, iters=ITERS, x=X, g=G, duals=D, phase1_iters=P1)
