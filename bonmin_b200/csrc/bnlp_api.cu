@@ -1,0 +1,436 @@
+// C ABI implementation (include/bnlp.h): model upload, batched solve / eval / OA launches.
+// Product code — must not reference anything under oracle/.  No CPU fallback: every compute entry point
+// needs a CUDA device and fails loudly without one.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/bnlp.h"
+#include "bnlp_internal.h"
+
+namespace bnlp {
+constexpr double kInfD = 1e19;
+}
+#include "bnlp_eval.cuh"
+#include "bnlp_ipm.cuh"
+
+namespace bnlp {
+bool model_from_desc(const bnlp_tape_desc *d, HostModel &M, std::string &err);
+}
+
+using namespace bnlp;
+
+static thread_local std::string g_err;
+static void set_err(const std::string &s) { g_err = s; }
+extern "C" const char *bnlp_last_error(void) { return g_err.c_str(); }
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      set_err(std::string(#call) + ": " + cudaGetErrorString(e_));                                 \
+      return -1;                                                                                   \
+    }                                                                                              \
+  } while (0)
+
+struct bnlp_problem {
+  HostModel M;
+};
+
+namespace {
+
+template <class T>
+struct DBuf {
+  T *p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t cnt) {
+    if (cnt <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    if (cudaMalloc(&p, std::max<size_t>(cnt, 1) * sizeof(T)) != cudaSuccess) return -1;
+    cap = cnt;
+    return 0;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct Device {
+  int id = 0;
+  int sms = 0;
+  size_t smem_optin = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // model
+  DBuf<double> c, A, Qp, row_sgn, row_bnd, gl, gu, xl, xu;
+  DBuf<int> qidx, row_fn, fn_row_up, fn_row_lo;
+  EvalModelDev ev;   // eval / OA view of the tape
+  DBuf<int> e_int;   // packed integer arrays of the eval tape
+  DBuf<double> e_dbl;
+  // solve buffers
+  DBuf<double> dXL, dXU, dX0, dOBJ, dX, dG, dD, ws;
+  DBuf<int> dST, dIT, queue;
+  DBuf<long long> stats;
+  // eval buffers
+  DBuf<double> eX, eLAM, eF, eG, eGF, eJ, eH, eX2, eDU, oVal, oLB, oUB;
+  DBuf<int> oRS, oCI, oSR;
+  DevModel dm{};
+};
+
+}  // namespace
+
+struct bnlp_engine {
+  const bnlp_problem *prob = nullptr;
+  HostModel M;
+  std::vector<Device> devs;
+  bnlp_options opt{};
+  int R = 0, E = 0;
+  int nq = 0;
+  long long launches = 0;
+  long long last_iters = 0, last_fact = 0;
+  double last_ms = 0.0;
+  bool ipm_supported = true;
+  std::string ipm_unsupported_why;
+  int h_in_smem = 1;
+  size_t smem_bytes = 0;
+  size_t ws_doubles = 0;
+  int nnz_jac = 0, nnz_hes = 0, m_nl = 0;
+};
+
+extern "C" bnlp_problem *bnlp_problem_from_tape(const bnlp_tape_desc *desc, char *err, size_t errlen) {
+  auto *p = new bnlp_problem();
+  std::string e;
+  if (!model_from_desc(desc, p->M, e)) {
+    if (err && errlen) snprintf(err, errlen, "%s", e.c_str());
+    set_err(e);
+    delete p;
+    return nullptr;
+  }
+  return p;
+}
+
+extern "C" bnlp_problem *bnlp_problem_from_nl(const char *nl_text, size_t len, char *err, size_t errlen) {
+  auto *p = new bnlp_problem();
+  std::string e;
+  if (!parse_nl(nl_text, len, p->M, e)) {
+    if (err && errlen) snprintf(err, errlen, "%s", e.c_str());
+    set_err(e);
+    delete p;
+    return nullptr;
+  }
+  return p;
+}
+
+extern "C" void bnlp_problem_free(bnlp_problem *p) { delete p; }
+
+extern "C" int bnlp_problem_sizes(const bnlp_problem *p, int *n, int *m, int *nnz_jac, int *nnz_hess) {
+  if (!p) return -1;
+  if (n) *n = p->M.n;
+  if (m) *m = p->M.m;
+  if (nnz_jac) *nnz_jac = (int)p->M.jac_row.size();
+  if (nnz_hess) *nnz_hess = (int)p->M.hes_row.size();
+  return 0;
+}
+
+extern "C" int bnlp_problem_info(const bnlp_problem *p, int *jac_irow, int *jac_jcol, int *hes_irow, int *hes_jcol,
+                                 int *var_type, int *con_nonlinear, double *xl, double *xu, double *gl, double *gu,
+                                 double *x0) {
+  if (!p) return -1;
+  const HostModel &M = p->M;
+  auto cp = [](auto *dst, const auto &v) { if (dst && !v.empty()) std::copy(v.begin(), v.end(), dst); };
+  cp(jac_irow, M.jac_row); cp(jac_jcol, M.jac_col); cp(hes_irow, M.hes_row); cp(hes_jcol, M.hes_col);
+  cp(var_type, M.vtype); cp(con_nonlinear, M.con_nonlinear);
+  cp(xl, M.xl); cp(xu, M.xu); cp(gl, M.gl); cp(gu, M.gu); cp(x0, M.x0);
+  return 0;
+}
+
+static size_t ipm_smem_doubles(int n, int m, int R, int h_in_smem) {
+  const int N = n + 1;
+  const int npad = (N + 2 + 3) & ~3;
+  size_t d = 0;
+  if (h_in_smem) d += (size_t)(((N + 2) * (N + 3) / 2) + 1) & ~(size_t)1;
+  d += (size_t)(IPM_NW + 1) * npad;
+  d += (size_t)7 * npad;
+  const int Rp = (R + 1) & ~1, Kp = (m + 2) & ~1;
+  d += (size_t)10 * Rp + (size_t)5 * Kp + (size_t)IPM_NW * 12;
+  d += (size_t)(N + 2) / 2 + 1;
+  return d;
+}
+
+template <class T>
+static int upload(DBuf<T> &b, const std::vector<T> &v) {
+  if (b.reserve(v.size())) return -1;
+  if (!v.empty() && cudaMemcpy(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) return -1;
+  return 0;
+}
+
+int build_eval_tape(const HostModel &M, std::vector<int> &ints, std::vector<double> &dbls, EvalModelHostOffsets &off);
+
+extern "C" bnlp_engine *bnlp_engine_create(const bnlp_problem *prob, const int *device_ids, int ndev,
+                                           const bnlp_options *opt) {
+  if (!prob) { set_err("null problem"); return nullptr; }
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+    set_err("bnlp_engine_create: no CUDA device available (there is no CPU fallback)");
+    return nullptr;
+  }
+  auto *E = new bnlp_engine();
+  E->prob = prob;
+  E->M = prob->M;
+  if (opt) E->opt = *opt;
+  if (E->opt.tol <= 0) E->opt.tol = 1e-8;
+  if (E->opt.max_iter <= 0) E->opt.max_iter = 3000;
+  const HostModel &M = E->M;
+  const int n = M.n, m = M.m;
+  const size_t P = (size_t)n * (n + 1) / 2;
+  E->nnz_jac = (int)M.jac_row.size();
+  E->nnz_hes = (int)M.hes_row.size();
+  for (int i = 0; i < m; ++i) E->m_nl += M.con_nonlinear[i];
+
+  // ---- IPM view of the model: dense A, one packed quadratic block per function, one-sided rows
+  std::vector<double> A((size_t)(m + 1) * n, 0.0);
+  for (int k = 0; k <= m; ++k)
+    for (int e = M.lin_start[k]; e < M.lin_start[k + 1]; ++e) A[(size_t)k * n + M.lin_col[e]] += M.lin_val[e];
+  std::vector<int> qidx(m + 1, -1);
+  std::vector<double> Qp;
+  auto block_of = [&](int fn) {
+    if (qidx[fn] < 0) { qidx[fn] = (int)(Qp.size() / P); Qp.resize(Qp.size() + P, 0.0); }
+    return Qp.data() + (size_t)qidx[fn] * P;
+  };
+  for (size_t q = 0; q < M.qd_fn.size(); ++q) {
+    double *dst = block_of(M.qd_fn[q]);
+    const double *src = M.qd.data() + q * P;
+    for (size_t e = 0; e < P; ++e) dst[e] += src[e];
+  }
+  for (size_t e = 0; e < M.qs_fn.size(); ++e) {
+    double *dst = block_of(M.qs_fn[e]);
+    dst[(size_t)M.qs_i[e] * (M.qs_i[e] + 1) / 2 + M.qs_j[e]] += M.qs_v[e];
+  }
+  E->nq = (int)(Qp.size() / P);
+  std::vector<int> row_fn, fn_up(m + 1, -1), fn_lo(m + 1, -1);
+  std::vector<double> row_sgn, row_bnd;
+  for (int i = 0; i < m; ++i) {
+    const bool lo = M.gl[i] > -kInf, hi = M.gu[i] < kInf;
+    if (lo && hi && M.gl[i] == M.gu[i]) { E->E++; continue; }
+    if (hi) { fn_up[i + 1] = (int)row_fn.size(); row_fn.push_back(i + 1); row_sgn.push_back(1.0); row_bnd.push_back(M.gu[i]); }
+    if (lo) { fn_lo[i + 1] = (int)row_fn.size(); row_fn.push_back(i + 1); row_sgn.push_back(-1.0); row_bnd.push_back(-M.gl[i]); }
+  }
+  E->R = (int)row_fn.size();
+  if (E->E > 0) { E->ipm_supported = false; E->ipm_unsupported_why = "equality rows are not supported by the batched IPM yet"; }
+  if (!M.terms.empty()) { E->ipm_supported = false; E->ipm_unsupported_why = "general nonlinear terms are not supported by the batched IPM yet"; }
+  if (n > 32 * IPM_MAXC) { E->ipm_supported = false; E->ipm_unsupported_why = "n > 512 is not supported by the batched IPM yet"; }
+
+  std::vector<int> ids;
+  if (ndev <= 0 || !device_ids) ids.push_back(0);
+  else ids.assign(device_ids, device_ids + ndev);
+  E->devs.resize(ids.size());
+
+  std::vector<int> e_ints;
+  std::vector<double> e_dbls;
+  EvalModelHostOffsets eoff;
+  build_eval_tape(M, e_ints, e_dbls, eoff);
+
+  for (size_t d = 0; d < ids.size(); ++d) {
+    Device &D = E->devs[d];
+    D.id = ids[d];
+    if (D.id < 0 || D.id >= count || cudaSetDevice(D.id) != cudaSuccess) {
+      set_err("bad device id");
+      delete E;
+      return nullptr;
+    }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, D.id);
+    D.sms = prop.multiProcessorCount;
+    D.smem_optin = prop.sharedMemPerBlockOptin;
+    cudaStreamCreateWithFlags(&D.stream, cudaStreamNonBlocking);
+    cudaEventCreate(&D.ev0);
+    cudaEventCreate(&D.ev1);
+    int bad = 0;
+    bad |= upload(D.c, M.c); bad |= upload(D.A, A); bad |= upload(D.qidx, qidx); bad |= upload(D.Qp, Qp);
+    bad |= upload(D.row_fn, row_fn); bad |= upload(D.row_sgn, row_sgn); bad |= upload(D.row_bnd, row_bnd);
+    bad |= upload(D.fn_row_up, fn_up); bad |= upload(D.fn_row_lo, fn_lo);
+    bad |= upload(D.gl, M.gl); bad |= upload(D.gu, M.gu); bad |= upload(D.xl, M.xl); bad |= upload(D.xu, M.xu);
+    bad |= upload(D.e_int, e_ints); bad |= upload(D.e_dbl, e_dbls);
+    if (bad) { set_err("device upload failed"); delete E; return nullptr; }
+    D.ev = make_eval_model_dev(eoff, D.e_int.p, D.e_dbl.p, D.gl.p, D.gu.p);
+    DevModel &dm = D.dm;
+    dm.n = n; dm.m = m; dm.N = n + 1; dm.R = E->R; dm.nq = E->nq; dm.P = (int)P;
+    dm.npad = (dm.N + 2 + 3) & ~3;
+    dm.c = D.c.p; dm.A = D.A.p; dm.qidx = D.qidx.p; dm.Qp = D.Qp.p;
+    dm.row_fn = D.row_fn.p; dm.row_sgn = D.row_sgn.p; dm.row_bnd = D.row_bnd.p;
+    dm.fn_row_up = D.fn_row_up.p; dm.fn_row_lo = D.fn_row_lo.p; dm.gl = D.gl.p; dm.gu = D.gu.p;
+    if (d == 0) {
+      const size_t need = ipm_smem_doubles(n, m, E->R, 1) * sizeof(double);
+      E->h_in_smem = need + 1024 <= D.smem_optin ? 1 : 0;
+      E->smem_bytes = ipm_smem_doubles(n, m, E->R, E->h_in_smem) * sizeof(double);
+      if (E->smem_bytes + 1024 > D.smem_optin) { E->ipm_supported = false; E->ipm_unsupported_why = "iterate vectors do not fit shared memory"; }
+      E->ws_doubles = (size_t)2 * (m + 1) * n + (E->h_in_smem ? 0 : (size_t)(n + 3) * (n + 4) / 2 + 2);
+      E->ws_doubles = (E->ws_doubles + 1) & ~(size_t)1;
+    }
+    if (E->ipm_supported &&
+        cudaFuncSetAttribute(ipm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)E->smem_bytes) != cudaSuccess) {
+      set_err(std::string("cudaFuncSetAttribute(ipm_kernel): ") + cudaGetErrorString(cudaGetLastError()));
+      delete E;
+      return nullptr;
+    }
+    D.queue.reserve(1);
+    D.stats.reserve(2);
+  }
+  return E;
+}
+
+extern "C" void bnlp_engine_free(bnlp_engine *E) {
+  if (!E) return;
+  for (Device &D : E->devs) {
+    cudaSetDevice(D.id);
+    for (auto *b : {&D.c, &D.A, &D.Qp, &D.row_sgn, &D.row_bnd, &D.gl, &D.gu, &D.xl, &D.xu, &D.e_dbl, &D.dXL, &D.dXU,
+                    &D.dX0, &D.dOBJ, &D.dX, &D.dG, &D.dD, &D.ws, &D.eX, &D.eLAM, &D.eF, &D.eG, &D.eGF, &D.eJ, &D.eH,
+                    &D.eX2, &D.eDU, &D.oVal, &D.oLB, &D.oUB})
+      b->release();
+    for (auto *b : {&D.qidx, &D.row_fn, &D.fn_row_up, &D.fn_row_lo, &D.e_int, &D.dST, &D.dIT, &D.queue, &D.oRS, &D.oCI,
+                    &D.oSR})
+      b->release();
+    D.stats.release();
+    if (D.stream) cudaStreamDestroy(D.stream);
+    if (D.ev0) cudaEventDestroy(D.ev0);
+    if (D.ev1) cudaEventDestroy(D.ev1);
+  }
+  delete E;
+}
+
+static int launch_ipm(bnlp_engine *E, Device &D, int B, const double *dXL, const double *dXU, const double *dX0,
+                      int x0_per_child, double *dOBJ, int *dST, int *dIT, double *dX, double *dG, double *dD,
+                      cudaStream_t stream) {
+  if (!E->ipm_supported) { set_err("bnlp_solve_batch: " + E->ipm_unsupported_why); return -2; }
+  if (B <= 0) return 0;
+  int ctas = E->opt.ctas_per_device > 0 ? E->opt.ctas_per_device : D.sms;
+  ctas = std::min(ctas, B);
+  if (D.ws.reserve((size_t)ctas * E->ws_doubles)) { set_err("workspace allocation failed"); return -1; }
+  CK(cudaMemsetAsync(D.queue.p, 0, sizeof(int), stream));
+  CK(cudaMemsetAsync(D.stats.p, 0, 2 * sizeof(long long), stream));
+  IpmArgs a{};
+  a.B = B; a.XL = dXL; a.XU = dXU; a.X0 = dX0; a.x0_stride = x0_per_child ? E->M.n : 0;
+  a.OBJ = dOBJ; a.STATUS = dST; a.ITERS = dIT; a.X = dX; a.G = dG; a.DUALS = dD;
+  a.queue = D.queue.p; a.ws = D.ws.p; a.ws_stride = E->ws_doubles; a.h_in_smem = E->h_in_smem; a.stats = D.stats.p;
+  a.o = IpmOpt();
+  a.o.tol = E->opt.tol; a.o.max_iter = E->opt.max_iter;
+  ipm_kernel<<<ctas, IPM_NT, E->smem_bytes, stream>>>(D.dm, a);
+  E->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int bnlp_solve_batch_device(bnlp_engine *E, int dev_index, int B, const double *dXL, const double *dXU,
+                                       const double *dX0, int x0_per_child, double *dOBJ, int *dSTATUS, int *dITERS,
+                                       double *dX, double *dG, double *dDUALS, void *stream) {
+  if (!E || dev_index < 0 || dev_index >= (int)E->devs.size()) { set_err("bad engine/device"); return -1; }
+  Device &D = E->devs[dev_index];
+  CK(cudaSetDevice(D.id));
+  return launch_ipm(E, D, B, dXL, dXU, dX0, x0_per_child, dOBJ, dSTATUS, dITERS, dX, dG, dDUALS, (cudaStream_t)stream);
+}
+
+extern "C" int bnlp_solve_batch(bnlp_engine *E, int B, const double *XL, const double *XU, const double *X0,
+                                int x0_per_child, double *OBJ, int *STATUS, int *ITERS, double *X, double *G,
+                                double *DUALS) {
+  if (!E) { set_err("null engine"); return -1; }
+  if (B <= 0) return 0;
+  const int n = E->M.n, m = E->M.m, nd = (int)E->devs.size();
+  const int per = (B + nd - 1) / nd;  // contiguous child shards, one per device
+  // phase 1: enqueue copies + kernels on every device
+  for (int d = 0; d < nd; ++d) {
+    const int b0 = d * per, nb = std::min(per, B - b0);
+    if (nb <= 0) break;
+    Device &D = E->devs[d];
+    CK(cudaSetDevice(D.id));
+    if (D.dXL.reserve((size_t)nb * n) || D.dXU.reserve((size_t)nb * n) || D.dX0.reserve((size_t)(x0_per_child ? nb : 1) * n) ||
+        D.dOBJ.reserve(nb) || D.dST.reserve(nb) || D.dIT.reserve(nb) || D.dX.reserve((size_t)nb * n) ||
+        D.dG.reserve((size_t)nb * std::max(m, 1)) || D.dD.reserve((size_t)nb * (2 * n + m))) {
+      set_err("device allocation failed");
+      return -1;
+    }
+    CK(cudaEventRecord(D.ev0, D.stream));
+    CK(cudaMemcpyAsync(D.dXL.p, XL + (size_t)b0 * n, (size_t)nb * n * 8, cudaMemcpyHostToDevice, D.stream));
+    CK(cudaMemcpyAsync(D.dXU.p, XU + (size_t)b0 * n, (size_t)nb * n * 8, cudaMemcpyHostToDevice, D.stream));
+    CK(cudaMemcpyAsync(D.dX0.p, X0 + (x0_per_child ? (size_t)b0 * n : 0), (size_t)(x0_per_child ? nb : 1) * n * 8,
+                       cudaMemcpyHostToDevice, D.stream));
+    int rc = launch_ipm(E, D, nb, D.dXL.p, D.dXU.p, D.dX0.p, x0_per_child, D.dOBJ.p, D.dST.p, D.dIT.p,
+                        X ? D.dX.p : nullptr, G ? D.dG.p : nullptr, DUALS ? D.dD.p : nullptr, D.stream);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(OBJ + b0, D.dOBJ.p, (size_t)nb * 8, cudaMemcpyDeviceToHost, D.stream));
+    CK(cudaMemcpyAsync(STATUS + b0, D.dST.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, D.stream));
+    CK(cudaMemcpyAsync(ITERS + b0, D.dIT.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, D.stream));
+    if (X) CK(cudaMemcpyAsync(X + (size_t)b0 * n, D.dX.p, (size_t)nb * n * 8, cudaMemcpyDeviceToHost, D.stream));
+    if (G && m) CK(cudaMemcpyAsync(G + (size_t)b0 * m, D.dG.p, (size_t)nb * m * 8, cudaMemcpyDeviceToHost, D.stream));
+    if (DUALS) CK(cudaMemcpyAsync(DUALS + (size_t)b0 * (2 * n + m), D.dD.p, (size_t)nb * (2 * n + m) * 8, cudaMemcpyDeviceToHost, D.stream));
+    CK(cudaEventRecord(D.ev1, D.stream));
+  }
+  // phase 2: wait and collect statistics
+  E->last_iters = E->last_fact = 0;
+  E->last_ms = 0.0;
+  for (int d = 0; d < nd; ++d) {
+    const int b0 = d * per;
+    if (b0 >= B) break;
+    Device &D = E->devs[d];
+    CK(cudaSetDevice(D.id));
+    CK(cudaStreamSynchronize(D.stream));
+    long long st[2] = {0, 0};
+    CK(cudaMemcpy(st, D.stats.p, sizeof(st), cudaMemcpyDeviceToHost));
+    E->last_iters += st[0]; E->last_fact += st[1];
+    float ms = 0;
+    cudaEventElapsedTime(&ms, D.ev0, D.ev1);
+    E->last_ms = std::max(E->last_ms, (double)ms);
+  }
+  return 0;
+}
+
+extern "C" int bnlp_engine_stats(const bnlp_engine *E, long long *iterations, long long *factorisations, double *device_ms) {
+  if (!E) return -1;
+  if (iterations) *iterations = E->last_iters;
+  if (factorisations) *factorisations = E->last_fact;
+  if (device_ms) *device_ms = E->last_ms;
+  return 0;
+}
+extern "C" long long bnlp_engine_launches(const bnlp_engine *E) { return E ? E->launches : 0; }
+
+// ------------------------------------------------------------------------------------------------ FP64 peak probe
+__global__ void fp64_peak_kernel(double *out, int iters) {
+  double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double b = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+    a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+extern "C" double bnlp_measure_fp64_peak(bnlp_engine *E, int dev_index) {
+  if (!E || dev_index < 0 || dev_index >= (int)E->devs.size()) return -1.0;
+  Device &D = E->devs[dev_index];
+  if (cudaSetDevice(D.id) != cudaSuccess) return -1.0;
+  const int blocks = D.sms * 4, threads = 512, iters = 1 << 16;
+  double *out = nullptr;
+  if (cudaMalloc(&out, (size_t)blocks * threads * 8) != cudaSuccess) return -1.0;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(e0, D.stream);
+    fp64_peak_kernel<<<blocks, threads, 0, D.stream>>>(out, iters);
+    cudaEventRecord(e1, D.stream);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    E->launches++;
+    const double fl = 2.0 * 8.0 * (double)iters * blocks * threads;
+    if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(out);
+  return best;
+}
+
+#include "bnlp_api_eval.inc"

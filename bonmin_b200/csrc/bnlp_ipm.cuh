@@ -1,0 +1,929 @@
+// Batched primal-dual interior-point kernel: ONE CTA PER CHILD RELAXATION, persistent CTAs pulling
+// children from an atomic work queue (variable iteration counts never hold an SM hostage).
+//
+// Replaces, for a whole batch, what Bonmin reaches one child at a time through
+//   TNLPSolver::OptimizeTNLP            /root/reference/src/Interfaces/BonTNLPSolver.hpp:127
+//   IpoptSolver::OptimizeTNLP           /root/reference/src/Interfaces/Ipopt/BonIpoptSolver.cpp:134-176
+// under Bonmin's Ipopt option set (BonIpoptSolver.cpp:265-297) and fills the TMINLP2TNLP result
+// fields (BonTMINLP2TNLP.cpp:474-509).  Algorithm: DESIGN.md §4 (condensed form
+// H = W + Sigma_x + J' Sigma_s J, probing mu oracle, filter line search, exact phase-1 for infeasibility).
+//
+// Data layout per CTA
+//   shared memory : packed lower triangle of the augmented condensed matrix [H; rhs0'; rhs1'] ((N+2)(N+3)/2 f64,
+//                   N = n+1 incl. the phase-1 elastic), all iterate vectors, a 17 x Npad staging area
+//   global (L2)   : raw gradients grad[(m+1) x n] and directional products uq[(m+1) x n] of this child
+//   shared by all : the model (c, A dense, packed quadratic blocks Qp) — read-only, L2 resident
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+namespace bnlp {
+
+constexpr int IPM_NT = 512;           // threads per CTA
+constexpr int IPM_NW = IPM_NT / 32;   // warps per CTA
+constexpr int IPM_KC = 16;            // rank of one staged SYRK / trailing update
+constexpr int IPM_NB = 8;             // Cholesky panel width
+constexpr int IPM_MAXC = 16;          // column accumulators per lane in the symmetric mat-vec: n <= 512
+
+// TNLPSolver::ReturnStatus (BonTNLPSolver.hpp:29-44)
+enum { ST_iterationLimit = -3, ST_computationError = -2, ST_solvedOptimal = 1, ST_solvedOptimalTol = 2,
+       ST_provenInfeasible = 3 };
+
+struct IpmOpt {
+  double tol = 1e-8, acceptable_tol = 1e-6;
+  int max_iter = 3000, acceptable_iter = 15;
+  double dual_inf_tol = 1.0, constr_viol_tol = 1e-4, compl_inf_tol = 1e-4;
+  double bound_relax = 1e-8, bound_push = 0.01, bound_frac = 0.01;
+  double tau_min = 0.99, sigma_min = 1e-6, sigma_max = 100, mu_min = 1e-11, mu_max_fact = 1e3, mu_max = 1e5;
+  double s_max = 100, kappa_sigma = 1e10;
+  double gamma_theta = 1e-4, gamma_phi = 1e-8, eta_phi = 1e-8, s_phi = 2.3, s_theta = 1.1, delta = 1.0;
+  double alpha_min_frac = 0.05, alpha_red = 0.5;
+  double theta_max_fact = 1e4, theta_min_fact = 1e-4;
+  double scal_max_grad = 100.0;
+  double infeas_ytol = 1e8, infeas_ctol = 1e-3, infeas_tol = 1e-7;
+  int max_phase1 = 8;
+  double mu_safeguard = 1e-4;
+};
+
+struct DevModel {
+  int n, m, N, R, nq, P, npad;
+  const double *c, *A;          // (m+1), (m+1) x n
+  const int *qidx;              // m+1 : packed block index or -1
+  const double *Qp;             // nq x P packed lower triangles
+  const int *row_fn;            // R one-sided rows  sgn * F_fn(x) <= bnd
+  const double *row_sgn, *row_bnd;
+  const int *fn_row_up, *fn_row_lo;  // m+1 : row index of the upper / lower side of a function, or -1
+  const double *gl, *gu;        // m
+};
+
+struct IpmArgs {
+  int B;
+  const double *XL, *XU, *X0;   // device: B x n, B x n, (x0_stride ? B x n : n)
+  int x0_stride;
+  double *OBJ; int *STATUS; int *ITERS;
+  double *X, *G, *DUALS;        // B x n, B x m, B x (2n+m); any may be null
+  int *queue;                   // work-queue counter (zeroed by the host)
+  double *ws; size_t ws_stride; // per-CTA global workspace (doubles)
+  int h_in_smem;
+  long long *stats;             // [0] total iterations, [1] factorisations (optional)
+  IpmOpt o;
+};
+
+__device__ __forceinline__ int tri(int i) { return (i * (i + 1)) >> 1; }
+
+// ---- block reductions: v[0..NS) summed, v[NS..NS+NM) maxed; result broadcast to every thread
+template <int NS, int NM>
+__device__ __forceinline__ void block_reduce(double *v, double *red) {
+  constexpr int K = NS + NM;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      double t = __shfl_xor_sync(0xffffffffu, v[k], o);
+      v[k] = (k < NS) ? v[k] + t : fmax(v[k], t);
+    }
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) red[w * K + k] = v[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    double a = red[k];
+    for (int q = 1; q < IPM_NW; ++q) a = (k < NS) ? a + red[q * K + k] : fmax(a, red[q * K + k]);
+    v[k] = a;
+  }
+}
+
+// ---- H[i,k] += sign * sum_c M[c][i] * M[c][k]   for lo <= k <= i < hi  (packed lower triangle, 4x4 register tiles)
+// M is staged in shared memory as K rows of length ld (entries outside [lo,hi) must be zero-padded to a multiple of 4).
+__device__ __forceinline__ void syrk_tiles(double *H, int lo, int hi, const double *M, int ld, int K, double sign) {
+  const int b0 = lo >> 2, b1 = (hi + 3) >> 2;     // tile block range
+  const int nb = b1 - b0;
+  const int ntiles = (nb * (nb + 1)) >> 1;
+  for (int t = threadIdx.x; t < ntiles; t += IPM_NT) {
+    // linear lower-triangular index -> (bi, bk)
+    int bi = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while (tri(bi + 1) <= t) ++bi;
+    while (tri(bi) > t) --bi;
+    const int bk = t - tri(bi);
+    const int i0 = (b0 + bi) << 2, k0 = (b0 + bk) << 2;
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+    for (int c = 0; c < K; ++c) {
+      const double *Mc = M + c * ld;
+      const double2 a01 = *reinterpret_cast<const double2 *>(Mc + i0);
+      const double2 a23 = *reinterpret_cast<const double2 *>(Mc + i0 + 2);
+      const double2 b01 = *reinterpret_cast<const double2 *>(Mc + k0);
+      const double2 b23 = *reinterpret_cast<const double2 *>(Mc + k0 + 2);
+      const double av[4] = {a01.x, a01.y, a23.x, a23.y};
+      const double bv[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int i = i0 + a;
+      if (i < lo || i >= hi) continue;
+      double *Hi = H + tri(i);
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int k = k0 + b;
+        if (k >= lo && k <= i) Hi[k] += sign * acc[a][b];
+      }
+    }
+  }
+}
+
+// ---- blocked right-looking Cholesky of rows/cols [0,N) of the packed matrix; rows [N, Nrows) are carried along
+// (they hold right-hand sides, so the forward substitution L w = rhs happens inside the factorisation).
+// Returns false (block-uniform) on a non-positive pivot.
+__device__ __forceinline__ bool chol_packed(double *H, int N, int Nrows, double *stage, int ld) {
+  for (int j0 = 0; j0 < N; j0 += IPM_NB) {
+    const int nb = min(IPM_NB, N - j0);
+    for (int c = 0; c < nb; ++c) {
+      const int j = j0 + c;
+      __syncthreads();
+      const double d = H[tri(j) + j];
+      if (!(d > 0.0) || !isfinite(d)) return false;
+      const double r = sqrt(d), inv = 1.0 / r;
+      // scale column j (rows j+1 .. Nrows-1)
+      for (int i = j + 1 + threadIdx.x; i < Nrows; i += IPM_NT) H[tri(i) + j] *= inv;
+      __syncthreads();
+      if (threadIdx.x == 0) H[tri(j) + j] = r;
+      // update the remaining panel columns j+1 .. j0+nb-1
+      const int rem = nb - c - 1;
+      if (rem > 0) {
+        const int rows = Nrows - (j + 1);
+        for (int e = threadIdx.x; e < rows * rem; e += IPM_NT) {
+          const int i = j + 1 + e / rem, cc = j + 1 + e % rem;
+          if (cc <= i || i >= N) {
+            if (cc <= i) H[tri(i) + cc] -= H[tri(i) + j] * H[tri(cc) + j];
+            else if (i >= N) H[tri(i) + cc] -= H[tri(i) + j] * H[tri(cc) + j];
+          }
+        }
+      }
+    }
+    const int lo = j0 + nb;
+    if (lo >= Nrows) break;
+    __syncthreads();
+    // stage the panel: stage[c][i] = L[i, j0+c] for i in [lo, Nrows), zero elsewhere in the touched tile range
+    const int lo4 = lo & ~3, hi4 = (Nrows + 3) & ~3;
+    for (int e = threadIdx.x; e < nb * (hi4 - lo4); e += IPM_NT) {
+      const int c = e / (hi4 - lo4), i = lo4 + e % (hi4 - lo4);
+      stage[c * ld + i] = (i >= lo && i < Nrows) ? H[tri(i) + j0 + c] : 0.0;
+    }
+    __syncthreads();
+    syrk_tiles(H, lo, Nrows, stage, ld, nb, -1.0);
+  }
+  __syncthreads();
+  return true;
+}
+
+// ---- backward substitution L' x = w for the two right-hand sides stored in rows N and N+1 (warps 0 and 1)
+__device__ __forceinline__ void backsolve2(double *H, int N) {
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (w < 2) {
+    double *b = H + tri(N + w);
+    for (int i = N - 1; i >= 0; --i) {
+      const double *Li = H + tri(i);
+      const double xi = b[i] / Li[i];
+      __syncwarp();
+      for (int k = lane; k < i; k += 32) b[k] -= Li[k] * xi;
+      if (lane == 0) b[i] = xi;
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+}
+
+// ---- u_k = Q_k d for every packed quadratic block (symmetric mat-vec: each packed element is read once);
+// uq[k][0..n) written to global, du[k] = d.u_k.  `stage` needs (IPM_NW + 1) * ld doubles.
+__device__ __forceinline__ void pass_U(const DevModel &M, const double *d, double *uq, double *du, double *stage,
+                                       int ld, double *red) {
+  const int n = M.n, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nc = (n + 31) >> 5;
+  double *urow = stage + IPM_NW * ld;
+  for (int k = 0; k <= M.m; ++k) {
+    const int q = M.qidx[k];
+    if (q < 0) {
+      if (threadIdx.x == 0) du[k] = 0.0;
+      continue;
+    }
+    const double *Q = M.Qp + (size_t)q * M.P;
+    double col[IPM_MAXC];
+#pragma unroll
+    for (int c = 0; c < IPM_MAXC; ++c) col[c] = 0.0;
+    for (int r = w; r < n; r += IPM_NW) {
+      const double *Qr = Q + tri(r);
+      const double dr = d[r];
+      double rs = 0.0;
+#pragma unroll
+      for (int c = 0; c < IPM_MAXC; ++c) {
+        const int j = lane + 32 * c;
+        if (c < nc && j <= r) {
+          const double qv = __ldg(Qr + j);
+          rs = fma(qv, d[j], rs);
+          if (j < r) col[c] = fma(qv, dr, col[c]);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
+      if (lane == 0) urow[r] = rs;
+    }
+#pragma unroll
+    for (int c = 0; c < IPM_MAXC; ++c) {
+      const int j = lane + 32 * c;
+      if (c < nc && j < n) stage[w * ld + j] = col[c];
+    }
+    __syncthreads();
+    double part = 0.0;
+    for (int j = threadIdx.x; j < n; j += IPM_NT) {
+      double u = urow[j];
+      for (int ww = 0; ww < IPM_NW; ++ww) u += stage[ww * ld + j];
+      uq[(size_t)k * n + j] = u;
+      part = fma(d[j], u, part);
+    }
+    double v[1] = {part};
+    block_reduce<1, 0>(v, red);
+    if (threadIdx.x == 0) du[k] = v[0];
+    __syncthreads();
+  }
+  __syncthreads();
+}
+
+// out[k] = base_k . d  for k = 0..m  (base = raw gradients, one warp per function)
+__device__ __forceinline__ void dots_grad(const DevModel &M, const double *grad, const double *d0, const double *d1,
+                                          double *g0, double *g1) {
+  const int n = M.n, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int k = w; k <= M.m; k += IPM_NW) {
+    const double *g = grad + (size_t)k * n;
+    double a = 0.0, b = 0.0;
+    for (int j = lane; j < n; j += 32) {
+      const double gv = g[j];
+      a = fma(gv, d0[j], a);
+      b = fma(gv, d1[j], b);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (lane == 0) { g0[k] = a; g1[k] = b; }
+  }
+  __syncthreads();
+}
+
+enum { F_FIXED = 1, F_HASL = 2, F_HASU = 4 };
+
+__global__ void __launch_bounds__(IPM_NT, 1) ipm_kernel(DevModel M, IpmArgs A) {
+  extern __shared__ __align__(16) double smem[];
+  const int n = M.n, m = M.m, N = M.N, R = M.R, npad = M.npad;
+  const int tid = threadIdx.x;
+  const IpmOpt &o = A.o;
+  // ---- carve shared memory
+  double *sp = smem;
+  const int Haug = tri(N + 2);
+  double *H;
+  double *ws = A.ws + (size_t)blockIdx.x * A.ws_stride;
+  double *grad = ws;                              // (m+1) x n
+  double *uq = grad + (size_t)(m + 1) * n;        // (m+1) x n
+  if (A.h_in_smem) { H = sp; sp += (Haug + 1) & ~1; } else { H = uq + (size_t)(m + 1) * n; }
+  double *stage = sp; sp += (IPM_NW + 1) * npad;
+  double *x = sp; sp += npad;
+  double *zL = sp; sp += npad;
+  double *zU = sp; sp += npad;
+  double *Lr = sp; sp += npad;
+  double *Ur = sp; sp += npad;
+  double *dx = sp; sp += npad;
+  double *Sx = sp; sp += npad;
+  const int Rp = (R + 1) & ~1, Kp = (m + 2) & ~1;
+  double *s = sp; sp += Rp;
+  double *v = sp; sp += Rp;
+  double *rc = sp; sp += Rp;
+  double *ds = sp; sp += Rp;
+  double *dv = sp; sp += Rp;
+  double *Ss = sp; sp += Rp;
+  double *bb = sp; sp += Rp;
+  double *fsc = sp; sp += Rp;       // sc_r * sgn_r
+  double *jd0 = sp; sp += Rp;       // J d0, J d1 per row
+  double *jd1 = sp; sp += Rp;
+  double *val = sp; sp += Kp;
+  double *gd0 = sp; sp += Kp;
+  double *gd1 = sp; sp += Kp;
+  double *du = sp; sp += Kp;
+  double *wq = sp; sp += Kp;
+  double *red = sp; sp += IPM_NW * 12;
+  int *flg = reinterpret_cast<int *>(sp);  // N ints
+  __shared__ int s_child;
+  double *d0 = H + tri(N), *d1 = H + tri(N + 1);   // solutions live in the augmented rows
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_child = atomicAdd(A.queue, 1);
+    __syncthreads();
+    const int child = s_child;
+    if (child >= A.B) break;
+    const double *xl = A.XL + (size_t)child * n, *xu = A.XU + (size_t)child * n;
+    const double *x0 = A.X0 + (size_t)child * A.x0_stride;
+
+    // ------------------------------------------------------------------ bounds, fixed variables, start point
+    double acc2[2] = {0.0, 0.0};  // [0] sum inconsistent, [1] max width
+    double badw = 0.0;
+    for (int j = tid; j < N; j += IPM_NT) {
+      int f = 0;
+      double l, u, xx;
+      if (j < n) {
+        l = xl[j]; u = xu[j];
+        if (l > -kInfD) f |= F_HASL;
+        if (u < kInfD) f |= F_HASU;
+        if (u < l) { acc2[0] += 1.0; badw = fmax(badw, l - u); }
+        if (u <= l) f |= F_FIXED;
+        acc2[1] = fmax(acc2[1], u - l);
+        xx = x0[j];
+        double lr = l, ur = u;
+        if (f & F_FIXED) { xx = l; }
+        else {
+          if (f & F_HASL) lr = l - o.bound_relax * fmax(1.0, fabs(l));
+          if (f & F_HASU) ur = u + o.bound_relax * fmax(1.0, fabs(u));
+          if ((f & F_HASL) && (f & F_HASU)) {
+            const double pl = fmin(o.bound_push * fmax(1.0, fabs(lr)), o.bound_frac * (ur - lr));
+            const double pu = fmin(o.bound_push * fmax(1.0, fabs(ur)), o.bound_frac * (ur - lr));
+            xx = fmin(fmax(xx, lr + pl), ur - pu);
+          } else if (f & F_HASL) xx = fmax(xx, lr + o.bound_push * fmax(1.0, fabs(lr)));
+          else if (f & F_HASU) xx = fmin(xx, ur - o.bound_push * fmax(1.0, fabs(ur)));
+        }
+        Lr[j] = lr; Ur[j] = ur;
+      } else {  // elastic t: fixed at 0 outside phase 1
+        f = F_HASL | F_FIXED; xx = 0.0; Lr[j] = -o.bound_relax; Ur[j] = kInfD;
+      }
+      x[j] = xx; flg[j] = f; zL[j] = 0.0; zU[j] = 0.0;
+    }
+    {
+      double r2[3] = {acc2[0], acc2[1], badw};
+      block_reduce<1, 2>(r2, red);
+      acc2[0] = r2[0]; acc2[1] = r2[1]; badw = r2[2];
+    }
+    const bool inconsistent = acc2[0] > 0.0;
+    const bool all_fixed = !inconsistent && acc2[1] <= 1e-5;
+    if (inconsistent) {  // evaluate at the start point clipped into the (crossed) box
+      for (int j = tid; j < n; j += IPM_NT) {
+        const double lo = fmin(xl[j], xu[j]), hi = fmax(xl[j], xu[j]);
+        x[j] = fmin(fmax(x0[j], lo), hi);
+      }
+    } else if (all_fixed) {
+      for (int j = tid; j < n; j += IPM_NT) x[j] = xl[j];
+    }
+    __syncthreads();
+
+    // ------------------------------------------------------------------ full evaluation at x: grad_k = a_k + Q_k x
+    pass_U(M, x, uq, du, stage, npad, red);
+    {
+      const int w = tid >> 5, lane = tid & 31;
+      for (int k = w; k <= m; k += IPM_NW) {
+        const double *a = M.A + (size_t)k * n;
+        double *g = grad + (size_t)k * n;
+        const bool hq = M.qidx[k] >= 0;
+        const double *u = uq + (size_t)k * n;
+        double acc = 0.0;
+        for (int j = lane; j < n; j += 32) {
+          const double aj = a[j], uj = hq ? u[j] : 0.0;
+          g[j] = aj + uj;
+          acc = fma(x[j], aj + 0.5 * uj, acc);
+        }
+#pragma unroll
+        for (int q = 16; q > 0; q >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, q);
+        if (lane == 0) val[k] = M.c[k] + acc;
+      }
+    }
+    __syncthreads();
+
+    int status = 0;
+    int iters = 0;
+    double objv = 0.0;
+    bool with_duals = false;
+    double sf = 1.0;
+    bool done = false;
+
+    if (inconsistent || all_fixed) {
+      // all-variables-fixed short cut (BonTNLPSolver.cpp:78-161) / trivially infeasible crossed bounds
+      double t[1] = {0.0};
+      double infe = 0.0;
+      for (int i = tid; i < m; i += IPM_NT) {
+        const double g = val[i + 1];
+        if (M.gu[i] < kInfD) t[0] = fmax(t[0], g - M.gu[i]);
+        if (M.gl[i] > -kInfD) t[0] = fmax(t[0], M.gl[i] - g);
+        if (g - M.gl[i] < -1e-7 || g - M.gu[i] > 1e-7) infe = 1.0;
+      }
+      double r2[2] = {t[0], infe};
+      block_reduce<0, 2>(r2, red);
+      if (inconsistent) { status = ST_provenInfeasible; objv = fmax(badw, r2[0]); }
+      else { status = (r2[1] > 0.0) ? ST_provenInfeasible : ST_solvedOptimal; objv = val[0]; }
+      done = true;
+    }
+
+    bool phase1 = false;
+    int phase1_entries = 0, iters_main = 0, acceptable_cnt = 0;
+    double theta_init = -1.0, mu_max = -1.0, delta_w_last = 0.0;
+    double th_hist[4] = {0, 0, 0, 0}, a_last0 = 1.0, a_last1 = 1.0;
+    long long nfact = 0;
+
+    if (!done) {
+      // ---------------------------------------------------------------- gradient-based scaling, rows, slacks
+      {
+        const int w = tid >> 5, lane = tid & 31;
+        for (int k = w; k <= m; k += IPM_NW) {
+          const double *g = grad + (size_t)k * n;
+          double gm = 0.0;
+          for (int j = lane; j < n; j += 32)
+            if (!(flg[j] & F_FIXED)) gm = fmax(gm, fabs(g[j]));
+#pragma unroll
+          for (int q = 16; q > 0; q >>= 1) gm = fmax(gm, __shfl_xor_sync(0xffffffffu, gm, q));
+          if (lane == 0) wq[k] = (gm > o.scal_max_grad) ? o.scal_max_grad / gm : 1.0;
+        }
+      }
+      __syncthreads();
+      sf = wq[0];
+      for (int r = tid; r < R; r += IPM_NT) {
+        const int fn = M.row_fn[r];
+        const double sc = wq[fn], sg = M.row_sgn[r];
+        const double b = sc * M.row_bnd[r];
+        fsc[r] = sc * sg;
+        bb[r] = b + o.bound_relax * fmax(1.0, fabs(b));
+      }
+      __syncthreads();
+    }
+
+    // helpers (all block-uniform)
+    auto init_slacks_mults = [&]() {
+      for (int r = tid; r < R; r += IPM_NT) {
+        const double h = fsc[r] * val[M.row_fn[r]] - (phase1 ? x[n] : 0.0);
+        s[r] = fmax(bb[r] - h, o.bound_push * fmax(1.0, fabs(bb[r])));
+        v[r] = 1.0;
+      }
+      for (int j = tid; j < N; j += IPM_NT) {
+        const int f = flg[j];
+        zL[j] = (!(f & F_FIXED) && (f & F_HASL)) ? 1.0 : 0.0;
+        zU[j] = (!(f & F_FIXED) && (f & F_HASU)) ? 1.0 : 0.0;
+      }
+      __syncthreads();
+    };
+    if (!done) init_slacks_mults();
+
+    while (!done) {
+      const double of = phase1 ? 0.0 : sf;
+      const double tcur = phase1 ? x[n] : 0.0;
+      // ---------------------------------------------------------------- residuals and error measures
+      // sweep 1 over rows: rc, Ss, sums
+      double a9[9];  // sums: th, sum_v, compl_sum(rows); max: compl_inf, cviol, cviol_unsc, vmax, viol_max ; sum viol_l1
+      double th_p = 0, sumv_p = 0, cs_p = 0, vl1_p = 0, ci_p = 0, cv_p = 0, cvu_p = 0, vmax_p = 0, viol_p = -1e300;
+      for (int r = tid; r < R; r += IPM_NT) {
+        const double hraw = fsc[r] * val[M.row_fn[r]];
+        const double res = hraw - tcur + s[r] - bb[r];
+        rc[r] = res;
+        Ss[r] = v[r] / s[r];
+        th_p += fabs(res);
+        sumv_p += v[r];
+        cs_p += s[r] * v[r];
+        vl1_p += fmax(0.0, hraw - bb[r]);
+        ci_p = fmax(ci_p, s[r] * v[r]);
+        cv_p = fmax(cv_p, fabs(res));
+        cvu_p = fmax(cvu_p, fabs(res) / fabs(fsc[r]));
+        vmax_p = fmax(vmax_p, v[r]);
+        viol_p = fmax(viol_p, hraw - bb[r]);
+      }
+      __syncthreads();
+      // sweep 2 over variables: gradient of the Lagrangian (J' v), rhs vectors, Sigma_x
+      double di_p = 0, sumz_p = 0, nz_p = 0;
+      for (int j = tid; j < N; j += IPM_NT) {
+        const int f = flg[j];
+        double r0 = 0.0, r1 = 0.0, sx = 0.0;
+        if (!(f & F_FIXED)) {
+          double g0 = (j < n) ? of * grad[j] : (phase1 ? 1.0 : 0.0);
+          double jv = 0.0, a0 = 0.0, a1 = 0.0;
+          if (j < n) {
+            for (int r = 0; r < R; ++r) {
+              const double Jrj = fsc[r] * grad[(size_t)M.row_fn[r] * n + j];
+              jv = fma(Jrj, v[r], jv);
+              a0 = fma(Jrj, Ss[r] * rc[r], a0);
+              a1 += Jrj / s[r];
+            }
+          } else {
+            for (int r = 0; r < R; ++r) { jv -= v[r]; a0 -= Ss[r] * rc[r]; a1 -= 1.0 / s[r]; }
+          }
+          const double gl = g0 + jv;
+          di_p = fmax(di_p, fabs(gl - zL[j] + zU[j]));
+          r0 = -g0 - a0;
+          r1 = -a1;
+          if (f & F_HASL) {
+            const double sl = x[j] - Lr[j];
+            ci_p = fmax(ci_p, sl * zL[j]); cs_p += sl * zL[j]; sumz_p += zL[j]; nz_p += 1.0;
+            sx += zL[j] / sl; r1 += 1.0 / sl;
+          }
+          if (f & F_HASU) {
+            const double su = Ur[j] - x[j];
+            ci_p = fmax(ci_p, su * zU[j]); cs_p += su * zU[j]; sumz_p += zU[j]; nz_p += 1.0;
+            sx += zU[j] / su; r1 -= 1.0 / su;
+          }
+        }
+        Sx[j] = sx;
+        d0[j] = r0;   // right-hand sides go straight into the augmented rows
+        d1[j] = r1;
+      }
+      a9[0] = th_p; a9[1] = sumv_p; a9[2] = cs_p; a9[3] = vl1_p; a9[4] = sumz_p; a9[5] = nz_p;
+      double m6[6] = {ci_p, cv_p, cvu_p, vmax_p, viol_p, di_p};
+      {
+        double all[12] = {a9[0], a9[1], a9[2], a9[3], a9[4], a9[5], m6[0], m6[1], m6[2], m6[3], m6[4], m6[5]};
+        block_reduce<6, 6>(all, red);
+        a9[0] = all[0]; a9[1] = all[1]; a9[2] = all[2]; a9[3] = all[3]; a9[4] = all[4]; a9[5] = all[5];
+        m6[0] = all[6]; m6[1] = all[7]; m6[2] = all[8]; m6[3] = all[9]; m6[4] = all[10]; m6[5] = all[11];
+      }
+      const double th = a9[0], sum_v = a9[1], vl1 = a9[3];
+      const double nz = a9[5] + (double)R, sum_z = a9[4] + sum_v;
+      const double compl_inf = m6[0], cviol = m6[1], cviol_unsc = m6[2], ymax = m6[3], viol_max = m6[4], dual_inf = m6[5];
+      const double avg_compl = nz > 0 ? a9[2] / nz : 0.0;
+      if (theta_init < 0) theta_init = th;
+      const double s_d = fmax(o.s_max, (sum_v + sum_z) / fmax(1.0, (double)R + nz)) / o.s_max;
+      const double s_c = fmax(o.s_max, sum_z / fmax(1.0, nz)) / o.s_max;
+      const double E0 = fmax(fmax(dual_inf / s_d, cviol), compl_inf / s_c);
+      if (mu_max < 0) mu_max = fmin(o.mu_max, o.mu_max_fact * fmax(avg_compl, 1e-300));
+
+      // ---------------------------------------------------------------- termination tests
+      const double osc = phase1 ? 1.0 : sf;
+      const bool conv = E0 <= o.tol && dual_inf / osc <= o.dual_inf_tol && cviol_unsc <= o.constr_viol_tol &&
+                        compl_inf / osc <= o.compl_inf_tol;
+      const bool acc = E0 <= o.acceptable_tol && cviol_unsc <= 1e-2 && compl_inf / osc <= 1e-2;
+      acceptable_cnt = acc ? acceptable_cnt + 1 : 0;
+      bool to_main = false, to_p1 = false;
+      if (phase1) {
+        if (vl1 <= 0.0) to_main = true;
+        else if (conv || acceptable_cnt >= o.acceptable_iter) {
+          if (viol_max > o.infeas_tol) { status = ST_provenInfeasible; done = true; break; }
+          to_main = true;
+        }
+      } else {
+        if (conv) { status = ST_solvedOptimal; objv = val[0]; with_duals = true; done = true; break; }
+        if (acceptable_cnt >= o.acceptable_iter) { status = ST_solvedOptimalTol; objv = val[0]; with_duals = true; done = true; break; }
+      }
+      if (!to_main && iters >= o.max_iter) { status = ST_iterationLimit; objv = val[0]; with_duals = true; done = true; break; }
+      if (!to_main && !phase1) {
+        th_hist[iters_main & 3] = vl1;
+        const double vold = th_hist[(iters_main + 1) & 3];
+        bool stall = iters_main >= 3 && vold > 0.0 && vl1 > 0.9 * vold && a_last0 < 0.3 && a_last1 < 0.3;
+        iters_main++;
+        if (phase1_entries > 0) stall = false;
+        if (th > o.infeas_ctol && (ymax > o.infeas_ytol || stall) && vl1 > 0.0) {
+          if (phase1_entries >= o.max_phase1) { status = ST_iterationLimit; objv = val[0]; with_duals = true; done = true; break; }
+          to_p1 = true;
+        }
+      }
+      if (to_main) {
+        __syncthreads();
+        phase1 = false; iters_main = 0;
+        if (tid == 0) { flg[n] |= F_FIXED; x[n] = 0.0; }
+        __syncthreads();
+        init_slacks_mults();
+        theta_init = -1; mu_max = -1; acceptable_cnt = 0;
+        ++iters;
+        continue;
+      }
+      auto enter_phase1 = [&]() {
+        __syncthreads();
+        phase1 = true; phase1_entries++;
+        const double vm = fmax(0.0, viol_max), T = fmax(1.0, vm);
+        if (tid == 0) { flg[n] &= ~F_FIXED; Lr[n] = -T; x[n] = 1.1 * vm + 0.1 * T; }
+        __syncthreads();
+        init_slacks_mults();
+        theta_init = -1; mu_max = -1; acceptable_cnt = 0;
+      };
+      if (to_p1) { enter_phase1(); ++iters; continue; }
+
+      // ---------------------------------------------------------------- condensed matrix + factorisation
+      for (int k = tid; k <= m; k += IPM_NT) {
+        double w = (k == 0) ? of : 0.0;
+        const int ru = M.fn_row_up[k], rl = M.fn_row_lo[k];
+        if (ru >= 0) w += v[ru] * fsc[ru];
+        if (rl >= 0) w += v[rl] * fsc[rl];
+        wq[k] = w;
+      }
+      __syncthreads();
+      double delta_w = 0.0;
+      bool fact_ok = false;
+      for (int attempt = 0; attempt < 45; ++attempt) {
+        // W pass: H[i,k] = sum_q wq[q] Qp_q[i,k] (+ diagonal), one warp per row, fixed rows/cols -> identity
+        {
+          const int w = tid >> 5, lane = tid & 31;
+          for (int i = w; i < N; i += IPM_NW) {
+            double *Hi = H + tri(i);
+            const int fi = flg[i] & F_FIXED;
+            for (int k = lane; k <= i; k += 32) {
+              double a = 0.0;
+              if (fi || (flg[k] & F_FIXED)) a = (i == k) ? 1.0 : 0.0;
+              else {
+                if (i < n) {
+                  const size_t e = (size_t)tri(i) + k;
+                  for (int fn = 0; fn <= m; ++fn) {
+                    const int q = M.qidx[fn];
+                    if (q >= 0) a = fma(wq[fn], __ldg(M.Qp + (size_t)q * M.P + e), a);
+                  }
+                }
+                if (i == k) a += Sx[i] + delta_w;
+              }
+              Hi[k] = a;
+            }
+          }
+        }
+        __syncthreads();
+        // J' Sigma_s J through staged rank-KC updates: stage[c][j] = sqrt(Ss_r) J[r][j]
+        for (int r0 = 0; r0 < R; r0 += IPM_KC) {
+          const int kc = min(IPM_KC, R - r0);
+          for (int e = tid; e < kc * npad; e += IPM_NT) {
+            const int c = e / npad, j = e % npad, r = r0 + c;
+            double vv = 0.0;
+            if (j < N && !(flg[j] & F_FIXED)) {
+              const double sq = sqrt(Ss[r]);
+              vv = (j < n) ? sq * fsc[r] * grad[(size_t)M.row_fn[r] * n + j] : -sq;
+            }
+            stage[c * npad + j] = vv;
+          }
+          __syncthreads();
+          syrk_tiles(H, 0, N, stage, npad, kc, 1.0);
+          __syncthreads();
+        }
+        ++nfact;
+        if (chol_packed(H, N, N + 2, stage, npad)) { fact_ok = true; break; }
+        // inertia correction (first_hessian_perturbation 1e-4, x100 then x8, /3 between iterations)
+        if (delta_w == 0.0) delta_w = (delta_w_last == 0.0) ? 1e-4 : fmax(1e-20, delta_w_last / 3.0);
+        else delta_w *= (delta_w_last == 0.0 ? 100.0 : 8.0);
+        if (delta_w > 1e20) break;
+        __syncthreads();
+        // the failed factorisation destroyed the right-hand sides: rebuild them
+        for (int j = tid; j < N; j += IPM_NT) {
+          const int f = flg[j];
+          double r0 = 0.0, r1 = 0.0;
+          if (!(f & F_FIXED)) {
+            double g0 = (j < n) ? of * grad[j] : (phase1 ? 1.0 : 0.0);
+            double a0 = 0.0, a1 = 0.0;
+            if (j < n) {
+              for (int r = 0; r < R; ++r) {
+                const double Jrj = fsc[r] * grad[(size_t)M.row_fn[r] * n + j];
+                a0 = fma(Jrj, Ss[r] * rc[r], a0);
+                a1 += Jrj / s[r];
+              }
+            } else {
+              for (int r = 0; r < R; ++r) { a0 -= Ss[r] * rc[r]; a1 -= 1.0 / s[r]; }
+            }
+            r0 = -g0 - a0; r1 = -a1;
+            if (f & F_HASL) r1 += 1.0 / (x[j] - Lr[j]);
+            if (f & F_HASU) r1 -= 1.0 / (Ur[j] - x[j]);
+          }
+          d0[j] = r0; d1[j] = r1;
+        }
+        __syncthreads();
+      }
+      if (!fact_ok) { status = ST_computationError; objv = val[0]; with_duals = true; done = true; break; }
+      if (delta_w > 0) delta_w_last = delta_w;
+      backsolve2(H, N);   // d0 = H^-1 rhs0, d1 = H^-1 rhs1
+
+      // ---------------------------------------------------------------- J d0, J d1 per row
+      dots_grad(M, grad, d0, d1, gd0, gd1);
+      for (int r = tid; r < R; r += IPM_NT) {
+        const int fn = M.row_fn[r];
+        jd0[r] = fsc[r] * gd0[fn] - d0[n];
+        jd1[r] = fsc[r] * gd1[fn] - d1[n];
+      }
+      __syncthreads();
+
+      // direction for a given mu, evaluated on the fly:  dx = d0 + mu d1
+      // fraction-to-the-boundary + (optional) complementarity at the trial point
+      auto ftb = [&](double mu, double tau, double &ap, double &ad) {
+        double mn[2] = {-1.0, -1.0};  // max of -alpha  => min alpha
+        for (int j = tid; j < N; j += IPM_NT) {
+          const int f = flg[j];
+          if (f & F_FIXED) continue;
+          const double dxj = d0[j] + mu * d1[j];
+          if (f & F_HASL) {
+            const double sl = x[j] - Lr[j];
+            if (dxj < 0) mn[0] = fmax(mn[0], -(-tau * sl / dxj));
+            const double dz = mu / sl - zL[j] - zL[j] / sl * dxj;
+            if (dz < 0) mn[1] = fmax(mn[1], -(-tau * zL[j] / dz));
+          }
+          if (f & F_HASU) {
+            const double su = Ur[j] - x[j];
+            if (dxj > 0) mn[0] = fmax(mn[0], -(tau * su / dxj));
+            const double dz = mu / su - zU[j] + zU[j] / su * dxj;
+            if (dz < 0) mn[1] = fmax(mn[1], -(-tau * zU[j] / dz));
+          }
+        }
+        for (int r = tid; r < R; r += IPM_NT) {
+          const double dsr = -rc[r] - (jd0[r] + mu * jd1[r]);
+          const double dvr = mu / s[r] - v[r] - Ss[r] * dsr;
+          if (dsr < 0) mn[0] = fmax(mn[0], -(-tau * s[r] / dsr));
+          if (dvr < 0) mn[1] = fmax(mn[1], -(-tau * v[r] / dvr));
+        }
+        block_reduce<0, 2>(mn, red);
+        ap = fmin(1.0, -mn[0]); ad = fmin(1.0, -mn[1]);
+      };
+      // ---------------------------------------------------------------- probing oracle: sigma = (mu_aff/mu)^3
+      double mu;
+      {
+        double ap, ad;
+        ftb(0.0, 1.0, ap, ad);
+        double t[1] = {0.0};
+        for (int j = tid; j < N; j += IPM_NT) {
+          const int f = flg[j];
+          if (f & F_FIXED) continue;
+          const double dxj = d0[j];
+          if (f & F_HASL) {
+            const double sl = x[j] - Lr[j];
+            const double dz = -zL[j] - zL[j] / sl * dxj;
+            t[0] += (sl + ap * dxj) * (zL[j] + ad * dz);
+          }
+          if (f & F_HASU) {
+            const double su = Ur[j] - x[j];
+            const double dz = -zU[j] + zU[j] / su * dxj;
+            t[0] += (su - ap * dxj) * (zU[j] + ad * dz);
+          }
+        }
+        for (int r = tid; r < R; r += IPM_NT) {
+          const double dsr = -rc[r] - jd0[r];
+          const double dvr = -v[r] - Ss[r] * dsr;
+          t[0] += (s[r] + ap * dsr) * (v[r] + ad * dvr);
+        }
+        block_reduce<1, 0>(t, red);
+        const double mu_aff = nz > 0 ? t[0] / nz : 0.0;
+        double sigma = avg_compl > 0 ? pow(mu_aff / avg_compl, 3.0) : o.sigma_min;
+        sigma = fmin(fmax(sigma, o.sigma_min), o.sigma_max);
+        mu = fmin(fmax(sigma * avg_compl, o.mu_min), mu_max);
+        mu = fmax(mu, fmin(avg_compl, o.mu_safeguard * fmax(cviol, dual_inf / s_d)));
+      }
+      const double tau = fmax(o.tau_min, 1.0 - mu);
+      double ap_max, ad;
+      ftb(mu, tau, ap_max, ad);
+      // final direction
+      for (int j = tid; j < N; j += IPM_NT) dx[j] = (flg[j] & F_FIXED) ? 0.0 : d0[j] + mu * d1[j];
+      for (int r = tid; r < R; r += IPM_NT) {
+        ds[r] = -rc[r] - (jd0[r] + mu * jd1[r]);
+        dv[r] = mu / s[r] - v[r] - Ss[r] * ds[r];
+      }
+      for (int k = tid; k <= m; k += IPM_NT) gd0[k] = gd0[k] + mu * gd1[k];   // gd = grad_k . dx
+      __syncthreads();
+
+      // ---------------------------------------------------------------- u_k = Q_k dx, du_k = dx.u_k
+      pass_U(M, dx, uq, du, stage, npad, red);
+
+      // ---------------------------------------------------------------- filter line search
+      const double dxt = phase1 ? dx[n] : 0.0;
+      auto merit = [&](double a, double &theta, double &phi) {
+        double t2[2] = {0.0, 0.0};
+        const double t = tcur + a * dxt;
+        for (int r = tid; r < R; r += IPM_NT) {
+          const int fn = M.row_fn[r];
+          const double hv = fsc[r] * (val[fn] + a * gd0[fn] + 0.5 * a * a * du[fn]) - t;
+          const double sv = s[r] + a * ds[r];
+          t2[0] += fabs(hv + sv - bb[r]);
+          t2[1] -= mu * log(sv);
+        }
+        for (int j = tid; j < N; j += IPM_NT) {
+          const int f = flg[j];
+          if (f & F_FIXED) continue;
+          const double xv = x[j] + a * dx[j];
+          if (f & F_HASL) t2[1] -= mu * log(xv - Lr[j]);
+          if (f & F_HASU) t2[1] -= mu * log(Ur[j] - xv);
+        }
+        block_reduce<2, 0>(t2, red);
+        theta = t2[0];
+        phi = t2[1] + (phase1 ? t : sf * (val[0] + a * gd0[0] + 0.5 * a * a * du[0]));
+      };
+      double theta0, phi0;
+      merit(0.0, theta0, phi0);
+      double dphi;
+      {
+        double t[1] = {0.0};
+        for (int r = tid; r < R; r += IPM_NT) t[0] -= mu * ds[r] / s[r];
+        for (int j = tid; j < N; j += IPM_NT) {
+          const int f = flg[j];
+          if (f & F_FIXED) continue;
+          if (f & F_HASL) t[0] -= mu * dx[j] / (x[j] - Lr[j]);
+          if (f & F_HASU) t[0] += mu * dx[j] / (Ur[j] - x[j]);
+        }
+        block_reduce<1, 0>(t, red);
+        dphi = t[0] + (phase1 ? dxt : sf * gd0[0]);
+      }
+      const double theta_min = o.theta_min_fact * fmax(1.0, theta_init);
+      const double theta_max = o.theta_max_fact * fmax(1.0, theta_init);
+      double amin = o.gamma_theta;
+      if (dphi < 0) {
+        amin = fmin(amin, o.gamma_phi * theta0 / (-dphi));
+        if (theta0 <= theta_min) amin = fmin(amin, o.delta * pow(theta0, o.s_theta) / pow(-dphi, o.s_phi));
+      }
+      amin *= o.alpha_min_frac;
+      double alpha = ap_max;
+      bool accepted = false;
+      for (int bt = 0; bt < 60; ++bt) {
+        double th_t, ph_t;
+        merit(alpha, th_t, ph_t);
+        const double fuzz = 10.0 * 2.220446049250313e-16 * fabs(phi0);
+        const bool sw = dphi < 0 && theta0 <= theta_min && alpha * pow(-dphi, o.s_phi) > o.delta * pow(theta0, o.s_theta);
+        bool ok;
+        if (sw) ok = ph_t - phi0 <= o.eta_phi * alpha * dphi + fuzz;
+        else ok = (th_t <= (1 - o.gamma_theta) * theta0) || (ph_t - phi0 <= -o.gamma_phi * theta0 + fuzz);
+        if (!(th_t <= theta_max)) ok = false;
+        if (!isfinite(ph_t)) ok = false;
+        if (ok) { accepted = true; break; }
+        alpha *= o.alpha_red;
+        if (alpha < amin) break;
+      }
+      if (!accepted) {
+        if (phase1 || phase1_entries >= o.max_phase1) { status = ST_iterationLimit; objv = val[0]; with_duals = true; done = true; break; }
+        enter_phase1();
+        ++iters;
+        continue;
+      }
+      a_last1 = a_last0; a_last0 = alpha;
+
+      // ---------------------------------------------------------------- accept the step
+      __syncthreads();
+      for (int j = tid; j < N; j += IPM_NT) {
+        const int f = flg[j];
+        if (f & F_FIXED) continue;
+        const double dxj = dx[j];
+        const double xo = x[j];
+        const double xn = xo + alpha * dxj;
+        if (f & F_HASL) {
+          const double sl = xo - Lr[j];
+          const double dz = mu / sl - zL[j] - zL[j] / sl * dxj;
+          const double sn = xn - Lr[j];
+          zL[j] = fmin(fmax(zL[j] + ad * dz, mu / (o.kappa_sigma * sn)), o.kappa_sigma * mu / sn);
+        }
+        if (f & F_HASU) {
+          const double su = Ur[j] - xo;
+          const double dz = mu / su - zU[j] + zU[j] / su * dxj;
+          const double sn = Ur[j] - xn;
+          zU[j] = fmin(fmax(zU[j] + ad * dz, mu / (o.kappa_sigma * sn)), o.kappa_sigma * mu / sn);
+        }
+        x[j] = xn;
+      }
+      for (int r = tid; r < R; r += IPM_NT) {
+        const double sn = s[r] + alpha * ds[r];
+        s[r] = sn;
+        v[r] = fmin(fmax(v[r] + ad * dv[r], mu / (o.kappa_sigma * sn)), o.kappa_sigma * mu / sn);
+      }
+      for (int k = tid; k <= m; k += IPM_NT) val[k] += alpha * gd0[k] + 0.5 * alpha * alpha * du[k];
+      for (int k = 0; k <= m; ++k) {
+        if (M.qidx[k] < 0) continue;
+        double *g = grad + (size_t)k * n;
+        const double *u = uq + (size_t)k * n;
+        for (int j = tid; j < n; j += IPM_NT) g[j] += alpha * u[j];
+      }
+      __syncthreads();
+      ++iters;
+    }
+
+    // ------------------------------------------------------------------ results (TMINLP2TNLP layout)
+    __syncthreads();
+    if (status == ST_provenInfeasible && !(inconsistent || all_fixed)) {
+      double t[1] = {0.0};
+      for (int i = tid; i < m; i += IPM_NT) {
+        const double g = val[i + 1];
+        if (M.gu[i] < kInfD) t[0] = fmax(t[0], g - M.gu[i]);
+        if (M.gl[i] > -kInfD) t[0] = fmax(t[0], M.gl[i] - g);
+      }
+      block_reduce<0, 1>(t, red);
+      objv = t[0];   // max-norm violation, BonTMINLP2TNLP.cpp:503-505
+    }
+    if (tid == 0) {
+      A.OBJ[child] = objv; A.STATUS[child] = status; A.ITERS[child] = iters;
+      if (A.stats) { atomicAdd((unsigned long long *)&A.stats[0], (unsigned long long)iters);
+                     atomicAdd((unsigned long long *)&A.stats[1], (unsigned long long)nfact); }
+    }
+    if (A.X) for (int j = tid; j < n; j += IPM_NT) A.X[(size_t)child * n + j] = all_fixed ? xl[j] : fmin(fmax(x[j], fmin(xl[j], xu[j])), fmax(xl[j], xu[j]));
+    if (A.G) for (int i = tid; i < m; i += IPM_NT) A.G[(size_t)child * m + i] = val[i + 1];
+    if (A.DUALS) {
+      double *D = A.DUALS + (size_t)child * (2 * n + m);
+      for (int j = tid; j < n; j += IPM_NT) {
+        D[j] = with_duals ? zL[j] / sf : 0.0;
+        D[n + j] = with_duals ? zU[j] / sf : 0.0;
+      }
+      for (int i = tid; i < m; i += IPM_NT) {
+        double lam = 0.0;
+        if (with_duals) {
+          const int ru = M.fn_row_up[i + 1], rl = M.fn_row_lo[i + 1];
+          if (ru >= 0) lam += v[ru] * fsc[ru] / sf;
+          if (rl >= 0) lam += v[rl] * fsc[rl] / sf;
+        }
+        D[2 * n + i] = lam;
+      }
+    }
+  }
+}
+
+}  // namespace bnlp

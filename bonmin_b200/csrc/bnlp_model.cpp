@@ -1,0 +1,130 @@
+// Host-side model compiler: structured description -> HostModel with derived sparsity structures.
+// Restates the *data contract* of Bonmin::TMINLP (src/Interfaces/BonTMINLP.hpp:226-333): sizes, bounds, types,
+// Jacobian triplet structure (row-major here), lower-triangular Lagrangian-Hessian structure.
+#include "bnlp_internal.h"
+
+#include <algorithm>
+#include <set>
+
+#include "../../include/bnlp.h"
+
+namespace bnlp {
+
+void HostModel::finalize() {
+  const size_t P = (size_t)n * (n + 1) / 2;
+  // which functions have which kind of nonlinearity
+  std::vector<char> dense_q(m + 1, 0);
+  for (int fn : qd_fn) dense_q[fn] = 1;
+  std::vector<std::set<int>> cols(m + 1);
+  std::set<std::pair<int, int>> hes;
+  std::vector<char> nonlin(m + 1, 0);
+  for (int k = 0; k <= m; ++k)
+    for (int e = lin_start[k]; e < lin_start[k + 1]; ++e) cols[k].insert(lin_col[e]);
+  for (size_t q = 0; q < qd_fn.size(); ++q) {
+    const int fn = qd_fn[q];
+    nonlin[fn] = 1;
+    for (int j = 0; j < n; ++j) cols[fn].insert(j);
+  }
+  bool any_dense = !qd_fn.empty();
+  if (any_dense) {
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j <= i; ++j) hes.insert({i, j});
+  }
+  for (size_t e = 0; e < qs_fn.size(); ++e) {
+    nonlin[qs_fn[e]] = 1;
+    cols[qs_fn[e]].insert(qs_i[e]);
+    cols[qs_fn[e]].insert(qs_j[e]);
+    hes.insert({std::max(qs_i[e], qs_j[e]), std::min(qs_i[e], qs_j[e])});
+  }
+  for (const Term &t : terms) {
+    nonlin[t.fn] = 1;
+    for (int a : t.vars) {
+      cols[t.fn].insert(a);
+      for (int b : t.vars) hes.insert({std::max(a, b), std::min(a, b)});
+    }
+  }
+  (void)P;
+  jac_row.clear(); jac_col.clear(); jac_start.assign(m + 1, 0);
+  for (int i = 0; i < m; ++i) {
+    jac_start[i] = (int)jac_row.size();
+    for (int j : cols[i + 1]) { jac_row.push_back(i); jac_col.push_back(j); }
+  }
+  jac_start[m] = (int)jac_row.size();
+  hes_row.clear(); hes_col.clear();
+  for (auto &p : hes) { hes_row.push_back(p.first); hes_col.push_back(p.second); }
+  grad_f_cols.assign(cols[0].begin(), cols[0].end());
+  con_nonlinear.assign(m, 0);
+  for (int i = 0; i < m; ++i) con_nonlinear[i] = nonlin[i + 1];
+  obj_nonlinear = nonlin[0];
+}
+
+bool model_from_desc(const bnlp_tape_desc *d, HostModel &M, std::string &err) {
+  if (!d || d->n <= 0 || d->m < 0) { err = "bad sizes"; return false; }
+  const int n = d->n, m = d->m;
+  M.n = n; M.m = m;
+  M.xl.assign(d->xl, d->xl + n); M.xu.assign(d->xu, d->xu + n);
+  M.gl.assign(d->gl, d->gl + m); M.gu.assign(d->gu, d->gu + m);
+  if (d->x0) M.x0.assign(d->x0, d->x0 + n); else M.x0.assign(n, 0.0);
+  if (d->var_type) M.vtype.assign(d->var_type, d->var_type + n); else M.vtype.assign(n, 0);
+  M.c.assign(d->c, d->c + m + 1);
+  M.lin_start.assign(d->lin_start, d->lin_start + m + 2);
+  const int nl = M.lin_start[m + 1];
+  M.lin_col.assign(d->lin_col, d->lin_col + nl);
+  M.lin_val.assign(d->lin_val, d->lin_val + nl);
+  for (int e = 0; e < nl; ++e)
+    if (M.lin_col[e] < 0 || M.lin_col[e] >= n) { err = "linear column out of range"; return false; }
+  const size_t P = (size_t)n * (n + 1) / 2;
+  M.qd_fn.assign(d->qd_fn, d->qd_fn + d->n_qdense);
+  M.qd.assign(d->qd, d->qd + (size_t)d->n_qdense * P);
+  for (int fn : M.qd_fn)
+    if (fn < 0 || fn > m) { err = "dense quadratic function index out of range"; return false; }
+  M.qs_fn.assign(d->qs_fn, d->qs_fn + d->n_qsparse);
+  M.qs_i.assign(d->qs_i, d->qs_i + d->n_qsparse);
+  M.qs_j.assign(d->qs_j, d->qs_j + d->n_qsparse);
+  M.qs_v.assign(d->qs_v, d->qs_v + d->n_qsparse);
+  for (int e = 0; e < d->n_qsparse; ++e) {
+    if (M.qs_fn[e] < 0 || M.qs_fn[e] > m || M.qs_i[e] < 0 || M.qs_i[e] >= n || M.qs_j[e] < 0 || M.qs_j[e] >= n) {
+      err = "sparse quadratic index out of range"; return false;
+    }
+    if (M.qs_i[e] < M.qs_j[e]) std::swap(M.qs_i[e], M.qs_j[e]);
+  }
+  M.terms.clear();
+  for (int t = 0; t < d->n_terms; ++t) {
+    Term T;
+    T.fn = d->term_fn[t];
+    if (T.fn < 0 || T.fn > m) { err = "term function index out of range"; return false; }
+    T.vars.assign(d->term_var + d->term_var_start[t], d->term_var + d->term_var_start[t + 1]);
+    if ((int)T.vars.size() > BNLP_MAX_TERM_VARS) { err = "term has more than BNLP_MAX_TERM_VARS variables"; return false; }
+    for (int v : T.vars) if (v < 0 || v >= n) { err = "term variable out of range"; return false; }
+    const int a = d->term_op_start[t], b = d->term_op_start[t + 1];
+    T.op.assign(d->term_op + a, d->term_op + b);
+    T.iarg.assign(d->term_iarg + a, d->term_iarg + b);
+    T.darg.assign(d->term_darg + a, d->term_darg + b);
+    // validate stack discipline
+    int depth = 0, maxd = 0;
+    for (size_t k = 0; k < T.op.size(); ++k) {
+      switch (T.op[k]) {
+        case BNLP_OP_CONST: depth++; break;
+        case BNLP_OP_VAR:
+          if (T.iarg[k] < 0 || T.iarg[k] >= (int)T.vars.size()) { err = "term VAR slot out of range"; return false; }
+          depth++; break;
+        case BNLP_OP_ADD: case BNLP_OP_SUB: case BNLP_OP_MUL: case BNLP_OP_DIV: case BNLP_OP_POW:
+          if (depth < 2) { err = "term stack underflow"; return false; }
+          depth--; break;
+        case BNLP_OP_NEG: case BNLP_OP_POWC: case BNLP_OP_EXP: case BNLP_OP_LOG: case BNLP_OP_SQRT:
+        case BNLP_OP_SIN: case BNLP_OP_COS: case BNLP_OP_SQR: case BNLP_OP_ABS:
+          if (depth < 1) { err = "term stack underflow"; return false; }
+          break;
+        default: err = "unknown term opcode"; return false;
+      }
+      maxd = std::max(maxd, depth);
+    }
+    if (depth != 1) { err = "term program does not leave exactly one value"; return false; }
+    if (maxd > BNLP_MAX_TERM_STACK) { err = "term stack deeper than BNLP_MAX_TERM_STACK"; return false; }
+    M.terms.push_back(std::move(T));
+  }
+  M.finalize();
+  return true;
+}
+
+}  // namespace bnlp

@@ -1,0 +1,290 @@
+"""ctypes binding of the C ABI (include/bnlp.h).  This is plumbing: every number is produced by
+libbnlp.so's CUDA kernels.  There is no CPU fallback — a missing library or GPU raises."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBPATH = os.path.join(_HERE, "libbnlp.so")
+_lib = None
+
+c_int, c_dbl, c_void = ctypes.c_int, ctypes.c_double, ctypes.c_void_p
+P_int, P_dbl = ctypes.POINTER(c_int), ctypes.POINTER(c_dbl)
+
+
+class BnlpError(RuntimeError):
+    pass
+
+
+class TapeDesc(ctypes.Structure):
+    _fields_ = [("n", c_int), ("m", c_int), ("xl", P_dbl), ("xu", P_dbl), ("gl", P_dbl), ("gu", P_dbl),
+                ("var_type", P_int), ("x0", P_dbl), ("c", P_dbl), ("lin_start", P_int), ("lin_col", P_int),
+                ("lin_val", P_dbl), ("n_qdense", c_int), ("qd_fn", P_int), ("qd", P_dbl), ("n_qsparse", c_int),
+                ("qs_fn", P_int), ("qs_i", P_int), ("qs_j", P_int), ("qs_v", P_dbl), ("n_terms", c_int),
+                ("term_fn", P_int), ("term_var_start", P_int), ("term_var", P_int), ("term_op_start", P_int),
+                ("term_op", P_int), ("term_iarg", P_int), ("term_darg", P_dbl)]
+
+
+class Options(ctypes.Structure):
+    _fields_ = [("tol", c_dbl), ("max_iter", c_int), ("ctas_per_device", c_int)]
+
+
+class OaTols(ctypes.Structure):
+    _fields_ = [("tiny", c_dbl), ("very_tiny", c_dbl), ("rhs_relax", c_dbl), ("infty", c_dbl)]
+
+
+EXPORTS = ["bnlp_last_error", "bnlp_problem_from_nl", "bnlp_problem_from_tape", "bnlp_problem_free",
+           "bnlp_problem_sizes", "bnlp_problem_info", "bnlp_engine_create", "bnlp_engine_free", "bnlp_eval_batch",
+           "bnlp_solve_batch", "bnlp_solve_batch_device", "bnlp_oa_capacity", "bnlp_oa_batch", "bnlp_engine_stats",
+           "bnlp_engine_launches", "bnlp_measure_fp64_peak"]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIBPATH):
+            raise BnlpError(f"{_LIBPATH} is missing: run `python -m bonmin_b200.build` (no CPU fallback exists)")
+        L = ctypes.CDLL(_LIBPATH)
+        L.bnlp_last_error.restype = ctypes.c_char_p
+        L.bnlp_problem_from_tape.restype = c_void
+        L.bnlp_problem_from_tape.argtypes = [ctypes.POINTER(TapeDesc), ctypes.c_char_p, ctypes.c_size_t]
+        L.bnlp_problem_from_nl.restype = c_void
+        L.bnlp_problem_from_nl.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t]
+        L.bnlp_problem_free.argtypes = [c_void]
+        L.bnlp_problem_sizes.argtypes = [c_void, P_int, P_int, P_int, P_int]
+        L.bnlp_problem_info.argtypes = [c_void] + [c_void] * 11
+        L.bnlp_engine_create.restype = c_void
+        L.bnlp_engine_create.argtypes = [c_void, P_int, c_int, ctypes.POINTER(Options)]
+        L.bnlp_engine_free.argtypes = [c_void]
+        L.bnlp_eval_batch.argtypes = [c_void, c_int, c_void, c_void, c_dbl, c_void, c_void, c_void, c_void, c_void]
+        L.bnlp_solve_batch.argtypes = [c_void, c_int, c_void, c_void, c_void, c_int] + [c_void] * 6
+        L.bnlp_solve_batch_device.argtypes = [c_void, c_int, c_int, c_void, c_void, c_void, c_int] + [c_void] * 7
+        L.bnlp_oa_capacity.argtypes = [c_void, c_int, P_int, ctypes.POINTER(ctypes.c_size_t)]
+        L.bnlp_oa_batch.argtypes = [c_void, c_int, c_void, c_void, c_void, c_void, c_void, c_dbl, c_int,
+                                    ctypes.POINTER(OaTols), c_void, c_void, c_void, c_void, c_void, c_void]
+        L.bnlp_engine_stats.argtypes = [c_void, ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_longlong),
+                                        P_dbl]
+        L.bnlp_engine_launches.restype = ctypes.c_longlong
+        L.bnlp_engine_launches.argtypes = [c_void]
+        L.bnlp_measure_fp64_peak.restype = c_dbl
+        L.bnlp_measure_fp64_peak.argtypes = [c_void, c_int]
+        _lib = L
+    return _lib
+
+
+def _err():
+    return lib().bnlp_last_error().decode()
+
+
+def _d(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _pd(a):
+    return a.ctypes.data_as(P_dbl)
+
+
+def _pi(a):
+    return a.ctypes.data_as(P_int)
+
+
+def _vp(a):
+    return None if a is None else a.ctypes.data_as(c_void)
+
+
+class Problem:
+    """A compiled model (`bnlp_problem`)."""
+
+    def __init__(self, handle):
+        if not handle:
+            raise BnlpError(_err())
+        self.h = handle
+        n, m, nj, nh = c_int(), c_int(), c_int(), c_int()
+        lib().bnlp_problem_sizes(self.h, n, m, nj, nh)
+        self.n, self.m, self.nnz_jac, self.nnz_hess = n.value, m.value, nj.value, nh.value
+
+    @classmethod
+    def from_model(cls, model):
+        """StructuredModel (bonmin_b200.instances) -> bnlp_problem_from_tape."""
+        n, m = int(model.n), int(model.m)
+        A = _d(model.A)
+        keep = []  # arrays must stay alive during the call
+        lin_start, lin_col, lin_val = [0], [], []
+        for k in range(m + 1):
+            nzc = np.flatnonzero(A[k])
+            lin_col.extend(nzc.tolist())
+            lin_val.extend(A[k, nzc].tolist())
+            lin_start.append(len(lin_col))
+        terms = model.get("terms", [])
+        tv_start, tv, to_start, top, tia, tda, tfn = [0], [], [0], [], [], [], []
+        for fn, vars_, prog in terms:
+            tfn.append(fn)
+            tv.extend(vars_)
+            tv_start.append(len(tv))
+            for op, ia, da in prog:
+                top.append(op)
+                tia.append(ia)
+                tda.append(da)
+            to_start.append(len(top))
+        arrs = dict(xl=_d(model.xl), xu=_d(model.xu), gl=_d(model.gl), gu=_d(model.gu), vt=_i(model.vtype),
+                    x0=_d(model.x0), c=_d(model.c), ls=_i(lin_start), lc=_i(lin_col), lv=_d(lin_val),
+                    qdf=_i(model.qd_fn), qd=_d(model.qd), qsf=_i(model.qs_fn), qsi=_i(model.qs_i),
+                    qsj=_i(model.qs_j), qsv=_d(model.qs_v), tfn=_i(tfn), tvs=_i(tv_start), tv=_i(tv),
+                    tos=_i(to_start), top=_i(top), tia=_i(tia), tda=_d(tda))
+        d = TapeDesc(n, m, _pd(arrs["xl"]), _pd(arrs["xu"]), _pd(arrs["gl"]), _pd(arrs["gu"]), _pi(arrs["vt"]),
+                     _pd(arrs["x0"]), _pd(arrs["c"]), _pi(arrs["ls"]), _pi(arrs["lc"]), _pd(arrs["lv"]),
+                     len(arrs["qdf"]), _pi(arrs["qdf"]), _pd(arrs["qd"]), len(arrs["qsf"]), _pi(arrs["qsf"]),
+                     _pi(arrs["qsi"]), _pi(arrs["qsj"]), _pd(arrs["qsv"]), len(tfn), _pi(arrs["tfn"]),
+                     _pi(arrs["tvs"]), _pi(arrs["tv"]), _pi(arrs["tos"]), _pi(arrs["top"]), _pi(arrs["tia"]),
+                     _pd(arrs["tda"]))
+        err = ctypes.create_string_buffer(512)
+        h = lib().bnlp_problem_from_tape(ctypes.byref(d), err, 512)
+        if not h:
+            raise BnlpError(err.value.decode())
+        del keep
+        return cls(h)
+
+    @classmethod
+    def from_nl(cls, text):
+        if isinstance(text, str):
+            text = text.encode()
+        err = ctypes.create_string_buffer(512)
+        h = lib().bnlp_problem_from_nl(text, len(text), err, 512)
+        if not h:
+            raise BnlpError(err.value.decode())
+        return cls(h)
+
+    def info(self):
+        n, m = self.n, self.m
+        out = dict(jac_irow=np.zeros(self.nnz_jac, np.int32), jac_jcol=np.zeros(self.nnz_jac, np.int32),
+                   hes_irow=np.zeros(self.nnz_hess, np.int32), hes_jcol=np.zeros(self.nnz_hess, np.int32),
+                   var_type=np.zeros(n, np.int32), con_nonlinear=np.zeros(m, np.int32), xl=np.zeros(n),
+                   xu=np.zeros(n), gl=np.zeros(m), gu=np.zeros(m), x0=np.zeros(n))
+        lib().bnlp_problem_info(self.h, *[_vp(out[k]) for k in
+                                          ("jac_irow", "jac_jcol", "hes_irow", "hes_jcol", "var_type",
+                                           "con_nonlinear", "xl", "xu", "gl", "gu", "x0")])
+        return out
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().bnlp_problem_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+class Engine:
+    """`bnlp_engine`: the tape replicated on the listed devices."""
+
+    def __init__(self, problem: Problem, devices=(0,), tol=0.0, max_iter=0, ctas_per_device=0):
+        self.problem = problem
+        ids = _i(list(devices))
+        opt = Options(tol, max_iter, ctas_per_device)
+        self.h = lib().bnlp_engine_create(problem.h, _pi(ids), len(ids), ctypes.byref(opt))
+        if not self.h:
+            raise BnlpError(_err())
+        self.n, self.m = problem.n, problem.m
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise BnlpError(f"engine error {rc}: {_err()}")
+
+    def solve_batch(self, XL, XU, X0, want_x=True, want_g=True, want_duals=True):
+        """B x TNLPSolver::OptimizeTNLP with host buffers (copies inside the call)."""
+        n, m = self.n, self.m
+        XL = _d(np.atleast_2d(XL))
+        XU = _d(np.atleast_2d(XU))
+        B = XL.shape[0]
+        X0 = _d(X0)
+        per_child = int(X0.ndim == 2)
+        OBJ = np.zeros(B)
+        ST = np.zeros(B, np.int32)
+        IT = np.zeros(B, np.int32)
+        X = np.zeros((B, n)) if want_x else None
+        G = np.zeros((B, m)) if want_g else None
+        D = np.zeros((B, 2 * n + m)) if want_duals else None
+        self._ck(lib().bnlp_solve_batch(self.h, B, _vp(XL), _vp(XU), _vp(X0), per_child, _vp(OBJ), _vp(ST), _vp(IT),
+                                        _vp(X), _vp(G), _vp(D)))
+        return dict(obj=OBJ, status=ST, iters=IT, x=X, g=G, duals=D)
+
+    def solve_batch_device(self, dXL, dXU, dX0, dOBJ, dST, dIT, dX=None, dG=None, dD=None, x0_per_child=False,
+                           stream=0, dev_index=0):
+        """Device-pointer variant (torch tensors or raw ints); asynchronous on `stream`."""
+        def ptr(t):
+            if t is None:
+                return None
+            return c_void(t if isinstance(t, int) else t.data_ptr())
+        B = dOBJ.shape[0]
+        self._ck(lib().bnlp_solve_batch_device(self.h, dev_index, B, ptr(dXL), ptr(dXU), ptr(dX0), int(x0_per_child),
+                                               ptr(dOBJ), ptr(dST), ptr(dIT), ptr(dX), ptr(dG), ptr(dD),
+                                               c_void(stream)))
+
+    def eval_batch(self, X, LAM=None, sigma=1.0, want=("f", "g", "gradf", "jac", "hess")):
+        n, m = self.n, self.m
+        X = _d(np.atleast_2d(X))
+        B = X.shape[0]
+        LAMa = None if LAM is None else _d(np.atleast_2d(LAM))
+        F = np.zeros(B) if "f" in want else None
+        G = np.zeros((B, m)) if "g" in want else None
+        GF = np.zeros((B, n)) if "gradf" in want else None
+        J = np.zeros((B, self.problem.nnz_jac)) if "jac" in want else None
+        H = np.zeros((B, self.problem.nnz_hess)) if "hess" in want else None
+        self._ck(lib().bnlp_eval_batch(self.h, B, _vp(X), _vp(LAMa), float(sigma), _vp(F), _vp(G), _vp(GF), _vp(J),
+                                       _vp(H)))
+        return dict(f=F, g=G, gradf=GF, jac=J, hess=H)
+
+    def oa_batch(self, X, DUALS=None, XL=None, XU=None, X2=None, theta=0.0, get_obj=0, tols=None):
+        """B x OsiTMINLPInterface::getOuterApproximation -> CSR rows (see include/bnlp.h)."""
+        n = self.n
+        X = _d(np.atleast_2d(X))
+        B = X.shape[0]
+        rpp = c_int()
+        cap = ctypes.c_size_t()
+        self._ck(lib().bnlp_oa_capacity(self.h, B, ctypes.byref(rpp), ctypes.byref(cap)))
+        nrows = B * rpp.value
+        row_start = np.zeros(nrows + 1, np.int32)
+        col = np.zeros(cap.value, np.int32)
+        val = np.zeros(cap.value)
+        LB = np.zeros(nrows)
+        UB = np.zeros(nrows)
+        src = np.zeros(nrows, np.int32)
+        info = self.problem.info()
+        XL = _d(info["xl"] if XL is None else XL)
+        XU = _d(info["xu"] if XU is None else XU)
+        Du = None if DUALS is None else _d(np.atleast_2d(DUALS))
+        X2a = None if X2 is None else _d(np.atleast_2d(X2))
+        t = tols or OaTols(1e-8, 1e-17, 1e-8, 1e19)
+        self._ck(lib().bnlp_oa_batch(self.h, B, _vp(X), _vp(Du), _vp(XL), _vp(XU), _vp(X2a), float(theta),
+                                     int(get_obj), ctypes.byref(t), _vp(row_start), _vp(col), _vp(val), _vp(LB),
+                                     _vp(UB), _vp(src)))
+        return dict(rows_per_point=rpp.value, row_start=row_start, col=col, val=val, lb=LB, ub=UB, src_row=src)
+
+    def stats(self):
+        it, fa, ms = ctypes.c_longlong(), ctypes.c_longlong(), c_dbl()
+        lib().bnlp_engine_stats(self.h, ctypes.byref(it), ctypes.byref(fa), ctypes.byref(ms))
+        return dict(iterations=it.value, factorisations=fa.value, device_ms=ms.value)
+
+    def launches(self):
+        return int(lib().bnlp_engine_launches(self.h))
+
+    def fp64_peak_tflops(self, dev_index=0):
+        return float(lib().bnlp_measure_fp64_peak(self.h, dev_index))
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().bnlp_engine_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,156 @@
+/* bnlp.h — C ABI of the B200 batched NLP-relaxation engine (libbnlp.so).
+ *
+ * This is the drop-in boundary for Bonmin's data-parallel hot path.  Every entry point states the
+ * reference interface it replaces (paths relative to the Bonmin source tree).  Plain pointers and
+ * sizes only; no exceptions cross the ABI; naming/ownership mirror the reference's own C API
+ * (src/Interfaces/BonStdCInterface.h:133-204: opaque handles, Create/Free pairs, caller-owned arrays).
+ *
+ * Conventions (identical to the reference):
+ *   - duals layout [z_L (n) | z_U (n) | lambda (m)]         src/Interfaces/BonTMINLP2TNLP.cpp:491-498
+ *   - lambda sign: L = f + lambda'g (Ipopt)                  src/Interfaces/BonOsiTMINLPInterface.cpp:1968-1974
+ *   - STATUS values are Bonmin::TNLPSolver::ReturnStatus     src/Interfaces/BonTNLPSolver.hpp:29-44
+ *   - an infeasible child reports obj = max-norm violation   src/Interfaces/BonTMINLP2TNLP.cpp:503-505
+ *   - |bound| >= 1e19 means infinite                         src/Interfaces/BonOsiTMINLPInterface.cpp:3002-3005
+ *   - all structure indices are 0-based (C_STYLE)            src/Interfaces/BonTMINLP.hpp:286-315
+ * Return value of every int function: 0 = ok, <0 = engine error (message via bnlp_last_error()); the
+ * host adapters map a negative return to TNLPSolver::exception.  One host thread drives one engine.
+ * There is NO CPU fallback: without a CUDA device bnlp_engine_create fails.
+ */
+#ifndef BNLP_H
+#define BNLP_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bnlp_problem bnlp_problem;
+typedef struct bnlp_engine bnlp_engine;
+
+/* TNLPSolver::ReturnStatus (src/Interfaces/BonTNLPSolver.hpp:29-44) */
+enum {
+  BNLP_iterationLimit = -3, BNLP_timeLimit = 5, BNLP_doesNotConverge = -8, BNLP_computationError = -2,
+  BNLP_notEnoughFreedom = -1, BNLP_illDefinedProblem = -4, BNLP_illegalOption = -5,
+  BNLP_externalException = -6, BNLP_exception = -7, BNLP_solvedOptimal = 1, BNLP_solvedOptimalTol = 2,
+  BNLP_provenInfeasible = 3, BNLP_unbounded = 4
+};
+
+/* opcodes of a nonlinear element term (postfix program over the term's local variable slots) */
+enum {
+  BNLP_OP_CONST = 0, BNLP_OP_VAR = 1, BNLP_OP_ADD = 2, BNLP_OP_SUB = 3, BNLP_OP_MUL = 4, BNLP_OP_DIV = 5,
+  BNLP_OP_NEG = 6, BNLP_OP_POWC = 7 /* x^darg */, BNLP_OP_POW = 8, BNLP_OP_EXP = 9, BNLP_OP_LOG = 10,
+  BNLP_OP_SQRT = 11, BNLP_OP_SIN = 12, BNLP_OP_COS = 13, BNLP_OP_SQR = 14, BNLP_OP_ABS = 15
+};
+#define BNLP_MAX_TERM_VARS 6
+#define BNLP_MAX_TERM_STACK 12
+
+/* Structured model ("flat tape" input): every function k (k = 0 objective, k = 1..m rows) is
+ *     F_k(x) = c[k] + a_k.x + 1/2 x'Q_k x + sum_t phi_t(x[term vars])
+ * This is the closed-form statement of what a Bonmin::TMINLP exposes through callbacks
+ * (src/Interfaces/BonTMINLP.hpp:226-333: get_nlp_info, get_bounds_info, get_variables_types,
+ *  get_starting_point, eval_f/grad_f/g/jac_g/h). */
+typedef struct bnlp_tape_desc {
+  int n, m;
+  const double *xl, *xu;       /* n */
+  const double *gl, *gu;       /* m */
+  const int *var_type;         /* n : 0 continuous, 1 binary, 2 integer (TMINLP::VariableType) */
+  const double *x0;            /* n : starting point (may be NULL = 0) */
+  const double *c;             /* m+1 */
+  const int *lin_start;        /* m+2 : CSR over functions 0..m */
+  const int *lin_col;
+  const double *lin_val;
+  int n_qdense;                /* dense quadratic blocks */
+  const int *qd_fn;            /* n_qdense : function index of each block */
+  const double *qd;            /* n_qdense x n(n+1)/2 : packed lower triangle, row-major (r >= c) */
+  int n_qsparse;               /* sparse quadratic triplets, i >= j, Q_ij = Q_ji = v */
+  const int *qs_fn, *qs_i, *qs_j;
+  const double *qs_v;
+  int n_terms;                 /* nonlinear element terms */
+  const int *term_fn;          /* n_terms */
+  const int *term_var_start;   /* n_terms+1 -> term_var */
+  const int *term_var;
+  const int *term_op_start;    /* n_terms+1 -> term_op / term_iarg / term_darg */
+  const int *term_op;
+  const int *term_iarg;
+  const double *term_darg;
+} bnlp_tape_desc;
+
+typedef struct bnlp_options {
+  double tol;                  /* Ipopt tol, default 1e-8 (doc/options_list_ipopt_content.tex L2689) */
+  int max_iter;                /* default 3000 (L2671) */
+  int ctas_per_device;         /* 0 = one persistent CTA per SM */
+} bnlp_options;
+
+const char *bnlp_last_error(void);
+
+/* --- model -------------------------------------------------------------------------------------
+ * bnlp_problem_from_nl   replaces  AmplTMINLP::Initialize -> new Ipopt::AmplTNLP -> ASL reader
+ *                        (src/Interfaces/Ampl/BonAmplTMINLP.cpp:83-204,473-564)
+ * bnlp_problem_from_tape replaces a user TMINLP subclass (examples/CppExample/MyTMINLP.cpp:12-217) */
+bnlp_problem *bnlp_problem_from_nl(const char *nl_text, size_t len, char *err, size_t errlen);
+bnlp_problem *bnlp_problem_from_tape(const bnlp_tape_desc *desc, char *err, size_t errlen);
+void bnlp_problem_free(bnlp_problem *);
+
+/* get_nlp_info (BonTMINLP.hpp:226-229) */
+int bnlp_problem_sizes(const bnlp_problem *, int *n, int *m, int *nnz_jac, int *nnz_hess);
+/* structure + bounds + types: get_bounds_info :238, get_variables_types :208, get_constraints_linearity :220,
+ * eval_jac_g/eval_h structure calls :286-315, get_starting_point :251.  Any pointer may be NULL. */
+int bnlp_problem_info(const bnlp_problem *, int *jac_irow, int *jac_jcol, int *hes_irow, int *hes_jcol,
+                      int *var_type, int *con_nonlinear, double *xl, double *xu, double *gl, double *gu,
+                      double *x0);
+
+/* --- engine ------------------------------------------------------------------------------------
+ * replaces the construction of an IpoptSolver (src/Interfaces/BonOsiTMINLPInterface.cpp:448-496). The tape
+ * is uploaded (replicated) to every listed device. */
+bnlp_engine *bnlp_engine_create(const bnlp_problem *, const int *device_ids, int ndev, const bnlp_options *);
+void bnlp_engine_free(bnlp_engine *);
+
+/* B x {eval_f, eval_grad_f, eval_g, eval_jac_g values, eval_h values} (BonTMINLP.hpp:268-315).
+ * X: B x n.  LAM: B x m or NULL (then 0), sigma = obj_factor.  Outputs (any may be NULL):
+ * F: B, G: B x m, GRADF: B x n, JVAL: B x nnz_jac, HVAL: B x nnz_hess.  Host pointers. */
+int bnlp_eval_batch(bnlp_engine *, int B, const double *X, const double *LAM, double sigma, double *F,
+                    double *G, double *GRADF, double *JVAL, double *HVAL);
+
+/* B child relaxations = B x TNLPSolver::OptimizeTNLP (src/Interfaces/BonTNLPSolver.hpp:127,
+ * src/Interfaces/Ipopt/BonIpoptSolver.cpp:134-176), differing only in their bound vectors
+ * (src/Algorithms/Branching/BonChooseVariable.cpp:807-905).  XL, XU: B x n.  X0: n (shared, x0_per_child = 0)
+ * or B x n.  Outputs: OBJ B, STATUS B, ITERS B, X B x n, G B x m, DUALS B x (2n+m); X/G/DUALS may be NULL.
+ * Host pointers; copies are inside the call. */
+int bnlp_solve_batch(bnlp_engine *, int B, const double *XL, const double *XU, const double *X0,
+                     int x0_per_child, double *OBJ, int *STATUS, int *ITERS, double *X, double *G,
+                     double *DUALS);
+/* Same with DEVICE pointers on device `dev_index` of the engine (inputs already resident in HBM; runs on `stream`,
+ * a cudaStream_t passed as void*, no synchronisation). */
+int bnlp_solve_batch_device(bnlp_engine *, int dev_index, int B, const double *dXL, const double *dXU,
+                            const double *dX0, int x0_per_child, double *dOBJ, int *dSTATUS, int *dITERS,
+                            double *dX, double *dG, double *dDUALS, void *stream);
+
+/* Outer-approximation rows at B points = B x OsiTMINLPInterface::getOuterApproximation
+ * (src/Interfaces/BonOsiTMINLPInterface.cpp:1924-2107 incl. cleanNnz :1881-1919).
+ * X: B x n; DUALS: B x (2n+m) or NULL (multipliers pick the side of ranged rows); XL/XU: n column bounds used by
+ * cleanNnz; X2 (B x n or NULL) + theta: violation filter; getObj as in the reference (0/1/2).
+ * Output is CSR with a fixed capacity of (m_nl + 1) rows per point:
+ *   row_start: B*(m_nl+1)+1, col_idx/val: capacity from bnlp_oa_capacity(), LB/UB: B*(m_nl+1),
+ *   src_row: B*(m_nl+1) (constraint index, m for the objective cut, -1 = row not generated). */
+typedef struct bnlp_oa_tols {
+  double tiny;        /* tiny_element 1e-8       (BonOsiTMINLPInterface.cpp:236-241) */
+  double very_tiny;   /* very_tiny_element 1e-17 (:243-247) */
+  double rhs_relax;   /* oa_rhs_relax 1e-8       (:222-228) */
+  double infty;       /* 1e19 */
+} bnlp_oa_tols;
+int bnlp_oa_capacity(const bnlp_engine *, int B, int *rows_per_point, size_t *nnz_capacity);
+int bnlp_oa_batch(bnlp_engine *, int B, const double *X, const double *DUALS, const double *XL, const double *XU,
+                  const double *X2, double theta, int getObj, const bnlp_oa_tols *tols, int *row_start,
+                  int *col_idx, double *val, double *LB, double *UB, int *src_row);
+
+/* statistics of the last solve call: total IPM iterations, factorisations, device milliseconds
+ * (counterparts of totalIterations_/totalNlpSolveTime_, src/Interfaces/BonOsiTMINLPInterface.hpp:482-495) */
+int bnlp_engine_stats(const bnlp_engine *, long long *iterations, long long *factorisations, double *device_ms);
+/* number of kernel launches issued by the engine since creation (bench.py's gpu_launches) */
+long long bnlp_engine_launches(const bnlp_engine *);
+/* measured FP64 FMA peak of device dev_index in TFLOP/s (micro-kernel; roofline denominator) */
+double bnlp_measure_fp64_peak(bnlp_engine *, int dev_index);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
