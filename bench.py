@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""bench.py — child NLP relaxations solved per second (BASELINE.json metric) on N B200s of one node.
+
+Workload (BASELINE config C3): SYN-MIQCP(n=200, n_int=100, m_q=40, m_l=40, seed=20261020);
+one STEP = one batch of B child relaxations PER GPU (strong-branching / node children: root bounds + random
+prior branchings + one final branch, shared start point = root optimum), solved to Bonmin's Ipopt tolerances.
+Ranks solve disjoint child index ranges (weak scaling, no data-path collective; NCCL only gathers the
+per-child {objective,status} and all-reduces the incumbent bound, outside the kernel).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
+
+`value`   : device-timed throughput, inputs resident in HBM (CUDA events on the launching stream, L2 flushed
+            between steps, max over ranks).
+`e2e`     : the same metric through the C ABI call bnlp_solve_batch with HOST buffers (H2D of the bounds and
+            D2H of objective/status/iters/x inside the timed region).
+`roofline`: FP64 pipe.  achieved = algorithmic FLOPs (SURVEY.md §8d F_iter x iterations actually taken) / kernel
+            time; peak = FP64 FMA peak measured live by a micro-kernel (MEASURED_PEAKS.json has no FP64 entry).
+`cpu_baseline`: the CPU oracle (restatement of the Bonmin/Ipopt path; Ipopt itself is unavailable offline) on all
+            host cores, on a bounded sample of the same children.  --impl reference times the same thing per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from bonmin_b200 import instances as I  # noqa: E402
+
+C3 = dict(n=200, n_int=100, m_q=40, m_l=40, seed=20261020)
+WORKLOAD = "C3 SYN-MIQCP(n=200,n_int=100,m_q=40,m_l=40,seed=20261020) child relaxations, shared start point x*"
+
+
+def f_iter(n, m_q, m_l, r=2, t=1):
+    """Algorithmic FLOPs of one IPM iteration."""
+    m = m_q + m_l
+    return (t * (2 * n * n * (m_q + 1) + 2 * m_l * n) + m_q * n * (n + 1) + m * n * (n + 1) + n ** 3 / 3.0
+            + r * (2 * n * n + 4 * m * n))
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [s.strip() for s in out.strip().split(",")]
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for nm, v in zip(names, f[2:]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def make_children(model, xs, B, first):
+    return I.c3_children(model, xs, B, first=first)
+
+
+def cpu_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU path for this workload.  The real Bonmin/Ipopt cannot be built or
+    installed offline (no Ipopt/ASL/Osi/Cbc), so this times the CPU oracle restatement — all host
+    threads, each step a bounded sample of the same children."""
+    if rank != 0:
+        return
+    from oracle import ipm
+    ipm.build()
+    model = I.syn_miqcp(**C3)
+    dense = ipm.dense_arrays(model)
+    root = ipm.solve_batch(model, model.xl, model.xu, model.x0, dense=dense)
+    xs = root["x"][0]
+    cores = cpu_cores()
+    sample = args.ref_sample
+    XL, XU = make_children(model, xs, sample, 0)
+    for _ in range(args.warmup):
+        ipm.solve_batch(model, XL[: max(cores, 32)], XU[: max(cores, 32)], xs, threads=cores, dense=dense)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ipm.solve_batch(model, XL, XU, xs, threads=cores, dense=dense)
+    dt = time.perf_counter() - t0
+    val = sample * args.steps / dt
+    line = {"impl": "reference", "metric": "child NLP relaxations solved/sec", "value": val, "unit": "relaxations/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "children_per_step": sample},
+            "cpu_baseline": {"value": val, "unit": "relaxations/s", "cores": cores, "kind": "port",
+                             "sample": f"{sample} children per step (first {sample} of the C3 child sequence), "
+                                       "CPU restatement of the Bonmin/Ipopt path (Ipopt 3.13 unavailable offline)"},
+            "e2e": {"value": val, "unit": "relaxations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=4096, help="children per GPU per step")
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--ref-sample", type=int, default=1024)
+    ap.add_argument("--cpu-sample", type=int, default=2048)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from bonmin_b200 import build
+    from bonmin_b200.engine import Engine, Problem
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        build.build()
+    if world > 1:
+        dist.barrier()
+
+    model = I.syn_miqcp(**C3)
+    n, m = model.n, model.m
+    B = args.batch
+    eng = Engine(Problem.from_model(model), devices=[local_rank])
+    root = eng.solve_batch(model.xl, model.xu, model.x0)
+    assert root["status"][0] == 1
+    xs = root["x"][0]
+    XL, XU = make_children(model, xs, B, first=rank * B)
+
+    # ---------------- device-resident arm
+    stream = torch.cuda.current_stream()
+    dXL = torch.from_numpy(XL).to(dev)
+    dXU = torch.from_numpy(XU).to(dev)
+    dX0 = torch.from_numpy(xs).to(dev)
+    dOBJ = torch.zeros(B, dtype=torch.float64, device=dev)
+    dST = torch.zeros(B, dtype=torch.int32, device=dev)
+    dIT = torch.zeros(B, dtype=torch.int32, device=dev)
+    dX = torch.zeros(B, n, dtype=torch.float64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step_device():
+        eng.solve_batch_device(dXL, dXU, dX0, dOBJ, dST, dIT, dX, None, None, stream=stream.cuda_stream)
+
+    for _ in range(args.warmup):
+        step_device()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.launches()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    torch.cuda.synchronize()
+    for k in range(args.steps):
+        flush.fill_(k)              # evict L2 between timed steps (untimed)
+        ev[k][0].record(stream)
+        step_device()
+        ev[k][1].record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    launches = eng.launches() - launches0
+    iters_total = int(dIT.sum().item())          # iterations of ONE step (identical inputs every step)
+    status = dST.cpu().numpy()
+    obj_dev = dOBJ.cpu().numpy()
+
+    # ---------------- end-to-end arm through the C ABI with host buffers (pinned)
+    hXL = torch.from_numpy(XL).pin_memory().numpy()
+    hXU = torch.from_numpy(XU).pin_memory().numpy()
+    for _ in range(2):
+        eng.solve_batch(hXL, hXU, xs, want_g=False, want_duals=False)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r = eng.solve_batch(hXL, hXU, xs, want_g=False, want_duals=False)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    assert np.array_equal(r["status"], status)
+    h2d = 2 * B * n * 8 + n * 8
+    d2h = B * (8 + 4 + 4) + B * n * 8
+
+    # ---------------- exchange step: gather per-child results, all-reduce the incumbent bound
+    t_ms = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(iters_total), float((status == 1).sum()), float((status == 3).sum())],
+                       dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        gathered = [torch.zeros_like(dOBJ) for _ in range(world)]
+        dist.all_gather(gathered, dOBJ)
+        best = torch.where(dST == 1, dOBJ, torch.full_like(dOBJ, float("inf"))).min()
+        dist.all_reduce(best, op=dist.ReduceOp.MIN)
+    dev_ms_max, e2e_ms_max = t_ms.tolist()
+    iters_all, n_opt, n_inf = tot.tolist()
+
+    if rank == 0:
+        total = B * world
+        value = total * args.steps / (dev_ms_max * 1e-3)
+        e2e = total * args.steps / (e2e_ms_max * 1e-3)
+        peak = eng.fp64_peak_tflops(0)
+        fl_step = f_iter(C3["n"], C3["m_q"], C3["m_l"]) * iters_total      # this rank's kernel
+        kern_ms = dev_ms / args.steps
+        achieved = fl_step / (kern_ms * 1e-3) / 1e12
+        line = {
+            "metric": "child NLP relaxations solved/sec", "value": value, "unit": "relaxations/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "children_per_gpu_per_step": B, "children_per_step": total,
+                       "l2": "256 MiB flush write between timed steps (untimed)",
+                       "mean_ipm_iterations": iters_all / total, "optimal": int(n_opt), "infeasible": int(n_inf)},
+            "e2e": {"value": e2e, "unit": "relaxations/s", "h2d_bytes_per_step": h2d * world,
+                    "d2h_bytes_per_step": d2h * world},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "fp64", "kernel": "ipm_kernel", "achieved": achieved, "peak": peak,
+                         "unit": "TFLOP/s", "frac": achieved / peak if peak > 0 else None, "traffic": None,
+                         "peak_source": "FP64 FMA micro-kernel measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
+                         "flops_per_iteration": f_iter(C3["n"], C3["m_q"], C3["m_l"]),
+                         "iterations_per_launch": iters_total, "kernel_ms": kern_ms},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import ipm
+            ipm.build()
+            cores = cpu_cores()
+            S = min(args.cpu_sample, B)
+            dense = ipm.dense_arrays(model)
+            ipm.solve_batch(model, XL[:cores], XU[:cores], xs, threads=cores, dense=dense)
+            t0 = time.perf_counter()
+            o = ipm.solve_batch(model, XL[:S], XU[:S], xs, threads=cores, dense=dense)
+            dt = time.perf_counter() - t0
+            same = o["status"] == status[:S]
+            okk = o["status"] == 1
+            rel = np.abs(o["obj"] - obj_dev[:S]) / np.maximum(1.0, np.abs(o["obj"]))
+            line["cpu_baseline"] = {"value": S / dt, "unit": "relaxations/s", "cores": cores, "kind": "port",
+                                    "sample": f"first {S} children of the step's batch, one relaxation per thread; "
+                                              "CPU restatement of the Bonmin/Ipopt path (Ipopt 3.13 unavailable offline)"}
+            line["parity"] = {"checked": int(S), "status_mismatches": int((~same).sum()),
+                              "max_rel_obj_diff": float(rel[okk & same].max(initial=0.0)), "tolerance": 1e-6}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -66,7 +67,7 @@ struct Device {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // model
-  DBuf<double> c, A, Qp, row_sgn, row_bnd, gl, gu, xl, xu;
+  DBuf<double> c, A, Qp, Qf, row_sgn, row_bnd, gl, gu, xl, xu;
   DBuf<int> qidx, row_fn, fn_row_up, fn_row_lo;
   EvalModelDev ev;   // eval / OA view of the tape
   DBuf<int> e_int;   // packed integer arrays of the eval tape
@@ -156,8 +157,8 @@ static size_t ipm_smem_doubles(int n, int m, int R, int h_in_smem) {
   d += (size_t)(IPM_NW + 1) * npad;
   d += (size_t)7 * npad;
   const int Rp = (R + 1) & ~1, Kp = (m + 2) & ~1;
-  d += (size_t)10 * Rp + (size_t)5 * Kp + (size_t)IPM_NW * 12;
-  d += (size_t)(N + 2) / 2 + 1;
+  d += (size_t)10 * Rp + (size_t)6 * Kp + (size_t)IPM_NW * 12;
+  d += (size_t)(((N + 1) & ~1) * 2 + 2 * Kp) / 2 + 2;   // flg, fixlist, qblk, qfn (ints)
   return d;
 }
 
@@ -211,6 +212,14 @@ extern "C" bnlp_engine *bnlp_engine_create(const bnlp_problem *prob, const int *
     dst[(size_t)M.qs_i[e] * (M.qs_i[e] + 1) / 2 + M.qs_j[e]] += M.qs_v[e];
   }
   E->nq = (int)(Qp.size() / P);
+  std::vector<double> Qf((size_t)E->nq * n * n);
+  for (int q = 0; q < E->nq; ++q)
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j <= i; ++j) {
+        const double v = Qp[(size_t)q * P + (size_t)i * (i + 1) / 2 + j];
+        Qf[((size_t)q * n + i) * n + j] = v;
+        Qf[((size_t)q * n + j) * n + i] = v;
+      }
   std::vector<int> row_fn, fn_up(m + 1, -1), fn_lo(m + 1, -1);
   std::vector<double> row_sgn, row_bnd;
   for (int i = 0; i < m; ++i) {
@@ -250,7 +259,7 @@ extern "C" bnlp_engine *bnlp_engine_create(const bnlp_problem *prob, const int *
     cudaEventCreate(&D.ev0);
     cudaEventCreate(&D.ev1);
     int bad = 0;
-    bad |= upload(D.c, M.c); bad |= upload(D.A, A); bad |= upload(D.qidx, qidx); bad |= upload(D.Qp, Qp);
+    bad |= upload(D.c, M.c); bad |= upload(D.A, A); bad |= upload(D.qidx, qidx); bad |= upload(D.Qp, Qp); bad |= upload(D.Qf, Qf);
     bad |= upload(D.row_fn, row_fn); bad |= upload(D.row_sgn, row_sgn); bad |= upload(D.row_bnd, row_bnd);
     bad |= upload(D.fn_row_up, fn_up); bad |= upload(D.fn_row_lo, fn_lo);
     bad |= upload(D.gl, M.gl); bad |= upload(D.gu, M.gu); bad |= upload(D.xl, M.xl); bad |= upload(D.xu, M.xu);
@@ -260,7 +269,7 @@ extern "C" bnlp_engine *bnlp_engine_create(const bnlp_problem *prob, const int *
     DevModel &dm = D.dm;
     dm.n = n; dm.m = m; dm.N = n + 1; dm.R = E->R; dm.nq = E->nq; dm.P = (int)P;
     dm.npad = (dm.N + 2 + 3) & ~3;
-    dm.c = D.c.p; dm.A = D.A.p; dm.qidx = D.qidx.p; dm.Qp = D.Qp.p;
+    dm.c = D.c.p; dm.A = D.A.p; dm.qidx = D.qidx.p; dm.Qp = D.Qp.p; dm.Qf = D.Qf.p;
     dm.row_fn = D.row_fn.p; dm.row_sgn = D.row_sgn.p; dm.row_bnd = D.row_bnd.p;
     dm.fn_row_up = D.fn_row_up.p; dm.fn_row_lo = D.fn_row_lo.p; dm.gl = D.gl.p; dm.gu = D.gu.p;
     if (d == 0) {
@@ -272,13 +281,14 @@ extern "C" bnlp_engine *bnlp_engine_create(const bnlp_problem *prob, const int *
       E->ws_doubles = (E->ws_doubles + 1) & ~(size_t)1;
     }
     if (E->ipm_supported &&
-        cudaFuncSetAttribute(ipm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)E->smem_bytes) != cudaSuccess) {
+        (cudaFuncSetAttribute(ipm_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)E->smem_bytes) != cudaSuccess ||
+         cudaFuncSetAttribute(ipm_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)E->smem_bytes) != cudaSuccess)) {
       set_err(std::string("cudaFuncSetAttribute(ipm_kernel): ") + cudaGetErrorString(cudaGetLastError()));
       delete E;
       return nullptr;
     }
     D.queue.reserve(1);
-    D.stats.reserve(2);
+    D.stats.reserve(12);
   }
   return E;
 }
@@ -287,7 +297,7 @@ extern "C" void bnlp_engine_free(bnlp_engine *E) {
   if (!E) return;
   for (Device &D : E->devs) {
     cudaSetDevice(D.id);
-    for (auto *b : {&D.c, &D.A, &D.Qp, &D.row_sgn, &D.row_bnd, &D.gl, &D.gu, &D.xl, &D.xu, &D.e_dbl, &D.dXL, &D.dXU,
+    for (auto *b : {&D.c, &D.A, &D.Qp, &D.Qf, &D.row_sgn, &D.row_bnd, &D.gl, &D.gu, &D.xl, &D.xu, &D.e_dbl, &D.dXL, &D.dXU,
                     &D.dX0, &D.dOBJ, &D.dX, &D.dG, &D.dD, &D.ws, &D.eX, &D.eLAM, &D.eF, &D.eG, &D.eGF, &D.eJ, &D.eH,
                     &D.eX2, &D.eDU, &D.oVal, &D.oLB, &D.oUB})
       b->release();
@@ -311,14 +321,16 @@ static int launch_ipm(bnlp_engine *E, Device &D, int B, const double *dXL, const
   ctas = std::min(ctas, B);
   if (D.ws.reserve((size_t)ctas * E->ws_doubles)) { set_err("workspace allocation failed"); return -1; }
   CK(cudaMemsetAsync(D.queue.p, 0, sizeof(int), stream));
-  CK(cudaMemsetAsync(D.stats.p, 0, 2 * sizeof(long long), stream));
+  CK(cudaMemsetAsync(D.stats.p, 0, 12 * sizeof(long long), stream));
   IpmArgs a{};
   a.B = B; a.XL = dXL; a.XU = dXU; a.X0 = dX0; a.x0_stride = x0_per_child ? E->M.n : 0;
   a.OBJ = dOBJ; a.STATUS = dST; a.ITERS = dIT; a.X = dX; a.G = dG; a.DUALS = dD;
   a.queue = D.queue.p; a.ws = D.ws.p; a.ws_stride = E->ws_doubles; a.h_in_smem = E->h_in_smem; a.stats = D.stats.p;
+  a.phase_cycles = getenv("BNLP_PHASE_TIMERS") ? D.stats.p + 2 : nullptr;
   a.o = IpmOpt();
   a.o.tol = E->opt.tol; a.o.max_iter = E->opt.max_iter;
-  ipm_kernel<<<ctas, IPM_NT, E->smem_bytes, stream>>>(D.dm, a);
+  if (E->M.n <= 256) ipm_kernel<8><<<ctas, IPM_NT, E->smem_bytes, stream>>>(D.dm, a);
+  else ipm_kernel<16><<<ctas, IPM_NT, E->smem_bytes, stream>>>(D.dm, a);
   E->launches++;
   CK(cudaGetLastError());
   return 0;
@@ -377,8 +389,14 @@ extern "C" int bnlp_solve_batch(bnlp_engine *E, int B, const double *XL, const d
     Device &D = E->devs[d];
     CK(cudaSetDevice(D.id));
     CK(cudaStreamSynchronize(D.stream));
-    long long st[2] = {0, 0};
+    long long st[12] = {0};
     CK(cudaMemcpy(st, D.stats.p, sizeof(st), cudaMemcpyDeviceToHost));
+    if (getenv("BNLP_PHASE_TIMERS")) {
+      static const char *nm[10] = {"residuals", "W pass", "J'SJ", "cholesky", "backsolve", "direction", "U pass", "linesearch", "update", "init"};
+      long long tot = 0;
+      for (int q = 0; q < 10; ++q) tot += st[2 + q];
+      for (int q = 0; q < 10; ++q) fprintf(stderr, "[bnlp phase] %-10s %6.2f%%  %.0f cyc/iter\n", nm[q], 100.0 * st[2 + q] / (tot ? tot : 1), (double)st[2 + q] / (st[0] ? st[0] : 1));
+    }
     E->last_iters += st[0]; E->last_fact += st[1];
     float ms = 0;
     cudaEventElapsedTime(&ms, D.ev0, D.ev1);

@@ -49,7 +49,8 @@ struct DevModel {
   int n, m, N, R, nq, P, npad;
   const double *c, *A;          // (m+1), (m+1) x n
   const int *qidx;              // m+1 : packed block index or -1
-  const double *Qp;             // nq x P packed lower triangles
+  const double *Qp;             // nq x P packed lower triangles (Hessian accumulation)
+  const double *Qf;             // nq x n x n full symmetric copies (mat-vecs)
   const int *row_fn;            // R one-sided rows  sgn * F_fn(x) <= bnd
   const double *row_sgn, *row_bnd;
   const int *fn_row_up, *fn_row_lo;  // m+1 : row index of the upper / lower side of a function, or -1
@@ -66,10 +67,18 @@ struct IpmArgs {
   double *ws; size_t ws_stride; // per-CTA global workspace (doubles)
   int h_in_smem;
   long long *stats;             // [0] total iterations, [1] factorisations (optional)
+  long long *phase_cycles;      // 10 counters or null
   IpmOpt o;
 };
 
 __device__ __forceinline__ int tri(int i) { return (i * (i + 1)) >> 1; }
+
+// streaming read of shared read-only model data (no L1 allocation: one CTA per SM never re-reads it from L1)
+__device__ __forceinline__ double ld_stream(const double *p) {
+  double v;
+  asm("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
 
 // ---- block reductions: v[0..NS) summed, v[NS..NS+NM) maxed; result broadcast to every thread
 template <int NS, int NM>
@@ -145,41 +154,75 @@ __device__ __forceinline__ void syrk_tiles(double *H, int lo, int hi, const doub
 
 // ---- blocked right-looking Cholesky of rows/cols [0,N) of the packed matrix; rows [N, Nrows) are carried along
 // (they hold right-hand sides, so the forward substitution L w = rhs happens inside the factorisation).
-// Returns false (block-uniform) on a non-positive pivot.
-__device__ __forceinline__ bool chol_packed(double *H, int N, int Nrows, double *stage, int ld) {
+// Per 8-column panel: (1) one thread factors the 8x8 diagonal block in registers, (2) every other row of the panel is
+// solved against it by its own thread (TRSM) and staged, (3) the trailing matrix gets a rank-8 update from register
+// tiles.  The DIAGONAL of L is stored as its RECIPROCAL.  Returns false (block-uniform) on a non-positive pivot.
+__device__ __forceinline__ bool chol_packed(double *H, int N, int Nrows, double *stage, int ld, int *fail) {
   for (int j0 = 0; j0 < N; j0 += IPM_NB) {
     const int nb = min(IPM_NB, N - j0);
-    for (int c = 0; c < nb; ++c) {
-      const int j = j0 + c;
-      __syncthreads();
-      const double d = H[tri(j) + j];
-      if (!(d > 0.0) || !isfinite(d)) return false;
-      const double r = sqrt(d), inv = 1.0 / r;
-      // scale column j (rows j+1 .. Nrows-1)
-      for (int i = j + 1 + threadIdx.x; i < Nrows; i += IPM_NT) H[tri(i) + j] *= inv;
-      __syncthreads();
-      if (threadIdx.x == 0) H[tri(j) + j] = r;
-      // update the remaining panel columns j+1 .. j0+nb-1
-      const int rem = nb - c - 1;
-      if (rem > 0) {
-        const int rows = Nrows - (j + 1);
-        for (int e = threadIdx.x; e < rows * rem; e += IPM_NT) {
-          const int i = j + 1 + e / rem, cc = j + 1 + e % rem;
-          if (cc <= i || i >= N) {
-            if (cc <= i) H[tri(i) + cc] -= H[tri(i) + j] * H[tri(cc) + j];
-            else if (i >= N) H[tri(i) + cc] -= H[tri(i) + j] * H[tri(cc) + j];
-          }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double a[IPM_NB][IPM_NB];
+#pragma unroll
+      for (int i = 0; i < IPM_NB; ++i)
+#pragma unroll
+        for (int k = 0; k <= i; ++k) a[i][k] = (i < nb) ? H[tri(j0 + i) + j0 + k] : (i == k ? 1.0 : 0.0);
+      bool ok = true;
+#pragma unroll
+      for (int j = 0; j < IPM_NB; ++j) {
+        double d = a[j][j];
+#pragma unroll
+        for (int k = 0; k < j; ++k) d = fma(-a[j][k], a[j][k], d);
+        if (!(d > 0.0) || !isfinite(d)) ok = false;
+        const double inv = rsqrt(d);
+        a[j][j] = inv;   // reciprocal of the diagonal entry
+#pragma unroll
+        for (int i = j + 1; i < IPM_NB; ++i) {
+          double v = a[i][j];
+#pragma unroll
+          for (int k = 0; k < j; ++k) v = fma(-a[i][k], a[j][k], v);
+          a[i][j] = v * inv;
         }
       }
+#pragma unroll
+      for (int i = 0; i < IPM_NB; ++i)
+#pragma unroll
+        for (int k = 0; k <= i; ++k)
+          if (i < nb) H[tri(j0 + i) + j0 + k] = a[i][k];
+      *fail = ok ? 0 : 1;
     }
+    __syncthreads();
+    if (*fail) return false;
     const int lo = j0 + nb;
     if (lo >= Nrows) break;
-    __syncthreads();
-    // stage the panel: stage[c][i] = L[i, j0+c] for i in [lo, Nrows), zero elsewhere in the touched tile range
     const int lo4 = lo & ~3, hi4 = (Nrows + 3) & ~3;
-    for (int e = threadIdx.x; e < nb * (hi4 - lo4); e += IPM_NT) {
-      const int c = e / (hi4 - lo4), i = lo4 + e % (hi4 - lo4);
-      stage[c * ld + i] = (i >= lo && i < Nrows) ? H[tri(i) + j0 + c] : 0.0;
+    // TRSM: row i of the panel, x L_D' = a  (L_D strictly lower from shared memory, diagonal as reciprocal)
+    for (int i = lo4 + threadIdx.x; i < hi4; i += IPM_NT) {
+      double xr[IPM_NB];
+      if (i >= lo && i < Nrows) {
+        double *Hi = H + tri(i) + j0;
+#pragma unroll
+        for (int c = 0; c < IPM_NB; ++c) xr[c] = (c < nb) ? Hi[c] : 0.0;
+#pragma unroll
+        for (int c = 0; c < IPM_NB; ++c) {
+          if (c < nb) {
+            const double *Lc = H + tri(j0 + c) + j0;
+            double v = xr[c];
+#pragma unroll
+            for (int k = 0; k < c; ++k) v = fma(-xr[k], Lc[k], v);
+            xr[c] = v * Lc[c];
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < IPM_NB; ++c)
+          if (c < nb) Hi[c] = xr[c];
+      } else {
+#pragma unroll
+        for (int c = 0; c < IPM_NB; ++c) xr[c] = 0.0;
+      }
+#pragma unroll
+      for (int c = 0; c < IPM_NB; ++c)
+        if (c < nb) stage[c * ld + i] = xr[c];
     }
     __syncthreads();
     syrk_tiles(H, lo, Nrows, stage, ld, nb, -1.0);
@@ -188,74 +231,103 @@ __device__ __forceinline__ bool chol_packed(double *H, int N, int Nrows, double 
   return true;
 }
 
-// ---- backward substitution L' x = w for the two right-hand sides stored in rows N and N+1 (warps 0 and 1)
+// ---- backward substitution L' x = w for the two right-hand sides stored in rows N and N+1 (warps 0 and 1),
+// blocked by the same 8-row panels (diagonal of L holds reciprocals)
 __device__ __forceinline__ void backsolve2(double *H, int N) {
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (w < 2) {
     double *b = H + tri(N + w);
-    for (int i = N - 1; i >= 0; --i) {
-      const double *Li = H + tri(i);
-      const double xi = b[i] / Li[i];
+    const int nblk = (N + IPM_NB - 1) / IPM_NB;
+    for (int blk = nblk - 1; blk >= 0; --blk) {
+      const int i0 = blk * IPM_NB, nb = min(IPM_NB, N - i0);
+      // solve the diagonal block (every lane redundantly; all reads are broadcasts)
+      double xr[IPM_NB];
+#pragma unroll
+      for (int c = 0; c < IPM_NB; ++c) xr[c] = (c < nb) ? b[i0 + c] : 0.0;
+#pragma unroll
+      for (int c = IPM_NB - 1; c >= 0; --c) {
+        if (c < nb) {
+          double v = xr[c];
+#pragma unroll
+          for (int cc = c + 1; cc < IPM_NB; ++cc)
+            if (cc < nb) v = fma(-H[tri(i0 + cc) + i0 + c], xr[cc], v);
+          xr[c] = v * H[tri(i0 + c) + i0 + c];
+        }
+      }
       __syncwarp();
-      for (int k = lane; k < i; k += 32) b[k] -= Li[k] * xi;
-      if (lane == 0) b[i] = xi;
+      if (lane < nb) b[i0 + lane] = (lane == 0) ? xr[0] : (lane == 1) ? xr[1] : (lane == 2) ? xr[2] : (lane == 3) ? xr[3]
+                                  : (lane == 4) ? xr[4] : (lane == 5) ? xr[5] : (lane == 6) ? xr[6] : xr[7];
+      // b[k] -= sum_c L[i0+c][k] x_c   for k < i0
+      for (int k = lane; k < i0; k += 32) {
+        double v = b[k];
+#pragma unroll
+        for (int c = 0; c < IPM_NB; ++c)
+          if (c < nb) v = fma(-H[tri(i0 + c) + k], xr[c], v);
+        b[k] = v;
+      }
       __syncwarp();
     }
   }
   __syncthreads();
 }
 
-// ---- u_k = Q_k d for every packed quadratic block (symmetric mat-vec: each packed element is read once);
-// uq[k][0..n) written to global, du[k] = d.u_k.  `stage` needs (IPM_NW + 1) * ld doubles.
-__device__ __forceinline__ void pass_U(const DevModel &M, const double *d, double *uq, double *du, double *stage,
-                                       int ld, double *red) {
+// ---- u_k = Q_k d for every quadratic block, from the FULL (n x n, row-major) copies: one warp per row, four rows
+// in flight per warp (aligned, fully coalesced 8-byte loads; lane l owns columns l + 32c and keeps d there in
+// registers).  uq[k][0..n) goes to global; du[k] = d.u_k is reduced afterwards by one warp per block.
+template <int MAXC>
+__device__ __forceinline__ void pass_U(const DevModel &M, const double *d, double *uq, double *du, const int *qfn,
+                                       int nqf) {
   const int n = M.n, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nc = (n + 31) >> 5;
-  double *urow = stage + IPM_NW * ld;
-  for (int k = 0; k <= M.m; ++k) {
-    const int q = M.qidx[k];
-    if (q < 0) {
-      if (threadIdx.x == 0) du[k] = 0.0;
-      continue;
+  double dreg[MAXC];
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) dreg[c] = (c < nc && lane + 32 * c < n) ? d[lane + 32 * c] : 0.0;
+  const int nrows = nqf * n;
+  for (int g = w * 4; g < nrows; g += IPM_NW * 4) {
+    const double *Qr[4];
+    double *out[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int rho = min(g + u, nrows - 1);
+      const int qi = rho / n, r = rho - qi * n;
+      const int k = qfn[qi];
+      Qr[u] = M.Qf + ((size_t)M.qidx[k] * n + r) * n;
+      out[u] = uq + (size_t)k * n + r;
     }
-    const double *Q = M.Qp + (size_t)q * M.P;
-    double col[IPM_MAXC];
+    double rs[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-    for (int c = 0; c < IPM_MAXC; ++c) col[c] = 0.0;
-    for (int r = w; r < n; r += IPM_NW) {
-      const double *Qr = Q + tri(r);
-      const double dr = d[r];
-      double rs = 0.0;
+    for (int c4 = 0; c4 < MAXC; c4 += 4) {
+      if (c4 < nc) {
+        double qv[4][4];
 #pragma unroll
-      for (int c = 0; c < IPM_MAXC; ++c) {
-        const int j = lane + 32 * c;
-        if (c < nc && j <= r) {
-          const double qv = __ldg(Qr + j);
-          rs = fma(qv, d[j], rs);
-          if (j < r) col[c] = fma(qv, dr, col[c]);
+        for (int cc = 0; cc < 4; ++cc) {
+          const int j = min(lane + 32 * (c4 + cc), n - 1);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) qv[cc][u] = ld_stream(Qr[u] + j);
         }
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+          for (int u = 0; u < 4; ++u) rs[u] = fma(qv[cc][u], dreg[c4 + cc], rs[u]);   // dreg is 0 beyond n
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
-      if (lane == 0) urow[r] = rs;
     }
 #pragma unroll
-    for (int c = 0; c < IPM_MAXC; ++c) {
-      const int j = lane + 32 * c;
-      if (c < nc && j < n) stage[w * ld + j] = col[c];
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) rs[u] += __shfl_xor_sync(0xffffffffu, rs[u], o);
     }
-    __syncthreads();
+    if (lane < 4 && g + lane < nrows) *((lane == 0) ? out[0] : (lane == 1) ? out[1] : (lane == 2) ? out[2] : out[3]) =
+        (lane == 0) ? rs[0] : (lane == 1) ? rs[1] : (lane == 2) ? rs[2] : rs[3];
+  }
+  __syncthreads();
+  for (int qi = w; qi < nqf; qi += IPM_NW) {
+    const int k = qfn[qi];
+    const double *uk = uq + (size_t)k * n;
     double part = 0.0;
-    for (int j = threadIdx.x; j < n; j += IPM_NT) {
-      double u = urow[j];
-      for (int ww = 0; ww < IPM_NW; ++ww) u += stage[ww * ld + j];
-      uq[(size_t)k * n + j] = u;
-      part = fma(d[j], u, part);
-    }
-    double v[1] = {part};
-    block_reduce<1, 0>(v, red);
-    if (threadIdx.x == 0) du[k] = v[0];
-    __syncthreads();
+    for (int j = lane; j < n; j += 32) part = fma(d[j], uk[j], part);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) du[k] = part;
   }
   __syncthreads();
 }
@@ -284,6 +356,18 @@ __device__ __forceinline__ void dots_grad(const DevModel &M, const double *grad,
 
 enum { F_FIXED = 1, F_HASL = 2, F_HASU = 4 };
 
+// optional per-phase cycle counters (IpmArgs::phase_cycles != nullptr): 0 residuals 1 W pass 2 J'SJ 3 Cholesky
+// 4 back-substitution 5 direction/mu 6 U pass 7 line search 8 update 9 init
+#define PH_MARK(idx)                                               \
+  do {                                                             \
+    if (A.phase_cycles) {                                          \
+      const long long t_ = clock64();                              \
+      ph[idx] += t_ - ph_t0;                                       \
+      ph_t0 = t_;                                                  \
+    }                                                              \
+  } while (0)
+
+template <int MAXC>
 __global__ void __launch_bounds__(IPM_NT, 1) ipm_kernel(DevModel M, IpmArgs A) {
   extern __shared__ __align__(16) double smem[];
   const int n = M.n, m = M.m, N = M.N, R = M.R, npad = M.npad;
@@ -320,11 +404,25 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_kernel(DevModel M, IpmArgs A) {
   double *gd0 = sp; sp += Kp;
   double *gd1 = sp; sp += Kp;
   double *du = sp; sp += Kp;
-  double *wq = sp; sp += Kp;
+  double *wq = sp; sp += 2 * Kp;
   double *red = sp; sp += IPM_NW * 12;
   int *flg = reinterpret_cast<int *>(sp);  // N ints
-  __shared__ int s_child;
+  int *fixlist = flg + ((N + 1) & ~1);     // N ints
+  int *qblk = fixlist + ((N + 1) & ~1);    // m+1 ints
+  int *qfn = qblk + Kp;                    // m+1 ints: functions that own a quadratic block
+  double *qwt = wq + Kp;                   // m+1 weights of the compact list
+  __shared__ int s_child, s_nqa, s_nfix, s_fail;
   double *d0 = H + tri(N), *d1 = H + tri(N + 1);   // solutions live in the augmented rows
+  __shared__ int s_nqf;
+  if (tid == 0) {
+    int c = 0;
+    for (int k = 0; k <= m; ++k)
+      if (M.qidx[k] >= 0) qfn[c++] = k;
+    s_nqf = c;
+  }
+  for (int k = tid; k <= m; k += IPM_NT) du[k] = 0.0;
+  __syncthreads();
+  const int nqf = s_nqf;
 
   for (;;) {
     __syncthreads();
@@ -332,6 +430,8 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_kernel(DevModel M, IpmArgs A) {
     __syncthreads();
     const int child = s_child;
     if (child >= A.B) break;
+    long long ph[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long ph_t0 = A.phase_cycles ? clock64() : 0;
     const double *xl = A.XL + (size_t)child * n, *xu = A.XU + (size_t)child * n;
     const double *x0 = A.X0 + (size_t)child * A.x0_stride;
 
@@ -385,7 +485,7 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_kernel(DevModel M, IpmArgs A) {
     __syncthreads();
 
     // ------------------------------------------------------------------ full evaluation at x: grad_k = a_k + Q_k x
-    pass_U(M, x, uq, du, stage, npad, red);
+    pass_U<MAXC>(M, x, uq, du, qfn, nqf);
     {
       const int w = tid >> 5, lane = tid & 31;
       for (int k = w; k <= m; k += IPM_NW) {
@@ -477,6 +577,7 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_kernel(DevModel M, IpmArgs A) {
       __syncthreads();
     };
     if (!done) init_slacks_mults();
+    PH_MARK(9);
 
     while (!done) {
       const double of = phase1 ? 0.0 : sf;
@@ -606,6 +707,7 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_kernel(DevModel M, IpmArgs A) {
       };
       if (to_p1) { enter_phase1(); ++iters; continue; }
 
+      PH_MARK(0);
       // ---------------------------------------------------------------- condensed matrix + factorisation
       for (int k = tid; k <= m; k += IPM_NT) {
         double w = (k == 0) ? of : 0.0;
@@ -615,51 +717,94 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_kernel(DevModel M, IpmArgs A) {
         wq[k] = w;
       }
       __syncthreads();
+      if (tid == 0) {  // compact list of quadratic blocks with a non-zero weight
+        int c = 0;
+        for (int k = 0; k <= m; ++k)
+          if (M.qidx[k] >= 0 && wq[k] != 0.0) { qblk[c] = M.qidx[k]; qwt[c] = wq[k]; ++c; }
+        s_nqa = c;
+        int f = 0;
+        for (int j = 0; j < N; ++j)
+          if (flg[j] & F_FIXED) fixlist[f++] = j;
+        s_nfix = f;
+      }
+      __syncthreads();
+      const int nqa = s_nqa, nfix = s_nfix;
       double delta_w = 0.0;
       bool fact_ok = false;
       for (int attempt = 0; attempt < 45; ++attempt) {
         // W pass: H[i,k] = sum_q wq[q] Qp_q[i,k] (+ diagonal), one warp per row, fixed rows/cols -> identity
         {
-          const int w = tid >> 5, lane = tid & 31;
-          for (int i = w; i < N; i += IPM_NW) {
-            double *Hi = H + tri(i);
-            const int fi = flg[i] & F_FIXED;
-            for (int k = lane; k <= i; k += 32) {
-              double a = 0.0;
-              if (fi || (flg[k] & F_FIXED)) a = (i == k) ? 1.0 : 0.0;
-              else {
-                if (i < n) {
-                  const size_t e = (size_t)tri(i) + k;
-                  for (int fn = 0; fn <= m; ++fn) {
-                    const int q = M.qidx[fn];
-                    if (q >= 0) a = fma(wq[fn], __ldg(M.Qp + (size_t)q * M.P + e), a);
-                  }
-                }
-                if (i == k) a += Sx[i] + delta_w;
+          const int P = M.P;
+          for (int base = 0; base < P; base += 4 * IPM_NT) {
+            int idx[4];
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) idx[u] = min(base + u * IPM_NT + tid, P - 1);
+            int qi = 0;
+            for (; qi + 4 <= nqa; qi += 4) {
+              double qv[4][4];
+#pragma unroll
+              for (int a = 0; a < 4; ++a) {
+                const double *Qb = M.Qp + (size_t)qblk[qi + a] * P;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) qv[a][u] = ld_stream(Qb + idx[u]);
               }
-              Hi[k] = a;
+#pragma unroll
+              for (int a = 0; a < 4; ++a) {
+                const double wgt = qwt[qi + a];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) acc[u] = fma(wgt, qv[a][u], acc[u]);
+              }
+            }
+            for (; qi < nqa; ++qi) {
+              const double *Qb = M.Qp + (size_t)qblk[qi] * P;
+              const double wgt = qwt[qi];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) acc[u] = fma(wgt, ld_stream(Qb + idx[u]), acc[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int e = base + u * IPM_NT + tid;
+              if (e < P) H[e] = acc[u];
             }
           }
+          // elastic row
+          for (int k = tid; k <= n; k += IPM_NT) H[tri(n) + k] = 0.0;
         }
         __syncthreads();
+        // fixed variables: identity rows/columns; then the diagonal Sigma_x + delta_w
+        for (int e = tid; e < nfix * N; e += IPM_NT) {
+          const int j = fixlist[e / N], t = e % N;
+          if (t < j) H[tri(j) + t] = 0.0;
+          else if (t > j) H[tri(t) + j] = 0.0;
+        }
+        __syncthreads();
+        for (int j = tid; j < N; j += IPM_NT) {
+          if (flg[j] & F_FIXED) H[tri(j) + j] = 1.0;
+          else H[tri(j) + j] += Sx[j] + delta_w;
+        }
+        __syncthreads();
+        PH_MARK(1);
         // J' Sigma_s J through staged rank-KC updates: stage[c][j] = sqrt(Ss_r) J[r][j]
         for (int r0 = 0; r0 < R; r0 += IPM_KC) {
           const int kc = min(IPM_KC, R - r0);
-          for (int e = tid; e < kc * npad; e += IPM_NT) {
-            const int c = e / npad, j = e % npad, r = r0 + c;
-            double vv = 0.0;
-            if (j < N && !(flg[j] & F_FIXED)) {
-              const double sq = sqrt(Ss[r]);
-              vv = (j < n) ? sq * fsc[r] * grad[(size_t)M.row_fn[r] * n + j] : -sq;
+          for (int c = tid >> 5; c < kc; c += IPM_NW) {   // one warp per staged row
+            const int r = r0 + c;
+            const double sq = sqrt(Ss[r]), f = sq * fsc[r];
+            const double *g = grad + (size_t)M.row_fn[r] * n;
+            for (int j = tid & 31; j < npad; j += 32) {
+              double vv = 0.0;
+              if (j < N && !(flg[j] & F_FIXED)) vv = (j < n) ? f * g[j] : -sq;
+              stage[c * npad + j] = vv;
             }
-            stage[c * npad + j] = vv;
           }
           __syncthreads();
           syrk_tiles(H, 0, N, stage, npad, kc, 1.0);
           __syncthreads();
         }
         ++nfact;
-        if (chol_packed(H, N, N + 2, stage, npad)) { fact_ok = true; break; }
+        PH_MARK(2);
+        if (chol_packed(H, N, N + 2, stage, npad, &s_fail)) { fact_ok = true; break; }
         // inertia correction (first_hessian_perturbation 1e-4, x100 then x8, /3 between iterations)
         if (delta_w == 0.0) delta_w = (delta_w_last == 0.0) ? 1e-4 : fmax(1e-20, delta_w_last / 3.0);
         else delta_w *= (delta_w_last == 0.0 ? 100.0 : 8.0);
@@ -691,7 +836,9 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_kernel(DevModel M, IpmArgs A) {
       }
       if (!fact_ok) { status = ST_computationError; objv = val[0]; with_duals = true; done = true; break; }
       if (delta_w > 0) delta_w_last = delta_w;
+      PH_MARK(3);
       backsolve2(H, N);   // d0 = H^-1 rhs0, d1 = H^-1 rhs1
+      PH_MARK(4);
 
       // ---------------------------------------------------------------- J d0, J d1 per row
       dots_grad(M, grad, d0, d1, gd0, gd1);
@@ -777,9 +924,11 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_kernel(DevModel M, IpmArgs A) {
       for (int k = tid; k <= m; k += IPM_NT) gd0[k] = gd0[k] + mu * gd1[k];   // gd = grad_k . dx
       __syncthreads();
 
+      PH_MARK(5);
       // ---------------------------------------------------------------- u_k = Q_k dx, du_k = dx.u_k
-      pass_U(M, dx, uq, du, stage, npad, red);
+      pass_U<MAXC>(M, dx, uq, du, qfn, nqf);
 
+      PH_MARK(6);
       // ---------------------------------------------------------------- filter line search
       const double dxt = phase1 ? dx[n] : 0.0;
       auto merit = [&](double a, double &theta, double &phi) {
@@ -850,6 +999,7 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_kernel(DevModel M, IpmArgs A) {
       }
       a_last1 = a_last0; a_last0 = alpha;
 
+      PH_MARK(7);
       // ---------------------------------------------------------------- accept the step
       __syncthreads();
       for (int j = tid; j < N; j += IPM_NT) {
@@ -886,6 +1036,7 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_kernel(DevModel M, IpmArgs A) {
       }
       __syncthreads();
       ++iters;
+      PH_MARK(8);
     }
 
     // ------------------------------------------------------------------ results (TMINLP2TNLP layout)
@@ -902,6 +1053,8 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_kernel(DevModel M, IpmArgs A) {
     }
     if (tid == 0) {
       A.OBJ[child] = objv; A.STATUS[child] = status; A.ITERS[child] = iters;
+      if (A.phase_cycles)
+        for (int q = 0; q < 10; ++q) atomicAdd((unsigned long long *)&A.phase_cycles[q], (unsigned long long)ph[q]);
       if (A.stats) { atomicAdd((unsigned long long *)&A.stats[0], (unsigned long long)iters);
                      atomicAdd((unsigned long long *)&A.stats[1], (unsigned long long)nfact); }
     }

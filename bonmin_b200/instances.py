@@ -130,7 +130,7 @@ def c3_children(model: StructuredModel, xstar: np.ndarray, B: int, first: int = 
     for b in range(B):
         k = first + b
         r = np.random.Generator(np.random.PCG64(7 + k))
-        d = int(r.integers(0, 21))
+        d = min(int(r.integers(0, 21)), n_int)
         if d:
             for jj in r.choice(n_int, d, replace=False):
                 j = ints[jj]

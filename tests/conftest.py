@@ -1,0 +1,26 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def oracle_ipm():
+    from oracle import ipm
+    ipm.build()
+    return ipm
+
+
+@pytest.fixture(scope="session")
+def bnlp_lib():
+    from bonmin_b200 import build, engine
+    build.build()
+    return engine.lib()

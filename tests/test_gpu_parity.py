@@ -1,0 +1,156 @@
+"""GPU suite (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle on the same seeded inputs.
+Bar (BASELINE.json north_star): same feasibility status per child, objective within 1e-6 relative."""
+import numpy as np
+import pytest
+
+from bonmin_b200 import instances as I
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-6
+
+
+def _engine(model, **kw):
+    from bonmin_b200.engine import Engine, Problem
+    return Engine(Problem.from_model(model), **kw)
+
+
+def _compare(r, o, want_iters=False):
+    assert (r["status"] == o["status"]).all(), np.flatnonzero(r["status"] != o["status"])
+    ok = o["status"] == 1
+    rel = np.abs(r["obj"] - o["obj"]) / np.maximum(1.0, np.abs(o["obj"]))
+    assert rel[ok].max(initial=0.0) <= RTOL
+    return ok
+
+
+def test_mytoy_goldens(bnlp_lib, oracle_ipm):
+    m = I.mytoy()
+    XL = np.tile(m.xl, (3, 1))
+    XU = np.tile(m.xu, (3, 1))
+    XL[1, 2] = 1.0
+    XU[2, 2] = 0.0
+    eng = _engine(m)
+    r = eng.solve_batch(XL, XU, m.x0)
+    o = oracle_ipm.solve_batch(m, XL, XU, m.x0)
+    _compare(r, o)
+    sq5 = 5 ** 0.5
+    assert r["obj"][0] == pytest.approx(-(1.5 + sq5 / 2), rel=1e-7)       # InterfaceTest.cpp:134
+    assert r["duals"][0][8] == pytest.approx(sq5, rel=1e-6)               # :155-159
+    assert r["duals"][0][9] == pytest.approx(1.0, rel=1e-6)
+    assert r["x"][1][2] == 1.0 and r["x"][2][2] == 0.0                    # :165-189
+    assert list(r["status"]) == [1, 1, 1]
+    np.testing.assert_allclose(r["x"], o["x"], atol=1e-6)
+    np.testing.assert_allclose(r["duals"], o["duals"], atol=1e-5)
+
+
+@pytest.mark.parametrize("shape,B", [((100, 50, 20, 20, 20261019), 256), ((200, 100, 40, 40, 20261020), 300)])
+def test_children_parity(bnlp_lib, oracle_ipm, shape, B):
+    m = I.syn_miqcp(*shape)
+    eng = _engine(m)
+    root = eng.solve_batch(m.xl, m.xu, m.x0)
+    oroot = oracle_ipm.solve_batch(m, m.xl, m.xu, m.x0)
+    _compare(root, oroot)
+    xs = root["x"][0]
+    XL, XU = I.c3_children(m, xs, B)
+    r = eng.solve_batch(XL, XU, xs)
+    o = oracle_ipm.solve_batch(m, XL, XU, xs, threads=8)
+    ok = _compare(r, o)
+    assert ok.sum() > B // 2
+    np.testing.assert_allclose(r["x"][ok], o["x"][ok], atol=1e-5)
+    np.testing.assert_allclose(r["g"][ok], o["g"][ok], atol=1e-5)
+    st = eng.stats()
+    assert st["iterations"] == int(r["iters"].sum())
+
+
+def test_infeasible_children_status(bnlp_lib, oracle_ipm):
+    """Constraint-infeasible children (not just crossed bounds): status parity, and obj = max-norm violation
+    (BonTMINLP2TNLP.cpp:503-505) within 1e-4 relative."""
+    m = I.syn_miqcp(30, 15, 6, 6, 5)
+    eng = _engine(m)
+    xs = eng.solve_batch(m.xl, m.xu, m.x0)["x"][0]
+    rng = np.random.default_rng(1)
+    B = 200
+    XL = np.tile(m.xl, (B, 1))
+    XU = np.tile(m.xu, (B, 1))
+    for b in range(B):
+        for j in rng.choice(15, rng.integers(1, 12), replace=False):
+            if rng.random() < 0.5:
+                XL[b, j] = XU[b, j] = rng.integers(0, 11)
+            else:
+                v = rng.integers(0, 10)
+                if rng.random() < 0.5:
+                    XL[b, j] = v + 1
+                else:
+                    XU[b, j] = v
+    r = eng.solve_batch(XL, XU, xs)
+    o = oracle_ipm.solve_batch(m, XL, XU, xs, threads=8)
+    _compare(r, o)
+    inf = o["status"] == 3
+    assert inf.sum() >= 10
+    np.testing.assert_allclose(r["obj"][inf], o["obj"][inf], rtol=1e-4)
+
+
+def test_edge_cases(bnlp_lib, oracle_ipm):
+    m = I.syn_miqcp(20, 10, 4, 4, 9)
+    eng = _engine(m)
+    xs = eng.solve_batch(m.xl, m.xu, m.x0)["x"][0]
+    XL = np.tile(m.xl, (4, 1))
+    XU = np.tile(m.xu, (4, 1))
+    XL[0] = XU[0] = np.round(m.x0)            # all fixed -> zeroDimension short cut (BonTNLPSolver.cpp:78-161)
+    XL[1, 0], XU[1, 0] = 5.0, 4.0             # crossed bounds
+    XL[2, :10] = XU[2, :10] = np.round(xs[:10])  # all integers fixed (the NLP(y) of OA)
+    r = eng.solve_batch(XL, XU, xs)           # child 3: the root itself
+    o = oracle_ipm.solve_batch(m, XL, XU, xs)
+    _compare(r, o)
+    assert r["iters"][0] == 0 and r["status"][1] == 3
+    # per-child start points and B = 1
+    r1 = eng.solve_batch(XL[3], XU[3], np.tile(xs, (1, 1)))
+    assert r1["status"][0] == 1 and abs(r1["obj"][0] - r["obj"][3]) <= RTOL * abs(r["obj"][3])
+    # outputs may be skipped
+    r2 = eng.solve_batch(XL, XU, xs, want_x=False, want_g=False, want_duals=False)
+    assert np.array_equal(r2["obj"], r["obj"])
+
+
+def test_determinism_and_queue_order(bnlp_lib):
+    """The work queue hands children to CTAs in a timing-dependent order; results must not depend on it."""
+    m = I.syn_miqcp(40, 20, 8, 8, 3)
+    eng = _engine(m)
+    xs = eng.solve_batch(m.xl, m.xu, m.x0)["x"][0]
+    XL, XU = I.c3_children(m, xs, 400)
+    a = eng.solve_batch(XL, XU, xs)
+    b = eng.solve_batch(XL, XU, xs)
+    eng2 = _engine(m, ctas_per_device=7)
+    c = eng2.solve_batch(XL, XU, xs)
+    for k in ("obj", "status", "iters", "x"):
+        assert np.array_equal(a[k], b[k]) and np.array_equal(a[k], c[k])
+
+
+def test_size_independent_properties_full_batch(bnlp_lib):
+    """BASELINE-size batch (C3, 4096 children) checked through properties that need no oracle:
+    (i) optimal children are feasible for the original rows and bounds, (ii) a child's optimum is never below its
+    parent's (relaxation monotonicity), (iii) KKT stationarity holds with the returned multipliers."""
+    m = I.config_c3()
+    eng = _engine(m)
+    root = eng.solve_batch(m.xl, m.xu, m.x0)
+    xs = root["x"][0]
+    B = 4096
+    XL, XU = I.c3_children(m, xs, B)
+    r = eng.solve_batch(XL, XU, xs)
+    ok = r["status"] == 1
+    assert ok.sum() > B // 2 and set(np.unique(r["status"])) <= {1, 2, 3}
+    assert (r["obj"][ok] >= root["obj"][0] - 1e-6 * abs(root["obj"][0])).all()
+    assert (r["g"][ok] <= m.gu + 1e-6 * (1 + np.abs(m.gu))).all()
+    assert (r["x"][ok] >= XL[ok]).all() and (r["x"][ok] <= XU[ok]).all()
+    # stationarity on a sample: grad f + J' lambda - zL + zU = 0
+    from bonmin_b200.instances import unpack_lower
+    n = m.n
+    Q = {int(fn): unpack_lower(m.qd[k], n) for k, fn in enumerate(m.qd_fn)}
+    for b in np.flatnonzero(ok)[:16]:
+        x = r["x"][b]
+        lam = r["duals"][b][2 * n:]
+        g = m.A[0] + Q[0] @ x
+        for i in range(m.m):
+            gi = m.A[i + 1] + (Q[i + 1] @ x if (i + 1) in Q else 0.0)
+            g = g + lam[i] * gi
+        g = g - r["duals"][b][:n] + r["duals"][b][n:2 * n]
+        free = XU[b] > XL[b]
+        assert np.abs(g[free]).max() <= 1e-5 * (1 + np.abs(m.A[0]).max())

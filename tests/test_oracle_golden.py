@@ -1,0 +1,120 @@
+"""CPU suite: pin the oracle against the reference's own known answers on test/mytoy.nl
+(test/InterfaceTest.cpp:122-189) and against an independent solver (scipy SLSQP) on synthetic shapes."""
+import numpy as np
+import pytest
+
+from bonmin_b200 import instances as I
+
+SQ5 = 5 ** 0.5
+
+
+def test_mytoy_root_relaxation(oracle_ipm):
+    # InterfaceTest.cpp:122-162: obj = -(3/2+sqrt5/2), y1 = x = 1/2+1/sqrt5, y2 = 1/2+1/(2 sqrt5),
+    # activities c1 = 1/4, c2 = 0, multipliers sqrt5 and 1 (CoinRelFltEq 1e-7)
+    m = I.mytoy()
+    r = oracle_ipm.solve_batch(m, m.xl, m.xu, m.x0)
+    assert r["status"][0] == 1 and r["iters"][0] > 0
+    assert r["obj"][0] == pytest.approx(-(1.5 + SQ5 / 2), rel=1e-7)
+    x = r["x"][0]
+    assert x[0] == pytest.approx(0.5 + 1 / SQ5, rel=1e-6)
+    assert x[1] == pytest.approx(0.5 + 1 / (2 * SQ5), rel=1e-6)
+    assert x[2] == pytest.approx(0.5 + 1 / SQ5, rel=1e-6)
+    assert r["g"][0][0] == pytest.approx(0.25, rel=1e-6)
+    assert r["g"][0][1] == pytest.approx(0.0, abs=1e-6)
+    lam = r["duals"][0][2 * m.n:]
+    assert lam[0] == pytest.approx(SQ5, rel=1e-6)
+    assert lam[1] == pytest.approx(1.0, rel=1e-6)
+    assert lam[2] == pytest.approx(0.0, abs=1e-6)
+
+
+def test_mytoy_children(oracle_ipm):
+    # InterfaceTest.cpp:165-189: x>=1 -> optimal with x = 1 (single-point feasible set); x<=0 -> optimal with x = 0.
+    m = I.mytoy()
+    XL = np.tile(m.xl, (2, 1))
+    XU = np.tile(m.xu, (2, 1))
+    XL[0, 2] = 1.0
+    XU[1, 2] = 0.0
+    r = oracle_ipm.solve_batch(m, XL, XU, m.x0)
+    assert list(r["status"]) == [1, 1]
+    assert r["x"][0][2] == 1.0 and r["x"][1][2] == 0.0
+    # analytic objectives -2.5 and -(1+1/sqrt2); the x>=1 child is only reachable thanks to the 1e-8 bound
+    # relaxation, which moves its optimum by O(sqrt(1e-8))
+    assert r["obj"][0] == pytest.approx(-2.5, abs=5e-4)
+    assert r["obj"][1] == pytest.approx(-(1 + 2 ** -0.5), rel=1e-6)
+
+
+def test_all_fixed_shortcut(oracle_ipm):
+    # BonTNLPSolver.cpp:78-161: every |xu-xl| <= 1e-5 -> evaluate at xl, feasibility tolerance 1e-7
+    m = I.mytoy()
+    x = np.array([0.5, 0.5, 0.0, 1.0])
+    r = oracle_ipm.solve_batch(m, x, x, m.x0)
+    assert r["status"][0] == 1 and r["iters"][0] == 0
+    assert r["obj"][0] == pytest.approx(-1.0)
+    x = np.array([2.0, 2.0, 1.0, 1.0])
+    r = oracle_ipm.solve_batch(m, x, x, m.x0)
+    assert r["status"][0] == 3
+
+
+def _scipy_solve(model, dense, xl, xu, x0):
+    from scipy.optimize import minimize
+    c, A, qidx, Q = dense
+    n = model.n
+
+    def fn(k):
+        Qk = Q[qidx[k]] if qidx[k] >= 0 else np.zeros((n, n))
+        return (lambda x: c[k] + A[k] @ x + 0.5 * x @ Qk @ x), (lambda x: A[k] + Qk @ x)
+    f0, g0 = fn(0)
+    cons = []
+    for i in range(model.m):
+        fi, gi = fn(i + 1)
+        cons.append({"type": "ineq", "fun": (lambda x, fi=fi, i=i: model.gu[i] - fi(x)),
+                     "jac": (lambda x, gi=gi: -gi(x))})
+    res = minimize(f0, np.clip(x0, xl, xu), jac=g0, bounds=list(zip(xl, xu)), constraints=cons, method="SLSQP",
+                   options={"maxiter": 500, "ftol": 1e-12})
+    viol = max([0.0] + [-cc["fun"](res.x) for cc in cons])
+    return res.fun, viol
+
+
+def test_against_scipy_on_random_children(oracle_ipm):
+    """Independent cross-check: same optimum within 1e-6 relative and the same
+    feasible/infeasible verdict as SLSQP on 60 random children of a small SYN-MIQCP."""
+    m = I.syn_miqcp(30, 15, 6, 6, 5)
+    dense = oracle_ipm.dense_arrays(m)
+    root = oracle_ipm.solve_batch(m, m.xl, m.xu, m.x0, dense=dense)
+    assert root["status"][0] == 1
+    xs = root["x"][0]
+    rng = np.random.default_rng(1)
+    B = 60
+    XL = np.tile(m.xl, (B, 1))
+    XU = np.tile(m.xu, (B, 1))
+    for b in range(B):
+        for j in rng.choice(15, rng.integers(1, 12), replace=False):
+            if rng.random() < 0.5:
+                XL[b, j] = XU[b, j] = rng.integers(0, 11)
+            else:
+                v = rng.integers(0, 10)
+                if rng.random() < 0.5:
+                    XL[b, j] = v + 1
+                else:
+                    XU[b, j] = v
+    r = oracle_ipm.solve_batch(m, XL, XU, xs, threads=4, dense=dense)
+    n_inf = 0
+    for b in range(B):
+        fun, viol = _scipy_solve(m, dense, XL[b], XU[b], xs)
+        if r["status"][b] == 1:
+            assert viol < 1e-5, (b, viol)
+            assert abs(fun - r["obj"][b]) <= 1e-6 * max(1.0, abs(fun)), (b, fun, r["obj"][b])
+        else:
+            assert r["status"][b] == 3
+            assert viol > 1e-6, (b, viol)
+            n_inf += 1
+    assert n_inf >= 3  # the sample does contain infeasible children
+
+
+def test_threads_agree(oracle_ipm):
+    m = I.syn_miqcp(20, 10, 4, 4, 9)
+    root = oracle_ipm.solve_batch(m, m.xl, m.xu, m.x0)
+    XL, XU = I.c3_children(m, root["x"][0], 32)
+    a = oracle_ipm.solve_batch(m, XL, XU, root["x"][0], threads=1)
+    b = oracle_ipm.solve_batch(m, XL, XU, root["x"][0], threads=4)
+    assert (a["status"] == b["status"]).all() and np.array_equal(a["obj"], b["obj"])
