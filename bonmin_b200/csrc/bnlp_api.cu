@@ -169,7 +169,8 @@ static int upload(DBuf<T> &b, const std::vector<T> &v) {
   return 0;
 }
 
-int build_eval_tape(const HostModel &M, std::vector<int> &ints, std::vector<double> &dbls, EvalModelHostOffsets &off);
+int build_eval_tape(const HostModel &M, bool densified, std::vector<int> &ints, std::vector<double> &dbls,
+                    EvalModelHostOffsets &off, const std::vector<int> &qidx);
 
 extern "C" bnlp_engine *bnlp_engine_create(const bnlp_problem *prob, const int *device_ids, int ndev,
                                            const bnlp_options *opt) {
@@ -207,7 +208,8 @@ extern "C" bnlp_engine *bnlp_engine_create(const bnlp_problem *prob, const int *
     const double *src = M.qd.data() + q * P;
     for (size_t e = 0; e < P; ++e) dst[e] += src[e];
   }
-  for (size_t e = 0; e < M.qs_fn.size(); ++e) {
+  const bool densify = n <= 32 * IPM_MAXC;   // small models: every quadratic part becomes a dense block
+  for (size_t e = 0; densify && e < M.qs_fn.size(); ++e) {
     double *dst = block_of(M.qs_fn[e]);
     dst[(size_t)M.qs_i[e] * (M.qs_i[e] + 1) / 2 + M.qs_j[e]] += M.qs_v[e];
   }
@@ -241,7 +243,7 @@ extern "C" bnlp_engine *bnlp_engine_create(const bnlp_problem *prob, const int *
   std::vector<int> e_ints;
   std::vector<double> e_dbls;
   EvalModelHostOffsets eoff;
-  build_eval_tape(M, e_ints, e_dbls, eoff);
+  build_eval_tape(M, densify, e_ints, e_dbls, eoff, qidx);
 
   for (size_t d = 0; d < ids.size(); ++d) {
     Device &D = E->devs[d];
@@ -266,6 +268,7 @@ extern "C" bnlp_engine *bnlp_engine_create(const bnlp_problem *prob, const int *
     bad |= upload(D.e_int, e_ints); bad |= upload(D.e_dbl, e_dbls);
     if (bad) { set_err("device upload failed"); delete E; return nullptr; }
     D.ev = make_eval_model_dev(eoff, D.e_int.p, D.e_dbl.p, D.gl.p, D.gu.p);
+    D.ev.qidx = D.qidx.p; D.ev.Qp = D.Qp.p; D.ev.Qf = D.Qf.p;
     DevModel &dm = D.dm;
     dm.n = n; dm.m = m; dm.N = n + 1; dm.R = E->R; dm.nq = E->nq; dm.P = (int)P;
     dm.npad = (dm.N + 2 + 3) & ~3;

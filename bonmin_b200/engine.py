@@ -33,7 +33,8 @@ class Options(ctypes.Structure):
 
 
 class OaTols(ctypes.Structure):
-    _fields_ = [("tiny", c_dbl), ("very_tiny", c_dbl), ("rhs_relax", c_dbl), ("infty", c_dbl)]
+    _fields_ = [("tiny", c_dbl), ("very_tiny", c_dbl), ("rhs_relax", c_dbl), ("infty", c_dbl),
+                ("skip_non_violated", c_int)]
 
 
 EXPORTS = ["bnlp_last_error", "bnlp_problem_from_nl", "bnlp_problem_from_tape", "bnlp_problem_free",
@@ -261,7 +262,7 @@ class Engine:
         XU = _d(info["xu"] if XU is None else XU)
         Du = None if DUALS is None else _d(np.atleast_2d(DUALS))
         X2a = None if X2 is None else _d(np.atleast_2d(X2))
-        t = tols or OaTols(1e-8, 1e-17, 1e-8, 1e19)
+        t = tols or OaTols(1e-8, 1e-17, 1e-8, 1e19, 0)
         self._ck(lib().bnlp_oa_batch(self.h, B, _vp(X), _vp(Du), _vp(XL), _vp(XU), _vp(X2a), float(theta),
                                      int(get_obj), ctypes.byref(t), _vp(row_start), _vp(col), _vp(val), _vp(LB),
                                      _vp(UB), _vp(src)))

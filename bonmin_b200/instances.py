@@ -185,3 +185,105 @@ def mytoy() -> StructuredModel:
         qs_fn=np.array([1, 1], np.int32), qs_i=np.array([0, 1], np.int32),
         qs_j=np.array([0, 1], np.int32), qs_v=np.array([2.0, 2.0]),
         name="mytoy"))
+
+
+# opcodes of include/bnlp.h (BNLP_OP_*)
+OP_CONST, OP_VAR, OP_MUL, OP_EXP = 0, 1, 4, 9
+
+
+def syn_cvx_minlp(n: int, n_bin: int, m_nl: int, m_l: int, seed: int, dense_quadratic: bool = True) -> StructuredModel:
+    """SYN-CVX-MINLP(n, n_bin, m_nl, m_l, seed) of SURVEY.md Appendix B (C4):
+    g_i(x) = sum_{j in S_i} exp(alpha_ij x_j) + 1/2 x'(B_i'B_i)x + a_i'x <= b_i, |S_i| = 10, rank-4 B_i; linear
+    objective; big-M linking rows x_c <= 5 z_b are part of m_l."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    m = m_nl + m_l
+    xl = np.zeros(n)
+    xu = np.where(np.arange(n) < n_bin, 1.0, 5.0)
+    vtype = np.where(np.arange(n) < n_bin, BINARY, CONTINUOUS).astype(np.int32)
+    x0 = np.empty(n)
+    x0[:n_bin] = rng.integers(0, 2, size=n_bin)
+    x0[n_bin:] = rng.uniform(0.5, 2.0, size=n - n_bin)
+    npair = min(n_bin, n - n_bin, m_l)
+    for p in range(npair):          # keep x0 feasible for the linking rows
+        if x0[p] < 0.5:
+            x0[n_bin + p] = 0.0
+    cobj = np.where(np.arange(n) < n_bin, rng.uniform(0, 2, n), rng.uniform(-1, 1, n))
+    A = np.zeros((m + 1, n))
+    c = np.zeros(m + 1)
+    gl = np.full(m, -INF)
+    gu = np.zeros(m)
+    A[0] = cobj
+    qd, qd_fn, terms = [], [], []
+    for i in range(1, m_nl + 1):
+        S = rng.choice(n, 10, replace=False)
+        alpha = rng.uniform(0.1, 0.5, 10)
+        Bi = rng.standard_normal((4, n)) / 2.0
+        Qi = Bi.T @ Bi
+        ai = rng.standard_normal(n)
+        ai[rng.random(n) < 0.9] = 0.0
+        gi = float(np.exp(alpha * x0[S]).sum() + 0.5 * x0 @ Qi @ x0 + ai @ x0)
+        A[i] = ai
+        gu[i - 1] = gi + 0.1 * (1 + abs(gi))
+        qd.append(pack_lower(Qi))
+        qd_fn.append(i)
+        for j, al in zip(S, alpha):
+            terms.append((i, [int(j)], [(OP_CONST, 0, float(al)), (OP_VAR, 0, 0.0), (OP_MUL, 0, 0.0),
+                                          (OP_EXP, 0, 0.0)]))
+    for r in range(m_l):
+        i = m_nl + 1 + r
+        if r < npair:
+            A[i, n_bin + r] = 1.0
+            A[i, r] = -5.0
+            gu[i - 1] = 0.0
+        else:
+            li = rng.standard_normal(n)
+            li[rng.random(n) < 0.9] = 0.0
+            A[i] = li
+            gu[i - 1] = li @ x0 + rng.uniform(0.5, 1.5)
+    return _empty_sparse(StructuredModel(
+        n=n, m=m, xl=xl, xu=xu, gl=gl, gu=gu, vtype=vtype, x0=x0, c=c, A=A,
+        qd_fn=np.array(qd_fn, np.int32), qd=np.array(qd).reshape(len(qd_fn), n * (n + 1) // 2), terms=terms,
+        name=f"SYN-CVX-MINLP(n={n},n_bin={n_bin},m_nl={m_nl},m_l={m_l},seed={seed})"))
+
+
+def config_c4() -> StructuredModel:
+    return syn_cvx_minlp(500, 250, 100, 100, 20261021)
+
+
+def syn_portfolio(N: int, seed: int) -> StructuredModel:
+    """SYN-PORTFOLIO(N, seed) of SURVEY.md Appendix B (C5): variables w (N, [0,1]) then z (N, binary);
+    min -mu'w s.t. w'Sigma w <= sigma2_max, 1'w = 1, w_j <= z_j, 1'z <= 10."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    F = rng.standard_normal((N, 20)) * 0.1
+    d = rng.uniform(0.01, 0.05, N)
+    Sigma = F @ F.T + np.diag(d)
+    mu = rng.uniform(0.02, 0.15, N)
+    top = np.argsort(-mu)[:10]
+    weq = np.zeros(N)
+    weq[top] = 0.1
+    s2 = 1.5 * float(weq @ Sigma @ weq)
+    n, m = 2 * N, N + 3
+    A = np.zeros((m + 1, n))
+    c = np.zeros(m + 1)
+    gl = np.full(m, -INF)
+    gu = np.zeros(m)
+    A[0, :N] = -mu
+    Qfull = np.zeros((n, n))
+    Qfull[:N, :N] = 2.0 * Sigma          # 1/2 x'Qx = w'Sigma w
+    gu[0] = s2
+    A[2, :N] = 1.0
+    gl[1] = gu[1] = 1.0
+    for j in range(N):
+        A[3 + j, j] = 1.0
+        A[3 + j, N + j] = -1.0
+    A[3 + N, N:] = 1.0
+    gu[2 + N] = 10.0
+    x0 = np.concatenate([weq, (weq > 0).astype(float)])
+    return _empty_sparse(StructuredModel(
+        n=n, m=m, xl=np.zeros(n), xu=np.ones(n), gl=gl, gu=gu,
+        vtype=np.concatenate([np.zeros(N, np.int32), np.full(N, BINARY, np.int32)]), x0=x0, c=c, A=A,
+        qd_fn=np.array([1], np.int32), qd=pack_lower(Qfull)[None, :], name=f"SYN-PORTFOLIO(N={N},seed={seed})"))
+
+
+def config_c5() -> StructuredModel:
+    return syn_portfolio(200, 20261022)

@@ -136,6 +136,8 @@ typedef struct bnlp_oa_tols {
   double very_tiny;   /* very_tiny_element 1e-17 (:243-247) */
   double rhs_relax;   /* oa_rhs_relax 1e-8       (:222-228) */
   double infty;       /* 1e19 */
+  int skip_non_violated; /* 0 = reference behaviour at oa log level 0: the x2/theta filter never drops a
+                            constraint cut (BonOsiTMINLPInterface.cpp:2018-2020); 1 = drop cuts violated by < theta */
 } bnlp_oa_tols;
 int bnlp_oa_capacity(const bnlp_engine *, int B, int *rows_per_point, size_t *nnz_capacity);
 int bnlp_oa_batch(bnlp_engine *, int B, const double *X, const double *DUALS, const double *XL, const double *XU,

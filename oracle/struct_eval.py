@@ -1,0 +1,268 @@
+"""CPU oracle (TEST INFRASTRUCTURE ONLY) for model evaluation and outer-approximation cut assembly.
+
+* `Evaluator`  restates what the reference obtains from TMINLP::eval_f/eval_grad_f/eval_g/eval_jac_g/eval_h
+  (src/Interfaces/BonTMINLP.hpp:268-315; for .nl models forwarded to ASL, src/Interfaces/Ampl/BonAmplTMINLP.cpp:629-661)
+  on a StructuredModel, in plain numpy / Python.
+* `outer_approximation` restates OsiTMINLPInterface::getOuterApproximation line by line
+  (src/Interfaces/BonOsiTMINLPInterface.cpp:1924-2107) including cleanNnz (:1881-1919) and its quirks
+  (dead lb relaxation, two infinities, objective cut with hard-coded 1e-15).
+Pinned against the reference's known answers for test/mytoy.nl (test/InterfaceTest.cpp:191-264: OA row
+(2/sqrt5, 1/sqrt5 | 1/2 + 3/(2 sqrt5)))."""
+from __future__ import annotations
+
+import math
+import sys
+
+import numpy as np
+
+DBL_MAX = sys.float_info.max
+
+# opcodes: include/bnlp.h
+(OP_CONST, OP_VAR, OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_NEG, OP_POWC, OP_POW, OP_EXP, OP_LOG, OP_SQRT, OP_SIN, OP_COS,
+ OP_SQR, OP_ABS) = range(16)
+
+
+class _HD:
+    """value / gradient / Hessian triple w.r.t. the local variables of a term (second-order forward mode)."""
+    __slots__ = ("v", "g", "h")
+
+    def __init__(self, v, g, h):
+        self.v, self.g, self.h = v, g, h
+
+    def unary(self, f, f1, f2):
+        return _HD(f, f1 * self.g, f2 * np.outer(self.g, self.g) + f1 * self.h)
+
+
+def _mul(a, b):
+    return _HD(a.v * b.v, a.v * b.g + b.v * a.g, a.v * b.h + b.v * a.h + np.outer(a.g, b.g) + np.outer(b.g, a.g))
+
+
+def eval_term(vars_, prog, x):
+    nv = len(vars_)
+    st = []
+    for op, ia, da in prog:
+        if op == OP_CONST:
+            st.append(_HD(float(da), np.zeros(nv), np.zeros((nv, nv))))
+        elif op == OP_VAR:
+            g = np.zeros(nv)
+            g[ia] = 1.0
+            st.append(_HD(float(x[vars_[ia]]), g, np.zeros((nv, nv))))
+        elif op in (OP_ADD, OP_SUB):
+            b = st.pop()
+            a = st.pop()
+            s = 1.0 if op == OP_ADD else -1.0
+            st.append(_HD(a.v + s * b.v, a.g + s * b.g, a.h + s * b.h))
+        elif op == OP_MUL:
+            b = st.pop()
+            a = st.pop()
+            st.append(_mul(a, b))
+        elif op == OP_DIV:
+            b = st.pop()
+            a = st.pop()
+            r = 1.0 / b.v
+            st.append(_mul(a, b.unary(r, -r * r, 2 * r ** 3)))
+        elif op == OP_POW:
+            b = st.pop()
+            a = st.pop()
+            t = _mul(a.unary(math.log(a.v), 1 / a.v, -1 / a.v ** 2), b)
+            e = math.exp(t.v)
+            st.append(t.unary(e, e, e))
+        else:
+            a = st.pop()
+            v = a.v
+            if op == OP_NEG:
+                st.append(a.unary(-v, -1.0, 0.0))
+            elif op == OP_SQR:
+                st.append(a.unary(v * v, 2 * v, 2.0))
+            elif op == OP_POWC:
+                p = da
+                f1 = 0.0 if p == 0 else p * v ** (p - 1)
+                f2 = 0.0 if p in (0.0, 1.0) else p * (p - 1) * v ** (p - 2)
+                st.append(a.unary(v ** p, f1, f2))
+            elif op == OP_EXP:
+                e = math.exp(v)
+                st.append(a.unary(e, e, e))
+            elif op == OP_LOG:
+                st.append(a.unary(math.log(v), 1 / v, -1 / v ** 2))
+            elif op == OP_SQRT:
+                s = math.sqrt(v)
+                st.append(a.unary(s, 0.5 / s, -0.25 / (s * v)))
+            elif op == OP_SIN:
+                st.append(a.unary(math.sin(v), math.cos(v), -math.sin(v)))
+            elif op == OP_COS:
+                st.append(a.unary(math.cos(v), -math.sin(v), -math.cos(v)))
+            elif op == OP_ABS:
+                st.append(a.unary(abs(v), 1.0 if v >= 0 else -1.0, 0.0))
+            else:
+                raise ValueError(op)
+    assert len(st) == 1
+    return st[0]
+
+
+class Evaluator:
+    """Dense reference evaluation of a StructuredModel at one point."""
+
+    def __init__(self, model):
+        self.m_ = model
+        n, m = model.n, model.m
+        self.Q = {}
+        il = np.tril_indices(n)
+        for k, fn in enumerate(model.qd_fn):
+            Q = np.zeros((n, n))
+            Q[il] = model.qd[k]
+            self.Q[int(fn)] = Q + Q.T - np.diag(np.diag(Q))
+        for fn, i, j, v in zip(model.qs_fn, model.qs_i, model.qs_j, model.qs_v):
+            Q = self.Q.setdefault(int(fn), np.zeros((n, n)))
+            Q[i, j] += v
+            if i != j:
+                Q[j, i] += v
+        self.terms = model.get("terms", [])
+        # sparsity structures exactly as the product derives them (HostModel::finalize)
+        cols = [set(np.flatnonzero(model.A[k]).tolist()) for k in range(m + 1)]
+        hes = set()
+        nonlin = np.zeros(m + 1, bool)
+        for fn in model.qd_fn:
+            cols[fn] |= set(range(n))
+            nonlin[fn] = True
+        if len(model.qd_fn):
+            hes |= {(i, j) for i in range(n) for j in range(i + 1)}
+        for fn, i, j in zip(model.qs_fn, model.qs_i, model.qs_j):
+            cols[fn] |= {int(i), int(j)}
+            hes.add((max(i, j), min(i, j)))
+            nonlin[fn] = True
+        for fn, vars_, _ in self.terms:
+            nonlin[fn] = True
+            cols[fn] |= set(vars_)
+            hes |= {(max(a, b), min(a, b)) for a in vars_ for b in vars_}
+        self.jac = [(i, j) for i in range(m) for j in sorted(cols[i + 1])]
+        self.hes = sorted(hes)
+        self.con_nonlinear = nonlin[1:]
+        self.obj_nonlinear = bool(nonlin[0])
+
+    def dense(self, x, lam=None, sigma=1.0):
+        """values (m+1), dense gradients (m+1, n), dense Lagrangian Hessian (n, n)."""
+        M = self.m_
+        n, m = M.n, M.m
+        x = np.asarray(x, float)
+        vals = M.c + M.A @ x
+        grads = np.array(M.A, float).copy()
+        w = np.zeros(m + 1)
+        w[0] = sigma
+        if lam is not None:
+            w[1:] = lam
+        H = np.zeros((n, n))
+        for fn, Q in self.Q.items():
+            u = Q @ x
+            vals[fn] += 0.5 * x @ u
+            grads[fn] += u
+            H += w[fn] * Q
+        for fn, vars_, prog in self.terms:
+            r = eval_term(vars_, prog, x)
+            vals[fn] += r.v
+            for a, va in enumerate(vars_):
+                grads[fn, va] += r.g[a]
+                for b, vb in enumerate(vars_):
+                    H[va, vb] += w[fn] * r.h[a, b]
+        return vals, grads, H
+
+    def sparse(self, x, lam=None, sigma=1.0):
+        vals, grads, H = self.dense(x, lam, sigma)
+        jv = np.array([grads[i + 1, j] for i, j in self.jac])
+        hv = np.array([H[i, j] for i, j in self.hes])
+        return dict(f=vals[0], g=vals[1:], gradf=grads[0], jac=jv, hess=hv)
+
+
+def clean_nnz(value, colLower, colUpper, rowLower, rowUpper, colsol, lbub, tiny, veryTiny, infty):
+    """BonOsiTMINLPInterface.cpp:1881-1919; lbub = [lb, ub] is updated in place; returns keep flag."""
+    if abs(value) >= tiny:
+        return True
+    if abs(value) < veryTiny:
+        return False
+    colUpBounded = colUpper < infty
+    colLoBounded = colLower > -infty
+    rowNotLoBounded = rowLower <= -infty
+    rowNotUpBounded = rowUpper >= infty
+    pos = value > 0
+    if colUpBounded and pos and rowNotUpBounded:
+        lbub[0] += value * (colsol - colUpper)
+        return False
+    if colUpBounded and not pos and rowNotLoBounded:
+        lbub[1] += value * (colsol - colUpper)
+        return False
+    if colLoBounded and not pos and rowNotUpBounded:
+        lbub[0] += value * (colsol - colLower)
+        return False
+    if colLoBounded and pos and rowNotLoBounded:
+        lbub[1] += value * (colsol - colLower)
+        return False
+    return True
+
+
+def outer_approximation(ev: Evaluator, x, duals=None, xl=None, xu=None, x2=None, theta=0.0, get_obj=0,
+                        tiny=1e-8, very_tiny=1e-17, rhs_relax=1e-8, infty_=1e19, log_level=0):
+    """Returns a list of cuts (src_row, cols, vals, lb, ub); src_row == m is the objective cut.
+    `duals` is the full [zL|zU|lambda] vector or None (then the ranged-row side selection is skipped)."""
+    M = ev.m_
+    n, m = M.n, M.m
+    infty = DBL_MAX                       # getInfinity() = COIN_DBL_MAX (:1256-1260)
+    xl = M.xl if xl is None else xl
+    xu = M.xu if xu is None else xu
+    r = ev.sparse(x)
+    g, jv = r["g"], r["jac"]
+    cuts = []
+    rows = {}
+    for i in range(m):
+        if not ev.con_nonlinear[i]:
+            continue
+        lb = M.gl[i] - g[i] if M.gl[i] > -infty_ else -infty
+        ub = M.gu[i] - g[i] if M.gu[i] < infty_ else infty
+        if duals is not None and M.gl[i] > -infty and M.gu[i] < infty:      # :1968-1974
+            d = duals[2 * n + i]
+            if d >= 0:
+                lb = -infty
+            if d <= 0:
+                ub = infty
+        rows[i] = dict(cols=[], vals=[], lbub=[lb, ub])
+    for (i, j), v in zip(ev.jac, jv):                                         # :1981-1999
+        if i not in rows:
+            continue
+        c = rows[i]
+        if clean_nnz(v, xl[j], xu[j], M.gl[i], M.gu[i], x[j], c["lbub"], tiny, very_tiny, infty_):
+            c["cols"].append(j)
+            c["vals"].append(v)
+            if c["lbub"][0] > -infty:
+                c["lbub"][0] += v * x[j]
+            if c["lbub"][1] < infty:
+                c["lbub"][1] += v * x[j]
+    for i, c in rows.items():
+        lb, ub = c["lbub"]
+        if x2 is not None:                                                    # :2011-2023
+            rhs = float(np.dot(c["vals"], np.asarray(x2)[c["cols"]])) if c["cols"] else 0.0
+            violation = max(0.0, rhs - ub, lb - rhs)
+            if violation < theta and log_level > 0:
+                continue
+        if lb > infty:                                                        # dead code in the reference (:2043)
+            lb -= rhs_relax * max(abs(lb), 1.0)
+        if ub < infty:
+            ub += rhs_relax * max(abs(ub), 1.0)
+        cuts.append((i, list(c["cols"]), list(c["vals"]), lb, ub))
+    if get_obj == 2 or (get_obj and ev.obj_nonlinear):                        # :2053-2105
+        f, obj = r["f"], r["gradf"]
+        lbub = [-f, -f]
+        cols, vals = [], []
+        for i in range(n):
+            if clean_nnz(obj[i], xl[i], xu[i], -infty, 0.0, x[i], lbub, tiny, 1e-15, infty_):
+                cols.append(i)
+                vals.append(obj[i])
+                lbub[0] += obj[i] * x[i]
+                lbub[1] += obj[i] * x[i]
+        cols.append(n)
+        vals.append(-1.0)
+        gen = True
+        if x2 is not None:
+            rhs = float(np.dot(vals, np.asarray(x2)[cols]))
+            if max(0.0, rhs - lbub[1]) < theta:
+                gen = False
+        if gen:
+            cuts.append((m, cols, vals, -DBL_MAX, lbub[1]))
+    return cuts

@@ -1,0 +1,115 @@
+"""GPU suite (-m gpu): batched tape evaluation and OA cut kernels through the C ABI vs the numpy oracle.
+Structure (indices, row counts) must be identical; values within 1e-12 relative."""
+import numpy as np
+import pytest
+
+from bonmin_b200 import instances as I
+from oracle.struct_eval import Evaluator, outer_approximation
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(model):
+    from bonmin_b200.engine import Engine, Problem
+    return Engine(Problem.from_model(model))
+
+
+MODELS = [lambda: I.mytoy(), lambda: I.syn_miqcp(40, 20, 8, 8, 3), lambda: I.syn_cvx_minlp(30, 10, 5, 8, 3),
+          lambda: I.syn_cvx_minlp(120, 40, 20, 25, 5)]
+
+
+@pytest.mark.parametrize("mk", MODELS)
+def test_eval_batch_parity(bnlp_lib, mk):
+    m = mk()
+    ev = Evaluator(m)
+    eng = _engine(m)
+    info = eng.problem.info()
+    assert list(zip(info["jac_irow"], info["jac_jcol"])) == ev.jac
+    assert list(zip(info["hes_irow"], info["hes_jcol"])) == [(int(a), int(b)) for a, b in ev.hes]
+    rng = np.random.default_rng(0)
+    B = 37
+    X = np.clip(m.x0 + rng.normal(0, 0.3, (B, m.n)), np.maximum(m.xl, -20), np.minimum(m.xu, 20))
+    LAM = rng.normal(0, 1, (B, m.m))
+    r = eng.eval_batch(X, LAM, sigma=0.7)
+    for b in range(B):
+        o = ev.sparse(X[b], LAM[b], 0.7)
+        for k in ("f", "g", "gradf", "jac", "hess"):
+            np.testing.assert_allclose(r[k][b], o[k], rtol=1e-12, atol=1e-12 * (1 + np.abs(o[k]).max(initial=0)))
+    # LAM = None means zero multipliers; outputs may be skipped
+    r2 = eng.eval_batch(X, None, sigma=1.0, want=("f", "hess"))
+    o = ev.sparse(X[0], np.zeros(m.m), 1.0)
+    np.testing.assert_allclose(r2["hess"][0], o["hess"], rtol=1e-12, atol=1e-13)
+    assert r2["g"] is None and r2["jac"] is None
+
+
+def _cuts_from_csr(out, b):
+    rpp = out["rows_per_point"]
+    cuts = []
+    for s in range(rpp):
+        o = b * rpp + s
+        if out["src_row"][o] < 0:
+            continue
+        a, e = out["row_start"][o], out["row_start"][o + 1]
+        cuts.append((int(out["src_row"][o]), out["col"][a:e].tolist(), out["val"][a:e], out["lb"][o], out["ub"][o]))
+    return cuts
+
+
+@pytest.mark.parametrize("mk", MODELS)
+@pytest.mark.parametrize("get_obj", [0, 2])
+def test_oa_batch_parity(bnlp_lib, mk, get_obj):
+    m = mk()
+    ev = Evaluator(m)
+    eng = _engine(m)
+    rng = np.random.default_rng(1)
+    B = 19
+    X = np.clip(m.x0 + rng.normal(0, 0.2, (B, m.n)), np.maximum(m.xl, -20), np.minimum(m.xu, 20))
+    X[:, ::7] = np.where(np.isfinite(m.xl[::7]) & (m.xl[::7] > -1e18), m.xl[::7], X[:, ::7])  # some columns at a bound
+    D = rng.normal(0, 1, (B, 2 * m.n + m.m))
+    D[:, 2 * m.n::3] = 0.0
+    out = eng.oa_batch(X, DUALS=D, get_obj=get_obj)
+    for b in range(B):
+        ref = outer_approximation(ev, X[b], duals=D[b], get_obj=get_obj)
+        got = _cuts_from_csr(out, b)
+        assert [c[0] for c in got] == [c[0] for c in ref]
+        for g, r in zip(got, ref):
+            assert g[1] == r[1]                                   # identical structure after cleanNnz
+            np.testing.assert_allclose(g[2], r[2], rtol=1e-12, atol=1e-14)
+            assert g[3] == pytest.approx(r[3], rel=1e-12, abs=1e-12)
+            assert g[4] == pytest.approx(r[4], rel=1e-12, abs=1e-12)
+
+
+def test_oa_mytoy_golden_and_tiny_coefficients(bnlp_lib):
+    sq5 = 5 ** 0.5
+    m = I.mytoy()
+    eng = _engine(m)
+    x = np.array([[.5 + 1 / sq5, .5 + 1 / (2 * sq5), .5 + 1 / sq5, 0.]])
+    d = np.zeros((1, 11))
+    d[0, 8], d[0, 9] = sq5, 1.0
+    out = eng.oa_batch(x, DUALS=d)
+    (row, cols, vals, lb, ub), = _cuts_from_csr(out, 0)
+    assert row == 0 and cols == [0, 1]
+    np.testing.assert_allclose(vals, [2 / sq5, 1 / sq5], rtol=1e-12)       # InterfaceTest.cpp:255-260
+    rhs = .5 + 3 / (2 * sq5)
+    assert ub == pytest.approx(rhs * (1 + 1e-8), rel=1e-12)                 # :230-231 (+ oa_rhs_relax)
+    # a point where 2*y1-1 is "tiny": the coefficient is absorbed into the rhs through the column bound (cleanNnz)
+    ev = Evaluator(m)
+    x = np.array([[0.5 + 2e-9, 0.9, 0.4, 1.0]])
+    out = eng.oa_batch(x, DUALS=d)
+    ref = outer_approximation(ev, x[0], duals=d[0])
+    got = _cuts_from_csr(out, 0)
+    assert got[0][1] == ref[0][1] == [1]
+    assert got[0][4] == pytest.approx(ref[0][4], rel=1e-12)
+
+
+def test_oa_violation_filter_and_no_duals(bnlp_lib):
+    from bonmin_b200.engine import OaTols
+    m = I.syn_cvx_minlp(30, 10, 5, 8, 3)
+    ev = Evaluator(m)
+    eng = _engine(m)
+    X = np.tile(m.x0 + 0.05, (3, 1))
+    X2 = np.tile(np.append(m.x0, 0.0), (3, 1))
+    out = eng.oa_batch(X, X2=X2, theta=1e9, get_obj=2)
+    ref = outer_approximation(ev, X[0], x2=X2[0], theta=1e9, get_obj=2)
+    assert [c[0] for c in _cuts_from_csr(out, 0)] == [c[0] for c in ref]   # constraint cuts kept, objective cut filtered
+    out = eng.oa_batch(X, X2=X2, theta=1e9, get_obj=2, tols=OaTols(1e-8, 1e-17, 1e-8, 1e19, 1))
+    assert _cuts_from_csr(out, 0) == []
