@@ -1,0 +1,137 @@
+"""Independent (pure-Python) AMPL .nl reader used ONLY as a checker for the product's C++ reader
+(bonmin_b200/csrc/bnlp_nl.cpp).  TEST INFRASTRUCTURE ONLY.  Evaluates expression trees directly."""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+INF = 1e19
+_UN = {15: abs, 16: lambda a: -a, 39: math.sqrt, 41: math.sin, 43: math.log, 44: math.exp, 46: math.cos,
+       76: lambda a: a * a}
+_BIN = {0: lambda a, b: a + b, 1: lambda a, b: a - b, 2: lambda a, b: a * b, 3: lambda a, b: a / b,
+        5: lambda a, b: a ** b, 75: lambda a, b: a ** b, 77: lambda a, b: a ** b}
+
+
+class NlModel:
+    def __init__(self, text: str):
+        lines = []
+        for ln in text.splitlines():
+            ln = ln.split("#")[0].strip()
+            if ln:
+                lines.append(ln)
+        self._l, self._p = lines, 0
+        assert self._next()[0] == "g"
+        h = [int(float(t)) for t in self._next().split()]
+        self.n, self.m = h[0], h[1]
+        self._next(); self._next()
+        h5 = [int(t) for t in self._next().split()]
+        self.nlvc, self.nlvo, self.nlvb = h5[:3]
+        self._next()
+        self.nbv, self.niv, self.nlvbi, self.nlvci, self.nlvoi = [int(t) for t in self._next().split()][:5]
+        self._next(); self._next(); self._next()
+        n, m = self.n, self.m
+        self.xl = np.full(n, -INF); self.xu = np.full(n, INF)
+        self.gl = np.full(m, -INF); self.gu = np.full(m, INF)
+        self.x0 = np.zeros(n)
+        self.expr = {k: ("n", 0.0) for k in range(m + 1)}
+        self.lin = np.zeros((m + 1, n))
+        self.sense = 0
+        while self._p < len(self._l):
+            s = self._next()
+            k = s[0]
+            if k == "C":
+                self.expr[int(s[1:]) + 1] = self._expr()
+            elif k == "O":
+                self.sense = int(s[1:].split()[1])
+                self.expr[0] = self._expr()
+            elif k in "rb":
+                for i in range(m if k == "r" else n):
+                    t = self._next().split()
+                    code = int(t[0])
+                    lo, up = -INF, INF
+                    if code == 0:
+                        lo, up = float(t[1]), float(t[2])
+                    elif code == 1:
+                        up = float(t[1])
+                    elif code == 2:
+                        lo = float(t[1])
+                    elif code == 4:
+                        lo = up = float(t[1])
+                    if k == "r":
+                        self.gl[i], self.gu[i] = lo, up
+                    else:
+                        self.xl[i], self.xu[i] = lo, up
+            elif k == "k":
+                for _ in range(int(s[1:])):
+                    self._next()
+            elif k in "JG":
+                idx, cnt = [int(t) for t in s[1:].split()]
+                fn = idx + 1 if k == "J" else 0
+                for _ in range(cnt):
+                    v, a = self._next().split()
+                    self.lin[fn, int(v)] += float(a)
+            elif k == "x":
+                for _ in range(int(s[1:])):
+                    v, a = self._next().split()
+                    self.x0[int(v)] = float(a)
+            else:
+                raise ValueError(s)
+
+    def _next(self):
+        s = self._l[self._p]
+        self._p += 1
+        return s
+
+    def _expr(self):
+        s = self._next()
+        if s[0] == "n":
+            return ("n", float(s[1:]))
+        if s[0] == "v":
+            return ("v", int(s[1:]))
+        op = int(s[1:])
+        if op == 54:
+            return ("sum", [self._expr() for _ in range(int(self._next()))])
+        if op in _UN:
+            return ("u", op, self._expr())
+        if op in _BIN:
+            a = self._expr()
+            return ("b", op, a, self._expr())
+        raise ValueError(f"opcode {op}")
+
+    def _ev(self, e, x):
+        t = e[0]
+        if t == "n":
+            return e[1]
+        if t == "v":
+            return x[e[1]]
+        if t == "sum":
+            return sum(self._ev(k, x) for k in e[1])
+        if t == "u":
+            return _UN[e[1]](self._ev(e[2], x))
+        return _BIN[e[1]](self._ev(e[2], x), self._ev(e[3], x))
+
+    def values(self, x):
+        """[f, g_1..g_m] at x (minimisation form: a maximised objective is negated)."""
+        v = np.array([self._ev(self.expr[k], x) + self.lin[k] @ x for k in range(self.m + 1)])
+        if self.sense == 1:
+            v[0] = -v[0]
+        return v
+
+    def var_types(self):
+        """BonAmplTMINLP.cpp:473-564."""
+        n = self.n
+        vt = np.zeros(n, int)
+        end = self.nlvb - self.nlvbi
+        start, end = end, end + self.nlvbi
+        vt[start:end] = 2
+        start, end = end, max(end, end + self.nlvc - self.nlvci - self.nlvb)
+        start, end = end, end + self.nlvci
+        vt[start:end] = 2
+        start, end = end, max(end, end + self.nlvo - max(self.nlvb, self.nlvc) - self.nlvoi)
+        start, end = end, end + self.nlvoi
+        vt[start:end] = 2
+        start = n - self.nbv - self.niv
+        vt[start:start + self.nbv] = 1
+        vt[start + self.nbv:n] = 2
+        return vt

@@ -1,0 +1,102 @@
+"""The .nl reader/tape compiler of the product (host C++, no GPU needed for structure) against the reference's
+fixture goldens (test/InterfaceTest.cpp:59-121) and against an independent pure-Python reader."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from bonmin_b200 import instances as I, nlwrite
+from oracle.nl_reader import NlModel
+from oracle.struct_eval import Evaluator
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _problem(txt):
+    from bonmin_b200.engine import Problem
+    return Problem.from_nl(txt)
+
+
+def test_mytoy_get_methods(bnlp_lib):
+    # testGetMethods (InterfaceTest.cpp:59-121): n=4, m=3, col bounds [0,inf),[0,inf),[0,1],[0,5], row uppers 1/4,0,2,
+    # types continuous, continuous, binary, integer
+    gold = json.load(open(os.path.join(G, "mytoy_golden.json")))
+    p = _problem(open(os.path.join(G, "mytoy.nl")).read())
+    assert (p.n, p.m, p.nnz_jac, p.nnz_hess) == (gold["n"], gold["m"], gold["nnz_jac"], gold["nnz_hess"])
+    info = p.info()
+    assert list(info["var_type"]) == gold["var_type"]
+    assert list(info["xl"]) == gold["xl"] and list(info["xu"]) == gold["xu"] and list(info["gu"]) == gold["gu"]
+    assert (info["gl"] <= -1e19).all()
+    assert [list(map(int, e)) for e in zip(info["jac_irow"], info["jac_jcol"])] == gold["jac_structure"]
+    assert list(info["con_nonlinear"]) == [1, 0, 0]
+
+
+def test_python_reader_agrees_on_fixture():
+    nm = NlModel(open(os.path.join(G, "mytoy.nl")).read())
+    assert list(nm.var_types()) == [0, 0, 1, 2]
+    ev = Evaluator(I.mytoy())
+    x = np.array([0.3, 0.9, 0.4, 2.0])
+    np.testing.assert_allclose(nm.values(x), ev.dense(x)[0], rtol=1e-14)
+
+
+@pytest.mark.parametrize("name", ["miqcp_n8", "cvx_n10"])
+def test_written_samples_structure(bnlp_lib, name):
+    s = json.load(open(os.path.join(G, "nl_samples.json")))[name]
+    txt = open(os.path.join(G, "nl_samples", name + ".nl")).read()
+    p = _problem(txt)
+    assert (p.n, p.m, p.nnz_jac, p.nnz_hess) == (s["n"], s["m"], s["nnz_jac"], s["nnz_hess"])
+    info = p.info()
+    assert [list(map(int, e)) for e in zip(info["jac_irow"], info["jac_jcol"])] == s["jac"]
+    np.testing.assert_allclose(info["gu"], s["gu"])
+    nm = NlModel(txt)
+    for x, v in zip(s["points"], s["values"]):
+        np.testing.assert_allclose(nm.values(np.array(x)), v, rtol=1e-12, atol=1e-12)
+
+
+def test_writer_roundtrip_and_errors(bnlp_lib):
+    m = I.syn_cvx_minlp(14, 0, 3, 4, 2)
+    p = _problem(nlwrite.write_nl(m))
+    ev = Evaluator(m)
+    assert (p.nnz_jac, p.nnz_hess) == (len(ev.jac), len(ev.hes))
+    from bonmin_b200.engine import BnlpError
+    with pytest.raises(BnlpError):
+        _problem("b3 0 1 0\n")                      # binary .nl
+    with pytest.raises(BnlpError):
+        _problem(open(os.path.join(G, "mytoy.nl")).read().replace("o5", "o38", 1))   # unsupported opcode (tan)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["miqcp_n8", "cvx_n10"])
+def test_nl_eval_matches_python_reader(bnlp_lib, name):
+    from bonmin_b200.engine import Engine
+    s = json.load(open(os.path.join(G, "nl_samples.json")))[name]
+    txt = open(os.path.join(G, "nl_samples", name + ".nl")).read()
+    eng = Engine(_problem(txt))
+    X = np.array(s["points"])
+    r = eng.eval_batch(X, None, 1.0, want=("f", "g"))
+    for b in range(len(X)):
+        np.testing.assert_allclose(np.concatenate([[r["f"][b]], r["g"][b]]), s["values"][b], rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.gpu
+def test_mytoy_nl_solve_goldens(bnlp_lib, oracle_ipm):
+    """Config C1 plumbing: the fixture .nl through reader -> tape -> batched IPM gives the reference's known answers
+    (InterfaceTest.cpp:122-189)."""
+    from bonmin_b200.engine import Engine
+    gold = json.load(open(os.path.join(G, "mytoy_golden.json")))
+    eng = Engine(_problem(open(os.path.join(G, "mytoy.nl")).read()))
+    info = eng.problem.info()
+    XL = np.tile(info["xl"], (3, 1))
+    XU = np.tile(info["xu"], (3, 1))
+    XL[1, 2] = 1.0
+    XU[2, 2] = 0.0
+    r = eng.solve_batch(XL, XU, info["x0"])
+    assert list(r["status"]) == [1, 1, 1]
+    assert r["obj"][0] == pytest.approx(gold["root"]["obj"], rel=gold["root"]["rel_tol"])
+    np.testing.assert_allclose(r["x"][0][:3], gold["root"]["x"], rtol=1e-6)
+    np.testing.assert_allclose(r["duals"][0][8:], gold["root"]["lambda"], atol=1e-6)
+    assert r["x"][1][2] == 1.0 and r["x"][2][2] == 0.0
+    assert r["obj"][2] == pytest.approx(gold["children"]["x<=0"]["obj"], rel=1e-6)
+    o = oracle_ipm.solve_batch(I.mytoy(), XL, XU, info["x0"])
+    np.testing.assert_allclose(r["obj"], o["obj"], rtol=1e-6)
