@@ -1,0 +1,100 @@
+"""ctypes front end of the host B-BB driver (bonmin_b200/host).  `run_engine` is the product path (C++ driver calling
+the CUDA engine directly); `run_callback` runs the same driver with any Python batch solver (tests use the CPU oracle
+to check that both arithmetic providers reach the same MINLP optimum)."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+from . import engine as _e
+
+c_int, c_dbl, c_void = ctypes.c_int, ctypes.c_double, ctypes.c_void_p
+P_int, P_dbl = ctypes.POINTER(c_int), ctypes.POINTER(c_dbl)
+
+
+class BbOptions(ctypes.Structure):
+    _fields_ = [("number_strong_branch", c_int), ("number_before_trust", c_int), ("node_limit", c_int),
+                ("log_level", c_int), ("integer_tolerance", c_dbl), ("cutoff_decr", c_dbl), ("time_limit", c_dbl)]
+
+
+class BbResult(ctypes.Structure):
+    _fields_ = [("status", c_int), ("nodes", c_int), ("nlp_solves", c_int), ("sb_batches", c_int),
+                ("sb_children", c_int), ("served_from_sb_cache", c_int), ("ipm_iterations", ctypes.c_longlong),
+                ("best_obj", c_dbl), ("best_bound", c_dbl), ("seconds", c_dbl)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+CB = ctypes.CFUNCTYPE(c_int, c_void, c_int, P_dbl, P_dbl, P_dbl, P_dbl, P_int, P_int, P_dbl, P_dbl, P_dbl)
+_host = None
+
+
+def host_lib():
+    global _host
+    if _host is None:
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libbnlp_host.so")
+        if not os.path.exists(path):
+            from . import build
+            build.build_host()
+        _host = ctypes.CDLL(path)
+    return _host
+
+
+def _opts(number_strong_branch=0, number_before_trust=0, node_limit=0, time_limit=0.0):
+    return BbOptions(number_strong_branch, number_before_trust, node_limit, 0, 0.0, 0.0, time_limit)
+
+
+def run_engine(eng: "_e.Engine", **kw):
+    res = BbResult()
+    x = np.zeros(eng.n)
+    L = _e.lib()
+    L.bnlp_bb_run_engine.argtypes = [c_void, c_void, ctypes.POINTER(BbOptions), ctypes.POINTER(BbResult), c_void]
+    o = _opts(**kw)
+    rc = L.bnlp_bb_run_engine(eng.h, eng.problem.h, ctypes.byref(o), ctypes.byref(res), x.ctypes.data_as(c_void))
+    if rc:
+        raise _e.BnlpError("bnlp_bb_run_engine failed")
+    d = res.as_dict()
+    d["best_x"] = x
+    return d
+
+
+def run_callback(model, solve_batch, **kw):
+    """solve_batch(XL, XU, x0) -> dict(obj, status, iters, x) with the meaning of Engine.solve_batch."""
+    n, m = model.n, model.m
+
+    def cb(ctx, B, XL, XU, X0, OBJ, ST, IT, X, G, D):
+        xl = np.ctypeslib.as_array(XL, (B, n)).copy()
+        xu = np.ctypeslib.as_array(XU, (B, n)).copy()
+        x0 = np.ctypeslib.as_array(X0, (n,)).copy()
+        r = solve_batch(xl, xu, x0)
+        np.ctypeslib.as_array(OBJ, (B,))[:] = r["obj"]
+        np.ctypeslib.as_array(ST, (B,))[:] = r["status"]
+        np.ctypeslib.as_array(IT, (B,))[:] = r["iters"]
+        if X:
+            np.ctypeslib.as_array(X, (B, n))[:] = r["x"]
+        if G and m:
+            np.ctypeslib.as_array(G, (B, m))[:] = r["g"]
+        if D:
+            np.ctypeslib.as_array(D, (B, 2 * n + m))[:] = r["duals"]
+        return 0
+
+    res = BbResult()
+    x = np.zeros(n)
+    arr = dict(vt=np.ascontiguousarray(model.vtype, np.int32), xl=np.ascontiguousarray(model.xl, float),
+               xu=np.ascontiguousarray(model.xu, float), gl=np.ascontiguousarray(model.gl, float),
+               gu=np.ascontiguousarray(model.gu, float), x0=np.ascontiguousarray(model.x0, float))
+    L = host_lib()
+    L.bnlp_bb_run_cb.argtypes = [c_int, c_int, c_void, c_void, c_void, c_void, c_void, c_void, CB, c_void,
+                                 ctypes.POINTER(BbOptions), ctypes.POINTER(BbResult), c_void]
+    o = _opts(**kw)
+    keep = CB(cb)
+    rc = L.bnlp_bb_run_cb(n, m, *[arr[k].ctypes.data_as(c_void) for k in ("vt", "xl", "xu", "gl", "gu", "x0")], keep,
+                          None, ctypes.byref(o), ctypes.byref(res), x.ctypes.data_as(c_void))
+    if rc:
+        raise RuntimeError("bnlp_bb_run_cb failed")
+    d = res.as_dict()
+    d["best_x"] = x
+    return d

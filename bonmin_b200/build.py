@@ -8,8 +8,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbnlp.so")
-SOURCES = ["bnlp_api.cu", "bnlp_model.cpp", "bnlp_nl.cpp"]
-HEADERS = ["bnlp_internal.h", "bnlp_ipm.cuh", "bnlp_eval.cuh", "bnlp_api_eval.inc", "../../include/bnlp.h"]
+SOURCES = ["bnlp_api.cu", "bnlp_model.cpp", "bnlp_nl.cpp", "../host/B200Solver.cpp", "../host/host_cabi.cpp"]
+HOST_LIB = os.path.join(HERE, "libbnlp_host.so")
+HEADERS = ["../host/B200Solver.hpp", "../host/bonmin_shim.hpp", "bnlp_internal.h", "bnlp_ipm.cuh", "bnlp_eval.cuh", "bnlp_api_eval.inc", "../../include/bnlp.h"]
 
 
 def _stale() -> bool:
@@ -28,12 +29,21 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-shared", "-o", LIB] + srcs
+           "-Xcompiler", "-fPIC", "-shared", "-DBNLP_WITH_ENGINE", "-o", LIB] + srcs
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
     subprocess.check_call(cmd)
+    build_host()
     return LIB
+
+
+def build_host() -> str:
+    """Host-only library (adapters + B-BB driver with a callback solver): needs no CUDA, used by the CPU tests."""
+    host = os.path.join(HERE, "host")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", HOST_LIB,
+                           os.path.join(host, "B200Solver.cpp"), os.path.join(host, "host_cabi.cpp")])
+    return HOST_LIB
 
 
 if __name__ == "__main__":

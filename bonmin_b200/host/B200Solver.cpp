@@ -1,0 +1,303 @@
+#include "B200Solver.hpp"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <queue>
+
+namespace Bonmin {
+
+static double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// Contract of OptimizeTNLP (BonIpoptSolver.cpp:134-176, Filter/BonFilterSolver.cpp:574-645): read sizes, bounds and
+// the start point from the TNLP, solve, and finish by filling x_sol / g_sol / duals_sol / obj_value exactly as
+// TMINLP2TNLP::finalize_solution would (BonTMINLP2TNLP.cpp:474-509).  An engine error maps to TNLPSolver::exception.
+TNLPSolver::ReturnStatus B200Solver::OptimizeTNLP(TMINLP2TNLP &t) {
+  const double t0 = now_s();
+  const int n = t.n, m = t.m;
+  double obj = 0;
+  int st = 0, it = 0;
+  t.x_sol.assign(n, 0.0); t.g_sol.assign(m, 0.0); t.duals_sol.assign(2 * n + m, 0.0);
+  const int rc = solve_(1, t.x_l.data(), t.x_u.data(), t.x_init.data(), &obj, &st, &it, t.x_sol.data(), t.g_sol.data(),
+                        t.duals_sol.data());
+  cpu_time_ = now_s() - t0;
+  iterations_ = it;
+  if (rc != 0) { t.return_status = exception; return exception; }
+  t.obj_value = obj;
+  t.return_status = (ReturnStatus)st;
+  return (ReturnStatus)st;
+}
+
+int B200Solver::OptimizeBatch(const TMINLP2TNLP &p, const std::vector<double> &XL, const std::vector<double> &XU, int B,
+                              std::vector<Child> &out) {
+  const int n = p.n;
+  std::vector<double> OBJ(B), X((size_t)B * n);
+  std::vector<int> ST(B), IT(B);
+  const int rc = solve_(B, XL.data(), XU.data(), p.x_init.data(), OBJ.data(), ST.data(), IT.data(), X.data(), nullptr, nullptr);
+  out.resize(B);
+  for (int b = 0; b < B; ++b) {
+    out[b].obj = OBJ[b];
+    out[b].status = rc ? exception : (ReturnStatus)ST[b];
+    out[b].iters = IT[b];
+    out[b].x.assign(X.begin() + (size_t)b * n, X.begin() + (size_t)(b + 1) * n);
+    total_batch_iterations_ += IT[b];
+  }
+  return rc;
+}
+
+void BatchedStrongBranchingSolver::markHotStart(OsiTMINLPInterface *si) {
+  const int n = si->getNumCols();
+  xl0_.assign(si->getColLower(), si->getColLower() + n);
+  xu0_.assign(si->getColUpper(), si->getColUpper() + n);
+  cache_.clear();
+}
+
+void BatchedStrongBranchingSolver::prefetch(OsiTMINLPInterface *si, const std::vector<int> &cols,
+                                            const std::vector<double> &down_ub, const std::vector<double> &up_lb) {
+  const int n = si->getNumCols(), K = (int)cols.size();
+  std::vector<double> XL((size_t)2 * K * n), XU((size_t)2 * K * n);
+  for (int i = 0; i < K; ++i)
+    for (int w = 0; w < 2; ++w) {
+      double *l = &XL[((size_t)2 * i + w) * n], *u = &XU[((size_t)2 * i + w) * n];
+      std::copy(xl0_.begin(), xl0_.end(), l);
+      std::copy(xu0_.begin(), xu0_.end(), u);
+      if (w == 0) u[cols[i]] = down_ub[i]; else l[cols[i]] = up_lb[i];
+    }
+  std::vector<B200Solver::Child> res;
+  app_->OptimizeBatch(*si->problem(), XL, XU, 2 * K, res);
+  for (int i = 0; i < K; ++i)
+    for (int w = 0; w < 2; ++w) cache_[{cols[i], w}] = std::move(res[2 * i + w]);
+}
+
+const B200Solver::Child *BatchedStrongBranchingSolver::lookup(int col, bool up) const {
+  auto it = cache_.find({col, up ? 1 : 0});
+  return it == cache_.end() ? nullptr : &it->second;
+}
+
+// solveFromHotStart must leave the child's objective in problem()->set_obj_value and, if optimal, the point in
+// Set_x_sol, because HotInfo::updateInformation reads getObjValue()/isProvenOptimal() right after
+// (BonChooseVariable.cpp:1131-1142; cf. BonLpBranchingSolver.cpp:181-182).
+TNLPSolver::ReturnStatus BatchedStrongBranchingSolver::solveFromHotStart(OsiTMINLPInterface *si) {
+  const int n = si->getNumCols();
+  const double *l = si->getColLower(), *u = si->getColUpper();
+  int col = -1, way = 0, ndiff = 0;
+  for (int j = 0; j < n; ++j) {
+    if (u[j] != xu0_[j]) { col = j; way = 0; ndiff++; }
+    if (l[j] != xl0_[j]) { col = j; way = 1; ndiff++; }
+  }
+  const B200Solver::Child *c = (ndiff == 1) ? lookup(col, way == 1) : nullptr;
+  if (!c) {  // not a prefetched child: solve it on the spot (batch of one) — same answer, just not amortised
+    misses_++;
+    return si->solver()->OptimizeTNLP(*si->problem());
+  }
+  hits_++;
+  si->problem()->set_obj_value(c->obj);
+  if (c->status == TNLPSolver::solvedOptimal || c->status == TNLPSolver::solvedOptimalTol) si->problem()->Set_x_sol(n, c->x.data());
+  si->problem()->return_status = c->status;
+  return c->status;
+}
+
+void BatchedStrongBranchingSolver::unmarkHotStart(OsiTMINLPInterface *) {}
+
+int BatchedChooseVariable::doStrongBranching(const std::vector<int> &cols, double parent_obj,
+                                             std::vector<StrongResult> &results) {
+  const int K = (int)cols.size();
+  std::vector<double> xsol(si_->getColSolution(), si_->getColSolution() + si_->getNumCols());
+  std::vector<double> dn(K), up(K);
+  for (int i = 0; i < K; ++i) { dn[i] = std::floor(xsol[cols[i]]); up[i] = std::ceil(xsol[cols[i]]); }
+  si_->markHotStart();                                   // :799
+  sb_->prefetch(si_, cols, dn, up);                      // ONE batch of 2K children (Appendix C)
+  results.assign(K, StrongResult());
+  int returnCode = 0;
+  for (int iDo = 0; iDo < K; ++iDo) {                    // :807-948, unchanged control flow
+    StrongResult &r = results[iDo];
+    r.col = cols[iDo]; r.value = xsol[cols[iDo]];
+    for (int w = 0; w < 2; ++w) {
+      const double saveL = si_->getColLower()[r.col], saveU = si_->getColUpper()[r.col];
+      if (w == 0) si_->setColUpper(r.col, dn[iDo]); else si_->setColLower(r.col, up[iDo]);   // branch->branch(solver) :820
+      si_->solveFromHotStart();                          // :822
+      // HotInfo::updateInformation (:1118-1145) + OsiHotInfo: 0 feasible, 1 infeasible, 2 not finished
+      int status;
+      const double obj = si_->getObjValue();
+      if (si_->isProvenOptimal()) status = 0;
+      else if (si_->isProvenPrimalInfeasible()) status = (std::fabs(obj) < 1e-6) ? 2 : 1;
+      else status = 2;
+      r.status[w] = status;
+      r.obj[w] = obj;
+      r.change[w] = (status == 0) ? std::max(0.0, obj - parent_obj) : 0.0;
+      si_->setColLower(r.col, saveL); si_->setColUpper(r.col, saveU);   // restore bounds :853-858
+    }
+    if (r.status[0] == 1 && r.status[1] == 1) returnCode = -1;          // :916-919 (the loop continues)
+  }
+  si_->unmarkHotStart();                                 // :955
+  return returnCode;
+}
+
+int BatchedChooseVariable::choose(const std::vector<StrongResult> &results, double parent_obj, double cutoff,
+                                  bool have_solution, int depth, int &bestWhichWay,
+                                  std::vector<std::pair<int, int>> &fixings) const {
+  const double MAXMIN = (have_solution && depth > 10) ? maxmin_crit_have_sol : maxmin_crit_no_sol;   // :965-977
+  double bestTrusted = -1e300;
+  int best = -1;
+  fixings.clear();
+  for (size_t i = 0; i < results.size(); ++i) {
+    const StrongResult &r = results[i];
+    double est[2];
+    for (int w = 0; w < 2; ++w) {
+      if (r.status[w] != 1) est[w] = r.change[w];
+      else {  // infeasible - just say expensive (:692-697, :716-721), and fix the variable the other way
+        est[w] = (cutoff < 1e50) ? 2.0 * (cutoff - parent_obj) : 2.0 * std::fabs(parent_obj);
+        fixings.push_back({r.col, w});
+      }
+    }
+    const double value = MAXMIN * std::min(est[1], est[0]) + (1.0 - MAXMIN) * std::max(est[1], est[0]);
+    if (value > bestTrusted) { bestTrusted = value; best = (int)i; bestWhichWay = est[1] > est[0] ? 0 : 1; }
+  }
+  return best;
+}
+
+// ------------------------------------------------------------------------------------------------ host B-BB driver
+namespace {
+struct Node {
+  std::vector<double> xl, xu;
+  double bound;      // parent objective (lower bound)
+  int depth;
+  // result pre-solved by strong branching (served from the SB cache instead of re-solving: SURVEY Appendix C note 2)
+  bool solved = false;
+  double obj = 0;
+  int status = 0;
+  std::vector<double> x;
+};
+struct Cmp { bool operator()(const Node *a, const Node *b) const { return a->bound > b->bound; } };
+}  // namespace
+
+BbResult bb_run(TMINLP2TNLP &root, BatchSolveFn solve, const BbOptions &opt) {
+  BbResult R;
+  const double t0 = now_s();
+  const int n = root.n;
+  B200Solver app(solve);
+  OsiTMINLPInterface si(&root, &app);
+  BatchedStrongBranchingSolver sb(&app);
+  si.SetStrongBrachingSolver(&sb);
+  BatchedChooseVariable chooser(&si, &sb);
+  chooser.integer_tolerance = opt.integer_tolerance;
+  std::vector<int> ints;
+  for (int j = 0; j < n; ++j) if (root.var_types[j] != 0) ints.push_back(j);
+  std::vector<double> pc_sum[2], pc_cnt[2];   // pseudo-costs per column and direction
+  for (int w = 0; w < 2; ++w) { pc_sum[w].assign(n, 0.0); pc_cnt[w].assign(n, 0.0); }
+
+  // root relaxation (Bab::branchAndBound: model_.initialSolve, then the root primal becomes the start point of every
+  // later NLP: src/CbcBonmin/BonCbc.cpp:452,492-505)
+  si.initialSolve();
+  R.nlp_solves++;
+  if (!si.isProvenOptimal()) { R.status = si.isProvenPrimalInfeasible() ? 1 : 2; R.seconds = now_s() - t0; return R; }
+  root.setxInit(n, root.x_sol.data());
+  std::priority_queue<Node *, std::vector<Node *>, Cmp> heap;
+  Node *first = new Node{root.x_l, root.x_u, root.obj_value, 0};
+  first->solved = true; first->obj = root.obj_value; first->status = (int)root.return_status; first->x = root.x_sol;
+  Node *dive = first;   // node processed next without going through the heap (depth-first plunge on the better child)
+  double cutoff = 1e100;
+  const std::vector<double> xl_root = root.x_l, xu_root = root.x_u;
+
+  while (dive || !heap.empty()) {
+    Node *nd = dive;
+    dive = nullptr;
+    if (!nd) { nd = heap.top(); heap.pop(); }
+    if (nd->bound >= cutoff) { delete nd; continue; }
+    if (R.nodes >= opt.node_limit || now_s() - t0 > opt.time_limit) { R.status = 2; delete nd; break; }
+    R.nodes++;
+    root.x_l = nd->xl; root.x_u = nd->xu;
+    if (nd->solved) {
+      R.served_from_sb_cache += (nd != first);
+      root.obj_value = nd->obj; root.x_sol = nd->x; root.return_status = (TNLPSolver::ReturnStatus)nd->status;
+      si.optimizationStatus_ = (TNLPSolver::ReturnStatus)nd->status;
+    } else {
+      si.resolve();
+      R.nlp_solves++;
+    }
+    if (!si.isProvenOptimal()) { delete nd; continue; }           // infeasible or failed node: fathom
+    const double obj = root.obj_value;
+    if (obj >= cutoff) { delete nd; continue; }
+    const std::vector<double> x = root.x_sol;
+    // integer infeasibilities
+    std::vector<std::pair<double, int>> frac;
+    for (int j : ints) {
+      const double f = std::fabs(x[j] - std::round(x[j]));
+      if (f > opt.integer_tolerance) frac.push_back({-f, j});
+    }
+    if (frac.empty()) {   // new incumbent; Cbc's cutoff = incumbent - cutoff_decr
+      if (obj < R.best_obj) { R.best_obj = obj; R.best_x = x; cutoff = obj - opt.cutoff_decr; }
+      delete nd;
+      continue;
+    }
+    std::sort(frac.begin(), frac.end());   // most fractional first (setupList's second list, :357-360)
+    // candidates needing strong branching: untrusted pseudo-costs (:633-643), at most number_strong_branch
+    std::vector<int> cand;
+    for (auto &f : frac) {
+      const int j = f.second;
+      if ((int)cand.size() >= opt.number_strong_branch) break;
+      if (std::min(pc_cnt[0][j], pc_cnt[1][j]) < opt.number_before_trust) cand.push_back(j);
+    }
+    int bcol = -1, bway = 0;
+    std::vector<StrongResult> res;
+    if (!cand.empty()) {
+      const int rc = chooser.doStrongBranching(cand, obj, res);
+      R.sb_batches++; R.sb_children += 2 * (int)cand.size();
+      if (rc == -1) { delete nd; continue; }                       // both ways infeasible: node infeasible
+      std::vector<std::pair<int, int>> fix;
+      const int bi = chooser.choose(res, obj, cutoff, R.best_obj < 1e99, nd->depth, bway, fix);
+      for (auto &r : res)                                           // pseudo-cost update from SB (:994-1026)
+        for (int w = 0; w < 2; ++w)
+          if (r.status[w] == 0) {
+            const double dist = (w == 0) ? r.value - std::floor(r.value) : std::ceil(r.value) - r.value;
+            if (dist > 1e-6) { pc_sum[w][r.col] += r.change[w] / dist; pc_cnt[w][r.col] += 1.0; }
+          }
+      for (auto &f : fix) {   // a side proven infeasible fixes the variable to the other side (:698-704, 722-728)
+        const double v = x[f.first];
+        if (f.second == 0) nd->xl[f.first] = std::max(nd->xl[f.first], std::ceil(v));
+        else nd->xu[f.first] = std::min(nd->xu[f.first], std::floor(v));
+      }
+      if (bi >= 0) bcol = res[bi].col;
+    }
+    if (bcol < 0) {   // all candidates trusted: pseudo-cost score with the same max-min rule
+      double best = -1e300;
+      const double MAXMIN = (R.best_obj < 1e99 && nd->depth > 10) ? chooser.maxmin_crit_have_sol : chooser.maxmin_crit_no_sol;
+      for (auto &f : frac) {
+        const int j = f.second;
+        const double dn = (pc_cnt[0][j] > 0 ? pc_sum[0][j] / pc_cnt[0][j] : 1.0) * (x[j] - std::floor(x[j]));
+        const double up = (pc_cnt[1][j] > 0 ? pc_sum[1][j] / pc_cnt[1][j] : 1.0) * (std::ceil(x[j]) - x[j]);
+        const double v = MAXMIN * std::min(dn, up) + (1 - MAXMIN) * std::max(dn, up);
+        if (v > best) { best = v; bcol = j; bway = up > dn ? 0 : 1; }
+      }
+    }
+    // two children; results of the strong-branching solves are reused when the bounds are exactly those that were solved
+    Node *ch[2];
+    for (int w = 0; w < 2; ++w) {
+      ch[w] = new Node{nd->xl, nd->xu, obj, nd->depth + 1};
+      if (w == 0) ch[w]->xu[bcol] = std::floor(x[bcol]); else ch[w]->xl[bcol] = std::ceil(x[bcol]);
+      const B200Solver::Child *c = nullptr;
+      bool same = true;   // fixings applied after SB change the bounds: then the cached result is no longer this child
+      for (int j = 0; j < n && same; ++j)
+        if (j != bcol && (nd->xl[j] != root.x_l[j] || nd->xu[j] != root.x_u[j])) same = false;
+      if (same && !res.empty()) c = sb.lookup(bcol, w == 1);
+      if (c) { ch[w]->solved = true; ch[w]->obj = c->obj; ch[w]->status = (int)c->status; ch[w]->x = c->x;
+               if (c->status == 1 || c->status == 2) ch[w]->bound = std::max(obj, c->obj); }
+    }
+    // follow the preferred way first, keep the other on the heap (probed-dive flavour, BonDiver.cpp:255-316)
+    dive = ch[bway];
+    heap.push(ch[1 - bway]);
+    delete nd;
+  }
+  while (!heap.empty()) { R.best_bound = std::min(R.best_bound < -1e99 ? 1e100 : R.best_bound, heap.top()->bound); delete heap.top(); heap.pop(); }
+  if (dive) delete dive;
+  if (R.status == 0) { R.status = R.best_obj < 1e99 ? 0 : 1; R.best_bound = R.best_obj; }
+  R.ipm_iterations = si.totalIterations() + app.totalBatchIterations();
+  R.seconds = now_s() - t0;
+  root.x_l = xl_root; root.x_u = xu_root;
+  return R;
+}
+
+}  // namespace Bonmin

@@ -1,0 +1,113 @@
+// Host adapters that put the batched engine behind Bonmin's own plugin interfaces.
+//   B200Solver                     : TNLPSolver            (replaces IpoptSolver, src/Interfaces/Ipopt/BonIpoptSolver.cpp)
+//   BatchedStrongBranchingSolver   : StrongBranchingSolver (new value of `variable_selection`, BonBonminSetup.cpp:434-469)
+//   BatchedChooseVariable          : the doStrongBranching override of SURVEY.md Appendix C
+//                                    (src/Algorithms/Branching/BonChooseVariable.cpp:787-957 replayed against a prefetch)
+//   bb_run                         : a small host B-BB driver (Cbc is not available here) restating Bonmin's B-BB
+//                                    node loop closely enough to report "B-BB wall time to optimum" (SURVEY.md §7 step 2).
+// The arithmetic provider is abstracted as a batch-solve callback so the same host logic runs on the CUDA engine
+// (bnlp_solve_batch) in the product and on the CPU oracle in tests — the adapters never compute anything themselves.
+#pragma once
+#include <functional>
+#include <map>
+#include <utility>
+
+#include "bonmin_shim.hpp"
+
+namespace Bonmin {
+
+// B x OptimizeTNLP: same argument meaning as bnlp_solve_batch (include/bnlp.h)
+using BatchSolveFn = std::function<int(int B, const double *XL, const double *XU, const double *X0, double *OBJ,
+                                       int *STATUS, int *ITERS, double *X, double *G, double *DUALS)>;
+
+class B200Solver : public TNLPSolver {
+ public:
+  explicit B200Solver(BatchSolveFn fn) : solve_(std::move(fn)) {}
+  TNLPSolver *clone() override { return new B200Solver(solve_); }
+  ReturnStatus OptimizeTNLP(TMINLP2TNLP &tnlp) override;
+  ReturnStatus ReOptimizeTNLP(TMINLP2TNLP &tnlp) override { return OptimizeTNLP(tnlp); }
+  double CPUTime() override { return cpu_time_; }
+  int IterationCount() override { return iterations_; }
+  const std::string &solverName() const override { return name_; }
+  // the batched sibling: children differ only in bounds; results in TMINLP2TNLP layout
+  struct Child { double obj; ReturnStatus status; int iters; std::vector<double> x; };
+  int OptimizeBatch(const TMINLP2TNLP &parent, const std::vector<double> &XL, const std::vector<double> &XU, int B,
+                    std::vector<Child> &out);
+  long totalBatchIterations() const { return total_batch_iterations_; }
+
+ private:
+  BatchSolveFn solve_;
+  std::string name_ = "B200 batched IPM";
+  double cpu_time_ = 0;
+  int iterations_ = 0;
+  long total_batch_iterations_ = 0;
+};
+
+// Strong-branching plugin: prefetch() solves all 2K children of a node as ONE batch; solveFromHotStart() then serves
+// the child selected by diffing the interface's current bounds against the hot-start snapshot.
+class BatchedStrongBranchingSolver : public StrongBranchingSolver {
+ public:
+  explicit BatchedStrongBranchingSolver(B200Solver *app) : app_(app) {}
+  void markHotStart(OsiTMINLPInterface *si) override;
+  TNLPSolver::ReturnStatus solveFromHotStart(OsiTMINLPInterface *si) override;
+  void unmarkHotStart(OsiTMINLPInterface *si) override;
+  // candidates: (column, down bound = floor(x), up bound = ceil(x)); called between markHotStart and the replay loop
+  void prefetch(OsiTMINLPInterface *si, const std::vector<int> &cols, const std::vector<double> &down_ub,
+                const std::vector<double> &up_lb);
+  int cacheHits() const { return hits_; }
+  int cacheMisses() const { return misses_; }
+  const B200Solver::Child *lookup(int col, bool up) const;
+
+ private:
+  B200Solver *app_;
+  std::vector<double> xl0_, xu0_;
+  std::map<std::pair<int, int>, B200Solver::Child> cache_;   // (column, way) -> result
+  int hits_ = 0, misses_ = 0;
+};
+
+struct StrongResult {  // what HotInfo holds per candidate (BonChooseVariable.hpp:109-113: -1 not done, 0 feasible, 1 infeasible, 2 not finished)
+  int col;
+  double value;
+  int status[2];     // [down, up]
+  double change[2];
+  double obj[2];
+};
+
+class BatchedChooseVariable {
+ public:
+  BatchedChooseVariable(OsiTMINLPInterface *si, BatchedStrongBranchingSolver *sb) : si_(si), sb_(sb) {}
+  double maxmin_crit_no_sol = 0.7, maxmin_crit_have_sol = 0.1;   // BonChooseVariable.cpp:170-175
+  double integer_tolerance = 1e-6;                               // BonBabSetupBase.cpp:478-482
+  // doStrongBranching (BonChooseVariable.cpp:787-957): one prefetch, then the reference's sequential loop replayed
+  // against it.  Returns -1 if some candidate is infeasible both ways (node infeasible), else 0.
+  int doStrongBranching(const std::vector<int> &cols, double parent_obj, std::vector<StrongResult> &results);
+  // scoring of chooseVariable (BonChooseVariable.cpp:682-747); returns the index into results (or -1) and the way
+  int choose(const std::vector<StrongResult> &results, double parent_obj, double cutoff, bool have_solution, int depth,
+             int &bestWhichWay, std::vector<std::pair<int, int>> &fixings) const;
+
+ private:
+  OsiTMINLPInterface *si_;
+  BatchedStrongBranchingSolver *sb_;
+};
+
+struct BbOptions {
+  int number_strong_branch = 20;        // BonBabSetupBase.cpp:547-550
+  int number_before_trust = 8;          // :554-559
+  double integer_tolerance = 1e-6;      // :478-482
+  double cutoff_decr = 1e-5;            // :507-513
+  double allowable_gap = 0.0, allowable_fraction_gap = 0.0;   // :484-497
+  int node_limit = 1000000;
+  double time_limit = 1e10;
+  int log_level = 0;
+};
+struct BbResult {
+  int status = 0;               // 0 optimal, 1 infeasible, 2 node/time limit
+  double best_obj = 1e100, best_bound = -1e100;
+  std::vector<double> best_x;
+  int nodes = 0, nlp_solves = 0, sb_batches = 0, sb_children = 0, served_from_sb_cache = 0;
+  long ipm_iterations = 0;
+  double seconds = 0;
+};
+BbResult bb_run(TMINLP2TNLP &root, BatchSolveFn solve, const BbOptions &opt);
+
+}  // namespace Bonmin

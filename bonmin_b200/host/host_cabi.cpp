@@ -1,0 +1,59 @@
+// C entry points of the host layer (used by bench.py, tests and the `bnlp_bb` command): the B-BB driver with a
+// batch-solve callback.  In the product the callback is bnlp_solve_batch on a CUDA engine (bnlp_bb_run_engine in
+// bnlp_api.cu); tests may pass the CPU oracle to check that both give the same MINLP optimum.
+#include <cstring>
+
+#include "../../include/bnlp.h"
+#include "B200Solver.hpp"
+
+extern "C" {
+
+int bnlp_bb_run_cb(int n, int m, const int *var_type, const double *xl, const double *xu, const double *gl,
+                   const double *gu, const double *x0, bnlp_batch_solve_cb cb, void *ctx, const bnlp_bb_options *o,
+                   bnlp_bb_result *res, double *best_x) {
+  using namespace Bonmin;
+  TMINLP2TNLP root;
+  root.n = n; root.m = m;
+  root.var_types.assign(var_type, var_type + n);
+  root.x_l.assign(xl, xl + n); root.x_u.assign(xu, xu + n);
+  root.g_l.assign(gl, gl + m); root.g_u.assign(gu, gu + m);
+  root.x_init.assign(x0, x0 + n);
+  BbOptions opt;
+  if (o) {
+    if (o->number_strong_branch > 0) opt.number_strong_branch = o->number_strong_branch;
+    if (o->number_before_trust > 0) opt.number_before_trust = o->number_before_trust;
+    if (o->node_limit > 0) opt.node_limit = o->node_limit;
+    if (o->integer_tolerance > 0) opt.integer_tolerance = o->integer_tolerance;
+    if (o->cutoff_decr > 0) opt.cutoff_decr = o->cutoff_decr;
+    if (o->time_limit > 0) opt.time_limit = o->time_limit;
+    opt.log_level = o->log_level;
+  }
+  BatchSolveFn fn = [cb, ctx](int B, const double *XL, const double *XU, const double *X0, double *OBJ, int *ST, int *IT,
+                              double *X, double *G, double *D) { return cb(ctx, B, XL, XU, X0, OBJ, ST, IT, X, G, D); };
+  BbResult r = bb_run(root, fn, opt);
+  res->status = r.status; res->nodes = r.nodes; res->nlp_solves = r.nlp_solves; res->sb_batches = r.sb_batches;
+  res->sb_children = r.sb_children; res->served_from_sb_cache = r.served_from_sb_cache;
+  res->ipm_iterations = r.ipm_iterations; res->best_obj = r.best_obj; res->best_bound = r.best_bound; res->seconds = r.seconds;
+  if (best_x && !r.best_x.empty()) memcpy(best_x, r.best_x.data(), sizeof(double) * n);
+  return 0;
+}
+
+#ifdef BNLP_WITH_ENGINE
+// Product path: the same driver with the CUDA engine as arithmetic provider (no Python in between).
+int bnlp_bb_run_engine(bnlp_engine *E, const bnlp_problem *P, const bnlp_bb_options *o, bnlp_bb_result *res,
+                       double *best_x) {
+  int n = 0, m = 0;
+  if (!E || !P || bnlp_problem_sizes(P, &n, &m, nullptr, nullptr)) return -1;
+  std::vector<int> vt(n);
+  std::vector<double> xl(n), xu(n), gl(m), gu(m), x0(n);
+  bnlp_problem_info(P, nullptr, nullptr, nullptr, nullptr, vt.data(), nullptr, xl.data(), xu.data(), gl.data(), gu.data(),
+                    x0.data());
+  auto cb = [](void *ctx, int B, const double *XL, const double *XU, const double *X0, double *OBJ, int *ST, int *IT,
+               double *X, double *G, double *D) {
+    return bnlp_solve_batch((bnlp_engine *)ctx, B, XL, XU, X0, 0, OBJ, ST, IT, X, G, D);
+  };
+  return bnlp_bb_run_cb(n, m, vt.data(), xl.data(), xu.data(), gl.data(), gu.data(), x0.data(), cb, E, o, res, best_x);
+}
+#endif
+
+}  // extern "C"

@@ -152,6 +152,32 @@ long long bnlp_engine_launches(const bnlp_engine *);
 /* measured FP64 FMA peak of device dev_index in TFLOP/s (micro-kernel; roofline denominator) */
 double bnlp_measure_fp64_peak(bnlp_engine *, int dev_index);
 
+/* --- host B-BB driver (host control flow, NOT accelerated; Cbc is not part of this engine) --------------------
+ * Restates the node loop that Bab::branchAndBound + BonChooseVariable run for algorithm B-BB
+ * (src/CbcBonmin/BonCbc.cpp:104-690, src/Algorithms/Branching/BonChooseVariable.cpp:599-957): NLP relaxation per node,
+ * strong branching with all 2K children of a node solved as ONE batch and the reference's sequential loop replayed
+ * against the cached results, max-min scoring, pseudo-costs, best-bound + plunge.  Option names/defaults:
+ * src/Algorithms/BonBabSetupBase.cpp:478-559.  0 in an option field means "reference default". */
+typedef int (*bnlp_batch_solve_cb)(void *ctx, int B, const double *XL, const double *XU, const double *X0, double *OBJ,
+                                   int *STATUS, int *ITERS, double *X, double *G, double *DUALS);
+typedef struct bnlp_bb_options {
+  int number_strong_branch, number_before_trust, node_limit, log_level;
+  double integer_tolerance, cutoff_decr, time_limit;
+} bnlp_bb_options;
+typedef struct bnlp_bb_result {
+  int status;                 /* 0 optimal, 1 infeasible, 2 limit reached */
+  int nodes, nlp_solves, sb_batches, sb_children, served_from_sb_cache;
+  long long ipm_iterations;
+  double best_obj, best_bound, seconds;
+} bnlp_bb_result;
+/* arithmetic provider = any batch solver with bnlp_solve_batch's meaning (tests pass the CPU oracle here) */
+int bnlp_bb_run_cb(int n, int m, const int *var_type, const double *xl, const double *xu, const double *gl,
+                   const double *gu, const double *x0, bnlp_batch_solve_cb cb, void *ctx, const bnlp_bb_options *o,
+                   bnlp_bb_result *res, double *best_x);
+/* arithmetic provider = the CUDA engine */
+int bnlp_bb_run_engine(bnlp_engine *, const bnlp_problem *, const bnlp_bb_options *o, bnlp_bb_result *res,
+                       double *best_x);
+
 #ifdef __cplusplus
 }
 #endif

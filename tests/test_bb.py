@@ -1,0 +1,64 @@
+"""Host B-BB driver (bonmin_b200/host): strong branching with batched children behind Bonmin's plugin interfaces.
+CPU tests run the driver with the CPU oracle as arithmetic provider; the GPU test checks that the CUDA engine behind
+the same driver reaches the same MINLP optimum (north_star: same final optimum within 1e-6)."""
+import numpy as np
+import pytest
+
+from bonmin_b200 import bb, instances as I
+
+
+def _oracle_solver(model, oracle_ipm):
+    dense = oracle_ipm.dense_arrays(model)
+    return lambda XL, XU, x0: oracle_ipm.solve_batch(model, XL, XU, x0, threads=4, dense=dense)
+
+
+def test_bb_mytoy_optimum(oracle_ipm):
+    # config C1: B-BB on the toy; true optimum -2.5 at x=1, y=(1,1/2), z=0 (not asserted by the reference)
+    m = I.mytoy()
+    r = bb.run_callback(m, _oracle_solver(m, oracle_ipm))
+    assert r["status"] == 0
+    assert r["best_obj"] == pytest.approx(-2.5, abs=5e-4)        # the 1e-8 bound relaxation moves it by O(1e-4)
+    assert r["best_x"][2] == pytest.approx(1.0, abs=1e-6) and r["best_x"][3] == pytest.approx(0.0, abs=1e-6)
+    assert r["sb_children"] > 0 and r["nodes"] >= 1
+
+
+def test_bb_strong_branching_settings_agree(oracle_ipm):
+    m = I.syn_miqcp(12, 6, 3, 3, 4)
+    s = _oracle_solver(m, oracle_ipm)
+    a = bb.run_callback(m, s, number_strong_branch=6)
+    b = bb.run_callback(m, s, number_strong_branch=2, number_before_trust=1)
+    assert a["status"] == b["status"] == 0
+    assert a["best_obj"] == pytest.approx(b["best_obj"], rel=1e-6)
+    xi = a["best_x"][:6]
+    assert np.abs(xi - np.round(xi)).max() <= 1e-6
+    # every child of a strong-branched node that is later explored is served from the batch (Appendix C note 2)
+    assert a["served_from_sb_cache"] > 0 and a["nlp_solves"] < a["nodes"]
+
+
+def test_bb_optimum_is_a_valid_lower_bound_of_enumeration(oracle_ipm):
+    """Tiny instance: enumerate all integer assignments of 3 integer variables in [0,10] and solve the continuous
+    NLP for each with the oracle; the B-BB optimum must equal the best of them."""
+    m = I.syn_miqcp(6, 3, 2, 2, 8)
+    s = _oracle_solver(m, oracle_ipm)
+    r = bb.run_callback(m, s, number_strong_branch=3)
+    pts = np.array([(a, b, c) for a in range(11) for b in range(11) for c in range(11)], float)
+    XL = np.tile(m.xl, (len(pts), 1))
+    XU = np.tile(m.xu, (len(pts), 1))
+    XL[:, :3] = pts
+    XU[:, :3] = pts
+    o = s(XL, XU, m.x0)
+    best = o["obj"][o["status"] == 1].min()
+    assert r["best_obj"] == pytest.approx(best, rel=1e-6)
+
+
+@pytest.mark.gpu
+def test_bb_engine_matches_oracle(bnlp_lib, oracle_ipm):
+    from bonmin_b200.engine import Engine, Problem
+    for m, kw in [(I.mytoy(), {}), (I.syn_miqcp(20, 10, 4, 4, 9), dict(number_strong_branch=10)),
+                  (I.syn_miqcp(40, 20, 8, 8, 3), dict(number_strong_branch=16, node_limit=400))]:
+        eng = Engine(Problem.from_model(m))
+        g = bb.run_engine(eng, **kw)
+        c = bb.run_callback(m, _oracle_solver(m, oracle_ipm), **kw)
+        assert g["status"] == c["status"]
+        assert g["best_obj"] == pytest.approx(c["best_obj"], rel=1e-6)
+        assert g["nodes"] == c["nodes"] and g["sb_children"] == c["sb_children"]
