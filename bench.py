@@ -91,6 +91,14 @@ def make_children(model, xs, B, first):
     return I.c3_children(model, xs, B, first=first)
 
 
+def _all_gather(t, world):
+    import torch
+    import torch.distributed as dist
+    out = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(out, t)
+    return out
+
+
 def cpu_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -239,10 +247,12 @@ def main():
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-        gathered = [torch.zeros_like(dOBJ) for _ in range(world)]
-        dist.all_gather(gathered, dOBJ)
-        best = torch.where(dST == 1, dOBJ, torch.full_like(dOBJ, float("inf"))).min()
-        dist.all_reduce(best, op=dist.ReduceOp.MIN)
+    # every rank gets every child's {objective, status} and the best bound (what a multi-GPU B-BB node needs)
+    from bonmin_b200 import shard
+    all_obj, all_st = shard.gather_children(dOBJ, dST, B * world) if world == 1 else (
+        torch.cat([t for t in _all_gather(dOBJ, world)]), torch.cat([t for t in _all_gather(dST, world)]))
+    mine = torch.where(dST == 1, dOBJ, torch.full_like(dOBJ, float("inf"))).min().item()
+    best_bound = shard.allreduce_incumbent(mine, dev)
     dev_ms_max, e2e_ms_max = t_ms.tolist()
     iters_all, n_opt, n_inf = tot.tolist()
 
@@ -260,7 +270,8 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "children_per_gpu_per_step": B, "children_per_step": total,
                        "l2": "256 MiB flush write between timed steps (untimed)",
-                       "mean_ipm_iterations": iters_all / total, "optimal": int(n_opt), "infeasible": int(n_inf)},
+                       "mean_ipm_iterations": iters_all / total, "optimal": int(n_opt), "infeasible": int(n_inf),
+                       "best_child_objective": best_bound},
             "e2e": {"value": e2e, "unit": "relaxations/s", "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": d2h * world},
             "gpu_launches": launches,
