@@ -10,7 +10,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbnlp.so")
 SOURCES = ["bnlp_api.cu", "bnlp_model.cpp", "bnlp_nl.cpp", "../host/B200Solver.cpp", "../host/host_cabi.cpp"]
 HOST_LIB = os.path.join(HERE, "libbnlp_host.so")
-HEADERS = ["../host/B200Solver.hpp", "../host/bonmin_shim.hpp", "bnlp_internal.h", "bnlp_ipm.cuh", "bnlp_eval.cuh", "bnlp_api_eval.inc", "../../include/bnlp.h"]
+HEADERS = ["../host/B200Solver.hpp", "../host/bonmin_shim.hpp", "bnlp_internal.h", "bnlp_ipm.cuh", "bnlp_ipm_coop.cuh", "bnlp_eval.cuh", "bnlp_api_eval.inc", "../../include/bnlp.h"]
 
 
 def _stale() -> bool:

@@ -19,6 +19,7 @@ constexpr double kInfD = 1e19;
 }
 #include "bnlp_eval.cuh"
 #include "bnlp_ipm.cuh"
+#include "bnlp_ipm_coop.cuh"
 
 namespace bnlp {
 bool model_from_desc(const bnlp_tape_desc *d, HostModel &M, std::string &err);
@@ -73,7 +74,8 @@ struct Device {
   DBuf<int> e_int;   // packed integer arrays of the eval tape
   DBuf<double> e_dbl;
   // solve buffers
-  DBuf<double> dXL, dXU, dX0, dOBJ, dX, dG, dD, ws;
+  DBuf<double> dXL, dXU, dX0, dOBJ, dX, dG, dD, ws, cxw, cW, cxd;
+  DBuf<int> cidle;
   DBuf<int> dST, dIT, queue;
   DBuf<long long> stats;
   // eval buffers
@@ -98,6 +100,9 @@ struct bnlp_engine {
   std::string ipm_unsupported_why;
   int h_in_smem = 1;
   size_t smem_bytes = 0;
+  bool coop_ok = false;
+  size_t coop_smem_bytes = 0;
+  int nqpad = 0, ldd = 0;
   size_t ws_doubles = 0;
   int nnz_jac = 0, nnz_hes = 0, m_nl = 0;
 };
@@ -159,6 +164,19 @@ static size_t ipm_smem_doubles(int n, int m, int R, int h_in_smem) {
   const int Rp = (R + 1) & ~1, Kp = (m + 2) & ~1;
   d += (size_t)10 * Rp + (size_t)6 * Kp + (size_t)IPM_NW * 12;
   d += (size_t)(((N + 1) & ~1) * 2 + 2 * Kp) / 2 + 2;   // flg, fixlist, qblk, qfn (ints)
+  return d;
+}
+
+static size_t ipm_smem_doubles_coop(int n, int m, int R) {
+  const int N = n + 1;
+  const int npad = (N + 2 + 3) & ~3;
+  const int lds = ((N + 2 + 7) & ~7) + 4;
+  size_t d = (size_t)(((N + 2) * (N + 3) / 2) + 1) & ~(size_t)1;
+  d += (size_t)(IPM_NW + 1) * lds;
+  d += (size_t)7 * npad;
+  const int Rp = (R + 1) & ~1, Kp = (m + 2) & ~1;
+  d += (size_t)10 * Rp + (size_t)6 * Kp + (size_t)IPM_NW * 12;
+  d += (size_t)(((N + 1) & ~1) * 2 + 2 * Kp) / 2 + 2;
   return d;
 }
 
@@ -282,6 +300,22 @@ extern "C" bnlp_engine *bnlp_engine_create(const bnlp_problem *prob, const int *
       if (E->smem_bytes + 1024 > D.smem_optin) { E->ipm_supported = false; E->ipm_unsupported_why = "iterate vectors do not fit shared memory"; }
       E->ws_doubles = (size_t)2 * (m + 1) * n + (E->h_in_smem ? 0 : (size_t)(n + 3) * (n + 4) / 2 + 2);
       E->ws_doubles = (E->ws_doubles + 1) & ~(size_t)1;
+      // cooperative DMMA kernel: needs H in shared memory, n <= 256 and the group weights to fit the staging area
+      E->nqpad = (std::max(E->nq, 1) + 3) & ~3;
+      E->ldd = (((n + 3) & ~3) | 4);
+      if ((E->ldd & 7) != 4) E->ldd += 4;
+      const int lds = ((n + 1 + 2 + 7) & ~7) + 4;
+      E->coop_smem_bytes = ipm_smem_doubles_coop(n, m, E->R) * sizeof(double);
+      int coopAttr = 0;
+      cudaDeviceGetAttribute(&coopAttr, cudaDevAttrCooperativeLaunch, D.id);
+      E->coop_ok = E->ipm_supported && coopAttr && n <= 256 && E->nq > 0 && E->coop_smem_bytes + 1024 <= D.smem_optin &&
+                   (size_t)COOP_RB * E->nqpad <= (size_t)(IPM_NW + 1) * lds && (size_t)COOP_RB * E->ldd <= (size_t)(IPM_NW + 1) * lds &&
+                   !getenv("BNLP_NO_COOP");
+    }
+    if (E->coop_ok &&
+        cudaFuncSetAttribute(ipm_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)E->coop_smem_bytes) != cudaSuccess) {
+      E->coop_ok = false;
+      cudaGetLastError();
     }
     if (E->ipm_supported &&
         (cudaFuncSetAttribute(ipm_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)E->smem_bytes) != cudaSuccess ||
@@ -301,10 +335,10 @@ extern "C" void bnlp_engine_free(bnlp_engine *E) {
   for (Device &D : E->devs) {
     cudaSetDevice(D.id);
     for (auto *b : {&D.c, &D.A, &D.Qp, &D.Qf, &D.row_sgn, &D.row_bnd, &D.gl, &D.gu, &D.xl, &D.xu, &D.e_dbl, &D.dXL, &D.dXU,
-                    &D.dX0, &D.dOBJ, &D.dX, &D.dG, &D.dD, &D.ws, &D.eX, &D.eLAM, &D.eF, &D.eG, &D.eGF, &D.eJ, &D.eH,
+                    &D.dX0, &D.dOBJ, &D.dX, &D.dG, &D.dD, &D.ws, &D.cxw, &D.cW, &D.cxd, &D.eX, &D.eLAM, &D.eF, &D.eG, &D.eGF, &D.eJ, &D.eH,
                     &D.eX2, &D.eDU, &D.oVal, &D.oLB, &D.oUB})
       b->release();
-    for (auto *b : {&D.qidx, &D.row_fn, &D.fn_row_up, &D.fn_row_lo, &D.e_int, &D.dST, &D.dIT, &D.queue, &D.oRS, &D.oCI,
+    for (auto *b : {&D.qidx, &D.row_fn, &D.fn_row_up, &D.fn_row_lo, &D.e_int, &D.dST, &D.dIT, &D.queue, &D.cidle, &D.oRS, &D.oCI,
                     &D.oSR})
       b->release();
     D.stats.release();
@@ -332,7 +366,16 @@ static int launch_ipm(bnlp_engine *E, Device &D, int B, const double *dXL, const
   a.phase_cycles = getenv("BNLP_PHASE_TIMERS") ? D.stats.p + 2 : nullptr;
   a.o = IpmOpt();
   a.o.tol = E->opt.tol; a.o.max_iter = E->opt.max_iter;
-  if (E->M.n <= 256) ipm_kernel<8><<<ctas, IPM_NT, E->smem_bytes, stream>>>(D.dm, a);
+  if (E->coop_ok) {
+    CoopBufs cb{};
+    const size_t P = (size_t)D.dm.P;
+    if (D.cxw.reserve((size_t)ctas * E->nqpad) || D.cW.reserve((size_t)ctas * P) || D.cxd.reserve((size_t)ctas * E->ldd) ||
+        D.cidle.reserve(2)) { set_err("cooperative buffers: allocation failed"); return -1; }
+    CK(cudaMemsetAsync(D.cidle.p, 0, 2 * sizeof(int), stream));
+    cb.xw = D.cxw.p; cb.Wbuf = D.cW.p; cb.xd = D.cxd.p; cb.idle_cnt = D.cidle.p; cb.nqpad = E->nqpad; cb.ldd = E->ldd;
+    void *args[] = {(void *)&D.dm, (void *)&a, (void *)&cb};
+    CK(cudaLaunchCooperativeKernel((void *)ipm_coop_kernel, dim3(ctas), dim3(IPM_NT), args, E->coop_smem_bytes, stream));
+  } else if (E->M.n <= 256) ipm_kernel<8><<<ctas, IPM_NT, E->smem_bytes, stream>>>(D.dm, a);
   else ipm_kernel<16><<<ctas, IPM_NT, E->smem_bytes, stream>>>(D.dm, a);
   E->launches++;
   CK(cudaGetLastError());
