@@ -232,14 +232,18 @@ extern "C" bnlp_engine *bnlp_engine_create(const bnlp_problem *prob, const int *
     dst[(size_t)M.qs_i[e] * (M.qs_i[e] + 1) / 2 + M.qs_j[e]] += M.qs_v[e];
   }
   E->nq = (int)(Qp.size() / P);
-  std::vector<double> Qf((size_t)E->nq * n * n);
-  for (int q = 0; q < E->nq; ++q)
+  // device strides: 128-byte aligned packed blocks and full-matrix rows (every request is a whole cache line)
+  const size_t ldp = (P + 15) & ~(size_t)15, ldq = ((size_t)n + 15) & ~(size_t)15;
+  std::vector<double> Qf((size_t)E->nq * n * ldq, 0.0), QpD((size_t)E->nq * ldp, 0.0);
+  for (int q = 0; q < E->nq; ++q) {
+    std::copy(Qp.begin() + (size_t)q * P, Qp.begin() + (size_t)(q + 1) * P, QpD.begin() + (size_t)q * ldp);
     for (int i = 0; i < n; ++i)
       for (int j = 0; j <= i; ++j) {
         const double v = Qp[(size_t)q * P + (size_t)i * (i + 1) / 2 + j];
-        Qf[((size_t)q * n + i) * n + j] = v;
-        Qf[((size_t)q * n + j) * n + i] = v;
+        Qf[((size_t)q * n + i) * ldq + j] = v;
+        Qf[((size_t)q * n + j) * ldq + i] = v;
       }
+  }
   std::vector<int> row_fn, fn_up(m + 1, -1), fn_lo(m + 1, -1);
   std::vector<double> row_sgn, row_bnd;
   for (int i = 0; i < m; ++i) {
@@ -279,17 +283,18 @@ extern "C" bnlp_engine *bnlp_engine_create(const bnlp_problem *prob, const int *
     cudaEventCreate(&D.ev0);
     cudaEventCreate(&D.ev1);
     int bad = 0;
-    bad |= upload(D.c, M.c); bad |= upload(D.A, A); bad |= upload(D.qidx, qidx); bad |= upload(D.Qp, Qp); bad |= upload(D.Qf, Qf);
+    bad |= upload(D.c, M.c); bad |= upload(D.A, A); bad |= upload(D.qidx, qidx); bad |= upload(D.Qp, QpD); bad |= upload(D.Qf, Qf);
     bad |= upload(D.row_fn, row_fn); bad |= upload(D.row_sgn, row_sgn); bad |= upload(D.row_bnd, row_bnd);
     bad |= upload(D.fn_row_up, fn_up); bad |= upload(D.fn_row_lo, fn_lo);
     bad |= upload(D.gl, M.gl); bad |= upload(D.gu, M.gu); bad |= upload(D.xl, M.xl); bad |= upload(D.xu, M.xu);
     bad |= upload(D.e_int, e_ints); bad |= upload(D.e_dbl, e_dbls);
     if (bad) { set_err("device upload failed"); delete E; return nullptr; }
     D.ev = make_eval_model_dev(eoff, D.e_int.p, D.e_dbl.p, D.gl.p, D.gu.p);
-    D.ev.qidx = D.qidx.p; D.ev.Qp = D.Qp.p; D.ev.Qf = D.Qf.p;
+    D.ev.qidx = D.qidx.p; D.ev.Qp = D.Qp.p; D.ev.Qf = D.Qf.p; D.ev.ldp = (int)ldp; D.ev.ldq = (int)ldq;
     DevModel &dm = D.dm;
     dm.n = n; dm.m = m; dm.N = n + 1; dm.R = E->R; dm.nq = E->nq; dm.P = (int)P;
     dm.npad = (dm.N + 2 + 3) & ~3;
+    dm.ldp = (int)ldp; dm.ldq = (int)ldq;
     dm.c = D.c.p; dm.A = D.A.p; dm.qidx = D.qidx.p; dm.Qp = D.Qp.p; dm.Qf = D.Qf.p;
     dm.row_fn = D.row_fn.p; dm.row_sgn = D.row_sgn.p; dm.row_bnd = D.row_bnd.p;
     dm.fn_row_up = D.fn_row_up.p; dm.fn_row_lo = D.fn_row_lo.p; dm.gl = D.gl.p; dm.gu = D.gu.p;
@@ -302,18 +307,18 @@ extern "C" bnlp_engine *bnlp_engine_create(const bnlp_problem *prob, const int *
       E->ws_doubles = (E->ws_doubles + 1) & ~(size_t)1;
       // cooperative DMMA kernel: needs H in shared memory, n <= 256 and the group weights to fit the staging area
       E->nqpad = (std::max(E->nq, 1) + 3) & ~3;
-      E->ldd = (((n + 3) & ~3) | 4);
-      if ((E->ldd & 7) != 4) E->ldd += 4;
+      E->ldd = ((n + 15) & ~15) + 1;   // >= roundup16(n); stride = 1 (mod 16) doubles: conflict-free permuted-k fragments
       const int lds = ((n + 1 + 2 + 7) & ~7) + 4;
       E->coop_smem_bytes = ipm_smem_doubles_coop(n, m, E->R) * sizeof(double);
       int coopAttr = 0;
       cudaDeviceGetAttribute(&coopAttr, cudaDevAttrCooperativeLaunch, D.id);
       E->coop_ok = E->ipm_supported && coopAttr && n <= 256 && E->nq > 0 && E->coop_smem_bytes + 1024 <= D.smem_optin &&
-                   (size_t)COOP_RB * E->nqpad <= (size_t)(IPM_NW + 1) * lds && (size_t)COOP_RB * E->ldd <= (size_t)(IPM_NW + 1) * lds &&
+                   (size_t)COOP_RB * (E->nqpad + 4) <= (size_t)(IPM_NW + 1) * lds && (size_t)COOP_RB * E->ldd <= (size_t)(IPM_NW + 1) * lds &&
                    !getenv("BNLP_NO_COOP");
     }
     if (E->coop_ok &&
-        cudaFuncSetAttribute(ipm_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)E->coop_smem_bytes) != cudaSuccess) {
+        (cudaFuncSetAttribute(ipm_coop_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)E->coop_smem_bytes) != cudaSuccess ||
+         cudaFuncSetAttribute(ipm_coop_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)E->coop_smem_bytes) != cudaSuccess)) {
       E->coop_ok = false;
       cudaGetLastError();
     }
@@ -369,12 +374,13 @@ static int launch_ipm(bnlp_engine *E, Device &D, int B, const double *dXL, const
   if (E->coop_ok) {
     CoopBufs cb{};
     const size_t P = (size_t)D.dm.P;
-    if (D.cxw.reserve((size_t)ctas * E->nqpad) || D.cW.reserve((size_t)ctas * P) || D.cxd.reserve((size_t)ctas * E->ldd) ||
+    if (D.cxw.reserve((size_t)ctas * E->nqpad) || D.cW.reserve((size_t)ctas * D.dm.ldp) || D.cxd.reserve((size_t)ctas * E->ldd) ||
         D.cidle.reserve(2)) { set_err("cooperative buffers: allocation failed"); return -1; }
     CK(cudaMemsetAsync(D.cidle.p, 0, 2 * sizeof(int), stream));
     cb.xw = D.cxw.p; cb.Wbuf = D.cW.p; cb.xd = D.cxd.p; cb.idle_cnt = D.cidle.p; cb.nqpad = E->nqpad; cb.ldd = E->ldd;
     void *args[] = {(void *)&D.dm, (void *)&a, (void *)&cb};
-    CK(cudaLaunchCooperativeKernel((void *)ipm_coop_kernel, dim3(ctas), dim3(IPM_NT), args, E->coop_smem_bytes, stream));
+    CK(cudaLaunchCooperativeKernel(a.phase_cycles ? (void *)ipm_coop_kernel<true> : (void *)ipm_coop_kernel<false>, dim3(ctas), dim3(IPM_NT), args,
+                                   E->coop_smem_bytes, stream));
   } else if (E->M.n <= 256) ipm_kernel<8><<<ctas, IPM_NT, E->smem_bytes, stream>>>(D.dm, a);
   else ipm_kernel<16><<<ctas, IPM_NT, E->smem_bytes, stream>>>(D.dm, a);
   E->launches++;
@@ -438,7 +444,9 @@ extern "C" int bnlp_solve_batch(bnlp_engine *E, int B, const double *XL, const d
     long long st[12] = {0};
     CK(cudaMemcpy(st, D.stats.p, sizeof(st), cudaMemcpyDeviceToHost));
     if (getenv("BNLP_PHASE_TIMERS")) {
-      static const char *nm[10] = {"residuals", "W pass", "J'SJ", "cholesky", "backsolve", "direction", "U pass", "linesearch", "update", "init"};
+      static const char *nm0[10] = {"residuals", "W pass", "J'SJ", "cholesky", "backsolve", "direction", "U pass", "linesearch", "update", "init"};
+      static const char *nm1[10] = {"top+J'SJ", "gridsync", "W coop", "cholesky", "solve+dir", "U coop", "linesearch", "update", "addW+fix", "idle/init"};
+      const char **nm = E->coop_ok ? nm1 : nm0;
       long long tot = 0;
       for (int q = 0; q < 10; ++q) tot += st[2 + q];
       for (int q = 0; q < 10; ++q) fprintf(stderr, "[bnlp phase] %-10s %6.2f%%  %.0f cyc/iter\n", nm[q], 100.0 * st[2 + q] / (tot ? tot : 1), (double)st[2 + q] / (st[0] ? st[0] : 1));

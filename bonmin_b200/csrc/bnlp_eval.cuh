@@ -46,6 +46,7 @@ struct EvalModelDev {
   // dense quadratic blocks shared with the IPM model
   const int *qidx;         // m+1
   const double *Qp, *Qf;
+  int ldp, ldq;            // strides of the packed blocks / full-matrix rows
 };
 
 inline EvalModelDev make_eval_model_dev(const EvalModelHostOffsets &o, const int *I, const double *D, const double *gl,
@@ -219,10 +220,10 @@ __global__ void __launch_bounds__(EV_NT) eval_kernel(EvalModelDev M, EvalArgs A)
   // ---- dense quadratic blocks: one warp per function, u = Q x row by row from the full copy
   for (int qi = w; qi < M.nfq; qi += NWARP) {
     const int k = M.fq_fn[qi], dense = M.fq_dense[qi];
-    const double *Q = M.Qf + (size_t)M.qidx[k] * n * n;
+    const double *Q = M.Qf + (size_t)M.qidx[k] * n * M.ldq;
     double vacc = 0.0;
     for (int r = 0; r < n; ++r) {
-      const double *Qr = Q + (size_t)r * n;
+      const double *Qr = Q + (size_t)r * M.ldq;
       double u = 0.0;
       for (int j = lane; j < n; j += 32) u = fma(Qr[j], x[j], u);
 #pragma unroll
@@ -262,7 +263,7 @@ __global__ void __launch_bounds__(EV_NT) eval_kernel(EvalModelDev M, EvalArgs A)
         for (int qi = 0; qi < M.nfq; ++qi) {
           const int k = M.fq_fn[qi];
           const double wgt = (k == 0) ? A.sigma : (lam ? lam[k - 1] : 0.0);
-          if (wgt != 0.0) a = fma(wgt, M.Qp[(size_t)M.qidx[k] * M.P + pe], a);
+          if (wgt != 0.0) a = fma(wgt, M.Qp[(size_t)M.qidx[k] * M.ldp + pe], a);
         }
       }
       hv[e] = a;

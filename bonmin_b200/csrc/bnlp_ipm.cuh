@@ -47,6 +47,7 @@ struct IpmOpt {
 
 struct DevModel {
   int n, m, N, R, nq, P, npad;
+  int ldp, ldq;                 // strides: packed block (multiple of 16 doubles), full-matrix row (multiple of 16)
   const double *c, *A;          // (m+1), (m+1) x n
   const int *qidx;              // m+1 : packed block index or -1
   const double *Qp;             // nq x P packed lower triangles (Hessian accumulation)
@@ -77,6 +78,12 @@ __device__ __forceinline__ int tri(int i) { return (i * (i + 1)) >> 1; }
 __device__ __forceinline__ double ld_stream(const double *p) {
   double v;
   asm("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+// same load, but pinned where it is written (volatile): used for explicit software prefetch
+__device__ __forceinline__ double ld_stream_v(const double *p) {
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
   return v;
 }
 
@@ -291,7 +298,7 @@ __device__ __forceinline__ void pass_U(const DevModel &M, const double *d, doubl
       const int rho = min(g + u, nrows - 1);
       const int qi = rho / n, r = rho - qi * n;
       const int k = qfn[qi];
-      Qr[u] = M.Qf + ((size_t)M.qidx[k] * n + r) * n;
+      Qr[u] = M.Qf + ((size_t)M.qidx[k] * n + r) * M.ldq;
       out[u] = uq + (size_t)k * n + r;
     }
     double rs[4] = {0.0, 0.0, 0.0, 0.0};
@@ -745,7 +752,7 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_kernel(DevModel M, IpmArgs A) {
               double qv[4][4];
 #pragma unroll
               for (int a = 0; a < 4; ++a) {
-                const double *Qb = M.Qp + (size_t)qblk[qi + a] * P;
+                const double *Qb = M.Qp + (size_t)qblk[qi + a] * M.ldp;
 #pragma unroll
                 for (int u = 0; u < 4; ++u) qv[a][u] = ld_stream(Qb + idx[u]);
               }
@@ -757,7 +764,7 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_kernel(DevModel M, IpmArgs A) {
               }
             }
             for (; qi < nqa; ++qi) {
-              const double *Qb = M.Qp + (size_t)qblk[qi] * P;
+              const double *Qb = M.Qp + (size_t)qblk[qi] * M.ldp;
               const double wgt = qwt[qi];
 #pragma unroll
               for (int u = 0; u < 4; ++u) acc[u] = fma(wgt, ld_stream(Qb + idx[u]), acc[u]);

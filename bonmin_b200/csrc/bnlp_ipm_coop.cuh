@@ -21,166 +21,233 @@
 namespace bnlp {
 namespace cg = cooperative_groups;
 
+#if defined(UEXP) && UEXP == 2
+#define UEXP_LOAD(p) (1.0 + 0.0 * (double)((size_t)(p) & 1))
+#else
+#define UEXP_LOAD(p) ld_stream_v(p)
+#endif
+__device__ unsigned long long g_dbg_cycles[4];
 constexpr int COOP_RB = 16;   // children per cooperative group (two m8 tiles)
 
 __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
 // ---- H[i,k] += sign * sum_c M[c][i] M[c][k], lo <= k <= i < hi, 8x8 tiles on the FP64 tensor pipe.
 // M: K rows (K multiple of 4) of length ld in shared memory, zero outside [lo,hi) within the touched tile range.
-__device__ __forceinline__ void syrk_dmma(double *H, int lo, int hi, const double *M, int ld, int K, double sign) {
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b0 = lo >> 3, nb = ((hi + 7) >> 3) - b0;
-  const int ntiles = (nb * (nb + 1)) >> 1;
+// A warp owns strips of up to four column tiles of one tile row (A fragment loaded once, four independent DMMA chains).
+// Only column tiles bk in [bkmin, bkmax] are touched; the work is shared by warps w0 .. w0+nw-1.
+__device__ __forceinline__ void syrk_dmma(double *H, int lo, int hi, const double *M, int ld, int K, double sign,
+                                          int bkmin = 0, int bkmax = 1 << 28, int w0 = 0, int nw = IPM_NW) {
+  const int w = (threadIdx.x >> 5) - w0, lane = threadIdx.x & 31;
+  if (w < 0 || w >= nw) return;
+  const int b0 = lo >> 3, b1 = (hi + 7) >> 3;
+  const int kb0 = max(b0, bkmin), kb1 = min(b1 - 1, bkmax);
+  if (kb1 < kb0) return;
   const int lr = lane >> 2, lc = lane & 3;
-  for (int t = w; t < ntiles; t += IPM_NW) {
-    int bi = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
-    while (tri(bi + 1) <= t) ++bi;
-    while (tri(bi) > t) --bi;
-    const int bk = t - tri(bi);
-    const int i0 = (b0 + bi) << 3, k0 = (b0 + bk) << 3;
-    double c0 = 0.0, c1 = 0.0;
-    const double *Ma = M + lc * ld + i0 + lr, *Mb = M + lc * ld + k0 + lr;
-    for (int c = 0; c < K; c += 4) {
-      dmma(c0, c1, Ma[c * ld], Mb[c * ld]);
+  // walk over the valid strips only: tile row bi >= kb0 owns ((min(bi,kb1) - kb0) >> 2) + 1 strips of <= 4 tiles
+  int bi = kb0, qq = w;
+  for (;;) {
+    int nqr = ((min(bi, kb1) - kb0) >> 2) + 1;
+    while (qq >= nqr) {
+      qq -= nqr;
+      if (++bi >= b1) return;
+      nqr = ((min(bi, kb1) - kb0) >> 2) + 1;
     }
-    const int i = i0 + lr, k = k0 + 2 * lc;
-    if (i >= lo && i < hi) {
-      double *Hi = H + tri(i);
-      if (k >= lo && k <= i) Hi[k] += sign * c0;
-      if (k + 1 >= lo && k + 1 <= i) Hi[k + 1] += sign * c1;
+    const int kq = kb0 + 4 * qq;
+    const int klast = min(bi, kb1);
+    const int nt = min(4, klast - kq + 1);
+    double acc[4][2];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) acc[t][0] = acc[t][1] = 0.0;
+    const double *Ma = M + lc * ld + (bi << 3) + lr, *Mb = M + lc * ld + (kq << 3) + lr;
+    if (nt == 4) {
+      for (int c = 0; c < K; c += 4) {
+        const double av = Ma[c * ld];
+        const double b0v = Mb[c * ld], b1v = Mb[c * ld + 8], b2v = Mb[c * ld + 16], b3v = Mb[c * ld + 24];
+        dmma(acc[0][0], acc[0][1], av, b0v);
+        dmma(acc[1][0], acc[1][1], av, b1v);
+        dmma(acc[2][0], acc[2][1], av, b2v);
+        dmma(acc[3][0], acc[3][1], av, b3v);
+      }
+    } else {
+      for (int c = 0; c < K; c += 4) {
+        const double av = Ma[c * ld];
+#pragma unroll
+        for (int t = 0; t < 3; ++t)
+          if (t < nt) dmma(acc[t][0], acc[t][1], av, Mb[c * ld + 8 * t]);
+      }
     }
+    const int i = (bi << 3) + lr;
+    double *Hi = H + tri(i) + (kq << 3) + 2 * lc;
+    // interior strip: every touched element is inside [lo,hi) and strictly below the diagonal -> no per-element tests
+    const bool interior = (bi << 3) >= lo && (bi << 3) + 7 < hi && (kq << 3) >= lo && kq + nt - 1 < bi;
+    if (interior) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        if (t < nt) {
+          Hi[8 * t] = fma(sign, acc[t][0], Hi[8 * t]);
+          Hi[8 * t + 1] = fma(sign, acc[t][1], Hi[8 * t + 1]);
+        }
+      }
+    } else if (i >= lo && i < hi) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        if (t < nt) {
+          const int k = ((kq + t) << 3) + 2 * lc;
+          if (k >= lo && k <= i) Hi[8 * t] = fma(sign, acc[t][0], Hi[8 * t]);
+          if (k + 1 >= lo && k + 1 <= i) Hi[8 * t + 1] = fma(sign, acc[t][1], Hi[8 * t + 1]);
+        }
+      }
+    }
+    qq += nw;
   }
+}
+
+// factor the 8x8 diagonal block at j0 and overwrite it with the INVERSE of its Cholesky factor; *fail = 1 on a
+// non-positive pivot.  Done by ONE thread entirely in registers (fully unrolled): the 8 dependent rsqrt steps are
+// the critical path of the whole factorisation, and the in-register version is ~3x shorter than a warp-shuffle one
+// (f64 shuffles cost 36 cycles each on this part; measured in scripts/micro/dmma_bench.cu).
+__device__ __noinline__ void chol_diag_block(double *H, int j0, int nb, int *fail) {
+  if ((threadIdx.x & 31) != 0) return;
+  double a[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int k = 0; k <= i; ++k) a[i][k] = (i < nb) ? H[tri(j0 + i) + j0 + k] : ((i == k) ? 1.0 : 0.0);
+  bool ok = true;
+  double rs[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {   // right-looking: the updates of one step are independent FMAs
+    const double d = a[j][j];
+    if (!(d > 0.0) || !isfinite(d)) ok = false;
+    rs[j] = rsqrt(d);
+#pragma unroll
+    for (int i = j + 1; i < 8; ++i) a[i][j] *= rs[j];
+#pragma unroll
+    for (int i = j + 1; i < 8; ++i)
+#pragma unroll
+      for (int k = j + 1; k <= i; ++k) a[i][k] = fma(-a[i][j], a[k][j], a[i][k]);
+  }
+  // in-place inverse of the lower-triangular factor, column by column: X_jj = 1/L_jj = rs_j,
+  // X_ij = -rs_i * sum_{k=j}^{i-1} L_ik X_kj
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    double x[8];
+    x[j] = rs[j];
+#pragma unroll
+    for (int i = j + 1; i < 8; ++i) {
+      double acc = 0.0;
+#pragma unroll
+      for (int k = j; k < i; ++k) acc = fma(a[i][k], x[k], acc);
+      x[i] = -rs[i] * acc;
+    }
+#pragma unroll
+    for (int i = j; i < 8; ++i) a[i][j] = x[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int k = 0; k <= i; ++k)
+      if (i < nb) H[tri(j0 + i) + j0 + k] = a[i][k];
+  *fail = ok ? 0 : 1;
 }
 
 // ---- blocked Cholesky, 8-column panels; rows [N, Nrows) carry right-hand sides (forward substitution for free).
 // After the call the 8x8 DIAGONAL BLOCKS of H hold the INVERSES of the diagonal blocks of L (lower triangular), the
-// off-diagonal part holds L.  Returns false (block-uniform) on a non-positive pivot.
-__device__ __forceinline__ bool chol_dmma(double *H, int N, int Nrows, double *stage, int ld, int *fail) {
+// off-diagonal part holds L.  Per panel: TRSM as an 8x8 DMMA with the inverse block (one warp per 8 rows), the next
+// panel's block column is updated first, then warp 0 factors the next diagonal block WHILE warps 1..15 finish the
+// trailing update (look-ahead).  Returns false (block-uniform) on a non-positive pivot.
+__device__ __forceinline__ bool chol_dmma(double *H, int N, int Nrows, double *stage, int ld, int *fail, long long *dbg) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int lr = lane >> 2, lc = lane & 3;
+  long long t0 = dbg ? clock64() : 0;
+#define CH_MARK(i) do { if (dbg) { __syncthreads(); long long t_ = clock64(); dbg[i] += t_ - t0; t0 = t_; } } while (0)
+  __syncthreads();
+  if (w == 0) chol_diag_block(H, 0, min(8, N), fail);
+  __syncthreads();
+  if (*fail) return false;
+  CH_MARK(0);
   for (int j0 = 0; j0 < N; j0 += 8) {
     const int nb = min(8, N - j0);
-    __syncthreads();
-    if (w == 0) {
-      // lane r (< 8) owns row r of the diagonal block
-      double a[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) a[k] = (lane < nb && k <= lane) ? H[tri(j0 + lane) + j0 + k] : ((lane == k) ? 1.0 : 0.0);
-      bool ok = true;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const double d = __shfl_sync(0xffffffffu, a[j], j);
-        if (!(d > 0.0) || !isfinite(d)) ok = false;
-        const double rs = rsqrt(d);
-        const double colj = (lane > j) ? a[j] * rs : ((lane == j) ? d * rs : 0.0);
-        if (lane >= j) a[j] = colj;
-#pragma unroll
-        for (int k = j + 1; k < 8; ++k) {
-          const double ck = __shfl_sync(0xffffffffu, colj, k);
-          if (lane >= k) a[k] = fma(-colj, ck, a[k]);
-        }
-      }
-      // inverse X = L^-1 (row r on lane r): X[r][c] = (delta_rc - sum_{k<r} L[r][k] X[k][c]) / L[r][r]
-      double x[8], acc[8];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) { acc[c] = (lane == c) ? 1.0 : 0.0; x[c] = 0.0; }
-      double mydiag = 1.0;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) if (lane == k) mydiag = a[k];
-      const double myrinv = 1.0 / mydiag;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        // row k is final once all rows < k have been pushed: finalise on lane k
-        if (lane == k) {
-#pragma unroll
-          for (int c = 0; c < 8; ++c) x[c] = (c <= k) ? acc[c] * myrinv : 0.0;
-        }
-#pragma unroll
-        for (int c = 0; c <= k; ++c) {
-          const double xkc = __shfl_sync(0xffffffffu, x[c], k);
-          if (lane > k) acc[c] = fma(-a[k], xkc, acc[c]);
-        }
-      }
-      if (lane < nb) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c)
-          if (c <= lane) H[tri(j0 + lane) + j0 + c] = x[c];
-      }
-      if (lane == 0) *fail = ok ? 0 : 1;
-    }
-    __syncthreads();
-    if (*fail) return false;
     const int lo = j0 + nb;
     if (lo >= Nrows) break;
     const int lo8 = lo & ~7, hi8 = (Nrows + 7) & ~7;
-    // TRSM as a multiply with the inverse block: x_c = sum_{k<=c} a_k X[c][k]; also stage the panel for the update
-    for (int i = lo8 + threadIdx.x; i < hi8; i += IPM_NT) {
-      double xr[8];
-      if (i >= lo && i < Nrows) {
-        double *Hi = H + tri(i) + j0;
-        double ar[8];
+    // TRSM: X_panel = A_panel * Xinv'   (C[8 rows x 8] = A[8 x 8] * B[8 x 8], B[k][c] = Xinv[c][k])
+    for (int i0 = lo8 + 8 * w; i0 < hi8; i0 += 8 * IPM_NW) {
+      const int i = i0 + lr;
+      const bool iv = i >= lo && i < Nrows;
+      double c0 = 0.0, c1 = 0.0;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) ar[c] = (c < nb) ? Hi[c] : 0.0;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          double v = 0.0;
-          if (c < nb) {
-            const double *Xc = H + tri(j0 + c) + j0;
-#pragma unroll
-            for (int k = 0; k <= c; ++k) v = fma(ar[k], Xc[k], v);
-          }
-          xr[c] = v;
-        }
-#pragma unroll
-        for (int c = 0; c < 8; ++c)
-          if (c < nb) Hi[c] = xr[c];
-      } else {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) xr[c] = 0.0;
+      for (int ks = 0; ks < 2; ++ks) {
+        const int kk = 4 * ks + lc;
+        const double av = (iv && kk < nb) ? H[tri(i) + j0 + kk] : 0.0;
+        const double bv = (lr < nb && kk <= lr) ? H[tri(j0 + lr) + j0 + kk] : 0.0;
+        dmma(c0, c1, av, bv);
       }
-#pragma unroll
-      for (int c = 0; c < 8; ++c) stage[c * ld + i] = xr[c];
+      const int cc = 2 * lc;
+      if (iv) {
+        if (cc < nb) H[tri(i) + j0 + cc] = c0;
+        if (cc + 1 < nb) H[tri(i) + j0 + cc + 1] = c1;
+      }
+      stage[cc * ld + i] = (iv && cc < nb) ? c0 : 0.0;
+      stage[(cc + 1) * ld + i] = (iv && cc + 1 < nb) ? c1 : 0.0;
     }
     __syncthreads();
-    syrk_dmma(H, lo, Nrows, stage, ld, 8, -1.0);
+    CH_MARK(1);
+    if (lo >= N) break;                     // only right-hand-side rows were left
+    const int bnext = lo >> 3;              // lo is a multiple of 8 here
+    syrk_dmma(H, lo, Nrows, stage, ld, 8, -1.0, bnext, bnext);          // the next panel's block column first
+    __syncthreads();
+    {
+      const long long tq0 = dbg ? clock64() : 0;
+      if (w == 0) chol_diag_block(H, lo, min(8, N - lo), fail);           // look-ahead: next diagonal block ...
+      else syrk_dmma(H, lo, Nrows, stage, ld, 8, -1.0, bnext + 1, 1 << 28, 1, IPM_NW - 1);   // ... under the rest of the update
+      if (dbg && (threadIdx.x == 0 || threadIdx.x == 32)) atomicAdd((unsigned long long *)&g_dbg_cycles[threadIdx.x >> 5], (unsigned long long)(clock64() - tq0));
+    }
+    __syncthreads();
+    if (*fail) return false;
+    CH_MARK(2);
   }
   __syncthreads();
   return true;
 }
 
-// ---- backward substitution L' x = w for the right-hand sides in rows N and N+1 (warps 0 and 1), 8-row blocks,
-// diagonal blocks given as inverses: x_blk = X' w_blk
-__device__ __forceinline__ void backsolve_inv(double *H, int N) {
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (w < 2) {
-    double *b = H + tri(N + w);
-    const int nblk = (N + 7) >> 3;
-    for (int blk = nblk - 1; blk >= 0; --blk) {
-      const int i0 = blk << 3, nb = min(8, N - i0);
-      double xc = 0.0;   // lane c < nb computes x_c = sum_{k>=c} X[k][c] w_k
-      if (lane < nb) {
+// ---- backward substitution L' x = w for the two right-hand sides in rows N and N+1, 8-row blocks, diagonal blocks
+// given as inverses.  Per block: 16 threads form x_blk = X' w_blk for both right-hand sides, then every remaining
+// entry w[k], k < i0, is updated by its own thread (8 FMAs).
+__device__ __forceinline__ void backsolve_inv(double *H, int N, double *xs /* 16 doubles of scratch */) {
+  const int tid = threadIdx.x;
+  const int nblk = (N + 7) >> 3;
+  double *b0 = H + tri(N), *b1 = H + tri(N + 1);
+  const int half = tid >> 8, kk = tid & 255;   // threads 0..255 serve rhs 0, 256..511 rhs 1  (N <= 256)
+  double *bh = half ? b1 : b0;
+  for (int blk = nblk - 1; blk >= 0; --blk) {
+    const int i0 = blk << 3, nb = min(8, N - i0);
+    if (tid < 16) {
+      const int rhs = tid >> 3, c = tid & 7;
+      const double *bb_ = rhs ? b1 : b0;
+      double xc = 0.0;
+      if (c < nb) {
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-          if (k < nb && k >= lane) xc = fma(H[tri(i0 + k) + i0 + lane], b[i0 + k], xc);
+          if (k < nb && k >= c) xc = fma(H[tri(i0 + k) + i0 + c], bb_[i0 + k], xc);
       }
-      double xr[8];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) xr[c] = __shfl_sync(0xffffffffu, xc, c);
-      __syncwarp();
-      if (lane < nb) b[i0 + lane] = xc;
-      for (int k = lane; k < i0; k += 32) {
-        double v = b[k];
-#pragma unroll
-        for (int c = 0; c < 8; ++c)
-          if (c < nb) v = fma(-H[tri(i0 + c) + k], xr[c], v);
-        b[k] = v;
-      }
-      __syncwarp();
+      xs[tid] = xc;
     }
+    __syncthreads();
+    if (kk < i0) {
+      double v = bh[kk];
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        if (c < nb) v = fma(-H[tri(i0 + c) + kk], xs[half * 8 + c], v);
+      bh[kk] = v;
+    } else if (kk < i0 + nb) {
+      bh[kk] = xs[half * 8 + (kk - i0)];
+    }
+    __syncthreads();
   }
-  __syncthreads();
 }
 
 struct CoopBufs {
@@ -193,6 +260,7 @@ struct CoopBufs {
 
 enum { CS_NEED_CHILD = 0, CS_INIT = 1, CS_ITER = 2, CS_IDLE = 3 };
 
+template <bool TIMERS>
 __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs A, CoopBufs CB) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(16) double smem[];
@@ -245,7 +313,7 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
   if (tid == 0) {
     int c = 0;
     for (int k = 0; k <= m; ++k)
-      if (M.qidx[k] >= 0) qfn[c++] = k;
+      if (M.qidx[k] >= 0) { qfn[c] = k; qblk[c] = M.qidx[k]; ++c; }
     s_nqf = c;
   }
   for (int k = tid; k <= m; k += IPM_NT) du[k] = 0.0;
@@ -270,6 +338,13 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
   double theta_init = -1.0, mu_max = -1.0, delta_w_last = 0.0, delta_w = 0.0;
   double th_hist[4] = {0, 0, 0, 0}, a_last0 = 1.0, a_last1 = 1.0;
   long long nfact = 0;
+  long long chdbg[TIMERS ? 3 : 1] = {0};
+  long long dbg2[TIMERS ? 8 : 1] = {0};
+  long long dbg_t0 = 0;
+#define D2_START() do { if constexpr (TIMERS) dbg_t0 = clock64(); } while (0)
+#define D2_MARK(i) do { if constexpr (TIMERS) { __syncthreads(); long long t_ = clock64(); dbg2[i] += t_ - dbg_t0; dbg_t0 = t_; } } while (0)
+#undef PH_MARK
+#define PH_MARK(idx) do { if constexpr (TIMERS) { const long long t_ = clock64(); ph[idx] += t_ - ph_t0; ph_t0 = t_; } } while (0)
   // values carried from the top of an iteration to its later phases
   double it_nz = 0, it_avg_compl = 0, it_cviol = 0, it_dual_inf = 0, it_s_d = 1, it_viol_max = 0, it_of = 0, it_tcur = 0;
   double it_mu = 0, it_ap_max = 0, it_ad = 0;
@@ -465,6 +540,7 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
     const double of = phase1 ? 0.0 : sf;
     const double tcur = phase1 ? x[n] : 0.0;
     it_of = of; it_tcur = tcur;
+    D2_START();
     double th_p = 0, sumv_p = 0, cs_p = 0, vl1_p = 0, ci_p = 0, cv_p = 0, cvu_p = 0, vmax_p = 0, viol_p = -1e300;
     for (int r = tid; r < R; r += IPM_NT) {
       const double hraw = fsc[r] * val[M.row_fn[r]];
@@ -483,26 +559,40 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
       vmax_p = fmax(vmax_p, v[r]);
       viol_p = fmax(viol_p, hraw - bb[r]);
     }
+    D2_MARK(0);
     // H := 0 (rows < N), then J' Sigma_s J by staged rank-16 DMMA updates; the same staged rows give J'v, J'(Ss rc), J'(1/s)
     for (int e = tid; e < tri(N); e += IPM_NT) H[e] = 0.0;
     double jv = 0.0, a0 = 0.0, a1 = 0.0;
     __syncthreads();
+    D2_MARK(1);
+    // warp c stages row c of a chunk; its raw gradient row is prefetched into registers one chunk ahead
+    double gpre[8];
+    auto prefetch_row = [&](int r) {
+      const double *g = grad + (size_t)M.row_fn[min(r, R - 1)] * n;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) gpre[u] = g[min(lane + 32 * u, n - 1)];
+    };
+    if (R > 0) prefetch_row(wid);
     for (int r0 = 0; r0 < R; r0 += IPM_KC) {
       const int kc = min(IPM_KC, R - r0), kc4 = (kc + 3) & ~3;
-      for (int c = wid; c < kc4; c += IPM_NW) {
-        const int r = r0 + c;
+      {
+        const int c = wid, r = r0 + c;   // IPM_KC == IPM_NW: one row per warp
         if (c < kc) {
           const double sq = sqrt(Ss[r]), f = sq * fsc[r];
-          const double *g = grad + (size_t)M.row_fn[r] * n;
-          for (int j = lane; j < lds; j += 32) {
-            double vv = 0.0;
-            if (j < N && !(flg[j] & F_FIXED)) vv = (j < n) ? f * g[j] : -sq;
-            stage[c * lds + j] = vv;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int j = lane + 32 * u;
+            if (j < lds) {
+              double vv = 0.0;
+              if (j < N && !(flg[j] & F_FIXED)) vv = (j < n) ? f * gpre[u] : -sq;
+              stage[c * lds + j] = vv;
+            }
           }
-        } else {
+        } else if (c < kc4) {
           for (int j = lane; j < lds; j += 32) stage[c * lds + j] = 0.0;
         }
       }
+      if (r0 + IPM_KC < R) prefetch_row(r0 + IPM_KC + wid);
       __syncthreads();
       if (tid < N) {
         for (int c = 0; c < kc; ++c) {
@@ -515,6 +605,7 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
       syrk_dmma(H, 0, N, stage, lds, kc4, 1.0);
       __syncthreads();
     }
+    D2_MARK(2);
     // sweep over variables: Lagrangian gradient, right-hand sides (into the augmented rows), Sigma_x
     double di_p = 0, sumz_p = 0, nz_p = 0;
     for (int j = tid; j < N; j += IPM_NT) {   // N <= IPM_NT: one variable per thread, jv/a0/a1 belong to j = tid
@@ -543,6 +634,7 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
     }
     double all[12] = {th_p, sumv_p, cs_p, vl1_p, sumz_p, nz_p, ci_p, cv_p, cvu_p, vmax_p, viol_p, di_p};
     block_reduce<6, 6>(all, red);
+    D2_MARK(3);
     const double th = all[0], sum_v = all[1], vl1 = all[3];
     const double nz = all[5] + (double)R, sum_z = all[4] + sum_v;
     const double compl_inf = all[6], cviol = all[7], cviol_unsc = all[8], ymax = all[9], viol_max = all[10], dual_inf = all[11];
@@ -613,6 +705,8 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
     return 0;
   };
 
+  long long ph[TIMERS ? 10 : 1] = {0};
+  long long ph_t0 = TIMERS ? clock64() : 0;
   for (int step = 0;; ++step) {
     // =================================================================== A: local pre-phase
     for (;;) {
@@ -637,64 +731,76 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
     if (state != CS_ITER)
       for (int j = tid; j < ldd; j += IPM_NT) __stcg(CB.xd + (size_t)cta * ldd + j, (state == CS_INIT && j < n) ? x[j] : 0.0);
     if (tid == 0) atomicAdd(&CB.idle_cnt[step & 1], state == CS_IDLE ? 1 : 0);
+    PH_MARK(0);
     grid.sync();   // ------------------------------------------------------------------------------ barrier 1
+    PH_MARK(1);
     if (*((volatile int *)&CB.idle_cnt[step & 1]) == G) break;
     if (cta == 0 && tid == 0) CB.idle_cnt[(step + 1) & 1] = 0;
 
     // =================================================================== B: cooperative W pass (DMMA)
+    // Every global request is a whole 128-byte line: lane (lc, lr) loads the double2 {e0+2lr, e0+2lr+1} of packed block
+    // 4u+lc; the even elements feed one m8n8k4 tile, the odd ones a second tile, so a lane ends up owning four
+    // consecutive elements of W for one child (two 16-byte stores).
     if (coop_on) {
-      // weights of my group -> shared memory: wsm[16][nqpad]
-      double *wsm = stage;
+      double *wsm = stage;   // wsm[16][ldw], ldw = 4 (mod 8): conflict-free A fragments
+      const int ldw = nqpad + ((nqpad & 7) == 4 ? 0 : 4);
       for (int e = tid; e < COOP_RB * nqpad; e += IPM_NT) {
-        const int b = my_g * COOP_RB + e / nqpad;
-        wsm[e] = (b < G) ? __ldcg(CB.xw + (size_t)b * nqpad + e % nqpad) : 0.0;
+        const int row = e / nqpad, col = e % nqpad;
+        const int b = my_g * COOP_RB + row;
+        wsm[row * ldw + col] = (b < G) ? __ldcg(CB.xw + (size_t)b * nqpad + col) : 0.0;
       }
       __syncthreads();
-      const int NT8 = (P + 7) >> 3;
-      const int t0 = (int)(((long long)NT8 * my_s) / NS), t1 = (int)(((long long)NT8 * (my_s + 1)) / NS);
+      const int NT16 = (P + 15) >> 4;
+      const int t0 = (int)(((long long)NT16 * my_s) / NS), t1 = (int)(((long long)NT16 * (my_s + 1)) / NS);
       const int lr = lane >> 2, lc = lane & 3;
       for (int t = t0 + wid; t < t1; t += IPM_NW) {
-        const int e = min(8 * t + lr, P - 1);
-        const bool ev = 8 * t + lr < P;
-        double c00 = 0, c01 = 0, c10 = 0, c11 = 0;
-        for (int ks = 0; ks < nqpad; ks += 16) {   // 4 k-steps in flight
-          double bq[4];
+        const int e0 = 16 * t;                       // ldp is a multiple of 16: the line always exists (zero padded)
+        double cE0 = 0, cE1 = 0, cE2 = 0, cE3 = 0, cO0 = 0, cO1 = 0, cO2 = 0, cO3 = 0;
+        for (int ks = 0; ks < nqpad; ks += 32) {     // 8 k-steps (32 blocks) per round
+          double2 qv[8];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < 8; ++u) {
             const int qi = ks + 4 * u + lc;
-            const int qc = min(qi, nqf - 1);
-            const double qv = ld_stream(M.Qp + (size_t)M.qidx[qfn[qc]] * P + e);
-            bq[u] = (qi < nqf && ev && ks + 4 * u < nqpad) ? qv : 0.0;
+            const double2 *Qb = reinterpret_cast<const double2 *>(M.Qp + (size_t)qblk[min(qi, nqf - 1)] * M.ldp + e0) + lr;
+            qv[u] = __ldg(Qb);
+            if (qi >= nqf) { qv[u].x = 0.0; qv[u].y = 0.0; }
           }
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < 8; ++u) {
             if (ks + 4 * u < nqpad) {
               const int kk = ks + 4 * u + lc;
-              dmma(c00, c01, wsm[lr * nqpad + kk], bq[u]);
-              dmma(c10, c11, wsm[(8 + lr) * nqpad + kk], bq[u]);
+              const double w0v = wsm[lr * ldw + kk], w1v = wsm[(8 + lr) * ldw + kk];
+              dmma(cE0, cE1, w0v, qv[u].x);
+              dmma(cE2, cE3, w1v, qv[u].x);
+              dmma(cO0, cO1, w0v, qv[u].y);
+              dmma(cO2, cO3, w1v, qv[u].y);
             }
           }
         }
-        // C[row = child lr (+8)][col = element 2*lc, 2*lc+1]
-        const int ecol = 8 * t + 2 * lc;
+        // even tile: C[child lr (+8)][n = 2lc, 2lc+1] <-> elements e0 + 4lc, e0 + 4lc + 2; odd tile: e0 + 4lc + 1, + 3
         const int b0i = my_g * COOP_RB + lr, b1i = b0i + 8;
-        if (b0i < G) {
-          if (ecol < P) __stcg(CB.Wbuf + (size_t)b0i * P + ecol, c00);
-          if (ecol + 1 < P) __stcg(CB.Wbuf + (size_t)b0i * P + ecol + 1, c01);
+        const int ec = e0 + 4 * lc;
+        if (b0i < G && ec < P) {   // Wbuf rows have stride ldp too
+          double2 *dst = reinterpret_cast<double2 *>(CB.Wbuf + (size_t)b0i * M.ldp + ec);
+          __stcg(dst, make_double2(cE0, cO0));
+          __stcg(dst + 1, make_double2(cE1, cO1));
         }
-        if (b1i < G) {
-          if (ecol < P) __stcg(CB.Wbuf + (size_t)b1i * P + ecol, c10);
-          if (ecol + 1 < P) __stcg(CB.Wbuf + (size_t)b1i * P + ecol + 1, c11);
+        if (b1i < G && ec < P) {
+          double2 *dst = reinterpret_cast<double2 *>(CB.Wbuf + (size_t)b1i * M.ldp + ec);
+          __stcg(dst, make_double2(cE2, cO2));
+          __stcg(dst + 1, make_double2(cE3, cO3));
         }
       }
     }
+    PH_MARK(2);
     grid.sync();   // ------------------------------------------------------------------------------ barrier 2
+    PH_MARK(1);
 
     // =================================================================== C: factorisation, direction (per child)
     if (state == CS_ITER) {
       const double of = it_of;
       // H += W  (rows < n), fixed rows/cols -> identity, diagonal += Sigma_x + delta_w
-      const double *Wb = CB.Wbuf + (size_t)cta * P;
+      const double *Wb = CB.Wbuf + (size_t)cta * M.ldp;
       for (int e = tid; e < P; e += IPM_NT) H[e] += __ldcg(Wb + e);
       __syncthreads();
       const int nfix = s_nfix;
@@ -710,7 +816,8 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
       }
       ++nfact;
       retry = false;
-      if (!chol_dmma(H, N, N + 2, stage, lds, &s_fail)) {
+      PH_MARK(8);
+      if (!chol_dmma(H, N, N + 2, stage, lds, &s_fail, TIMERS ? chdbg : nullptr)) {
         // inertia correction: retry the whole step with a larger delta_w (first 1e-4, x100 then x8, /3 between iterations)
         if (delta_w == 0.0) delta_w = (delta_w_last == 0.0) ? 1e-4 : fmax(1e-20, delta_w_last / 3.0);
         else delta_w *= (delta_w_last == 0.0 ? 100.0 : 8.0);
@@ -721,8 +828,12 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
       } else {
         if (delta_w > 0) delta_w_last = delta_w;
         delta_w = 0.0; fact_attempts = 0;
-        backsolve_inv(H, N);
+        PH_MARK(3);
+        D2_START();
+        backsolve_inv(H, N, red);
+        D2_MARK(4);
         dots_grad(M, grad, d0, d1, gd0, gd1);
+        D2_MARK(5);
         for (int r = tid; r < R; r += IPM_NT) {
           const int fn = M.row_fn[r];
           jd0[r] = fsc[r] * gd0[fn] - d0[n];
@@ -793,6 +904,7 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
         double ap_max, ad;
         ftb(mu, tau, ap_max, ad);
         it_mu = mu; it_ap_max = ap_max; it_ad = ad;
+        D2_MARK(6);
         for (int j = tid; j < N; j += IPM_NT) dx[j] = (flg[j] & F_FIXED) ? 0.0 : d0[j] + mu * d1[j];
         for (int r = tid; r < R; r += IPM_NT) {
           ds[r] = -rc[r] - (jd0[r] + mu * jd1[r]);
@@ -800,13 +912,19 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
         }
         for (int k = tid; k <= m; k += IPM_NT) gd0[k] = gd0[k] + mu * gd1[k];
         __syncthreads();
+        D2_MARK(7);
       }
       (void)of;
       for (int j = tid; j < ldd; j += IPM_NT) __stcg(CB.xd + (size_t)cta * ldd + j, j < n ? dx[j] : 0.0);
     }
+    PH_MARK(4);
     grid.sync();   // ------------------------------------------------------------------------------ barrier 3
+    PH_MARK(1);
 
     // =================================================================== D: cooperative U pass (DMMA)
+    // Whole-line requests again: lane (lr, lc) loads the 32-byte sector lc of the 128-byte line {row r0+lr, columns
+    // 16g .. 16g+15}; k-step s of that group contracts over the columns {16g + 4lc + s}, which is only a permutation of
+    // the summation index, so the B fragments are read from Dsm at the same permuted columns.
     if (coop_on) {
       double *Dsm = stage;   // [16][ldd]
       for (int e = tid; e < COOP_RB * ldd; e += IPM_NT) {
@@ -817,28 +935,41 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
       const int tpb = (n + 7) >> 3, ntile = nqf * tpb;
       const int t0 = (int)(((long long)ntile * my_s) / NS), t1 = (int)(((long long)ntile * (my_s + 1)) / NS);
       const int lr = lane >> 2, lc = lane & 3;
-      const int n4 = (n + 3) & ~3;
+      const int ngrp = (n + 15) >> 4;       // 16-column groups (Qf rows are zero padded to ldq = roundup16(n))
       for (int t = t0 + wid; t < t1; t += IPM_NW) {
         const int qi = t / tpb, r0 = (t - qi * tpb) << 3;
         const int k = qfn[qi];
         const int r = r0 + lr;
-        const double *Qrow = M.Qf + ((size_t)M.qidx[k] * n + min(r, n - 1)) * n;
+        const double2 *Qrow = reinterpret_cast<const double2 *>(M.Qf + ((size_t)qblk[qi] * n + min(r, n - 1)) * M.ldq) + 2 * lc;
         const bool rv = r < n;
         double c00 = 0, c01 = 0, c10 = 0, c11 = 0;
-        for (int ks = 0; ks < n4; ks += 32) {   // 8 k-steps in flight
-          double aq[8];
+        // software pipeline over pairs of groups: 4 x 16-byte loads in flight ahead of the DMMAs that consume them
+        double2 aq[2][4];
+        auto loadgrp = [&](int g, double2 *dst) {
+          const int g0 = min(g, ngrp - 1), g1 = min(g + 1, ngrp - 1);
+          dst[0] = __ldg(Qrow + 8 * g0); dst[1] = __ldg(Qrow + 8 * g0 + 1);
+          dst[2] = __ldg(Qrow + 8 * g1); dst[3] = __ldg(Qrow + 8 * g1 + 1);
+        };
+        loadgrp(0, aq[0]);
+        for (int g = 0; g < ngrp; g += 4) {
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int col = ks + 4 * u + lc;
-            const double qv = ld_stream(Qrow + min(col, n - 1));
-            aq[u] = (rv && col < n) ? qv : 0.0;
-          }
+          for (int half = 0; half < 2; ++half) {
+            const int gc = g + 2 * half;
+            if (gc < ngrp) {
+              if (gc + 2 < ngrp) loadgrp(gc + 2, aq[half ^ 1]);
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int col = ks + 4 * u + lc;
-            if (ks + 4 * u < n4) {
-              dmma(c00, c01, aq[u], Dsm[lr * ldd + col]);
-              dmma(c10, c11, aq[u], Dsm[(8 + lr) * ldd + col]);
+              for (int h = 0; h < 2; ++h) {
+                if (gc + h < ngrp) {
+                  const int cb = 16 * (gc + h) + 4 * lc;
+                  const double av[4] = {aq[half][2 * h].x, aq[half][2 * h].y, aq[half][2 * h + 1].x, aq[half][2 * h + 1].y};
+#pragma unroll
+                  for (int s4 = 0; s4 < 4; ++s4) {
+                    const double a = rv ? av[s4] : 0.0;
+                    dmma(c00, c01, a, Dsm[lr * ldd + cb + s4]);
+                    dmma(c10, c11, a, Dsm[(8 + lr) * ldd + cb + s4]);
+                  }
+                }
+              }
             }
           }
         }
@@ -854,10 +985,13 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
         }
       }
     }
+    PH_MARK(5);
     grid.sync();   // ------------------------------------------------------------------------------ barrier 4
+    PH_MARK(1);
 
     // =================================================================== E: initialisation tail / line search + update
     if (state == CS_INIT) {
+      PH_MARK(9);
       if (finish_init()) { write_results(); state = CS_NEED_CHILD; }
       else state = CS_ITER;
     } else if (state == CS_ITER) {
@@ -954,6 +1088,7 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
         continue;
       }
       a_last1 = a_last0; a_last0 = alpha;
+      PH_MARK(6);
       __syncthreads();
       for (int j = tid; j < N; j += IPM_NT) {
         const int f = flg[j];
@@ -987,7 +1122,14 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
       }
       __syncthreads();
       ++iters;
+      PH_MARK(7);
     }
+  }
+  if constexpr (TIMERS) {
+  if (tid == 0 && cta == 0) printf("[dbg all] diag-warp %llu syrkrest-warp1 %llu\n", g_dbg_cycles[0], g_dbg_cycles[1]);
+  if (tid == 0 && cta == 0) printf("[dbg cta0] chol: diag0 %lld trsm %lld syrk+diag %lld | top: rows %lld zeroH %lld chunks %lld vars %lld | C: backsolve %lld dots %lld ftb/mu %lld dir %lld\n", chdbg[0], chdbg[1], chdbg[2], dbg2[0], dbg2[1], dbg2[2], dbg2[3], dbg2[4], dbg2[5], dbg2[6], dbg2[7]);
+  if (A.phase_cycles && tid == 0)
+    for (int q = 0; q < 10; ++q) atomicAdd((unsigned long long *)&A.phase_cycles[q], (unsigned long long)ph[q]);
   }
 }
 
