@@ -69,7 +69,8 @@ struct Device {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // model
   DBuf<double> c, A, Qp, Qf, row_sgn, row_bnd, gl, gu, xl, xu;
-  DBuf<int> qidx, row_fn, fn_row_up, fn_row_lo;
+  DBuf<int> qidx, row_fn, fn_row_up, fn_row_lo, eq_fn, fn_eq;
+  DBuf<double> eq_bnd;
   EvalModelDev ev;   // eval / OA view of the tape
   DBuf<int> e_int;   // packed integer arrays of the eval tape
   DBuf<double> e_dbl;
@@ -154,11 +155,11 @@ extern "C" int bnlp_problem_info(const bnlp_problem *p, int *jac_irow, int *jac_
   return 0;
 }
 
-static size_t ipm_smem_doubles(int n, int m, int R, int h_in_smem) {
+static size_t ipm_smem_doubles(int n, int m, int R, int E, int h_in_smem) {
   const int N = n + 1;
   const int npad = (N + 2 + 3) & ~3;
-  size_t d = 0;
-  if (h_in_smem) d += (size_t)(((N + 2) * (N + 3) / 2) + 1) & ~(size_t)1;
+  size_t d = 5 * IPM_MAXE + IPM_MAXE * IPM_MAXE;
+  if (h_in_smem) d += (size_t)(((N + 2 + E) * (N + 3 + E) / 2) + 1) & ~(size_t)1;
   d += (size_t)(IPM_NW + 1) * npad;
   d += (size_t)7 * npad;
   const int Rp = (R + 1) & ~1, Kp = (m + 2) & ~1;
@@ -244,16 +245,17 @@ extern "C" bnlp_engine *bnlp_engine_create(const bnlp_problem *prob, const int *
         Qf[((size_t)q * n + j) * ldq + i] = v;
       }
   }
-  std::vector<int> row_fn, fn_up(m + 1, -1), fn_lo(m + 1, -1);
+  std::vector<int> row_fn, fn_up(m + 1, -1), fn_lo(m + 1, -1), eq_fn, fn_eq(m + 1, -1);
+  std::vector<double> eq_bnd;
   std::vector<double> row_sgn, row_bnd;
   for (int i = 0; i < m; ++i) {
     const bool lo = M.gl[i] > -kInf, hi = M.gu[i] < kInf;
-    if (lo && hi && M.gl[i] == M.gu[i]) { E->E++; continue; }
+    if (lo && hi && M.gl[i] == M.gu[i]) { fn_eq[i + 1] = E->E++; eq_fn.push_back(i + 1); eq_bnd.push_back(M.gl[i]); continue; }
     if (hi) { fn_up[i + 1] = (int)row_fn.size(); row_fn.push_back(i + 1); row_sgn.push_back(1.0); row_bnd.push_back(M.gu[i]); }
     if (lo) { fn_lo[i + 1] = (int)row_fn.size(); row_fn.push_back(i + 1); row_sgn.push_back(-1.0); row_bnd.push_back(-M.gl[i]); }
   }
   E->R = (int)row_fn.size();
-  if (E->E > 0) { E->ipm_supported = false; E->ipm_unsupported_why = "equality rows are not supported by the batched IPM yet"; }
+  if (E->E > IPM_MAXE) { E->ipm_supported = false; E->ipm_unsupported_why = "more than 8 equality rows are not supported by the batched IPM yet"; }
   if (!M.terms.empty()) { E->ipm_supported = false; E->ipm_unsupported_why = "general nonlinear terms are not supported by the batched IPM yet"; }
   if (n > 32 * IPM_MAXC) { E->ipm_supported = false; E->ipm_unsupported_why = "n > 512 is not supported by the batched IPM yet"; }
 
@@ -286,6 +288,7 @@ extern "C" bnlp_engine *bnlp_engine_create(const bnlp_problem *prob, const int *
     bad |= upload(D.c, M.c); bad |= upload(D.A, A); bad |= upload(D.qidx, qidx); bad |= upload(D.Qp, QpD); bad |= upload(D.Qf, Qf);
     bad |= upload(D.row_fn, row_fn); bad |= upload(D.row_sgn, row_sgn); bad |= upload(D.row_bnd, row_bnd);
     bad |= upload(D.fn_row_up, fn_up); bad |= upload(D.fn_row_lo, fn_lo);
+    bad |= upload(D.eq_fn, eq_fn); bad |= upload(D.fn_eq, fn_eq); bad |= upload(D.eq_bnd, eq_bnd);
     bad |= upload(D.gl, M.gl); bad |= upload(D.gu, M.gu); bad |= upload(D.xl, M.xl); bad |= upload(D.xu, M.xu);
     bad |= upload(D.e_int, e_ints); bad |= upload(D.e_dbl, e_dbls);
     if (bad) { set_err("device upload failed"); delete E; return nullptr; }
@@ -298,12 +301,13 @@ extern "C" bnlp_engine *bnlp_engine_create(const bnlp_problem *prob, const int *
     dm.c = D.c.p; dm.A = D.A.p; dm.qidx = D.qidx.p; dm.Qp = D.Qp.p; dm.Qf = D.Qf.p;
     dm.row_fn = D.row_fn.p; dm.row_sgn = D.row_sgn.p; dm.row_bnd = D.row_bnd.p;
     dm.fn_row_up = D.fn_row_up.p; dm.fn_row_lo = D.fn_row_lo.p; dm.gl = D.gl.p; dm.gu = D.gu.p;
+    dm.E = E->E; dm.eq_fn = D.eq_fn.p; dm.eq_bnd = D.eq_bnd.p; dm.fn_eq = D.fn_eq.p;
     if (d == 0) {
-      const size_t need = ipm_smem_doubles(n, m, E->R, 1) * sizeof(double);
+      const size_t need = ipm_smem_doubles(n, m, E->R, E->E, 1) * sizeof(double);
       E->h_in_smem = need + 1024 <= D.smem_optin ? 1 : 0;
-      E->smem_bytes = ipm_smem_doubles(n, m, E->R, E->h_in_smem) * sizeof(double);
+      E->smem_bytes = ipm_smem_doubles(n, m, E->R, E->E, E->h_in_smem) * sizeof(double);
       if (E->smem_bytes + 1024 > D.smem_optin) { E->ipm_supported = false; E->ipm_unsupported_why = "iterate vectors do not fit shared memory"; }
-      E->ws_doubles = (size_t)2 * (m + 1) * n + (E->h_in_smem ? 0 : (size_t)(n + 3) * (n + 4) / 2 + 2);
+      E->ws_doubles = (size_t)2 * (m + 1) * n + (E->h_in_smem ? 0 : (size_t)(n + 3 + E->E) * (n + 4 + E->E) / 2 + 2);
       E->ws_doubles = (E->ws_doubles + 1) & ~(size_t)1;
       // cooperative DMMA kernel: needs H in shared memory, n <= 256 and the group weights to fit the staging area
       E->nqpad = (std::max(E->nq, 1) + 3) & ~3;
@@ -312,7 +316,7 @@ extern "C" bnlp_engine *bnlp_engine_create(const bnlp_problem *prob, const int *
       E->coop_smem_bytes = ipm_smem_doubles_coop(n, m, E->R) * sizeof(double);
       int coopAttr = 0;
       cudaDeviceGetAttribute(&coopAttr, cudaDevAttrCooperativeLaunch, D.id);
-      E->coop_ok = E->ipm_supported && coopAttr && n <= 256 && E->nq > 0 && E->coop_smem_bytes + 1024 <= D.smem_optin &&
+      E->coop_ok = E->ipm_supported && coopAttr && n <= 256 && E->nq > 0 && E->E == 0 && E->coop_smem_bytes + 1024 <= D.smem_optin &&
                    (size_t)COOP_RB * (E->nqpad + 4) <= (size_t)(IPM_NW + 1) * lds && (size_t)COOP_RB * E->ldd <= (size_t)(IPM_NW + 1) * lds &&
                    !getenv("BNLP_NO_COOP");
     }
@@ -340,10 +344,10 @@ extern "C" void bnlp_engine_free(bnlp_engine *E) {
   for (Device &D : E->devs) {
     cudaSetDevice(D.id);
     for (auto *b : {&D.c, &D.A, &D.Qp, &D.Qf, &D.row_sgn, &D.row_bnd, &D.gl, &D.gu, &D.xl, &D.xu, &D.e_dbl, &D.dXL, &D.dXU,
-                    &D.dX0, &D.dOBJ, &D.dX, &D.dG, &D.dD, &D.ws, &D.cxw, &D.cW, &D.cxd, &D.eX, &D.eLAM, &D.eF, &D.eG, &D.eGF, &D.eJ, &D.eH,
+                    &D.dX0, &D.dOBJ, &D.dX, &D.dG, &D.dD, &D.ws, &D.cxw, &D.cW, &D.cxd, &D.eq_bnd, &D.eX, &D.eLAM, &D.eF, &D.eG, &D.eGF, &D.eJ, &D.eH,
                     &D.eX2, &D.eDU, &D.oVal, &D.oLB, &D.oUB})
       b->release();
-    for (auto *b : {&D.qidx, &D.row_fn, &D.fn_row_up, &D.fn_row_lo, &D.e_int, &D.dST, &D.dIT, &D.queue, &D.cidle, &D.oRS, &D.oCI,
+    for (auto *b : {&D.qidx, &D.row_fn, &D.fn_row_up, &D.fn_row_lo, &D.e_int, &D.dST, &D.dIT, &D.queue, &D.cidle, &D.eq_fn, &D.fn_eq, &D.oRS, &D.oCI,
                     &D.oSR})
       b->release();
     D.stats.release();

@@ -23,6 +23,7 @@ constexpr int IPM_NT = 512;           // threads per CTA
 constexpr int IPM_NW = IPM_NT / 32;   // warps per CTA
 constexpr int IPM_KC = 16;            // rank of one staged SYRK / trailing update
 constexpr int IPM_NB = 8;             // Cholesky panel width
+constexpr int IPM_MAXE = 8;           // equality rows supported by the Schur-complement path
 constexpr int IPM_MAXC = 16;          // column accumulators per lane in the symmetric mat-vec: n <= 512
 
 // TNLPSolver::ReturnStatus (BonTNLPSolver.hpp:29-44)
@@ -55,6 +56,10 @@ struct DevModel {
   const int *row_fn;            // R one-sided rows  sgn * F_fn(x) <= bnd
   const double *row_sgn, *row_bnd;
   const int *fn_row_up, *fn_row_lo;  // m+1 : row index of the upper / lower side of a function, or -1
+  int E;                        // equality rows (g_L == g_U): handled through a Schur complement, E <= IPM_MAXE
+  const int *eq_fn;             // E : function index
+  const double *eq_bnd;         // E : right-hand side
+  const int *fn_eq;             // m+1 : equality index of a function, or -1
   const double *gl, *gu;        // m
 };
 
@@ -382,7 +387,8 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_kernel(DevModel M, IpmArgs A) {
   const IpmOpt &o = A.o;
   // ---- carve shared memory
   double *sp = smem;
-  const int Haug = tri(N + 2);
+  const int E = M.E;
+  const int Haug = tri(N + 2 + E);
   double *H;
   double *ws = A.ws + (size_t)blockIdx.x * A.ws_stride;
   double *grad = ws;                              // (m+1) x n
@@ -413,6 +419,12 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_kernel(DevModel M, IpmArgs A) {
   double *du = sp; sp += Kp;
   double *wq = sp; sp += 2 * Kp;
   double *red = sp; sp += IPM_NW * 12;
+  double *ye = sp; sp += IPM_MAXE;       // equality multipliers, residuals, scales, step parts, Schur complement
+  double *ce = sp; sp += IPM_MAXE;
+  double *esc = sp; sp += IPM_MAXE;
+  double *de0 = sp; sp += IPM_MAXE;
+  double *de1 = sp; sp += IPM_MAXE;
+  double *Ssc = sp; sp += IPM_MAXE * IPM_MAXE;
   int *flg = reinterpret_cast<int *>(sp);  // N ints
   int *fixlist = flg + ((N + 1) & ~1);     // N ints
   int *qblk = fixlist + ((N + 1) & ~1);    // m+1 ints
@@ -566,6 +578,7 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_kernel(DevModel M, IpmArgs A) {
         fsc[r] = sc * sg;
         bb[r] = b + o.bound_relax * fmax(1.0, fabs(b));
       }
+      for (int e = tid; e < E; e += IPM_NT) esc[e] = wq[M.eq_fn[e]];
       __syncthreads();
     }
 
@@ -581,6 +594,7 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_kernel(DevModel M, IpmArgs A) {
         zL[j] = (!(f & F_FIXED) && (f & F_HASL)) ? 1.0 : 0.0;
         zU[j] = (!(f & F_FIXED) && (f & F_HASU)) ? 1.0 : 0.0;
       }
+      for (int e = tid; e < E; e += IPM_NT) ye[e] = 0.0;
       __syncthreads();
     };
     if (!done) init_slacks_mults();
@@ -608,6 +622,16 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_kernel(DevModel M, IpmArgs A) {
         vmax_p = fmax(vmax_p, v[r]);
         viol_p = fmax(viol_p, hraw - bb[r]);
       }
+      double sumye_p = 0.0;
+      for (int e = tid; e < E; e += IPM_NT) {
+        const double res = esc[e] * (val[M.eq_fn[e]] - M.eq_bnd[e]);
+        ce[e] = res;
+        th_p += fabs(res);
+        cv_p = fmax(cv_p, fabs(res));
+        cvu_p = fmax(cvu_p, fabs(res) / esc[e]);
+        sumye_p += fabs(ye[e]);
+      }
+      sumv_p += sumye_p;   // enters s_d only (sum of all constraint multipliers)
       __syncthreads();
       // sweep 2 over variables: gradient of the Lagrangian (J' v), rhs vectors, Sigma_x
       double di_p = 0, sumz_p = 0, nz_p = 0;
@@ -616,6 +640,8 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_kernel(DevModel M, IpmArgs A) {
         double r0 = 0.0, r1 = 0.0, sx = 0.0;
         if (!(f & F_FIXED)) {
           double g0 = (j < n) ? of * grad[j] : (phase1 ? 1.0 : 0.0);
+          if (j < n)
+            for (int e = 0; e < E; ++e) g0 = fma(esc[e] * grad[(size_t)M.eq_fn[e] * n + j], ye[e], g0);
           double jv = 0.0, a0 = 0.0, a1 = 0.0;
           if (j < n) {
             for (int r = 0; r < R; ++r) {
@@ -646,8 +672,14 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_kernel(DevModel M, IpmArgs A) {
         d0[j] = r0;   // right-hand sides go straight into the augmented rows
         d1[j] = r1;
       }
-      a9[0] = th_p; a9[1] = sumv_p; a9[2] = cs_p; a9[3] = vl1_p; a9[4] = sumz_p; a9[5] = nz_p;
+      a9[0] = th_p; a9[1] = sumv_p - sumye_p; a9[2] = cs_p; a9[3] = vl1_p; a9[4] = sumz_p; a9[5] = nz_p;
       double m6[6] = {ci_p, cv_p, cvu_p, vmax_p, viol_p, di_p};
+      double sum_ye = 0.0;
+      if (E > 0) {
+        double t1[1] = {sumye_p};
+        block_reduce<1, 0>(t1, red);
+        sum_ye = t1[0];
+      }
       {
         double all[12] = {a9[0], a9[1], a9[2], a9[3], a9[4], a9[5], m6[0], m6[1], m6[2], m6[3], m6[4], m6[5]};
         block_reduce<6, 6>(all, red);
@@ -659,7 +691,7 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_kernel(DevModel M, IpmArgs A) {
       const double compl_inf = m6[0], cviol = m6[1], cviol_unsc = m6[2], ymax = m6[3], viol_max = m6[4], dual_inf = m6[5];
       const double avg_compl = nz > 0 ? a9[2] / nz : 0.0;
       if (theta_init < 0) theta_init = th;
-      const double s_d = fmax(o.s_max, (sum_v + sum_z) / fmax(1.0, (double)R + nz)) / o.s_max;
+      const double s_d = fmax(o.s_max, (sum_v + sum_ye + sum_z) / fmax(1.0, (double)R + (double)E + nz)) / o.s_max;
       const double s_c = fmax(o.s_max, sum_z / fmax(1.0, nz)) / o.s_max;
       const double E0 = fmax(fmax(dual_inf / s_d, cviol), compl_inf / s_c);
       if (mu_max < 0) mu_max = fmin(o.mu_max, o.mu_max_fact * fmax(avg_compl, 1e-300));
@@ -721,6 +753,8 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_kernel(DevModel M, IpmArgs A) {
         const int ru = M.fn_row_up[k], rl = M.fn_row_lo[k];
         if (ru >= 0) w += v[ru] * fsc[ru];
         if (rl >= 0) w += v[rl] * fsc[rl];
+        const int ei = M.fn_eq[k];
+        if (ei >= 0) w += ye[ei] * esc[ei];
         wq[k] = w;
       }
       __syncthreads();
@@ -809,9 +843,15 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_kernel(DevModel M, IpmArgs A) {
           syrk_tiles(H, 0, N, stage, npad, kc, 1.0);
           __syncthreads();
         }
+        // equality rows A_e ride along as extra rows: after the factorisation they hold Y_e = L^-1 A_e'
+        for (int e = 0; e < E; ++e) {
+          double *Ye = H + tri(N + 2 + e);
+          const double *g = grad + (size_t)M.eq_fn[e] * n;
+          for (int j = tid; j < N; j += IPM_NT) Ye[j] = (j < n && !(flg[j] & F_FIXED)) ? esc[e] * g[j] : 0.0;
+        }
         ++nfact;
         PH_MARK(2);
-        if (chol_packed(H, N, N + 2, stage, npad, &s_fail)) { fact_ok = true; break; }
+        if (chol_packed(H, N, N + 2 + E, stage, npad, &s_fail)) { fact_ok = true; break; }
         // inertia correction (first_hessian_perturbation 1e-4, x100 then x8, /3 between iterations)
         if (delta_w == 0.0) delta_w = (delta_w_last == 0.0) ? 1e-4 : fmax(1e-20, delta_w_last / 3.0);
         else delta_w *= (delta_w_last == 0.0 ? 100.0 : 8.0);
@@ -823,6 +863,8 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_kernel(DevModel M, IpmArgs A) {
           double r0 = 0.0, r1 = 0.0;
           if (!(f & F_FIXED)) {
             double g0 = (j < n) ? of * grad[j] : (phase1 ? 1.0 : 0.0);
+            if (j < n)
+              for (int e = 0; e < E; ++e) g0 = fma(esc[e] * grad[(size_t)M.eq_fn[e] * n + j], ye[e], g0);
             double a0 = 0.0, a1 = 0.0;
             if (j < n) {
               for (int r = 0; r < R; ++r) {
@@ -844,6 +886,56 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_kernel(DevModel M, IpmArgs A) {
       if (!fact_ok) { status = ST_computationError; objv = val[0]; with_duals = true; done = true; break; }
       if (delta_w > 0) delta_w_last = delta_w;
       PH_MARK(3);
+      if (E > 0) {
+        // S = Y Y' (+ tiny regularisation), t0 = Y w0 + c_e, t1 = Y w1: one warp per entry
+        const int w = tid >> 5, lane = tid & 31;
+        for (int p = w; p < E * E + 2 * E; p += IPM_NW) {
+          const double *ra, *rb;
+          if (p < E * E) { ra = H + tri(N + 2 + p / E); rb = H + tri(N + 2 + p % E); }
+          else { const int q = p - E * E; ra = H + tri(N + 2 + (q >> 1)); rb = (q & 1) ? d1 : d0; }
+          double acc = 0.0;
+          for (int j = lane; j < N; j += 32) acc = fma(ra[j], rb[j], acc);
+#pragma unroll
+          for (int q = 16; q > 0; q >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, q);
+          if (lane == 0) {
+            if (p < E * E) Ssc[p] = acc;
+            else { const int q = p - E * E; if (q & 1) de1[q >> 1] = acc; else de0[q >> 1] = acc + ce[q >> 1]; }
+          }
+        }
+        __syncthreads();
+        if (tid == 0) {
+          bool ok = true;
+          for (int a = 0; a < E; ++a) Ssc[a * E + a] += 1e-14 * (1.0 + Ssc[a * E + a]);
+          for (int j = 0; j < E; ++j) {     // Cholesky of the E x E Schur complement
+            double d = Ssc[j * E + j];
+            for (int k = 0; k < j; ++k) d -= Ssc[j * E + k] * Ssc[j * E + k];
+            if (!(d > 0.0)) { ok = false; break; }
+            d = sqrt(d);
+            Ssc[j * E + j] = d;
+            for (int i = j + 1; i < E; ++i) {
+              double vv = Ssc[i * E + j];
+              for (int k = 0; k < j; ++k) vv -= Ssc[i * E + k] * Ssc[j * E + k];
+              Ssc[i * E + j] = vv / d;
+            }
+          }
+          if (ok) {
+            for (int rhs = 0; rhs < 2; ++rhs) {
+              double *t = rhs ? de1 : de0;
+              for (int i = 0; i < E; ++i) { double vv = t[i]; for (int k = 0; k < i; ++k) vv -= Ssc[i * E + k] * t[k]; t[i] = vv / Ssc[i * E + i]; }
+              for (int i = E - 1; i >= 0; --i) { double vv = t[i]; for (int k = i + 1; k < E; ++k) vv -= Ssc[k * E + i] * t[k]; t[i] = vv / Ssc[i * E + i]; }
+            }
+          }
+          s_fail = ok ? 0 : 1;
+        }
+        __syncthreads();
+        if (s_fail) { status = ST_computationError; objv = val[0]; with_duals = true; done = true; break; }
+        for (int j = tid; j < N; j += IPM_NT) {
+          double w0 = d0[j], w1 = d1[j];
+          for (int e = 0; e < E; ++e) { const double yv = H[tri(N + 2 + e) + j]; w0 = fma(-yv, de0[e], w0); w1 = fma(-yv, de1[e], w1); }
+          d0[j] = w0; d1[j] = w1;
+        }
+        __syncthreads();
+      }
       backsolve2(H, N);   // d0 = H^-1 rhs0, d1 = H^-1 rhs1
       PH_MARK(4);
 
@@ -948,6 +1040,10 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_kernel(DevModel M, IpmArgs A) {
           t2[0] += fabs(hv + sv - bb[r]);
           t2[1] -= mu * log(sv);
         }
+        for (int e = tid; e < E; e += IPM_NT) {
+          const int fn = M.eq_fn[e];
+          t2[0] += fabs(esc[e] * (val[fn] + a * gd0[fn] + 0.5 * a * a * du[fn] - M.eq_bnd[e]));
+        }
         for (int j = tid; j < N; j += IPM_NT) {
           const int f = flg[j];
           if (f & F_FIXED) continue;
@@ -1034,6 +1130,7 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_kernel(DevModel M, IpmArgs A) {
         s[r] = sn;
         v[r] = fmin(fmax(v[r] + ad * dv[r], mu / (o.kappa_sigma * sn)), o.kappa_sigma * mu / sn);
       }
+      for (int e = tid; e < E; e += IPM_NT) ye[e] += alpha * (de0[e] + mu * de1[e]);
       for (int k = tid; k <= m; k += IPM_NT) val[k] += alpha * gd0[k] + 0.5 * alpha * alpha * du[k];
       for (int k = 0; k <= m; ++k) {
         if (M.qidx[k] < 0) continue;
@@ -1079,6 +1176,8 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_kernel(DevModel M, IpmArgs A) {
           const int ru = M.fn_row_up[i + 1], rl = M.fn_row_lo[i + 1];
           if (ru >= 0) lam += v[ru] * fsc[ru] / sf;
           if (rl >= 0) lam += v[rl] * fsc[rl] / sf;
+          const int ei = M.fn_eq[i + 1];
+          if (ei >= 0) lam += ye[ei] * esc[ei] / sf;
         }
         D[2 * n + i] = lam;
       }

@@ -154,3 +154,21 @@ def test_size_independent_properties_full_batch(bnlp_lib):
         g = g - r["duals"][b][:n] + r["duals"][b][n:2 * n]
         free = XU[b] > XL[b]
         assert np.abs(g[free]).max() <= 1e-5 * (1 + np.abs(m.A[0]).max())
+
+
+def test_equality_rows_portfolio(bnlp_lib, oracle_ipm):
+    """C5 shape (SYN-PORTFOLIO): a budget EQUALITY row handled through the Schur-complement path of the general kernel;
+    strong-branching children on the binaries z_j."""
+    for N, B in [(20, 60), (200, 48)]:
+        m = I.syn_portfolio(N, 20261022)
+        eng = _engine(m)
+        root = eng.solve_batch(m.xl, m.xu, m.x0)
+        oroot = oracle_ipm.solve_batch(m, m.xl, m.xu, m.x0)
+        _compare(root, oroot)
+        assert abs(root["x"][0][:N].sum() - 1.0) < 1e-6
+        xs = root["x"][0]
+        XL, XU = I.c3_children(m, xs, B)
+        r = eng.solve_batch(XL, XU, xs)
+        o = oracle_ipm.solve_batch(m, XL, XU, xs, threads=8)
+        ok = _compare(r, o)
+        np.testing.assert_allclose(r["duals"][ok][:, 2 * m.n + 1], o["duals"][ok][:, 2 * m.n + 1], rtol=1e-4, atol=1e-6)
