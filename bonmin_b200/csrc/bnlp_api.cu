@@ -163,7 +163,7 @@ static size_t ipm_smem_doubles(int n, int m, int R, int E, int h_in_smem) {
   d += (size_t)(IPM_NW + 1) * npad;
   d += (size_t)7 * npad;
   const int Rp = (R + 1) & ~1, Kp = (m + 2) & ~1;
-  d += (size_t)10 * Rp + (size_t)6 * Kp + (size_t)IPM_NW * 12;
+  d += (size_t)10 * Rp + (size_t)8 * Kp + (size_t)IPM_NW * 12;
   d += (size_t)(((N + 1) & ~1) * 2 + 2 * Kp) / 2 + 2;   // flg, fixlist, qblk, qfn (ints)
   return d;
 }
@@ -256,7 +256,6 @@ extern "C" bnlp_engine *bnlp_engine_create(const bnlp_problem *prob, const int *
   }
   E->R = (int)row_fn.size();
   if (E->E > IPM_MAXE) { E->ipm_supported = false; E->ipm_unsupported_why = "more than 8 equality rows are not supported by the batched IPM yet"; }
-  if (!M.terms.empty()) { E->ipm_supported = false; E->ipm_unsupported_why = "general nonlinear terms are not supported by the batched IPM yet"; }
   if (n > 32 * IPM_MAXC) { E->ipm_supported = false; E->ipm_unsupported_why = "n > 512 is not supported by the batched IPM yet"; }
 
   std::vector<int> ids;
@@ -301,13 +300,15 @@ extern "C" bnlp_engine *bnlp_engine_create(const bnlp_problem *prob, const int *
     dm.c = D.c.p; dm.A = D.A.p; dm.qidx = D.qidx.p; dm.Qp = D.Qp.p; dm.Qf = D.Qf.p;
     dm.row_fn = D.row_fn.p; dm.row_sgn = D.row_sgn.p; dm.row_bnd = D.row_bnd.p;
     dm.fn_row_up = D.fn_row_up.p; dm.fn_row_lo = D.fn_row_lo.p; dm.gl = D.gl.p; dm.gu = D.gu.p;
+    dm.n_terms = D.ev.n_terms; dm.term_fn = D.ev.term_fn; dm.term_var_start = D.ev.term_var_start; dm.term_var = D.ev.term_var;
+    dm.term_op_start = D.ev.term_op_start; dm.term_op = D.ev.term_op; dm.term_iarg = D.ev.term_iarg; dm.term_darg = D.ev.term_darg;
     dm.E = E->E; dm.eq_fn = D.eq_fn.p; dm.eq_bnd = D.eq_bnd.p; dm.fn_eq = D.fn_eq.p;
     if (d == 0) {
       const size_t need = ipm_smem_doubles(n, m, E->R, E->E, 1) * sizeof(double);
       E->h_in_smem = need + 1024 <= D.smem_optin ? 1 : 0;
       E->smem_bytes = ipm_smem_doubles(n, m, E->R, E->E, E->h_in_smem) * sizeof(double);
       if (E->smem_bytes + 1024 > D.smem_optin) { E->ipm_supported = false; E->ipm_unsupported_why = "iterate vectors do not fit shared memory"; }
-      E->ws_doubles = (size_t)2 * (m + 1) * n + (E->h_in_smem ? 0 : (size_t)(n + 3 + E->E) * (n + 4 + E->E) / 2 + 2);
+      E->ws_doubles = (size_t)2 * (m + 1) * n + (size_t)M.terms.size() * (1 + TV + TH) + (E->h_in_smem ? 0 : (size_t)(n + 3 + E->E) * (n + 4 + E->E) / 2 + 2);
       E->ws_doubles = (E->ws_doubles + 1) & ~(size_t)1;
       // cooperative DMMA kernel: needs H in shared memory, n <= 256 and the group weights to fit the staging area
       E->nqpad = (std::max(E->nq, 1) + 3) & ~3;
@@ -316,7 +317,7 @@ extern "C" bnlp_engine *bnlp_engine_create(const bnlp_problem *prob, const int *
       E->coop_smem_bytes = ipm_smem_doubles_coop(n, m, E->R) * sizeof(double);
       int coopAttr = 0;
       cudaDeviceGetAttribute(&coopAttr, cudaDevAttrCooperativeLaunch, D.id);
-      E->coop_ok = E->ipm_supported && coopAttr && n <= 256 && E->nq > 0 && E->E == 0 && E->coop_smem_bytes + 1024 <= D.smem_optin &&
+      E->coop_ok = E->ipm_supported && coopAttr && n <= 256 && E->nq > 0 && E->E == 0 && M.terms.empty() && E->coop_smem_bytes + 1024 <= D.smem_optin &&
                    (size_t)COOP_RB * (E->nqpad + 4) <= (size_t)(IPM_NW + 1) * lds && (size_t)COOP_RB * E->ldd <= (size_t)(IPM_NW + 1) * lds &&
                    !getenv("BNLP_NO_COOP");
     }

@@ -85,7 +85,8 @@ __device__ inline void hd_unary(HDual &a, int nv, double f, double f1, double f2
   a.v = f;
 }
 
-__device__ inline void eval_term(const EvalModelDev &M, int t, const double *x, HDual *st, HDual &out, int order) {
+template <class MM>
+__device__ inline void eval_term(const MM &M, int t, const double *x, HDual *st, HDual &out, int order) {
   const int v0 = M.term_var_start[t], nv = M.term_var_start[t + 1] - v0;
   const int p0 = M.term_op_start[t], p1 = M.term_op_start[t + 1];
   const int nh = order >= 2 ? nv * (nv + 1) / 2 : 0;

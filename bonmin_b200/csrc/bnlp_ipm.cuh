@@ -17,6 +17,8 @@
 #include <cuda_runtime.h>
 #include <math.h>
 
+#include "bnlp_eval.cuh"
+
 namespace bnlp {
 
 constexpr int IPM_NT = 512;           // threads per CTA
@@ -60,6 +62,10 @@ struct DevModel {
   const int *eq_fn;             // E : function index
   const double *eq_bnd;         // E : right-hand side
   const int *fn_eq;             // m+1 : equality index of a function, or -1
+  // general nonlinear element terms (postfix programs, include/bnlp.h); evaluated by eval_term (bnlp_eval.cuh)
+  int n_terms;
+  const int *term_fn, *term_var_start, *term_var, *term_op_start, *term_op, *term_iarg;
+  const double *term_darg;
   const double *gl, *gu;        // m
 };
 
@@ -393,7 +399,9 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_kernel(DevModel M, IpmArgs A) {
   double *ws = A.ws + (size_t)blockIdx.x * A.ws_stride;
   double *grad = ws;                              // (m+1) x n
   double *uq = grad + (size_t)(m + 1) * n;        // (m+1) x n
-  if (A.h_in_smem) { H = sp; sp += (Haug + 1) & ~1; } else { H = uq + (size_t)(m + 1) * n; }
+  const int NTm = M.n_terms;
+  double *tgl = uq + (size_t)(m + 1) * n;          // per term: value, local gradient (TV), packed local Hessian (TH)
+  if (A.h_in_smem) { H = sp; sp += (Haug + 1) & ~1; } else { H = tgl + (size_t)NTm * (1 + TV + TH); }
   double *stage = sp; sp += (IPM_NW + 1) * npad;
   double *x = sp; sp += npad;
   double *zL = sp; sp += npad;
@@ -418,6 +426,8 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_kernel(DevModel M, IpmArgs A) {
   double *gd1 = sp; sp += Kp;
   double *du = sp; sp += Kp;
   double *wq = sp; sp += 2 * Kp;
+  double *tval = sp; sp += Kp;       // element-term values per function at x / at a trial point
+  double *tvt = sp; sp += Kp;
   double *red = sp; sp += IPM_NW * 12;
   double *ye = sp; sp += IPM_MAXE;       // equality multipliers, residuals, scales, step parts, Schur complement
   double *ce = sp; sp += IPM_MAXE;
@@ -524,6 +534,38 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_kernel(DevModel M, IpmArgs A) {
       }
     }
     __syncthreads();
+
+    // ---- element terms: evaluate at x, add values/gradients to val/grad (sgn = +1) or remove the stored ones (-1)
+    auto terms_remove = [&]() {
+      if (NTm == 0) return;
+      for (int t = tid; t < NTm; t += IPM_NT) {
+        const int fn = M.term_fn[t], v0 = M.term_var_start[t], nv = M.term_var_start[t + 1] - v0;
+        const double *rec = tgl + (size_t)t * (1 + TV + TH);
+        for (int a = 0; a < nv; ++a) atomicAdd(&grad[(size_t)fn * n + M.term_var[v0 + a]], -rec[1 + a]);
+      }
+      for (int k = tid; k <= m; k += IPM_NT) val[k] -= tval[k];
+      __syncthreads();
+    };
+    auto terms_add = [&]() {
+      if (NTm == 0) return;
+      for (int k = tid; k <= m; k += IPM_NT) tval[k] = 0.0;
+      __syncthreads();
+      HDual st[TS];
+      HDual r;
+      for (int t = tid; t < NTm; t += IPM_NT) {
+        eval_term(M, t, x, st, r, 2);
+        const int fn = M.term_fn[t], v0 = M.term_var_start[t], nv = M.term_var_start[t + 1] - v0;
+        double *rec = tgl + (size_t)t * (1 + TV + TH);
+        rec[0] = r.v;
+        for (int a = 0; a < nv; ++a) { rec[1 + a] = r.g[a]; atomicAdd(&grad[(size_t)fn * n + M.term_var[v0 + a]], r.g[a]); }
+        for (int a = 0; a < nv * (nv + 1) / 2; ++a) rec[1 + TV + a] = r.h[a];
+        atomicAdd(&tval[fn], r.v);
+      }
+      __syncthreads();
+      for (int k = tid; k <= m; k += IPM_NT) val[k] += tval[k];
+      __syncthreads();
+    };
+    terms_add();
 
     int status = 0;
     int iters = 0;
@@ -813,6 +855,20 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_kernel(DevModel M, IpmArgs A) {
           for (int k = tid; k <= n; k += IPM_NT) H[tri(n) + k] = 0.0;
         }
         __syncthreads();
+        if (NTm > 0) {   // + sum_t w_fn(t) * Hessian of term t (stored at the last evaluation)
+          for (int t = tid; t < NTm; t += IPM_NT) {
+            const int fn = M.term_fn[t], v0 = M.term_var_start[t], nv = M.term_var_start[t + 1] - v0;
+            const double wgt = wq[fn];
+            if (wgt == 0.0) continue;
+            const double *rec = tgl + (size_t)t * (1 + TV + TH) + 1 + TV;
+            for (int a = 0; a < nv; ++a)
+              for (int b = 0; b <= a; ++b) {
+                const int i = M.term_var[v0 + a], j = M.term_var[v0 + b];
+                atomicAdd(&H[tri(max(i, j)) + min(i, j)], wgt * rec[a * (a + 1) / 2 + b]);
+              }
+          }
+          __syncthreads();
+        }
         // fixed variables: identity rows/columns; then the diagonal Sigma_x + delta_w
         for (int e = tid; e < nfix * N; e += IPM_NT) {
           const int j = fixlist[e / N], t = e % N;
@@ -1022,6 +1078,18 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_kernel(DevModel M, IpmArgs A) {
       }
       for (int k = tid; k <= m; k += IPM_NT) gd0[k] = gd0[k] + mu * gd1[k];   // gd = grad_k . dx
       __syncthreads();
+      const double gd_obj_total = gd0[0];   // directional derivative of f uses the total gradient
+      if (NTm > 0) {   // the closed-form trial values use the quadratic part only: remove the terms' share of grad.dx
+        __syncthreads();
+        for (int t = tid; t < NTm; t += IPM_NT) {
+          const int fn = M.term_fn[t], v0 = M.term_var_start[t], nv = M.term_var_start[t + 1] - v0;
+          const double *rec = tgl + (size_t)t * (1 + TV + TH);
+          double acc = 0.0;
+          for (int a = 0; a < nv; ++a) acc = fma(rec[1 + a], dx[M.term_var[v0 + a]], acc);
+          atomicAdd(&gd0[fn], -acc);
+        }
+        __syncthreads();
+      }
 
       PH_MARK(5);
       // ---------------------------------------------------------------- u_k = Q_k dx, du_k = dx.u_k
@@ -1033,16 +1101,28 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_kernel(DevModel M, IpmArgs A) {
       auto merit = [&](double a, double &theta, double &phi) {
         double t2[2] = {0.0, 0.0};
         const double t = tcur + a * dxt;
+        if (NTm > 0) {   // element terms at the trial point (values only); Sx is free here and holds x + a dx
+          for (int k = tid; k <= m; k += IPM_NT) tvt[k] = -tval[k];
+          for (int j = tid; j < n; j += IPM_NT) Sx[j] = x[j] + a * dx[j];
+          __syncthreads();
+          HDual st[TS];
+          HDual r;
+          for (int tt = tid; tt < NTm; tt += IPM_NT) {
+            eval_term(M, tt, Sx, st, r, 0);
+            atomicAdd(&tvt[M.term_fn[tt]], r.v);
+          }
+          __syncthreads();
+        }
         for (int r = tid; r < R; r += IPM_NT) {
           const int fn = M.row_fn[r];
-          const double hv = fsc[r] * (val[fn] + a * gd0[fn] + 0.5 * a * a * du[fn]) - t;
+          const double hv = fsc[r] * (val[fn] + a * gd0[fn] + 0.5 * a * a * du[fn] + (NTm > 0 ? tvt[fn] : 0.0)) - t;
           const double sv = s[r] + a * ds[r];
           t2[0] += fabs(hv + sv - bb[r]);
           t2[1] -= mu * log(sv);
         }
         for (int e = tid; e < E; e += IPM_NT) {
           const int fn = M.eq_fn[e];
-          t2[0] += fabs(esc[e] * (val[fn] + a * gd0[fn] + 0.5 * a * a * du[fn] - M.eq_bnd[e]));
+          t2[0] += fabs(esc[e] * (val[fn] + a * gd0[fn] + 0.5 * a * a * du[fn] + (NTm > 0 ? tvt[fn] : 0.0) - M.eq_bnd[e]));
         }
         for (int j = tid; j < N; j += IPM_NT) {
           const int f = flg[j];
@@ -1053,7 +1133,7 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_kernel(DevModel M, IpmArgs A) {
         }
         block_reduce<2, 0>(t2, red);
         theta = t2[0];
-        phi = t2[1] + (phase1 ? t : sf * (val[0] + a * gd0[0] + 0.5 * a * a * du[0]));
+        phi = t2[1] + (phase1 ? t : sf * (val[0] + a * gd0[0] + 0.5 * a * a * du[0] + (NTm > 0 ? tvt[0] : 0.0)));
       };
       double theta0, phi0;
       merit(0.0, theta0, phi0);
@@ -1068,7 +1148,7 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_kernel(DevModel M, IpmArgs A) {
           if (f & F_HASU) t[0] += mu * dx[j] / (Ur[j] - x[j]);
         }
         block_reduce<1, 0>(t, red);
-        dphi = t[0] + (phase1 ? dxt : sf * gd0[0]);
+        dphi = t[0] + (phase1 ? dxt : sf * gd_obj_total);
       }
       const double theta_min = o.theta_min_fact * fmax(1.0, theta_init);
       const double theta_max = o.theta_max_fact * fmax(1.0, theta_init);
@@ -1105,6 +1185,7 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_kernel(DevModel M, IpmArgs A) {
       PH_MARK(7);
       // ---------------------------------------------------------------- accept the step
       __syncthreads();
+      terms_remove();
       for (int j = tid; j < N; j += IPM_NT) {
         const int f = flg[j];
         if (f & F_FIXED) continue;
@@ -1139,6 +1220,7 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_kernel(DevModel M, IpmArgs A) {
         for (int j = tid; j < n; j += IPM_NT) g[j] += alpha * u[j];
       }
       __syncthreads();
+      terms_add();
       ++iters;
       PH_MARK(8);
     }

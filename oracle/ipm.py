@@ -59,8 +59,6 @@ def _p(a, t=ctypes.c_double):
 
 
 def solve_batch(model, XL, XU, x0, threads=1, max_iter=0, dense=None):
-    if model.get("terms"):
-        raise NotImplementedError("oracle IPM: general nonlinear terms are not restated yet")
     n, m = model.n, model.m
     XL = np.ascontiguousarray(np.atleast_2d(XL), dtype=np.float64)
     XU = np.ascontiguousarray(np.atleast_2d(XU), dtype=np.float64)
@@ -80,7 +78,21 @@ def solve_batch(model, XL, XU, x0, threads=1, max_iter=0, dense=None):
     G = np.zeros((B, max(m, 1)))[:, :m].copy() if m else np.zeros((B, 0))
     D = np.zeros((B, 2 * n + m))
     ci = ctypes.c_int
+    tfn, tvs, tv, tos, top, tia, tda = [], [0], [], [0], [], [], []
+    for fn, vars_, prog in model.get("terms", []):
+        tfn.append(fn)
+        tv.extend(vars_)
+        tvs.append(len(tv))
+        for op, ia, da in prog:
+            top.append(op)
+            tia.append(ia)
+            tda.append(da)
+        tos.append(len(top))
+    ti = lambda a: np.ascontiguousarray(a if len(a) else [0], dtype=np.int32)  # noqa: E731
+    tfn_a, tvs_a, tv_a, tos_a, top_a, tia_a = ti(tfn), ti(tvs), ti(tv), ti(tos), ti(top), ti(tia)
+    tda_a = np.ascontiguousarray(tda if len(tda) else [0.0], dtype=np.float64)
     lib().oracle_solve_batch(ci(n), ci(m), _p(xl), _p(xu), _p(gl), _p(gu), _p(c), _p(A), _p(qidx, ci), _p(Q),
-                             ci(B), _p(XL), _p(XU), _p(x0), ci(per_child), ci(threads), ci(max_iter),
+                             ci(len(tfn)), _p(tfn_a, ci), _p(tvs_a, ci), _p(tv_a, ci), _p(tos_a, ci), _p(top_a, ci),
+                             _p(tia_a, ci), _p(tda_a), ci(B), _p(XL), _p(XU), _p(x0), ci(per_child), ci(threads), ci(max_iter),
                              _p(OBJ), _p(STATUS, ci), _p(ITERS, ci), _p(X), _p(G), _p(D), _p(P1, ci))
     return dict(obj=OBJ, status=STATUS, iters=ITERS, x=X, g=G, duals=D, phase1_iters=P1)

@@ -56,7 +56,73 @@ struct OModel {
   const double *A;                  // (m+1) x n dense linear part
   const int *qidx;                  // m+1: index of the dense quadratic block or -1
   const double *Q;                  // nq x n x n symmetric, convention 1/2 x'Qx
+  // general nonlinear element terms phi_t(x[vars]) added to function term_fn[t]: postfix programs (include/bnlp.h)
+  int n_terms = 0;
+  const int *term_fn = nullptr, *term_var_start = nullptr, *term_var = nullptr, *term_op_start = nullptr,
+            *term_op = nullptr, *term_iarg = nullptr;
+  const double *term_darg = nullptr;
 };
+
+// second-order forward mode over the (<= 6) local variables of a term
+constexpr int TVm = 6;
+struct HD { double v; double g[TVm]; double h[TVm][TVm]; };
+enum { OP_CONST = 0, OP_VAR, OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_NEG, OP_POWC, OP_POW, OP_EXP, OP_LOG, OP_SQRT, OP_SIN,
+       OP_COS, OP_SQR, OP_ABS };
+static void hd_unary(HD &a, int nv, double f, double f1, double f2) {
+  for (int i = 0; i < nv; ++i)
+    for (int j = 0; j < nv; ++j) a.h[i][j] = f2 * a.g[i] * a.g[j] + f1 * a.h[i][j];
+  for (int i = 0; i < nv; ++i) a.g[i] *= f1;
+  a.v = f;
+}
+static void hd_mul(HD &a, const HD &b, int nv) {
+  for (int i = 0; i < nv; ++i)
+    for (int j = 0; j < nv; ++j) a.h[i][j] = a.v * b.h[i][j] + b.v * a.h[i][j] + a.g[i] * b.g[j] + a.g[j] * b.g[i];
+  for (int i = 0; i < nv; ++i) a.g[i] = a.v * b.g[i] + b.v * a.g[i];
+  a.v *= b.v;
+}
+static HD eval_term(const OModel &M, int t, const double *x) {
+  const int v0 = M.term_var_start[t], nv = M.term_var_start[t + 1] - v0;
+  HD st[16];
+  int sp = 0;
+  for (int p = M.term_op_start[t]; p < M.term_op_start[t + 1]; ++p) {
+    const int op = M.term_op[p];
+    if (op == OP_CONST || op == OP_VAR) {
+      HD &z = st[sp++];
+      std::memset(&z, 0, sizeof(HD));
+      if (op == OP_CONST) z.v = M.term_darg[p];
+      else { z.v = x[M.term_var[v0 + M.term_iarg[p]]]; z.g[M.term_iarg[p]] = 1.0; }
+    } else if (op == OP_ADD || op == OP_SUB || op == OP_MUL || op == OP_DIV || op == OP_POW) {
+      HD &b = st[sp - 1];
+      HD &a = st[sp - 2];
+      --sp;
+      if (op == OP_ADD || op == OP_SUB) {
+        const double sg = op == OP_ADD ? 1.0 : -1.0;
+        a.v += sg * b.v;
+        for (int i = 0; i < nv; ++i) { a.g[i] += sg * b.g[i]; for (int j = 0; j < nv; ++j) a.h[i][j] += sg * b.h[i][j]; }
+      } else if (op == OP_MUL) hd_mul(a, b, nv);
+      else if (op == OP_DIV) { const double r = 1.0 / b.v; hd_unary(b, nv, r, -r * r, 2 * r * r * r); hd_mul(a, b, nv); }
+      else { const double la = std::log(a.v); hd_unary(a, nv, la, 1.0 / a.v, -1.0 / (a.v * a.v)); hd_mul(a, b, nv);
+             const double e = std::exp(a.v); hd_unary(a, nv, e, e, e); }
+    } else {
+      HD &a = st[sp - 1];
+      const double v = a.v;
+      switch (op) {
+        case OP_NEG: hd_unary(a, nv, -v, -1.0, 0.0); break;
+        case OP_SQR: hd_unary(a, nv, v * v, 2 * v, 2.0); break;
+        case OP_POWC: { const double p_ = M.term_darg[p];
+                        hd_unary(a, nv, std::pow(v, p_), p_ == 0 ? 0.0 : p_ * std::pow(v, p_ - 1),
+                                 (p_ == 0 || p_ == 1) ? 0.0 : p_ * (p_ - 1) * std::pow(v, p_ - 2)); break; }
+        case OP_EXP: { const double e = std::exp(v); hd_unary(a, nv, e, e, e); break; }
+        case OP_LOG: hd_unary(a, nv, std::log(v), 1.0 / v, -1.0 / (v * v)); break;
+        case OP_SQRT: { const double q = std::sqrt(v); hd_unary(a, nv, q, 0.5 / q, -0.25 / (q * v)); break; }
+        case OP_SIN: hd_unary(a, nv, std::sin(v), std::cos(v), -std::sin(v)); break;
+        case OP_COS: hd_unary(a, nv, std::cos(v), -std::sin(v), -std::cos(v)); break;
+        case OP_ABS: hd_unary(a, nv, std::fabs(v), v >= 0 ? 1.0 : -1.0, 0.0); break;
+      }
+    }
+  }
+  return st[0];
+}
 
 struct OOpt {
   double tol = 1e-8, acceptable_tol = 1e-6;
@@ -125,6 +191,8 @@ struct Solver {
   std::vector<Row> rows, eqs;
   std::vector<double> val, grad;      // raw function values (m+1) and gradients (m+1) x n
   std::vector<double> uq, gd, du;     // Q_k dx, grad_k.dx, dx.Q_k dx per function
+  std::vector<double> tval;           // (m+1) sum of element-term values per function at x (val = quadratic part + tval)
+  std::vector<HD> tcur;               // per term: value / gradient / Hessian at x
   std::vector<double> x, s, v, zL, zU, ye;
   std::vector<double> h, J, ce, Ae;   // scaled one-sided rows, R x N Jacobian; equalities E x N
   double sf = 1.0;
@@ -152,6 +220,26 @@ struct Solver {
       }
       val[k] = vv;
     }
+    add_terms(+1.0);
+  }
+  // evaluate the element terms at x and add (sgn=+1) them to val/grad; remove_terms() undoes the previous addition
+  void add_terms(double) {
+    tval.assign(m + 1, 0.0);
+    tcur.resize(M.n_terms);
+    for (int t = 0; t < M.n_terms; ++t) {
+      tcur[t] = eval_term(M, t, x.data());
+      const int fn = M.term_fn[t], v0 = M.term_var_start[t], nv = M.term_var_start[t + 1] - v0;
+      tval[fn] += tcur[t].v;
+      for (int a = 0; a < nv; ++a) grad[(size_t)fn * n + M.term_var[v0 + a]] += tcur[t].g[a];
+    }
+    for (int k = 0; k <= m; ++k) val[k] += tval[k];
+  }
+  void remove_terms() {
+    for (int t = 0; t < M.n_terms; ++t) {
+      const int fn = M.term_fn[t], v0 = M.term_var_start[t], nv = M.term_var_start[t + 1] - v0;
+      for (int a = 0; a < nv; ++a) grad[(size_t)fn * n + M.term_var[v0 + a]] -= tcur[t].g[a];
+    }
+    for (int k = 0; k <= m; ++k) val[k] -= tval[k];
   }
   void build_rows_values() {  // h, J, ce, Ae from raw val/grad (+ elastic column)
     for (int r = 0; r < R; ++r) {
@@ -462,6 +550,21 @@ int Solver::run(const double *xl, const double *xu, const double *x0, double *ob
       addQ(0, of);
       for (int r = 0; r < R; ++r) addQ(rows[r].fn, v[r] * rows[r].sc * rows[r].sgn);
       for (int e = 0; e < E; ++e) addQ(eqs[e].fn, ye[e] * eqs[e].sc);
+      if (M.n_terms > 0) {
+        std::vector<double> wfn(m + 1, 0.0);
+        wfn[0] = of;
+        for (int r = 0; r < R; ++r) wfn[rows[r].fn] += v[r] * rows[r].sc * rows[r].sgn;
+        for (int e = 0; e < E; ++e) wfn[eqs[e].fn] += ye[e] * eqs[e].sc;
+        for (int t = 0; t < M.n_terms; ++t) {
+          const int fn = M.term_fn[t], v0 = M.term_var_start[t], nv = M.term_var_start[t + 1] - v0;
+          if (wfn[fn] == 0.0) continue;
+          for (int a = 0; a < nv; ++a)
+            for (int b = 0; b < nv; ++b) {
+              const int i = M.term_var[v0 + a], j = M.term_var[v0 + b];
+              if (j <= i) H[(size_t)i * N + j] += wfn[fn] * tcur[t].h[a][b];
+            }
+        }
+      }
       for (int r = 0; r < R; ++r) {
         const double *Jr = &J[(size_t)r * N];
         double w = Ss[r];
@@ -609,22 +712,36 @@ int Solver::run(const double *xl, const double *xu, const double *x0, double *ob
       for (int i = 0; i < n; ++i) a += g[i] * dx[i];
       gd[k] = a; du[k] = b;
     }
+    // closed-form trial values use the quadratic part only: remove the terms' share of grad.dx
+    for (int t = 0; t < M.n_terms; ++t) {
+      const int fn = M.term_fn[t], v0 = M.term_var_start[t], nv = M.term_var_start[t + 1] - v0;
+      for (int a = 0; a < nv; ++a) gd[fn] -= tcur[t].g[a] * dx[M.term_var[v0 + a]];
+    }
+    std::vector<double> tvt(m + 1, 0.0), xt(M.n_terms > 0 ? n : 0);
+    auto trial_terms = [&](double a) {   // sum of element-term values per function at x + a dx
+      std::fill(tvt.begin(), tvt.end(), 0.0);
+      if (M.n_terms == 0) return;
+      for (int j = 0; j < n; ++j) xt[j] = x[j] + a * dx[j];
+      for (int t = 0; t < M.n_terms; ++t) tvt[M.term_fn[t]] += eval_term(M, t, xt.data()).v;
+    };
 
     // ---- filter line search on (theta, phi_mu) against the current iterate
+    auto fval = [&](int k, double a) { return val[k] - tval[k] + a * gd[k] + 0.5 * a * a * du[k] + tvt[k]; };
     auto merit = [&](double a, double &theta, double &phi) {
       double t = phase1 ? x[n] + a * dx[n] : 0.0;
+      trial_terms(a);
       theta = 0;
-      phi = phase1 ? t : sf * (val[0] + a * gd[0] + 0.5 * a * a * du[0]);
+      phi = phase1 ? t : sf * fval(0, a);
       for (int r = 0; r < R; ++r) {
         const Row &w = rows[r];
-        double hv = w.sc * w.sgn * (val[w.fn] + a * gd[w.fn] + 0.5 * a * a * du[w.fn]) - t;
+        double hv = w.sc * w.sgn * fval(w.fn, a) - t;
         double sv = s[r] + a * ds[r];
         theta += std::fabs(hv + sv - w.b);
         phi -= mu * std::log(sv);
       }
       for (int e = 0; e < E; ++e) {
         const Row &w = eqs[e];
-        theta += std::fabs(w.sc * (val[w.fn] + a * gd[w.fn] + 0.5 * a * a * du[w.fn] - w.b));
+        theta += std::fabs(w.sc * (fval(w.fn, a) - w.b));
       }
       for (int j = 0; j < N; ++j) {
         if (fixed[j]) continue;
@@ -635,7 +752,13 @@ int Solver::run(const double *xl, const double *xu, const double *x0, double *ob
     };
     double theta0, phi0;
     merit(0.0, theta0, phi0);
-    double dphi = phase1 ? dx[n] : sf * gd[0];
+    double gd0_total = gd[0];
+    for (int t = 0; t < M.n_terms; ++t)
+      if (M.term_fn[t] == 0) {
+        const int v0 = M.term_var_start[t], nv = M.term_var_start[t + 1] - v0;
+        for (int a = 0; a < nv; ++a) gd0_total += tcur[t].g[a] * dx[M.term_var[v0 + a]];
+      }
+    double dphi = phase1 ? dx[n] : sf * gd0_total;
     for (int r = 0; r < R; ++r) dphi -= mu * ds[r] / s[r];
     for (int j = 0; j < N; ++j) {
       if (fixed[j]) continue;
@@ -688,6 +811,7 @@ int Solver::run(const double *xl, const double *xu, const double *x0, double *ob
     }
     for (int r = 0; r < R; ++r) { s[r] += alpha * ds[r]; v[r] += ad * dv[r]; }
     for (int e = 0; e < E; ++e) ye[e] += alpha * dye[e];
+    if (M.n_terms > 0) remove_terms();
     for (int k = 0; k <= m; ++k) {
       val[k] += alpha * gd[k] + 0.5 * alpha * alpha * du[k];
       if (M.qidx[k] >= 0) {
@@ -696,6 +820,7 @@ int Solver::run(const double *xl, const double *xu, const double *x0, double *ob
         for (int i = 0; i < n; ++i) g[i] += alpha * u[i];
       }
     }
+    if (M.n_terms > 0) add_terms(+1.0);
     build_rows_values();
     // keep bound multipliers within [mu/(kappa s), kappa mu/s] (kappa_sigma 1e10, L3022)
     for (int j = 0; j < N; ++j) {
@@ -716,11 +841,15 @@ void oracle_set_verbose(int v) { g_verbose = v; }
 // or per-child X0 [B x n] when x0_per_child != 0) on `threads` host threads.
 // Outputs follow TMINLP2TNLP's result layout (BonTMINLP2TNLP.cpp:474-509).
 int oracle_solve_batch(int n, int m, const double *xl, const double *xu, const double *gl, const double *gu,
-                       const double *c, const double *A, const int *qidx, const double *Q, int B,
+                       const double *c, const double *A, const int *qidx, const double *Q, int n_terms,
+                       const int *term_fn, const int *term_var_start, const int *term_var, const int *term_op_start,
+                       const int *term_op, const int *term_iarg, const double *term_darg, int B,
                        const double *XL, const double *XU, const double *X0, int x0_per_child, int threads,
                        int max_iter, double *OBJ, int *STATUS, int *ITERS, double *X, double *G, double *DUALS,
                        int *P1ITERS) {
   OModel M{n, m, xl, xu, gl, gu, c, A, qidx, Q};
+  M.n_terms = n_terms; M.term_fn = term_fn; M.term_var_start = term_var_start; M.term_var = term_var;
+  M.term_op_start = term_op_start; M.term_op = term_op; M.term_iarg = term_iarg; M.term_darg = term_darg;
   OOpt opt;
   if (max_iter > 0) opt.max_iter = max_iter;
   std::atomic<int> next(0);

@@ -172,3 +172,25 @@ def test_equality_rows_portfolio(bnlp_lib, oracle_ipm):
         o = oracle_ipm.solve_batch(m, XL, XU, xs, threads=8)
         ok = _compare(r, o)
         np.testing.assert_allclose(r["duals"][ok][:, 2 * m.n + 1], o["duals"][ok][:, 2 * m.n + 1], rtol=1e-4, atol=1e-6)
+
+
+def test_element_terms_cvx_minlp(bnlp_lib, oracle_ipm):
+    """C4 shape (SYN-CVX-MINLP): exp() element terms + dense rank-4 quadratics + big-M rows; the NLP(y) solves of
+    OA / node NLPs go through the general kernel (element terms evaluated by the second-order stack machine)."""
+    for args, B in [((30, 10, 5, 8, 3), 40), ((120, 40, 20, 25, 5), 64)]:
+        m = I.syn_cvx_minlp(*args)
+        eng = _engine(m)
+        root = eng.solve_batch(m.xl, m.xu, m.x0)
+        oroot = oracle_ipm.solve_batch(m, m.xl, m.xu, m.x0)
+        _compare(root, oroot)
+        assert root["status"][0] == 1
+        xs = root["x"][0]
+        XL, XU = I.c3_children(m, xs, B)
+        # a few children with all binaries fixed (the NLP(y) of OACutGenerator2::performOa)
+        nb = args[1]
+        XL[:4, :nb] = XU[:4, :nb] = np.round(xs[:nb])
+        r = eng.solve_batch(XL, XU, xs)
+        o = oracle_ipm.solve_batch(m, XL, XU, xs, threads=8)
+        ok = _compare(r, o)
+        assert ok.sum() >= B // 3
+        np.testing.assert_allclose(r["x"][ok], o["x"][ok], atol=1e-5)

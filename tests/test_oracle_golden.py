@@ -118,3 +118,26 @@ def test_threads_agree(oracle_ipm):
     a = oracle_ipm.solve_batch(m, XL, XU, root["x"][0], threads=1)
     b = oracle_ipm.solve_batch(m, XL, XU, root["x"][0], threads=4)
     assert (a["status"] == b["status"]).all() and np.array_equal(a["obj"], b["obj"])
+
+
+def test_oracle_terms_and_equalities_against_scipy(oracle_ipm):
+    """Element terms (exp) and an equality row: the oracle against SLSQP."""
+    from scipy.optimize import minimize
+    from oracle.struct_eval import Evaluator
+    m = I.syn_cvx_minlp(20, 6, 4, 6, 7)
+    ev = Evaluator(m)
+    r = oracle_ipm.solve_batch(m, m.xl, m.xu, m.x0)
+    assert r["status"][0] == 1
+    cons = [{"type": "ineq", "fun": (lambda x, i=i: m.gu[i] - ev.dense(x)[0][i + 1])} for i in range(m.m)]
+    res = minimize(lambda x: ev.dense(x)[0][0], m.x0, bounds=list(zip(m.xl, m.xu)), constraints=cons, method="SLSQP",
+                   options={"ftol": 1e-12, "maxiter": 300})
+    assert abs(res.fun - r["obj"][0]) <= 1e-6 * max(1.0, abs(res.fun))
+    p = I.syn_portfolio(12, 5)
+    rp = oracle_ipm.solve_batch(p, p.xl, p.xu, p.x0)
+    assert rp["status"][0] == 1 and abs(rp["x"][0][:12].sum() - 1.0) < 1e-6
+    evp = Evaluator(p)
+    consp = [{"type": "ineq", "fun": (lambda x, i=i: p.gu[i] - evp.dense(x)[0][i + 1])} for i in range(p.m) if i != 1]
+    consp.append({"type": "eq", "fun": lambda x: x[:12].sum() - 1.0})
+    resp = minimize(lambda x: evp.dense(x)[0][0], p.x0, bounds=list(zip(p.xl, p.xu)), constraints=consp,
+                    method="SLSQP", options={"ftol": 1e-12, "maxiter": 300})
+    assert abs(resp.fun - rp["obj"][0]) <= 1e-6 * max(1.0, abs(resp.fun))
