@@ -132,6 +132,12 @@ def bb_section(args, local_rank):
         "optimum_cpu": c["best_obj"], "same_optimum_1e-6": bool(abs(g["best_obj"] - c["best_obj"]) <= 1e-6 * max(1.0, abs(c["best_obj"]))),
         "status": g["status"], "nodes": g["nodes"], "child_nlps": g["sb_children"], "ipm_iterations": g["ipm_iterations"],
         "served_from_sb_cache": g["served_from_sb_cache"]}
+    # the same search with 32 best-bound nodes expanded per round: all their strong-branching children in ONE launch
+    g32 = bb.run_engine(eng, **dict(kw, parallel_nodes=32))
+    out["to_optimum_32_nodes_per_round"] = {
+        "gpu_wall_s": g32["seconds"], "optimum_gpu": g32["best_obj"], "nodes": g32["nodes"], "launch_rounds": g32["sb_batches"],
+        "child_nlps": g32["sb_children"],
+        "same_optimum_1e-6": bool(abs(g32["best_obj"] - c["best_obj"]) <= 1e-6 * max(1.0, abs(c["best_obj"])))}
     eng.close()
     m = I.config_c2()
     eng = Engine(Problem.from_model(m), devices=[local_rank])

@@ -16,7 +16,8 @@ P_int, P_dbl = ctypes.POINTER(c_int), ctypes.POINTER(c_dbl)
 
 class BbOptions(ctypes.Structure):
     _fields_ = [("number_strong_branch", c_int), ("number_before_trust", c_int), ("node_limit", c_int),
-                ("log_level", c_int), ("integer_tolerance", c_dbl), ("cutoff_decr", c_dbl), ("time_limit", c_dbl)]
+                ("log_level", c_int), ("integer_tolerance", c_dbl), ("cutoff_decr", c_dbl), ("time_limit", c_dbl),
+                ("parallel_nodes", c_int)]
 
 
 class BbResult(ctypes.Structure):
@@ -43,8 +44,8 @@ def host_lib():
     return _host
 
 
-def _opts(number_strong_branch=0, number_before_trust=0, node_limit=0, time_limit=0.0):
-    return BbOptions(number_strong_branch, number_before_trust, node_limit, 0, 0.0, 0.0, time_limit)
+def _opts(number_strong_branch=0, number_before_trust=0, node_limit=0, time_limit=0.0, parallel_nodes=0):
+    return BbOptions(number_strong_branch, number_before_trust, node_limit, 0, 0.0, 0.0, time_limit, parallel_nodes)
 
 
 def run_engine(eng: "_e.Engine", **kw):

@@ -52,7 +52,38 @@ void BatchedStrongBranchingSolver::markHotStart(OsiTMINLPInterface *si) {
   const int n = si->getNumCols();
   xl0_.assign(si->getColLower(), si->getColLower() + n);
   xu0_.assign(si->getColUpper(), si->getColUpper() + n);
-  cache_.clear();
+  if (!preloaded_) cache_.clear();
+}
+
+void BatchedStrongBranchingSolver::prefetchMany(OsiTMINLPInterface *si, const std::vector<NodeRequest> &reqs) {
+  const int n = si->getNumCols();
+  size_t total = 0;
+  for (auto &r : reqs) total += 2 * r.cols.size();
+  std::vector<double> XL(total * n), XU(total * n);
+  size_t row = 0;
+  for (auto &r : reqs)
+    for (size_t i = 0; i < r.cols.size(); ++i)
+      for (int w = 0; w < 2; ++w, ++row) {
+        std::copy(r.xl.begin(), r.xl.end(), &XL[row * n]);
+        std::copy(r.xu.begin(), r.xu.end(), &XU[row * n]);
+        if (w == 0) XU[row * n + r.cols[i]] = r.down_ub[i]; else XL[row * n + r.cols[i]] = r.up_lb[i];
+      }
+  std::vector<B200Solver::Child> res;
+  if (total) app_->OptimizeBatch(*si->problem(), XL, XU, (int)total, res);
+  multi_.assign(reqs.size(), {});
+  multi_bounds_.clear();
+  row = 0;
+  for (size_t q = 0; q < reqs.size(); ++q) {
+    multi_bounds_.push_back({reqs[q].xl, reqs[q].xu});
+    for (size_t i = 0; i < reqs[q].cols.size(); ++i)
+      for (int w = 0; w < 2; ++w, ++row) multi_[q][{reqs[q].cols[i], w}] = std::move(res[row]);
+  }
+}
+
+void BatchedStrongBranchingSolver::useNode(int i) {
+  cache_ = std::move(multi_[i]);
+  xl0_ = multi_bounds_[i].first; xu0_ = multi_bounds_[i].second;
+  preloaded_ = true;
 }
 
 void BatchedStrongBranchingSolver::prefetch(OsiTMINLPInterface *si, const std::vector<int> &cols,
@@ -100,7 +131,7 @@ TNLPSolver::ReturnStatus BatchedStrongBranchingSolver::solveFromHotStart(OsiTMIN
   return c->status;
 }
 
-void BatchedStrongBranchingSolver::unmarkHotStart(OsiTMINLPInterface *) {}
+void BatchedStrongBranchingSolver::unmarkHotStart(OsiTMINLPInterface *) { preloaded_ = false; }
 
 int BatchedChooseVariable::doStrongBranching(const std::vector<int> &cols, double parent_obj,
                                              std::vector<StrongResult> &results) {
@@ -109,7 +140,7 @@ int BatchedChooseVariable::doStrongBranching(const std::vector<int> &cols, doubl
   std::vector<double> dn(K), up(K);
   for (int i = 0; i < K; ++i) { dn[i] = std::floor(xsol[cols[i]]); up[i] = std::ceil(xsol[cols[i]]); }
   si_->markHotStart();                                   // :799
-  sb_->prefetch(si_, cols, dn, up);                      // ONE batch of 2K children (Appendix C)
+  if (!sb_->preloaded()) sb_->prefetch(si_, cols, dn, up);   // ONE batch of 2K children (Appendix C)
   results.assign(K, StrongResult());
   int returnCode = 0;
   for (int iDo = 0; iDo < K; ++iDo) {                    // :807-948, unchanged control flow
@@ -202,7 +233,111 @@ BbResult bb_run(TMINLP2TNLP &root, BatchSolveFn solve, const BbOptions &opt) {
   double cutoff = 1e100;
   const std::vector<double> xl_root = root.x_l, xu_root = root.x_u;
 
-  while (dive || !heap.empty()) {
+  if (opt.parallel_nodes > 1) {
+    // ---- round-based expansion: the P best open nodes per round; their node NLPs are one batch and the strong-
+    // branching children of all of them are one batch (independent relaxations sharing tape and start point)
+    heap.push(first);
+    dive = nullptr;
+    auto candidates_of = [&](const std::vector<double> &x) {
+      std::vector<std::pair<double, int>> frac;
+      for (int j : ints) {
+        const double f = std::fabs(x[j] - std::round(x[j]));
+        if (f > opt.integer_tolerance) frac.push_back({-f, j});
+      }
+      std::sort(frac.begin(), frac.end());
+      return frac;
+    };
+    while (!heap.empty()) {
+      if (R.nodes >= opt.node_limit || now_s() - t0 > opt.time_limit) { R.status = 2; break; }
+      std::vector<Node *> batch;
+      while (!heap.empty() && (int)batch.size() < opt.parallel_nodes) {
+        Node *nd = heap.top(); heap.pop();
+        if (nd->bound >= cutoff) { delete nd; continue; }
+        batch.push_back(nd);
+      }
+      if (batch.empty()) break;
+      // 1. node relaxations that were not pre-solved by strong branching
+      std::vector<int> need;
+      for (size_t i = 0; i < batch.size(); ++i) if (!batch[i]->solved) need.push_back((int)i);
+      if (!need.empty()) {
+        std::vector<double> XL(need.size() * n), XU(need.size() * n);
+        for (size_t q = 0; q < need.size(); ++q) {
+          std::copy(batch[need[q]]->xl.begin(), batch[need[q]]->xl.end(), &XL[q * n]);
+          std::copy(batch[need[q]]->xu.begin(), batch[need[q]]->xu.end(), &XU[q * n]);
+        }
+        std::vector<B200Solver::Child> res;
+        app.OptimizeBatch(root, XL, XU, (int)need.size(), res);
+        R.nlp_solves += (int)need.size();
+        for (size_t q = 0; q < need.size(); ++q) {
+          Node *nd = batch[need[q]];
+          nd->solved = true; nd->obj = res[q].obj; nd->status = (int)res[q].status; nd->x = res[q].x;
+        }
+      } 
+      // 2. fathoming, incumbents, candidate lists
+      std::vector<Node *> open;
+      std::vector<BatchedStrongBranchingSolver::NodeRequest> reqs;
+      for (Node *nd : batch) {
+        R.nodes++;
+        R.served_from_sb_cache += (nd != first && need.empty());
+        const bool optimal = nd->status == TNLPSolver::solvedOptimal || nd->status == TNLPSolver::solvedOptimalTol;
+        if (!optimal || nd->obj >= cutoff) { delete nd; continue; }
+        auto frac = candidates_of(nd->x);
+        if (frac.empty()) {
+          if (nd->obj < R.best_obj) { R.best_obj = nd->obj; R.best_x = nd->x; cutoff = nd->obj - opt.cutoff_decr; }
+          delete nd;
+          continue;
+        }
+        BatchedStrongBranchingSolver::NodeRequest rq;
+        rq.xl = nd->xl; rq.xu = nd->xu;
+        for (auto &f : frac) {
+          if ((int)rq.cols.size() >= opt.number_strong_branch) break;
+          rq.cols.push_back(f.second);
+          rq.down_ub.push_back(std::floor(nd->x[f.second]));
+          rq.up_lb.push_back(std::ceil(nd->x[f.second]));
+        }
+        open.push_back(nd);
+        reqs.push_back(std::move(rq));
+      }
+      if (open.empty()) continue;
+      // 3. ONE batch for the strong-branching children of every open node of the round
+      sb.prefetchMany(&si, reqs);
+      R.sb_batches++;
+      for (auto &rq : reqs) R.sb_children += 2 * (int)rq.cols.size();
+      // 4. per node: the reference's sequential loop replayed against its cache, scoring, branching
+      for (size_t q = 0; q < open.size(); ++q) {
+        Node *nd = open[q];
+        if (nd->obj >= cutoff) { delete nd; continue; }
+        root.x_l = nd->xl; root.x_u = nd->xu;
+        root.obj_value = nd->obj; root.x_sol = nd->x; root.return_status = (TNLPSolver::ReturnStatus)nd->status;
+        si.optimizationStatus_ = (TNLPSolver::ReturnStatus)nd->status;
+        sb.useNode((int)q);
+        std::vector<StrongResult> res;
+        const int rc = chooser.doStrongBranching(reqs[q].cols, nd->obj, res);
+        if (rc == -1) { delete nd; continue; }
+        int bway = 0;
+        std::vector<std::pair<int, int>> fix;
+        const int bi = chooser.choose(res, nd->obj, cutoff, R.best_obj < 1e99, nd->depth, bway, fix);
+        bool fixed_any = !fix.empty();
+        for (auto &f : fix) {
+          const double v = nd->x[f.first];
+          if (f.second == 0) nd->xl[f.first] = std::max(nd->xl[f.first], std::ceil(v));
+          else nd->xu[f.first] = std::min(nd->xu[f.first], std::floor(v));
+        }
+        const int bcol = res[bi].col;
+        for (int w = 0; w < 2; ++w) {
+          Node *ch = new Node{nd->xl, nd->xu, nd->obj, nd->depth + 1};
+          if (w == 0) ch->xu[bcol] = std::floor(nd->x[bcol]); else ch->xl[bcol] = std::ceil(nd->x[bcol]);
+          const B200Solver::Child *c = fixed_any ? nullptr : sb.lookup(bcol, w == 1);
+          if (c) { ch->solved = true; ch->obj = c->obj; ch->status = (int)c->status; ch->x = c->x;
+                   if (c->status == 1 || c->status == 2) ch->bound = std::max(nd->obj, c->obj); }
+          if (ch->solved && !(ch->status == 1 || ch->status == 2)) { delete ch; continue; }   // pre-solved and infeasible
+          heap.push(ch);
+        }
+        delete nd;
+      }
+    }
+  }
+  while (opt.parallel_nodes <= 1 && (dive || !heap.empty())) {
     Node *nd = dive;
     dive = nullptr;
     if (!nd) { nd = heap.top(); heap.pop(); }

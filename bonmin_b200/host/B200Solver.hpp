@@ -54,6 +54,12 @@ class BatchedStrongBranchingSolver : public StrongBranchingSolver {
   // candidates: (column, down bound = floor(x), up bound = ceil(x)); called between markHotStart and the replay loop
   void prefetch(OsiTMINLPInterface *si, const std::vector<int> &cols, const std::vector<double> &down_ub,
                 const std::vector<double> &up_lb);
+  // Many nodes at once: the strong-branching children of several open nodes go into ONE batch (they share the start
+  // point, BonCbc.cpp:492-505); useNode(i) then makes node i's results the active cache for the replay loop.
+  struct NodeRequest { std::vector<double> xl, xu; std::vector<int> cols; std::vector<double> down_ub, up_lb; };
+  void prefetchMany(OsiTMINLPInterface *si, const std::vector<NodeRequest> &reqs);
+  void useNode(int i);
+  bool preloaded() const { return preloaded_; }
   int cacheHits() const { return hits_; }
   int cacheMisses() const { return misses_; }
   const B200Solver::Child *lookup(int col, bool up) const;
@@ -62,6 +68,9 @@ class BatchedStrongBranchingSolver : public StrongBranchingSolver {
   B200Solver *app_;
   std::vector<double> xl0_, xu0_;
   std::map<std::pair<int, int>, B200Solver::Child> cache_;   // (column, way) -> result
+  std::vector<std::map<std::pair<int, int>, B200Solver::Child>> multi_;
+  std::vector<std::pair<std::vector<double>, std::vector<double>>> multi_bounds_;
+  bool preloaded_ = false;
   int hits_ = 0, misses_ = 0;
 };
 
@@ -97,6 +106,7 @@ struct BbOptions {
   double cutoff_decr = 1e-5;            // :507-513
   double allowable_gap = 0.0, allowable_fraction_gap = 0.0;   // :484-497
   int node_limit = 1000000;
+  int parallel_nodes = 1;               // > 1: that many best-bound nodes are expanded per round with ONE batched launch
   double time_limit = 1e10;
   int log_level = 0;
 };

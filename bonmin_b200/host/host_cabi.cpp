@@ -27,6 +27,7 @@ int bnlp_bb_run_cb(int n, int m, const int *var_type, const double *xl, const do
     if (o->cutoff_decr > 0) opt.cutoff_decr = o->cutoff_decr;
     if (o->time_limit > 0) opt.time_limit = o->time_limit;
     opt.log_level = o->log_level;
+    if (o->parallel_nodes > 0) opt.parallel_nodes = o->parallel_nodes;
   }
   BatchSolveFn fn = [cb, ctx](int B, const double *XL, const double *XU, const double *X0, double *OBJ, int *ST, int *IT,
                               double *X, double *G, double *D) { return cb(ctx, B, XL, XU, X0, OBJ, ST, IT, X, G, D); };

@@ -163,6 +163,8 @@ typedef int (*bnlp_batch_solve_cb)(void *ctx, int B, const double *XL, const dou
 typedef struct bnlp_bb_options {
   int number_strong_branch, number_before_trust, node_limit, log_level;
   double integer_tolerance, cutoff_decr, time_limit;
+  int parallel_nodes;          /* > 1: expand that many best-bound nodes per round with one batched launch (not in the
+                                  reference: its tree search is strictly one node at a time) */
 } bnlp_bb_options;
 typedef struct bnlp_bb_result {
   int status;                 /* 0 optimal, 1 infeasible, 2 limit reached */

@@ -51,6 +51,18 @@ def test_bb_optimum_is_a_valid_lower_bound_of_enumeration(oracle_ipm):
     assert r["best_obj"] == pytest.approx(best, rel=1e-6)
 
 
+def test_bb_parallel_nodes_same_optimum(oracle_ipm):
+    """Expanding several best-bound nodes per round (one batched launch for all their children) changes the node
+    order, not the optimum."""
+    m = I.syn_miqcp(24, 12, 5, 5, 6)
+    s = _oracle_solver(m, oracle_ipm)
+    a = bb.run_callback(m, s, number_strong_branch=12, number_before_trust=1000000)
+    b = bb.run_callback(m, s, number_strong_branch=12, number_before_trust=1000000, parallel_nodes=8)
+    assert a["status"] == b["status"] == 0
+    assert a["best_obj"] == pytest.approx(b["best_obj"], rel=1e-6)
+    assert b["sb_batches"] < a["sb_batches"]
+
+
 @pytest.mark.gpu
 def test_bb_engine_matches_oracle(bnlp_lib, oracle_ipm):
     from bonmin_b200.engine import Engine, Problem
