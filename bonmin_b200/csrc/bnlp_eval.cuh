@@ -464,6 +464,98 @@ __global__ void oa_rows_kernel(EvalModelDev M, OaArgs A) {
   }
 }
 
+// ---- violation probes: OsiTMINLPInterface::getConstraintsViolation / getNonLinearitiesViolation
+// (BonOsiTMINLPInterface.cpp:1839-1876): max over NONLINEAR rows of the bound violation (bounds beyond +-1e10 ignored);
+// with OBJ != null the result is max(norm, f(x) - obj).  One warp per point.
+__global__ void violation_kernel(EvalModelDev M, int B, const double *G, const double *F, const double *OBJ, double *VIOL) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (gw >= B) return;
+  double norm = 0.0;
+  for (int s = lane; s < M.mnl; s += 32) {
+    const int i = M.nl_rows[s];
+    const double g = G[(size_t)gw * M.m + i];
+    double rv = 0.0;
+    if (M.gl[i] > -1e10) rv = fmax(0.0, M.gl[i] - g);
+    if (M.gu[i] < 1e10) rv = fmax(rv, g - M.gu[i]);
+    norm = fmax(norm, rv);
+  }
+#pragma unroll
+  for (int q = 16; q > 0; q >>= 1) norm = fmax(norm, __shfl_xor_sync(0xffffffffu, norm, q));
+  if (lane == 0) {
+    if (OBJ) { const double d = F[gw] - OBJ[gw]; if (d > norm) norm = d; }
+    VIOL[gw] = norm;
+  }
+}
+
+// ---- Benders cut: OsiTMINLPInterface::getBendersCut (BonOsiTMINLPInterface.cpp:2111-2202): the lambda-weighted
+// aggregate of the linearisations of the nonlinear rows with |lambda| > 1e-6 (+ the objective cut when the objective is
+// nonlinear and the point is a proven optimum).  One CTA per point; the dense coefficient vector lives in `cut` (B x (n+1)).
+struct BendersArgs {
+  int B, with_obj;
+  const double *X, *DUALS, *XL, *XU, *F, *G, *GRADF, *JVAL;
+  bnlp_oa_tols tol;
+  double *cut;          // B x (n+1), zeroed by the kernel
+  int *col_idx; double *val; int *row_len; double *UB;   // outputs: fixed capacity n+1 per point
+};
+__global__ void benders_kernel(EvalModelDev M, BendersArgs A) {
+  const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x, n = M.n, m = M.m;
+  __shared__ double s_ub[2];   // [0] ub accumulated, [1] scratch
+  __shared__ int s_cnt;
+  const double *x = A.X + (size_t)b * n;
+  const double *lam = A.DUALS + (size_t)b * (2 * n + m) + 2 * n;
+  double *cut = A.cut + (size_t)b * (n + 1);
+  for (int j = tid; j <= n; j += nt) cut[j] = 0.0;
+  if (tid == 0) { s_ub[0] = 0.0; s_cnt = 0; }
+  __syncthreads();
+  double ub_p = 0.0, lb_dummy = 0.0;
+  for (int s = tid; s < M.mnl; s += nt) {
+    const int i = M.nl_rows[s];
+    const double l = lam[i];
+    if (fabs(l) > 1e-6) ub_p += l * ((l < 0 ? M.gl[i] : M.gu[i]) - A.G[(size_t)b * m + i]);
+  }
+  for (int s = 0; s < M.mnl; ++s) {
+    const int i = M.nl_rows[s];
+    const double l = lam[i];
+    if (!(fabs(l) > 1e-6)) continue;
+    for (int p = M.jac_start[i] + tid; p < M.jac_start[i + 1]; p += nt) {
+      const int col = M.jac_col[p];
+      const double coeff = l * A.JVAL[(size_t)b * M.nnz_jac + p];
+      if (clean_nnz(coeff, A.XL[col], A.XU[col], M.gl[i], M.gu[i], x[col], lb_dummy, ub_p, A.tol.tiny, A.tol.very_tiny, A.tol.infty)) {
+        atomicAdd(&cut[col], coeff);
+        ub_p += coeff * x[col];
+      }
+    }
+  }
+  atomicAdd(&s_ub[0], ub_p);
+  __syncthreads();
+  if (A.with_obj) {
+    __syncthreads();
+    if (tid == 0) s_ub[0] = -A.F[b];   // the reference overwrites ub here (:2173)
+    __syncthreads();
+    double up = 0.0;
+    for (int j = tid; j < n; j += nt) {
+      const double c = A.GRADF[(size_t)b * n + j];
+      if (clean_nnz(c, A.XL[j], A.XU[j], -DBL_MAX, 0.0, x[j], lb_dummy, up, A.tol.tiny, 1e-15, A.tol.infty)) {
+        cut[j] += c;   // column j is owned by this thread in this phase
+        up += c * x[j];
+      }
+    }
+    atomicAdd(&s_ub[0], up);
+    __syncthreads();
+  }
+  // sparse vector: (n, -1) first when the objective cut is included, then the columns with |coef| > 1e-20 in order
+  if (tid == 0) {
+    int *ci = A.col_idx + (size_t)b * (n + 1);
+    double *cv = A.val + (size_t)b * (n + 1);
+    int c = 0;
+    if (A.with_obj) { ci[c] = n; cv[c] = -1.0; ++c; }
+    for (int j = 0; j < n; ++j)
+      if (fabs(cut[j]) > 1e-20) { ci[c] = j; cv[c] = cut[j]; ++c; }
+    A.row_len[b] = c;
+    A.UB[b] = s_ub[0];
+  }
+}
+
 // exclusive scan of the row counts into CSR row_start (single CTA; rows = B*(mnl+1))
 __global__ void oa_scan_kernel(const int *cnt, int *row_start, int rows) {
   __shared__ int part[1024];

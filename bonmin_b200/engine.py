@@ -40,7 +40,8 @@ class OaTols(ctypes.Structure):
 EXPORTS = ["bnlp_last_error", "bnlp_problem_from_nl", "bnlp_problem_from_tape", "bnlp_problem_free",
            "bnlp_problem_sizes", "bnlp_problem_info", "bnlp_engine_create", "bnlp_engine_free", "bnlp_eval_batch",
            "bnlp_solve_batch", "bnlp_solve_batch_device", "bnlp_oa_capacity", "bnlp_oa_batch", "bnlp_engine_stats",
-           "bnlp_engine_launches", "bnlp_measure_fp64_peak", "bnlp_bb_run_cb", "bnlp_bb_run_engine"]
+           "bnlp_engine_launches", "bnlp_measure_fp64_peak", "bnlp_bb_run_cb", "bnlp_bb_run_engine", "bnlp_violation_batch",
+           "bnlp_benders_batch"]
 
 
 def lib():
@@ -66,6 +67,9 @@ def lib():
         L.bnlp_oa_capacity.argtypes = [c_void, c_int, P_int, ctypes.POINTER(ctypes.c_size_t)]
         L.bnlp_oa_batch.argtypes = [c_void, c_int, c_void, c_void, c_void, c_void, c_void, c_dbl, c_int,
                                     ctypes.POINTER(OaTols), c_void, c_void, c_void, c_void, c_void, c_void]
+        L.bnlp_violation_batch.argtypes = [c_void, c_int, c_void, c_void, c_void, c_void]
+        L.bnlp_benders_batch.argtypes = [c_void, c_int, c_void, c_void, c_void, c_void, c_int, ctypes.POINTER(OaTols),
+                                         c_void, c_void, c_void, c_void]
         L.bnlp_engine_stats.argtypes = [c_void, ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_longlong),
                                         P_dbl]
         L.bnlp_engine_launches.restype = ctypes.c_longlong
@@ -267,6 +271,33 @@ class Engine:
                                      int(get_obj), ctypes.byref(t), _vp(row_start), _vp(col), _vp(val), _vp(LB),
                                      _vp(UB), _vp(src)))
         return dict(rows_per_point=rpp.value, row_start=row_start, col=col, val=val, lb=LB, ub=UB, src_row=src)
+
+    def violation_batch(self, X, OBJ=None):
+        """getConstraintsViolation (OBJ None) / getNonLinearitiesViolation per point."""
+        X = _d(np.atleast_2d(X))
+        B = X.shape[0]
+        V = np.zeros(B)
+        F = np.zeros(B)
+        O = None if OBJ is None else _d(OBJ)
+        self._ck(lib().bnlp_violation_batch(self.h, B, _vp(X), _vp(O), _vp(V), _vp(F)))
+        return V, F
+
+    def benders_batch(self, X, DUALS, XL=None, XU=None, with_objective=True, tols=None):
+        n = self.n
+        X = _d(np.atleast_2d(X))
+        B = X.shape[0]
+        info = self.problem.info()
+        XL = _d(info["xl"] if XL is None else XL)
+        XU = _d(info["xu"] if XU is None else XU)
+        Du = _d(np.atleast_2d(DUALS))
+        rl = np.zeros(B, np.int32)
+        ci = np.zeros((B, n + 1), np.int32)
+        cv = np.zeros((B, n + 1))
+        ub = np.zeros(B)
+        t = tols or OaTols(1e-8, 1e-17, 1e-8, 1e19, 0)
+        self._ck(lib().bnlp_benders_batch(self.h, B, _vp(X), _vp(Du), _vp(XL), _vp(XU), int(with_objective),
+                                          ctypes.byref(t), _vp(rl), _vp(ci), _vp(cv), _vp(ub)))
+        return [(ci[b, :rl[b]].tolist(), cv[b, :rl[b]].copy(), ub[b]) for b in range(B)]
 
     def stats(self):
         it, fa, ms = ctypes.c_longlong(), ctypes.c_longlong(), c_dbl()

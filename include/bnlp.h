@@ -144,6 +144,17 @@ int bnlp_oa_batch(bnlp_engine *, int B, const double *X, const double *DUALS, co
                   const double *X2, double theta, int getObj, const bnlp_oa_tols *tols, int *row_start,
                   int *col_idx, double *val, double *LB, double *UB, int *src_row);
 
+/* B x OsiTMINLPInterface::getConstraintsViolation (OBJ == NULL) or getNonLinearitiesViolation (OBJ: B objective values)
+ * (src/Interfaces/BonOsiTMINLPInterface.cpp:1839-1876): max bound violation over the NONLINEAR rows (bounds beyond
+ * +-1e10 ignored), and max with f(x) - obj.  VIOL: B.  F (optional): f(x) per point. */
+int bnlp_violation_batch(bnlp_engine *, int B, const double *X, const double *OBJ, double *VIOL, double *F);
+/* B x OsiTMINLPInterface::getBendersCut (src/Interfaces/BonOsiTMINLPInterface.cpp:2111-2202): one aggregated cut per point,
+ * sum over nonlinear rows with |lambda| > 1e-6 of lambda * (linearisation), plus the objective cut when the objective is
+ * nonlinear and with_objective != 0 (the reference's isProvenOptimal()).  Output: fixed capacity n+1 per point
+ * (col_idx/val: B x (n+1), row_len: B), UB: B; the cut's lower bound is -COIN_DBL_MAX. */
+int bnlp_benders_batch(bnlp_engine *, int B, const double *X, const double *DUALS, const double *XL, const double *XU,
+                       int with_objective, const bnlp_oa_tols *tols, int *row_len, int *col_idx, double *val, double *UB);
+
 /* statistics of the last solve call: total IPM iterations, factorisations, device milliseconds
  * (counterparts of totalIterations_/totalNlpSolveTime_, src/Interfaces/BonOsiTMINLPInterface.hpp:482-495) */
 int bnlp_engine_stats(const bnlp_engine *, long long *iterations, long long *factorisations, double *device_ms);

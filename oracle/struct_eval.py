@@ -266,3 +266,62 @@ def outer_approximation(ev: Evaluator, x, duals=None, xl=None, xu=None, x2=None,
         if gen:
             cuts.append((m, cols, vals, -DBL_MAX, lbub[1]))
     return cuts
+
+
+def constraints_violation(ev: Evaluator, x, obj=None):
+    """getConstraintsViolation / getNonLinearitiesViolation (BonOsiTMINLPInterface.cpp:1839-1876)."""
+    M = ev.m_
+    vals = ev.dense(x)[0]
+    norm = 0.0
+    for i in range(M.m):
+        if not ev.con_nonlinear[i]:
+            continue
+        rv = 0.0
+        if M.gl[i] > -1e10:
+            rv = max(0.0, M.gl[i] - vals[i + 1])
+        if M.gu[i] < 1e10:
+            rv = max(rv, vals[i + 1] - M.gu[i])
+        norm = max(norm, rv)
+    if obj is not None and vals[0] - obj > norm:
+        norm = vals[0] - obj
+    return norm, vals[0]
+
+
+def benders_cut(ev: Evaluator, x, duals, xl=None, xu=None, with_objective=True, tiny=1e-8, very_tiny=1e-17,
+                infty_=1e19):
+    """getBendersCut (BonOsiTMINLPInterface.cpp:2111-2202) -> (cols, vals, ub); lb is -COIN_DBL_MAX."""
+    M = ev.m_
+    n, m = M.n, M.m
+    xl = M.xl if xl is None else xl
+    xu = M.xu if xu is None else xu
+    r = ev.sparse(x)
+    g, jv = r["g"], r["jac"]
+    lam = duals[2 * n:]
+    cut = np.zeros(n + 1)
+    lbub = [0.0, 0.0]
+    keep = np.zeros(m, bool)
+    for i in range(m):
+        if ev.con_nonlinear[i] and abs(lam[i]) > 1e-6:
+            keep[i] = True
+            lbub[1] += lam[i] * ((M.gl[i] if lam[i] < 0 else M.gu[i]) - g[i])
+    for (i, j), v in zip(ev.jac, jv):
+        if not keep[i]:
+            continue
+        coeff = lam[i] * v
+        if clean_nnz(coeff, xl[j], xu[j], M.gl[i], M.gu[i], x[j], lbub, tiny, very_tiny, infty_):
+            cut[j] += coeff
+            lbub[1] += coeff * x[j]
+    cols, vals = [], []
+    if ev.obj_nonlinear and with_objective:
+        lbub[1] = -r["f"]
+        for i in range(n):
+            if clean_nnz(r["gradf"][i], xl[i], xu[i], -DBL_MAX, 0.0, x[i], lbub, tiny, 1e-15, infty_):
+                cut[i] += r["gradf"][i]
+                lbub[1] += r["gradf"][i] * x[i]
+        cols.append(n)
+        vals.append(-1.0)
+    for i in range(n):
+        if abs(cut[i]) > 1e-20:
+            cols.append(i)
+            vals.append(cut[i])
+    return cols, np.array(vals), lbub[1]

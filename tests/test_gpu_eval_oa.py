@@ -113,3 +113,28 @@ def test_oa_violation_filter_and_no_duals(bnlp_lib):
     assert [c[0] for c in _cuts_from_csr(out, 0)] == [c[0] for c in ref]   # constraint cuts kept, objective cut filtered
     out = eng.oa_batch(X, X2=X2, theta=1e9, get_obj=2, tols=OaTols(1e-8, 1e-17, 1e-8, 1e19, 1))
     assert _cuts_from_csr(out, 0) == []
+
+
+@pytest.mark.parametrize("mk", MODELS[1:])
+def test_violation_and_benders_parity(bnlp_lib, mk):
+    from oracle.struct_eval import benders_cut, constraints_violation
+    m = mk()
+    ev = Evaluator(m)
+    eng = _engine(m)
+    rng = np.random.default_rng(3)
+    B = 11
+    X = np.clip(m.x0 + rng.normal(0, 0.4, (B, m.n)), np.maximum(m.xl, -20), np.minimum(m.xu, 20))
+    V, F = eng.violation_batch(X)
+    OBJ = F - rng.uniform(0, 2, B)
+    V2, _ = eng.violation_batch(X, OBJ)
+    D = rng.normal(0, 1, (B, 2 * m.n + m.m))
+    D[:, 2 * m.n::2] *= 1e-8            # some multipliers below the 1e-6 threshold
+    cuts = eng.benders_batch(X, D)
+    for b in range(B):
+        v, f = constraints_violation(ev, X[b])
+        assert V[b] == pytest.approx(v, rel=1e-12, abs=1e-12) and F[b] == pytest.approx(f, rel=1e-12)
+        assert V2[b] == pytest.approx(constraints_violation(ev, X[b], OBJ[b])[0], rel=1e-12, abs=1e-12)
+        cols, vals, ub = benders_cut(ev, X[b], D[b])
+        assert cuts[b][0] == cols
+        np.testing.assert_allclose(cuts[b][1], vals, rtol=1e-11, atol=1e-13)
+        assert cuts[b][2] == pytest.approx(ub, rel=1e-11, abs=1e-11)
