@@ -1,4 +1,8 @@
-"""In-tree build of libbnlp.so (sm_100a only).  `python -m bonmin_b200.build`."""
+"""In-tree build of libbnlp.so (sm_100a only).  `python -m bonmin_b200.build [--force] [-v]`.
+
+Every source is compiled to an object under csrc/_obj/ (the three big kernels are separate translation units, so they
+compile in parallel) and linked into bonmin_b200/libbnlp.so; objects are rebuilt when their source or any header is
+newer."""
 from __future__ import annotations
 
 import os
@@ -7,33 +11,62 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libbnlp.so")
-SOURCES = ["bnlp_api.cu", "bnlp_model.cpp", "bnlp_nl.cpp", "../host/B200Solver.cpp", "../host/host_cabi.cpp"]
+SOURCES = ["bnlp_launch_ipm.cu", "bnlp_launch_coop.cu", "bnlp_api.cu", "bnlp_model.cpp", "bnlp_nl.cpp",
+           "../host/B200Solver.cpp", "../host/host_cabi.cpp"]
 HOST_LIB = os.path.join(HERE, "libbnlp_host.so")
-HEADERS = ["../host/B200Solver.hpp", "../host/bonmin_shim.hpp", "bnlp_internal.h", "bnlp_ipm.cuh", "bnlp_ipm_coop.cuh", "bnlp_eval.cuh", "bnlp_api_eval.inc", "../../include/bnlp.h"]
+HEADERS = ["../host/B200Solver.hpp", "../host/bonmin_shim.hpp", "bnlp_internal.h", "bnlp_ipm.cuh", "bnlp_ipm_coop.cuh",
+           "bnlp_dense.cuh", "bnlp_eval.cuh", "bnlp_api_eval.inc", "../../include/bnlp.h"]
+# headers each source depends on (None = all)
+DEPS = {
+    "bnlp_launch_ipm.cu": ["bnlp_internal.h", "bnlp_ipm.cuh", "bnlp_eval.cuh", "../../include/bnlp.h"],
+    "bnlp_launch_coop.cu": ["bnlp_internal.h", "bnlp_ipm.cuh", "bnlp_ipm_coop.cuh", "bnlp_dense.cuh", "bnlp_eval.cuh",
+                            "../../include/bnlp.h"],
+}
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
+              "-DBNLP_WITH_ENGINE"]
+
+
+def _mtime(p: str) -> float:
+    return os.path.getmtime(p) if os.path.exists(p) else 0.0
+
+
+def _obj_of(src: str) -> str:
+    return os.path.join(OBJ, os.path.basename(src).rsplit(".", 1)[0] + ".o")
+
+
+def _obj_stale(src: str) -> bool:
+    o = _obj_of(src)
+    if not os.path.exists(o):
+        return True
+    t = os.path.getmtime(o)
+    deps = [src] + (DEPS.get(src) or HEADERS)
+    return any(_mtime(os.path.join(CSRC, d)) > t for d in deps)
 
 
 def _stale() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    for f in SOURCES + HEADERS:
-        p = os.path.join(CSRC, f)
-        if os.path.exists(p) and os.path.getmtime(p) > t:
-            return True
-    return False
+    return any(_mtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
-    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-shared", "-DBNLP_WITH_ENGINE", "-o", LIB] + srcs
-    if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-    subprocess.check_call(cmd)
+    os.makedirs(OBJ, exist_ok=True)
+    procs = []
+    for s in SOURCES:
+        if not force and not _obj_stale(s):
+            continue
+        cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, s), "-o", _obj_of(s)]
+        procs.append((s, subprocess.Popen(cmd)))
+    bad = [s for s, p in procs if p.wait() != 0]
+    if bad:
+        raise RuntimeError(f"nvcc failed for {bad}")
+    subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] +
+                          [_obj_of(s) for s in SOURCES])
     build_host()
     return LIB
 

@@ -17,12 +17,19 @@
 namespace bnlp {
 constexpr double kInfD = 1e19;
 }
+#define BNLP_EVAL_KERNELS
 #include "bnlp_eval.cuh"
 #include "bnlp_ipm.cuh"
 #include "bnlp_ipm_coop.cuh"
 
 namespace bnlp {
 bool model_from_desc(const bnlp_tape_desc *d, HostModel &M, std::string &err);
+// kernel launchers live in their own translation units (bnlp_launch_ipm.cu, bnlp_launch_coop.cu) so the three big
+// kernels compile in parallel
+cudaError_t ipm_general_set_smem(size_t smem);
+cudaError_t ipm_general_launch(bool wide, int ctas, size_t smem, cudaStream_t stream, const DevModel &M, const IpmArgs &A);
+cudaError_t ipm_coop_set_smem(size_t smem);
+cudaError_t ipm_coop_launch(bool timers, int ctas, size_t smem, cudaStream_t stream, DevModel &M, IpmArgs &A, CoopBufs &CB);
 }
 
 using namespace bnlp;
@@ -321,15 +328,11 @@ extern "C" bnlp_engine *bnlp_engine_create(const bnlp_problem *prob, const int *
                    (size_t)COOP_RB * (E->nqpad + 4) <= (size_t)(IPM_NW + 1) * lds && (size_t)COOP_RB * E->ldd <= (size_t)(IPM_NW + 1) * lds &&
                    !getenv("BNLP_NO_COOP");
     }
-    if (E->coop_ok &&
-        (cudaFuncSetAttribute(ipm_coop_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)E->coop_smem_bytes) != cudaSuccess ||
-         cudaFuncSetAttribute(ipm_coop_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)E->coop_smem_bytes) != cudaSuccess)) {
+    if (E->coop_ok && ipm_coop_set_smem(E->coop_smem_bytes) != cudaSuccess) {
       E->coop_ok = false;
       cudaGetLastError();
     }
-    if (E->ipm_supported &&
-        (cudaFuncSetAttribute(ipm_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)E->smem_bytes) != cudaSuccess ||
-         cudaFuncSetAttribute(ipm_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)E->smem_bytes) != cudaSuccess)) {
+    if (E->ipm_supported && ipm_general_set_smem(E->smem_bytes) != cudaSuccess) {
       set_err(std::string("cudaFuncSetAttribute(ipm_kernel): ") + cudaGetErrorString(cudaGetLastError()));
       delete E;
       return nullptr;
@@ -383,11 +386,8 @@ static int launch_ipm(bnlp_engine *E, Device &D, int B, const double *dXL, const
         D.cidle.reserve(2)) { set_err("cooperative buffers: allocation failed"); return -1; }
     CK(cudaMemsetAsync(D.cidle.p, 0, 2 * sizeof(int), stream));
     cb.xw = D.cxw.p; cb.Wbuf = D.cW.p; cb.xd = D.cxd.p; cb.idle_cnt = D.cidle.p; cb.nqpad = E->nqpad; cb.ldd = E->ldd;
-    void *args[] = {(void *)&D.dm, (void *)&a, (void *)&cb};
-    CK(cudaLaunchCooperativeKernel(a.phase_cycles ? (void *)ipm_coop_kernel<true> : (void *)ipm_coop_kernel<false>, dim3(ctas), dim3(IPM_NT), args,
-                                   E->coop_smem_bytes, stream));
-  } else if (E->M.n <= 256) ipm_kernel<8><<<ctas, IPM_NT, E->smem_bytes, stream>>>(D.dm, a);
-  else ipm_kernel<16><<<ctas, IPM_NT, E->smem_bytes, stream>>>(D.dm, a);
+    CK(ipm_coop_launch(a.phase_cycles != nullptr, ctas, E->coop_smem_bytes, stream, D.dm, a, cb));
+  } else CK(ipm_general_launch(E->M.n > 256, ctas, E->smem_bytes, stream, D.dm, a));
   E->launches++;
   CK(cudaGetLastError());
   return 0;

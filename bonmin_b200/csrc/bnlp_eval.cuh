@@ -190,6 +190,7 @@ __device__ inline int jac_pos(const EvalModelDev &M, int fn, int col, int dense)
   return -1;
 }
 
+#ifdef BNLP_EVAL_KERNELS   // the __global__ entry points are compiled by bnlp_api.cu only
 __global__ void __launch_bounds__(EV_NT) eval_kernel(EvalModelDev M, EvalArgs A) {
   extern __shared__ double fv[];   // m+1 function values
   const int b = blockIdx.x, tid = threadIdx.x, n = M.n, m = M.m;
@@ -593,5 +594,7 @@ __global__ void oa_compact_kernel(EvalModelDev M, OaArgs A, const int *row_start
   const int dst = row_start[gw];
   for (int p = lane; p < cntv; p += 32) { col_idx[dst + p] = tcol[p]; val[dst + p] = tval[p]; }
 }
+
+#endif  // BNLP_EVAL_KERNELS
 
 }  // namespace bnlp

@@ -34,6 +34,10 @@ __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
                : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+}  // namespace bnlp
+#include "bnlp_dense.cuh"
+namespace bnlp {
+
 // ---- H[i,k] += sign * sum_c M[c][i] M[c][k], lo <= k <= i < hi, 8x8 tiles on the FP64 tensor pipe.
 // M: K rows (K multiple of 4) of length ld in shared memory, zero outside [lo,hi) within the touched tile range.
 // A warp owns strips of up to four column tiles of one tile row (A fragment loaded once, four independent DMMA chains).
@@ -109,7 +113,7 @@ __device__ __forceinline__ void syrk_dmma(double *H, int lo, int hi, const doubl
 // non-positive pivot.  Done by ONE thread entirely in registers (fully unrolled): the 8 dependent rsqrt steps are
 // the critical path of the whole factorisation, and the in-register version is ~3x shorter than a warp-shuffle one
 // (f64 shuffles cost 36 cycles each on this part; measured in scripts/micro/dmma_bench.cu).
-__device__ __noinline__ void chol_diag_block(double *H, int j0, int nb, int *fail) {
+static __device__ __noinline__ void chol_diag_block(double *H, int j0, int nb, int *fail) {
   if ((threadIdx.x & 31) != 0) return;
   double a[8][8];
 #pragma unroll
@@ -817,7 +821,7 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
       ++nfact;
       retry = false;
       PH_MARK(8);
-      if (!chol_dmma(H, N, N + 2, stage, lds, &s_fail, TIMERS ? chdbg : nullptr)) {
+      if (!chol3(H, N, N + 2, stage, lds, &s_fail)) {
         // inertia correction: retry the whole step with a larger delta_w (first 1e-4, x100 then x8, /3 between iterations)
         if (delta_w == 0.0) delta_w = (delta_w_last == 0.0) ? 1e-4 : fmax(1e-20, delta_w_last / 3.0);
         else delta_w *= (delta_w_last == 0.0 ? 100.0 : 8.0);
