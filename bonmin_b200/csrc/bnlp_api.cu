@@ -87,7 +87,7 @@ struct Device {
   DBuf<int> dST, dIT, queue;
   DBuf<long long> stats;
   // eval buffers
-  DBuf<double> eX, eLAM, eF, eG, eGF, eJ, eH, eX2, eDU, oVal, oLB, oUB;
+  DBuf<double> eX, eLAM, eF, eG, eGF, eJ, eH, eX2, eDU, eU, oVal, oLB, oUB;
   DBuf<int> oRS, oCI, oSR;
   DevModel dm{};
 };
@@ -349,7 +349,7 @@ extern "C" void bnlp_engine_free(bnlp_engine *E) {
     cudaSetDevice(D.id);
     for (auto *b : {&D.c, &D.A, &D.Qp, &D.Qf, &D.row_sgn, &D.row_bnd, &D.gl, &D.gu, &D.xl, &D.xu, &D.e_dbl, &D.dXL, &D.dXU,
                     &D.dX0, &D.dOBJ, &D.dX, &D.dG, &D.dD, &D.ws, &D.cxw, &D.cW, &D.cxd, &D.eq_bnd, &D.eX, &D.eLAM, &D.eF, &D.eG, &D.eGF, &D.eJ, &D.eH,
-                    &D.eX2, &D.eDU, &D.oVal, &D.oLB, &D.oUB})
+                    &D.eX2, &D.eDU, &D.eU, &D.oVal, &D.oLB, &D.oUB})
       b->release();
     for (auto *b : {&D.qidx, &D.row_fn, &D.fn_row_up, &D.fn_row_lo, &D.e_int, &D.dST, &D.dIT, &D.queue, &D.cidle, &D.eq_fn, &D.fn_eq, &D.oRS, &D.oCI,
                     &D.oSR})

@@ -175,6 +175,7 @@ struct EvalArgs {
   const double *LAM;    // B x m or null
   double sigma;
   double *F, *G, *GRADF, *JVAL, *HVAL;   // any may be null
+  const double *U;      // B x nfq x n : u = Q x of every dense quadratic block, from quad_batch_kernel (null if nfq == 0)
 };
 
 __device__ inline int jac_pos(const EvalModelDev &M, int fn, int col, int dense) {
@@ -191,6 +192,68 @@ __device__ inline int jac_pos(const EvalModelDev &M, int fn, int col, int dense)
 }
 
 #ifdef BNLP_EVAL_KERNELS   // the __global__ entry points are compiled by bnlp_api.cu only
+// ---- u_{b,q} = Q_q x_b for EVERY dense quadratic block and a whole batch of points, as a dense contraction on the FP64
+// tensor pipe (mma.sync m8n8k4 f64): C[8 matrix rows x 8 points] += Qf[8 x 4] * X'[4 x 8].  CTA (s, g) stages the PB
+// points of group g in shared memory (row stride = 1 mod 16 doubles: conflict-free fragments) and serves slice s of the
+// (block, 8-row tile) list, so a block element crosses L2 -> SM once per PB points instead of once per point (the
+// per-point version re-read all blocks for every point: 200 MB per point at C4).  Every global request is a whole
+// 128-byte line: lane (lr, lc) loads sector lc of {row r0+lr, columns 16g .. 16g+15}; k-step s contracts over the
+// columns {16g + 4lc + s}, a permutation of the summation index that the B fragments follow.
+constexpr int QB_NT = 256;
+__device__ __forceinline__ void dmma_ev(double &c0, double &c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+template <int PB>
+__global__ void __launch_bounds__(QB_NT, 1) quad_batch_kernel(EvalModelDev M, int B, const double *X, double *U, int ldd) {
+  extern __shared__ double Dsm[];   // [PB][ldd]
+  const int n = M.n, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  constexpr int NW = QB_NT / 32, NP = PB / 8;
+  const int b0 = blockIdx.y * PB;
+  for (int e = tid; e < PB * ldd; e += QB_NT) {
+    const int b = b0 + e / ldd, j = e % ldd;
+    Dsm[e] = (b < B && j < n) ? X[(size_t)b * n + j] : 0.0;
+  }
+  __syncthreads();
+  const int tpb = (n + 7) >> 3, ntile = M.nfq * tpb;
+  const int t0 = (int)(((long long)ntile * blockIdx.x) / gridDim.x), t1 = (int)(((long long)ntile * (blockIdx.x + 1)) / gridDim.x);
+  const int lr = lane >> 2, lc = lane & 3;
+  const int ngrp = (n + 15) >> 4;
+  for (int t = t0 + wid; t < t1; t += NW) {
+    const int qi = t / tpb, r0 = (t - qi * tpb) << 3;
+    const int k = M.fq_fn[qi];
+    const int r = r0 + lr;
+    const bool rv = r < n;
+    const double2 *Qrow = reinterpret_cast<const double2 *>(M.Qf + ((size_t)M.qidx[k] * n + min(r, n - 1)) * M.ldq) + 2 * lc;
+    double acc[NP][2];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) acc[p][0] = acc[p][1] = 0.0;
+    double2 a0 = __ldg(Qrow), a1 = __ldg(Qrow + 1);
+    for (int g = 0; g < ngrp; ++g) {
+      const int gn = min(g + 1, ngrp - 1);
+      const double2 n0 = __ldg(Qrow + 8 * gn), n1 = __ldg(Qrow + 8 * gn + 1);   // next group in flight under the DMMAs
+      const int cb = 16 * g + 4 * lc;
+      const double av[4] = {a0.x, a0.y, a1.x, a1.y};
+#pragma unroll
+      for (int s4 = 0; s4 < 4; ++s4) {
+        const double a = rv ? av[s4] : 0.0;
+#pragma unroll
+        for (int p = 0; p < NP; ++p) dmma_ev(acc[p][0], acc[p][1], a, Dsm[(8 * p + lr) * ldd + cb + s4]);
+      }
+      a0 = n0; a1 = n1;
+    }
+    // C[row lr][point 8p + 2lc, + 1]: for a fixed (p, half) the eight lanes lr = 0..7 write 64 contiguous bytes
+    if (rv) {
+#pragma unroll
+      for (int p = 0; p < NP; ++p)
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int b = b0 + 8 * p + 2 * lc + hh;
+          if (b < B) U[((size_t)b * M.nfq + qi) * n + r] = acc[p][hh];
+        }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(EV_NT) eval_kernel(EvalModelDev M, EvalArgs A) {
   extern __shared__ double fv[];   // m+1 function values
   const int b = blockIdx.x, tid = threadIdx.x, n = M.n, m = M.m;
@@ -219,26 +282,23 @@ __global__ void __launch_bounds__(EV_NT) eval_kernel(EvalModelDev M, EvalArgs A)
     if (lane == 0) fv[k] += acc;
   }
   __syncthreads();
-  // ---- dense quadratic blocks: one warp per function, u = Q x row by row from the full copy
+  // ---- dense quadratic blocks: u = Q x comes from quad_batch_kernel (one contraction for the whole batch); one warp per
+  // function adds 1/2 x.u to the value and u to the gradient / Jacobian row
   for (int qi = w; qi < M.nfq; qi += NWARP) {
     const int k = M.fq_fn[qi], dense = M.fq_dense[qi];
-    const double *Q = M.Qf + (size_t)M.qidx[k] * n * M.ldq;
+    const double *u = A.U + ((size_t)b * M.nfq + qi) * n;
     double vacc = 0.0;
-    for (int r = 0; r < n; ++r) {
-      const double *Qr = Q + (size_t)r * M.ldq;
-      double u = 0.0;
-      for (int j = lane; j < n; j += 32) u = fma(Qr[j], x[j], u);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) u += __shfl_xor_sync(0xffffffffu, u, o);
-      if (lane == 0) {
-        vacc = fma(0.5 * x[r], u, vacc);
-        if (k == 0) { if (gf) gf[r] += u; }
-        else if (jv) {
-          const int p = jac_pos(M, k, r, dense);
-          if (p >= 0) jv[p] += u;
-        }
+    for (int r = lane; r < n; r += 32) {
+      const double ur = u[r];
+      vacc = fma(0.5 * x[r], ur, vacc);
+      if (k == 0) { if (gf) gf[r] += ur; }
+      else if (jv) {
+        const int p = jac_pos(M, k, r, dense);
+        if (p >= 0) jv[p] += ur;
       }
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) vacc += __shfl_xor_sync(0xffffffffu, vacc, o);
     if (lane == 0) fv[k] += vacc;
   }
   __syncthreads();

@@ -1,0 +1,42 @@
+"""Outer-approximation throughput on C4: B x getOuterApproximation through the C ABI (host buffers).
+Prints one JSON line: points/s, cuts/s, algorithmic GB/s against the measured HBM peak, CPU oracle beside it."""
+import json, os, sys, time
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bonmin_b200 import instances as I
+from bonmin_b200.engine import Engine, Problem
+
+
+def run(B=1024, reps=5, cpu_points=8, model=None):
+    m = model or I.config_c4()
+    eng = Engine(Problem.from_model(m))
+    rng = np.random.default_rng(5)
+    X = np.clip(m.x0 + rng.uniform(-0.3, 0.3, size=(B, m.n)), m.xl, m.xu)
+    X[:, m.vtype != 0] = np.round(X[:, m.vtype != 0])
+    r = eng.oa_batch(X, None, m.xl, m.xu, get_obj=1)          # warm-up (allocations)
+    r = eng.oa_batch(X, None, m.xl, m.xu, get_obj=1)
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        r = eng.oa_batch(X, None, m.xl, m.xu, get_obj=1)
+        ts.append(time.perf_counter() - t0)
+    t = float(np.median(ts))
+    ncuts = int((r["src_row"] >= 0).sum())
+    nnz = int(r["row_start"][-1])
+    alg_bytes = B * (8 * m.n + 8 * m.m) + nnz * 12 + ncuts * 16     # x, duals in; rows out
+    out = {"workload": m.name, "points": B, "cuts": ncuts, "nnz": nnz, "e2e_ms": t * 1e3, "points_per_s": B / t,
+           "cuts_per_s": ncuts / t, "algorithmic_GB_per_s_e2e": alg_bytes / t / 1e9}
+    if cpu_points:
+        from oracle import struct_eval as SE
+        ev = SE.Evaluator(m)
+        t0 = time.perf_counter()
+        for b in range(cpu_points):
+            SE.outer_approximation(ev, X[b], None, m.xl, m.xu, get_obj=1)
+        out["cpu_oracle_points_per_s"] = cpu_points / (time.perf_counter() - t0)
+    eng.close()
+    return out
+
+
+if __name__ == "__main__":
+    B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+    print(json.dumps(run(B)))
