@@ -195,6 +195,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=2048)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-bb", action="store_true", help="skip the B-BB wall-time-to-optimum section")
+    ap.add_argument("--no-oa", action="store_true", help="skip the C4 outer-approximation section")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -322,7 +323,7 @@ def main():
                     "d2h_bytes_per_step": d2h * world},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "fp64", "kernel": "ipm_kernel", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "fp64", "kernel": "ipm_coop_kernel", "achieved": achieved, "peak": peak,
                          "unit": "TFLOP/s", "frac": achieved / peak if peak > 0 else None, "traffic": None,
                          "peak_source": "FP64 FMA micro-kernel measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
                          "flops_per_iteration": f_iter(C3["n"], C3["m_q"], C3["m_l"]),
@@ -348,6 +349,11 @@ def main():
                               "max_rel_obj_diff": float(rel[okk & same].max(initial=0.0)), "tolerance": 1e-6}
         if world == 1 and not args.no_bb:
             line["bb"] = bb_section(args, local_rank)
+        if world == 1 and not args.no_oa:
+            sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "scripts"))
+            import bench_oa
+            eng.close()
+            line["oa"] = bench_oa.run(B=512, reps=3, cpu_points=4)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -41,7 +41,7 @@ EXPORTS = ["bnlp_last_error", "bnlp_problem_from_nl", "bnlp_problem_from_tape", 
            "bnlp_problem_sizes", "bnlp_problem_info", "bnlp_engine_create", "bnlp_engine_free", "bnlp_eval_batch",
            "bnlp_solve_batch", "bnlp_solve_batch_device", "bnlp_oa_capacity", "bnlp_oa_batch", "bnlp_engine_stats",
            "bnlp_engine_launches", "bnlp_measure_fp64_peak", "bnlp_bb_run_cb", "bnlp_bb_run_engine", "bnlp_violation_batch",
-           "bnlp_benders_batch"]
+           "bnlp_benders_batch", "bnlp_branching_tqp", "bnlp_tqp_solve_batch"]
 
 
 def lib():
@@ -70,6 +70,9 @@ def lib():
         L.bnlp_violation_batch.argtypes = [c_void, c_int, c_void, c_void, c_void, c_void]
         L.bnlp_benders_batch.argtypes = [c_void, c_int, c_void, c_void, c_void, c_void, c_int, ctypes.POINTER(OaTols),
                                          c_void, c_void, c_void, c_void]
+        L.bnlp_branching_tqp.restype = c_void
+        L.bnlp_branching_tqp.argtypes = [c_void, c_void, c_void, P_dbl, ctypes.c_char_p, ctypes.c_size_t]
+        L.bnlp_tqp_solve_batch.argtypes = [c_void, c_void, c_void, c_int] + [c_void] * 6
         L.bnlp_engine_stats.argtypes = [c_void, ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_longlong),
                                         P_dbl]
         L.bnlp_engine_launches.restype = ctypes.c_longlong
@@ -298,6 +301,33 @@ class Engine:
         self._ck(lib().bnlp_benders_batch(self.h, B, _vp(X), _vp(Du), _vp(XL), _vp(XU), int(with_objective),
                                           ctypes.byref(t), _vp(rl), _vp(ci), _vp(cv), _vp(ub)))
         return [(ci[b, :rl[b]].tolist(), cv[b, :rl[b]].copy(), ub[b]) for b in range(B)]
+
+    def branching_tqp(self, x_sol, duals_sol):
+        """BranchingTQP at (x_sol, duals_sol): returns (Problem of the QP in displacement variables, f(x_sol))."""
+        x = _d(x_sol)
+        du = _d(duals_sol)
+        f0 = c_dbl()
+        err = ctypes.create_string_buffer(512)
+        h = lib().bnlp_branching_tqp(self.h, _vp(x), _vp(du), ctypes.byref(f0), err, 512)
+        if not h:
+            raise BnlpError(err.value.decode() or _err())
+        return Problem(h), f0.value
+
+    def tqp_solve_batch(self, x_sol, duals_sol, XL, XU, want_x=True):
+        """B x QpBranchingSolver::solveFromHotStart: children (original-variable bounds) on the QP surrogate."""
+        n = self.n
+        XL = _d(np.atleast_2d(XL))
+        XU = _d(np.atleast_2d(XU))
+        B = XL.shape[0]
+        x = _d(x_sol)
+        du = _d(duals_sol)
+        out = dict(obj=np.zeros(B), status=np.zeros(B, np.int32), iters=np.zeros(B, np.int32))
+        X = np.zeros((B, n)) if want_x else None
+        self._ck(lib().bnlp_tqp_solve_batch(self.h, _vp(x), _vp(du), B, _vp(XL), _vp(XU), _vp(out["obj"]),
+                                            _vp(out["status"]), _vp(out["iters"]), _vp(X)))
+        if want_x:
+            out["x"] = X
+        return out
 
     def stats(self):
         it, fa, ms = ctypes.c_longlong(), ctypes.c_longlong(), c_dbl()

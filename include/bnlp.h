@@ -155,6 +155,21 @@ int bnlp_violation_batch(bnlp_engine *, int B, const double *X, const double *OB
 int bnlp_benders_batch(bnlp_engine *, int B, const double *X, const double *DUALS, const double *XL, const double *XU,
                        int with_objective, const bnlp_oa_tols *tols, int *row_len, int *col_idx, double *val, double *UB);
 
+/* QP strong branching.
+ * bnlp_branching_tqp   = Bonmin::BranchingTQP (src/Interfaces/BonBranchingTQP.cpp:22-108 construction, :136-153 bounds,
+ *   :192-309 callbacks): the node NLP frozen at its optimum (x_sol: n, duals_sol: 2n+m = [z_L|z_U|lambda]) as a QP in the
+ *   displacement d = x - x_sol:  min grad f(x_sol).d + 1/2 d'W d  (W = Hessian of the Lagrangian, obj_factor 1),
+ *   g_L - g(x_sol) <= J(x_sol) d <= g_U - g(x_sol),  x_L - x_sol <= d <= x_U - x_sol.  Returned as an ordinary problem
+ *   (caller frees); *obj_val = f(x_sol).
+ * bnlp_tqp_solve_batch = B x QpBranchingSolver::solveFromHotStart (src/Algorithms/Branching/BonQpBranchingSolver.cpp:50-116):
+ *   children given by their bounds in the ORIGINAL variables (XL, XU: B x n), solved on that QP from d = 0; results as
+ *   BranchingTQP::finalize_solution reports them (BonBranchingTQP.cpp:311-333): X = x_sol + d, OBJ = QP objective +
+ *   f(x_sol), an infeasible child keeps its violation.  X may be NULL. */
+bnlp_problem *bnlp_branching_tqp(bnlp_engine *, const double *x_sol, const double *duals_sol, double *obj_val, char *err,
+                                 size_t errlen);
+int bnlp_tqp_solve_batch(bnlp_engine *, const double *x_sol, const double *duals_sol, int B, const double *XL,
+                         const double *XU, double *OBJ, int *STATUS, int *ITERS, double *X);
+
 /* statistics of the last solve call: total IPM iterations, factorisations, device milliseconds
  * (counterparts of totalIterations_/totalNlpSolveTime_, src/Interfaces/BonOsiTMINLPInterface.hpp:482-495) */
 int bnlp_engine_stats(const bnlp_engine *, long long *iterations, long long *factorisations, double *device_ms);

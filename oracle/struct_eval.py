@@ -325,3 +325,25 @@ def benders_cut(ev: Evaluator, x, duals, xl=None, xu=None, with_objective=True, 
             cols.append(i)
             vals.append(cut[i])
     return cols, np.array(vals), lbub[1]
+
+
+def branching_tqp_model(model, ev: Evaluator, x_sol, duals_sol):
+    """CPU restatement of Bonmin::BranchingTQP (src/Interfaces/BonBranchingTQP.cpp:22-108,136-153,192-243): the node NLP
+    frozen at (x_sol, duals_sol) as a QP in d = x - x_sol.  Returns (StructuredModel of the QP, f(x_sol)).
+    Test infrastructure only."""
+    from bonmin_b200.instances import StructuredModel, pack_lower, _empty_sparse
+    n, m = model.n, model.m
+    x = np.asarray(x_sol, float)
+    lam = np.asarray(duals_sol, float)[2 * n:]
+    vals, grads, W = ev.dense(x, lam, 1.0)
+    g = vals[1:]
+    INF = 1e19
+    xl = np.where(model.xl > -INF, model.xl - x, model.xl)
+    xu = np.where(model.xu < INF, model.xu - x, model.xu)
+    gl = np.where(model.gl > -INF, model.gl - g, model.gl)
+    gu = np.where(model.gu < INF, model.gu - g, model.gu)
+    A = np.array(grads, float)
+    q = StructuredModel(n=n, m=m, xl=xl, xu=xu, gl=gl, gu=gu, vtype=np.asarray(model.vtype, np.int32).copy(),
+                        x0=np.zeros(n), c=np.zeros(m + 1), A=A, qd_fn=np.array([0], np.int32),
+                        qd=pack_lower(W).reshape(1, n * (n + 1) // 2), terms=[], name="TQP(" + str(model.get("name", "")) + ")")
+    return _empty_sparse(q), float(vals[0])

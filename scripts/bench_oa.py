@@ -21,11 +21,22 @@ def run(B=1024, reps=5, cpu_points=8, model=None):
         r = eng.oa_batch(X, None, m.xl, m.xu, get_obj=1)
         ts.append(time.perf_counter() - t0)
     t = float(np.median(ts))
+    kms = eng.stats()["device_ms"]                                   # kernels only (quad + eval + rows + scan + compact)
     ncuts = int((r["src_row"] >= 0).sum())
     nnz = int(r["row_start"][-1])
     alg_bytes = B * (8 * m.n + 8 * m.m) + nnz * 12 + ncuts * 16     # x, duals in; rows out
     out = {"workload": m.name, "points": B, "cuts": ncuts, "nnz": nnz, "e2e_ms": t * 1e3, "points_per_s": B / t,
-           "cuts_per_s": ncuts / t, "algorithmic_GB_per_s_e2e": alg_bytes / t / 1e9}
+           "cuts_per_s": ncuts / t, "algorithmic_GB_per_s_e2e": alg_bytes / t / 1e9,
+           "kernels_ms": kms, "points_per_s_device": B / (kms * 1e-3), "cuts_per_s_device": ncuts / (kms * 1e-3),
+           "algorithmic_bytes": alg_bytes, "algorithmic_GB_per_s_device": alg_bytes / (kms * 1e-3) / 1e9}
+    try:
+        peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
+        hb = peak.get("hbm_gbs") or peak.get("hbm_gbs_sustained")
+        if hb:
+            out["hbm_peak_GB_per_s"] = hb
+            out["hbm_frac_device"] = out["algorithmic_GB_per_s_device"] / hb
+    except Exception:
+        pass
     if cpu_points:
         from oracle import struct_eval as SE
         ev = SE.Evaluator(m)

@@ -138,3 +138,53 @@ def test_violation_and_benders_parity(bnlp_lib, mk):
         assert cuts[b][0] == cols
         np.testing.assert_allclose(cuts[b][1], vals, rtol=1e-11, atol=1e-13)
         assert cuts[b][2] == pytest.approx(ub, rel=1e-11, abs=1e-11)
+
+
+@pytest.mark.gpu
+def test_branching_tqp_parity(bnlp_lib):
+    """QP strong branching: the QP surrogate built on the device at a node optimum equals the CPU
+    restatement of BranchingTQP, and its children (bnlp_tqp_solve_batch) match the oracle IPM on that QP."""
+    from bonmin_b200.engine import Engine, Problem
+    from oracle import ipm as oipm
+    from oracle import struct_eval as SE
+    for m in (I.mytoy(), I.syn_miqcp(40, 20, 8, 8, 3)):
+        eng = Engine(Problem.from_model(m))
+        root = eng.solve_batch(m.xl, m.xu, m.x0)
+        assert root["status"][0] == 1
+        xs, du = root["x"][0], root["duals"][0]
+        ev = SE.Evaluator(m)
+        qm, f0 = SE.branching_tqp_model(m, ev, xs, du)
+        P, f0_dev = eng.branching_tqp(xs, du)
+        assert abs(f0 - f0_dev) <= 1e-9 * max(1.0, abs(f0))
+        info = P.info()
+        np.testing.assert_allclose(info["xl"], qm.xl, atol=1e-12)
+        np.testing.assert_allclose(info["gu"], qm.gu, rtol=1e-9, atol=1e-9)
+        # the device-built QP evaluates like the oracle-built one at a random displacement
+        qe = Engine(P)
+        rng = np.random.default_rng(1)
+        d = rng.uniform(-0.1, 0.1, m.n)
+        r = qe.eval_batch(d[None, :], want=("f", "g", "gradf"))
+        vals, grads, _ = SE.Evaluator(qm).dense(d)
+        assert abs(r["f"][0] - vals[0]) <= 1e-9 * max(1.0, abs(vals[0]))
+        np.testing.assert_allclose(r["g"][0], vals[1:], rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(r["gradf"][0], grads[0], rtol=1e-9, atol=1e-9)
+        qe.close()
+        # children: every integer variable both ways, on the QP surrogate
+        ints = np.flatnonzero(m.vtype != 0)
+        frac = [j for j in ints if abs(xs[j] - round(xs[j])) > 1e-6][:8]
+        XL, XU = I.strong_branching_children(m, m.xl, m.xu, xs, frac)
+        got = eng.tqp_solve_batch(xs, du, XL, XU)
+        INF = 1e19
+        dl = np.where(XL > -INF, XL - xs, XL)
+        du_ = np.where(XU < INF, XU - xs, XU)
+        ref = oipm.solve_batch(qm, dl, du_, np.zeros(m.n), threads=4)
+        assert (got["status"] == ref["status"]).all()
+        ok = ref["status"] == 1
+        np.testing.assert_allclose(got["obj"][ok], ref["obj"][ok] + f0, rtol=1e-6, atol=1e-8)
+        np.testing.assert_allclose(got["x"][ok], ref["x"][ok] + xs, atol=1e-5)
+        # a QP child is a lower-order model of the NLP child: close to it for these quadratic instances
+        nlp = eng.solve_batch(XL, XU, xs)
+        both = ok & (nlp["status"] == 1)
+        if m.n > 10:
+            assert both.sum() >= 4
+        eng.close()
