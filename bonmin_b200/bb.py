@@ -17,7 +17,7 @@ P_int, P_dbl = ctypes.POINTER(c_int), ctypes.POINTER(c_dbl)
 class BbOptions(ctypes.Structure):
     _fields_ = [("number_strong_branch", c_int), ("number_before_trust", c_int), ("node_limit", c_int),
                 ("log_level", c_int), ("integer_tolerance", c_dbl), ("cutoff_decr", c_dbl), ("time_limit", c_dbl),
-                ("parallel_nodes", c_int)]
+                ("parallel_nodes", c_int), ("variable_selection", c_int)]
 
 
 class BbResult(ctypes.Structure):
@@ -44,8 +44,14 @@ def host_lib():
     return _host
 
 
-def _opts(number_strong_branch=0, number_before_trust=0, node_limit=0, time_limit=0.0, parallel_nodes=0):
-    return BbOptions(number_strong_branch, number_before_trust, node_limit, 0, 0.0, 0.0, time_limit, parallel_nodes)
+QCB = ctypes.CFUNCTYPE(c_int, c_void, P_dbl, P_dbl, c_int, P_dbl, P_dbl, P_dbl, P_int, P_int, P_dbl)
+VARIABLE_SELECTION = {"strong-branching": 0, "qp-strong-branching": 1}
+
+
+def _opts(number_strong_branch=0, number_before_trust=0, node_limit=0, time_limit=0.0, parallel_nodes=0,
+          variable_selection="strong-branching"):
+    return BbOptions(number_strong_branch, number_before_trust, node_limit, 0, 0.0, 0.0, time_limit, parallel_nodes,
+                     VARIABLE_SELECTION[variable_selection])
 
 
 def run_engine(eng: "_e.Engine", **kw):
@@ -62,9 +68,24 @@ def run_engine(eng: "_e.Engine", **kw):
     return d
 
 
-def run_callback(model, solve_batch, **kw):
-    """solve_batch(XL, XU, x0) -> dict(obj, status, iters, x) with the meaning of Engine.solve_batch."""
+def run_callback(model, solve_batch, tqp_solve=None, **kw):
+    """solve_batch(XL, XU, x0) -> dict(obj, status, iters, x) with the meaning of Engine.solve_batch.
+    tqp_solve(x_sol, duals_sol, XL, XU) -> dict(obj, status, iters, x) with the meaning of Engine.tqp_solve_batch
+    (needed for variable_selection="qp-strong-branching")."""
     n, m = model.n, model.m
+
+    def qcb(ctx, XS, DU, B, XL, XU, OBJ, ST, IT, X):
+        xs = np.ctypeslib.as_array(XS, (n,)).copy()
+        du = np.ctypeslib.as_array(DU, (2 * n + m,)).copy()
+        xl = np.ctypeslib.as_array(XL, (B, n)).copy()
+        xu = np.ctypeslib.as_array(XU, (B, n)).copy()
+        r = tqp_solve(xs, du, xl, xu)
+        np.ctypeslib.as_array(OBJ, (B,))[:] = r["obj"]
+        np.ctypeslib.as_array(ST, (B,))[:] = r["status"]
+        np.ctypeslib.as_array(IT, (B,))[:] = r["iters"]
+        if X:
+            np.ctypeslib.as_array(X, (B, n))[:] = r["x"]
+        return 0
 
     def cb(ctx, B, XL, XU, X0, OBJ, ST, IT, X, G, D):
         xl = np.ctypeslib.as_array(XL, (B, n)).copy()
@@ -88,12 +109,13 @@ def run_callback(model, solve_batch, **kw):
                xu=np.ascontiguousarray(model.xu, float), gl=np.ascontiguousarray(model.gl, float),
                gu=np.ascontiguousarray(model.gu, float), x0=np.ascontiguousarray(model.x0, float))
     L = host_lib()
-    L.bnlp_bb_run_cb.argtypes = [c_int, c_int, c_void, c_void, c_void, c_void, c_void, c_void, CB, c_void,
-                                 ctypes.POINTER(BbOptions), ctypes.POINTER(BbResult), c_void]
+    L.bnlp_bb_run_cb2.argtypes = [c_int, c_int, c_void, c_void, c_void, c_void, c_void, c_void, CB, QCB, c_void,
+                                  ctypes.POINTER(BbOptions), ctypes.POINTER(BbResult), c_void]
     o = _opts(**kw)
     keep = CB(cb)
-    rc = L.bnlp_bb_run_cb(n, m, *[arr[k].ctypes.data_as(c_void) for k in ("vt", "xl", "xu", "gl", "gu", "x0")], keep,
-                          None, ctypes.byref(o), ctypes.byref(res), x.ctypes.data_as(c_void))
+    keepq = QCB(qcb) if tqp_solve is not None else ctypes.cast(None, QCB)
+    rc = L.bnlp_bb_run_cb2(n, m, *[arr[k].ctypes.data_as(c_void) for k in ("vt", "xl", "xu", "gl", "gu", "x0")], keep,
+                           keepq, None, ctypes.byref(o), ctypes.byref(res), x.ctypes.data_as(c_void))
     if rc:
         raise RuntimeError("bnlp_bb_run_cb failed")
     d = res.as_dict()

@@ -52,6 +52,10 @@ void BatchedStrongBranchingSolver::markHotStart(OsiTMINLPInterface *si) {
   const int n = si->getNumCols();
   xl0_.assign(si->getColLower(), si->getColLower() + n);
   xu0_.assign(si->getColUpper(), si->getColUpper() + n);
+  if (qp_) {   // BranchingTQP's constructor: freeze the node optimum and its multipliers (BonBranchingTQP.cpp:41-43)
+    xsol0_ = si->problem()->x_sol;
+    duals0_ = si->problem()->duals_sol;
+  }
   if (!preloaded_) cache_.clear();
 }
 
@@ -98,7 +102,22 @@ void BatchedStrongBranchingSolver::prefetch(OsiTMINLPInterface *si, const std::v
       if (w == 0) u[cols[i]] = down_ub[i]; else l[cols[i]] = up_lb[i];
     }
   std::vector<B200Solver::Child> res;
-  app_->OptimizeBatch(*si->problem(), XL, XU, 2 * K, res);
+  if (qp_ && (int)xsol0_.size() == n && (int)duals0_.size() == 2 * n + si->problem()->m) {
+    const int B = 2 * K;
+    std::vector<double> OBJ(B), X((size_t)B * n);
+    std::vector<int> ST(B), IT(B);
+    const int rc = qp_(xsol0_.data(), duals0_.data(), B, XL.data(), XU.data(), OBJ.data(), ST.data(), IT.data(), X.data());
+    res.resize(B);
+    for (int b = 0; b < B; ++b) {
+      res[b].obj = OBJ[b];
+      res[b].status = rc ? TNLPSolver::exception : (TNLPSolver::ReturnStatus)ST[b];
+      res[b].iters = IT[b];
+      res[b].x.assign(X.begin() + (size_t)b * n, X.begin() + (size_t)(b + 1) * n);
+      qp_iterations_ += IT[b];
+    }
+  } else {
+    app_->OptimizeBatch(*si->problem(), XL, XU, 2 * K, res);
+  }
   for (int i = 0; i < K; ++i)
     for (int w = 0; w < 2; ++w) cache_[{cols[i], w}] = std::move(res[2 * i + w]);
 }
@@ -205,7 +224,7 @@ struct Node {
 struct Cmp { bool operator()(const Node *a, const Node *b) const { return a->bound > b->bound; } };
 }  // namespace
 
-BbResult bb_run(TMINLP2TNLP &root, BatchSolveFn solve, const BbOptions &opt) {
+BbResult bb_run(TMINLP2TNLP &root, BatchSolveFn solve, const BbOptions &opt, TqpSolveFn tqp) {
   BbResult R;
   const double t0 = now_s();
   const int n = root.n;
@@ -213,6 +232,8 @@ BbResult bb_run(TMINLP2TNLP &root, BatchSolveFn solve, const BbOptions &opt) {
   OsiTMINLPInterface si(&root, &app);
   BatchedStrongBranchingSolver sb(&app);
   si.SetStrongBrachingSolver(&sb);
+  const bool qp_mode = opt.variable_selection == 1 && tqp;
+  if (qp_mode) sb.setQpSurrogate(tqp);
   BatchedChooseVariable chooser(&si, &sb);
   chooser.integer_tolerance = opt.integer_tolerance;
   std::vector<int> ints;
@@ -233,7 +254,7 @@ BbResult bb_run(TMINLP2TNLP &root, BatchSolveFn solve, const BbOptions &opt) {
   double cutoff = 1e100;
   const std::vector<double> xl_root = root.x_l, xu_root = root.x_u;
 
-  if (opt.parallel_nodes > 1) {
+  if (opt.parallel_nodes > 1 && !qp_mode) {
     // ---- round-based expansion: the P best open nodes per round; their node NLPs are one batch and the strong-
     // branching children of all of them are one batch (independent relaxations sharing tape and start point)
     heap.push(first);
@@ -337,7 +358,7 @@ BbResult bb_run(TMINLP2TNLP &root, BatchSolveFn solve, const BbOptions &opt) {
       }
     }
   }
-  while (opt.parallel_nodes <= 1 && (dive || !heap.empty())) {
+  while ((opt.parallel_nodes <= 1 || qp_mode) && (dive || !heap.empty())) {
     Node *nd = dive;
     dive = nullptr;
     if (!nd) { nd = heap.top(); heap.pop(); }
@@ -417,7 +438,7 @@ BbResult bb_run(TMINLP2TNLP &root, BatchSolveFn solve, const BbOptions &opt) {
       bool same = true;   // fixings applied after SB change the bounds: then the cached result is no longer this child
       for (int j = 0; j < n && same; ++j)
         if (j != bcol && (nd->xl[j] != root.x_l[j] || nd->xu[j] != root.x_u[j])) same = false;
-      if (same && !res.empty()) c = sb.lookup(bcol, w == 1);
+      if (same && !res.empty() && !qp_mode) c = sb.lookup(bcol, w == 1);   // QP children are surrogates, never node results
       if (c) { ch[w]->solved = true; ch[w]->obj = c->obj; ch[w]->status = (int)c->status; ch[w]->x = c->x;
                if (c->status == 1 || c->status == 2) ch[w]->bound = std::max(obj, c->obj); }
     }
@@ -429,7 +450,7 @@ BbResult bb_run(TMINLP2TNLP &root, BatchSolveFn solve, const BbOptions &opt) {
   while (!heap.empty()) { R.best_bound = std::min(R.best_bound < -1e99 ? 1e100 : R.best_bound, heap.top()->bound); delete heap.top(); heap.pop(); }
   if (dive) delete dive;
   if (R.status == 0) { R.status = R.best_obj < 1e99 ? 0 : 1; R.best_bound = R.best_obj; }
-  R.ipm_iterations = si.totalIterations() + app.totalBatchIterations();
+  R.ipm_iterations = si.totalIterations() + app.totalBatchIterations() + sb.qpIterations();
   R.seconds = now_s() - t0;
   root.x_l = xl_root; root.x_u = xu_root;
   return R;

@@ -20,6 +20,11 @@ namespace Bonmin {
 using BatchSolveFn = std::function<int(int B, const double *XL, const double *XU, const double *X0, double *OBJ,
                                        int *STATUS, int *ITERS, double *X, double *G, double *DUALS)>;
 
+// B x QpBranchingSolver::solveFromHotStart (BonQpBranchingSolver.cpp:96-116): the node's optimum (x_sol, duals_sol) and
+// the children's bounds in the original variables; same meaning as bnlp_tqp_solve_batch (include/bnlp.h)
+using TqpSolveFn = std::function<int(const double *x_sol, const double *duals_sol, int B, const double *XL,
+                                     const double *XU, double *OBJ, int *STATUS, int *ITERS, double *X)>;
+
 class B200Solver : public TNLPSolver {
  public:
   explicit B200Solver(BatchSolveFn fn) : solve_(std::move(fn)) {}
@@ -48,6 +53,10 @@ class B200Solver : public TNLPSolver {
 class BatchedStrongBranchingSolver : public StrongBranchingSolver {
  public:
   explicit BatchedStrongBranchingSolver(B200Solver *app) : app_(app) {}
+  // QpBranchingSolver flavour (BonQpBranchingSolver.cpp:50-116): children are solved on the BranchingTQP surrogate built
+  // at the node optimum that markHotStart sees, instead of as full NLPs
+  void setQpSurrogate(TqpSolveFn f) { qp_ = std::move(f); }
+  bool isQp() const { return (bool)qp_; }
   void markHotStart(OsiTMINLPInterface *si) override;
   TNLPSolver::ReturnStatus solveFromHotStart(OsiTMINLPInterface *si) override;
   void unmarkHotStart(OsiTMINLPInterface *si) override;
@@ -62,16 +71,20 @@ class BatchedStrongBranchingSolver : public StrongBranchingSolver {
   bool preloaded() const { return preloaded_; }
   int cacheHits() const { return hits_; }
   int cacheMisses() const { return misses_; }
+  long qpIterations() const { return qp_iterations_; }
   const B200Solver::Child *lookup(int col, bool up) const;
 
  private:
   B200Solver *app_;
+  TqpSolveFn qp_;
+  std::vector<double> xsol0_, duals0_;   // node optimum at markHotStart (what BranchingTQP's constructor reads)
   std::vector<double> xl0_, xu0_;
   std::map<std::pair<int, int>, B200Solver::Child> cache_;   // (column, way) -> result
   std::vector<std::map<std::pair<int, int>, B200Solver::Child>> multi_;
   std::vector<std::pair<std::vector<double>, std::vector<double>>> multi_bounds_;
   bool preloaded_ = false;
   int hits_ = 0, misses_ = 0;
+  long qp_iterations_ = 0;
 };
 
 struct StrongResult {  // what HotInfo holds per candidate (BonChooseVariable.hpp:109-113: -1 not done, 0 feasible, 1 infeasible, 2 not finished)
@@ -107,6 +120,7 @@ struct BbOptions {
   double allowable_gap = 0.0, allowable_fraction_gap = 0.0;   // :484-497
   int node_limit = 1000000;
   int parallel_nodes = 1;               // > 1: that many best-bound nodes are expanded per round with ONE batched launch
+  int variable_selection = 0;           // 0 NLP strong branching, 1 QP strong branching (needs a TqpSolveFn)
   double time_limit = 1e10;
   int log_level = 0;
 };
@@ -118,6 +132,6 @@ struct BbResult {
   long ipm_iterations = 0;
   double seconds = 0;
 };
-BbResult bb_run(TMINLP2TNLP &root, BatchSolveFn solve, const BbOptions &opt);
+BbResult bb_run(TMINLP2TNLP &root, BatchSolveFn solve, const BbOptions &opt, TqpSolveFn tqp = nullptr);
 
 }  // namespace Bonmin

@@ -11,6 +11,12 @@ extern "C" {
 int bnlp_bb_run_cb(int n, int m, const int *var_type, const double *xl, const double *xu, const double *gl,
                    const double *gu, const double *x0, bnlp_batch_solve_cb cb, void *ctx, const bnlp_bb_options *o,
                    bnlp_bb_result *res, double *best_x) {
+  return bnlp_bb_run_cb2(n, m, var_type, xl, xu, gl, gu, x0, cb, nullptr, ctx, o, res, best_x);
+}
+
+int bnlp_bb_run_cb2(int n, int m, const int *var_type, const double *xl, const double *xu, const double *gl,
+                    const double *gu, const double *x0, bnlp_batch_solve_cb cb, bnlp_tqp_solve_cb qp_cb, void *ctx,
+                    const bnlp_bb_options *o, bnlp_bb_result *res, double *best_x) {
   using namespace Bonmin;
   TMINLP2TNLP root;
   root.n = n; root.m = m;
@@ -28,10 +34,15 @@ int bnlp_bb_run_cb(int n, int m, const int *var_type, const double *xl, const do
     if (o->time_limit > 0) opt.time_limit = o->time_limit;
     opt.log_level = o->log_level;
     if (o->parallel_nodes > 0) opt.parallel_nodes = o->parallel_nodes;
+    opt.variable_selection = o->variable_selection;
   }
+  TqpSolveFn qfn;
+  if (qp_cb)
+    qfn = [qp_cb, ctx](const double *xs, const double *du, int B, const double *XL, const double *XU, double *OBJ, int *ST,
+                       int *IT, double *X) { return qp_cb(ctx, xs, du, B, XL, XU, OBJ, ST, IT, X); };
   BatchSolveFn fn = [cb, ctx](int B, const double *XL, const double *XU, const double *X0, double *OBJ, int *ST, int *IT,
                               double *X, double *G, double *D) { return cb(ctx, B, XL, XU, X0, OBJ, ST, IT, X, G, D); };
-  BbResult r = bb_run(root, fn, opt);
+  BbResult r = bb_run(root, fn, opt, qfn);
   res->status = r.status; res->nodes = r.nodes; res->nlp_solves = r.nlp_solves; res->sb_batches = r.sb_batches;
   res->sb_children = r.sb_children; res->served_from_sb_cache = r.served_from_sb_cache;
   res->ipm_iterations = r.ipm_iterations; res->best_obj = r.best_obj; res->best_bound = r.best_bound; res->seconds = r.seconds;
@@ -53,7 +64,9 @@ int bnlp_bb_run_engine(bnlp_engine *E, const bnlp_problem *P, const bnlp_bb_opti
                double *X, double *G, double *D) {
     return bnlp_solve_batch((bnlp_engine *)ctx, B, XL, XU, X0, 0, OBJ, ST, IT, X, G, D);
   };
-  return bnlp_bb_run_cb(n, m, vt.data(), xl.data(), xu.data(), gl.data(), gu.data(), x0.data(), cb, E, o, res, best_x);
+  auto qcb = [](void *ctx, const double *xs, const double *du, int B, const double *XL, const double *XU, double *OBJ,
+                int *ST, int *IT, double *X) { return bnlp_tqp_solve_batch((bnlp_engine *)ctx, xs, du, B, XL, XU, OBJ, ST, IT, X); };
+  return bnlp_bb_run_cb2(n, m, vt.data(), xl.data(), xu.data(), gl.data(), gu.data(), x0.data(), cb, qcb, E, o, res, best_x);
 }
 #endif
 

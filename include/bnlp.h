@@ -191,6 +191,10 @@ typedef struct bnlp_bb_options {
   double integer_tolerance, cutoff_decr, time_limit;
   int parallel_nodes;          /* > 1: expand that many best-bound nodes per round with one batched launch (not in the
                                   reference: its tree search is strictly one node at a time) */
+  int variable_selection;      /* 0 = NLP strong branching (`variable_selection strong-branching`), 1 = QP strong
+                                  branching (`qp-strong-branching`, src/Algorithms/BonBonminSetup.cpp:447-455): the 2K
+                                  children of a node are solved on the BranchingTQP surrogate; their results rank the
+                                  candidates only (trustStrongForSolution = false, never reused as node relaxations) */
 } bnlp_bb_options;
 typedef struct bnlp_bb_result {
   int status;                 /* 0 optimal, 1 infeasible, 2 limit reached */
@@ -202,6 +206,12 @@ typedef struct bnlp_bb_result {
 int bnlp_bb_run_cb(int n, int m, const int *var_type, const double *xl, const double *xu, const double *gl,
                    const double *gu, const double *x0, bnlp_batch_solve_cb cb, void *ctx, const bnlp_bb_options *o,
                    bnlp_bb_result *res, double *best_x);
+/* same, plus the QP-surrogate provider used when variable_selection = 1 (meaning of bnlp_tqp_solve_batch) */
+typedef int (*bnlp_tqp_solve_cb)(void *ctx, const double *x_sol, const double *duals_sol, int B, const double *XL,
+                                 const double *XU, double *OBJ, int *STATUS, int *ITERS, double *X);
+int bnlp_bb_run_cb2(int n, int m, const int *var_type, const double *xl, const double *xu, const double *gl,
+                    const double *gu, const double *x0, bnlp_batch_solve_cb cb, bnlp_tqp_solve_cb qp_cb, void *ctx,
+                    const bnlp_bb_options *o, bnlp_bb_result *res, double *best_x);
 /* arithmetic provider = the CUDA engine */
 int bnlp_bb_run_engine(bnlp_engine *, const bnlp_problem *, const bnlp_bb_options *o, bnlp_bb_result *res,
                        double *best_x);

@@ -74,3 +74,48 @@ def test_bb_engine_matches_oracle(bnlp_lib, oracle_ipm):
         assert g["status"] == c["status"]
         assert g["best_obj"] == pytest.approx(c["best_obj"], rel=1e-6)
         assert g["nodes"] == c["nodes"] and g["sb_children"] == c["sb_children"]
+
+
+def _oracle_tqp(model, oracle_ipm):
+    """tqp_solve provider built from the CPU restatement of BranchingTQP + the oracle IPM."""
+    from oracle import struct_eval as SE
+    ev = SE.Evaluator(model)
+    INF = 1e19
+
+    def solve(xs, du, XL, XU):
+        qm, f0 = SE.branching_tqp_model(model, ev, xs, du)
+        dl = np.where(XL > -INF, XL - xs, XL)
+        dh = np.where(XU < INF, XU - xs, XU)
+        r = oracle_ipm.solve_batch(qm, dl, dh, np.zeros(model.n), threads=4)
+        r["obj"] = np.where(r["status"] == 3, r["obj"], r["obj"] + f0)
+        r["x"] = r["x"] + xs
+        return r
+    return solve
+
+
+def test_bb_qp_strong_branching_same_optimum(oracle_ipm):
+    """variable_selection = qp-strong-branching (a8): the candidates are ranked on the BranchingTQP surrogate; the tree
+    differs, the MINLP optimum does not, and QP children are never reused as node relaxations."""
+    for m, kw in [(I.mytoy(), {}), (I.syn_miqcp(12, 6, 3, 3, 4), dict(number_strong_branch=6))]:
+        s = _oracle_solver(m, oracle_ipm)
+        a = bb.run_callback(m, s, **kw)
+        q = bb.run_callback(m, s, tqp_solve=_oracle_tqp(m, oracle_ipm), variable_selection="qp-strong-branching", **kw)
+        assert a["status"] == q["status"] == 0
+        assert q["best_obj"] == pytest.approx(a["best_obj"], rel=1e-6)
+        assert q["served_from_sb_cache"] == 0 and q["sb_children"] > 0
+        assert q["nlp_solves"] == q["nodes"]
+
+
+@pytest.mark.gpu
+def test_bb_engine_qp_strong_branching(bnlp_lib, oracle_ipm):
+    from bonmin_b200.engine import Engine, Problem
+    for m, kw in [(I.mytoy(), {}), (I.syn_miqcp(20, 10, 4, 4, 9), dict(number_strong_branch=10))]:
+        eng = Engine(Problem.from_model(m))
+        g = bb.run_engine(eng, variable_selection="qp-strong-branching", **kw)
+        c = bb.run_callback(m, _oracle_solver(m, oracle_ipm), tqp_solve=_oracle_tqp(m, oracle_ipm),
+                            variable_selection="qp-strong-branching", **kw)
+        n = bb.run_engine(eng, **kw)
+        assert g["status"] == c["status"] == 0
+        assert g["best_obj"] == pytest.approx(c["best_obj"], rel=1e-6)
+        assert g["best_obj"] == pytest.approx(n["best_obj"], rel=1e-6)
+        assert g["nodes"] == c["nodes"] and g["sb_children"] == c["sb_children"]
