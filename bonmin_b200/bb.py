@@ -121,3 +121,79 @@ def run_callback(model, solve_batch, tqp_solve=None, **kw):
     d = res.as_dict()
     d["best_x"] = x
     return d
+
+
+class DiveOptions(ctypes.Structure):
+    _fields_ = [("rule", c_int), ("speculate", c_int), ("integer_tolerance", c_dbl), ("percentage_to_fix", c_dbl),
+                ("seed", ctypes.c_uint)]
+
+
+class DiveResult(ctypes.Structure):
+    _fields_ = [("found", c_int), ("steps", c_int), ("nlp_solves", c_int), ("batches", c_int),
+                ("ipm_iterations", ctypes.c_longlong), ("obj", c_dbl)]
+
+
+GCB = ctypes.CFUNCTYPE(c_int, c_void, P_dbl, P_dbl)
+DIVE_RULES = {"fractional": 0, "vectorLength": 1}
+
+
+def dive_engine(eng: "_e.Engine", node, cutoff=1e100, rule="fractional", speculate=True, xl=None, xu=None):
+    """HeuristicDive from a solved relaxation `node` (dict with x, g, obj of Engine.solve_batch row 0) on the engine."""
+    info = eng.problem.info()
+    xl = np.ascontiguousarray(info["xl"] if xl is None else xl, float)
+    xu = np.ascontiguousarray(info["xu"] if xu is None else xu, float)
+    xs = np.ascontiguousarray(node["x"], float)
+    gs = np.ascontiguousarray(node["g"], float)
+    res, x = DiveResult(), np.zeros(eng.n)
+    o = DiveOptions(DIVE_RULES[rule], int(speculate), 0.0, 0.0, 1)
+    L = _e.lib()
+    L.bnlp_dive_run_engine.argtypes = [c_void, c_void, c_void, c_void, c_void, c_void, c_dbl, c_dbl,
+                                       ctypes.POINTER(DiveOptions), ctypes.POINTER(DiveResult), c_void]
+    rc = L.bnlp_dive_run_engine(eng.h, eng.problem.h, xl.ctypes.data_as(c_void), xu.ctypes.data_as(c_void),
+                                xs.ctypes.data_as(c_void), gs.ctypes.data_as(c_void), float(node["obj"]), float(cutoff),
+                                ctypes.byref(o), ctypes.byref(res), x.ctypes.data_as(c_void))
+    if rc:
+        raise _e.BnlpError("bnlp_dive_run_engine failed")
+    d = {k: getattr(res, k) for k, _ in res._fields_}
+    d["x"] = x
+    return d
+
+
+def dive_callback(model, solve_batch, grad_f, column_length, node, cutoff=1e100, rule="fractional", speculate=True):
+    """Same dive with Python providers: solve_batch as in run_callback, grad_f(x) -> gradient of the objective."""
+    n, m = model.n, model.m
+
+    def cb(ctx, B, XL, XU, X0, OBJ, ST, IT, X, G, D):
+        r = solve_batch(np.ctypeslib.as_array(XL, (B, n)).copy(), np.ctypeslib.as_array(XU, (B, n)).copy(),
+                        np.ctypeslib.as_array(X0, (n,)).copy())
+        np.ctypeslib.as_array(OBJ, (B,))[:] = r["obj"]
+        np.ctypeslib.as_array(ST, (B,))[:] = r["status"]
+        np.ctypeslib.as_array(IT, (B,))[:] = r["iters"]
+        if X:
+            np.ctypeslib.as_array(X, (B, n))[:] = r["x"]
+        if G and m:
+            np.ctypeslib.as_array(G, (B, m))[:] = r["g"]
+        return 0
+
+    def gcb(ctx, X, GF):
+        np.ctypeslib.as_array(GF, (n,))[:] = grad_f(np.ctypeslib.as_array(X, (n,)).copy())
+        return 0
+
+    arr = dict(vt=np.ascontiguousarray(model.vtype, np.int32), xl=np.ascontiguousarray(model.xl, float),
+               xu=np.ascontiguousarray(model.xu, float), gl=np.ascontiguousarray(model.gl, float),
+               gu=np.ascontiguousarray(model.gu, float), xs=np.ascontiguousarray(node["x"], float),
+               gs=np.ascontiguousarray(node["g"], float), cl=np.ascontiguousarray(column_length, np.int32))
+    res, x = DiveResult(), np.zeros(n)
+    o = DiveOptions(DIVE_RULES[rule], int(speculate), 0.0, 0.0, 1)
+    L = host_lib()
+    L.bnlp_dive_run_cb.argtypes = [c_int, c_int] + [c_void] * 7 + [c_dbl, c_void, c_dbl, CB, GCB, c_void,
+                                                                   ctypes.POINTER(DiveOptions), ctypes.POINTER(DiveResult), c_void]
+    k1, k2 = CB(cb), GCB(gcb)
+    p = lambda k: arr[k].ctypes.data_as(c_void)
+    rc = L.bnlp_dive_run_cb(n, m, p("vt"), p("xl"), p("xu"), p("gl"), p("gu"), p("xs"), p("gs"), float(node["obj"]), p("cl"),
+                            float(cutoff), k1, k2, None, ctypes.byref(o), ctypes.byref(res), x.ctypes.data_as(c_void))
+    if rc:
+        raise RuntimeError("bnlp_dive_run_cb failed")
+    d = {k: getattr(res, k) for k, _ in res._fields_}
+    d["x"] = x
+    return d

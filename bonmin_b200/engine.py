@@ -40,7 +40,7 @@ class OaTols(ctypes.Structure):
 EXPORTS = ["bnlp_last_error", "bnlp_problem_from_nl", "bnlp_problem_from_tape", "bnlp_problem_free",
            "bnlp_problem_sizes", "bnlp_problem_info", "bnlp_engine_create", "bnlp_engine_free", "bnlp_eval_batch",
            "bnlp_solve_batch", "bnlp_solve_batch_device", "bnlp_oa_capacity", "bnlp_oa_batch", "bnlp_engine_stats",
-           "bnlp_engine_launches", "bnlp_measure_fp64_peak", "bnlp_bb_run_cb", "bnlp_bb_run_cb2", "bnlp_bb_run_engine", "bnlp_violation_batch",
+           "bnlp_engine_launches", "bnlp_measure_fp64_peak", "bnlp_bb_run_cb", "bnlp_bb_run_cb2", "bnlp_bb_run_engine", "bnlp_dive_run_cb", "bnlp_dive_run_engine", "bnlp_violation_batch",
            "bnlp_benders_batch", "bnlp_branching_tqp", "bnlp_tqp_solve_batch"]
 
 

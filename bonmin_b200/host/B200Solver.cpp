@@ -456,4 +456,149 @@ BbResult bb_run(TMINLP2TNLP &root, BatchSolveFn solve, const BbOptions &opt, Tqp
   return R;
 }
 
+// ------------------------------------------------------------------------------------------------ NLP diving
+DiveResult dive_run(TMINLP2TNLP &minlp, BatchSolveFn solve, GradFFn grad_f, const std::vector<int> &column_length,
+                    double solutionValue, const DiveOptions &opt) {
+  DiveResult R;
+  const int n = minlp.n, m = minlp.m;
+  const double integerTolerance = opt.integer_tolerance;
+  double primalTolerance = 1.0e-6;
+  // adjustPrimalTolerance (:335-358)
+  for (int i = 0; i < m && i < (int)minlp.g_sol.size(); ++i) {
+    if (minlp.g_sol[i] < minlp.g_l[i] - primalTolerance) primalTolerance = minlp.g_l[i] - minlp.g_sol[i];
+    else if (minlp.g_sol[i] > minlp.g_u[i] + primalTolerance) primalTolerance = minlp.g_sol[i] - minlp.g_u[i];
+  }
+  std::vector<double> newSolution = minlp.x_sol, new_g = minlp.g_sol;
+  std::vector<int> integerColumns;
+  int numberFractionalVariables = 0;
+  for (int j = 0; j < n; ++j)
+    if (minlp.var_types[j] != 0) {
+      integerColumns.push_back(j);
+      if (std::fabs(std::floor(newSolution[j] + 0.5) - newSolution[j]) > integerTolerance) numberFractionalVariables++;
+    }
+  const int numberIntegers = (int)integerColumns.size();
+  const int maxNumberAtBoundToFix = (int)std::floor(opt.percentage_to_fix * numberIntegers);
+  unsigned long long rng = 0x5DEECE66DULL ^ opt.seed;
+  auto drand = [&]() { rng = (rng * 0x5DEECE66DULL + 0xB) & ((1ULL << 48) - 1); return (double)rng / (double)(1ULL << 48); };
+  std::vector<double> &x_l = minlp.x_l, &x_u = minlp.x_u;
+  std::vector<double> gradient(n, 0.0);
+  bool last_success = true;
+  double curObj = minlp.obj_value;   // objective of newSolution
+
+  auto select = [&](int &bestColumn, int &bestRound) {
+    bestColumn = -1; bestRound = -1;
+    double best = 1e300;
+    if (opt.rule == 1 && grad_f) grad_f(newSolution.data(), gradient.data());
+    for (int j : integerColumns) {
+      const double value = newSolution[j];
+      if (!(std::fabs(std::floor(value + 0.5) - value) > integerTolerance)) continue;
+      const double below = std::floor(value), above = std::ceil(value);
+      const double downFraction = below >= x_l[j] ? value - below : 1e300;
+      const double upFraction = above <= x_u[j] ? above - value : 1e300;
+      double score;
+      int round;
+      if (opt.rule == 0) {   // HeuristicDiveFractional::selectVariableToBranch (:55-108)
+        if (downFraction < upFraction) { score = downFraction; round = -1; }
+        else if (downFraction > upFraction) { score = upFraction; round = 1; }
+        else if (drand() < 0.5) { score = downFraction; round = -1; }
+        else { score = upFraction; round = 1; }
+      } else {               // HeuristicDiveVectorLength::selectVariableToBranch (:93-159)
+        const double g = gradient[j];
+        double objdelta;
+        if (g >= 0.0 && upFraction < 1e300) { objdelta = g * upFraction; round = 1; }
+        else if (g < 0.0 && downFraction < 1e300) { objdelta = g * downFraction; round = -1; }
+        else if (upFraction < 1e300) { objdelta = g * upFraction; round = 1; }
+        else { objdelta = g * downFraction; round = -1; }
+        const int len = j < (int)column_length.size() ? column_length[j] : 0;
+        score = (objdelta + 1e-6) / ((double)len + 1.0);
+      }
+      if (score < best) { best = score; bestColumn = j; bestRound = round; }
+    }
+  };
+
+  struct Attempt { std::vector<double> xl, xu; };
+  while (numberFractionalVariables) {
+    R.steps++;
+    int bestColumn, bestRound;
+    select(bestColumn, bestRound);
+    // integer variables sitting at a bound get fixed there, up to percentage_to_fix of them (:146-169)
+    std::vector<int> columnFixed;
+    std::vector<double> originalBound;
+    std::vector<char> fixedAtLowerBound;
+    for (int j : integerColumns) {
+      const double value = newSolution[j];
+      if (std::fabs(std::floor(value + 0.5) - value) <= integerTolerance && (int)columnFixed.size() < maxNumberAtBoundToFix) {
+        if (std::fabs(x_l[j] - value) <= integerTolerance && x_l[j] != x_u[j]) {
+          columnFixed.push_back(j); originalBound.push_back(x_u[j]); fixedAtLowerBound.push_back(1);
+          x_u[j] = x_l[j];
+        } else if (std::fabs(x_u[j] - value) <= integerTolerance && x_l[j] != x_u[j]) {
+          columnFixed.push_back(j); originalBound.push_back(x_l[j]); fixedAtLowerBound.push_back(0);
+          x_l[j] = x_u[j];
+        }
+        if ((int)columnFixed.size() == maxNumberAtBoundToFix) break;
+      }
+    }
+    if (bestColumn < 0) break;
+    const double keepL = x_l[bestColumn], keepU = x_u[bestColumn];
+    const double dn = std::floor(newSolution[bestColumn]), up = std::ceil(newSolution[bestColumn]);
+    // the ladder of :171-207 as explicit bound sets: 0 = fixings + round, 1 = no fixings + round, 2 = no fixings + flip
+    std::vector<Attempt> ladder;
+    auto with_round = [&](std::vector<double> xl, std::vector<double> xu, int round) {
+      xl[bestColumn] = keepL; xu[bestColumn] = keepU;
+      if (round < 0) xu[bestColumn] = dn; else xl[bestColumn] = up;
+      return Attempt{std::move(xl), std::move(xu)};
+    };
+    ladder.push_back(with_round(x_l, x_u, bestRound));
+    std::vector<double> nl = x_l, nu = x_u;
+    for (size_t i = 0; i < columnFixed.size(); ++i) {
+      if (fixedAtLowerBound[i]) nu[columnFixed[i]] = originalBound[i]; else nl[columnFixed[i]] = originalBound[i];
+    }
+    if (!columnFixed.empty()) ladder.push_back(with_round(nl, nu, bestRound));
+    ladder.push_back(with_round(nl, nu, -bestRound));
+    const int L = (int)ladder.size();
+    std::vector<double> OBJ(L), X((size_t)L * n), G((size_t)L * std::max(m, 1));
+    std::vector<int> ST(L, 0), IT(L, 0);
+    std::vector<char> have(L, 0);
+    auto run = [&](int a0, int cnt) {
+      std::vector<double> XL((size_t)cnt * n), XU((size_t)cnt * n);
+      for (int a = 0; a < cnt; ++a) {
+        std::copy(ladder[a0 + a].xl.begin(), ladder[a0 + a].xl.end(), &XL[(size_t)a * n]);
+        std::copy(ladder[a0 + a].xu.begin(), ladder[a0 + a].xu.end(), &XU[(size_t)a * n]);
+      }
+      const int rc = solve(cnt, XL.data(), XU.data(), minlp.x_init.data(), &OBJ[a0], &ST[a0], &IT[a0], &X[(size_t)a0 * n],
+                           &G[(size_t)a0 * std::max(m, 1)], nullptr);
+      R.batches++;
+      R.nlp_solves += cnt;
+      for (int a = 0; a < cnt; ++a) { have[a0 + a] = 1; R.ipm_iterations += IT[a0 + a]; if (rc) ST[a0 + a] = TNLPSolver::exception; }
+    };
+    if (opt.speculate) run(0, L);
+    int used = -1;
+    for (int a = 0; a < L; ++a) {       // replay: first attempt whose status is Ipopt SUCCESS (:173)
+      if (!have[a]) run(a, 1);
+      if (ST[a] == TNLPSolver::solvedOptimal) { used = a; break; }
+    }
+    last_success = used >= 0;
+    if (used >= 0) { x_l = ladder[used].xl; x_u = ladder[used].xu; }
+    else { x_l = ladder[L - 1].xl; x_u = ladder[L - 1].xu; break; }
+    newSolution.assign(X.begin() + (size_t)used * n, X.begin() + (size_t)(used + 1) * n);
+    if (m) new_g.assign(G.begin() + (size_t)used * m, G.begin() + (size_t)(used + 1) * m);
+    curObj = OBJ[used];
+    if (curObj >= solutionValue) break;              // eval_f at the new point (:216-219)
+    numberFractionalVariables = 0;
+    for (int j : integerColumns)
+      if (std::fabs(std::floor(newSolution[j] + 0.5) - newSolution[j]) > integerTolerance) numberFractionalVariables++;
+  }
+  // final checks (:231-279): bounds, integrality, rows within the primal tolerance, better than the incumbent
+  bool feasible = last_success;
+  for (int j = 0; j < n && feasible; ++j) {
+    const double value = newSolution[j];
+    if (value < x_l[j] || value > x_u[j]) feasible = false;
+    else if (minlp.var_types[j] != 0 && std::fabs(std::floor(value + 0.5) - value) > integerTolerance) feasible = false;
+  }
+  for (int i = 0; i < m && feasible; ++i)
+    if (new_g[i] < minlp.g_l[i] - primalTolerance || new_g[i] > minlp.g_u[i] + primalTolerance) feasible = false;
+  if (feasible && curObj < solutionValue) { R.found = true; R.obj = curObj; R.x = newSolution; }
+  return R;
+}
+
 }  // namespace Bonmin

@@ -132,6 +132,29 @@ struct BbResult {
   long ipm_iterations = 0;
   double seconds = 0;
 };
+// ---- NLP diving heuristics (src/CbcBonmin/Heuristics/BonHeuristicDive.cpp:67-302): a chain of NLPs with progressive
+// rounding.  Each step's retry ladder (with at-bound fixings -> without them -> other rounding direction, :171-207) is up
+// to three NLPs that differ only in bounds: with speculate = true they are ONE batch and the ladder is replayed against it.
+using GradFFn = std::function<int(const double *x, double *grad_f)>;   // TMINLP::eval_grad_f at one point
+struct DiveOptions {
+  int rule = 0;                       // 0 = HeuristicDiveFractional (:55-108), 1 = HeuristicDiveVectorLength (:93-159)
+  double integer_tolerance = 1e-6;    // CbcModel::CbcIntegerTolerance
+  double percentage_to_fix = 0.2;     // BonHeuristicDive.cpp:32
+  bool speculate = true;
+  unsigned seed = 1;                  // tie-break of the fractional rule (CoinDrand48 in the reference)
+};
+struct DiveResult {
+  bool found = false;
+  double obj = 1e100;
+  std::vector<double> x;
+  int steps = 0, nlp_solves = 0, batches = 0;
+  long ipm_iterations = 0;
+};
+// node = the relaxation the dive starts from (x_sol, g_sol, bounds; modified like the reference modifies its clone);
+// column_length = number of rows each column appears in (Jacobian structure), only for rule 1; solution_value = incumbent
+DiveResult dive_run(TMINLP2TNLP &node, BatchSolveFn solve, GradFFn grad_f, const std::vector<int> &column_length,
+                    double solution_value, const DiveOptions &opt);
+
 BbResult bb_run(TMINLP2TNLP &root, BatchSolveFn solve, const BbOptions &opt, TqpSolveFn tqp = nullptr);
 
 }  // namespace Bonmin

@@ -50,7 +50,60 @@ int bnlp_bb_run_cb2(int n, int m, const int *var_type, const double *xl, const d
   return 0;
 }
 
+int bnlp_dive_run_cb(int n, int m, const int *var_type, const double *xl, const double *xu, const double *gl,
+                     const double *gu, const double *x_sol, const double *g_sol, double obj_sol, const int *column_length,
+                     double cutoff, bnlp_batch_solve_cb cb, bnlp_grad_f_cb grad_cb, void *ctx, const bnlp_dive_options *o,
+                     bnlp_dive_result *res, double *better_x) {
+  using namespace Bonmin;
+  TMINLP2TNLP node;
+  node.n = n; node.m = m;
+  node.var_types.assign(var_type, var_type + n);
+  node.x_l.assign(xl, xl + n); node.x_u.assign(xu, xu + n);
+  node.g_l.assign(gl, gl + m); node.g_u.assign(gu, gu + m);
+  node.x_init.assign(x_sol, x_sol + n);
+  node.x_sol.assign(x_sol, x_sol + n);
+  node.g_sol.assign(g_sol, g_sol + m);
+  node.obj_value = obj_sol;
+  DiveOptions opt;
+  if (o) {
+    opt.rule = o->rule; opt.speculate = o->speculate != 0; opt.seed = o->seed;
+    if (o->integer_tolerance > 0) opt.integer_tolerance = o->integer_tolerance;
+    if (o->percentage_to_fix > 0) opt.percentage_to_fix = o->percentage_to_fix;
+  }
+  BatchSolveFn fn = [cb, ctx](int B, const double *XL, const double *XU, const double *X0, double *OBJ, int *ST, int *IT,
+                              double *X, double *G, double *D) { return cb(ctx, B, XL, XU, X0, OBJ, ST, IT, X, G, D); };
+  GradFFn gfn;
+  if (grad_cb) gfn = [grad_cb, ctx](const double *x, double *g) { return grad_cb(ctx, x, g); };
+  std::vector<int> len;
+  if (column_length) len.assign(column_length, column_length + n);
+  DiveResult r = dive_run(node, fn, gfn, len, cutoff, opt);
+  res->found = r.found ? 1 : 0; res->steps = r.steps; res->nlp_solves = r.nlp_solves; res->batches = r.batches;
+  res->ipm_iterations = r.ipm_iterations; res->obj = r.obj;
+  if (better_x && r.found) memcpy(better_x, r.x.data(), sizeof(double) * n);
+  return 0;
+}
+
 #ifdef BNLP_WITH_ENGINE
+int bnlp_dive_run_engine(bnlp_engine *E, const bnlp_problem *P, const double *xl, const double *xu, const double *x_sol,
+                         const double *g_sol, double obj_sol, double cutoff, const bnlp_dive_options *o,
+                         bnlp_dive_result *res, double *better_x) {
+  int n = 0, m = 0, nj = 0;
+  if (!E || !P || bnlp_problem_sizes(P, &n, &m, &nj, nullptr)) return -1;
+  std::vector<int> vt(n), jc(nj), len(n, 0);
+  std::vector<double> gl(m), gu(m);
+  bnlp_problem_info(P, nullptr, jc.data(), nullptr, nullptr, vt.data(), nullptr, nullptr, nullptr, gl.data(), gu.data(), nullptr);
+  for (int e = 0; e < nj; ++e) len[jc[e]]++;   // HeuristicDiveVectorLength::setInternalVariables (:50-91): rows per column
+  auto cb = [](void *ctx, int B, const double *XL, const double *XU, const double *X0, double *OBJ, int *ST, int *IT,
+               double *X, double *G, double *D) {
+    return bnlp_solve_batch((bnlp_engine *)ctx, B, XL, XU, X0, 0, OBJ, ST, IT, X, G, D);
+  };
+  auto gcb = [](void *ctx, const double *x, double *g) {
+    return bnlp_eval_batch((bnlp_engine *)ctx, 1, x, nullptr, 1.0, nullptr, nullptr, g, nullptr, nullptr);
+  };
+  return bnlp_dive_run_cb(n, m, vt.data(), xl, xu, gl.data(), gu.data(), x_sol, g_sol, obj_sol, len.data(), cutoff, cb, gcb, E,
+                          o, res, better_x);
+}
+
 // Product path: the same driver with the CUDA engine as arithmetic provider (no Python in between).
 int bnlp_bb_run_engine(bnlp_engine *E, const bnlp_problem *P, const bnlp_bb_options *o, bnlp_bb_result *res,
                        double *best_x) {

@@ -216,6 +216,31 @@ int bnlp_bb_run_cb2(int n, int m, const int *var_type, const double *xl, const d
 int bnlp_bb_run_engine(bnlp_engine *, const bnlp_problem *, const bnlp_bb_options *o, bnlp_bb_result *res,
                        double *best_x);
 
+/* --- NLP diving heuristics (host control flow; the NLPs of a step are one batch) --------------------------------
+ * Restates HeuristicDive::solution (src/CbcBonmin/Heuristics/BonHeuristicDive.cpp:67-302) with the selection rules of
+ * HeuristicDiveFractional (BonHeuristicDiveFractional.cpp:55-108, rule 0) and HeuristicDiveVectorLength
+ * (BonHeuristicDiveVectorLength.cpp:93-159, rule 1).  The dive starts from a solved relaxation (xl/xu: its bounds, x_sol,
+ * g_sol, obj_sol); cutoff = incumbent value (1e100 if none).  speculate != 0: the retry ladder of one step (:171-207 — with
+ * at-bound fixings, without them, other rounding direction) is solved as ONE batch and replayed; 0: one NLP at a time. */
+typedef int (*bnlp_grad_f_cb)(void *ctx, const double *x, double *grad_f);
+typedef struct bnlp_dive_options {
+  int rule, speculate;
+  double integer_tolerance, percentage_to_fix;   /* 0 = reference defaults 1e-6, 0.2 */
+  unsigned seed;
+} bnlp_dive_options;
+typedef struct bnlp_dive_result {
+  int found, steps, nlp_solves, batches;
+  long long ipm_iterations;
+  double obj;
+} bnlp_dive_result;
+int bnlp_dive_run_cb(int n, int m, const int *var_type, const double *xl, const double *xu, const double *gl,
+                     const double *gu, const double *x_sol, const double *g_sol, double obj_sol, const int *column_length,
+                     double cutoff, bnlp_batch_solve_cb cb, bnlp_grad_f_cb grad_cb, void *ctx, const bnlp_dive_options *o,
+                     bnlp_dive_result *res, double *better_x);
+int bnlp_dive_run_engine(bnlp_engine *, const bnlp_problem *, const double *xl, const double *xu, const double *x_sol,
+                         const double *g_sol, double obj_sol, double cutoff, const bnlp_dive_options *o,
+                         bnlp_dive_result *res, double *better_x);
+
 #ifdef __cplusplus
 }
 #endif
