@@ -32,6 +32,11 @@ class Options(ctypes.Structure):
     _fields_ = [("tol", c_dbl), ("max_iter", c_int), ("ctas_per_device", c_int)]
 
 
+class LpDims(ctypes.Structure):
+    _fields_ = [("n_cols", ctypes.c_int), ("n_rows", ctypes.c_int), ("nnz", ctypes.c_int), ("has_alpha", ctypes.c_int),
+                ("obj_offset", ctypes.c_double)]
+
+
 class OaTols(ctypes.Structure):
     _fields_ = [("tiny", c_dbl), ("very_tiny", c_dbl), ("rhs_relax", c_dbl), ("infty", c_dbl),
                 ("skip_non_violated", c_int)]
@@ -41,7 +46,8 @@ EXPORTS = ["bnlp_last_error", "bnlp_problem_from_nl", "bnlp_problem_from_tape", 
            "bnlp_problem_sizes", "bnlp_problem_info", "bnlp_engine_create", "bnlp_engine_free", "bnlp_eval_batch",
            "bnlp_solve_batch", "bnlp_solve_batch_device", "bnlp_oa_capacity", "bnlp_oa_batch", "bnlp_engine_stats",
            "bnlp_engine_launches", "bnlp_measure_fp64_peak", "bnlp_bb_run_cb", "bnlp_bb_run_cb2", "bnlp_bb_run_engine", "bnlp_dive_run_cb", "bnlp_dive_run_engine", "bnlp_violation_batch",
-           "bnlp_benders_batch", "bnlp_branching_tqp", "bnlp_tqp_solve_batch"]
+           "bnlp_benders_batch", "bnlp_branching_tqp", "bnlp_tqp_solve_batch",
+           "bnlp_extract_linear_relaxation"]
 
 
 def lib():
@@ -73,6 +79,8 @@ def lib():
         L.bnlp_branching_tqp.restype = c_void
         L.bnlp_branching_tqp.argtypes = [c_void, c_void, c_void, P_dbl, ctypes.c_char_p, ctypes.c_size_t]
         L.bnlp_tqp_solve_batch.argtypes = [c_void, c_void, c_void, c_int] + [c_void] * 6
+        L.bnlp_extract_linear_relaxation.argtypes = [c_void, c_void, c_void, c_void, c_void, c_int, ctypes.POINTER(OaTols),
+                                                     ctypes.POINTER(LpDims)] + [c_void] * 10
         L.bnlp_engine_stats.argtypes = [c_void, ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_longlong),
                                         P_dbl]
         L.bnlp_engine_launches.restype = ctypes.c_longlong
@@ -328,6 +336,30 @@ class Engine:
         if want_x:
             out["x"] = X
         return out
+
+    def extract_linear_relaxation(self, x, duals=None, xl=None, xu=None, get_obj=True, tols=None):
+        """OsiTMINLPInterface::extractLinearRelaxation at x: the initial LP as a dict (CSR rows, bounds, objective)."""
+        n, m = self.n, self.m
+        cap = self.problem.nnz_jac + n + 1
+        rs = np.zeros(m + 2, np.int32)
+        ci = np.zeros(cap, np.int32)
+        cv = np.zeros(cap)
+        rl, ru, sr = np.zeros(m + 1), np.zeros(m + 1), np.zeros(m + 1, np.int32)
+        cl, cu, ob, ii = np.zeros(n + 1), np.zeros(n + 1), np.zeros(n + 1), np.zeros(n + 1, np.int32)
+        d = LpDims()
+        t = tols or OaTols(1e-8, 1e-17, 1e-8, 1e19, 0)
+        xx = _d(x)
+        du = None if duals is None else _d(duals)
+        xl_ = None if xl is None else _d(xl)
+        xu_ = None if xu is None else _d(xu)
+        self._ck(lib().bnlp_extract_linear_relaxation(self.h, _vp(xx), _vp(du), _vp(xl_), _vp(xu_), int(get_obj),
+                                                      ctypes.byref(t), ctypes.byref(d), _vp(rs), _vp(ci), _vp(cv), _vp(rl),
+                                                      _vp(ru), _vp(sr), _vp(cl), _vp(cu), _vp(ob), _vp(ii)))
+        R, C, Z = d.n_rows, d.n_cols, d.nnz
+        return dict(n_cols=C, n_rows=R, has_alpha=bool(d.has_alpha), obj_offset=d.obj_offset, row_start=rs[:R + 1].copy(),
+                    col_idx=ci[:Z].copy(), val=cv[:Z].copy(), row_lb=rl[:R].copy(), row_ub=ru[:R].copy(),
+                    src_row=sr[:R].copy(), col_lb=cl[:C].copy(), col_ub=cu[:C].copy(), obj=ob[:C].copy(),
+                    is_integer=ii[:C].copy())
 
     def stats(self):
         it, fa, ms = ctypes.c_longlong(), ctypes.c_longlong(), c_dbl()

@@ -170,6 +170,20 @@ bnlp_problem *bnlp_branching_tqp(bnlp_engine *, const double *x_sol, const doubl
 int bnlp_tqp_solve_batch(bnlp_engine *, const double *x_sol, const double *duals_sol, int B, const double *XL,
                          const double *XU, double *OBJ, int *STATUS, int *ITERS, double *X);
 
+/* The whole initial LP relaxation at x = OsiTMINLPInterface::extractLinearRelaxation + addObjectiveFunction
+ * (src/Interfaces/BonOsiTMINLPInterface.cpp:2378-2590): linear rows copied, nonlinear rows linearised at x with the
+ * +-1e-7 slack (:2430-2440), ranged nonlinear rows with a zero multiplier removed (:2421-2425) and one-sided by the sign
+ * of the multiplier otherwise, coefficients cleaned by cleanNnz, upper sides relaxed by oa_rhs_relax; getObj != 0: a linear
+ * objective is copied (offset -f(0)), a nonlinear one adds the column alpha (cost 1, free) and the objective cut.
+ * duals: 2n+m (getRowPrice layout) or NULL (= all zero); xl/xu: current column bounds or NULL (the model's).
+ * Output: row-major CSR; capacities row_start m+2, col_idx/val nnz_jac+n+1, row_lb/row_ub/src_row m+1 (src_row = model
+ * row, m for the objective cut), col_lb/col_ub/obj/is_integer n+1.  LP infinity = DBL_MAX (OsiClp's getInfinity()). */
+typedef struct bnlp_lp_dims { int n_cols, n_rows, nnz, has_alpha; double obj_offset; } bnlp_lp_dims;
+int bnlp_extract_linear_relaxation(bnlp_engine *, const double *x, const double *duals, const double *xl, const double *xu,
+                                   int getObj, const bnlp_oa_tols *tols, bnlp_lp_dims *dims, int *row_start, int *col_idx,
+                                   double *val, double *row_lb, double *row_ub, int *src_row, double *col_lb,
+                                   double *col_ub, double *obj, int *is_integer);
+
 /* statistics of the last solve call: total IPM iterations, factorisations, device milliseconds
  * (counterparts of totalIterations_/totalNlpSolveTime_, src/Interfaces/BonOsiTMINLPInterface.hpp:482-495) */
 int bnlp_engine_stats(const bnlp_engine *, long long *iterations, long long *factorisations, double *device_ms);

@@ -347,3 +347,74 @@ def branching_tqp_model(model, ev: Evaluator, x_sol, duals_sol):
                         x0=np.zeros(n), c=np.zeros(m + 1), A=A, qd_fn=np.array([0], np.int32),
                         qd=pack_lower(W).reshape(1, n * (n + 1) // 2), terms=[], name="TQP(" + str(model.get("name", "")) + ")")
     return _empty_sparse(q), float(vals[0])
+
+
+def extract_linear_relaxation(ev: Evaluator, x, duals=None, xl=None, xu=None, get_obj=True, tiny=1e-8, very_tiny=1e-17,
+                              rhs_relax=1e-8, infty_=1e19):
+    """CPU restatement of OsiTMINLPInterface::extractLinearRelaxation + addObjectiveFunction
+    (src/Interfaces/BonOsiTMINLPInterface.cpp:2378-2590).  Rows as (src_row, cols, vals, lb, ub).  Deviation shared with
+    the product: bounds of removed rows are removed with them (the reference leaves its bound arrays misaligned after
+    CoinPackedMatrix::deleteRows, :2494-2511).  Test infrastructure only."""
+    M = ev.m_
+    n, m = M.n, M.m
+    DMAX = np.finfo(float).max
+    x = np.asarray(x, float)
+    xl = M.xl if xl is None else xl
+    xu = M.xu if xu is None else xu
+    vals, grads, _ = ev.dense(x)
+    g = vals[1:]
+    rows = []
+    jac_by_row = {}
+    for (i, j) in ev.jac:
+        jac_by_row.setdefault(i, []).append(j)
+    for i in range(m):
+        rl, ru = M.gl[i], M.gu[i]
+        du = 0.0 if duals is None else duals[2 * n + i]
+        cols = jac_by_row.get(i, [])
+        v = [grads[i + 1, j] for j in cols]
+        if ev.con_nonlinear[i]:
+            if rl > -infty_ and ru < infty_ and abs(du) == 0.0:
+                continue
+            lb = (rl - g[i]) - 1e-07 if rl > -infty_ else -DMAX
+            ub = (ru - g[i]) + 1e-07 if ru < infty_ else DMAX
+            if rl > -infty_ and ru < infty_:
+                if du >= 0:
+                    lb = -DMAX
+                if du <= 0:
+                    ub = DMAX
+            lbub = [lb, ub]
+            for j, vj in zip(cols, v):
+                if clean_nnz(vj, xl[j], xu[j], rl, ru, x[j], lbub, tiny, very_tiny, infty_):
+                    if lbub[0] > -DMAX:
+                        lbub[0] += vj * x[j]
+                    if lbub[1] < DMAX:
+                        lbub[1] += vj * x[j]
+            lb, ub = lbub
+        else:
+            lb = rl if rl > -infty_ else -DMAX
+            ub = ru if ru < infty_ else DMAX
+        if ub < DMAX:
+            ub += rhs_relax * max(abs(ub), 1.0)
+        rows.append((i, list(cols), v, lb, ub))
+    out = dict(rows=rows, has_alpha=False, obj=np.zeros(n), obj_offset=0.0)
+    if get_obj:
+        if not ev.obj_nonlinear:
+            out["obj"] = grads[0].copy()
+            out["obj_offset"] = -float(ev.dense(np.zeros(n))[0][0])
+        else:
+            lbub = [-1e300, -vals[0]]
+            cols, v = [], []
+            has_rows = len(rows) > 0
+            for j in range(n):
+                if clean_nnz(grads[0, j], xl[j], xu[j], -DMAX, 0.0, x[j], lbub, tiny if has_rows else 1e-3,
+                             very_tiny if has_rows else 1e-8, infty_):
+                    cols.append(j)
+                    v.append(grads[0, j])
+                    lbub[0] += grads[0, j] * x[j]
+                    lbub[1] += grads[0, j] * x[j]
+            cols.append(n)
+            v.append(-1.0)
+            rows.append((m, cols, v, lbub[0], lbub[1]))
+            out["has_alpha"] = True
+            out["obj"] = np.concatenate([np.zeros(n), [1.0]])
+    return out

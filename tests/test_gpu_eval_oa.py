@@ -188,3 +188,33 @@ def test_branching_tqp_parity(bnlp_lib):
         if m.n > 10:
             assert both.sum() >= 4
         eng.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mk", MODELS)
+def test_extract_linear_relaxation_parity(bnlp_lib, mk):
+    """a10: the initial LP (extractLinearRelaxation + addObjectiveFunction) from the engine equals the CPU restatement:
+    same rows, same columns, coefficients and bounds to 1e-12."""
+    from oracle.struct_eval import extract_linear_relaxation
+    m = mk()
+    eng = _engine(m)
+    ev = Evaluator(m)
+    rng = np.random.default_rng(3)
+    x = np.clip(m.x0 + rng.uniform(-0.2, 0.2, m.n), m.xl, m.xu)
+    duals = np.concatenate([np.zeros(2 * m.n), rng.uniform(0.0, 1.0, m.m) * (rng.random(m.m) < 0.7)])
+    for get_obj in (True, False):
+        got = eng.extract_linear_relaxation(x, duals, get_obj=get_obj)
+        ref = extract_linear_relaxation(ev, x, duals, get_obj=get_obj)
+        assert got["n_rows"] == len(ref["rows"]) and got["has_alpha"] == ref["has_alpha"]
+        assert got["n_cols"] == m.n + (1 if ref["has_alpha"] else 0)
+        for r, (src, cols, vals, lb, ub) in enumerate(ref["rows"]):
+            a, b = got["row_start"][r], got["row_start"][r + 1]
+            assert got["src_row"][r] == src
+            assert got["col_idx"][a:b].tolist() == cols
+            np.testing.assert_allclose(got["val"][a:b], vals, rtol=1e-12, atol=1e-14)
+            assert got["row_lb"][r] == pytest.approx(lb, rel=1e-12, abs=1e-12)
+            assert got["row_ub"][r] == pytest.approx(ub, rel=1e-12, abs=1e-12)
+        np.testing.assert_allclose(got["obj"][:len(ref["obj"])], ref["obj"], rtol=1e-12, atol=1e-14)
+        assert got["obj_offset"] == pytest.approx(ref["obj_offset"], abs=1e-12)
+        assert (got["is_integer"][:m.n] == (np.asarray(m.vtype) != 0)).all()
+    eng.close()

@@ -72,3 +72,40 @@ def test_term_derivatives_finite_differences():
     Hn = np.array([((ev.dense(x + e * np.eye(m.n)[j])[1] - ev.dense(x - e * np.eye(m.n)[j])[1]) / (2 * e)).T @ w
                    for j in range(m.n)])
     assert np.abs(Hn - H0).max() < 1e-5
+
+
+def test_mytoy_extract_linear_relaxation_golden():
+    """test/InterfaceTest.cpp:191-264 (testOa): the OA LP at the root optimum has 4 columns, 3 rows, 7 nonzeros; row 0 =
+    (2/sqrt5) y1 + (1/sqrt5) y2 <= 1/2 + 3/(2 sqrt5) (+1e-7 nonlinear-row slack, +1e-8 relative oa_rhs_relax), row 1
+    <= 0 (+1e-8), row 2 <= 2 (1 + 1e-8); the linear objective is copied (no alpha column)."""
+    from oracle.struct_eval import extract_linear_relaxation
+    m = I.mytoy()
+    ev = Evaluator(m)
+    s5 = 5 ** 0.5
+    x = np.array([0.5 + 1 / s5, 0.5 + 1 / (2 * s5), 0.5 + 1 / s5, 0.0])   # root optimum: y1, y2, x, z
+    # the product orders variables as the model does; find y1, y2 through the nonlinear row's structure
+    lp = extract_linear_relaxation(ev, _toy_point(m, s5), None, get_obj=True)
+    rows = lp["rows"]
+    assert len(rows) == 3 and sum(len(r[1]) for r in rows) == 7 and not lp["has_alpha"]
+    nl = [r for r in rows if ev.con_nonlinear[r[0]]]
+    assert len(nl) == 1
+    coefs = sorted(abs(v) for v in nl[0][2])
+    assert coefs == pytest.approx([1 / s5, 2 / s5], rel=1e-12)
+    ub0 = 0.5 + 3 / (2 * s5)
+    assert nl[0][4] == pytest.approx((ub0 + 1e-7) * (1 + 1e-8), abs=1e-12)
+    assert nl[0][3] == -np.finfo(float).max
+    lin = sorted(r[4] for r in rows if not ev.con_nonlinear[r[0]])
+    assert lin == pytest.approx([1e-8, 2 * (1 + 1e-8)], abs=1e-15)
+    assert np.count_nonzero(lp["obj"]) == 3 and lp["obj_offset"] == 0.0
+
+
+def _toy_point(m, s5):
+    """root optimum of mytoy in the model's own variable order (from the oracle IPM, then snapped to the analytic values)."""
+    from oracle import ipm
+    r = ipm.solve_batch(m, m.xl[None, :], m.xu[None, :], m.x0)
+    x = r["x"][0].copy()
+    for j in range(m.n):
+        for target in (0.5 + 1 / s5, 0.5 + 1 / (2 * s5), 0.0):
+            if abs(x[j] - target) < 1e-5:
+                x[j] = target
+    return x
