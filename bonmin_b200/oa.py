@@ -1,0 +1,151 @@
+"""Host B-OA driver: the outer-approximation decomposition loop of OACutGenerator2::performOa
+(src/Algorithms/OaGenerators/BonOACutGenerator2.cpp:62-284, helpers BonSolverHelp.cpp:49-174, BonOaDecBase.cpp:237-400)
+around the batched engine.  Host control flow only (the reference's MILP master is Cbc; here the master is solved by
+HiGHS through scipy.optimize.milp — an external solver on either side).  What runs on the device:
+
+  * the NLP relaxation and every NLP(y) with the integers fixed      -> provider.solve   (bnlp_solve_batch)
+  * the initial LP (extractLinearRelaxation + addObjectiveFunction)   -> provider.extract (bnlp_extract_linear_relaxation)
+  * the linearisations of all nonlinear rows, at SEVERAL points per pass (the NLP(y) optimum and, ECP style, the master
+    point itself) in one call                                          -> provider.oa      (bnlp_oa_batch)
+
+A provider is any object with those three methods (tests run the same loop on the CPU oracle)."""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+
+DMAX = np.finfo(float).max
+
+
+class EngineProvider:
+    """Arithmetic provider = the CUDA engine (product path)."""
+
+    def __init__(self, eng, model_info=None):
+        self.eng = eng
+        info = model_info or eng.problem.info()
+        self.n, self.m = eng.n, eng.m
+        self.xl, self.xu = info["xl"], info["xu"]
+        self.vtype = info["var_type"]
+        self.x0 = info["x0"]
+
+    def solve(self, XL, XU, x0):
+        return self.eng.solve_batch(XL, XU, x0)
+
+    def extract(self, x, duals):
+        r = self.eng.extract_linear_relaxation(x, duals, get_obj=True)
+        rows = [(int(r["src_row"][k]), r["col_idx"][r["row_start"][k]:r["row_start"][k + 1]].tolist(),
+                 r["val"][r["row_start"][k]:r["row_start"][k + 1]].tolist(), float(r["row_lb"][k]), float(r["row_ub"][k]))
+                for k in range(r["n_rows"])]
+        return dict(rows=rows, has_alpha=r["has_alpha"], obj=r["obj"], obj_offset=r["obj_offset"])
+
+    def oa(self, X, X2=None, theta=0.0):
+        X = np.atleast_2d(X)
+        r = self.eng.oa_batch(X, None, self.xl, self.xu, X2=X2, theta=theta, get_obj=1)
+        out = []
+        for k in range(len(r["src_row"])):
+            if r["src_row"][k] < 0:
+                continue
+            a, b = r["row_start"][k], r["row_start"][k + 1]
+            out.append((int(r["src_row"][k]), r["col"][a:b].tolist(), r["val"][a:b].tolist(), float(r["lb"][k]), float(r["ub"][k])))
+        return out
+
+
+def _solve_master(n_cols, rows, obj, obj_offset, col_lb, col_ub, integer, cutoff):
+    """min obj.x over the cut rows with HiGHS; returns (status, x, bound): status 0 optimal, 1 infeasible / cut off."""
+    from scipy.optimize import Bounds, LinearConstraint, milp
+    from scipy.sparse import csr_matrix
+    indptr, idx, val, lo, hi = [0], [], [], [], []
+    for _, cols, vals, lb, ub in rows:
+        idx.extend(cols)
+        val.extend(vals)
+        indptr.append(len(idx))
+        lo.append(-np.inf if lb <= -1e100 else lb)
+        hi.append(np.inf if ub >= 1e100 else ub)
+    cons = []
+    if rows:
+        cons.append(LinearConstraint(csr_matrix((val, idx, indptr), shape=(len(rows), n_cols)), lo, hi))
+    if cutoff < 1e99:     # OsiDualObjectiveLimit (:150): only points better than the incumbent are of interest
+        cons.append(LinearConstraint(csr_matrix(np.asarray(obj)[None, :]), -np.inf, cutoff - obj_offset))
+    lb = np.where(np.asarray(col_lb) <= -1e100, -np.inf, col_lb)
+    ub = np.where(np.asarray(col_ub) >= 1e100, np.inf, col_ub)
+    res = milp(c=np.asarray(obj, float), constraints=cons, integrality=np.asarray(integer, int), bounds=Bounds(lb, ub),
+               options=dict(mip_rel_gap=0.0))
+    if res.status != 0 or res.x is None:
+        return 1, None, 1e200
+    return 0, res.x, float(res.fun) + obj_offset
+
+
+def run_oa(provider, integer_tolerance=1e-6, cutoff_increment=1e-5, gap_tol=1e-9, max_passes=200, time_limit=1e10,
+           add_master_point=True, log=None):
+    """B-OA.  Returns dict(status 0 optimal / 1 infeasible / 2 limit, best_obj, best_x, lower_bound, passes, nlp_solves,
+    cuts, oa_points, seconds)."""
+    t0 = time.perf_counter()
+    P = provider
+    n = P.n
+    ints = np.flatnonzero(np.asarray(P.vtype) != 0)
+    out = dict(status=2, best_obj=1e100, best_x=None, lower_bound=-1e200, passes=0, nlp_solves=0, cuts=0, oa_points=0)
+    # continuous relaxation and the initial LP at its optimum (BonOaDecBase / BonminSetup::initializeBHyb: the LP is
+    # extracted at the solution of the first NLP)
+    root = P.solve(np.asarray(P.xl)[None, :], np.asarray(P.xu)[None, :], P.x0)
+    out["nlp_solves"] += 1
+    if root["status"][0] not in (1, 2):
+        out["status"] = 1 if root["status"][0] == 3 else 2
+        out["seconds"] = time.perf_counter() - t0
+        return out
+    xr, dr = root["x"][0], root["duals"][0]
+    lp = P.extract(xr, dr)
+    rows = list(lp["rows"])
+    ncols = n + (1 if lp["has_alpha"] else 0)
+    obj = np.zeros(ncols)
+    obj[:len(lp["obj"])] = lp["obj"]
+    col_lb = np.concatenate([P.xl, [-DMAX]])[:ncols]
+    col_ub = np.concatenate([P.xu, [DMAX]])[:ncols]
+    integer = np.zeros(ncols, int)
+    integer[ints] = 1
+    cutoff, ub = 1e100, 1e100
+    last_y = None
+    while out["passes"] < max_passes and time.perf_counter() - t0 < time_limit:
+        st, xm, bound = _solve_master(ncols, rows, obj, lp["obj_offset"], col_lb, col_ub, integer, cutoff)   # subMip_->solve
+        if st != 0:                                       # master infeasible under the cutoff: the incumbent is optimal
+            out["lower_bound"] = max(out["lower_bound"], min(ub, 1e200))
+            out["status"] = 0 if ub < 1e99 else 1
+            break
+        out["lower_bound"] = max(out["lower_bound"], bound)
+        out["passes"] += 1
+        y = np.round(xm[ints])
+        if last_y is not None and np.array_equal(y, last_y):   # isDifferentOnIntegers == false: fathomed (:196-199)
+            out["status"] = 0 if ub < 1e99 else 1
+            break
+        last_y = y
+        if ub < 1e99 and (ub - bound) / max(abs(ub), 1e-10) < gap_tol:
+            out["status"] = 0
+            break
+        # NLP(y): integers fixed at the master's values (fixIntegers, BonSolverHelp.cpp:49-93)
+        XL, XU = np.array(P.xl, float), np.array(P.xu, float)
+        XL[ints] = XU[ints] = y
+        r = P.solve(XL[None, :], XU[None, :], xm[:n])
+        out["nlp_solves"] += 1
+        xs = r["x"][0]
+        if r["status"][0] in (1, 2):                      # post_nlp_solve: feasible -> incumbent and new cutoff (:146-151)
+            if r["obj"][0] < ub:
+                ub = float(r["obj"][0])
+                out["best_obj"], out["best_x"] = ub, xs.copy()
+            cutoff = ub * (1 - cutoff_increment) if ub > 0 else ub * (1 + cutoff_increment)
+            if ub == 0:
+                cutoff = -cutoff_increment
+        # linearise at the NLP(y) point (for an infeasible NLP(y): at its minimum-violation point) and at the master point
+        pts = [xs] + ([np.clip(xm[:n], P.xl, P.xu)] if add_master_point else [])
+        cuts = P.oa(np.array(pts), X2=None)
+        out["oa_points"] += len(pts)
+        new = 0
+        for c in cuts:
+            if c[0] == P.m and ncols == n:               # objective cut of a linear objective: not generated (:2053)
+                continue
+            rows.append(c)
+            new += 1
+        out["cuts"] += new
+        if log:
+            log(f"pass {out['passes']}: master {bound:.6f} ub {ub:.6f} cuts +{new}")
+    out["seconds"] = time.perf_counter() - t0
+    return out

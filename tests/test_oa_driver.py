@@ -1,0 +1,67 @@
+"""Host B-OA driver (bonmin_b200/oa.py): OACutGenerator2::performOa around the batched engine, master
+MILP by HiGHS.  Two different algorithms (B-OA here, B-BB in test_bb.py) must reach the same MINLP optimum."""
+import numpy as np
+import pytest
+
+from bonmin_b200 import bb, oa, instances as I
+from oracle import struct_eval as SE
+
+scipy_milp = pytest.importorskip("scipy.optimize", reason="HiGHS master needs scipy").milp
+
+
+class OracleProvider:
+    """Arithmetic provider = the CPU oracle (checker only)."""
+
+    def __init__(self, model, oracle_ipm):
+        self.model, self.ipm = model, oracle_ipm
+        self.dense = oracle_ipm.dense_arrays(model)
+        self.ev = SE.Evaluator(model)
+        self.n, self.m = model.n, model.m
+        self.xl, self.xu, self.vtype, self.x0 = model.xl, model.xu, model.vtype, model.x0
+
+    def solve(self, XL, XU, x0):
+        return self.ipm.solve_batch(self.model, XL, XU, x0, threads=4, dense=self.dense)
+
+    def extract(self, x, duals):
+        return SE.extract_linear_relaxation(self.ev, x, duals, get_obj=True)
+
+    def oa(self, X, X2=None, theta=0.0):
+        out = []
+        for x in np.atleast_2d(X):
+            out.extend(SE.outer_approximation(self.ev, x, None, self.xl, self.xu, get_obj=1))
+        return out
+
+
+def _bb_opt(m, oracle_ipm, **kw):
+    dense = oracle_ipm.dense_arrays(m)
+    return bb.run_callback(m, lambda XL, XU, x0: oracle_ipm.solve_batch(m, XL, XU, x0, threads=4, dense=dense), **kw)
+
+
+@pytest.mark.parametrize("mk", [lambda: I.mytoy(), lambda: I.syn_miqcp(12, 6, 3, 3, 4),
+                                lambda: I.syn_cvx_minlp(16, 6, 3, 5, 2)])
+def test_oa_reaches_the_bb_optimum(oracle_ipm, mk):
+    m = mk()
+    r = oa.run_oa(OracleProvider(m, oracle_ipm))
+    b = _bb_opt(m, oracle_ipm, number_strong_branch=6)
+    assert r["status"] == b["status"] == 0
+    # both stop on tolerances (B-BB cutoff_decr 1e-5, B-OA cutoff increment 1e-5 relative, 1e-8 bound relaxation)
+    assert r["best_obj"] == pytest.approx(b["best_obj"], rel=2e-5, abs=2e-5)
+    xi = r["best_x"][np.asarray(m.vtype) != 0]
+    assert np.abs(xi - np.round(xi)).max() <= 1e-6
+    assert r["lower_bound"] <= r["best_obj"] + 1e-6 * max(1.0, abs(r["best_obj"])) or r["lower_bound"] >= 1e49
+    assert r["cuts"] > 0 and r["oa_points"] >= r["passes"]
+
+
+@pytest.mark.gpu
+def test_oa_engine_matches_oracle(bnlp_lib, oracle_ipm):
+    from bonmin_b200.engine import Engine, Problem
+    for m in (I.mytoy(), I.syn_miqcp(12, 6, 3, 3, 4), I.syn_cvx_minlp(16, 6, 3, 5, 2)):
+        eng = Engine(Problem.from_model(m))
+        g = oa.run_oa(oa.EngineProvider(eng))
+        c = oa.run_oa(OracleProvider(m, oracle_ipm))
+        assert g["status"] == c["status"] == 0
+        assert g["best_obj"] == pytest.approx(c["best_obj"], rel=1e-6, abs=1e-8)
+        # the master (HiGHS) may pick another of several optimal integer points when cut coefficients differ in the last
+        # bit, so pass counts can differ by a few; the optimum cannot
+        assert abs(g["passes"] - c["passes"]) <= max(3, c["passes"] // 5)
+        eng.close()
