@@ -98,10 +98,15 @@ __device__ __forceinline__ double ld_stream_v(const double *p) {
   return v;
 }
 
-// ---- block reductions: v[0..NS) summed, v[NS..NS+NM) maxed; result broadcast to every thread
+// ---- block reductions: v[0..NS) summed, v[NS..NS+NM) maxed; result broadcast to every thread.
+// Stage 1: warp shuffles, lane 0 of every warp leaves its K partials in red[w*K + k].  Stage 2: thread 16k + q picks up
+// partial q of value k and the 16-lane groups finish with four more shuffles (all K values in parallel; the old version
+// had every thread walk all 16 x K partials).  Two barriers.
 template <int NS, int NM>
 __device__ __forceinline__ void block_reduce(double *v, double *red) {
   constexpr int K = NS + NM;
+  static_assert(K * IPM_NW <= IPM_NT && IPM_NW == 16, "stage 2 uses one thread per (value, warp) pair");
+  __shared__ double red_out[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) {
 #pragma unroll
@@ -110,19 +115,25 @@ __device__ __forceinline__ void block_reduce(double *v, double *red) {
       v[k] = (k < NS) ? v[k] + t : fmax(v[k], t);
     }
   }
-  __syncthreads();
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   if (lane == 0) {
 #pragma unroll
     for (int k = 0; k < K; ++k) red[w * K + k] = v[k];
   }
   __syncthreads();
+  if (threadIdx.x < ((K * IPM_NW + 31) & ~31)) {      // whole warps take part in the shuffles
+    const int k = threadIdx.x >> 4, q = threadIdx.x & 15;
+    double a = (k < K) ? red[q * K + k] : 0.0;
 #pragma unroll
-  for (int k = 0; k < K; ++k) {
-    double a = red[k];
-    for (int q = 1; q < IPM_NW; ++q) a = (k < NS) ? a + red[q * K + k] : fmax(a, red[q * K + k]);
-    v[k] = a;
+    for (int o = 8; o > 0; o >>= 1) {
+      const double t = __shfl_xor_sync(0xffffffffu, a, o);
+      a = (k < NS) ? a + t : fmax(a, t);
+    }
+    if (q == 0 && k < K) red_out[k] = a;
   }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < K; ++k) v[k] = red_out[k];
 }
 
 // ---- H[i,k] += sign * sum_c M[c][i] * M[c][k]   for lo <= k <= i < hi  (packed lower triangle, 4x4 register tiles)

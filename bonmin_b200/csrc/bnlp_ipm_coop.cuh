@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
   double th_hist[4] = {0, 0, 0, 0}, a_last0 = 1.0, a_last1 = 1.0;
   long long nfact = 0;
   long long chdbg[TIMERS ? 3 : 1] = {0};
-  long long dbg2[TIMERS ? 8 : 1] = {0};
+  long long dbg2[TIMERS ? 12 : 1] = {0};
   long long dbg_t0 = 0;
 #define D2_START() do { if constexpr (TIMERS) dbg_t0 = clock64(); } while (0)
 #define D2_MARK(i) do { if constexpr (TIMERS) { __syncthreads(); long long t_ = clock64(); dbg2[i] += t_ - dbg_t0; dbg_t0 = t_; } } while (0)
@@ -598,6 +598,7 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
       }
       if (r0 + IPM_KC < R) prefetch_row(r0 + IPM_KC + wid);
       __syncthreads();
+      D2_MARK(8);
       if (tid < N) {
         for (int c = 0; c < kc; ++c) {
           const double sv = stage[c * lds + tid];
@@ -606,8 +607,11 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
           a1 = fma(sv, p1[r0 + c], a1);
         }
       }
-      syrk_dmma(H, 0, N, stage, lds, kc4, 1.0);
+      D2_MARK(9);
+      if (kc4 == IPM_KC) syrk_dmma(H, 0, N, stage, lds, IPM_KC, 1.0);   // compile-time rank: the k loop unrolls
+      else syrk_dmma(H, 0, N, stage, lds, kc4, 1.0);
       __syncthreads();
+      D2_MARK(10);
     }
     D2_MARK(2);
     // sweep over variables: Lagrangian gradient, right-hand sides (into the augmented rows), Sigma_x
@@ -1131,7 +1135,7 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
   }
   if constexpr (TIMERS) {
   if (tid == 0 && cta == 0) printf("[dbg all] diag-warp %llu syrkrest-warp1 %llu\n", g_dbg_cycles[0], g_dbg_cycles[1]);
-  if (tid == 0 && cta == 0) printf("[dbg cta0] chol: diag0 %lld trsm %lld syrk+diag %lld | top: rows %lld zeroH %lld chunks %lld vars %lld | C: backsolve %lld dots %lld ftb/mu %lld dir %lld\n", chdbg[0], chdbg[1], chdbg[2], dbg2[0], dbg2[1], dbg2[2], dbg2[3], dbg2[4], dbg2[5], dbg2[6], dbg2[7]);
+  if (tid == 0 && cta == 0) printf("[dbg cta0] chol: diag0 %lld trsm %lld syrk+diag %lld | top: rows %lld zeroH %lld chunks %lld vars %lld | C: backsolve %lld dots %lld ftb/mu %lld dir %lld | chunk: stage %lld jt %lld syrk %lld\n", chdbg[0], chdbg[1], chdbg[2], dbg2[0], dbg2[1], dbg2[2], dbg2[3], dbg2[4], dbg2[5], dbg2[6], dbg2[7], dbg2[8], dbg2[9], dbg2[10]);
   if (A.phase_cycles && tid == 0)
     for (int q = 0; q < 10; ++q) atomicAdd((unsigned long long *)&A.phase_cycles[q], (unsigned long long)ph[q]);
   }
