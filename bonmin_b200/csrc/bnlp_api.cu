@@ -325,7 +325,8 @@ extern "C" bnlp_engine *bnlp_engine_create(const bnlp_problem *prob, const int *
       int coopAttr = 0;
       cudaDeviceGetAttribute(&coopAttr, cudaDevAttrCooperativeLaunch, D.id);
       E->coop_ok = E->ipm_supported && coopAttr && n <= 256 && E->nq > 0 && E->E == 0 && M.terms.empty() && E->coop_smem_bytes + 1024 <= D.smem_optin &&
-                   (size_t)COOP_RB * (E->nqpad + 4) <= (size_t)(IPM_NW + 1) * lds && (size_t)COOP_RB * E->ldd <= (size_t)(IPM_NW + 1) * lds &&
+                   (size_t)COOP_RB * (E->nqpad + 4) <= (size_t)(IPM_NW + 1) * lds &&
+                   (size_t)COOP_RB * E->ldd <= (size_t)(IPM_NW + 1) * lds + (size_t)(n + 3) * (n + 4) / 2 &&   // U-pass operands live in H + staging
                    !getenv("BNLP_NO_COOP");
     }
     if (E->coop_ok && ipm_coop_set_smem(E->coop_smem_bytes) != cudaSuccess) {

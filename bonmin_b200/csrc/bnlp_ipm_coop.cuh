@@ -27,7 +27,8 @@ namespace cg = cooperative_groups;
 #define UEXP_LOAD(p) ld_stream_v(p)
 #endif
 __device__ unsigned long long g_dbg_cycles[4];
-constexpr int COOP_RB = 16;   // children per cooperative group (two m8 tiles)
+constexpr int COOP_RB = 32;   // children per cooperative group (four m8 tiles): every block element crosses L2->SM once per 32 children
+constexpr int COOP_NP = COOP_RB / 8;
 
 __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -763,7 +764,9 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
       const int lr = lane >> 2, lc = lane & 3;
       for (int t = t0 + wid; t < t1; t += IPM_NW) {
         const int e0 = 16 * t;                       // ldp is a multiple of 16: the line always exists (zero padded)
-        double cE0 = 0, cE1 = 0, cE2 = 0, cE3 = 0, cO0 = 0, cO1 = 0, cO2 = 0, cO3 = 0;
+        double cE[COOP_NP][2], cO[COOP_NP][2];
+#pragma unroll
+        for (int p = 0; p < COOP_NP; ++p) cE[p][0] = cE[p][1] = cO[p][0] = cO[p][1] = 0.0;
         for (int ks = 0; ks < nqpad; ks += 32) {     // 8 k-steps (32 blocks) per round
           double2 qv[8];
 #pragma unroll
@@ -777,26 +780,25 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
           for (int u = 0; u < 8; ++u) {
             if (ks + 4 * u < nqpad) {
               const int kk = ks + 4 * u + lc;
-              const double w0v = wsm[lr * ldw + kk], w1v = wsm[(8 + lr) * ldw + kk];
-              dmma(cE0, cE1, w0v, qv[u].x);
-              dmma(cE2, cE3, w1v, qv[u].x);
-              dmma(cO0, cO1, w0v, qv[u].y);
-              dmma(cO2, cO3, w1v, qv[u].y);
+#pragma unroll
+              for (int p = 0; p < COOP_NP; ++p) {
+                const double wv = wsm[(8 * p + lr) * ldw + kk];
+                dmma(cE[p][0], cE[p][1], wv, qv[u].x);
+                dmma(cO[p][0], cO[p][1], wv, qv[u].y);
+              }
             }
           }
         }
-        // even tile: C[child lr (+8)][n = 2lc, 2lc+1] <-> elements e0 + 4lc, e0 + 4lc + 2; odd tile: e0 + 4lc + 1, + 3
-        const int b0i = my_g * COOP_RB + lr, b1i = b0i + 8;
+        // even tile: C[child 8p + lr][n = 2lc, 2lc+1] <-> elements e0 + 4lc, e0 + 4lc + 2; odd tile: e0 + 4lc + 1, + 3
         const int ec = e0 + 4 * lc;
-        if (b0i < G && ec < P) {   // Wbuf rows have stride ldp too
-          double2 *dst = reinterpret_cast<double2 *>(CB.Wbuf + (size_t)b0i * M.ldp + ec);
-          __stcg(dst, make_double2(cE0, cO0));
-          __stcg(dst + 1, make_double2(cE1, cO1));
-        }
-        if (b1i < G && ec < P) {
-          double2 *dst = reinterpret_cast<double2 *>(CB.Wbuf + (size_t)b1i * M.ldp + ec);
-          __stcg(dst, make_double2(cE2, cO2));
-          __stcg(dst + 1, make_double2(cE3, cO3));
+#pragma unroll
+        for (int p = 0; p < COOP_NP; ++p) {
+          const int bi = my_g * COOP_RB + 8 * p + lr;
+          if (bi < G && ec < P) {   // Wbuf rows have stride ldp too
+            double2 *dst = reinterpret_cast<double2 *>(CB.Wbuf + (size_t)bi * M.ldp + ec);
+            __stcg(dst, make_double2(cE[p][0], cO[p][0]));
+            __stcg(dst + 1, make_double2(cE[p][1], cO[p][1]));
+          }
         }
       }
     }
@@ -934,7 +936,7 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
     // 16g .. 16g+15}; k-step s of that group contracts over the columns {16g + 4lc + s}, which is only a permutation of
     // the summation index, so the B fragments are read from Dsm at the same permuted columns.
     if (coop_on) {
-      double *Dsm = stage;   // [16][ldd]
+      double *Dsm = H;   // [COOP_RB][ldd]: the factor in H (and the staging rows behind it) is dead until the next iteration
       for (int e = tid; e < COOP_RB * ldd; e += IPM_NT) {
         const int b = my_g * COOP_RB + e / ldd;
         Dsm[e] = (b < G) ? __ldcg(CB.xd + (size_t)b * ldd + e % ldd) : 0.0;
@@ -950,7 +952,9 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
         const int r = r0 + lr;
         const double2 *Qrow = reinterpret_cast<const double2 *>(M.Qf + ((size_t)qblk[qi] * n + min(r, n - 1)) * M.ldq) + 2 * lc;
         const bool rv = r < n;
-        double c00 = 0, c01 = 0, c10 = 0, c11 = 0;
+        double cu[COOP_NP][2];
+#pragma unroll
+        for (int p = 0; p < COOP_NP; ++p) cu[p][0] = cu[p][1] = 0.0;
         // software pipeline over pairs of groups: 4 x 16-byte loads in flight ahead of the DMMAs that consume them
         double2 aq[2][4];
         auto loadgrp = [&](int g, double2 *dst) {
@@ -973,23 +977,24 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
 #pragma unroll
                   for (int s4 = 0; s4 < 4; ++s4) {
                     const double a = rv ? av[s4] : 0.0;
-                    dmma(c00, c01, a, Dsm[lr * ldd + cb + s4]);
-                    dmma(c10, c11, a, Dsm[(8 + lr) * ldd + cb + s4]);
+#pragma unroll
+                    for (int p = 0; p < COOP_NP; ++p) dmma(cu[p][0], cu[p][1], a, Dsm[(8 * p + lr) * ldd + cb + s4]);
                   }
                 }
               }
             }
           }
         }
-        // C[row = matrix row lr][col = child 2*lc, 2*lc+1 (+8)]
+        // C[row = matrix row lr][col = child 8p + 2lc, + 1]
         if (rv) {
           const size_t off = (size_t)(m + 1) * n + (size_t)k * n + r;   // uq of the child's workspace
 #pragma unroll
-          for (int h = 0; h < 4; ++h) {
-            const int b = my_g * COOP_RB + (h >> 1) * 8 + 2 * lc + (h & 1);
-            const double cv = (h == 0) ? c00 : (h == 1) ? c01 : (h == 2) ? c10 : c11;
-            if (b < G) __stcg(A.ws + (size_t)b * A.ws_stride + off, cv);
-          }
+          for (int p = 0; p < COOP_NP; ++p)
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              const int b = my_g * COOP_RB + 8 * p + 2 * lc + hh;
+              if (b < G) __stcg(A.ws + (size_t)b * A.ws_stride + off, cu[p][hh]);
+            }
         }
       }
     }

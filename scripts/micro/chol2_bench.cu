@@ -27,14 +27,14 @@ __global__ void __launch_bounds__(512, 1) bench(int N, const double *H0, double 
   if (which == 1) ok = chol2<false>(H, N, Nrows, stage, lds, &fail, dbg);
   else if (which == 2) ok = chol2<true>(H, N, Nrows, stage, lds, &fail, dbg);
   else if (which == 3) ok = chol3(H, N, Nrows, stage, lds, &fail, dbg);
-  if (threadIdx.x == 0) for (int q = 0; q < 5; ++q) out[8 + q] = dbgl[q];
+  if (threadIdx.x == 0 && blockIdx.x == 0) for (int q = 0; q < 5; ++q) out[8 + q] = dbgl[q];
   __syncthreads();
   long long t1 = clock64();
   backsolve_inv(H, N, xs);
   __syncthreads();
   long long t2 = clock64();
-  if (threadIdx.x == 0) { out[0] = t1 - t0; out[1] = ok ? 1 : 0; out[2] = t2 - t1; }
-  for (int e = threadIdx.x; e < P; e += 512) Hout[e] = H[e];
+  if (threadIdx.x == 0 && blockIdx.x == 0) { out[0] = t1 - t0; out[1] = ok ? 1 : 0; out[2] = t2 - t1; }
+  if (blockIdx.x == 0) for (int e = threadIdx.x; e < P; e += 512) Hout[e] = H[e];
   // syrk timings (old vs new), full rank-16 update
   for (int e = threadIdx.x; e < 17 * lds; e += 512) stage[e] = 1e-3 * (e % 13);
   __syncthreads();
@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(512, 1) bench(int N, const double *H0, double 
   syrk_rt(H, 0, N, stage, lds, 16, 1.0, threadIdx.x >> 5, IPM_NW);
   __syncthreads();
   t2 = clock64();
-  if (threadIdx.x == 0) { out[3] = t1 - t0; out[4] = t2 - t1; }
+  if (threadIdx.x == 0 && blockIdx.x == 0) { out[3] = t1 - t0; out[4] = t2 - t1; }
   // small-phase probes
   for (int e = threadIdx.x; e < P; e += 512) H[e] = H0[e];
   __syncthreads();
@@ -58,11 +58,12 @@ __global__ void __launch_bounds__(512, 1) bench(int N, const double *H0, double 
   long long q6 = clock64(); __syncthreads(); long long q7 = clock64();
   trsm_rows8(H, 8, 8, 16, Nrows, stage + 8 * lds, lds);
   long long q8 = clock64(); __syncthreads(); long long q9 = clock64();
-  if (threadIdx.x == 0) { out[5] = q1 - q0; out[6] = q2 - q1; out[7] = q3 - q2; out[13] = q4 - q3; out[14] = q5 - q4; out[15] = q6 - q5; out[16] = q7 - q6; out[17] = q8 - q7; out[18] = q9 - q8; }
+  if (threadIdx.x == 0 && blockIdx.x == 0) { out[5] = q1 - q0; out[6] = q2 - q1; out[7] = q3 - q2; out[13] = q4 - q3; out[14] = q5 - q4; out[15] = q6 - q5; out[16] = q7 - q6; out[17] = q8 - q7; out[18] = q9 - q8; }
 }
 
 int main(int argc, char **argv) {
   const int N = argc > 1 ? atoi(argv[1]) : 201;
+  const int NB = argc > 2 ? atoi(argv[2]) : 1;
   const int Nrows = N + 2, P = Nrows * (Nrows + 1) / 2;
   std::vector<double> G((size_t)N * N), A((size_t)Nrows * Nrows, 0.0), Hp(P);
   unsigned s = 12345;
@@ -108,7 +109,7 @@ int main(int argc, char **argv) {
   for (int usedbg = 0; usedbg < 2; ++usedbg)
   for (int which = 0; which < 4; ++which) {
     long long h[32];
-    for (int rep = 0; rep < 3; ++rep) { bench<<<1, 512, smem>>>(N, dH0, dHo, dout, which, usedbg); cudaDeviceSynchronize(); }
+    for (int rep = 0; rep < 3; ++rep) { bench<<<NB, 512, smem>>>(N, dH0, dHo, dout, which, usedbg); cudaDeviceSynchronize(); }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(e)); return 1; }
     cudaMemcpy(h, dout, 256, cudaMemcpyDeviceToHost);
