@@ -199,7 +199,7 @@ __device__ inline int jac_pos(const EvalModelDev &M, int fn, int col, int dense)
 // per-point version re-read all blocks for every point: 200 MB per point at C4).  Every global request is a whole
 // 128-byte line: lane (lr, lc) loads sector lc of {row r0+lr, columns 16g .. 16g+15}; k-step s contracts over the
 // columns {16g + 4lc + s}, a permutation of the summation index that the B fragments follow.
-constexpr int QB_NT = 256;
+constexpr int QB_NT = 512;
 __device__ __forceinline__ void dmma_ev(double &c0, double &c1, double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
