@@ -197,3 +197,74 @@ def dive_callback(model, solve_batch, grad_f, column_length, node, cutoff=1e100,
     d = {k: getattr(res, k) for k, _ in res._fields_}
     d["x"] = x
     return d
+
+
+class RetryResult(ctypes.Structure):
+    _fields_ = [("used", c_int), ("num_failed", c_int), ("num_infeasible", c_int), ("nlp_solves", c_int), ("mean", c_dbl),
+                ("std_dev", c_dbl)]
+
+
+RETRY_MODES = {"robustness": 0, "cost": 1}
+
+
+def _retry_out(n, m):
+    return dict(obj=c_dbl(), status=c_int(), x=np.zeros(n), g=np.zeros(max(m, 1)), duals=np.zeros(2 * n + m))
+
+
+def resolve_engine(eng: "_e.Engine", mode, x_init, numsolve, xl=None, xu=None, cur_obj=1e100, cur_status=0,
+                   max_random_point_radius=0.0, seed=1):
+    """resolveForRobustness / resolveForCost on the engine: the restarts are ONE batch with per-child start points."""
+    info = eng.problem.info()
+    n, m = eng.n, eng.m
+    xl = np.ascontiguousarray(info["xl"] if xl is None else xl, float)
+    xu = np.ascontiguousarray(info["xu"] if xu is None else xu, float)
+    xi = np.ascontiguousarray(x_init, float)
+    res, o = RetryResult(), _retry_out(n, m)
+    L = _e.lib()
+    L.bnlp_resolve_engine.argtypes = [c_void, c_int, c_void, c_void, c_void, c_dbl, c_int, c_int, c_dbl, ctypes.c_uint,
+                                      ctypes.POINTER(RetryResult), P_dbl, P_int, c_void, c_void, c_void]
+    p = lambda a: a.ctypes.data_as(c_void)
+    rc = L.bnlp_resolve_engine(eng.h, RETRY_MODES[mode], p(xl), p(xu), p(xi), float(cur_obj), int(cur_status), int(numsolve),
+                               float(max_random_point_radius), seed, ctypes.byref(res), ctypes.byref(o["obj"]),
+                               ctypes.byref(o["status"]), p(o["x"]), p(o["g"]), p(o["duals"]))
+    if rc:
+        raise _e.BnlpError("bnlp_resolve_engine failed")
+    d = {k: getattr(res, k) for k, _ in res._fields_}
+    d.update(obj=o["obj"].value, status=o["status"].value, x=o["x"], g=o["g"][:m], duals=o["duals"])
+    return d
+
+
+def resolve_callback(model, solve_starts, mode, x_init, numsolve, cur_obj=1e100, cur_status=0, max_random_point_radius=0.0,
+                     seed=1):
+    """Same with a Python provider: solve_starts(XL, XU, X0[B x n]) -> dict like Engine.solve_batch."""
+    n, m = model.n, model.m
+
+    def cb(ctx, B, XL, XU, X0, OBJ, ST, IT, X, G, D):
+        r = solve_starts(np.ctypeslib.as_array(XL, (B, n)).copy(), np.ctypeslib.as_array(XU, (B, n)).copy(),
+                         np.ctypeslib.as_array(X0, (B, n)).copy())
+        np.ctypeslib.as_array(OBJ, (B,))[:] = r["obj"]
+        np.ctypeslib.as_array(ST, (B,))[:] = r["status"]
+        np.ctypeslib.as_array(IT, (B,))[:] = r["iters"]
+        np.ctypeslib.as_array(X, (B, n))[:] = r["x"]
+        if m:
+            np.ctypeslib.as_array(G, (B, m))[:] = r["g"]
+        np.ctypeslib.as_array(D, (B, 2 * n + m))[:] = r["duals"]
+        return 0
+
+    xl = np.ascontiguousarray(model.xl, float)
+    xu = np.ascontiguousarray(model.xu, float)
+    xi = np.ascontiguousarray(x_init, float)
+    res, o = RetryResult(), _retry_out(n, m)
+    L = host_lib()
+    L.bnlp_resolve_cb.argtypes = [c_int, c_int, c_int, c_void, c_void, c_void, c_dbl, c_int, c_int, c_dbl, ctypes.c_uint, CB,
+                                  c_void, ctypes.POINTER(RetryResult), P_dbl, P_int, c_void, c_void, c_void]
+    keep = CB(cb)
+    p = lambda a: a.ctypes.data_as(c_void)
+    rc = L.bnlp_resolve_cb(RETRY_MODES[mode], n, m, p(xl), p(xu), p(xi), float(cur_obj), int(cur_status), int(numsolve),
+                           float(max_random_point_radius), seed, keep, None, ctypes.byref(res), ctypes.byref(o["obj"]),
+                           ctypes.byref(o["status"]), p(o["x"]), p(o["g"]), p(o["duals"]))
+    if rc:
+        raise RuntimeError("bnlp_resolve_cb failed")
+    d = {k: getattr(res, k) for k, _ in res._fields_}
+    d.update(obj=o["obj"].value, status=o["status"].value, x=o["x"], g=o["g"][:m], duals=o["duals"])
+    return d

@@ -473,6 +473,12 @@ extern "C" int bnlp_engine_stats(const bnlp_engine *E, long long *iterations, lo
   return 0;
 }
 extern "C" long long bnlp_engine_launches(const bnlp_engine *E) { return E ? E->launches : 0; }
+extern "C" int bnlp_engine_sizes(const bnlp_engine *E, int *n, int *m) {
+  if (!E) return -1;
+  if (n) *n = E->M.n;
+  if (m) *m = E->M.m;
+  return 0;
+}
 
 // ------------------------------------------------------------------------------------------------ FP64 peak probe
 __global__ void fp64_peak_kernel(double *out, int iters) {

@@ -47,7 +47,8 @@ EXPORTS = ["bnlp_last_error", "bnlp_problem_from_nl", "bnlp_problem_from_tape", 
            "bnlp_solve_batch", "bnlp_solve_batch_device", "bnlp_oa_capacity", "bnlp_oa_batch", "bnlp_engine_stats",
            "bnlp_engine_launches", "bnlp_measure_fp64_peak", "bnlp_bb_run_cb", "bnlp_bb_run_cb2", "bnlp_bb_run_engine", "bnlp_dive_run_cb", "bnlp_dive_run_engine", "bnlp_violation_batch",
            "bnlp_benders_batch", "bnlp_branching_tqp", "bnlp_tqp_solve_batch",
-           "bnlp_extract_linear_relaxation"]
+           "bnlp_extract_linear_relaxation", "bnlp_constraint_oa_batch", "bnlp_engine_sizes",
+           "bnlp_resolve_cb", "bnlp_resolve_engine"]
 
 
 def lib():
@@ -81,6 +82,8 @@ def lib():
         L.bnlp_tqp_solve_batch.argtypes = [c_void, c_void, c_void, c_int] + [c_void] * 6
         L.bnlp_extract_linear_relaxation.argtypes = [c_void, c_void, c_void, c_void, c_void, c_int, ctypes.POINTER(OaTols),
                                                      ctypes.POINTER(LpDims)] + [c_void] * 10
+        L.bnlp_constraint_oa_batch.argtypes = [c_void, c_int, c_int, c_void, c_void, c_void, c_void, ctypes.POINTER(OaTols)] + \
+            [c_void] * 5
         L.bnlp_engine_stats.argtypes = [c_void, ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_longlong),
                                         P_dbl]
         L.bnlp_engine_launches.restype = ctypes.c_longlong
@@ -360,6 +363,21 @@ class Engine:
                     col_idx=ci[:Z].copy(), val=cv[:Z].copy(), row_lb=rl[:R].copy(), row_ub=ru[:R].copy(),
                     src_row=sr[:R].copy(), col_lb=cl[:C].copy(), col_ub=cu[:C].copy(), obj=ob[:C].copy(),
                     is_integer=ii[:C].copy())
+
+    def constraint_oa_batch(self, row, X, DUALS=None, XL=None, XU=None, tols=None):
+        """B x getConstraintOuterApproximation of row `row`: list of (cols, vals, lb, ub)."""
+        n = self.n
+        X = _d(np.atleast_2d(X))
+        B = X.shape[0]
+        Du = None if DUALS is None else _d(np.atleast_2d(DUALS))
+        xl = None if XL is None else _d(XL)
+        xu = None if XU is None else _d(XU)
+        rl, ci, cv = np.zeros(B, np.int32), np.zeros((B, n), np.int32), np.zeros((B, n))
+        lb, ub = np.zeros(B), np.zeros(B)
+        t = tols or OaTols(1e-8, 1e-17, 1e-8, 1e19, 0)
+        self._ck(lib().bnlp_constraint_oa_batch(self.h, B, int(row), _vp(X), _vp(Du), _vp(xl), _vp(xu), ctypes.byref(t),
+                                                _vp(rl), _vp(ci), _vp(cv), _vp(lb), _vp(ub)))
+        return [(ci[b, :rl[b]].tolist(), cv[b, :rl[b]].copy(), lb[b], ub[b]) for b in range(B)]
 
     def stats(self):
         it, fa, ms = ctypes.c_longlong(), ctypes.c_longlong(), c_dbl()

@@ -456,6 +456,102 @@ BbResult bb_run(TMINLP2TNLP &root, BatchSolveFn solve, const BbOptions &opt, Tqp
   return R;
 }
 
+// ------------------------------------------------------------------------------------------------ retry policies
+static bool is_abandoned(int st) {   // OsiTMINLPInterface::isAbandoned (:2907-2920)
+  return st == TNLPSolver::iterationLimit || st == TNLPSolver::computationError || st == TNLPSolver::illDefinedProblem ||
+         st == TNLPSolver::illegalOption || st == TNLPSolver::externalException || st == TNLPSolver::exception;
+}
+static bool is_optimal(int st) { return st == TNLPSolver::solvedOptimal || st == TNLPSolver::solvedOptimalTol; }
+
+void random_starting_point(const TMINLP2TNLP &t, double R, unsigned long long &rng, double *sol) {
+  for (int i = 0; i < t.n; ++i) {   // uniform mode (:1768-1777)
+    double lower = std::min(-R, t.x_u[i] - R);
+    lower = std::max(t.x_l[i], lower);
+    double upper = std::max(R, t.x_l[i] + R);
+    upper = std::min(t.x_u[i], upper);
+    lower = std::min(upper, lower);
+    upper = std::max(upper, lower);
+    rng = (rng * 0x5DEECE66DULL + 0xB) & ((1ULL << 48) - 1);
+    sol[i] = (double)rng / (double)(1ULL << 48) * (upper - lower) + lower;
+  }
+}
+
+namespace {
+struct StartsBatch {
+  int B, n, m;
+  std::vector<double> OBJ, X, G, D;
+  std::vector<int> ST, IT;
+  int run(const TMINLP2TNLP &t, BatchSolveStartsFn &solve, const std::vector<double> &X0) {
+    n = t.n; m = t.m; B = (int)(X0.size() / n);
+    std::vector<double> XL((size_t)B * n), XU((size_t)B * n);
+    for (int b = 0; b < B; ++b) {
+      std::copy(t.x_l.begin(), t.x_l.end(), &XL[(size_t)b * n]);
+      std::copy(t.x_u.begin(), t.x_u.end(), &XU[(size_t)b * n]);
+    }
+    OBJ.assign(B, 0.0); ST.assign(B, 0); IT.assign(B, 0);
+    X.assign((size_t)B * n, 0.0); G.assign((size_t)B * std::max(m, 1), 0.0); D.assign((size_t)B * (2 * n + m), 0.0);
+    const int rc = solve(B, XL.data(), XU.data(), X0.data(), OBJ.data(), ST.data(), IT.data(), X.data(), G.data(), D.data());
+    if (rc) ST.assign(B, (int)TNLPSolver::exception);
+    return rc;
+  }
+  void install(TMINLP2TNLP &t, int b) const {
+    t.x_sol.assign(X.begin() + (size_t)b * n, X.begin() + (size_t)(b + 1) * n);
+    t.g_sol.assign(G.begin() + (size_t)b * m, G.begin() + (size_t)(b + 1) * m);
+    t.duals_sol.assign(D.begin() + (size_t)b * (2 * n + m), D.begin() + (size_t)(b + 1) * (2 * n + m));
+    t.obj_value = OBJ[b];
+    t.return_status = (TNLPSolver::ReturnStatus)ST[b];
+  }
+};
+}  // namespace
+
+TNLPSolver::ReturnStatus resolve_for_robustness(TMINLP2TNLP &t, BatchSolveStartsFn solve, int numsolve, const RetryOptions &o,
+                                                RetryResult &r) {
+  const int n = t.n, B = 1 + std::max(0, numsolve);
+  std::vector<double> X0((size_t)B * n);
+  std::copy(t.x_init.begin(), t.x_init.begin() + n, X0.begin());          // resetStartingPoint (:1007)
+  unsigned long long rng = 0x5DEECE66DULL ^ o.seed;
+  for (int f = 1; f < B; ++f) random_starting_point(t, o.max_random_point_radius, rng, &X0[(size_t)f * n]);
+  StartsBatch S;
+  S.run(t, solve, X0);
+  r = RetryResult();
+  r.nlp_solves = B;
+  for (int f = 0; f < B; ++f) {                                             // first attempt that is not abandoned (:1024, :1057)
+    if (!is_abandoned(S.ST[f])) { r.used = f; S.install(t, f); return t.return_status; }
+    r.num_failed++;
+  }
+  S.install(t, B - 1);     // all abandoned: the caller throws newUnsolvedError or pretends infeasible (:1076-1091)
+  return t.return_status;
+}
+
+TNLPSolver::ReturnStatus resolve_for_cost(TMINLP2TNLP &t, BatchSolveStartsFn solve, int numsolve, const RetryOptions &o,
+                                          RetryResult &r) {
+  const int n = t.n, B = std::max(0, numsolve);
+  r = RetryResult();
+  if (B == 0) return t.return_status;
+  std::vector<double> X0((size_t)B * n);
+  unsigned long long rng = 0x5DEECE66DULL ^ o.seed;
+  for (int f = 0; f < B; ++f) random_starting_point(t, o.max_random_point_radius, rng, &X0[(size_t)f * n]);
+  StartsBatch S;
+  S.run(t, solve, X0);
+  r.nlp_solves = B;
+  double bestBound = is_optimal(t.return_status) ? t.obj_value : 1.7976931348623157e308;   // :858
+  double sum = 0;
+  int nopt = 0;
+  for (int f = 0; f < B; ++f) {
+    if (is_optimal(S.ST[f]) && S.OBJ[f] < bestBound) { bestBound = S.OBJ[f]; r.used = f + 1; S.install(t, f); }   // :890-901
+    if (is_abandoned(S.ST[f])) r.num_failed++;
+    else if (S.ST[f] == TNLPSolver::provenInfeasible) r.num_infeasible++;
+    if (is_optimal(S.ST[f])) { sum += S.OBJ[f]; nopt++; }
+  }
+  if (nopt) {
+    r.mean = sum / nopt;
+    double v = 0;
+    for (int f = 0; f < B; ++f) if (is_optimal(S.ST[f])) v += (S.OBJ[f] - r.mean) * (S.OBJ[f] - r.mean);
+    r.std_dev = std::sqrt(v / nopt);
+  }
+  return t.return_status;
+}
+
 // ------------------------------------------------------------------------------------------------ NLP diving
 DiveResult dive_run(TMINLP2TNLP &minlp, BatchSolveFn solve, GradFFn grad_f, const std::vector<int> &column_length,
                     double solutionValue, const DiveOptions &opt) {

@@ -132,6 +132,31 @@ struct BbResult {
   long ipm_iterations = 0;
   double seconds = 0;
 };
+// ---- retry policies of OsiTMINLPInterface around one NLP (BonOsiTMINLPInterface.cpp:836-1093).  The reference solves
+// the restarts one after the other; they differ only in their start point, so here they are ONE batch (per-child X0)
+// and the reference's sequential rule is replayed over the results in order.
+using BatchSolveStartsFn = std::function<int(int B, const double *XL, const double *XU, const double *X0 /* B x n */,
+                                             double *OBJ, int *STATUS, int *ITERS, double *X, double *G, double *DUALS)>;
+struct RetryOptions {
+  double max_random_point_radius = 1e5;   // BonOsiTMINLPInterface.cpp:128-134
+  unsigned seed = 1;                      // CoinDrand48 in the reference
+};
+struct RetryResult {
+  int used = -1;               // index of the start whose result was kept (0 = the user's start point), -1 = none
+  int num_failed = 0, num_infeasible = 0, nlp_solves = 0;
+  double mean = 0, std_dev = 0;   // of the optimal objectives (resolveForCost's statistics, :942-961)
+};
+// randomStartingPoint, uniform mode (:1749-1795)
+void random_starting_point(const TMINLP2TNLP &t, double radius, unsigned long long &rng, double *sol);
+// resolveForRobustness(numsolve) (:989-1093): the user's start point again, then numsolve random ones; the first that is
+// not abandoned wins.  Fills t's solution fields; returns the status (of the last attempt if all were abandoned).
+TNLPSolver::ReturnStatus resolve_for_robustness(TMINLP2TNLP &t, BatchSolveStartsFn solve, int numsolve, const RetryOptions &o,
+                                                RetryResult &r);
+// resolveForCost(numsolve) (:836-986): numsolve random starts; the best proven-optimal objective replaces the current
+// solution if it improves on it.
+TNLPSolver::ReturnStatus resolve_for_cost(TMINLP2TNLP &t, BatchSolveStartsFn solve, int numsolve, const RetryOptions &o,
+                                          RetryResult &r);
+
 // ---- NLP diving heuristics (src/CbcBonmin/Heuristics/BonHeuristicDive.cpp:67-302): a chain of NLPs with progressive
 // rounding.  Each step's retry ladder (with at-bound fixings -> without them -> other rounding direction, :171-207) is up
 // to three NLPs that differ only in bounds: with speculate = true they are ONE batch and the ladder is replayed against it.

@@ -50,6 +50,35 @@ int bnlp_bb_run_cb2(int n, int m, const int *var_type, const double *xl, const d
   return 0;
 }
 
+int bnlp_resolve_cb(int mode, int n, int m, const double *xl, const double *xu, const double *x_init, double cur_obj,
+                    int cur_status, int numsolve, double max_random_point_radius, unsigned seed,
+                    bnlp_batch_solve_cb cb, void *ctx, bnlp_retry_result *res, double *obj, int *status, double *x,
+                    double *g, double *duals) {
+  using namespace Bonmin;
+  TMINLP2TNLP t;
+  t.n = n; t.m = m;
+  t.x_l.assign(xl, xl + n); t.x_u.assign(xu, xu + n);
+  t.x_init.assign(x_init, x_init + n);
+  t.x_sol.assign(n, 0.0); t.g_sol.assign(m, 0.0); t.duals_sol.assign(2 * n + m, 0.0);
+  t.obj_value = cur_obj;
+  t.return_status = (TNLPSolver::ReturnStatus)cur_status;
+  RetryOptions o;
+  if (max_random_point_radius > 0) o.max_random_point_radius = max_random_point_radius;
+  o.seed = seed;
+  BatchSolveStartsFn fn = [cb, ctx](int B, const double *XL, const double *XU, const double *X0, double *OBJ, int *ST, int *IT,
+                                    double *X, double *G, double *D) { return cb(ctx, B, XL, XU, X0, OBJ, ST, IT, X, G, D); };
+  RetryResult r;
+  const TNLPSolver::ReturnStatus st = mode == 0 ? resolve_for_robustness(t, fn, numsolve, o, r) : resolve_for_cost(t, fn, numsolve, o, r);
+  if (res) { res->used = r.used; res->num_failed = r.num_failed; res->num_infeasible = r.num_infeasible;
+             res->nlp_solves = r.nlp_solves; res->mean = r.mean; res->std_dev = r.std_dev; }
+  if (obj) *obj = t.obj_value;
+  if (status) *status = (int)st;
+  if (x) memcpy(x, t.x_sol.data(), sizeof(double) * n);
+  if (g && m) memcpy(g, t.g_sol.data(), sizeof(double) * m);
+  if (duals) memcpy(duals, t.duals_sol.data(), sizeof(double) * (2 * n + m));
+  return 0;
+}
+
 int bnlp_dive_run_cb(int n, int m, const int *var_type, const double *xl, const double *xu, const double *gl,
                      const double *gu, const double *x_sol, const double *g_sol, double obj_sol, const int *column_length,
                      double cutoff, bnlp_batch_solve_cb cb, bnlp_grad_f_cb grad_cb, void *ctx, const bnlp_dive_options *o,
@@ -84,6 +113,22 @@ int bnlp_dive_run_cb(int n, int m, const int *var_type, const double *xl, const 
 }
 
 #ifdef BNLP_WITH_ENGINE
+int bnlp_resolve_engine(bnlp_engine *E, int mode, const double *xl, const double *xu, const double *x_init, double cur_obj,
+                        int cur_status, int numsolve, double max_random_point_radius, unsigned seed, bnlp_retry_result *res,
+                        double *obj, int *status, double *x, double *g, double *duals) {
+  if (!E) return -1;
+  // n, m from the engine's own evaluation entry point would need the problem; the starts callback gets them through ctx
+  struct Ctx { bnlp_engine *E; } ctx{E};
+  auto cb = [](void *c, int B, const double *XL, const double *XU, const double *X0, double *OBJ, int *ST, int *IT, double *X,
+               double *G, double *D) {
+    return bnlp_solve_batch(((Ctx *)c)->E, B, XL, XU, X0, 1 /* per-child start points */, OBJ, ST, IT, X, G, D);
+  };
+  int n = 0, m = 0;
+  if (bnlp_engine_sizes(E, &n, &m)) return -1;
+  return bnlp_resolve_cb(mode, n, m, xl, xu, x_init, cur_obj, cur_status, numsolve, max_random_point_radius, seed, cb, &ctx, res,
+                         obj, status, x, g, duals);
+}
+
 int bnlp_dive_run_engine(bnlp_engine *E, const bnlp_problem *P, const double *xl, const double *xu, const double *x_sol,
                          const double *g_sol, double obj_sol, double cutoff, const bnlp_dive_options *o,
                          bnlp_dive_result *res, double *better_x) {

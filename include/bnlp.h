@@ -184,9 +184,18 @@ int bnlp_extract_linear_relaxation(bnlp_engine *, const double *x, const double 
                                    double *val, double *row_lb, double *row_ub, int *src_row, double *col_lb,
                                    double *col_ub, double *obj, int *is_integer);
 
+/* B x OsiTMINLPInterface::getConstraintOuterApproximation (src/Interfaces/BonOsiTMINLPInterface.cpp:2207-2275): the
+ * linearisation of ONE row rowIdx (linear or nonlinear) at B points, side chosen by the multiplier, coefficients cleaned
+ * by cleanNnz, no rhs relaxation.  Output rows have fixed capacity n: col_idx/val B x n, row_len/LB/UB B. */
+int bnlp_constraint_oa_batch(bnlp_engine *, int B, int rowIdx, const double *X, const double *DUALS, const double *XL,
+                             const double *XU, const bnlp_oa_tols *tols, int *row_len, int *col_idx, double *val,
+                             double *LB, double *UB);
+
 /* statistics of the last solve call: total IPM iterations, factorisations, device milliseconds
  * (counterparts of totalIterations_/totalNlpSolveTime_, src/Interfaces/BonOsiTMINLPInterface.hpp:482-495) */
 int bnlp_engine_stats(const bnlp_engine *, long long *iterations, long long *factorisations, double *device_ms);
+/* sizes of the engine's problem (get_nlp_info, BonTMINLP.hpp:226-229) */
+int bnlp_engine_sizes(const bnlp_engine *, int *n, int *m);
 /* number of kernel launches issued by the engine since creation (bench.py's gpu_launches) */
 long long bnlp_engine_launches(const bnlp_engine *);
 /* measured FP64 FMA peak of device dev_index in TFLOP/s (micro-kernel; roofline denominator) */
@@ -254,6 +263,23 @@ int bnlp_dive_run_cb(int n, int m, const int *var_type, const double *xl, const 
 int bnlp_dive_run_engine(bnlp_engine *, const bnlp_problem *, const double *xl, const double *xu, const double *x_sol,
                          const double *g_sol, double obj_sol, double cutoff, const bnlp_dive_options *o,
                          bnlp_dive_result *res, double *better_x);
+
+/* --- retry policies around one NLP (host control flow; the restarts are one batch with per-child start points) ------
+ * mode 0 = OsiTMINLPInterface::resolveForRobustness(numsolve) (src/Interfaces/BonOsiTMINLPInterface.cpp:989-1093): the
+ *   user's start point, then numsolve uniform random points (randomStartingPoint, :1749-1795); the first result that is not
+ *   abandoned (isAbandoned, :2907-2920) is kept; *used = its index (0 = user point), -1 if every attempt was abandoned.
+ * mode 1 = resolveForCost(numsolve) (:836-986): numsolve random starts; the best proven-optimal objective replaces the
+ *   current solution (cur_obj / cur_status; pass cur_status = 0 if there is none) when it improves on it; *used = 1 + index
+ *   of the start that won, -1 if the current solution stays.
+ * The start callback has bnlp_batch_solve_cb's signature with X0 holding B x n start points. */
+typedef struct bnlp_retry_result { int used, num_failed, num_infeasible, nlp_solves; double mean, std_dev; } bnlp_retry_result;
+int bnlp_resolve_cb(int mode, int n, int m, const double *xl, const double *xu, const double *x_init, double cur_obj,
+                    int cur_status, int numsolve, double max_random_point_radius, unsigned seed,
+                    bnlp_batch_solve_cb cb_starts, void *ctx, bnlp_retry_result *res, double *obj, int *status, double *x,
+                    double *g, double *duals);
+int bnlp_resolve_engine(bnlp_engine *, int mode, const double *xl, const double *xu, const double *x_init, double cur_obj,
+                        int cur_status, int numsolve, double max_random_point_radius, unsigned seed, bnlp_retry_result *res,
+                        double *obj, int *status, double *x, double *g, double *duals);
 
 #ifdef __cplusplus
 }

@@ -418,3 +418,36 @@ def extract_linear_relaxation(ev: Evaluator, x, duals=None, xl=None, xu=None, ge
             out["has_alpha"] = True
             out["obj"] = np.concatenate([np.zeros(n), [1.0]])
     return out
+
+
+def constraint_outer_approximation(ev: Evaluator, row, x, duals=None, xl=None, xu=None, tiny=1e-8, very_tiny=1e-17,
+                                   infty_=1e19):
+    """CPU restatement of OsiTMINLPInterface::getConstraintOuterApproximation (BonOsiTMINLPInterface.cpp:2207-2275).
+    Returns (cols, vals, lb, ub).  Test infrastructure only."""
+    M = ev.m_
+    n = M.n
+    xl = M.xl if xl is None else xl
+    xu = M.xu if xu is None else xu
+    vals, grads, _ = ev.dense(x)
+    g = vals[1 + row]
+    rl, ru = M.gl[row], M.gu[row]
+    lbub = [rl - g if rl > -infty_ else -DBL_MAX, ru - g if ru < infty_ else DBL_MAX]
+    if rl > -DBL_MAX and ru < DBL_MAX:
+        du = 0.0 if duals is None else duals[2 * n + row]
+        if du >= 0:
+            lbub[0] = -DBL_MAX
+        if du <= 0:
+            lbub[1] = DBL_MAX
+    cols, out = [], []
+    for (i, j) in ev.jac:
+        if i != row:
+            continue
+        v = grads[1 + row, j]
+        if clean_nnz(v, xl[j], xu[j], rl, ru, x[j], lbub, tiny, very_tiny, infty_):
+            cols.append(j)
+            out.append(v)
+            if lbub[0] > -DBL_MAX:
+                lbub[0] += v * x[j]
+            if lbub[1] < DBL_MAX:
+                lbub[1] += v * x[j]
+    return cols, out, lbub[0], lbub[1]

@@ -218,3 +218,23 @@ def test_extract_linear_relaxation_parity(bnlp_lib, mk):
         assert got["obj_offset"] == pytest.approx(ref["obj_offset"], abs=1e-12)
         assert (got["is_integer"][:m.n] == (np.asarray(m.vtype) != 0)).all()
     eng.close()
+
+
+@pytest.mark.gpu
+def test_constraint_oa_batch_parity(bnlp_lib):
+    """getConstraintOuterApproximation for single rows (linear and nonlinear) at a batch of points."""
+    from oracle.struct_eval import constraint_outer_approximation
+    m = I.syn_cvx_minlp(30, 10, 5, 8, 3)
+    eng = _engine(m)
+    ev = Evaluator(m)
+    rng = np.random.default_rng(11)
+    X = np.clip(m.x0 + rng.uniform(-0.2, 0.2, (5, m.n)), m.xl, m.xu)
+    D = np.concatenate([np.zeros((5, 2 * m.n)), rng.uniform(0, 1, (5, m.m))], axis=1)
+    for row in (0, 3, m.m - 1):
+        got = eng.constraint_oa_batch(row, X, D)
+        for b in range(5):
+            cols, vals, lb, ub = constraint_outer_approximation(ev, row, X[b], D[b])
+            assert got[b][0] == cols
+            np.testing.assert_allclose(got[b][1], vals, rtol=1e-12, atol=1e-14)
+            assert got[b][2] == pytest.approx(lb, rel=1e-12, abs=1e-12) and got[b][3] == pytest.approx(ub, rel=1e-12, abs=1e-12)
+    eng.close()
