@@ -263,7 +263,11 @@ struct CoopBufs {
   int nqpad, ldd;
 };
 
-enum { CS_NEED_CHILD = 0, CS_INIT = 1, CS_ITER = 2, CS_IDLE = 3 };
+// CS_SKIP: an iterating child that sits one step out (after a phase switch everything is re-evaluated at the top of the
+// NEXT step instead of a second time in this one); CS_FINISH: converged at the top of this step — results are written
+// and the next child is fetched in phase C, where this CTA has nothing else to do.  Both keep the pre-barrier phase of
+// every CTA the same length (a straggler there makes all 148 CTAs wait).
+enum { CS_NEED_CHILD = 0, CS_INIT = 1, CS_ITER = 2, CS_IDLE = 3, CS_SKIP = 4, CS_FINISH = 5 };
 
 template <bool TIMERS>
 __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs A, CoopBufs CB) {
@@ -715,16 +719,19 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
   };
 
   long long ph[TIMERS ? 10 : 1] = {0};
+  long long bw[TIMERS ? 4 : 1] = {0};   // wait at each of the four grid barriers
+  int nsteps_iter = 0;
+#define PH_MARKB(b) do { if constexpr (TIMERS) { const long long t_ = clock64(); ph[1] += t_ - ph_t0; if (state == CS_ITER) bw[b] += t_ - ph_t0; ph_t0 = t_; } } while (0)
   long long ph_t0 = TIMERS ? clock64() : 0;
   for (int step = 0;; ++step) {
     // =================================================================== A: local pre-phase
-    for (;;) {
-      if (state == CS_NEED_CHILD) state = setup_child() ? CS_INIT : CS_IDLE;
-      if (state != CS_ITER) break;
+    if (state == CS_SKIP) state = CS_ITER;
+    if (state == CS_ITER) {
       const int act = top_of_iteration();
-      if (act == 0) break;
-      if (act == 2) { write_results(); state = CS_NEED_CHILD; }
+      if (act == 1) state = CS_SKIP;
+      else if (act == 2) state = CS_FINISH;
     }
+    if (state == CS_NEED_CHILD) state = setup_child() ? CS_INIT : CS_IDLE;
     // publish the Hessian weights (zero unless iterating) and, when initialising, the point to evaluate
     for (int qi = tid; qi < nqpad; qi += IPM_NT) {
       double w = 0.0;
@@ -742,7 +749,7 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
     if (tid == 0) atomicAdd(&CB.idle_cnt[step & 1], state == CS_IDLE ? 1 : 0);
     PH_MARK(0);
     grid.sync();   // ------------------------------------------------------------------------------ barrier 1
-    PH_MARK(1);
+    PH_MARKB(0);
     if (*((volatile int *)&CB.idle_cnt[step & 1]) == G) break;
     if (cta == 0 && tid == 0) CB.idle_cnt[(step + 1) & 1] = 0;
 
@@ -804,10 +811,14 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
     }
     PH_MARK(2);
     grid.sync();   // ------------------------------------------------------------------------------ barrier 2
-    PH_MARK(1);
+    PH_MARKB(1);
 
     // =================================================================== C: factorisation, direction (per child)
-    if (state == CS_ITER) {
+    if (state == CS_FINISH) {
+      write_results();
+      state = setup_child() ? CS_INIT : CS_IDLE;
+      for (int j = tid; j < ldd; j += IPM_NT) __stcg(CB.xd + (size_t)cta * ldd + j, (state == CS_INIT && j < n) ? x[j] : 0.0);
+    } else if (state == CS_ITER) {
       const double of = it_of;
       // H += W  (rows < n), fixed rows/cols -> identity, diagonal += Sigma_x + delta_w
       const double *Wb = CB.Wbuf + (size_t)cta * M.ldp;
@@ -929,7 +940,7 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
     }
     PH_MARK(4);
     grid.sync();   // ------------------------------------------------------------------------------ barrier 3
-    PH_MARK(1);
+    PH_MARKB(2);
 
     // =================================================================== D: cooperative U pass (DMMA)
     // Whole-line requests again: lane (lr, lc) loads the 32-byte sector lc of the 128-byte line {row r0+lr, columns
@@ -1000,7 +1011,7 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
     }
     PH_MARK(5);
     grid.sync();   // ------------------------------------------------------------------------------ barrier 4
-    PH_MARK(1);
+    PH_MARKB(3);
 
     // =================================================================== E: initialisation tail / line search + update
     if (state == CS_INIT) {
@@ -1139,6 +1150,7 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
     }
   }
   if constexpr (TIMERS) {
+  if (tid == 0 && (cta % 37) == 0) printf("[dbg cta %d] barrier waits while iterating: b1 %lld b2 %lld b3 %lld b4 %lld (cycles, whole launch)\n", cta, bw[0], bw[1], bw[2], bw[3]);
   if (tid == 0 && cta == 0) printf("[dbg all] diag-warp %llu syrkrest-warp1 %llu\n", g_dbg_cycles[0], g_dbg_cycles[1]);
   if (tid == 0 && cta == 0) printf("[dbg cta0] chol: diag0 %lld trsm %lld syrk+diag %lld | top: rows %lld zeroH %lld chunks %lld vars %lld | C: backsolve %lld dots %lld ftb/mu %lld dir %lld | chunk: stage %lld jt %lld syrk %lld\n", chdbg[0], chdbg[1], chdbg[2], dbg2[0], dbg2[1], dbg2[2], dbg2[3], dbg2[4], dbg2[5], dbg2[6], dbg2[7], dbg2[8], dbg2[9], dbg2[10]);
   if (A.phase_cycles && tid == 0)
