@@ -56,16 +56,45 @@ bool poly_mul(const Poly &a, const Poly &b, Poly &out) {
   return true;
 }
 
-// AMPL opcodes (public ASL opcode table); only the subset below is supported
-enum { O_PLUS = 0, O_MINUS = 1, O_MULT = 2, O_DIV = 3, O_POW = 5, O_ABS = 15, O_NEG = 16, O_SQRT = 39, O_SIN = 41,
-       O_LOG = 43, O_EXP = 44, O_COS = 46, O_SUMLIST = 54, O_1POW = 75, O_2POW = 76, O_CPOW = 77 };
+// AMPL opcodes (public ASL opcode table; not part of the reference tree); only the subset below is supported.
+// tanh, tan, sinh, log10, cosh are lowered at parse time to the operations the tape has (exp, sin, cos, log, /).
+enum { O_PLUS = 0, O_MINUS = 1, O_MULT = 2, O_DIV = 3, O_POW = 5, O_ABS = 15, O_NEG = 16, O_TANH = 37, O_TAN = 38,
+       O_SQRT = 39, O_SINH = 40, O_SIN = 41, O_LOG10 = 42, O_LOG = 43, O_EXP = 44, O_COSH = 45, O_COS = 46,
+       O_SUMLIST = 54, O_1POW = 75, O_2POW = 76, O_CPOW = 77 };
 
 int arity(int op) {
   switch (op) {
     case O_PLUS: case O_MINUS: case O_MULT: case O_DIV: case O_POW: case O_1POW: case O_CPOW: return 2;
-    case O_ABS: case O_NEG: case O_SQRT: case O_SIN: case O_LOG: case O_EXP: case O_COS: case O_2POW: return 1;
+    case O_ABS: case O_NEG: case O_SQRT: case O_SIN: case O_LOG: case O_EXP: case O_COS: case O_2POW:
+    case O_TANH: case O_TAN: case O_SINH: case O_LOG10: case O_COSH: return 1;
     case O_SUMLIST: return -1;
     default: return -2;
+  }
+}
+
+NodeP clone(const Node &e) {
+  NodeP c(new Node());
+  c->kind = e.kind; c->num = e.num; c->var = e.var; c->op = e.op;
+  for (auto &k : e.kids) c->kids.push_back(clone(*k));
+  return c;
+}
+NodeP num(double v) { NodeP c(new Node()); c->kind = Node::NUM; c->num = v; return c; }
+NodeP op1(int op, NodeP a) { NodeP c(new Node()); c->kind = Node::OP; c->op = op; c->kids.push_back(std::move(a)); return c; }
+NodeP op2(int op, NodeP a, NodeP b) {
+  NodeP c(new Node()); c->kind = Node::OP; c->op = op; c->kids.push_back(std::move(a)); c->kids.push_back(std::move(b)); return c;
+}
+// functions the tape has no opcode for, in terms of the ones it has
+NodeP lower_unary(int op, NodeP u) {
+  switch (op) {
+    case O_LOG10: return op2(O_MULT, num(0.43429448190325182765), op1(O_LOG, std::move(u)));
+    case O_TAN: { NodeP v = clone(*u); return op2(O_DIV, op1(O_SIN, std::move(u)), op1(O_COS, std::move(v))); }
+    case O_SINH: { NodeP v = clone(*u);
+                   return op2(O_MULT, num(0.5), op2(O_MINUS, op1(O_EXP, std::move(u)), op1(O_EXP, op1(O_NEG, std::move(v))))); }
+    case O_COSH: { NodeP v = clone(*u);
+                   return op2(O_MULT, num(0.5), op2(O_PLUS, op1(O_EXP, std::move(u)), op1(O_EXP, op1(O_NEG, std::move(v))))); }
+    case O_TANH:   // 1 - 2 / (exp(2u) + 1)
+      return op2(O_MINUS, num(1.0), op2(O_DIV, num(2.0), op2(O_PLUS, op1(O_EXP, op2(O_MULT, num(2.0), std::move(u))), num(1.0))));
+    default: return nullptr;
   }
 }
 
@@ -87,14 +116,16 @@ struct Lines {
   }
 };
 
-bool parse_expr(Lines &L, NodeP &out, std::string &err, int nvars) {
+// defs: the defined variables (V segments) read so far; a reference v(nvars + i) is replaced by a copy of definition i
+bool parse_expr(Lines &L, NodeP &out, std::string &err, int nvars, const std::vector<NodeP> *defs = nullptr) {
   std::string s;
   if (!L.next(s)) { err = "unexpected end of file in expression"; return false; }
   out.reset(new Node());
   if (s[0] == 'n') { out->kind = Node::NUM; out->num = strtod(s.c_str() + 1, nullptr); return true; }
   if (s[0] == 'v') {
     out->kind = Node::VAR; out->var = atoi(s.c_str() + 1);
-    if (out->var < 0 || out->var >= nvars) { err = "variable index out of range (defined variables are not supported)"; return false; }
+    if (out->var >= nvars && defs && out->var - nvars < (int)defs->size()) { out = clone(*(*defs)[out->var - nvars]); return true; }
+    if (out->var < 0 || out->var >= nvars) { err = "variable index out of range: " + s; return false; }
     return true;
   }
   if (s[0] == 'o') {
@@ -108,9 +139,10 @@ bool parse_expr(Lines &L, NodeP &out, std::string &err, int nvars) {
     }
     for (int i = 0; i < k; ++i) {
       NodeP kid;
-      if (!parse_expr(L, kid, err, nvars)) return false;
+      if (!parse_expr(L, kid, err, nvars, defs)) return false;
       out->kids.push_back(std::move(kid));
     }
+    if (NodeP low = (k == 1) ? lower_unary(out->op, clone(*out->kids[0])) : nullptr) out = std::move(low);
     return true;
   }
   err = "bad expression line: " + s;
@@ -272,7 +304,7 @@ bool parse_nl(const char *text, size_t len, HostModel &M, std::string &err) {
   if (!ints(h)) { err = "bad header line 8"; return false; }
   if (!ints(h)) { err = "bad header line 9"; return false; }
   if (!ints(h)) { err = "bad header line 10"; return false; }
-  for (long v : h) if (v != 0) { err = "common expressions (defined variables) are not supported"; return false; }
+  // line 10: numbers of common expressions (defined variables); they are substituted into the expressions that use them
 
   M = HostModel();
   M.n = n; M.m = m;
@@ -299,16 +331,39 @@ bool parse_nl(const char *text, size_t len, HostModel &M, std::string &err) {
   std::vector<std::map<int, double>> lin(m + 1);
   double obj_sign = 1.0;
   std::vector<Term> obj_terms;
+  std::vector<NodeP> defs;
   while (L.next(s)) {
     const char k = s[0];
-    if (k == 'C' || k == 'O') {
+    if (k == 'V') {   // defined variable n + i = sum of its linear terms + its expression
+      std::stringstream ss(s.substr(1));
+      int idx = 0, nlin = 0, usage = 0;
+      ss >> idx >> nlin >> usage;
+      if (idx != n + (int)defs.size()) { err = "defined variables must come in order: " + s; return false; }
+      NodeP sum(new Node());
+      sum->kind = Node::OP; sum->op = O_SUMLIST;
+      for (int i = 0; i < nlin; ++i) {
+        if (!L.next(s)) { err = "short V segment"; return false; }
+        std::stringstream s2(s);
+        int v; double a;
+        s2 >> v >> a;
+        NodeP ref(new Node());
+        if (v >= n && v - n < (int)defs.size()) ref = clone(*defs[v - n]);
+        else if (v >= 0 && v < n) { ref->kind = Node::VAR; ref->var = v; }
+        else { err = "V segment variable out of range"; return false; }
+        sum->kids.push_back(op2(O_MULT, num(a), std::move(ref)));
+      }
+      NodeP e;
+      if (!parse_expr(L, e, err, n, &defs)) return false;
+      sum->kids.push_back(std::move(e));
+      defs.push_back(std::move(sum));
+    } else if (k == 'C' || k == 'O') {
       std::stringstream ss(s.substr(1));
       int idx = 0, sense = 0;
       ss >> idx;
       if (k == 'O') ss >> sense;
       if ((k == 'C' && (idx < 0 || idx >= m)) || (k == 'O' && idx != 0)) { err = "segment index out of range: " + s; return false; }
       NodeP e;
-      if (!parse_expr(L, e, err, n)) return false;
+      if (!parse_expr(L, e, err, n, &defs)) return false;
       const int fn = (k == 'C') ? idx + 1 : 0;
       if (k == 'O' && sense == 1) obj_sign = -1.0;   // maximisation is solved as min -f (as Ipopt::AmplTNLP does)
       if (!lower(*e, (k == 'O') ? obj_sign : 1.0, fn, P[fn], M.terms, err)) return false;

@@ -7,8 +7,8 @@ import math
 import numpy as np
 
 INF = 1e19
-_UN = {15: abs, 16: lambda a: -a, 39: math.sqrt, 41: math.sin, 43: math.log, 44: math.exp, 46: math.cos,
-       76: lambda a: a * a}
+_UN = {15: abs, 16: lambda a: -a, 37: math.tanh, 38: math.tan, 39: math.sqrt, 40: math.sinh, 41: math.sin,
+       42: math.log10, 43: math.log, 44: math.exp, 45: math.cosh, 46: math.cos, 76: lambda a: a * a}
 _BIN = {0: lambda a, b: a + b, 1: lambda a, b: a - b, 2: lambda a, b: a * b, 3: lambda a, b: a / b,
         5: lambda a, b: a ** b, 75: lambda a, b: a ** b, 77: lambda a, b: a ** b}
 
@@ -37,10 +37,19 @@ class NlModel:
         self.expr = {k: ("n", 0.0) for k in range(m + 1)}
         self.lin = np.zeros((m + 1, n))
         self.sense = 0
+        self.defs = []      # defined variables (V segments): (linear terms, expression); index n + i
         while self._p < len(self._l):
             s = self._next()
             k = s[0]
-            if k == "C":
+            if k == "V":
+                idx, nlin, _ = [int(t) for t in s[1:].split()]
+                assert idx == n + len(self.defs)
+                lin = []
+                for _ in range(nlin):
+                    v, a = self._next().split()
+                    lin.append((int(v), float(a)))
+                self.defs.append((lin, self._expr()))
+            elif k == "C":
                 self.expr[int(s[1:]) + 1] = self._expr()
             elif k == "O":
                 self.sense = int(s[1:].split()[1])
@@ -104,6 +113,9 @@ class NlModel:
         if t == "n":
             return e[1]
         if t == "v":
+            if e[1] >= self.n:
+                lin, ex = self.defs[e[1] - self.n]
+                return sum(a * self._ev(("v", v), x) for v, a in lin) + self._ev(ex, x)
             return x[e[1]]
         if t == "sum":
             return sum(self._ev(k, x) for k in e[1])

@@ -100,3 +100,42 @@ def test_mytoy_nl_solve_goldens(bnlp_lib, oracle_ipm):
     assert r["obj"][2] == pytest.approx(gold["children"]["x<=0"]["obj"], rel=1e-6)
     o = oracle_ipm.solve_batch(I.mytoy(), XL, XU, info["x0"])
     np.testing.assert_allclose(r["obj"], o["obj"], rtol=1e-6)
+
+
+def _defvar_values(x):
+    v3 = 2 * x[0] + x[1] * x[2]
+    return np.array([np.sinh(x[0]) + v3 * v3, np.tanh(v3) + np.log10(x[2]), np.tan(x[0]) + np.cosh(x[1])])
+
+
+def test_defined_variables_and_lowered_functions(bnlp_lib):
+    """V segments (defined variables) are substituted; tanh/tan/sinh/cosh/log10 are lowered to the tape's own operations.
+    Structure on the CPU; the independent Python reader evaluates the same file against the closed form."""
+    txt = open(os.path.join(G, "nl_samples", "defvar_funcs.nl")).read()
+    p = _problem(txt)
+    assert (p.n, p.m) == (3, 2)
+    info = p.info()
+    assert list(info["con_nonlinear"]) == [1, 1]
+    assert [list(map(int, e)) for e in zip(info["jac_irow"], info["jac_jcol"])] == [[0, 0], [0, 1], [0, 2], [1, 0], [1, 1]]
+    np.testing.assert_allclose(info["xu"], [1.2, 2, 2])
+    nm = NlModel(txt)
+    for x in ([0.3, 0.7, 1.1], [1.0, 0.2, 0.9]):
+        np.testing.assert_allclose(nm.values(np.array(x)), _defvar_values(x), rtol=1e-13)
+
+
+@pytest.mark.gpu
+def test_defined_variables_eval_on_device(bnlp_lib):
+    from bonmin_b200.engine import Engine
+    txt = open(os.path.join(G, "nl_samples", "defvar_funcs.nl")).read()
+    eng = Engine(_problem(txt))
+    X = np.array([[0.3, 0.7, 1.1], [1.0, 0.2, 0.9], [0.5, 1.5, 0.6]])
+    r = eng.eval_batch(X, want=("f", "g", "gradf", "jac"))
+    h = 1e-6
+    for b, x in enumerate(X):
+        v = _defvar_values(x)
+        assert r["f"][b] == pytest.approx(v[0], rel=1e-12)
+        np.testing.assert_allclose(r["g"][b], v[1:], rtol=1e-12)
+        for j in range(3):                     # gradient of the objective by central differences
+            e = np.zeros(3); e[j] = h
+            fd = (_defvar_values(x + e)[0] - _defvar_values(x - e)[0]) / (2 * h)
+            assert r["gradf"][b, j] == pytest.approx(fd, rel=1e-6, abs=1e-7)
+    eng.close()
