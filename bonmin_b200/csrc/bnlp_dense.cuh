@@ -217,7 +217,7 @@ template <bool LOOKAHEAD>
 __device__ __forceinline__ bool chol2(double *H, int N, int Nrows, double *S, int ld, int *fail, long long *dbg = nullptr) {
   const int w = threadIdx.x >> 5;
   long long t0 = dbg ? clock64() : 0;
-#define C2_MARK(i) do { if (dbg) { long long t_ = clock64(); dbg[i] += t_ - t0; t0 = t_; } } while (0)
+#define C2_MARK(i) do { if (dbg && threadIdx.x == 0) { long long t_ = clock64(); dbg[i] += t_ - t0; t0 = t_; } } while (0)
   __syncthreads();
   if (w == 0) chol_diag8(H, 0, min(8, N), fail);
   __syncthreads();

@@ -267,6 +267,11 @@ struct CoopBufs {
 // NEXT step instead of a second time in this one); CS_FINISH: converged at the top of this step — results are written
 // and the next child is fetched in phase C, where this CTA has nothing else to do.  Both keep the pre-barrier phase of
 // every CTA the same length (a straggler there makes all 148 CTAs wait).
+struct CoopScalars {
+  double objv_, sf_, badw_, theta_init_, mu_max_, th_hist_[4];
+  double it_nz_, it_avg_compl_, it_cviol_, it_dual_inf_, it_s_d_, it_viol_max_, it_of_, it_tcur_, it_mu_, it_ap_max_, it_ad_;
+};
+
 enum { CS_NEED_CHILD = 0, CS_INIT = 1, CS_ITER = 2, CS_IDLE = 3, CS_SKIP = 4, CS_FINISH = 5 };
 
 template <bool TIMERS>
@@ -279,45 +284,49 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
   const int G = gridDim.x, cta = blockIdx.x;
   // ---- carve shared memory (same budget as ipm_kernel; the staging rows get a bank-friendly stride)
   const int lds = ((N + 2 + 7) & ~7) + 4;   // >= roundup8(N+2), stride = 4 (mod 8) doubles: conflict-free DMMA fragments
-  double *sp = smem;
+  // Only a few base pointers are kept; the vectors behind them are macros (base + k * stride), so their addresses are
+  // recomputed where used instead of holding ~30 registers for the whole kernel (same register-cap reason as CoopScalars).
   const int Haug = tri(N + 2);
-  double *H = sp; sp += (Haug + 1) & ~1;
-  double *stage = sp; sp += (IPM_NW + 1) * lds;
-  double *x = sp; sp += npad;
-  double *zL = sp; sp += npad;
-  double *zU = sp; sp += npad;
-  double *Lr = sp; sp += npad;
-  double *Ur = sp; sp += npad;
-  double *dx = sp; sp += npad;
-  double *Sx = sp; sp += npad;
+  double *const H = smem;
+  double *const stage = H + ((Haug + 1) & ~1);
+  double *const x = stage + (IPM_NW + 1) * lds;      // 7 vectors of npad: x zL zU Lr Ur dx Sx
   const int Rp = (R + 1) & ~1, Kp = (m + 2) & ~1;
-  double *s = sp; sp += Rp;
-  double *v = sp; sp += Rp;
-  double *rc = sp; sp += Rp;
-  double *ds = sp; sp += Rp;
-  double *dv = sp; sp += Rp;
-  double *Ss = sp; sp += Rp;
-  double *bb = sp; sp += Rp;
-  double *fsc = sp; sp += Rp;
-  double *jd0 = sp; sp += Rp;
-  double *jd1 = sp; sp += Rp;
-  double *val = sp; sp += Kp;
-  double *gd0 = sp; sp += Kp;
-  double *gd1 = sp; sp += Kp;
-  double *du = sp; sp += Kp;
-  double *wq = sp; sp += 2 * Kp;
-  double *red = sp; sp += IPM_NW * 12;
-  int *flg = reinterpret_cast<int *>(sp);
-  int *fixlist = flg + ((N + 1) & ~1);
-  int *qblk = fixlist + ((N + 1) & ~1);
-  int *qfn = qblk + Kp;
+  double *const s = x + 7 * npad;                    // 10 vectors of Rp: s v rc ds dv Ss bb fsc jd0 jd1
+  double *const val = s + 10 * Rp;                   // val gd0 gd1 du (Kp each), wq (2 Kp)
+  double *const red = val + 6 * Kp;
+#define zL (x + npad)
+#define zU (x + 2 * npad)
+#define Lr (x + 3 * npad)
+#define Ur (x + 4 * npad)
+#define dx (x + 5 * npad)
+#define Sx (x + 6 * npad)
+#define v (s + Rp)
+#define rc (s + 2 * Rp)
+#define ds (s + 3 * Rp)
+#define dv (s + 4 * Rp)
+#define Ss (s + 5 * Rp)
+#define bb (s + 6 * Rp)
+#define fsc (s + 7 * Rp)
+#define jd0 (s + 8 * Rp)
+#define jd1 (s + 9 * Rp)
+#define gd0 (val + Kp)
+#define gd1 (val + 2 * Kp)
+#define du (val + 3 * Kp)
+#define wq (val + 4 * Kp)
+  int *const flg = reinterpret_cast<int *>(red + IPM_NW * 12);
+#define fixlist (flg + ((N + 1) & ~1))
+#define qblk (flg + 2 * ((N + 1) & ~1))
+#define qfn (flg + 2 * ((N + 1) & ~1) + Kp)
   __shared__ int s_child, s_nfix, s_fail, s_nqf;
   double *ws = A.ws + (size_t)cta * A.ws_stride;
   double *grad = ws;
   double *uq = grad + (size_t)(m + 1) * n;
-  double *d0 = H + tri(N), *d1 = H + tri(N + 1);
+#define d0 (H + tri(N))
+#define d1 (H + tri(N + 1))
   // the three per-row scalars used by the J' products reuse ds/dv/jd0 (free at that point of the iteration)
-  double *pv = ds, *p0 = dv, *p1 = jd0;
+#define pv ds
+#define p0 dv
+#define p1 jd0
 
   if (tid == 0) {
     int c = 0;
@@ -341,22 +350,48 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
   int child = -1;
   const double *xl = nullptr, *xu = nullptr, *x0 = nullptr;
   int status = 0, iters = 0;
-  double objv = 0.0, sf = 1.0, badw = 0.0;
+  // CTA-uniform doubles that are only ever written with a value every thread has computed identically (after a block
+  // reduction) live in shared memory instead of 40 registers per thread: the kernel runs at the 128-register cap of a
+  // 512-thread CTA and what does not fit is spilled to local memory, which misses the 28 KB L1 left beside 220 KB of
+  // shared memory.  (Counters and anything updated read-modify-write stay in registers: no ordering between threads.)
+  __shared__ CoopScalars cs_;
+#define objv cs_.objv_
+#define sf cs_.sf_
+#define badw cs_.badw_
+#define theta_init cs_.theta_init_
+#define mu_cap cs_.mu_max_
+#define th_hist cs_.th_hist_
+#define it_nz cs_.it_nz_
+#define it_avg_compl cs_.it_avg_compl_
+#define it_cviol cs_.it_cviol_
+#define it_dual_inf cs_.it_dual_inf_
+#define it_s_d cs_.it_s_d_
+#define it_viol_max cs_.it_viol_max_
+#define it_of cs_.it_of_
+#define it_tcur cs_.it_tcur_
+#define it_mu cs_.it_mu_
+#define it_ap_max cs_.it_ap_max_
+#define it_ad cs_.it_ad_
+  objv = 0.0; sf = 1.0; badw = 0.0;
   bool with_duals = false, inconsistent = false, all_fixed = false, phase1 = false, retry = false;
   int phase1_entries = 0, iters_main = 0, acceptable_cnt = 0, fact_attempts = 0;
-  double theta_init = -1.0, mu_max = -1.0, delta_w_last = 0.0, delta_w = 0.0;
-  double th_hist[4] = {0, 0, 0, 0}, a_last0 = 1.0, a_last1 = 1.0;
+  double delta_w_last = 0.0, delta_w = 0.0;
+  double a_last0 = 1.0, a_last1 = 1.0;
+  theta_init = -1.0; mu_cap = -1.0;
+  th_hist[0] = th_hist[1] = th_hist[2] = th_hist[3] = 0.0;
   long long nfact = 0;
-  long long chdbg[TIMERS ? 3 : 1] = {0};
-  long long dbg2[TIMERS ? 12 : 1] = {0};
+  // timer build: counters live in shared memory and only thread 0 touches them, so the instrumented kernel keeps the
+  // register allocation (and spills) of the production one.  [0..9] phases, [10..13] barrier waits, [16..27] sub-phases
+  __shared__ long long s_tm[TIMERS ? 36 : 1];
+  if constexpr (TIMERS) { if (threadIdx.x < 36) s_tm[threadIdx.x] = 0; }
   long long dbg_t0 = 0;
-#define D2_START() do { if constexpr (TIMERS) dbg_t0 = clock64(); } while (0)
-#define D2_MARK(i) do { if constexpr (TIMERS) { __syncthreads(); long long t_ = clock64(); dbg2[i] += t_ - dbg_t0; dbg_t0 = t_; } } while (0)
+#define D2_START() do { if constexpr (TIMERS) { if (tid == 0) dbg_t0 = clock64(); } } while (0)
+#define D2_MARK(i) do { if constexpr (TIMERS) { __syncthreads(); if (tid == 0) { long long t_ = clock64(); s_tm[16 + (i)] += t_ - dbg_t0; dbg_t0 = t_; } } } while (0)
 #undef PH_MARK
-#define PH_MARK(idx) do { if constexpr (TIMERS) { const long long t_ = clock64(); ph[idx] += t_ - ph_t0; ph_t0 = t_; } } while (0)
+#define PH_MARK(idx) do { if constexpr (TIMERS) { if (tid == 0) { const long long t_ = clock64(); s_tm[idx] += t_ - ph_t0; ph_t0 = t_; } } } while (0)
   // values carried from the top of an iteration to its later phases
-  double it_nz = 0, it_avg_compl = 0, it_cviol = 0, it_dual_inf = 0, it_s_d = 1, it_viol_max = 0, it_of = 0, it_tcur = 0;
-  double it_mu = 0, it_ap_max = 0, it_ad = 0;
+  it_nz = 0; it_avg_compl = 0; it_cviol = 0; it_dual_inf = 0; it_s_d = 1; it_viol_max = 0; it_of = 0; it_tcur = 0;
+  it_mu = 0; it_ap_max = 0; it_ad = 0;
 
   auto init_slacks_mults = [&]() {
     for (int r = tid; r < R; r += IPM_NT) {
@@ -378,7 +413,7 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
     if (tid == 0) { flg[n] &= ~F_FIXED; Lr[n] = -T; x[n] = 1.1 * vm + 0.1 * T; }
     __syncthreads();
     init_slacks_mults();
-    theta_init = -1; mu_max = -1; acceptable_cnt = 0;
+    theta_init = -1; mu_cap = -1; acceptable_cnt = 0;
   };
 
   // ---- fetch + set up the next child; returns false when the queue is empty
@@ -392,7 +427,7 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
     x0 = A.X0 + (size_t)child * A.x0_stride;
     status = 0; iters = 0; objv = 0.0; sf = 1.0; with_duals = false; phase1 = false; retry = false;
     phase1_entries = 0; iters_main = 0; acceptable_cnt = 0; fact_attempts = 0;
-    theta_init = -1.0; mu_max = -1.0; delta_w_last = 0.0; delta_w = 0.0;
+    theta_init = -1.0; mu_cap = -1.0; delta_w_last = 0.0; delta_w = 0.0;
     th_hist[0] = th_hist[1] = th_hist[2] = th_hist[3] = 0.0; a_last0 = a_last1 = 1.0; nfact = 0;
     double acc0 = 0.0, acc1 = 0.0, bw = 0.0;
     for (int j = tid; j < N; j += IPM_NT) {
@@ -581,11 +616,11 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
 #pragma unroll
       for (int u = 0; u < 8; ++u) gpre[u] = g[min(lane + 32 * u, n - 1)];
     };
-    if (R > 0) prefetch_row(wid);
     for (int r0 = 0; r0 < R; r0 += IPM_KC) {
       const int kc = min(IPM_KC, R - r0), kc4 = (kc + 3) & ~3;
       {
         const int c = wid, r = r0 + c;   // IPM_KC == IPM_NW: one row per warp
+        if (c < kc) prefetch_row(r);       // eight loads in flight per lane; a prefetch one chunk ahead only spilled
         if (c < kc) {
           const double sq = sqrt(Ss[r]), f = sq * fsc[r];
 #pragma unroll
@@ -601,7 +636,6 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
           for (int j = lane; j < lds; j += 32) stage[c * lds + j] = 0.0;
         }
       }
-      if (r0 + IPM_KC < R) prefetch_row(r0 + IPM_KC + wid);
       __syncthreads();
       D2_MARK(8);
       if (tid < N) {
@@ -656,7 +690,7 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
     const double s_d = fmax(o.s_max, (sum_v + sum_z) / fmax(1.0, (double)R + nz)) / o.s_max;
     const double s_c = fmax(o.s_max, sum_z / fmax(1.0, nz)) / o.s_max;
     const double E0 = fmax(fmax(dual_inf / s_d, cviol), compl_inf / s_c);
-    if (mu_max < 0) mu_max = fmin(o.mu_max, o.mu_max_fact * fmax(avg_compl, 1e-300));
+    if (mu_cap < 0) mu_cap = fmin(o.mu_max, o.mu_max_fact * fmax(avg_compl, 1e-300));
     it_nz = nz; it_avg_compl = avg_compl; it_cviol = cviol; it_dual_inf = dual_inf; it_s_d = s_d; it_viol_max = viol_max;
 
     const double osc = phase1 ? 1.0 : sf;
@@ -699,7 +733,7 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
         s_nfix = f;
       }
       init_slacks_mults();
-      theta_init = -1; mu_max = -1; acceptable_cnt = 0;
+      theta_init = -1; mu_cap = -1; acceptable_cnt = 0;
       ++iters;
       return 1;
     }
@@ -718,10 +752,7 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
     return 0;
   };
 
-  long long ph[TIMERS ? 10 : 1] = {0};
-  long long bw[TIMERS ? 4 : 1] = {0};   // wait at each of the four grid barriers
-  int nsteps_iter = 0;
-#define PH_MARKB(b) do { if constexpr (TIMERS) { const long long t_ = clock64(); ph[1] += t_ - ph_t0; if (state == CS_ITER) bw[b] += t_ - ph_t0; ph_t0 = t_; } } while (0)
+#define PH_MARKB(b) do { if constexpr (TIMERS) { if (tid == 0) { const long long t_ = clock64(); s_tm[1] += t_ - ph_t0; if (state == CS_ITER) s_tm[10 + (b)] += t_ - ph_t0; ph_t0 = t_; } } } while (0)
   long long ph_t0 = TIMERS ? clock64() : 0;
   for (int step = 0;; ++step) {
     // =================================================================== A: local pre-phase
@@ -838,7 +869,7 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
       ++nfact;
       retry = false;
       PH_MARK(8);
-      if (!chol3(H, N, N + 2, stage, lds, &s_fail)) {
+      if (!chol3(H, N, N + 2, stage, lds, &s_fail, TIMERS ? &s_tm[27] : nullptr)) {
         // inertia correction: retry the whole step with a larger delta_w (first 1e-4, x100 then x8, /3 between iterations)
         if (delta_w == 0.0) delta_w = (delta_w_last == 0.0) ? 1e-4 : fmax(1e-20, delta_w_last / 3.0);
         else delta_w *= (delta_w_last == 0.0 ? 100.0 : 8.0);
@@ -918,7 +949,7 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
           const double mu_aff = it_nz > 0 ? t[0] / it_nz : 0.0;
           double sigma = it_avg_compl > 0 ? pow(mu_aff / it_avg_compl, 3.0) : o.sigma_min;
           sigma = fmin(fmax(sigma, o.sigma_min), o.sigma_max);
-          mu = fmin(fmax(sigma * it_avg_compl, o.mu_min), mu_max);
+          mu = fmin(fmax(sigma * it_avg_compl, o.mu_min), mu_cap);
           mu = fmax(mu, fmin(it_avg_compl, o.mu_safeguard * fmax(it_cviol, it_dual_inf / it_s_d)));
         }
         const double tau = fmax(o.tau_min, 1.0 - mu);
@@ -1150,12 +1181,57 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
     }
   }
   if constexpr (TIMERS) {
-  if (tid == 0 && (cta % 37) == 0) printf("[dbg cta %d] barrier waits while iterating: b1 %lld b2 %lld b3 %lld b4 %lld (cycles, whole launch)\n", cta, bw[0], bw[1], bw[2], bw[3]);
-  if (tid == 0 && cta == 0) printf("[dbg all] diag-warp %llu syrkrest-warp1 %llu\n", g_dbg_cycles[0], g_dbg_cycles[1]);
-  if (tid == 0 && cta == 0) printf("[dbg cta0] chol: diag0 %lld trsm %lld syrk+diag %lld | top: rows %lld zeroH %lld chunks %lld vars %lld | C: backsolve %lld dots %lld ftb/mu %lld dir %lld | chunk: stage %lld jt %lld syrk %lld\n", chdbg[0], chdbg[1], chdbg[2], dbg2[0], dbg2[1], dbg2[2], dbg2[3], dbg2[4], dbg2[5], dbg2[6], dbg2[7], dbg2[8], dbg2[9], dbg2[10]);
-  if (A.phase_cycles && tid == 0)
-    for (int q = 0; q < 10; ++q) atomicAdd((unsigned long long *)&A.phase_cycles[q], (unsigned long long)ph[q]);
+    if (tid == 0 && (cta % 37) == 0)
+      printf("[dbg cta %d] barrier waits while iterating: b1 %lld b2 %lld b3 %lld b4 %lld | top: rows %lld zeroH %lld vars %lld, chunk stage %lld J'v %lld syrk %lld | C: backsolve %lld dots %lld ftb/mu %lld dir %lld | chol3: diag0 %lld trsm %lld col8+diag %lld trailing+diag %lld (cycles, whole launch)\n",
+             cta, s_tm[10], s_tm[11], s_tm[12], s_tm[13], s_tm[16], s_tm[17], s_tm[19], s_tm[24], s_tm[25], s_tm[26], s_tm[20], s_tm[21], s_tm[22], s_tm[23], s_tm[27], s_tm[28], s_tm[29], s_tm[30]);
+    if (A.phase_cycles && tid == 0)
+      for (int q = 0; q < 10; ++q) atomicAdd((unsigned long long *)&A.phase_cycles[q], (unsigned long long)s_tm[q]);
   }
 }
+#undef zL
+#undef zU
+#undef Lr
+#undef Ur
+#undef dx
+#undef Sx
+#undef v
+#undef rc
+#undef ds
+#undef dv
+#undef Ss
+#undef bb
+#undef fsc
+#undef jd0
+#undef jd1
+#undef gd0
+#undef gd1
+#undef du
+#undef wq
+#undef fixlist
+#undef qblk
+#undef qfn
+#undef d0
+#undef d1
+#undef pv
+#undef p0
+#undef p1
+#undef objv
+#undef sf
+#undef badw
+#undef theta_init
+#undef mu_cap
+#undef th_hist
+#undef it_nz
+#undef it_avg_compl
+#undef it_cviol
+#undef it_dual_inf
+#undef it_s_d
+#undef it_viol_max
+#undef it_of
+#undef it_tcur
+#undef it_mu
+#undef it_ap_max
+#undef it_ad
+
 
 }  // namespace bnlp
