@@ -318,9 +318,8 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
 #define qblk (flg + 2 * ((N + 1) & ~1))
 #define qfn (flg + 2 * ((N + 1) & ~1) + Kp)
   __shared__ int s_child, s_nfix, s_fail, s_nqf;
-  double *ws = A.ws + (size_t)cta * A.ws_stride;
-  double *grad = ws;
-  double *uq = grad + (size_t)(m + 1) * n;
+#define grad (A.ws + (size_t)cta * A.ws_stride)
+#define uq (A.ws + (size_t)cta * A.ws_stride + (size_t)(m + 1) * n)
 #define d0 (H + tri(N))
 #define d1 (H + tri(N + 1))
   // the three per-row scalars used by the J' products reuse ds/dv/jd0 (free at that point of the iteration)
@@ -348,7 +347,9 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
   // ---- per-child state
   int state = CS_NEED_CHILD;
   int child = -1;
-  const double *xl = nullptr, *xu = nullptr, *x0 = nullptr;
+#define xl (A.XL + (size_t)child * n)
+#define xu (A.XU + (size_t)child * n)
+#define x0 (A.X0 + (size_t)child * A.x0_stride)
   int status = 0, iters = 0;
   // CTA-uniform doubles that are only ever written with a value every thread has computed identically (after a block
   // reduction) live in shared memory instead of 40 registers per thread: the kernel runs at the 128-register cap of a
@@ -423,8 +424,6 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
     __syncthreads();
     child = s_child;
     if (child >= A.B) return false;
-    xl = A.XL + (size_t)child * n; xu = A.XU + (size_t)child * n;
-    x0 = A.X0 + (size_t)child * A.x0_stride;
     status = 0; iters = 0; objv = 0.0; sf = 1.0; with_duals = false; phase1 = false; retry = false;
     phase1_entries = 0; iters_main = 0; acceptable_cnt = 0; fact_attempts = 0;
     theta_init = -1.0; mu_cap = -1.0; delta_w_last = 0.0; delta_w = 0.0;
@@ -1215,6 +1214,11 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
 #undef pv
 #undef p0
 #undef p1
+#undef xl
+#undef xu
+#undef x0
+#undef grad
+#undef uq
 #undef objv
 #undef sf
 #undef badw
