@@ -326,10 +326,10 @@ def main():
             "roofline": {"bound": "fp64", "kernel": "ipm_coop_kernel", "achieved": achieved, "peak": peak,
                          "unit": "TFLOP/s", "frac": achieved / peak if peak > 0 else None,
                          # DRAM bytes per launch: ncu dram__bytes_read + write of this kernel on this workload
-                         # (profiles/r1f_traffic.csv: 20.10 GB per 52 232-iteration launch), scaled by iterations
-                         "traffic": 20.10e9 / 52232 * iters_total,
+                         # (profiles/r1g_traffic.csv: 12.05 GB per 52 232-iteration launch), scaled by iterations
+                         "traffic": 12.05e9 / 52232 * iters_total,
                          "traffic_note": "exchange buffers of the cooperative passes (W, Q.dx) written through to HBM; "
-                                         "2.6 % of HBM bandwidth, the kernel is FP64-pipe / latency bound",
+                                         "2 % of HBM bandwidth, the kernel is FP64-pipe / latency bound",
                          "peak_source": "FP64 FMA micro-kernel measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
                          "flops_per_iteration": f_iter(C3["n"], C3["m_q"], C3["m_l"]),
                          "iterations_per_launch": iters_total, "kernel_ms": kern_ms},
