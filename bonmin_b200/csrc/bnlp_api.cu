@@ -24,6 +24,7 @@ constexpr double kInfD = 1e19;
 
 namespace bnlp {
 bool model_from_desc(const bnlp_tape_desc *d, HostModel &M, std::string &err);
+bool model_fp_variant(const HostModel &B, const bnlp_fp_desc &d, HostModel &M, std::string &err);
 // kernel launchers live in their own translation units (bnlp_launch_ipm.cu, bnlp_launch_coop.cu) so the three big
 // kernels compile in parallel
 cudaError_t ipm_general_set_smem(size_t smem);
@@ -137,6 +138,17 @@ extern "C" bnlp_problem *bnlp_problem_from_nl(const char *nl_text, size_t len, c
     return nullptr;
   }
   return p;
+}
+
+extern "C" bnlp_problem *bnlp_problem_fp(const bnlp_problem *base, const bnlp_fp_desc *desc, char *err, size_t errlen) {
+  std::string e;
+  if (!base || !desc) e = "null argument";
+  auto *p = new bnlp_problem();
+  if (e.empty() && model_fp_variant(base->M, *desc, p->M, e)) return p;
+  if (err && errlen) snprintf(err, errlen, "%s", e.c_str());
+  set_err(e);
+  delete p;
+  return nullptr;
 }
 
 extern "C" void bnlp_problem_free(bnlp_problem *p) { delete p; }
@@ -329,11 +341,12 @@ extern "C" bnlp_engine *bnlp_engine_create(const bnlp_problem *prob, const int *
                    (size_t)COOP_RB * E->ldd <= (size_t)(IPM_NW + 1) * lds + (size_t)(n + 3) * (n + 4) / 2 &&   // U-pass operands live in H + staging
                    !getenv("BNLP_NO_COOP");
     }
-    if (E->coop_ok && ipm_coop_set_smem(E->coop_smem_bytes) != cudaSuccess) {
+    // (the attribute is per kernel, not per engine: several engines with different needs may be alive, so opt in to the maximum)
+    if (E->coop_ok && ipm_coop_set_smem(D.smem_optin - 1024) != cudaSuccess) {
       E->coop_ok = false;
       cudaGetLastError();
     }
-    if (E->ipm_supported && ipm_general_set_smem(E->smem_bytes) != cudaSuccess) {
+    if (E->ipm_supported && ipm_general_set_smem(D.smem_optin - 1024) != cudaSuccess) {
       set_err(std::string("cudaFuncSetAttribute(ipm_kernel): ") + cudaGetErrorString(cudaGetLastError()));
       delete E;
       return nullptr;

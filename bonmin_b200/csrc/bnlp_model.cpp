@@ -4,7 +4,9 @@
 #include "bnlp_internal.h"
 
 #include <algorithm>
+#include <map>
 #include <set>
+#include <tuple>
 
 #include "../../include/bnlp.h"
 
@@ -123,6 +125,110 @@ bool model_from_desc(const bnlp_tape_desc *d, HostModel &M, std::string &err) {
     if (maxd > BNLP_MAX_TERM_STACK) { err = "term stack deeper than BNLP_MAX_TERM_STACK"; return false; }
     M.terms.push_back(std::move(T));
   }
+  M.finalize();
+  return true;
+}
+
+// ---- TNLP2FPNLP (src/Interfaces/BonTNLP2FPNLP.cpp:75-330) as a tape transformation.
+// The rounding target enters as k extra variables p (fixed per child through their bounds), so a whole batch of targets
+// is ONE problem whose children differ only in bounds:
+//   objective (use_fp_objective):  (1 - lambda) sigma f(x) + s lambda dist(x, p)             (:178-190)
+//     norm 2: dist = sum_i (x_i - p_i)^2                                                       (:80-84)
+//     norm 1: dist = sum_i [p_i <= 0.1 ? x_i : 1 - x_i]  ==  x_i (1 - 2 p_i) + p_i for p_i in {0, 1}   (:85-94)
+//   cutoff row (use_cutoff_constraint): the (new) objective <= cutoff                        (:150-155, :204-214)
+//   local-branching row: sum_i x_i (1 - 2 p_i) + p_i <= rhs                                  (:215-223)
+bool model_fp_variant(const HostModel &B, const bnlp_fp_desc &d, HostModel &M, std::string &err) {
+  const int n = B.n, m = B.m, k = d.n_inds;
+  if (k < 0 || (k > 0 && !d.inds)) { err = "bad index set"; return false; }
+  for (int i = 0; i < k; ++i) if (d.inds[i] < 0 || d.inds[i] >= n) { err = "index out of range"; return false; }
+  if (d.norm != 1 && d.norm != 2) { err = "norm must be 1 or 2"; return false; }
+  const int n2 = n + k, madd = (d.use_cutoff_constraint ? 1 : 0) + (d.use_local_branching_constraint ? 1 : 0), m2 = m + madd;
+  M = HostModel();
+  M.n = n2; M.m = m2;
+  M.xl = B.xl; M.xu = B.xu; M.x0 = B.x0; M.vtype = B.vtype;
+  M.xl.resize(n2, -kInf); M.xu.resize(n2, kInf); M.x0.resize(n2, 0.0); M.vtype.resize(n2, 0);
+  M.gl = B.gl; M.gu = B.gu;
+  const double fs = d.use_fp_objective ? (1.0 - d.lambda) * d.sigma : 1.0;      // scale of the original objective
+  const double ds = d.use_fp_objective ? d.objective_scaling_factor * d.lambda : 0.0;   // scale of the distance
+  // per-function pieces, function 0 rebuilt; rows 1..m copied; extra rows appended
+  struct Fn { double c = 0; std::vector<std::pair<int, double>> lin; std::vector<std::tuple<int, int, double>> q; };
+  std::vector<Fn> F(m2 + 1);
+  for (int fn = 0; fn <= m; ++fn) {
+    const double sc = fn == 0 ? fs : 1.0;
+    F[fn].c = sc * B.c[fn];
+    for (int e = B.lin_start[fn]; e < B.lin_start[fn + 1]; ++e) F[fn].lin.push_back({B.lin_col[e], sc * B.lin_val[e]});
+  }
+  for (size_t e = 0; e < B.qs_fn.size(); ++e)
+    F[B.qs_fn[e]].q.push_back({B.qs_i[e], B.qs_j[e], (B.qs_fn[e] == 0 ? fs : 1.0) * B.qs_v[e]});
+  auto add_dist = [&](Fn &f, double w) {       // w * dist(x, p)
+    for (int i = 0; i < k; ++i) {
+      const int xi = d.inds[i], pi = n + i;
+      if (d.norm == 2) {                        // w (x^2 - 2 x p + p^2): 1/2 x'Qx convention -> Q_xx = Q_pp = 2w, Q_px = -2w
+        f.q.push_back({xi, xi, 2.0 * w}); f.q.push_back({pi, pi, 2.0 * w}); f.q.push_back({pi, xi, -2.0 * w});
+      } else {                                  // w (x - 2 x p + p)
+        f.lin.push_back({xi, w}); f.lin.push_back({pi, w}); f.q.push_back({pi, xi, -2.0 * w});
+      }
+    }
+  };
+  if (d.use_fp_objective) add_dist(F[0], ds);
+  int row = m;
+  std::vector<int> copy_obj_rows;              // rows that repeat the objective (dense blocks / terms are duplicated below)
+  if (d.use_cutoff_constraint) {
+    ++row;
+    F[row] = F[0];
+    copy_obj_rows.push_back(row);
+    M.gl.push_back(-kInf); M.gu.push_back(d.cutoff);
+  }
+  if (d.use_local_branching_constraint) {
+    ++row;
+    const int keep = d.norm;
+    bnlp_fp_desc d1 = d; d1.norm = 1;
+    (void)keep;
+    for (int i = 0; i < k; ++i) {
+      const int xi = d.inds[i], pi = n + i;
+      F[row].lin.push_back({xi, 1.0}); F[row].lin.push_back({pi, 1.0}); F[row].q.push_back({pi, xi, -2.0});
+    }
+    M.gl.push_back(-kInf); M.gu.push_back(d.rhs_local_branching);
+  }
+  // dense blocks: re-packed for n2 variables (the packed rows of the first n variables come first, new rows are zero)
+  const size_t P = (size_t)n * (n + 1) / 2, P2 = (size_t)n2 * (n2 + 1) / 2;
+  auto push_block = [&](int fn, const double *src, double sc) {
+    M.qd_fn.push_back(fn);
+    const size_t off = M.qd.size();
+    M.qd.resize(off + P2, 0.0);
+    for (size_t e = 0; e < P; ++e) M.qd[off + e] = sc * src[e];
+  };
+  for (size_t q = 0; q < B.qd_fn.size(); ++q) {
+    const int fn = B.qd_fn[q];
+    push_block(fn, B.qd.data() + q * P, fn == 0 ? fs : 1.0);
+    if (fn == 0) for (int r : copy_obj_rows) push_block(r, B.qd.data() + q * P, fs);
+  }
+  // element terms: objective terms are scaled by appending  CONST fs; MUL  to their programs
+  auto scaled = [&](const Term &t, int fn, double sc) {
+    Term u = t;
+    u.fn = fn;
+    if (sc != 1.0) { u.op.push_back(BNLP_OP_CONST); u.iarg.push_back(0); u.darg.push_back(sc);
+                     u.op.push_back(BNLP_OP_MUL); u.iarg.push_back(0); u.darg.push_back(0.0); }
+    return u;
+  };
+  for (const Term &t : B.terms) {
+    M.terms.push_back(scaled(t, t.fn, t.fn == 0 ? fs : 1.0));
+    if (t.fn == 0) for (int r : copy_obj_rows) M.terms.push_back(scaled(t, r, fs));
+  }
+  // assemble CSR + triplets (duplicates merged)
+  M.c.assign(m2 + 1, 0.0);
+  M.lin_start.assign(m2 + 2, 0);
+  for (int fn = 0; fn <= m2; ++fn) {
+    M.c[fn] = F[fn].c;
+    std::map<int, double> rowm;
+    for (auto &kv : F[fn].lin) rowm[kv.first] += kv.second;
+    M.lin_start[fn] = (int)M.lin_col.size();
+    for (auto &kv : rowm) { M.lin_col.push_back(kv.first); M.lin_val.push_back(kv.second); }
+    std::map<std::pair<int, int>, double> qm;
+    for (auto &t : F[fn].q) { const int i = std::max(std::get<0>(t), std::get<1>(t)), j = std::min(std::get<0>(t), std::get<1>(t)); qm[{i, j}] += std::get<2>(t); }
+    for (auto &kv : qm) { M.qs_fn.push_back(fn); M.qs_i.push_back(kv.first.first); M.qs_j.push_back(kv.first.second); M.qs_v.push_back(kv.second); }
+  }
+  M.lin_start[m2 + 1] = (int)M.lin_col.size();
   M.finalize();
   return true;
 }

@@ -32,6 +32,14 @@ class Options(ctypes.Structure):
     _fields_ = [("tol", c_dbl), ("max_iter", c_int), ("ctas_per_device", c_int)]
 
 
+class FpDesc(ctypes.Structure):
+    _fields_ = [("n_inds", ctypes.c_int), ("inds", ctypes.POINTER(ctypes.c_int)), ("norm", ctypes.c_int),
+                ("lambda_", ctypes.c_double), ("sigma", ctypes.c_double), ("objective_scaling_factor", ctypes.c_double),
+                ("use_fp_objective", ctypes.c_int), ("use_cutoff_constraint", ctypes.c_int),
+                ("use_local_branching_constraint", ctypes.c_int), ("cutoff", ctypes.c_double),
+                ("rhs_local_branching", ctypes.c_double)]
+
+
 class LpDims(ctypes.Structure):
     _fields_ = [("n_cols", ctypes.c_int), ("n_rows", ctypes.c_int), ("nnz", ctypes.c_int), ("has_alpha", ctypes.c_int),
                 ("obj_offset", ctypes.c_double)]
@@ -48,7 +56,7 @@ EXPORTS = ["bnlp_last_error", "bnlp_problem_from_nl", "bnlp_problem_from_tape", 
            "bnlp_engine_launches", "bnlp_measure_fp64_peak", "bnlp_bb_run_cb", "bnlp_bb_run_cb2", "bnlp_bb_run_engine", "bnlp_dive_run_cb", "bnlp_dive_run_engine", "bnlp_violation_batch",
            "bnlp_benders_batch", "bnlp_branching_tqp", "bnlp_tqp_solve_batch",
            "bnlp_extract_linear_relaxation", "bnlp_constraint_oa_batch", "bnlp_engine_sizes",
-           "bnlp_resolve_cb", "bnlp_resolve_engine"]
+           "bnlp_resolve_cb", "bnlp_resolve_engine", "bnlp_problem_fp"]
 
 
 def lib():
@@ -62,6 +70,8 @@ def lib():
         L.bnlp_problem_from_tape.argtypes = [ctypes.POINTER(TapeDesc), ctypes.c_char_p, ctypes.c_size_t]
         L.bnlp_problem_from_nl.restype = c_void
         L.bnlp_problem_from_nl.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t]
+        L.bnlp_problem_fp.restype = c_void
+        L.bnlp_problem_fp.argtypes = [c_void, ctypes.POINTER(FpDesc), ctypes.c_char_p, ctypes.c_size_t]
         L.bnlp_problem_free.argtypes = [c_void]
         L.bnlp_problem_sizes.argtypes = [c_void, P_int, P_int, P_int, P_int]
         L.bnlp_problem_info.argtypes = [c_void] + [c_void] * 11
@@ -179,6 +189,19 @@ class Problem:
         if not h:
             raise BnlpError(err.value.decode())
         return cls(h)
+
+    def fp_variant(self, inds, norm=2, lam=1.0, sigma=1.0, objective_scaling_factor=1.0, use_fp_objective=True,
+                   cutoff=None, rhs_local_branching=None):
+        """TNLP2FPNLP as a new Problem with len(inds) extra target variables (see include/bnlp.h: bnlp_problem_fp)."""
+        ia = _i(inds)
+        d = FpDesc(len(ia), _pi(ia), int(norm), float(lam), float(sigma), float(objective_scaling_factor),
+                   int(use_fp_objective), int(cutoff is not None), int(rhs_local_branching is not None),
+                   float(cutoff or 0.0), float(rhs_local_branching or 0.0))
+        err = ctypes.create_string_buffer(512)
+        h = lib().bnlp_problem_fp(self.h, ctypes.byref(d), err, 512)
+        if not h:
+            raise BnlpError(err.value.decode())
+        return Problem(h)
 
     def info(self):
         n, m = self.n, self.m

@@ -90,6 +90,24 @@ bnlp_problem *bnlp_problem_from_nl(const char *nl_text, size_t len, char *err, s
 bnlp_problem *bnlp_problem_from_tape(const bnlp_tape_desc *desc, char *err, size_t errlen);
 void bnlp_problem_free(bnlp_problem *);
 
+/* Feasibility-pump / local-branching variant of a problem = Bonmin::TNLP2FPNLP (src/Interfaces/BonTNLP2FPNLP.cpp:75-330):
+ *   objective  (1 - lambda) sigma f(x) + objective_scaling_factor lambda dist(x, target)   when use_fp_objective
+ *              (norm 2: sum (x_i - t_i)^2; norm 1, binaries: sum [t_i <= 0.1 ? x_i : 1 - x_i]),
+ *   a cutoff row  (that objective) <= cutoff            when use_cutoff_constraint (pass the value set_cutoff computes, :52-63),
+ *   a local-branching row  sum [t_i <= 0.1 ? x_i : 1 - x_i] <= rhs   when use_local_branching_constraint.
+ * The target enters as n_inds EXTRA variables appended after the n original ones (variable n + i is the target of
+ * variable inds[i]); a child fixes them through its bounds (XL = XU = t_i), so a whole batch of rounding targets is one
+ * bnlp_solve_batch call on the returned problem.  Returns NULL on error. */
+typedef struct bnlp_fp_desc {
+  int n_inds;
+  const int *inds;
+  int norm;                                  /* 1 or 2 (BonTNLP2FPNLP.hpp: norm_) */
+  double lambda, sigma, objective_scaling_factor;
+  int use_fp_objective, use_cutoff_constraint, use_local_branching_constraint;
+  double cutoff, rhs_local_branching;
+} bnlp_fp_desc;
+bnlp_problem *bnlp_problem_fp(const bnlp_problem *base, const bnlp_fp_desc *desc, char *err, size_t errlen);
+
 /* get_nlp_info (BonTMINLP.hpp:226-229) */
 int bnlp_problem_sizes(const bnlp_problem *, int *n, int *m, int *nnz_jac, int *nnz_hess);
 /* structure + bounds + types: get_bounds_info :238, get_variables_types :208, get_constraints_linearity :220,

@@ -451,3 +451,85 @@ def constraint_outer_approximation(ev: Evaluator, row, x, duals=None, xl=None, x
             if lbub[1] < DBL_MAX:
                 lbub[1] += v * x[j]
     return cols, out, lbub[0], lbub[1]
+
+
+def fp_model(model, inds, norm=2, lam=1.0, sigma=1.0, scaling=1.0, use_fp_objective=True, cutoff=None, rhs_local_branching=None):
+    """CPU restatement of Bonmin::TNLP2FPNLP (src/Interfaces/BonTNLP2FPNLP.cpp:75-330) as a StructuredModel with the
+    rounding target as len(inds) extra variables (fixed per child through bounds).  Test infrastructure only."""
+    from bonmin_b200.instances import StructuredModel, pack_lower, unpack_lower, _empty_sparse, OP_CONST, OP_MUL
+    n, m, k = model.n, model.m, len(inds)
+    n2 = n + k
+    madd = (cutoff is not None) + (rhs_local_branching is not None)
+    m2 = m + madd
+    fs = (1.0 - lam) * sigma if use_fp_objective else 1.0
+    ds = scaling * lam if use_fp_objective else 0.0
+    Q = {}
+    for kk, fn in enumerate(model.qd_fn):
+        Q[int(fn)] = unpack_lower(model.qd[kk], n)
+    for fn, i, j, v in zip(model.qs_fn, model.qs_i, model.qs_j, model.qs_v):
+        q = Q.setdefault(int(fn), np.zeros((n, n)))
+        q[i, j] += v
+        if i != j:
+            q[j, i] += v
+    A = np.zeros((m2 + 1, n2))
+    A[:m + 1, :n] = model.A
+    c = np.zeros(m2 + 1)
+    c[:m + 1] = model.c
+    Q2 = {}
+    for fn, q in Q.items():
+        z = np.zeros((n2, n2))
+        z[:n, :n] = q
+        Q2[fn] = z
+    A[0] *= fs
+    c[0] *= fs
+    if 0 in Q2:
+        Q2[0] *= fs
+
+    def add_dist(fn, w, nrm):
+        q = Q2.setdefault(fn, np.zeros((n2, n2)))
+        for i, xi in enumerate(inds):
+            pi = n + i
+            if nrm == 2:
+                q[xi, xi] += 2 * w
+                q[pi, pi] += 2 * w
+                q[xi, pi] -= 2 * w
+                q[pi, xi] -= 2 * w
+            else:
+                A[fn, xi] += w
+                A[fn, pi] += w
+                q[xi, pi] -= 2 * w
+                q[pi, xi] -= 2 * w
+    if use_fp_objective:
+        add_dist(0, ds, norm)
+    terms = []
+    for fn, vars_, prog in model.get("terms", []):
+        sc = fs if fn == 0 else 1.0
+        p2 = list(prog) + ([(OP_CONST, 0, sc), (OP_MUL, 0, 0.0)] if sc != 1.0 else [])
+        terms.append((fn, list(vars_), p2))
+    gl = list(model.gl)
+    gu = list(model.gu)
+    row = m
+    if cutoff is not None:
+        row += 1
+        A[row] = A[0]
+        c[row] = c[0]
+        if 0 in Q2:
+            Q2[row] = Q2[0].copy()
+        for fn, vars_, prog in list(terms):
+            if fn == 0:
+                terms.append((row, list(vars_), list(prog)))
+        gl.append(-1e19)
+        gu.append(cutoff)
+    if rhs_local_branching is not None:
+        row += 1
+        add_dist(row, 1.0, 1)
+        gl.append(-1e19)
+        gu.append(rhs_local_branching)
+    fns = sorted(Q2)
+    qd = np.array([pack_lower(Q2[f]) for f in fns]).reshape(len(fns), n2 * (n2 + 1) // 2)
+    INF = 1e19
+    return _empty_sparse(StructuredModel(
+        n=n2, m=m2, xl=np.concatenate([model.xl, np.full(k, -INF)]), xu=np.concatenate([model.xu, np.full(k, INF)]),
+        gl=np.array(gl, float), gu=np.array(gu, float), vtype=np.concatenate([model.vtype, np.zeros(k, np.int32)]).astype(np.int32),
+        x0=np.concatenate([model.x0, np.zeros(k)]), c=c, A=A, qd_fn=np.array(fns, np.int32), qd=qd, terms=terms,
+        name="FP(" + str(model.get("name", "")) + ")"))

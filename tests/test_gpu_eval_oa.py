@@ -238,3 +238,52 @@ def test_constraint_oa_batch_parity(bnlp_lib):
             np.testing.assert_allclose(got[b][1], vals, rtol=1e-12, atol=1e-14)
             assert got[b][2] == pytest.approx(lb, rel=1e-12, abs=1e-12) and got[b][3] == pytest.approx(ub, rel=1e-12, abs=1e-12)
     eng.close()
+
+
+@pytest.mark.gpu
+def test_fp_variant_parity(bnlp_lib):
+    """TNLP2FPNLP (§8f rank 3): the feasibility-pump / local-branching variant built by the product evaluates like the
+    CPU restatement, and a batch of rounding targets (children that differ only in the bounds of the target variables)
+    solves to the oracle's optima; with lambda = 1 and norm 2 an unconstrained-in-effect pump step is a projection."""
+    from bonmin_b200.engine import Engine, Problem
+    from oracle import ipm as oipm
+    from oracle.struct_eval import fp_model
+    rng = np.random.default_rng(4)
+    for m, kw in [(I.syn_miqcp(20, 10, 4, 4, 9), dict(norm=2, lam=0.7, sigma=0.5, scaling=2.0)),
+                  (I.syn_cvx_minlp(16, 6, 3, 5, 2), dict(norm=1, lam=1.0, sigma=1.0, scaling=1.0, rhs_local_branching=3.0)),
+                  (I.syn_miqcp(12, 6, 3, 3, 4), dict(norm=2, lam=0.5, sigma=1.0, scaling=1.0, cutoff=-60.0)),
+                  (I.syn_miqcp(12, 6, 3, 3, 4), dict(norm=2, lam=0.5, sigma=1.0, scaling=1.0, cutoff=-100.0))]:   # last: cut off
+        inds = np.flatnonzero(np.asarray(m.vtype) != 0).astype(np.int32)
+        base = Problem.from_model(m)
+        P = base.fp_variant(inds, norm=kw["norm"], lam=kw["lam"], sigma=kw["sigma"], objective_scaling_factor=kw["scaling"],
+                            cutoff=kw.get("cutoff"), rhs_local_branching=kw.get("rhs_local_branching"))
+        ref = fp_model(m, inds, **kw)
+        assert (P.n, P.m) == (ref.n, ref.m)
+        eng = Engine(P)
+        ev = Evaluator(ref)
+        X = np.concatenate([np.clip(m.x0 + rng.uniform(-0.2, 0.2, (3, m.n)), m.xl, m.xu),
+                            rng.integers(0, 2, (3, len(inds))).astype(float)], axis=1)
+        r = eng.eval_batch(X, want=("f", "g", "gradf"))
+        for b in range(3):
+            vals, grads, _ = ev.dense(X[b])
+            assert r["f"][b] == pytest.approx(vals[0], rel=1e-11, abs=1e-11)
+            np.testing.assert_allclose(r["g"][b], vals[1:], rtol=1e-11, atol=1e-11)
+            np.testing.assert_allclose(r["gradf"][b], grads[0], rtol=1e-10, atol=1e-10)
+        # a batch of rounding targets: children differ only in the bounds of the target variables
+        B = 6
+        root = Engine(base).solve_batch(m.xl, m.xu, m.x0)["x"][0]
+        T = np.clip(np.round(root[inds] + rng.uniform(-0.6, 0.6, (B, len(inds)))), m.xl[inds], m.xu[inds])
+        if kw["norm"] == 1:
+            T = np.clip(T, 0, 1)
+        XL = np.tile(np.concatenate([m.xl, np.zeros(len(inds))]), (B, 1))
+        XU = np.tile(np.concatenate([m.xu, np.zeros(len(inds))]), (B, 1))
+        XL[:, m.n:] = T
+        XU[:, m.n:] = T
+        x0 = np.concatenate([root, T[0]])
+        g = eng.solve_batch(XL, XU, x0)
+        o = oipm.solve_batch(ref, XL, XU, x0, threads=4)
+        assert (g["status"] == o["status"]).all()
+        ok = o["status"] == 1
+        assert ok.all() or kw.get("cutoff") == -100.0       # the last case is infeasible under its cutoff row
+        np.testing.assert_allclose(g["obj"][ok], o["obj"][ok], rtol=1e-6, atol=1e-7)
+        eng.close()
