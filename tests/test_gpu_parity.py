@@ -196,3 +196,25 @@ def test_element_terms_cvx_minlp(bnlp_lib, oracle_ipm):
         # the general kernel accumulates element-term gradients with FP64 atomics (order not fixed): iterates differ in
         # the last bits from run to run, which moves weakly determined components of x by up to ~2e-5 at tol 1e-8
         np.testing.assert_allclose(r["x"][ok], o["x"][ok], atol=1e-4)
+
+
+def test_randomised_shapes(bnlp_lib, oracle_ipm):
+    """Random shapes, seeds and batch sizes (1 .. 300 children, groups of 32 not filled, more/fewer children than SMs):
+    same status for every child, objectives within 1e-6 (scripts/stress_parity.py is the long version)."""
+    rng = np.random.default_rng(20261020)
+    for _ in range(10):
+        n = int(rng.choice([30, 48, 64, 100, 128]))
+        m = I.syn_miqcp(n, n // 2, int(rng.integers(1, n // 5)), int(rng.integers(0, n // 5)), int(rng.integers(1, 10 ** 6)))
+        B = int(rng.choice([1, 7, 33, 64, 149, 300]))
+        eng = _engine(m)
+        root = eng.solve_batch(m.xl, m.xu, m.x0)
+        if root["status"][0] != 1:
+            eng.close()
+            continue
+        xs = root["x"][0]
+        XL, XU = I.c3_children(m, xs, B)
+        for b in range(0, B, 5):
+            j = int(rng.integers(0, n // 2))
+            XL[b, j] = XU[b, j] = np.round(rng.uniform(m.xl[j], m.xu[j]))
+        _compare(eng.solve_batch(XL, XU, xs), oracle_ipm.solve_batch(m, XL, XU, xs, threads=8))
+        eng.close()
