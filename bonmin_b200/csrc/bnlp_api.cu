@@ -382,7 +382,7 @@ static int launch_ipm(bnlp_engine *E, Device &D, int B, const double *dXL, const
   if (!E->ipm_supported) { set_err("bnlp_solve_batch: " + E->ipm_unsupported_why); return -2; }
   if (B <= 0) return 0;
   int ctas = E->opt.ctas_per_device > 0 ? E->opt.ctas_per_device : D.sms;
-  ctas = std::min(ctas, B);
+  if (!E->coop_ok) ctas = std::min(ctas, B);   // the cooperative kernel keeps every SM for its shared passes
   if (D.ws.reserve((size_t)ctas * E->ws_doubles)) { set_err("workspace allocation failed"); return -1; }
   CK(cudaMemsetAsync(D.queue.p, 0, sizeof(int), stream));
   CK(cudaMemsetAsync(D.stats.p, 0, 12 * sizeof(long long), stream));

@@ -338,7 +338,11 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
   const int nqf = s_nqf;
   const int nqpad = CB.nqpad, ldd = CB.ldd;
   // cooperative decomposition: CTA = (child group g, slice s)
-  const int NG = (G + COOP_RB - 1) / COOP_RB;
+  // Only the first Gc CTAs take children (Gc = the batch rounded up to whole groups, at most G); the cooperative passes
+  // of those NG groups are sliced over ALL G CTAs, so a small batch (one B-BB node: 64 children) still has every SM
+  // streaming the shared blocks.
+  const int Gc = min(G, (A.B + COOP_RB - 1) / COOP_RB * COOP_RB);
+  const int NG = (Gc + COOP_RB - 1) / COOP_RB;
   const int NS = max(1, G / NG);
   const int my_g = cta / NS, my_s = cta % NS;
   const bool coop_on = my_g < NG;
@@ -761,7 +765,7 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
       if (act == 1) state = CS_SKIP;
       else if (act == 2) state = CS_FINISH;
     }
-    if (state == CS_NEED_CHILD) state = setup_child() ? CS_INIT : CS_IDLE;
+    if (state == CS_NEED_CHILD) state = (cta < Gc && setup_child()) ? CS_INIT : CS_IDLE;
     // publish the Hessian weights (zero unless iterating) and, when initialising, the point to evaluate
     for (int qi = tid; qi < nqpad; qi += IPM_NT) {
       double w = 0.0;
@@ -793,7 +797,7 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
       for (int e = tid; e < COOP_RB * nqpad; e += IPM_NT) {
         const int row = e / nqpad, col = e % nqpad;
         const int b = my_g * COOP_RB + row;
-        wsm[row * ldw + col] = (b < G) ? __ldcg(CB.xw + (size_t)b * nqpad + col) : 0.0;
+        wsm[row * ldw + col] = (b < Gc) ? __ldcg(CB.xw + (size_t)b * nqpad + col) : 0.0;
       }
       __syncthreads();
       const int NT16 = (P + 15) >> 4;
@@ -831,7 +835,7 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
 #pragma unroll
         for (int p = 0; p < COOP_NP; ++p) {
           const int bi = my_g * COOP_RB + 8 * p + lr;
-          if (bi < G && ec < P) {   // Wbuf rows have stride ldp too
+          if (bi < Gc && ec < P) {   // Wbuf rows have stride ldp too
             double2 *dst = reinterpret_cast<double2 *>(CB.Wbuf + (size_t)bi * M.ldp + ec);
             __stcg(dst, make_double2(cE[p][0], cO[p][0]));
             __stcg(dst + 1, make_double2(cE[p][1], cO[p][1]));
@@ -846,7 +850,7 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
     // =================================================================== C: factorisation, direction (per child)
     if (state == CS_FINISH) {
       write_results();
-      state = setup_child() ? CS_INIT : CS_IDLE;
+      state = setup_child() ? CS_INIT : CS_IDLE;   // (only CTAs below Gc ever get here)
       for (int j = tid; j < ldd; j += IPM_NT) __stcg(CB.xd + (size_t)cta * ldd + j, (state == CS_INIT && j < n) ? x[j] : 0.0);
     } else if (state == CS_ITER) {
       const double of = it_of;
@@ -980,7 +984,7 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
       double *Dsm = H;   // [COOP_RB][ldd]: the factor in H (and the staging rows behind it) is dead until the next iteration
       for (int e = tid; e < COOP_RB * ldd; e += IPM_NT) {
         const int b = my_g * COOP_RB + e / ldd;
-        Dsm[e] = (b < G) ? __ldcg(CB.xd + (size_t)b * ldd + e % ldd) : 0.0;
+        Dsm[e] = (b < Gc) ? __ldcg(CB.xd + (size_t)b * ldd + e % ldd) : 0.0;
       }
       __syncthreads();
       const int tpb = (n + 7) >> 3, ntile = nqf * tpb;
@@ -1034,7 +1038,7 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
               const int b = my_g * COOP_RB + 8 * p + 2 * lc + hh;
-              if (b < G) __stcg(A.ws + (size_t)b * A.ws_stride + off, cu[p][hh]);
+              if (b < Gc) __stcg(A.ws + (size_t)b * A.ws_stride + off, cu[p][hh]);
             }
         }
       }
