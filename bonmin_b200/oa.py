@@ -39,6 +39,11 @@ class EngineProvider:
                 for k in range(r["n_rows"])]
         return dict(rows=rows, has_alpha=r["has_alpha"], obj=r["obj"], obj_offset=r["obj_offset"])
 
+    def violation(self, x, obj):
+        """getNonLinearitiesViolation(x, obj) (BonOsiTMINLPInterface.cpp:1869-1876)."""
+        v, _ = self.eng.violation_batch(np.atleast_2d(x), np.atleast_1d(obj))
+        return float(v[0])
+
     def oa(self, X, X2=None, theta=0.0):
         X = np.atleast_2d(X)
         r = self.eng.oa_batch(X, None, self.xl, self.xu, X2=X2, theta=theta, get_obj=1)
@@ -74,6 +79,56 @@ def _solve_master(n_cols, rows, obj, obj_offset, col_lb, col_ub, integer, cutoff
     if res.status != 0 or res.x is None:
         return 1, None, 1e200
     return 0, res.x, float(res.fun) + obj_offset
+
+
+def ecp_rounds(provider, lp, rounds=5, abs_violation_tol=1e-6, rel_violation_tol=1e-4, integer=None):
+    """EcpCuts::generateCuts (src/Algorithms/OaGenerators/BonEcpCuts.cpp:46-143) on an LP relaxation `lp` (what
+    provider.extract returns): while the LP optimum violates the nonlinear rows (getNonLinearitiesViolation), linearise
+    them AT THE LP POINT (getOuterApproximation with getObj = 1), install the cuts, re-solve.  Returns dict(obj = LP
+    bound after the rounds (1e308 if the LP became infeasible), violation, rounds, cuts, rows = the enlarged row list)."""
+    P = provider
+    n = P.n
+    rows = list(lp["rows"])
+    ncols = n + (1 if lp["has_alpha"] else 0)
+    obj = np.zeros(ncols)
+    obj[:len(lp["obj"])] = lp["obj"]
+    col_lb = np.concatenate([P.xl, [-DMAX]])[:ncols]
+    col_ub = np.concatenate([P.xu, [DMAX]])[:ncols]
+    integ = np.zeros(ncols, int) if integer is None else integer
+    out = dict(rounds=0, cuts=0, violation=0.0, obj=None)
+
+    def lp_solve():
+        st, x, val = _solve_master(ncols, rows, obj, lp["obj_offset"], col_lb, col_ub, integ, 1e100)
+        return st, x, val
+
+    st, x, val = lp_solve()
+    if st != 0:
+        out["obj"] = 1.7976931348623157e308
+        return out
+    alpha = (lambda xx: xx[n]) if ncols > n else (lambda xx: val)     # the LP's value of the objective (alpha column)
+    orig = P.violation(x[:n], alpha(x))
+    out["violation"] = orig
+    viol = orig
+    for i in range(rounds):
+        if not (viol > abs_violation_tol and viol > rel_violation_tol * orig):
+            break
+        cuts = [c for c in P.oa(x[:n][None, :]) if not (c[0] == P.m and ncols == n)]
+        if not cuts or i + 1 >= rounds:
+            break
+        rows.extend(cuts)
+        out["cuts"] += len(cuts)
+        out["rounds"] += 1
+        st, x, val = lp_solve()
+        if st != 0:
+            out["obj"] = 1.7976931348623157e308
+            out["rows"] = rows
+            return out
+        viol = P.violation(x[:n], alpha(x))
+        out["violation"] = viol
+    out["obj"] = val
+    out["rows"] = rows
+    out["x"] = x
+    return out
 
 
 def run_oa(provider, integer_tolerance=1e-6, cutoff_increment=1e-5, gap_tol=1e-9, max_passes=200, time_limit=1e10,

@@ -25,6 +25,9 @@ class OracleProvider:
     def extract(self, x, duals):
         return SE.extract_linear_relaxation(self.ev, x, duals, get_obj=True)
 
+    def violation(self, x, obj):
+        return float(SE.constraints_violation(self.ev, x, obj)[0])
+
     def oa(self, X, X2=None, theta=0.0):
         out = []
         for x in np.atleast_2d(X):
@@ -65,3 +68,40 @@ def test_oa_engine_matches_oracle(bnlp_lib, oracle_ipm):
         # bit, so pass counts can differ by a few; the optimum cannot
         assert abs(g["passes"] - c["passes"]) <= max(3, c["passes"] // 5)
         eng.close()
+
+
+def test_ecp_rounds_tighten_the_lp_bound(oracle_ipm):
+    """EcpCuts::generateCuts: cuts at successive LP optima raise the LP bound monotonically towards the NLP relaxation
+    value and shrink the violation of the nonlinear rows; the LP bound never exceeds the relaxation optimum (convexity)."""
+    m = I.syn_miqcp(12, 6, 3, 3, 4)
+    P = OracleProvider(m, oracle_ipm)
+    root = P.solve(m.xl[None, :], m.xu[None, :], m.x0)
+    # start from the OA at a point far from the optimum so that the first LP is loose
+    lp = P.extract(np.clip(m.x0, m.xl, m.xu), None)
+    prev, prev_viol = -1e300, None
+    first = oa.ecp_rounds(P, lp, rounds=1)["obj"]
+    for rounds in (1, 3, 8, 30):
+        r = oa.ecp_rounds(P, lp, rounds=rounds)
+        assert r["obj"] >= prev - 1e-9 and r["obj"] <= root["obj"][0] + 1e-6 * abs(root["obj"][0])
+        prev = r["obj"]
+        if rounds == 1:
+            assert r["cuts"] == 0            # numRounds 1: the cuts are generated but the LP is not re-solved (:86)
+        else:
+            assert r["cuts"] > 0 and r["violation"] <= (prev_viol if prev_viol is not None else 1e300) + 1e-9
+        prev_viol = r["violation"]
+    # Kelley-type cutting planes converge slowly; 30 rounds must have closed most of the gap of the first LP
+    assert root["obj"][0] - prev <= 0.25 * (root["obj"][0] - first)
+
+
+@pytest.mark.gpu
+def test_ecp_engine_matches_oracle(bnlp_lib, oracle_ipm):
+    from bonmin_b200.engine import Engine, Problem
+    m = I.syn_miqcp(12, 6, 3, 3, 4)
+    eng = Engine(Problem.from_model(m))
+    G, C = oa.EngineProvider(eng), OracleProvider(m, oracle_ipm)
+    x0 = np.clip(m.x0, m.xl, m.xu)
+    g = oa.ecp_rounds(G, G.extract(x0, None), rounds=8)
+    c = oa.ecp_rounds(C, C.extract(x0, None), rounds=8)
+    assert g["rounds"] == c["rounds"] and g["cuts"] == c["cuts"]
+    assert g["obj"] == pytest.approx(c["obj"], rel=1e-8) and g["violation"] == pytest.approx(c["violation"], rel=1e-6, abs=1e-9)
+    eng.close()
