@@ -283,8 +283,10 @@ class Engine:
                                        _vp(H)))
         return dict(f=F, g=G, gradf=GF, jac=J, hess=H)
 
-    def oa_batch(self, X, DUALS=None, XL=None, XU=None, X2=None, theta=0.0, get_obj=0, tols=None):
-        """B x OsiTMINLPInterface::getOuterApproximation -> CSR rows (see include/bnlp.h)."""
+    def oa_batch(self, X, DUALS=None, XL=None, XU=None, X2=None, theta=0.0, get_obj=0, tols=None, out=None):
+        """B x OsiTMINLPInterface::getOuterApproximation -> CSR rows (see include/bnlp.h).  `out`: a dict returned by an
+        earlier call with the same B, whose arrays are reused (a caller in a loop keeps its cut buffers: allocating and
+        first-touching ~300 MB per call costs more than the whole device side)."""
         n = self.n
         X = _d(np.atleast_2d(X))
         B = X.shape[0]
@@ -292,13 +294,17 @@ class Engine:
         cap = ctypes.c_size_t()
         self._ck(lib().bnlp_oa_capacity(self.h, B, ctypes.byref(rpp), ctypes.byref(cap)))
         nrows = B * rpp.value
-        row_start = np.zeros(nrows + 1, np.int32)
-        col = np.zeros(cap.value, np.int32)
-        val = np.zeros(cap.value)
-        LB = np.zeros(nrows)
-        UB = np.zeros(nrows)
-        src = np.zeros(nrows, np.int32)
-        info = self.problem.info()
+        if out is not None and len(out["src_row"]) == nrows and len(out["val"]) == cap.value:
+            row_start, col, val, LB, UB, src = (out[k] for k in ("row_start", "col", "val", "lb", "ub", "src_row"))
+        else:
+            row_start = np.zeros(nrows + 1, np.int32)
+            col = np.zeros(cap.value, np.int32)
+            val = np.zeros(cap.value)
+            LB = np.zeros(nrows)
+            UB = np.zeros(nrows)
+            src = np.zeros(nrows, np.int32)
+        if XL is None or XU is None:
+            info = self.problem.info()
         XL = _d(info["xl"] if XL is None else XL)
         XU = _d(info["xu"] if XU is None else XU)
         Du = None if DUALS is None else _d(np.atleast_2d(DUALS))

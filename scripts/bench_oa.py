@@ -16,9 +16,9 @@ def run(B=1024, reps=5, cpu_points=8, model=None):
     r = eng.oa_batch(X, None, m.xl, m.xu, get_obj=1)          # warm-up (allocations)
     r = eng.oa_batch(X, None, m.xl, m.xu, get_obj=1)
     ts = []
-    for _ in range(reps):
+    for _ in range(reps):            # the caller keeps its cut buffers (out=r), as an LP-side consumer would
         t0 = time.perf_counter()
-        r = eng.oa_batch(X, None, m.xl, m.xu, get_obj=1)
+        r = eng.oa_batch(X, None, m.xl, m.xu, get_obj=1, out=r)
         ts.append(time.perf_counter() - t0)
     t = float(np.median(ts))
     kms = eng.stats()["device_ms"]                                   # kernels only (quad + eval + rows + scan + compact)
