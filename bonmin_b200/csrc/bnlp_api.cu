@@ -9,6 +9,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/bnlp.h"
@@ -320,6 +321,8 @@ extern "C" bnlp_engine *bnlp_engine_create(const bnlp_problem *prob, const int *
     dm.row_fn = D.row_fn.p; dm.row_sgn = D.row_sgn.p; dm.row_bnd = D.row_bnd.p;
     dm.fn_row_up = D.fn_row_up.p; dm.fn_row_lo = D.fn_row_lo.p; dm.gl = D.gl.p; dm.gu = D.gu.p;
     dm.n_terms = D.ev.n_terms; dm.term_fn = D.ev.term_fn; dm.term_var_start = D.ev.term_var_start; dm.term_var = D.ev.term_var;
+    dm.fn_term_start = D.ev.fn_term_start; dm.fn_term_list = D.ev.fn_term_list; dm.hseg_start = D.ev.hseg_start;
+    dm.hseg_target = D.ev.hseg_target; dm.hent_term = D.ev.hent_term; dm.hent_lidx = D.ev.hent_lidx; dm.n_hseg = D.ev.n_hseg;
     dm.term_op_start = D.ev.term_op_start; dm.term_op = D.ev.term_op; dm.term_iarg = D.ev.term_iarg; dm.term_darg = D.ev.term_darg;
     dm.E = E->E; dm.eq_fn = D.eq_fn.p; dm.eq_bnd = D.eq_bnd.p; dm.fn_eq = D.fn_eq.p;
     if (d == 0) {
@@ -327,7 +330,7 @@ extern "C" bnlp_engine *bnlp_engine_create(const bnlp_problem *prob, const int *
       E->h_in_smem = need + 1024 <= D.smem_optin ? 1 : 0;
       E->smem_bytes = ipm_smem_doubles(n, m, E->R, E->E, E->h_in_smem) * sizeof(double);
       if (E->smem_bytes + 1024 > D.smem_optin) { E->ipm_supported = false; E->ipm_unsupported_why = "iterate vectors do not fit shared memory"; }
-      E->ws_doubles = (size_t)2 * (m + 1) * n + (size_t)M.terms.size() * (1 + TV + TH) + (E->h_in_smem ? 0 : (size_t)(n + 3 + E->E) * (n + 4 + E->E) / 2 + 2);
+      E->ws_doubles = (size_t)2 * (m + 1) * n + (size_t)M.terms.size() * (2 + TV + TH) + (E->h_in_smem ? 0 : (size_t)(n + 3 + E->E) * (n + 4 + E->E) / 2 + 2);
       E->ws_doubles = (E->ws_doubles + 1) & ~(size_t)1;
       // cooperative DMMA kernel: needs H in shared memory, n <= 256 and the group weights to fit the staging area
       E->nqpad = (std::max(E->nq, 1) + 3) & ~3;

@@ -28,6 +28,8 @@ struct EvalModelHostOffsets {
       term_fn = 0, term_var_start = 0, term_var = 0, term_op_start = 0, term_op = 0, term_iarg = 0, term_jpos = 0,
       term_hpos = 0, jac_start = 0, jac_col = 0, hes_row = 0, hes_col = 0, nl_rows = 0, fq_fn = 0, fq_dense = 0,
       row_cap_start = 0;
+  // fixed-order accumulation of element terms (IPM kernel): terms grouped by function, Hessian entries grouped by target
+  int fn_term_start = 0, fn_term_list = 0, hseg_start = 0, hseg_target = 0, hent_term = 0, hent_lidx = 0, n_hseg = 0;
   // offsets into the packed double buffer
   int c = 0, lin_val = 0, qs_v = 0, term_darg = 0;
 };
@@ -41,6 +43,9 @@ struct EvalModelDev {
   const int *fq_fn;        // functions that own a dense quadratic block (nfq)
   const int *fq_dense;     // 1 if the block came from an explicit dense block (full Jacobian row structure)
   const int *row_cap_start;  // mnl+2 : fixed-capacity offsets of the OA rows of one point
+  const int *fn_term_start, *fn_term_list;                       // m+2, n_terms : terms of each function, in tape order
+  const int *hseg_start, *hseg_target, *hent_term, *hent_lidx;   // Hessian entries grouped by packed target tri(i)+j
+  int n_hseg;
   const double *c, *lin_val, *qs_v, *term_darg;
   const double *gl, *gu;
   // dense quadratic blocks shared with the IPM model
@@ -62,6 +67,8 @@ inline EvalModelDev make_eval_model_dev(const EvalModelHostOffsets &o, const int
   e.term_jpos = I + o.term_jpos; e.term_hpos = I + o.term_hpos;
   e.jac_start = I + o.jac_start; e.jac_col = I + o.jac_col; e.hes_row = I + o.hes_row; e.hes_col = I + o.hes_col;
   e.nl_rows = I + o.nl_rows; e.fq_fn = I + o.fq_fn; e.fq_dense = I + o.fq_dense; e.row_cap_start = I + o.row_cap_start;
+  e.fn_term_start = I + o.fn_term_start; e.fn_term_list = I + o.fn_term_list; e.hseg_start = I + o.hseg_start;
+  e.hseg_target = I + o.hseg_target; e.hent_term = I + o.hent_term; e.hent_lidx = I + o.hent_lidx; e.n_hseg = o.n_hseg;
   e.c = D + o.c; e.lin_val = D + o.lin_val; e.qs_v = D + o.qs_v; e.term_darg = D + o.term_darg;
   e.gl = gl; e.gu = gu;
   return e;

@@ -26,6 +26,7 @@ constexpr int IPM_NW = IPM_NT / 32;   // warps per CTA
 constexpr int IPM_KC = 16;            // rank of one staged SYRK / trailing update
 constexpr int IPM_NB = 8;             // Cholesky panel width
 constexpr int IPM_MAXE = 8;           // equality rows supported by the Schur-complement path
+constexpr int TREC = 2 + TV + TH;     // per-term record: value, local gradient, packed local Hessian, trial value
 constexpr int IPM_MAXC = 16;          // column accumulators per lane in the symmetric mat-vec: n <= 512
 
 // TNLPSolver::ReturnStatus (BonTNLPSolver.hpp:29-44)
@@ -66,6 +67,9 @@ struct DevModel {
   int n_terms;
   const int *term_fn, *term_var_start, *term_var, *term_op_start, *term_op, *term_iarg;
   const double *term_darg;
+  // fixed-order accumulation of the terms (no floating-point atomics: results do not depend on thread timing)
+  const int *fn_term_start, *fn_term_list, *hseg_start, *hseg_target, *hent_term, *hent_lidx;
+  int n_hseg;
   const double *gl, *gu;        // m
 };
 
@@ -412,7 +416,7 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_kernel(DevModel M, IpmArgs A) {
   double *uq = grad + (size_t)(m + 1) * n;        // (m+1) x n
   const int NTm = M.n_terms;
   double *tgl = uq + (size_t)(m + 1) * n;          // per term: value, local gradient (TV), packed local Hessian (TH)
-  if (A.h_in_smem) { H = sp; sp += (Haug + 1) & ~1; } else { H = tgl + (size_t)NTm * (1 + TV + TH); }
+  if (A.h_in_smem) { H = sp; sp += (Haug + 1) & ~1; } else { H = tgl + (size_t)NTm * TREC; }
   double *stage = sp; sp += (IPM_NW + 1) * npad;
   double *x = sp; sp += npad;
   double *zL = sp; sp += npad;
@@ -547,33 +551,43 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_kernel(DevModel M, IpmArgs A) {
     __syncthreads();
 
     // ---- element terms: evaluate at x, add values/gradients to val/grad (sgn = +1) or remove the stored ones (-1)
+    // Accumulation order is fixed: thread k walks the terms of function k in tape order (M.fn_term_list).
     auto terms_remove = [&]() {
       if (NTm == 0) return;
-      for (int t = tid; t < NTm; t += IPM_NT) {
-        const int fn = M.term_fn[t], v0 = M.term_var_start[t], nv = M.term_var_start[t + 1] - v0;
-        const double *rec = tgl + (size_t)t * (1 + TV + TH);
-        for (int a = 0; a < nv; ++a) atomicAdd(&grad[(size_t)fn * n + M.term_var[v0 + a]], -rec[1 + a]);
+      for (int k = tid; k <= m; k += IPM_NT) {
+        for (int e = M.fn_term_start[k]; e < M.fn_term_start[k + 1]; ++e) {
+          const int t = M.fn_term_list[e], v0 = M.term_var_start[t], nv = M.term_var_start[t + 1] - v0;
+          const double *rec = tgl + (size_t)t * TREC;
+          for (int a = 0; a < nv; ++a) grad[(size_t)k * n + M.term_var[v0 + a]] -= rec[1 + a];
+        }
+        val[k] -= tval[k];
       }
-      for (int k = tid; k <= m; k += IPM_NT) val[k] -= tval[k];
       __syncthreads();
     };
     auto terms_add = [&]() {
       if (NTm == 0) return;
-      for (int k = tid; k <= m; k += IPM_NT) tval[k] = 0.0;
-      __syncthreads();
       HDual st[TS];
       HDual r;
       for (int t = tid; t < NTm; t += IPM_NT) {
         eval_term(M, t, x, st, r, 2);
-        const int fn = M.term_fn[t], v0 = M.term_var_start[t], nv = M.term_var_start[t + 1] - v0;
-        double *rec = tgl + (size_t)t * (1 + TV + TH);
+        const int v0 = M.term_var_start[t], nv = M.term_var_start[t + 1] - v0;
+        double *rec = tgl + (size_t)t * TREC;
         rec[0] = r.v;
-        for (int a = 0; a < nv; ++a) { rec[1 + a] = r.g[a]; atomicAdd(&grad[(size_t)fn * n + M.term_var[v0 + a]], r.g[a]); }
+        for (int a = 0; a < nv; ++a) rec[1 + a] = r.g[a];
         for (int a = 0; a < nv * (nv + 1) / 2; ++a) rec[1 + TV + a] = r.h[a];
-        atomicAdd(&tval[fn], r.v);
       }
       __syncthreads();
-      for (int k = tid; k <= m; k += IPM_NT) val[k] += tval[k];
+      for (int k = tid; k <= m; k += IPM_NT) {
+        double tv = 0.0;
+        for (int e = M.fn_term_start[k]; e < M.fn_term_start[k + 1]; ++e) {
+          const int t = M.fn_term_list[e], v0 = M.term_var_start[t], nv = M.term_var_start[t + 1] - v0;
+          const double *rec = tgl + (size_t)t * TREC;
+          tv += rec[0];
+          for (int a = 0; a < nv; ++a) grad[(size_t)k * n + M.term_var[v0 + a]] += rec[1 + a];
+        }
+        tval[k] = tv;
+        val[k] += tv;
+      }
       __syncthreads();
     };
     terms_add();
@@ -866,17 +880,14 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_kernel(DevModel M, IpmArgs A) {
           for (int k = tid; k <= n; k += IPM_NT) H[tri(n) + k] = 0.0;
         }
         __syncthreads();
-        if (NTm > 0) {   // + sum_t w_fn(t) * Hessian of term t (stored at the last evaluation)
-          for (int t = tid; t < NTm; t += IPM_NT) {
-            const int fn = M.term_fn[t], v0 = M.term_var_start[t], nv = M.term_var_start[t + 1] - v0;
-            const double wgt = wq[fn];
-            if (wgt == 0.0) continue;
-            const double *rec = tgl + (size_t)t * (1 + TV + TH) + 1 + TV;
-            for (int a = 0; a < nv; ++a)
-              for (int b = 0; b <= a; ++b) {
-                const int i = M.term_var[v0 + a], j = M.term_var[v0 + b];
-                atomicAdd(&H[tri(max(i, j)) + min(i, j)], wgt * rec[a * (a + 1) / 2 + b]);
-              }
+        if (NTm > 0) {   // + sum_t w_fn(t) * Hessian of term t (stored at the last evaluation); one thread per target entry
+          for (int sg = tid; sg < M.n_hseg; sg += IPM_NT) {
+            double acc = 0.0;
+            for (int e = M.hseg_start[sg]; e < M.hseg_start[sg + 1]; ++e) {
+              const int t = M.hent_term[e];
+              acc = fma(wq[M.term_fn[t]], tgl[(size_t)t * TREC + 1 + TV + M.hent_lidx[e]], acc);
+            }
+            H[M.hseg_target[sg]] += acc;
           }
           __syncthreads();
         }
@@ -1092,12 +1103,14 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_kernel(DevModel M, IpmArgs A) {
       const double gd_obj_total = gd0[0];   // directional derivative of f uses the total gradient
       if (NTm > 0) {   // the closed-form trial values use the quadratic part only: remove the terms' share of grad.dx
         __syncthreads();
-        for (int t = tid; t < NTm; t += IPM_NT) {
-          const int fn = M.term_fn[t], v0 = M.term_var_start[t], nv = M.term_var_start[t + 1] - v0;
-          const double *rec = tgl + (size_t)t * (1 + TV + TH);
+        for (int kf = tid; kf <= m; kf += IPM_NT) {
           double acc = 0.0;
-          for (int a = 0; a < nv; ++a) acc = fma(rec[1 + a], dx[M.term_var[v0 + a]], acc);
-          atomicAdd(&gd0[fn], -acc);
+          for (int e = M.fn_term_start[kf]; e < M.fn_term_start[kf + 1]; ++e) {
+            const int t = M.fn_term_list[e], v0 = M.term_var_start[t], nv = M.term_var_start[t + 1] - v0;
+            const double *rec = tgl + (size_t)t * TREC;
+            for (int a = 0; a < nv; ++a) acc = fma(rec[1 + a], dx[M.term_var[v0 + a]], acc);
+          }
+          gd0[kf] -= acc;
         }
         __syncthreads();
       }
@@ -1113,14 +1126,19 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_kernel(DevModel M, IpmArgs A) {
         double t2[2] = {0.0, 0.0};
         const double t = tcur + a * dxt;
         if (NTm > 0) {   // element terms at the trial point (values only); Sx is free here and holds x + a dx
-          for (int k = tid; k <= m; k += IPM_NT) tvt[k] = -tval[k];
           for (int j = tid; j < n; j += IPM_NT) Sx[j] = x[j] + a * dx[j];
           __syncthreads();
           HDual st[TS];
           HDual r;
           for (int tt = tid; tt < NTm; tt += IPM_NT) {
             eval_term(M, tt, Sx, st, r, 0);
-            atomicAdd(&tvt[M.term_fn[tt]], r.v);
+            tgl[(size_t)tt * TREC + TREC - 1] = r.v;       // trial value, summed per function in tape order below
+          }
+          __syncthreads();
+          for (int k = tid; k <= m; k += IPM_NT) {
+            double tv = -tval[k];
+            for (int e = M.fn_term_start[k]; e < M.fn_term_start[k + 1]; ++e) tv += tgl[(size_t)M.fn_term_list[e] * TREC + TREC - 1];
+            tvt[k] = tv;
           }
           __syncthreads();
         }
