@@ -345,28 +345,30 @@ __global__ void __launch_bounds__(EV_NT) eval_kernel(EvalModelDev M, EvalArgs A)
     }
   }
   __syncthreads();
-  // ---- general nonlinear element terms: one thread per term
+  // ---- general nonlinear element terms: one thread per FUNCTION walks its terms in tape order, so values, gradients and
+  // Jacobian entries are accumulated in a fixed order (only the optional Hessian values still use atomics: entries of
+  // different functions meet in the same position)
   if (M.n_terms > 0) {
     HDual st[TS];
     HDual r;
-    for (int t = tid; t < M.n_terms; t += EV_NT) {
-      const int k = M.term_fn[t];
-      eval_term(M, t, x, st, r, hv ? 2 : 1);
-      const int v0 = M.term_var_start[t], nv = M.term_var_start[t + 1] - v0;
-      atomicAdd(&fv[k], r.v);
-      for (int a = 0; a < nv; ++a) {
-        if (k == 0) { if (gf) atomicAdd(&gf[M.term_var[v0 + a]], r.g[a]); }
-        else if (jv) atomicAdd(&jv[M.term_jpos[v0 + a]], r.g[a]);
-      }
-      if (hv) {
-        const double wgt = (k == 0) ? A.sigma : (lam ? lam[k - 1] : 0.0);
-        if (wgt != 0.0)
+    for (int k = tid; k <= m; k += EV_NT) {
+      const double wgt = (k == 0) ? A.sigma : (lam ? lam[k - 1] : 0.0);
+      double fk = 0.0;
+      for (int e = M.fn_term_start[k]; e < M.fn_term_start[k + 1]; ++e) {
+        const int t = M.fn_term_list[e];
+        eval_term(M, t, x, st, r, hv ? 2 : 1);
+        const int v0 = M.term_var_start[t], nv = M.term_var_start[t + 1] - v0;
+        fk += r.v;
+        for (int a = 0; a < nv; ++a) {
+          if (k == 0) { if (gf) gf[M.term_var[v0 + a]] += r.g[a]; }
+          else if (jv) jv[M.term_jpos[v0 + a]] += r.g[a];
+        }
+        if (hv && wgt != 0.0)
           for (int a = 0; a < nv; ++a)
-            for (int c = 0; c <= a; ++c) {
-              // two local slots may map to the same structural entry only if a == c (variables of a term are distinct)
+            for (int c = 0; c <= a; ++c)
               atomicAdd(&hv[M.term_hpos[(size_t)t * TV * TV + a * TV + c]], wgt * r.h[a * (a + 1) / 2 + c]);
-            }
       }
+      fv[k] += fk;
     }
   }
   __syncthreads();
