@@ -222,3 +222,78 @@ def test_randomised_shapes(bnlp_lib, oracle_ipm):
             XL[b, j] = XU[b, j] = np.round(rng.uniform(m.xl[j], m.xu[j]))
         _compare(eng.solve_batch(XL, XU, xs), oracle_ipm.solve_batch(m, XL, XU, xs, threads=8))
         eng.close()
+
+
+def _custom(n, m, Q0=None, c0=None, A=None, gl=None, gu=None, xl=None, xu=None, x0=None, qd_rows=()):
+    """hand-built StructuredModel: objective 1/2 x'Q0 x + c0.x (Q0 may be None), rows A x (+ 1/2 x'Qi x for qd_rows)."""
+    INF = 1e19
+    Afull = np.zeros((m + 1, n))
+    if c0 is not None:
+        Afull[0] = c0
+    if A is not None:
+        Afull[1:] = A
+    qd_fn, qd = [], []
+    if Q0 is not None:
+        qd_fn.append(0)
+        qd.append(I.pack_lower(Q0))
+    for i, Qi in qd_rows:
+        qd_fn.append(i)
+        qd.append(I.pack_lower(Qi))
+    return I._empty_sparse(I.StructuredModel(
+        n=n, m=m, xl=np.full(n, -INF) if xl is None else np.asarray(xl, float), xu=np.full(n, INF) if xu is None else np.asarray(xu, float),
+        gl=np.full(m, -INF) if gl is None else np.asarray(gl, float), gu=np.full(m, INF) if gu is None else np.asarray(gu, float),
+        vtype=np.zeros(n, np.int32), x0=np.zeros(n) if x0 is None else np.asarray(x0, float), c=np.zeros(m + 1), A=Afull,
+        qd_fn=np.array(qd_fn, np.int32), qd=np.array(qd).reshape(len(qd_fn), n * (n + 1) // 2), name="custom"))
+
+
+def test_unusual_model_shapes(bnlp_lib, oracle_ipm):
+    """Shapes at the edge of the interface: no rows at all, one variable, free variables, a linear program (no
+    quadratic block anywhere), an equality-only model, a ranged row; each with a small batch of bound changes."""
+    rng = np.random.default_rng(12)
+    G = rng.standard_normal((6, 6))
+    Q = G @ G.T + np.eye(6)
+    models = {
+        "box QP without rows": _custom(6, 0, Q0=Q, c0=rng.standard_normal(6), xl=-np.ones(6), xu=np.ones(6)),
+        "one variable": _custom(1, 1, Q0=np.array([[2.0]]), c0=[-3.0], A=[[1.0]], gu=[1.0], xl=[-5.0], xu=[5.0]),
+        "free variables": _custom(6, 2, Q0=Q, c0=rng.standard_normal(6), A=rng.standard_normal((2, 6)), gu=[1.0, 2.0]),
+        "linear program": _custom(5, 3, c0=[1, 2, -1, 0.5, -2], A=rng.standard_normal((3, 5)), gu=[1, 1, 1], gl=[-1, -1, -1],
+                                  xl=-np.ones(5), xu=np.ones(5)),
+        "equality only": _custom(6, 2, Q0=Q, A=rng.standard_normal((2, 6)), gl=[0.5, -0.25], gu=[0.5, -0.25], xl=-3 * np.ones(6),
+                                 xu=3 * np.ones(6)),
+        "ranged quadratic row": _custom(6, 1, c0=rng.standard_normal(6), qd_rows=[(1, Q)], gl=[0.5], gu=[4.0], xl=-3 * np.ones(6),
+                                        xu=3 * np.ones(6)),
+    }
+    for name, m in models.items():
+        eng = _engine(m)
+        B = 5
+        XL = np.tile(m.xl, (B, 1))
+        XU = np.tile(m.xu, (B, 1))
+        XU[1, 0] = min(m.xu[0], 0.25)
+        XL[2, 0] = max(m.xl[0], -0.25)
+        XL[3, -1] = XU[3, -1] = 0.1           # one variable fixed
+        XL[4, 0], XU[4, 0] = 0.3, 0.2         # crossed bounds
+        r = eng.solve_batch(XL, XU, m.x0)
+        o = oracle_ipm.solve_batch(m, XL, XU, m.x0, threads=4)
+        assert (r["status"] == o["status"]).all(), (name, r["status"], o["status"])
+        ok = o["status"] == 1
+        assert ok[:4].any() or name == "linear program", name
+        np.testing.assert_allclose(r["obj"][ok], o["obj"][ok], rtol=1e-6, atol=1e-8, err_msg=name)
+        eng.close()
+
+
+def test_largest_supported_model(bnlp_lib, oracle_ipm):
+    """n = 512: the largest model the batched IPM accepts (condensed matrix in global memory); n = 513 is refused loudly."""
+    from bonmin_b200.engine import BnlpError
+    m = I.syn_miqcp(512, 8, 2, 3, 77)
+    eng = _engine(m)
+    XL = np.tile(m.xl, (2, 1))
+    XU = np.tile(m.xu, (2, 1))
+    XU[1, 0] = 3.0
+    r = eng.solve_batch(XL, XU, m.x0)
+    o = oracle_ipm.solve_batch(m, XL, XU, m.x0, threads=2)
+    _compare(r, o)
+    eng.close()
+    big = _engine(I.syn_miqcp(513, 4, 1, 1, 78))
+    with pytest.raises(BnlpError, match="512"):
+        big.solve_batch(XL[:, :1].repeat(513, 1), XU[:, :1].repeat(513, 1), np.zeros(513))
+    big.close()
