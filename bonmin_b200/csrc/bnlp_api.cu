@@ -115,6 +115,7 @@ struct bnlp_engine {
   int nqpad = 0, ldd = 0;
   size_t ws_doubles = 0;
   int nnz_jac = 0, nnz_hes = 0, m_nl = 0;
+  bnlp_engine *tqp_engine = nullptr;   // cached engine of the QP strong-branching surrogate (same shape at every node)
 };
 
 extern "C" bnlp_problem *bnlp_problem_from_tape(const bnlp_tape_desc *desc, char *err, size_t errlen) {
@@ -211,6 +212,60 @@ static int upload(DBuf<T> &b, const std::vector<T> &v) {
 int build_eval_tape(const HostModel &M, bool densified, std::vector<int> &ints, std::vector<double> &dbls,
                     EvalModelHostOffsets &off, const std::vector<int> &qidx);
 
+namespace {
+// IPM view of a model: dense A, one packed quadratic block per function (device strides), one-sided rows, equality rows
+struct IpmView {
+  std::vector<double> A, QpD, Qf, row_sgn, row_bnd, eq_bnd;
+  std::vector<int> qidx, row_fn, fn_up, fn_lo, eq_fn, fn_eq;
+  int nq = 0, nE = 0;
+  size_t ldp = 0, ldq = 0;
+};
+void build_ipm_view(const HostModel &M, IpmView &V) {
+  const int n = M.n, m = M.m;
+  const size_t P = (size_t)n * (n + 1) / 2;
+  V.A.assign((size_t)(m + 1) * n, 0.0);
+  for (int k = 0; k <= m; ++k)
+    for (int e = M.lin_start[k]; e < M.lin_start[k + 1]; ++e) V.A[(size_t)k * n + M.lin_col[e]] += M.lin_val[e];
+  V.qidx.assign(m + 1, -1);
+  std::vector<double> Qp;
+  auto block_of = [&](int fn) {
+    if (V.qidx[fn] < 0) { V.qidx[fn] = (int)(Qp.size() / P); Qp.resize(Qp.size() + P, 0.0); }
+    return Qp.data() + (size_t)V.qidx[fn] * P;
+  };
+  for (size_t q = 0; q < M.qd_fn.size(); ++q) {
+    double *dst = block_of(M.qd_fn[q]);
+    const double *src = M.qd.data() + q * P;
+    for (size_t e = 0; e < P; ++e) dst[e] += src[e];
+  }
+  const bool densify = n <= 32 * IPM_MAXC;   // small models: every quadratic part becomes a dense block
+  for (size_t e = 0; densify && e < M.qs_fn.size(); ++e) {
+    double *dst = block_of(M.qs_fn[e]);
+    dst[(size_t)M.qs_i[e] * (M.qs_i[e] + 1) / 2 + M.qs_j[e]] += M.qs_v[e];
+  }
+  V.nq = (int)(Qp.size() / P);
+  // device strides: 128-byte aligned packed blocks and full-matrix rows (every request is a whole cache line)
+  V.ldp = (P + 15) & ~(size_t)15; V.ldq = ((size_t)n + 15) & ~(size_t)15;
+  V.Qf.assign((size_t)V.nq * n * V.ldq, 0.0); V.QpD.assign((size_t)V.nq * V.ldp, 0.0);
+  for (int q = 0; q < V.nq; ++q) {
+    std::copy(Qp.begin() + (size_t)q * P, Qp.begin() + (size_t)(q + 1) * P, V.QpD.begin() + (size_t)q * V.ldp);
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j <= i; ++j) {
+        const double v = Qp[(size_t)q * P + (size_t)i * (i + 1) / 2 + j];
+        V.Qf[((size_t)q * n + i) * V.ldq + j] = v;
+        V.Qf[((size_t)q * n + j) * V.ldq + i] = v;
+      }
+  }
+  V.fn_up.assign(m + 1, -1); V.fn_lo.assign(m + 1, -1); V.fn_eq.assign(m + 1, -1);
+  V.nE = 0;
+  for (int i = 0; i < m; ++i) {
+    const bool lo = M.gl[i] > -kInf, hi = M.gu[i] < kInf;
+    if (lo && hi && M.gl[i] == M.gu[i]) { V.fn_eq[i + 1] = V.nE++; V.eq_fn.push_back(i + 1); V.eq_bnd.push_back(M.gl[i]); continue; }
+    if (hi) { V.fn_up[i + 1] = (int)V.row_fn.size(); V.row_fn.push_back(i + 1); V.row_sgn.push_back(1.0); V.row_bnd.push_back(M.gu[i]); }
+    if (lo) { V.fn_lo[i + 1] = (int)V.row_fn.size(); V.row_fn.push_back(i + 1); V.row_sgn.push_back(-1.0); V.row_bnd.push_back(-M.gl[i]); }
+  }
+}
+}  // namespace
+
 extern "C" bnlp_engine *bnlp_engine_create(const bnlp_problem *prob, const int *device_ids, int ndev,
                                            const bnlp_options *opt) {
   if (!prob) { set_err("null problem"); return nullptr; }
@@ -233,47 +288,14 @@ extern "C" bnlp_engine *bnlp_engine_create(const bnlp_problem *prob, const int *
   for (int i = 0; i < m; ++i) E->m_nl += M.con_nonlinear[i];
 
   // ---- IPM view of the model: dense A, one packed quadratic block per function, one-sided rows
-  std::vector<double> A((size_t)(m + 1) * n, 0.0);
-  for (int k = 0; k <= m; ++k)
-    for (int e = M.lin_start[k]; e < M.lin_start[k + 1]; ++e) A[(size_t)k * n + M.lin_col[e]] += M.lin_val[e];
-  std::vector<int> qidx(m + 1, -1);
-  std::vector<double> Qp;
-  auto block_of = [&](int fn) {
-    if (qidx[fn] < 0) { qidx[fn] = (int)(Qp.size() / P); Qp.resize(Qp.size() + P, 0.0); }
-    return Qp.data() + (size_t)qidx[fn] * P;
-  };
-  for (size_t q = 0; q < M.qd_fn.size(); ++q) {
-    double *dst = block_of(M.qd_fn[q]);
-    const double *src = M.qd.data() + q * P;
-    for (size_t e = 0; e < P; ++e) dst[e] += src[e];
-  }
-  const bool densify = n <= 32 * IPM_MAXC;   // small models: every quadratic part becomes a dense block
-  for (size_t e = 0; densify && e < M.qs_fn.size(); ++e) {
-    double *dst = block_of(M.qs_fn[e]);
-    dst[(size_t)M.qs_i[e] * (M.qs_i[e] + 1) / 2 + M.qs_j[e]] += M.qs_v[e];
-  }
-  E->nq = (int)(Qp.size() / P);
-  // device strides: 128-byte aligned packed blocks and full-matrix rows (every request is a whole cache line)
-  const size_t ldp = (P + 15) & ~(size_t)15, ldq = ((size_t)n + 15) & ~(size_t)15;
-  std::vector<double> Qf((size_t)E->nq * n * ldq, 0.0), QpD((size_t)E->nq * ldp, 0.0);
-  for (int q = 0; q < E->nq; ++q) {
-    std::copy(Qp.begin() + (size_t)q * P, Qp.begin() + (size_t)(q + 1) * P, QpD.begin() + (size_t)q * ldp);
-    for (int i = 0; i < n; ++i)
-      for (int j = 0; j <= i; ++j) {
-        const double v = Qp[(size_t)q * P + (size_t)i * (i + 1) / 2 + j];
-        Qf[((size_t)q * n + i) * ldq + j] = v;
-        Qf[((size_t)q * n + j) * ldq + i] = v;
-      }
-  }
-  std::vector<int> row_fn, fn_up(m + 1, -1), fn_lo(m + 1, -1), eq_fn, fn_eq(m + 1, -1);
-  std::vector<double> eq_bnd;
-  std::vector<double> row_sgn, row_bnd;
-  for (int i = 0; i < m; ++i) {
-    const bool lo = M.gl[i] > -kInf, hi = M.gu[i] < kInf;
-    if (lo && hi && M.gl[i] == M.gu[i]) { fn_eq[i + 1] = E->E++; eq_fn.push_back(i + 1); eq_bnd.push_back(M.gl[i]); continue; }
-    if (hi) { fn_up[i + 1] = (int)row_fn.size(); row_fn.push_back(i + 1); row_sgn.push_back(1.0); row_bnd.push_back(M.gu[i]); }
-    if (lo) { fn_lo[i + 1] = (int)row_fn.size(); row_fn.push_back(i + 1); row_sgn.push_back(-1.0); row_bnd.push_back(-M.gl[i]); }
-  }
+  IpmView V;
+  build_ipm_view(M, V);
+  std::vector<double> &A = V.A, &QpD = V.QpD, &Qf = V.Qf, &row_sgn = V.row_sgn, &row_bnd = V.row_bnd, &eq_bnd = V.eq_bnd;
+  std::vector<int> &qidx = V.qidx, &row_fn = V.row_fn, &fn_up = V.fn_up, &fn_lo = V.fn_lo, &eq_fn = V.eq_fn, &fn_eq = V.fn_eq;
+  const size_t ldp = V.ldp, ldq = V.ldq;
+  const bool densify = n <= 32 * IPM_MAXC;
+  E->nq = V.nq;
+  E->E = V.nE;
   E->R = (int)row_fn.size();
   if (E->E > IPM_MAXE) { E->ipm_supported = false; E->ipm_unsupported_why = "more than 8 equality rows are not supported by the batched IPM yet"; }
   if (n > 32 * IPM_MAXC) { E->ipm_supported = false; E->ipm_unsupported_why = "n > 512 is not supported by the batched IPM yet"; }
@@ -360,8 +382,32 @@ extern "C" bnlp_engine *bnlp_engine_create(const bnlp_problem *prob, const int *
   return E;
 }
 
+// Same structure, new numbers: refresh the model data of an existing engine in place (used by the QP strong-branching
+// surrogate, whose tape has the same shape at every node).  Returns 1 if reloaded, 0 if the structure differs.
+int engine_reload_values(bnlp_engine *Q, const HostModel &M) {
+  if (Q->M.n != M.n || Q->M.m != M.m || Q->M.terms.size() != M.terms.size() || !M.terms.empty()) return 0;
+  IpmView V;
+  build_ipm_view(M, V);
+  if (V.nq != Q->nq || V.nE != Q->E || (int)V.row_fn.size() != Q->R) return 0;
+  for (Device &D : Q->devs) {
+    if (cudaSetDevice(D.id) != cudaSuccess) return 0;
+    std::vector<int> old_q(M.m + 1), old_r(V.row_fn.size());
+    if (cudaMemcpy(old_q.data(), D.qidx.p, old_q.size() * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    if (!old_r.empty() && cudaMemcpy(old_r.data(), D.row_fn.p, old_r.size() * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    if (old_q != V.qidx || old_r != V.row_fn) return 0;
+    int bad = 0;
+    bad |= upload(D.c, M.c); bad |= upload(D.A, V.A); bad |= upload(D.Qp, V.QpD); bad |= upload(D.Qf, V.Qf);
+    bad |= upload(D.row_bnd, V.row_bnd); bad |= upload(D.eq_bnd, V.eq_bnd);
+    bad |= upload(D.gl, M.gl); bad |= upload(D.gu, M.gu); bad |= upload(D.xl, M.xl); bad |= upload(D.xu, M.xu);
+    if (bad) return 0;
+  }
+  Q->M = M;
+  return 1;
+}
+
 extern "C" void bnlp_engine_free(bnlp_engine *E) {
   if (!E) return;
+  if (E->tqp_engine) { bnlp_engine_free(E->tqp_engine); E->tqp_engine = nullptr; }
   for (Device &D : E->devs) {
     cudaSetDevice(D.id);
     for (auto *b : {&D.c, &D.A, &D.Qp, &D.Qf, &D.row_sgn, &D.row_bnd, &D.gl, &D.gu, &D.xl, &D.xu, &D.e_dbl, &D.dXL, &D.dXU,
