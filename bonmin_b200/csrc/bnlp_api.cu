@@ -492,6 +492,14 @@ extern "C" int bnlp_solve_batch(bnlp_engine *E, int B, const double *XL, const d
     int rc = launch_ipm(E, D, nb, D.dXL.p, D.dXU.p, D.dX0.p, x0_per_child, D.dOBJ.p, D.dST.p, D.dIT.p,
                         X ? D.dX.p : nullptr, G ? D.dG.p : nullptr, DUALS ? D.dD.p : nullptr, D.stream);
     if (rc) return rc;
+  }
+  // phase 1b: results back.  (Separate loop: a device-to-host copy into pageable memory blocks the host until the
+  // device's kernel has finished, so issuing it inside the launch loop would run the devices one after the other.)
+  for (int d = 0; d < nd; ++d) {
+    const int b0 = d * per, nb = std::min(per, B - b0);
+    if (nb <= 0) break;
+    Device &D = E->devs[d];
+    CK(cudaSetDevice(D.id));
     CK(cudaMemcpyAsync(OBJ + b0, D.dOBJ.p, (size_t)nb * 8, cudaMemcpyDeviceToHost, D.stream));
     CK(cudaMemcpyAsync(STATUS + b0, D.dST.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, D.stream));
     CK(cudaMemcpyAsync(ITERS + b0, D.dIT.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, D.stream));
