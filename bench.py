@@ -138,15 +138,24 @@ def bb_section(args, local_rank):
         "gpu_wall_s": g32["seconds"], "optimum_gpu": g32["best_obj"], "nodes": g32["nodes"], "launch_rounds": g32["sb_batches"],
         "child_nlps": g32["sb_children"],
         "same_optimum_1e-6": bool(abs(g32["best_obj"] - c["best_obj"]) <= 1e-6 * max(1.0, abs(c["best_obj"])))}
+    # variable_selection qp-strong-branching: the children are solved on the BranchingTQP surrogate (ranking only)
+    gq = bb.run_engine(eng, **dict(kw, variable_selection="qp-strong-branching"))
+    out["to_optimum_qp_strong_branching"] = {
+        "gpu_wall_s": gq["seconds"], "optimum_gpu": gq["best_obj"], "nodes": gq["nodes"], "child_qps": gq["sb_children"],
+        "same_optimum_1e-6": bool(abs(gq["best_obj"] - c["best_obj"]) <= 1e-6 * max(1.0, abs(c["best_obj"])))}
     eng.close()
     m = I.config_c2()
     eng = Engine(Problem.from_model(m), devices=[local_rank])
     kw = dict(number_strong_branch=32, number_before_trust=1000000, node_limit=300, time_limit=120.0)
     bb.run_engine(eng, **dict(kw, node_limit=10))
     g = bb.run_engine(eng, **kw)
+    g32 = bb.run_engine(eng, **dict(kw, parallel_nodes=32))
     out["c2_bounded"] = {"instance": m.name + ", B-BB, 32 candidates/node (64 children/node), first 300 nodes",
                          "gpu_wall_s": g["seconds"], "nodes": g["nodes"], "child_nlps": g["sb_children"],
-                         "children_per_s": g["sb_children"] / g["seconds"], "best_obj": g["best_obj"], "status": g["status"]}
+                         "children_per_s": g["sb_children"] / g["seconds"], "best_obj": g["best_obj"], "status": g["status"],
+                         "with_32_nodes_per_round": {"gpu_wall_s": g32["seconds"], "nodes": g32["nodes"],
+                                                     "child_nlps": g32["sb_children"],
+                                                     "children_per_s": g32["sb_children"] / max(g32["seconds"], 1e-9)}}
     eng.close()
     return out
 
