@@ -4,7 +4,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from bonmin_b200 import bb, instances as I
 from bonmin_b200.engine import Problem, Engine
 m = I.config_c2()
-eng = Engine(Problem.from_model(m))
+import torch
+nd = int(os.environ.get('BNLP_NDEV', '1'))
+eng = Engine(Problem.from_model(m), devices=list(range(min(nd, torch.cuda.device_count()))))
+print('devices', min(nd, torch.cuda.device_count()))
 P = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 T = float(sys.argv[2]) if len(sys.argv) > 2 else 60.0
 bb.run_engine(eng, number_strong_branch=32, number_before_trust=1000000, node_limit=20)
