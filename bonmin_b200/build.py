@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libbnlp.so")
-SOURCES = ["bnlp_launch_ipm.cu", "bnlp_launch_coop.cu", "bnlp_api.cu", "bnlp_model.cpp", "bnlp_nl.cpp",
+SOURCES = ["bnlp_launch_ipm.cu", "bnlp_launch_coop.cu", "bnlp_launch_coop256.cu", "bnlp_api.cu", "bnlp_model.cpp", "bnlp_nl.cpp",
            "../host/B200Solver.cpp", "../host/host_cabi.cpp"]
 HOST_LIB = os.path.join(HERE, "libbnlp_host.so")
 HEADERS = ["../host/B200Solver.hpp", "../host/bonmin_shim.hpp", "bnlp_internal.h", "bnlp_ipm.cuh", "bnlp_ipm_coop.cuh",
@@ -23,6 +23,8 @@ DEPS = {
     "bnlp_launch_ipm.cu": ["bnlp_internal.h", "bnlp_ipm.cuh", "bnlp_eval.cuh", "../../include/bnlp.h"],
     "bnlp_launch_coop.cu": ["bnlp_internal.h", "bnlp_ipm.cuh", "bnlp_ipm_coop.cuh", "bnlp_dense.cuh", "bnlp_eval.cuh",
                             "../../include/bnlp.h"],
+    "bnlp_launch_coop256.cu": ["bnlp_internal.h", "bnlp_ipm.cuh", "bnlp_ipm_coop.cuh", "bnlp_dense.cuh", "bnlp_eval.cuh",
+                               "../../include/bnlp.h"],
 }
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-DBNLP_WITH_ENGINE"]

@@ -36,6 +36,11 @@ cudaError_t ipm_coop_launch(bool timers, int ctas, size_t smem, cudaStream_t str
 
 using namespace bnlp;
 
+// 256-thread build of the cooperative kernel (bnlp_launch_coop256.cu)
+cudaError_t bnlp_coop256_set_smem(size_t smem);
+cudaError_t bnlp_coop256_launch(bool timers, int ctas, size_t smem, cudaStream_t stream, void *M, void *A, void *CB);
+int bnlp_coop256_max_ctas_per_sm(size_t smem);
+
 static thread_local std::string g_err;
 static void set_err(const std::string &s) { g_err = s; }
 extern "C" const char *bnlp_last_error(void) { return g_err.c_str(); }
@@ -111,6 +116,7 @@ struct bnlp_engine {
   int h_in_smem = 1;
   size_t smem_bytes = 0;
   bool coop_ok = false;
+  bool coop256 = false;   // small model: 256-thread CTAs, two per SM
   size_t coop_smem_bytes = 0;
   int nqpad = 0, ldd = 0;
   size_t ws_doubles = 0;
@@ -181,7 +187,7 @@ static size_t ipm_smem_doubles(int n, int m, int R, int E, int h_in_smem) {
   const int npad = (N + 2 + 3) & ~3;
   size_t d = 5 * IPM_MAXE + IPM_MAXE * IPM_MAXE;
   if (h_in_smem) d += (size_t)(((N + 2 + E) * (N + 3 + E) / 2) + 1) & ~(size_t)1;
-  d += (size_t)(IPM_NW + 1) * npad;
+  d += (size_t)(IPM_KC + 1) * npad;
   d += (size_t)7 * npad;
   const int Rp = (R + 1) & ~1, Kp = (m + 2) & ~1;
   d += (size_t)10 * Rp + (size_t)8 * Kp + (size_t)IPM_NW * 12;
@@ -194,7 +200,7 @@ static size_t ipm_smem_doubles_coop(int n, int m, int R) {
   const int npad = (N + 2 + 3) & ~3;
   const int lds = ((N + 2 + 7) & ~7) + 4;
   size_t d = (size_t)(((N + 2) * (N + 3) / 2) + 1) & ~(size_t)1;
-  d += (size_t)(IPM_NW + 1) * lds;
+  d += (size_t)(IPM_KC + 1) * lds;
   d += (size_t)7 * npad;
   const int Rp = (R + 1) & ~1, Kp = (m + 2) & ~1;
   d += (size_t)10 * Rp + (size_t)6 * Kp + (size_t)IPM_NW * 12;
@@ -362,11 +368,14 @@ extern "C" bnlp_engine *bnlp_engine_create(const bnlp_problem *prob, const int *
       int coopAttr = 0;
       cudaDeviceGetAttribute(&coopAttr, cudaDevAttrCooperativeLaunch, D.id);
       E->coop_ok = E->ipm_supported && coopAttr && n <= 256 && E->nq > 0 && E->E == 0 && M.terms.empty() && E->coop_smem_bytes + 1024 <= D.smem_optin &&
-                   (size_t)COOP_RB * (E->nqpad + 4) <= (size_t)(IPM_NW + 1) * lds &&
-                   (size_t)COOP_RB * E->ldd <= (size_t)(IPM_NW + 1) * lds + (size_t)(n + 3) * (n + 4) / 2 &&   // U-pass operands live in H + staging
+                   (size_t)COOP_RB * (E->nqpad + 4) <= (size_t)(IPM_KC + 1) * lds &&
+                   (size_t)COOP_RB * E->ldd <= (size_t)(IPM_KC + 1) * lds + (size_t)(n + 3) * (n + 4) / 2 &&   // U-pass operands live in H + staging
                    !getenv("BNLP_NO_COOP");
     }
     // (the attribute is per kernel, not per engine: several engines with different needs may be alive, so opt in to the maximum)
+    if (d == 0 && E->coop_ok && n + 3 <= 128 && !getenv("BNLP_NO_COOP256") && bnlp_coop256_set_smem(D.smem_optin - 1024) == cudaSuccess &&
+        bnlp_coop256_max_ctas_per_sm(E->coop_smem_bytes) >= 2)
+      E->coop256 = true;
     if (E->coop_ok && ipm_coop_set_smem(D.smem_optin - 1024) != cudaSuccess) {
       E->coop_ok = false;
       cudaGetLastError();
@@ -432,6 +441,10 @@ static int launch_ipm(bnlp_engine *E, Device &D, int B, const double *dXL, const
   if (B <= 0) return 0;
   int ctas = E->opt.ctas_per_device > 0 ? E->opt.ctas_per_device : D.sms;
   if (!E->coop_ok) ctas = std::min(ctas, B);   // the cooperative kernel keeps every SM for its shared passes
+  // small models: two 256-thread CTAs per SM interleave two children's latency chains (+50 % at C2) — worth it only when
+  // there are children for all of them; a strong-branching batch of one node keeps the 512-thread CTAs
+  const bool use256 = E->coop256 && E->opt.ctas_per_device <= 0 && B >= 2 * D.sms;
+  if (use256) ctas = 2 * D.sms;
   if (D.ws.reserve((size_t)ctas * E->ws_doubles)) { set_err("workspace allocation failed"); return -1; }
   CK(cudaMemsetAsync(D.queue.p, 0, sizeof(int), stream));
   CK(cudaMemsetAsync(D.stats.p, 0, 12 * sizeof(long long), stream));
@@ -449,7 +462,8 @@ static int launch_ipm(bnlp_engine *E, Device &D, int B, const double *dXL, const
         D.cidle.reserve(2)) { set_err("cooperative buffers: allocation failed"); return -1; }
     CK(cudaMemsetAsync(D.cidle.p, 0, 2 * sizeof(int), stream));
     cb.xw = D.cxw.p; cb.Wbuf = D.cW.p; cb.xd = D.cxd.p; cb.idle_cnt = D.cidle.p; cb.nqpad = E->nqpad; cb.ldd = E->ldd;
-    CK(ipm_coop_launch(a.phase_cycles != nullptr, ctas, E->coop_smem_bytes, stream, D.dm, a, cb));
+    if (use256) CK(bnlp_coop256_launch(a.phase_cycles != nullptr, ctas, E->coop_smem_bytes, stream, &D.dm, &a, &cb));
+    else CK(ipm_coop_launch(a.phase_cycles != nullptr, ctas, E->coop_smem_bytes, stream, D.dm, a, cb));
   } else CK(ipm_general_launch(E->M.n > 256, ctas, E->smem_bytes, stream, D.dm, a));
   E->launches++;
   CK(cudaGetLastError());

@@ -21,7 +21,10 @@
 
 namespace bnlp {
 
-constexpr int IPM_NT = 512;           // threads per CTA
+#ifndef BNLP_NT
+#define BNLP_NT 512
+#endif
+constexpr int IPM_NT = BNLP_NT;       // threads per CTA (512; the cooperative kernel is also built with 256 for two CTAs per SM)
 constexpr int IPM_NW = IPM_NT / 32;   // warps per CTA
 constexpr int IPM_KC = 16;            // rank of one staged SYRK / trailing update
 constexpr int IPM_NB = 8;             // Cholesky panel width
@@ -109,7 +112,7 @@ __device__ __forceinline__ double ld_stream_v(const double *p) {
 template <int NS, int NM>
 __device__ __forceinline__ void block_reduce(double *v, double *red) {
   constexpr int K = NS + NM;
-  static_assert(K * IPM_NW <= IPM_NT && IPM_NW == 16, "stage 2 uses one thread per (value, warp) pair");
+  static_assert(K * IPM_NW <= IPM_NT && (IPM_NW == 16 || IPM_NW == 8), "stage 2 uses one thread per (value, warp) pair");
   __shared__ double red_out[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) {
@@ -126,10 +129,10 @@ __device__ __forceinline__ void block_reduce(double *v, double *red) {
   }
   __syncthreads();
   if (threadIdx.x < ((K * IPM_NW + 31) & ~31)) {      // whole warps take part in the shuffles
-    const int k = threadIdx.x >> 4, q = threadIdx.x & 15;
+    const int k = threadIdx.x / IPM_NW, q = threadIdx.x % IPM_NW;
     double a = (k < K) ? red[q * K + k] : 0.0;
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) {
+    for (int o = IPM_NW / 2; o > 0; o >>= 1) {
       const double t = __shfl_xor_sync(0xffffffffu, a, o);
       a = (k < NS) ? a + t : fmax(a, t);
     }
@@ -401,7 +404,7 @@ enum { F_FIXED = 1, F_HASL = 2, F_HASU = 4 };
   } while (0)
 
 template <int MAXC>
-__global__ void __launch_bounds__(IPM_NT, 1) ipm_kernel(DevModel M, IpmArgs A) {
+__global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, IpmArgs A) {
   extern __shared__ __align__(16) double smem[];
   const int n = M.n, m = M.m, N = M.N, R = M.R, npad = M.npad;
   const int tid = threadIdx.x;
@@ -417,7 +420,7 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_kernel(DevModel M, IpmArgs A) {
   const int NTm = M.n_terms;
   double *tgl = uq + (size_t)(m + 1) * n;          // per term: value, local gradient (TV), packed local Hessian (TH)
   if (A.h_in_smem) { H = sp; sp += (Haug + 1) & ~1; } else { H = tgl + (size_t)NTm * TREC; }
-  double *stage = sp; sp += (IPM_NW + 1) * npad;
+  double *stage = sp; sp += (IPM_KC + 1) * npad;
   double *x = sp; sp += npad;
   double *zL = sp; sp += npad;
   double *zU = sp; sp += npad;

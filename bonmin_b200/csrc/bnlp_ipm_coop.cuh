@@ -226,7 +226,7 @@ __device__ __forceinline__ void backsolve_inv(double *H, int N, double *xs /* 16
   const int tid = threadIdx.x;
   const int nblk = (N + 7) >> 3;
   double *b0 = H + tri(N), *b1 = H + tri(N + 1);
-  const int half = tid >> 8, kk = tid & 255;   // threads 0..255 serve rhs 0, 256..511 rhs 1  (N <= 256)
+  const int half = tid / (IPM_NT / 2), kk = tid % (IPM_NT / 2);   // one half of the CTA per right-hand side (N <= IPM_NT / 2)
   double *bh = half ? b1 : b0;
   for (int blk = nblk - 1; blk >= 0; --blk) {
     const int i0 = blk << 3, nb = min(8, N - i0);
@@ -275,7 +275,7 @@ struct CoopScalars {
 enum { CS_NEED_CHILD = 0, CS_INIT = 1, CS_ITER = 2, CS_IDLE = 3, CS_SKIP = 4, CS_FINISH = 5 };
 
 template <bool TIMERS>
-__global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs A, CoopBufs CB) {
+__global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel M, IpmArgs A, CoopBufs CB) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(16) double smem[];
   const int n = M.n, m = M.m, N = M.N, R = M.R, npad = M.npad;
@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
   const int Haug = tri(N + 2);
   double *const H = smem;
   double *const stage = H + ((Haug + 1) & ~1);
-  double *const x = stage + (IPM_NW + 1) * lds;      // 7 vectors of npad: x zL zU Lr Ur dx Sx
+  double *const x = stage + (IPM_KC + 1) * lds;      // 7 vectors of npad: x zL zU Lr Ur dx Sx
   const int Rp = (R + 1) & ~1, Kp = (m + 2) & ~1;
   double *const s = x + 7 * npad;                    // 10 vectors of Rp: s v rc ds dv Ss bb fsc jd0 jd1
   double *const val = s + 10 * Rp;                   // val gd0 gd1 du (Kp each), wq (2 Kp)
@@ -621,8 +621,8 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
     };
     for (int r0 = 0; r0 < R; r0 += IPM_KC) {
       const int kc = min(IPM_KC, R - r0), kc4 = (kc + 3) & ~3;
-      {
-        const int c = wid, r = r0 + c;   // IPM_KC == IPM_NW: one row per warp
+      for (int c = wid; c < kc4; c += IPM_NW) {   // one staged row per warp (two with the 8-warp build)
+        const int r = r0 + c;
         if (c < kc) prefetch_row(r);       // eight loads in flight per lane; a prefetch one chunk ahead only spilled
         if (c < kc) {
           const double sq = sqrt(Ss[r]), f = sq * fsc[r];
@@ -635,7 +635,7 @@ __global__ void __launch_bounds__(IPM_NT, 1) ipm_coop_kernel(DevModel M, IpmArgs
               stage[c * lds + j] = vv;
             }
           }
-        } else if (c < kc4) {
+        } else {
           for (int j = lane; j < lds; j += 32) stage[c * lds + j] = 0.0;
         }
       }
