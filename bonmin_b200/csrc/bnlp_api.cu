@@ -92,6 +92,8 @@ struct Device {
   DBuf<double> dXL, dXU, dX0, dOBJ, dX, dG, dD, ws, cxw, cW, cxd;
   DBuf<int> cidle;
   DBuf<int> dST, dIT, queue;
+  DBuf<double> dPXL, dPXU, dCB;   // bnlp_solve_children: parent bounds and the one changed bound of each child
+  DBuf<int> dCP, dCC, dCW;
   DBuf<long long> stats;
   // eval buffers
   DBuf<double> eX, eLAM, eF, eG, eGF, eJ, eH, eX2, eDU, eU, oVal, oLB, oUB;
@@ -421,10 +423,10 @@ extern "C" void bnlp_engine_free(bnlp_engine *E) {
     cudaSetDevice(D.id);
     for (auto *b : {&D.c, &D.A, &D.Qp, &D.Qf, &D.row_sgn, &D.row_bnd, &D.gl, &D.gu, &D.xl, &D.xu, &D.e_dbl, &D.dXL, &D.dXU,
                     &D.dX0, &D.dOBJ, &D.dX, &D.dG, &D.dD, &D.ws, &D.cxw, &D.cW, &D.cxd, &D.eq_bnd, &D.eX, &D.eLAM, &D.eF, &D.eG, &D.eGF, &D.eJ, &D.eH,
-                    &D.eX2, &D.eDU, &D.eU, &D.oVal, &D.oLB, &D.oUB})
+                    &D.eX2, &D.eDU, &D.eU, &D.oVal, &D.oLB, &D.oUB, &D.dPXL, &D.dPXU, &D.dCB})
       b->release();
     for (auto *b : {&D.qidx, &D.row_fn, &D.fn_row_up, &D.fn_row_lo, &D.e_int, &D.dST, &D.dIT, &D.queue, &D.cidle, &D.eq_fn, &D.fn_eq, &D.oRS, &D.oCI,
-                    &D.oSR})
+                    &D.oSR, &D.dCP, &D.dCC, &D.dCW})
       b->release();
     D.stats.release();
     if (D.stream) cudaStreamDestroy(D.stream);
@@ -479,35 +481,11 @@ extern "C" int bnlp_solve_batch_device(bnlp_engine *E, int dev_index, int B, con
   return launch_ipm(E, D, B, dXL, dXU, dX0, x0_per_child, dOBJ, dSTATUS, dITERS, dX, dG, dDUALS, (cudaStream_t)stream);
 }
 
-extern "C" int bnlp_solve_batch(bnlp_engine *E, int B, const double *XL, const double *XU, const double *X0,
-                                int x0_per_child, double *OBJ, int *STATUS, int *ITERS, double *X, double *G,
-                                double *DUALS) {
-  if (!E) { set_err("null engine"); return -1; }
-  if (B <= 0) return 0;
+// Results of a launched batch back to the host, then wait and collect statistics (shared by bnlp_solve_batch and
+// bnlp_solve_children).
+static int collect_batch(bnlp_engine *E, int B, int per, double *OBJ, int *STATUS, int *ITERS, double *X, double *G, double *DUALS) {
   const int n = E->M.n, m = E->M.m, nd = (int)E->devs.size();
-  const int per = (B + nd - 1) / nd;  // contiguous child shards, one per device (SURVEY §8e)
-  // phase 1: enqueue copies + kernels on every device
-  for (int d = 0; d < nd; ++d) {
-    const int b0 = d * per, nb = std::min(per, B - b0);
-    if (nb <= 0) break;
-    Device &D = E->devs[d];
-    CK(cudaSetDevice(D.id));
-    if (D.dXL.reserve((size_t)nb * n) || D.dXU.reserve((size_t)nb * n) || D.dX0.reserve((size_t)(x0_per_child ? nb : 1) * n) ||
-        D.dOBJ.reserve(nb) || D.dST.reserve(nb) || D.dIT.reserve(nb) || D.dX.reserve((size_t)nb * n) ||
-        D.dG.reserve((size_t)nb * std::max(m, 1)) || D.dD.reserve((size_t)nb * (2 * n + m))) {
-      set_err("device allocation failed");
-      return -1;
-    }
-    CK(cudaEventRecord(D.ev0, D.stream));
-    CK(cudaMemcpyAsync(D.dXL.p, XL + (size_t)b0 * n, (size_t)nb * n * 8, cudaMemcpyHostToDevice, D.stream));
-    CK(cudaMemcpyAsync(D.dXU.p, XU + (size_t)b0 * n, (size_t)nb * n * 8, cudaMemcpyHostToDevice, D.stream));
-    CK(cudaMemcpyAsync(D.dX0.p, X0 + (x0_per_child ? (size_t)b0 * n : 0), (size_t)(x0_per_child ? nb : 1) * n * 8,
-                       cudaMemcpyHostToDevice, D.stream));
-    int rc = launch_ipm(E, D, nb, D.dXL.p, D.dXU.p, D.dX0.p, x0_per_child, D.dOBJ.p, D.dST.p, D.dIT.p,
-                        X ? D.dX.p : nullptr, G ? D.dG.p : nullptr, DUALS ? D.dD.p : nullptr, D.stream);
-    if (rc) return rc;
-  }
-  // phase 1b: results back.  (Separate loop: a device-to-host copy into pageable memory blocks the host until the
+  // results back.  (Separate loop: a device-to-host copy into pageable memory blocks the host until the
   // device's kernel has finished, so issuing it inside the launch loop would run the devices one after the other.)
   for (int d = 0; d < nd; ++d) {
     const int b0 = d * per, nb = std::min(per, B - b0);
@@ -547,6 +525,109 @@ extern "C" int bnlp_solve_batch(bnlp_engine *E, int B, const double *XL, const d
     E->last_ms = std::max(E->last_ms, (double)ms);
   }
   return 0;
+}
+
+
+
+// child b = the bounds of parent cp[b] with one bound of column cc[b] replaced (cw[b] == 0: upper bound, the down branch;
+// 1: lower bound, the up branch); X0 rows are copied per parent when x0_per_parent
+__global__ void expand_children_kernel(int B, int n, const double *__restrict__ pXL, const double *__restrict__ pXU,
+                                       const int *__restrict__ cp, const int *__restrict__ cc, const int *__restrict__ cw,
+                                       const double *__restrict__ cb, double *__restrict__ XL, double *__restrict__ XU,
+                                       const double *__restrict__ pX0, double *__restrict__ X0) {
+  const size_t total = (size_t)B * n;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int b = (int)(e / n), j = (int)(e % n);
+    const size_t src = (size_t)cp[b] * n + j;
+    const bool hit = (j == cc[b]);
+    XL[e] = (hit && cw[b] == 1) ? cb[b] : pXL[src];
+    XU[e] = (hit && cw[b] == 0) ? cb[b] : pXU[src];
+    if (X0) X0[e] = pX0[src];
+  }
+}
+
+extern "C" int bnlp_solve_children(bnlp_engine *E, int P, const double *parent_XL, const double *parent_XU, int B,
+                                   const int *child_parent, const int *child_col, const int *child_way,
+                                   const double *child_bound, const double *X0, int x0_per_parent, double *OBJ, int *STATUS,
+                                   int *ITERS, double *X, double *G, double *DUALS) {
+  if (!E) { set_err("null engine"); return -1; }
+  if (B <= 0) return 0;
+  if (!E->ipm_supported) { set_err("bnlp_solve_children: " + E->ipm_unsupported_why); return -2; }
+  const int n = E->M.n, m = E->M.m, nd = (int)E->devs.size();
+  for (int b = 0; b < B; ++b)
+    if (child_parent[b] < 0 || child_parent[b] >= P || child_col[b] < 0 || child_col[b] >= n || (child_way[b] | 1) != 1) {
+      set_err("bnlp_solve_children: child " + std::to_string(b) + " out of range");
+      return -1;
+    }
+  const int per = (B + nd - 1) / nd;
+  for (int d = 0; d < nd; ++d) {
+    const int b0 = d * per, nb = std::min(per, B - b0);
+    if (nb <= 0) break;
+    Device &D = E->devs[d];
+    CK(cudaSetDevice(D.id));
+    if (D.dXL.reserve((size_t)nb * n) || D.dXU.reserve((size_t)nb * n) || D.dX0.reserve((size_t)(x0_per_parent ? nb : 1) * n) ||
+        D.dOBJ.reserve(nb) || D.dST.reserve(nb) || D.dIT.reserve(nb) || D.dX.reserve((size_t)nb * n) ||
+        D.dG.reserve((size_t)nb * std::max(m, 1)) || D.dD.reserve((size_t)nb * (2 * n + m)) ||
+        D.dPXL.reserve((size_t)P * n * (x0_per_parent ? 2 : 1)) || D.dPXU.reserve((size_t)P * n) || D.dCB.reserve(nb) ||
+        D.dCP.reserve(nb) || D.dCC.reserve(nb) || D.dCW.reserve(nb)) {
+      set_err("device allocation failed");
+      return -1;
+    }
+    CK(cudaEventRecord(D.ev0, D.stream));
+    CK(cudaMemcpyAsync(D.dPXL.p, parent_XL, (size_t)P * n * 8, cudaMemcpyHostToDevice, D.stream));
+    CK(cudaMemcpyAsync(D.dPXU.p, parent_XU, (size_t)P * n * 8, cudaMemcpyHostToDevice, D.stream));
+    CK(cudaMemcpyAsync(D.dCP.p, child_parent + b0, (size_t)nb * 4, cudaMemcpyHostToDevice, D.stream));
+    CK(cudaMemcpyAsync(D.dCC.p, child_col + b0, (size_t)nb * 4, cudaMemcpyHostToDevice, D.stream));
+    CK(cudaMemcpyAsync(D.dCW.p, child_way + b0, (size_t)nb * 4, cudaMemcpyHostToDevice, D.stream));
+    CK(cudaMemcpyAsync(D.dCB.p, child_bound + b0, (size_t)nb * 8, cudaMemcpyHostToDevice, D.stream));
+    double *pX0 = nullptr;
+    if (x0_per_parent) {   // parent start points ride behind the parent lower bounds
+      pX0 = D.dPXL.p + (size_t)P * n;
+      CK(cudaMemcpyAsync(pX0, X0, (size_t)P * n * 8, cudaMemcpyHostToDevice, D.stream));
+    } else {
+      CK(cudaMemcpyAsync(D.dX0.p, X0, (size_t)n * 8, cudaMemcpyHostToDevice, D.stream));
+    }
+    const int blocks = (int)std::min<size_t>(((size_t)nb * n + 255) / 256, (size_t)D.sms * 8);
+    expand_children_kernel<<<blocks, 256, 0, D.stream>>>(nb, n, D.dPXL.p, D.dPXU.p, D.dCP.p, D.dCC.p, D.dCW.p, D.dCB.p, D.dXL.p,
+                                                         D.dXU.p, pX0, x0_per_parent ? D.dX0.p : nullptr);
+    CK(cudaGetLastError());
+    E->launches++;
+    int rc = launch_ipm(E, D, nb, D.dXL.p, D.dXU.p, D.dX0.p, x0_per_parent, D.dOBJ.p, D.dST.p, D.dIT.p,
+                        X ? D.dX.p : nullptr, G ? D.dG.p : nullptr, DUALS ? D.dD.p : nullptr, D.stream);
+    if (rc) return rc;
+  }
+  return collect_batch(E, B, per, OBJ, STATUS, ITERS, X, G, DUALS);
+}
+
+extern "C" int bnlp_solve_batch(bnlp_engine *E, int B, const double *XL, const double *XU, const double *X0,
+                                int x0_per_child, double *OBJ, int *STATUS, int *ITERS, double *X, double *G,
+                                double *DUALS) {
+  if (!E) { set_err("null engine"); return -1; }
+  if (B <= 0) return 0;
+  const int n = E->M.n, m = E->M.m, nd = (int)E->devs.size();
+  const int per = (B + nd - 1) / nd;  // contiguous child shards, one per device (SURVEY §8e)
+  // phase 1: enqueue copies + kernels on every device
+  for (int d = 0; d < nd; ++d) {
+    const int b0 = d * per, nb = std::min(per, B - b0);
+    if (nb <= 0) break;
+    Device &D = E->devs[d];
+    CK(cudaSetDevice(D.id));
+    if (D.dXL.reserve((size_t)nb * n) || D.dXU.reserve((size_t)nb * n) || D.dX0.reserve((size_t)(x0_per_child ? nb : 1) * n) ||
+        D.dOBJ.reserve(nb) || D.dST.reserve(nb) || D.dIT.reserve(nb) || D.dX.reserve((size_t)nb * n) ||
+        D.dG.reserve((size_t)nb * std::max(m, 1)) || D.dD.reserve((size_t)nb * (2 * n + m))) {
+      set_err("device allocation failed");
+      return -1;
+    }
+    CK(cudaEventRecord(D.ev0, D.stream));
+    CK(cudaMemcpyAsync(D.dXL.p, XL + (size_t)b0 * n, (size_t)nb * n * 8, cudaMemcpyHostToDevice, D.stream));
+    CK(cudaMemcpyAsync(D.dXU.p, XU + (size_t)b0 * n, (size_t)nb * n * 8, cudaMemcpyHostToDevice, D.stream));
+    CK(cudaMemcpyAsync(D.dX0.p, X0 + (x0_per_child ? (size_t)b0 * n : 0), (size_t)(x0_per_child ? nb : 1) * n * 8,
+                       cudaMemcpyHostToDevice, D.stream));
+    int rc = launch_ipm(E, D, nb, D.dXL.p, D.dXU.p, D.dX0.p, x0_per_child, D.dOBJ.p, D.dST.p, D.dIT.p,
+                        X ? D.dX.p : nullptr, G ? D.dG.p : nullptr, DUALS ? D.dD.p : nullptr, D.stream);
+    if (rc) return rc;
+  }
+  return collect_batch(E, B, per, OBJ, STATUS, ITERS, X, G, DUALS);
 }
 
 extern "C" int bnlp_engine_stats(const bnlp_engine *E, long long *iterations, long long *factorisations, double *device_ms) {

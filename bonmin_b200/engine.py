@@ -56,7 +56,7 @@ EXPORTS = ["bnlp_last_error", "bnlp_problem_from_nl", "bnlp_problem_from_tape", 
            "bnlp_engine_launches", "bnlp_measure_fp64_peak", "bnlp_bb_run_cb", "bnlp_bb_run_cb2", "bnlp_bb_run_engine", "bnlp_dive_run_cb", "bnlp_dive_run_engine", "bnlp_violation_batch",
            "bnlp_benders_batch", "bnlp_branching_tqp", "bnlp_tqp_solve_batch",
            "bnlp_extract_linear_relaxation", "bnlp_constraint_oa_batch", "bnlp_engine_sizes",
-           "bnlp_resolve_cb", "bnlp_resolve_engine", "bnlp_problem_fp"]
+           "bnlp_resolve_cb", "bnlp_resolve_engine", "bnlp_problem_fp", "bnlp_solve_children", "bnlp_bb_run_cb3"]
 
 
 def lib():
@@ -80,6 +80,7 @@ def lib():
         L.bnlp_engine_free.argtypes = [c_void]
         L.bnlp_eval_batch.argtypes = [c_void, c_int, c_void, c_void, c_dbl, c_void, c_void, c_void, c_void, c_void]
         L.bnlp_solve_batch.argtypes = [c_void, c_int, c_void, c_void, c_void, c_int] + [c_void] * 6
+        L.bnlp_solve_children.argtypes = [c_void, c_int, c_void, c_void, c_int] + [c_void] * 5 + [c_int] + [c_void] * 6
         L.bnlp_solve_batch_device.argtypes = [c_void, c_int, c_int, c_void, c_void, c_void, c_int] + [c_void] * 7
         L.bnlp_oa_capacity.argtypes = [c_void, c_int, P_int, ctypes.POINTER(ctypes.c_size_t)]
         L.bnlp_oa_batch.argtypes = [c_void, c_int, c_void, c_void, c_void, c_void, c_void, c_dbl, c_int,
@@ -255,6 +256,32 @@ class Engine:
         D = np.zeros((B, 2 * n + m)) if want_duals else None
         self._ck(lib().bnlp_solve_batch(self.h, B, _vp(XL), _vp(XU), _vp(X0), per_child, _vp(OBJ), _vp(ST), _vp(IT),
                                         _vp(X), _vp(G), _vp(D)))
+        return dict(obj=OBJ, status=ST, iters=IT, x=X, g=G, duals=D)
+
+    def solve_children(self, parent_XL, parent_XU, child_parent, child_col, child_way, child_bound, X0, want_x=True,
+                       want_g=False, want_duals=False):
+        """The strong-branching form of solve_batch (bnlp_solve_children): child b = parent child_parent[b] with the upper
+        (way 0) or lower (way 1) bound of column child_col[b] replaced by child_bound[b]; bound vectors are expanded on
+        the device.  X0: n (shared) or P x n (per parent)."""
+        n, m = self.n, self.m
+        PXL = _d(np.atleast_2d(parent_XL))
+        PXU = _d(np.atleast_2d(parent_XU))
+        P = PXL.shape[0]
+        cp = np.ascontiguousarray(child_parent, np.int32)
+        cc = np.ascontiguousarray(child_col, np.int32)
+        cw = np.ascontiguousarray(child_way, np.int32)
+        cb = _d(child_bound)
+        B = len(cp)
+        X0 = _d(X0)
+        per_parent = int(X0.ndim == 2)
+        OBJ = np.zeros(B)
+        ST = np.zeros(B, np.int32)
+        IT = np.zeros(B, np.int32)
+        X = np.zeros((B, n)) if want_x else None
+        G = np.zeros((B, m)) if want_g else None
+        D = np.zeros((B, 2 * n + m)) if want_duals else None
+        self._ck(lib().bnlp_solve_children(self.h, P, _vp(PXL), _vp(PXU), B, _vp(cp), _vp(cc), _vp(cw), _vp(cb), _vp(X0),
+                                           per_parent, _vp(OBJ), _vp(ST), _vp(IT), _vp(X), _vp(G), _vp(D)))
         return dict(obj=OBJ, status=ST, iters=IT, x=X, g=G, duals=D)
 
     def solve_batch_device(self, dXL, dXU, dX0, dOBJ, dST, dIT, dX=None, dG=None, dD=None, x0_per_child=False,

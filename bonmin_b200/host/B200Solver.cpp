@@ -4,6 +4,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <queue>
 
 namespace Bonmin {
@@ -31,21 +32,58 @@ TNLPSolver::ReturnStatus B200Solver::OptimizeTNLP(TMINLP2TNLP &t) {
   return (ReturnStatus)st;
 }
 
+std::shared_ptr<std::vector<double>> B200Solver::x_block(size_t cnt) {
+  // the previous batch's block is reused once nobody refers to it any more
+  if (!x_pool_ || x_pool_.use_count() > 1 || x_pool_->size() < cnt) x_pool_ = std::make_shared<std::vector<double>>(cnt);
+  return x_pool_;
+}
+
+int B200Solver::unpack(int rc, int B, int n, std::vector<Child> &out) {
+  out.resize(B);
+  for (int b = 0; b < B; ++b) {
+    out[b].obj = obj_buf_[b];
+    out[b].status = rc ? exception : (ReturnStatus)st_buf_[b];
+    out[b].iters = it_buf_[b];
+    out[b].block = x_pool_;
+    out[b].off = (size_t)b * n;
+    total_batch_iterations_ += it_buf_[b];
+  }
+  return rc;
+}
+
 int B200Solver::OptimizeBatch(const TMINLP2TNLP &p, const std::vector<double> &XL, const std::vector<double> &XU, int B,
                               std::vector<Child> &out) {
   const int n = p.n;
-  std::vector<double> OBJ(B), X((size_t)B * n);
-  std::vector<int> ST(B), IT(B);
-  const int rc = solve_(B, XL.data(), XU.data(), p.x_init.data(), OBJ.data(), ST.data(), IT.data(), X.data(), nullptr, nullptr);
-  out.resize(B);
-  for (int b = 0; b < B; ++b) {
-    out[b].obj = OBJ[b];
-    out[b].status = rc ? exception : (ReturnStatus)ST[b];
-    out[b].iters = IT[b];
-    out[b].x.assign(X.begin() + (size_t)b * n, X.begin() + (size_t)(b + 1) * n);
-    total_batch_iterations_ += IT[b];
+  if ((int)obj_buf_.size() < B) { obj_buf_.resize(B); st_buf_.resize(B); it_buf_.resize(B); }
+  double *X = x_block((size_t)B * n)->data();
+  const double ts0 = now_s();
+  const int rc = solve_(B, XL.data(), XU.data(), p.x_init.data(), obj_buf_.data(), st_buf_.data(), it_buf_.data(), X, nullptr, nullptr);
+  solve_seconds_ += now_s() - ts0;
+  return unpack(rc, B, n, out);
+}
+
+int B200Solver::OptimizeChildren(const TMINLP2TNLP &p, int P, const std::vector<double> &PXL, const std::vector<double> &PXU,
+                                 const std::vector<int> &cp, const std::vector<int> &cc, const std::vector<int> &cw,
+                                 const std::vector<double> &cb, std::vector<Child> &out) {
+  const int n = p.n, B = (int)cp.size();
+  if ((int)obj_buf_.size() < B) { obj_buf_.resize(B); st_buf_.resize(B); it_buf_.resize(B); }
+  double *X = x_block((size_t)B * n)->data();
+  int rc;
+  const double ts0 = now_s();
+  if (children_) {
+    rc = children_(P, PXL.data(), PXU.data(), B, cp.data(), cc.data(), cw.data(), cb.data(), p.x_init.data(), obj_buf_.data(),
+                   st_buf_.data(), it_buf_.data(), X);
+  } else {
+    if (xl_buf_.size() < (size_t)B * n) { xl_buf_.resize((size_t)B * n); xu_buf_.resize((size_t)B * n); }
+    for (int b = 0; b < B; ++b) {
+      std::copy(&PXL[(size_t)cp[b] * n], &PXL[(size_t)cp[b] * n] + n, &xl_buf_[(size_t)b * n]);
+      std::copy(&PXU[(size_t)cp[b] * n], &PXU[(size_t)cp[b] * n] + n, &xu_buf_[(size_t)b * n]);
+      (cw[b] == 0 ? xu_buf_ : xl_buf_)[(size_t)b * n + cc[b]] = cb[b];
+    }
+    rc = solve_(B, xl_buf_.data(), xu_buf_.data(), p.x_init.data(), obj_buf_.data(), st_buf_.data(), it_buf_.data(), X, nullptr, nullptr);
   }
-  return rc;
+  solve_seconds_ += now_s() - ts0;
+  return unpack(rc, B, n, out);
 }
 
 void BatchedStrongBranchingSolver::markHotStart(OsiTMINLPInterface *si) {
@@ -60,27 +98,33 @@ void BatchedStrongBranchingSolver::markHotStart(OsiTMINLPInterface *si) {
 }
 
 void BatchedStrongBranchingSolver::prefetchMany(OsiTMINLPInterface *si, const std::vector<NodeRequest> &reqs) {
-  const int n = si->getNumCols();
+  const int n = si->getNumCols(), P = (int)reqs.size();
   size_t total = 0;
   for (auto &r : reqs) total += 2 * r.cols.size();
-  std::vector<double> XL(total * n), XU(total * n);
+  std::vector<double> PXL((size_t)P * n), PXU((size_t)P * n), cb(total);
+  std::vector<int> cp(total), cc(total), cw(total);
   size_t row = 0;
-  for (auto &r : reqs)
+  for (int q = 0; q < P; ++q) {
+    const NodeRequest &r = reqs[q];
+    std::copy(r.xl.begin(), r.xl.end(), &PXL[(size_t)q * n]);
+    std::copy(r.xu.begin(), r.xu.end(), &PXU[(size_t)q * n]);
     for (size_t i = 0; i < r.cols.size(); ++i)
       for (int w = 0; w < 2; ++w, ++row) {
-        std::copy(r.xl.begin(), r.xl.end(), &XL[row * n]);
-        std::copy(r.xu.begin(), r.xu.end(), &XU[row * n]);
-        if (w == 0) XU[row * n + r.cols[i]] = r.down_ub[i]; else XL[row * n + r.cols[i]] = r.up_lb[i];
+        cp[row] = q; cc[row] = r.cols[i]; cw[row] = w;
+        cb[row] = (w == 0) ? r.down_ub[i] : r.up_lb[i];
       }
+  }
+  multi_.clear();   // drop the references to the previous round's result block so that it can be reused
+  cache_.clear();
   std::vector<B200Solver::Child> res;
-  if (total) app_->OptimizeBatch(*si->problem(), XL, XU, (int)total, res);
+  if (total) app_->OptimizeChildren(*si->problem(), P, PXL, PXU, cp, cc, cw, cb, res);
   multi_.assign(reqs.size(), {});
   multi_bounds_.clear();
   row = 0;
   for (size_t q = 0; q < reqs.size(); ++q) {
     multi_bounds_.push_back({reqs[q].xl, reqs[q].xu});
     for (size_t i = 0; i < reqs[q].cols.size(); ++i)
-      for (int w = 0; w < 2; ++w, ++row) multi_[q][{reqs[q].cols[i], w}] = std::move(res[row]);
+      for (int w = 0; w < 2; ++w, ++row) multi_[q].emplace_hint(multi_[q].end(), std::make_pair(reqs[q].cols[i], w), std::move(res[row]));
   }
 }
 
@@ -104,15 +148,16 @@ void BatchedStrongBranchingSolver::prefetch(OsiTMINLPInterface *si, const std::v
   std::vector<B200Solver::Child> res;
   if (qp_ && (int)xsol0_.size() == n && (int)duals0_.size() == 2 * n + si->problem()->m) {
     const int B = 2 * K;
-    std::vector<double> OBJ(B), X((size_t)B * n);
+    std::vector<double> OBJ(B);
+    auto blk = std::make_shared<std::vector<double>>((size_t)B * n);
     std::vector<int> ST(B), IT(B);
-    const int rc = qp_(xsol0_.data(), duals0_.data(), B, XL.data(), XU.data(), OBJ.data(), ST.data(), IT.data(), X.data());
+    const int rc = qp_(xsol0_.data(), duals0_.data(), B, XL.data(), XU.data(), OBJ.data(), ST.data(), IT.data(), blk->data());
     res.resize(B);
     for (int b = 0; b < B; ++b) {
       res[b].obj = OBJ[b];
       res[b].status = rc ? TNLPSolver::exception : (TNLPSolver::ReturnStatus)ST[b];
       res[b].iters = IT[b];
-      res[b].x.assign(X.begin() + (size_t)b * n, X.begin() + (size_t)(b + 1) * n);
+      res[b].block = blk; res[b].off = (size_t)b * n;
       qp_iterations_ += IT[b];
     }
   } else {
@@ -145,7 +190,7 @@ TNLPSolver::ReturnStatus BatchedStrongBranchingSolver::solveFromHotStart(OsiTMIN
   }
   hits_++;
   si->problem()->set_obj_value(c->obj);
-  if (c->status == TNLPSolver::solvedOptimal || c->status == TNLPSolver::solvedOptimalTol) si->problem()->Set_x_sol(n, c->x.data());
+  if (c->status == TNLPSolver::solvedOptimal || c->status == TNLPSolver::solvedOptimalTol) si->problem()->Set_x_sol(n, c->x());
   si->problem()->return_status = c->status;
   return c->status;
 }
@@ -224,11 +269,12 @@ struct Node {
 struct Cmp { bool operator()(const Node *a, const Node *b) const { return a->bound > b->bound; } };
 }  // namespace
 
-BbResult bb_run(TMINLP2TNLP &root, BatchSolveFn solve, const BbOptions &opt, TqpSolveFn tqp) {
+BbResult bb_run(TMINLP2TNLP &root, BatchSolveFn solve, const BbOptions &opt, TqpSolveFn tqp, ChildrenSolveFn children) {
   BbResult R;
   const double t0 = now_s();
   const int n = root.n;
   B200Solver app(solve);
+  if (children) app.setChildrenSolver(children);
   OsiTMINLPInterface si(&root, &app);
   BatchedStrongBranchingSolver sb(&app);
   si.SetStrongBrachingSolver(&sb);
@@ -254,6 +300,7 @@ BbResult bb_run(TMINLP2TNLP &root, BatchSolveFn solve, const BbOptions &opt, Tqp
   double cutoff = 1e100;
   const std::vector<double> xl_root = root.x_l, xu_root = root.x_u;
 
+  double t_prefetch = 0;
   if (opt.parallel_nodes > 1 && !qp_mode) {
     // ---- round-based expansion: the P best open nodes per round; their node NLPs are one batch and the strong-
     // branching children of all of them are one batch (independent relaxations sharing tape and start point)
@@ -291,7 +338,7 @@ BbResult bb_run(TMINLP2TNLP &root, BatchSolveFn solve, const BbOptions &opt, Tqp
         R.nlp_solves += (int)need.size();
         for (size_t q = 0; q < need.size(); ++q) {
           Node *nd = batch[need[q]];
-          nd->solved = true; nd->obj = res[q].obj; nd->status = (int)res[q].status; nd->x = res[q].x;
+          nd->solved = true; nd->obj = res[q].obj; nd->status = (int)res[q].status; nd->x.assign(res[q].x(), res[q].x() + n);
         }
       } 
       // 2. fathoming, incumbents, candidate lists
@@ -321,7 +368,9 @@ BbResult bb_run(TMINLP2TNLP &root, BatchSolveFn solve, const BbOptions &opt, Tqp
       }
       if (open.empty()) continue;
       // 3. ONE batch for the strong-branching children of every open node of the round
+      const double tp0 = now_s();
       sb.prefetchMany(&si, reqs);
+      t_prefetch += now_s() - tp0;
       R.sb_batches++;
       for (auto &rq : reqs) R.sb_children += 2 * (int)rq.cols.size();
       // 4. per node: the reference's sequential loop replayed against its cache, scoring, branching
@@ -349,7 +398,7 @@ BbResult bb_run(TMINLP2TNLP &root, BatchSolveFn solve, const BbOptions &opt, Tqp
           Node *ch = new Node{nd->xl, nd->xu, nd->obj, nd->depth + 1};
           if (w == 0) ch->xu[bcol] = std::floor(nd->x[bcol]); else ch->xl[bcol] = std::ceil(nd->x[bcol]);
           const B200Solver::Child *c = fixed_any ? nullptr : sb.lookup(bcol, w == 1);
-          if (c) { ch->solved = true; ch->obj = c->obj; ch->status = (int)c->status; ch->x = c->x;
+          if (c) { ch->solved = true; ch->obj = c->obj; ch->status = (int)c->status; ch->x.assign(c->x(), c->x() + n);
                    if (c->status == 1 || c->status == 2) ch->bound = std::max(nd->obj, c->obj); }
           if (ch->solved && !(ch->status == 1 || ch->status == 2)) { delete ch; continue; }   // pre-solved and infeasible
           heap.push(ch);
@@ -439,7 +488,7 @@ BbResult bb_run(TMINLP2TNLP &root, BatchSolveFn solve, const BbOptions &opt, Tqp
       for (int j = 0; j < n && same; ++j)
         if (j != bcol && (nd->xl[j] != root.x_l[j] || nd->xu[j] != root.x_u[j])) same = false;
       if (same && !res.empty() && !qp_mode) c = sb.lookup(bcol, w == 1);   // QP children are surrogates, never node results
-      if (c) { ch[w]->solved = true; ch[w]->obj = c->obj; ch[w]->status = (int)c->status; ch[w]->x = c->x;
+      if (c) { ch[w]->solved = true; ch[w]->obj = c->obj; ch[w]->status = (int)c->status; ch[w]->x.assign(c->x(), c->x() + n);
                if (c->status == 1 || c->status == 2) ch[w]->bound = std::max(obj, c->obj); }
     }
     // follow the preferred way first, keep the other on the heap (probed-dive flavour, BonDiver.cpp:255-316)
@@ -452,6 +501,9 @@ BbResult bb_run(TMINLP2TNLP &root, BatchSolveFn solve, const BbOptions &opt, Tqp
   if (R.status == 0) { R.status = R.best_obj < 1e99 ? 0 : 1; R.best_bound = R.best_obj; }
   R.ipm_iterations = si.totalIterations() + app.totalBatchIterations() + sb.qpIterations();
   R.seconds = now_s() - t0;
+  if (getenv("BNLP_BB_TIMERS"))
+    fprintf(stderr, "[bb timers] total %.3f s, prefetchMany %.3f s, inside the batch-solve callback %.3f s\n", R.seconds, t_prefetch,
+            app.solveSeconds());
   root.x_l = xl_root; root.x_u = xu_root;
   return R;
 }

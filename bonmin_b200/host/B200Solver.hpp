@@ -12,6 +12,8 @@
 #include <map>
 #include <utility>
 
+#include <memory>
+
 #include "bonmin_shim.hpp"
 
 namespace Bonmin {
@@ -25,6 +27,13 @@ using BatchSolveFn = std::function<int(int B, const double *XL, const double *XU
 using TqpSolveFn = std::function<int(const double *x_sol, const double *duals_sol, int B, const double *XL,
                                      const double *XU, double *OBJ, int *STATUS, int *ITERS, double *X)>;
 
+// The strong-branching form (same meaning as bnlp_solve_children, include/bnlp.h): child b = parent cp[b] of P with one
+// bound of column cc[b] replaced by cb[b] (cw[b] 0: upper bound, 1: lower bound); the bound vectors are expanded by the
+// provider (on the device in the product)
+using ChildrenSolveFn = std::function<int(int P, const double *PXL, const double *PXU, int B, const int *cp, const int *cc,
+                                          const int *cw, const double *cb, const double *X0, double *OBJ, int *STATUS,
+                                          int *ITERS, double *X)>;
+
 class B200Solver : public TNLPSolver {
  public:
   explicit B200Solver(BatchSolveFn fn) : solve_(std::move(fn)) {}
@@ -35,17 +44,36 @@ class B200Solver : public TNLPSolver {
   int IterationCount() override { return iterations_; }
   const std::string &solverName() const override { return name_; }
   // the batched sibling: children differ only in bounds; results in TMINLP2TNLP layout
-  struct Child { double obj; ReturnStatus status; int iters; std::vector<double> x; };
+  // (the primal points of one batch live in ONE shared block; a child refers to its row)
+  struct Child {
+    double obj; ReturnStatus status; int iters;
+    std::shared_ptr<std::vector<double>> block; size_t off = 0;
+    const double *x() const { return block->data() + off; }
+  };
   int OptimizeBatch(const TMINLP2TNLP &parent, const std::vector<double> &XL, const std::vector<double> &XU, int B,
                     std::vector<Child> &out);
+  // children of P parents, each one bound away from its parent (see ChildrenSolveFn); without a ChildrenSolveFn the
+  // bound vectors are expanded here and go through the BatchSolveFn
+  void setChildrenSolver(ChildrenSolveFn f) { children_ = std::move(f); }
+  int OptimizeChildren(const TMINLP2TNLP &parent, int P, const std::vector<double> &PXL, const std::vector<double> &PXU,
+                       const std::vector<int> &cp, const std::vector<int> &cc, const std::vector<int> &cw,
+                       const std::vector<double> &cb, std::vector<Child> &out);
   long totalBatchIterations() const { return total_batch_iterations_; }
+  double solveSeconds() const { return solve_seconds_; }
 
  private:
+  int unpack(int rc, int B, int n, std::vector<Child> &out);
+  std::shared_ptr<std::vector<double>> x_block(size_t cnt);
   BatchSolveFn solve_;
+  ChildrenSolveFn children_;
+  std::vector<double> obj_buf_, xl_buf_, xu_buf_;   // reused between calls: no fresh pages per round
+  std::vector<int> st_buf_, it_buf_;
+  std::shared_ptr<std::vector<double>> x_pool_;
   std::string name_ = "B200 batched IPM";
   double cpu_time_ = 0;
   int iterations_ = 0;
   long total_batch_iterations_ = 0;
+  double solve_seconds_ = 0;
 };
 
 // Strong-branching plugin: prefetch() solves all 2K children of a node as ONE batch; solveFromHotStart() then serves
@@ -180,6 +208,7 @@ struct DiveResult {
 DiveResult dive_run(TMINLP2TNLP &node, BatchSolveFn solve, GradFFn grad_f, const std::vector<int> &column_length,
                     double solution_value, const DiveOptions &opt);
 
-BbResult bb_run(TMINLP2TNLP &root, BatchSolveFn solve, const BbOptions &opt, TqpSolveFn tqp = nullptr);
+BbResult bb_run(TMINLP2TNLP &root, BatchSolveFn solve, const BbOptions &opt, TqpSolveFn tqp = nullptr,
+                ChildrenSolveFn children = nullptr);
 
 }  // namespace Bonmin

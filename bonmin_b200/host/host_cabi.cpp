@@ -17,6 +17,12 @@ int bnlp_bb_run_cb(int n, int m, const int *var_type, const double *xl, const do
 int bnlp_bb_run_cb2(int n, int m, const int *var_type, const double *xl, const double *xu, const double *gl,
                     const double *gu, const double *x0, bnlp_batch_solve_cb cb, bnlp_tqp_solve_cb qp_cb, void *ctx,
                     const bnlp_bb_options *o, bnlp_bb_result *res, double *best_x) {
+  return bnlp_bb_run_cb3(n, m, var_type, xl, xu, gl, gu, x0, cb, qp_cb, nullptr, ctx, o, res, best_x);
+}
+
+int bnlp_bb_run_cb3(int n, int m, const int *var_type, const double *xl, const double *xu, const double *gl,
+                    const double *gu, const double *x0, bnlp_batch_solve_cb cb, bnlp_tqp_solve_cb qp_cb,
+                    bnlp_children_solve_cb ch_cb, void *ctx, const bnlp_bb_options *o, bnlp_bb_result *res, double *best_x) {
   using namespace Bonmin;
   TMINLP2TNLP root;
   root.n = n; root.m = m;
@@ -42,7 +48,13 @@ int bnlp_bb_run_cb2(int n, int m, const int *var_type, const double *xl, const d
                        int *IT, double *X) { return qp_cb(ctx, xs, du, B, XL, XU, OBJ, ST, IT, X); };
   BatchSolveFn fn = [cb, ctx](int B, const double *XL, const double *XU, const double *X0, double *OBJ, int *ST, int *IT,
                               double *X, double *G, double *D) { return cb(ctx, B, XL, XU, X0, OBJ, ST, IT, X, G, D); };
-  BbResult r = bb_run(root, fn, opt, qfn);
+  ChildrenSolveFn cfn;
+  if (ch_cb)
+    cfn = [ch_cb, ctx](int P, const double *PXL, const double *PXU, int B, const int *cp, const int *cc, const int *cw,
+                       const double *cb2, const double *X0, double *OBJ, int *ST, int *IT, double *X) {
+      return ch_cb(ctx, P, PXL, PXU, B, cp, cc, cw, cb2, X0, OBJ, ST, IT, X);
+    };
+  BbResult r = bb_run(root, fn, opt, qfn, cfn);
   res->status = r.status; res->nodes = r.nodes; res->nlp_solves = r.nlp_solves; res->sb_batches = r.sb_batches;
   res->sb_children = r.sb_children; res->served_from_sb_cache = r.served_from_sb_cache;
   res->ipm_iterations = r.ipm_iterations; res->best_obj = r.best_obj; res->best_bound = r.best_bound; res->seconds = r.seconds;
@@ -164,7 +176,11 @@ int bnlp_bb_run_engine(bnlp_engine *E, const bnlp_problem *P, const bnlp_bb_opti
   };
   auto qcb = [](void *ctx, const double *xs, const double *du, int B, const double *XL, const double *XU, double *OBJ,
                 int *ST, int *IT, double *X) { return bnlp_tqp_solve_batch((bnlp_engine *)ctx, xs, du, B, XL, XU, OBJ, ST, IT, X); };
-  return bnlp_bb_run_cb2(n, m, vt.data(), xl.data(), xu.data(), gl.data(), gu.data(), x0.data(), cb, qcb, E, o, res, best_x);
+  auto ccb = [](void *ctx, int P, const double *PXL, const double *PXU, int B, const int *cp, const int *cc, const int *cw,
+                const double *cb2, const double *X0, double *OBJ, int *ST, int *IT, double *X) {
+    return bnlp_solve_children((bnlp_engine *)ctx, P, PXL, PXU, B, cp, cc, cw, cb2, X0, 0, OBJ, ST, IT, X, nullptr, nullptr);
+  };
+  return bnlp_bb_run_cb3(n, m, vt.data(), xl.data(), xu.data(), gl.data(), gu.data(), x0.data(), cb, qcb, ccb, E, o, res, best_x);
 }
 #endif
 

@@ -42,7 +42,8 @@ def test_mytoy_goldens(bnlp_lib, oracle_ipm):
     np.testing.assert_allclose(r["duals"], o["duals"], atol=1e-5)
 
 
-@pytest.mark.parametrize("shape,B", [((100, 50, 20, 20, 20261019), 256), ((200, 100, 40, 40, 20261020), 300)])
+@pytest.mark.parametrize("shape,B", [((100, 50, 20, 20, 20261019), 256), ((200, 100, 40, 40, 20261020), 300),
+                                     ((100, 50, 20, 20, 20261019), 640)])   # 640 >= 2 x SMs: the 256-thread, 2-CTA/SM kernel
 def test_children_parity(bnlp_lib, oracle_ipm, shape, B):
     m = I.syn_miqcp(*shape)
     eng = _engine(m)
@@ -122,6 +123,58 @@ def test_determinism_and_queue_order(bnlp_lib):
     c = eng2.solve_batch(XL, XU, xs)
     for k in ("obj", "status", "iters", "x"):
         assert np.array_equal(a[k], b[k]) and np.array_equal(a[k], c[k])
+
+
+def test_two_ctas_per_sm_variant_is_bit_identical(bnlp_lib):
+    """n + 3 <= 128 and B >= 2 x SMs selects the 256-thread build of the cooperative kernel (two children per SM); a fixed
+    CTA count keeps the 512-thread one.  Same arithmetic in the same order: identical bits."""
+    m = I.syn_miqcp(100, 50, 20, 20, 20261019)
+    xs = _engine(m).solve_batch(m.xl, m.xu, m.x0)["x"][0]
+    XL, XU = I.c3_children(m, xs, 1000)
+    a = _engine(m).solve_batch(XL, XU, xs)
+    b = _engine(m, ctas_per_device=148).solve_batch(XL, XU, xs)
+    for k in ("obj", "status", "iters", "x", "duals"):
+        assert np.array_equal(a[k], b[k]), k
+
+
+def test_solve_children_equals_explicit_bounds(bnlp_lib):
+    """bnlp_solve_children (parents + one changed bound per child, expanded on the device) against bnlp_solve_batch on the
+    host-expanded bound vectors: the same children, identical bits.  Includes per-parent start points and bad indices."""
+    m = I.syn_miqcp(60, 30, 12, 12, 3)
+    eng = _engine(m)
+    xs = eng.solve_batch(m.xl, m.xu, m.x0)["x"][0]
+    rng = np.random.default_rng(5)
+    ints = np.flatnonzero(np.asarray(m.vtype) != 0)
+    P, K = 5, 12
+    PXL, PXU = np.tile(m.xl, (P, 1)), np.tile(m.xu, (P, 1))
+    for q in range(1, P):                         # parents = the root with a few integers already branched on
+        for j in rng.choice(ints, q, replace=False):
+            if rng.random() < 0.5:
+                PXU[q, j] = np.floor(xs[j])
+            else:
+                PXL[q, j] = np.ceil(xs[j])
+    cp, cc, cw, cb = [], [], [], []
+    for q in range(P):
+        for j in rng.choice(ints, K, replace=False):
+            for w in (0, 1):
+                cp.append(q); cc.append(j); cw.append(w); cb.append(np.floor(xs[j]) if w == 0 else np.ceil(xs[j]))
+    cp, cc, cw, cb = map(np.asarray, (cp, cc, cw, cb))
+    XL, XU = PXL[cp].copy(), PXU[cp].copy()
+    for b in range(len(cp)):
+        (XU if cw[b] == 0 else XL)[b, cc[b]] = cb[b]
+    a = eng.solve_children(PXL, PXU, cp, cc, cw, cb, xs, want_g=True, want_duals=True)
+    b_ = eng.solve_batch(XL, XU, xs)
+    for k in ("obj", "status", "iters", "x", "g", "duals"):
+        assert np.array_equal(a[k], b_[k]), k
+    assert (a["status"] == 1).sum() > len(cp) // 2
+    X0p = np.tile(xs, (P, 1)) + 1e-3 * rng.standard_normal((P, m.n))
+    a = eng.solve_children(PXL, PXU, cp, cc, cw, cb, X0p)
+    b_ = eng.solve_batch(XL, XU, X0p[cp])
+    assert np.array_equal(a["obj"], b_["obj"]) and np.array_equal(a["status"], b_["status"])
+    from bonmin_b200.engine import BnlpError
+    bad = cp.copy(); bad[3] = P
+    with pytest.raises(BnlpError):
+        eng.solve_children(PXL, PXU, bad, cc, cw, cb, xs)
 
 
 def test_size_independent_properties_full_batch(bnlp_lib):
