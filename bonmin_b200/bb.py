@@ -87,11 +87,17 @@ def run_callback(model, solve_batch, tqp_solve=None, **kw):
             np.ctypeslib.as_array(X, (B, n))[:] = r["x"]
         return 0
 
+    failure = []
+
     def cb(ctx, B, XL, XU, X0, OBJ, ST, IT, X, G, D):
         xl = np.ctypeslib.as_array(XL, (B, n)).copy()
         xu = np.ctypeslib.as_array(XU, (B, n)).copy()
         x0 = np.ctypeslib.as_array(X0, (n,)).copy()
-        r = solve_batch(xl, xu, x0)
+        try:
+            r = solve_batch(xl, xu, x0)
+        except Exception as e:      # a provider failure must reach the driver as an error code (and the caller as an exception)
+            failure.append(e)
+            return -1
         np.ctypeslib.as_array(OBJ, (B,))[:] = r["obj"]
         np.ctypeslib.as_array(ST, (B,))[:] = r["status"]
         np.ctypeslib.as_array(IT, (B,))[:] = r["iters"]
@@ -117,7 +123,7 @@ def run_callback(model, solve_batch, tqp_solve=None, **kw):
     rc = L.bnlp_bb_run_cb2(n, m, *[arr[k].ctypes.data_as(c_void) for k in ("vt", "xl", "xu", "gl", "gu", "x0")], keep,
                            keepq, None, ctypes.byref(o), ctypes.byref(res), x.ctypes.data_as(c_void))
     if rc:
-        raise RuntimeError("bnlp_bb_run_cb failed")
+        raise RuntimeError("bnlp_bb_run_cb failed" + (f": {failure[0]!r}" if failure else ""))
     d = res.as_dict()
     d["best_x"] = x
     return d

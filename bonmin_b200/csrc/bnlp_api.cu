@@ -375,9 +375,12 @@ extern "C" bnlp_engine *bnlp_engine_create(const bnlp_problem *prob, const int *
                    !getenv("BNLP_NO_COOP");
     }
     // (the attribute is per kernel, not per engine: several engines with different needs may be alive, so opt in to the maximum)
-    if (d == 0 && E->coop_ok && n + 3 <= 128 && !getenv("BNLP_NO_COOP256") && bnlp_coop256_set_smem(D.smem_optin - 1024) == cudaSuccess &&
-        bnlp_coop256_max_ctas_per_sm(E->coop_smem_bytes) >= 2)
-      E->coop256 = true;
+    // (function attributes are per device: every device opts in; the variant is used only if all of them can)
+    {
+      const bool ok256 = E->coop_ok && n + 3 <= 128 && !getenv("BNLP_NO_COOP256") &&
+                         bnlp_coop256_set_smem(D.smem_optin - 1024) == cudaSuccess && bnlp_coop256_max_ctas_per_sm(E->coop_smem_bytes) >= 2;
+      E->coop256 = (d == 0) ? ok256 : (E->coop256 && ok256);
+    }
     if (E->coop_ok && ipm_coop_set_smem(D.smem_optin - 1024) != cudaSuccess) {
       E->coop_ok = false;
       cudaGetLastError();

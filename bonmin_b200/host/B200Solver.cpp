@@ -26,7 +26,7 @@ TNLPSolver::ReturnStatus B200Solver::OptimizeTNLP(TMINLP2TNLP &t) {
                         t.duals_sol.data());
   cpu_time_ = now_s() - t0;
   iterations_ = it;
-  if (rc != 0) { t.return_status = exception; return exception; }
+  if (rc != 0) { provider_errors_++; t.return_status = exception; return exception; }
   t.obj_value = obj;
   t.return_status = (ReturnStatus)st;
   return (ReturnStatus)st;
@@ -39,6 +39,7 @@ std::shared_ptr<std::vector<double>> B200Solver::x_block(size_t cnt) {
 }
 
 int B200Solver::unpack(int rc, int B, int n, std::vector<Child> &out) {
+  provider_errors_ += (rc != 0);
   out.resize(B);
   for (int b = 0; b < B; ++b) {
     out[b].obj = obj_buf_[b];
@@ -291,7 +292,7 @@ BbResult bb_run(TMINLP2TNLP &root, BatchSolveFn solve, const BbOptions &opt, Tqp
   // later NLP: src/CbcBonmin/BonCbc.cpp:452,492-505)
   si.initialSolve();
   R.nlp_solves++;
-  if (!si.isProvenOptimal()) { R.status = si.isProvenPrimalInfeasible() ? 1 : 2; R.seconds = now_s() - t0; return R; }
+  if (!si.isProvenOptimal()) { R.status = app.providerErrors() ? 3 : si.isProvenPrimalInfeasible() ? 1 : 2; R.seconds = now_s() - t0; return R; }
   root.setxInit(n, root.x_sol.data());
   std::priority_queue<Node *, std::vector<Node *>, Cmp> heap;
   Node *first = new Node{root.x_l, root.x_u, root.obj_value, 0};
@@ -317,6 +318,7 @@ BbResult bb_run(TMINLP2TNLP &root, BatchSolveFn solve, const BbOptions &opt, Tqp
     };
     while (!heap.empty()) {
       if (R.nodes >= opt.node_limit || now_s() - t0 > opt.time_limit) { R.status = 2; break; }
+      if (app.providerErrors()) break;   // a failed device call is an error, not an infeasible node
       std::vector<Node *> batch;
       while (!heap.empty() && (int)batch.size() < opt.parallel_nodes) {
         Node *nd = heap.top(); heap.pop();
@@ -413,6 +415,7 @@ BbResult bb_run(TMINLP2TNLP &root, BatchSolveFn solve, const BbOptions &opt, Tqp
     if (!nd) { nd = heap.top(); heap.pop(); }
     if (nd->bound >= cutoff) { delete nd; continue; }
     if (R.nodes >= opt.node_limit || now_s() - t0 > opt.time_limit) { R.status = 2; delete nd; break; }
+    if (app.providerErrors()) { delete nd; break; }
     R.nodes++;
     root.x_l = nd->xl; root.x_u = nd->xu;
     if (nd->solved) {
@@ -499,6 +502,7 @@ BbResult bb_run(TMINLP2TNLP &root, BatchSolveFn solve, const BbOptions &opt, Tqp
   while (!heap.empty()) { R.best_bound = std::min(R.best_bound < -1e99 ? 1e100 : R.best_bound, heap.top()->bound); delete heap.top(); heap.pop(); }
   if (dive) delete dive;
   if (R.status == 0) { R.status = R.best_obj < 1e99 ? 0 : 1; R.best_bound = R.best_obj; }
+  if (app.providerErrors()) R.status = 3;
   R.ipm_iterations = si.totalIterations() + app.totalBatchIterations() + sb.qpIterations();
   R.seconds = now_s() - t0;
   if (getenv("BNLP_BB_TIMERS"))

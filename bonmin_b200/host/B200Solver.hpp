@@ -60,6 +60,7 @@ class B200Solver : public TNLPSolver {
                        const std::vector<double> &cb, std::vector<Child> &out);
   long totalBatchIterations() const { return total_batch_iterations_; }
   double solveSeconds() const { return solve_seconds_; }
+  int providerErrors() const { return provider_errors_; }   // batch calls whose provider returned non-zero
 
  private:
   int unpack(int rc, int B, int n, std::vector<Child> &out);
@@ -74,6 +75,7 @@ class B200Solver : public TNLPSolver {
   int iterations_ = 0;
   long total_batch_iterations_ = 0;
   double solve_seconds_ = 0;
+  int provider_errors_ = 0;
 };
 
 // Strong-branching plugin: prefetch() solves all 2K children of a node as ONE batch; solveFromHotStart() then serves

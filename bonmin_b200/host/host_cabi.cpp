@@ -59,7 +59,7 @@ int bnlp_bb_run_cb3(int n, int m, const int *var_type, const double *xl, const d
   res->sb_children = r.sb_children; res->served_from_sb_cache = r.served_from_sb_cache;
   res->ipm_iterations = r.ipm_iterations; res->best_obj = r.best_obj; res->best_bound = r.best_bound; res->seconds = r.seconds;
   if (best_x && !r.best_x.empty()) memcpy(best_x, r.best_x.data(), sizeof(double) * n);
-  return 0;
+  return r.status == 3 ? -1 : 0;   // the arithmetic provider failed: an error, not a search result
 }
 
 int bnlp_resolve_cb(int mode, int n, int m, const double *xl, const double *xu, const double *x_init, double cur_obj,

@@ -249,7 +249,7 @@ typedef struct bnlp_bb_options {
                                   candidates only (trustStrongForSolution = false, never reused as node relaxations) */
 } bnlp_bb_options;
 typedef struct bnlp_bb_result {
-  int status;                 /* 0 optimal, 1 infeasible, 2 limit reached */
+  int status;                 /* 0 optimal, 1 infeasible, 2 limit reached, 3 the batch-solve provider returned an error (the call returns -1) */
   int nodes, nlp_solves, sb_batches, sb_children, served_from_sb_cache;
   long long ipm_iterations;
   double best_obj, best_bound, seconds;

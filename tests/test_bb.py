@@ -119,3 +119,18 @@ def test_bb_engine_qp_strong_branching(bnlp_lib, oracle_ipm):
         assert g["best_obj"] == pytest.approx(c["best_obj"], rel=1e-6)
         assert g["best_obj"] == pytest.approx(n["best_obj"], rel=1e-6)
         assert g["nodes"] == c["nodes"] and g["sb_children"] == c["sb_children"]
+
+
+def test_provider_error_is_not_a_fathomed_node():
+    """A batch-solve provider that fails must abort the search with an error (status 3 / RuntimeError), never be read as
+    'all children infeasible'."""
+    from bonmin_b200 import bb, instances as I
+    m = I.syn_miqcp(12, 6, 3, 3, 1)
+    calls = {"n": 0}
+
+    def broken(XL, XU, x0):
+        calls["n"] += 1
+        raise RuntimeError("device lost")
+    with pytest.raises(RuntimeError):
+        bb.run_callback(m, broken, number_strong_branch=4)
+    assert calls["n"] >= 1
