@@ -320,6 +320,42 @@ int bnlp_resolve_engine(bnlp_engine *, int mode, const double *xl, const double 
                         int cur_status, int numsolve, double max_random_point_radius, unsigned seed, bnlp_retry_result *res,
                         double *obj, int *status, double *x, double *g, double *duals);
 
+/* --- on-disk formats either side of the path (host code; bonmin_b200/host/node_files.cpp) -------------------------
+ * Failed-node dump = TMINLP2TNLP::outputDiffs (src/Interfaces/BonTMINLP2TNLP.cpp:551-615): writes <prob_name>.bounds
+ * ("LO|UP\tindex\tvalue" per bound that differs from the original model, CoinRelFltEq 1e-10) and <prob_name>.start
+ * ("n\t2n+m", x_init with 17 digits, then the 2n+m duals when duals_init != NULL). */
+int bnlp_write_node_files(const char *prob_name, int n, int m, const double *xl, const double *xu, const double *orig_xl,
+                          const double *orig_xu, const double *x_init, const double *duals_init);
+/* BoundsReader::readAndApply (src/Interfaces/BonBoundsReader.cpp:52-119): applies the file's LO/UP lines to xl/xu (the
+ * caller pre-fills them with the model's bounds).  Returns the number of lines applied, -1 on a malformed file. */
+int bnlp_read_bounds_file(const char *file, int n, double *xl, double *xu);
+/* StartPointReader::readFile (src/Interfaces/BonStartPointReader.cpp:15-37).  n_duals returns how many dual values the
+ * file really holds (outputDiffs omits them when the node had none). */
+int bnlp_read_start_file(const char *file, int *n_primals, int *n_duals, double *primals, int cap_primals, double *duals,
+                         int cap_duals);
+/* Batch replay file: all B children of one bnlp_solve_batch call in the same line format — <prob_name>.children
+ * ("BATCH\tn\tm\tB\tx0_per_child", then per child "CHILD\tk" and its LO/UP lines, 17 digits) and <prob_name>.start
+ * (the shared or per-child start points).  A GPU/CPU disagreement becomes a two-file repro. */
+int bnlp_write_batch_replay(const char *prob_name, int n, int m, int B, const double *XL, const double *XU,
+                            const double *orig_xl, const double *orig_xu, const double *X0, int x0_per_child);
+int bnlp_read_batch_replay_header(const char *file, int *n, int *m, int *B, int *x0_per_child);
+int bnlp_read_batch_replay(const char *file, int n, int B, const double *orig_xl, const double *orig_xu, double *XL,
+                           double *XU);
+/* AmplTMINLP::finalize_solution (src/Interfaces/Ampl/BonAmplTMINLP.cpp:712-753): message + AMPL solve_result_num for a
+ * TMINLP::SolverReturn (0 SUCCESS 3, 1 INFEASIBLE 220, 2 CONTINUOUS_UNBOUNDED 300, 3 LIMIT_EXCEEDED 421/410,
+ * 4 USER_INTERRUPT 422/411, 5 MINLP_ERROR 500); finished: 1 "Finished", 0 "Not finished", -1 "Aborted". */
+int bnlp_sol_status(int solver_return, int has_x, const char *app_name, char *message, size_t msglen, int *solve_result_num,
+                    int *finished);
+/* option integers of the first line of a text .nl file (opts[0] = count, then the values) — what the .sol file echoes */
+int bnlp_nl_header_options(const char *nl_text, size_t len, int *opts, int cap, double *vbtol);
+/* AmplTMINLP::write_solution (:769-794) -> ASL write_sol, text format (ASL is not in the reference tree: published format
+ * restated, parity unpinned): message, blank line, "Options" block, n_con, #duals, n_var, #primals, values (shortest
+ * round-trip decimals), "objno 0 <solve_result_num>".  x or y may be NULL (count 0 is written). */
+int bnlp_write_sol(const char *file, const char *message, const int *ampl_options, double ampl_vbtol, int n_con, int n_var,
+                   const double *x, const double *y, int solve_result_num);
+/* the non-AMPL fallback of finalize_solution (:758-766): "i\tx_i" lines and a closing -1 */
+int bnlp_write_plain_sol(const char *file, int n, const double *x);
+
 #ifdef __cplusplus
 }
 #endif

@@ -47,5 +47,8 @@ for trial in range(int(sys.argv[2]) if len(sys.argv) > 2 else 24):
     if flag:
         idx = np.flatnonzero(~same)[:5]
         print("   mismatching children", idx, r["status"][idx], o["status"][idx], r["obj"][idx], o["obj"][idx])
+        from bonmin_b200 import files   # two-file repro of the whole batch (gpurun_out/ travels back from the GPU box)
+        os.makedirs("gpurun_out", exist_ok=True)
+        files.write_batch_replay(f"gpurun_out/mismatch_{fam}_{n}_{m_q}_{m_l}_{seed}", XL, XU, m.xl, m.xu, xs, m=m.m)
     eng.close()
 print("trials with mismatches:", bad, "time", time.time() - t0)

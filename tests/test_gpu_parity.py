@@ -177,6 +177,21 @@ def test_solve_children_equals_explicit_bounds(bnlp_lib):
         eng.solve_children(PXL, PXU, bad, cc, cw, cb, xs)
 
 
+def test_batch_replay_file_reproduces_the_batch(bnlp_lib, tmp_path):
+    """A dumped batch (bonmin_b200.files.write_batch_replay) read back and solved again gives the same bits."""
+    from bonmin_b200 import files
+    m = I.syn_miqcp(40, 20, 8, 8, 3)
+    eng = _engine(m)
+    xs = eng.solve_batch(m.xl, m.xu, m.x0)["x"][0]
+    XL, XU = I.c3_children(m, xs, 50)
+    a = eng.solve_batch(XL, XU, xs)
+    files.write_batch_replay(str(tmp_path / "b"), XL, XU, m.xl, m.xu, xs, m=m.m)
+    rl, ru, x0 = files.read_batch_replay(str(tmp_path / "b"), m.xl, m.xu)
+    b = eng.solve_batch(rl, ru, x0)
+    for k in ("obj", "status", "iters", "x"):
+        assert np.array_equal(a[k], b[k]), k
+
+
 def test_size_independent_properties_full_batch(bnlp_lib):
     """BASELINE-size batch (C3, 4096 children) checked through properties that need no oracle:
     (i) optimal children are feasible for the original rows and bounds, (ii) a child's optimum is never below its
