@@ -26,6 +26,7 @@ constexpr double kInfD = 1e19;
 namespace bnlp {
 bool model_from_desc(const bnlp_tape_desc *d, HostModel &M, std::string &err);
 bool model_fp_variant(const HostModel &B, const bnlp_fp_desc &d, HostModel &M, std::string &err);
+bool model_cs_variant(const HostModel &B, int constr_index, HostModel &M, std::string &err);
 // kernel launchers live in their own translation units (bnlp_launch_ipm.cu, bnlp_launch_coop.cu) so the three big
 // kernels compile in parallel
 cudaError_t ipm_general_set_smem(size_t smem);
@@ -155,6 +156,17 @@ extern "C" bnlp_problem *bnlp_problem_fp(const bnlp_problem *base, const bnlp_fp
   if (!base || !desc) e = "null argument";
   auto *p = new bnlp_problem();
   if (e.empty() && model_fp_variant(base->M, *desc, p->M, e)) return p;
+  if (err && errlen) snprintf(err, errlen, "%s", e.c_str());
+  set_err(e);
+  delete p;
+  return nullptr;
+}
+
+extern "C" bnlp_problem *bnlp_problem_cut_strengthening(const bnlp_problem *base, int constr_index, char *err, size_t errlen) {
+  std::string e;
+  if (!base) e = "null argument";
+  auto *p = new bnlp_problem();
+  if (e.empty() && model_cs_variant(base->M, constr_index, p->M, e)) return p;
   if (err && errlen) snprintf(err, errlen, "%s", e.c_str());
   set_err(e);
   delete p;

@@ -137,6 +137,51 @@ bool model_from_desc(const bnlp_tape_desc *d, HostModel &M, std::string &err) {
 //     norm 1: dist = sum_i [p_i <= 0.1 ? x_i : 1 - x_i]  ==  x_i (1 - 2 p_i) + p_i for p_i in {0, 1}   (:85-94)
 //   cutoff row (use_cutoff_constraint): the (new) objective <= cutoff                        (:150-155, :204-214)
 //   local-branching row: sum_i x_i (1 - 2 p_i) + p_i <= rhs                                  (:215-223)
+// CutStrengthener::StrengtheningTNLP (src/Interfaces/BonCutStrengthener.cpp:306-560) as a model variant: the NLP
+//   min  obj_grad . x   s.t.  g_l <= g_i(x) <= g_u            (constraint row i of the base model)
+//   min  obj_grad . (x, z)   s.t.  f(x) - z <= 0              (constr_index == -1: the objective cut, z = the alpha column)
+// whose optimal value is the tightest valid right-hand side of the cut  obj_grad . x >= bound.  The cut coefficients are
+// per-cut data, so they enter as nv EXTRA variables p (variable nv + j multiplies variable j in the objective; nv = n, or
+// n + 1 with z); a child fixes them through its bounds, exactly like the feasibility-pump targets, so all the cuts of
+// one row are ONE batch.  With p fixed the objective is linear in the free variables (the p-x cross block of the Hessian
+// only touches fixed variables).  The reference restricts the NLP to the variables that appear in row i; the caller
+// gets the same problem by fixing the other variables at the cut point through the child's bounds.
+bool model_cs_variant(const HostModel &B, int ci, HostModel &M, std::string &err) {
+  const int n = B.n;
+  if (ci < -1 || ci >= B.m) { err = "constraint index out of range"; return false; }
+  const int nv = n + (ci == -1 ? 1 : 0), n2 = 2 * nv;
+  const int src = ci + 1;                         // function index in the base tape (0 = objective)
+  M = HostModel();
+  M.n = n2; M.m = 1;
+  M.xl.assign(n2, -kInf); M.xu.assign(n2, kInf); M.x0.assign(n2, 0.0); M.vtype.assign(n2, 0);
+  for (int j = 0; j < n; ++j) { M.xl[j] = B.xl[j]; M.xu[j] = B.xu[j]; M.x0[j] = B.x0[j]; M.vtype[j] = B.vtype[j]; }
+  if (ci == -1) { M.gl = {-kInf}; M.gu = {0.0}; }
+  else { M.gl = {B.gl[ci]}; M.gu = {B.gu[ci]}; }
+  M.c = {0.0, B.c[src]};
+  // objective: sum_j p_j x_j  (1/2 x'Qx convention: Q_{p_j, x_j} = 1)
+  for (int j = 0; j < nv; ++j) { M.qs_fn.push_back(0); M.qs_i.push_back(nv + j); M.qs_j.push_back(j); M.qs_v.push_back(1.0); }
+  // the row
+  M.lin_start = {0, 0};
+  for (int e = B.lin_start[src]; e < B.lin_start[src + 1]; ++e) { M.lin_col.push_back(B.lin_col[e]); M.lin_val.push_back(B.lin_val[e]); }
+  if (ci == -1) { M.lin_col.push_back(n); M.lin_val.push_back(-1.0); }
+  M.lin_start.push_back((int)M.lin_col.size());
+  for (size_t e = 0; e < B.qs_fn.size(); ++e)
+    if (B.qs_fn[e] == src) { M.qs_fn.push_back(1); M.qs_i.push_back(B.qs_i[e]); M.qs_j.push_back(B.qs_j[e]); M.qs_v.push_back(B.qs_v[e]); }
+  const size_t P = (size_t)n * (n + 1) / 2;
+  for (size_t q = 0; q < B.qd_fn.size(); ++q)
+    if (B.qd_fn[q] == src) {        // dense block -> triplets (the variant has 2 nv variables; the block only spans the first n)
+      const double *blk = B.qd.data() + q * P;
+      size_t e = 0;
+      for (int i = 0; i < n; ++i)
+        for (int j = 0; j <= i; ++j, ++e)
+          if (blk[e] != 0.0) { M.qs_fn.push_back(1); M.qs_i.push_back(i); M.qs_j.push_back(j); M.qs_v.push_back(blk[e]); }
+    }
+  for (const Term &t : B.terms)
+    if (t.fn == src) { Term u = t; u.fn = 1; M.terms.push_back(u); }
+  M.finalize();
+  return true;
+}
+
 bool model_fp_variant(const HostModel &B, const bnlp_fp_desc &d, HostModel &M, std::string &err) {
   const int n = B.n, m = B.m, k = d.n_inds;
   if (k < 0 || (k > 0 && !d.inds)) { err = "bad index set"; return false; }

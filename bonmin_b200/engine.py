@@ -59,7 +59,7 @@ EXPORTS = ["bnlp_last_error", "bnlp_problem_from_nl", "bnlp_problem_from_tape", 
            "bnlp_resolve_cb", "bnlp_resolve_engine", "bnlp_problem_fp", "bnlp_solve_children", "bnlp_bb_run_cb3",
            "bnlp_write_node_files", "bnlp_read_bounds_file", "bnlp_read_start_file", "bnlp_write_batch_replay",
            "bnlp_read_batch_replay_header", "bnlp_read_batch_replay", "bnlp_sol_status", "bnlp_nl_header_options",
-           "bnlp_write_sol", "bnlp_write_plain_sol"]
+           "bnlp_write_sol", "bnlp_write_plain_sol", "bnlp_problem_cut_strengthening"]
 
 
 def lib():
@@ -75,6 +75,8 @@ def lib():
         L.bnlp_problem_from_nl.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t]
         L.bnlp_problem_fp.restype = c_void
         L.bnlp_problem_fp.argtypes = [c_void, ctypes.POINTER(FpDesc), ctypes.c_char_p, ctypes.c_size_t]
+        L.bnlp_problem_cut_strengthening.restype = c_void
+        L.bnlp_problem_cut_strengthening.argtypes = [c_void, c_int, ctypes.c_char_p, ctypes.c_size_t]
         L.bnlp_problem_free.argtypes = [c_void]
         L.bnlp_problem_sizes.argtypes = [c_void, P_int, P_int, P_int, P_int]
         L.bnlp_problem_info.argtypes = [c_void] + [c_void] * 11
@@ -203,6 +205,15 @@ class Problem:
                    float(cutoff or 0.0), float(rhs_local_branching or 0.0))
         err = ctypes.create_string_buffer(512)
         h = lib().bnlp_problem_fp(self.h, ctypes.byref(d), err, 512)
+        if not h:
+            raise BnlpError(err.value.decode())
+        return Problem(h)
+
+    def cs_variant(self, constr_index):
+        """CutStrengthener::StrengtheningTNLP for row `constr_index` (-1: the objective cut) as a new Problem whose last
+        nv variables are the cut coefficients (see include/bnlp.h: bnlp_problem_cut_strengthening)."""
+        err = ctypes.create_string_buffer(512)
+        h = lib().bnlp_problem_cut_strengthening(self.h, int(constr_index), err, 512)
         if not h:
             raise BnlpError(err.value.decode())
         return Problem(h)

@@ -108,6 +108,16 @@ typedef struct bnlp_fp_desc {
 } bnlp_fp_desc;
 bnlp_problem *bnlp_problem_fp(const bnlp_problem *base, const bnlp_fp_desc *desc, char *err, size_t errlen);
 
+/* Cut-strengthening variant of a problem = CutStrengthener::StrengtheningTNLP
+ * (src/Interfaces/BonCutStrengthener.cpp:219-560):  min obj_grad.x  s.t.  g_l <= g_i(x) <= g_u  over the box — its optimal
+ * value is the tightest valid bound of the cut  obj_grad.x >= bound  (obj_grad = +/- the cut row, :349-354).
+ * constr_index = -1: the objective cut,  min obj_grad.(x, z)  s.t.  f(x) - z <= 0  (z = variable n, :438-441, :531-533).
+ * The cut coefficients are nv EXTRA variables (nv = n, or n + 1 with z; variable nv + j is the coefficient of variable
+ * j) that a child fixes through its bounds (XL = XU = obj_grad_j), so all cuts of one row are one bnlp_solve_batch
+ * call; variables that do not appear in row i are fixed at the cut point the same way (the reference leaves them out
+ * of the NLP, :362-376).  Returns NULL on error. */
+bnlp_problem *bnlp_problem_cut_strengthening(const bnlp_problem *base, int constr_index, char *err, size_t errlen);
+
 /* get_nlp_info (BonTMINLP.hpp:226-229) */
 int bnlp_problem_sizes(const bnlp_problem *, int *n, int *m, int *nnz_jac, int *nnz_hess);
 /* structure + bounds + types: get_bounds_info :238, get_variables_types :208, get_constraints_linearity :220,

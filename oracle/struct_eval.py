@@ -533,3 +533,52 @@ def fp_model(model, inds, norm=2, lam=1.0, sigma=1.0, scaling=1.0, use_fp_object
         gl=np.array(gl, float), gu=np.array(gu, float), vtype=np.concatenate([model.vtype, np.zeros(k, np.int32)]).astype(np.int32),
         x0=np.concatenate([model.x0, np.zeros(k)]), c=c, A=A, qd_fn=np.array(fns, np.int32), qd=qd, terms=terms,
         name="FP(" + str(model.get("name", "")) + ")"))
+
+
+def cs_model(model, constr_index):
+    """CPU restatement of CutStrengthener::StrengtheningTNLP (src/Interfaces/BonCutStrengthener.cpp:306-560) as a
+    StructuredModel:  min p.x  s.t.  g_l <= g_i(x) <= g_u  (constr_index = -1:  min p.(x, z)  s.t.  f(x) - z <= 0), the cut
+    coefficients p as nv extra variables fixed per child through bounds (nv = n, or n + 1 with z).  Test infrastructure
+    only; mirrors bnlp_problem_cut_strengthening."""
+    from bonmin_b200.instances import StructuredModel, pack_lower, unpack_lower, _empty_sparse
+    n = model.n
+    ci = int(constr_index)
+    if not -1 <= ci < model.m:
+        raise ValueError("constraint index out of range")
+    nv = n + (1 if ci == -1 else 0)
+    n2 = 2 * nv
+    src = ci + 1
+    Q0 = np.zeros((n2, n2))
+    for j in range(nv):
+        Q0[nv + j, j] = Q0[j, nv + j] = 1.0
+    Q1 = np.zeros((n2, n2))
+    for kk, fn in enumerate(model.qd_fn):
+        if int(fn) == src:
+            Q1[:n, :n] += unpack_lower(model.qd[kk], n)
+    for fn, i, j, v in zip(model.qs_fn, model.qs_i, model.qs_j, model.qs_v):
+        if int(fn) == src:
+            Q1[i, j] += v
+            if i != j:
+                Q1[j, i] += v
+    A = np.zeros((2, n2))
+    A[1, :n] = model.A[src]
+    if ci == -1:
+        A[1, n] = -1.0
+    INF = 1e19
+    xl = np.full(n2, -INF)
+    xu = np.full(n2, INF)
+    xl[:n], xu[:n] = model.xl, model.xu
+    x0 = np.zeros(n2)
+    x0[:n] = model.x0
+    vt = np.zeros(n2, np.int32)
+    vt[:n] = model.vtype
+    fns, blocks = [0], [pack_lower(Q0)]
+    if np.any(Q1):
+        fns.append(1)
+        blocks.append(pack_lower(Q1))
+    terms = [(1, list(v), list(p)) for fn, v, p in model.get("terms", []) if fn == src]
+    return _empty_sparse(StructuredModel(
+        n=n2, m=1, xl=xl, xu=xu, gl=np.array([-INF if ci == -1 else model.gl[ci]], float),
+        gu=np.array([0.0 if ci == -1 else model.gu[ci]], float), vtype=vt, x0=x0, c=np.array([0.0, model.c[src]]), A=A,
+        qd_fn=np.array(fns, np.int32), qd=np.array(blocks).reshape(len(fns), n2 * (n2 + 1) // 2), terms=terms,
+        name=f"CS{ci}(" + str(model.get("name", "")) + ")"))
