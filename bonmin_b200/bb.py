@@ -17,7 +17,7 @@ P_int, P_dbl = ctypes.POINTER(c_int), ctypes.POINTER(c_dbl)
 class BbOptions(ctypes.Structure):
     _fields_ = [("number_strong_branch", c_int), ("number_before_trust", c_int), ("node_limit", c_int),
                 ("log_level", c_int), ("integer_tolerance", c_dbl), ("cutoff_decr", c_dbl), ("time_limit", c_dbl),
-                ("parallel_nodes", c_int), ("variable_selection", c_int)]
+                ("parallel_nodes", c_int), ("variable_selection", c_int), ("priorities", ctypes.POINTER(c_int))]
 
 
 class BbResult(ctypes.Structure):
@@ -49,9 +49,13 @@ VARIABLE_SELECTION = {"strong-branching": 0, "qp-strong-branching": 1}
 
 
 def _opts(number_strong_branch=0, number_before_trust=0, node_limit=0, time_limit=0.0, parallel_nodes=0,
-          variable_selection="strong-branching"):
-    return BbOptions(number_strong_branch, number_before_trust, node_limit, 0, 0.0, 0.0, time_limit, parallel_nodes,
-                     VARIABLE_SELECTION[variable_selection])
+          variable_selection="strong-branching", priorities=None):
+    o = BbOptions(number_strong_branch, number_before_trust, node_limit, 0, 0.0, 0.0, time_limit, parallel_nodes,
+                  VARIABLE_SELECTION[variable_selection])
+    if priorities is not None:      # n ints, the LOWEST value is branched on first (kept alive on the struct)
+        o._pri = np.ascontiguousarray(priorities, np.int32)
+        o.priorities = o._pri.ctypes.data_as(ctypes.POINTER(c_int))
+    return o
 
 
 def run_engine(eng: "_e.Engine", **kw):

@@ -173,6 +173,28 @@ extern "C" bnlp_problem *bnlp_problem_cut_strengthening(const bnlp_problem *base
   return nullptr;
 }
 
+extern "C" int bnlp_problem_branching_info(const bnlp_problem *p, int *priorities, int *directions, double *up_pseudo, double *down_pseudo) {
+  if (!p) return -1;
+  const HostModel &M = p->M;
+  int mask = 0;
+  if (!M.br_priority.empty()) {
+    mask |= 1;
+    if (priorities) for (int i = 0; i < M.n; ++i) priorities[i] = -M.br_priority[i] + 9999;   // BonAmplTMINLP.cpp:231-236
+  }
+  if (!M.br_direction.empty()) {
+    mask |= 2;
+    if (directions) std::copy(M.br_direction.begin(), M.br_direction.end(), directions);
+  }
+  const std::vector<double> &up = !M.br_up_ps.empty() ? M.br_up_ps : M.br_down_ps;     // one given: used for both (:240-241)
+  const std::vector<double> &dn = !M.br_down_ps.empty() ? M.br_down_ps : M.br_up_ps;
+  if (!up.empty()) {
+    mask |= 4 | 8;
+    if (up_pseudo) std::copy(up.begin(), up.end(), up_pseudo);
+    if (down_pseudo) std::copy(dn.begin(), dn.end(), down_pseudo);
+  }
+  return mask;
+}
+
 extern "C" void bnlp_problem_free(bnlp_problem *p) { delete p; }
 
 extern "C" int bnlp_problem_sizes(const bnlp_problem *p, int *n, int *m, int *nnz_jac, int *nnz_hess) {

@@ -36,6 +36,10 @@ struct HostModel {
   std::vector<int> qs_fn, qs_i, qs_j;
   std::vector<double> qs_v;
   std::vector<Term> terms;
+  // branching information from the .nl variable suffixes (AmplTMINLP::read_priorities, BonAmplTMINLP.cpp:215-252);
+  // empty = suffix absent
+  std::vector<int> br_priority, br_direction;
+  std::vector<double> br_up_ps, br_down_ps;
   // derived structures (TMINLP::eval_jac_g / eval_h sparsity, BonTMINLP.hpp:286-315), 0-based
   std::vector<int> jac_row, jac_col;       // rows 0..m-1 (constraints only), row-major sorted
   std::vector<int> jac_start;              // m+1

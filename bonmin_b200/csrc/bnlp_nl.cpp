@@ -415,10 +415,32 @@ bool parse_nl(const char *text, size_t len, HostModel &M, std::string &err) {
       const int cnt = atoi(s.c_str() + 1);
       for (int i = 0; i < cnt; ++i) L.next(s);
     } else if (k == 'S') {
+      // suffix "S<kind> <count> <name>": kind & 3 = 0 variables, 1 constraints, 2 objectives, 3 problem; kind & 4 = real values.
+      // The variable suffixes AmplTMINLP::read_priorities uses are kept (BonAmplTMINLP.cpp:215-252); SOS suffixes
+      // (sosno / ref, read_sos :254-296) and the rest are skipped.
       std::stringstream ss(s.substr(1));
       int kind = 0, cnt = 0;
-      ss >> kind >> cnt;
-      for (int i = 0; i < cnt; ++i) L.next(s);   // suffixes (priorities, SOS: BonAmplTMINLP.cpp:127-168) are ignored
+      std::string name;
+      ss >> kind >> cnt >> name;
+      std::vector<int> *ti = nullptr;
+      std::vector<double> *td = nullptr;
+      if ((kind & 3) == 0) {
+        if (name == "priority") ti = &M.br_priority;
+        else if (name == "direction") ti = &M.br_direction;
+        else if (name == "upPseudocost") td = &M.br_up_ps;
+        else if (name == "downPseudocost") td = &M.br_down_ps;
+      }
+      if (ti) ti->assign(n, 0);
+      if (td) td->assign(n, 0.0);
+      for (int i = 0; i < cnt; ++i) {
+        L.next(s);
+        if (!ti && !td) continue;
+        std::stringstream s2(s);
+        int v; double a;
+        s2 >> v >> a;
+        if (v < 0 || v >= n) { err = "suffix index out of range"; return false; }
+        if (ti) (*ti)[v] = (int)a; else (*td)[v] = a;
+      }
     } else {
       err = std::string("unsupported .nl segment '") + k + "'";
       return false;

@@ -59,7 +59,7 @@ EXPORTS = ["bnlp_last_error", "bnlp_problem_from_nl", "bnlp_problem_from_tape", 
            "bnlp_resolve_cb", "bnlp_resolve_engine", "bnlp_problem_fp", "bnlp_solve_children", "bnlp_bb_run_cb3",
            "bnlp_write_node_files", "bnlp_read_bounds_file", "bnlp_read_start_file", "bnlp_write_batch_replay",
            "bnlp_read_batch_replay_header", "bnlp_read_batch_replay", "bnlp_sol_status", "bnlp_nl_header_options",
-           "bnlp_write_sol", "bnlp_write_plain_sol", "bnlp_problem_cut_strengthening"]
+           "bnlp_write_sol", "bnlp_write_plain_sol", "bnlp_problem_cut_strengthening", "bnlp_problem_branching_info"]
 
 
 def lib():
@@ -77,6 +77,7 @@ def lib():
         L.bnlp_problem_fp.argtypes = [c_void, ctypes.POINTER(FpDesc), ctypes.c_char_p, ctypes.c_size_t]
         L.bnlp_problem_cut_strengthening.restype = c_void
         L.bnlp_problem_cut_strengthening.argtypes = [c_void, c_int, ctypes.c_char_p, ctypes.c_size_t]
+        L.bnlp_problem_branching_info.argtypes = [c_void] * 5
         L.bnlp_problem_free.argtypes = [c_void]
         L.bnlp_problem_sizes.argtypes = [c_void, P_int, P_int, P_int, P_int]
         L.bnlp_problem_info.argtypes = [c_void] + [c_void] * 11
@@ -208,6 +209,17 @@ class Problem:
         if not h:
             raise BnlpError(err.value.decode())
         return Problem(h)
+
+    def branching_info(self):
+        """TMINLP::branchingInfo(): dict(priorities, directions, up, down), None for what the model does not have."""
+        n = self.n
+        pri, dr = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        up, dn = np.zeros(n), np.zeros(n)
+        mask = lib().bnlp_problem_branching_info(self.h, _vp(pri), _vp(dr), _vp(up), _vp(dn))
+        if mask < 0:
+            raise BnlpError("bnlp_problem_branching_info failed")
+        return dict(priorities=pri if mask & 1 else None, directions=dr if mask & 2 else None,
+                    up=up if mask & 4 else None, down=dn if mask & 8 else None)
 
     def cs_variant(self, constr_index):
         """CutStrengthener::StrengtheningTNLP for row `constr_index` (-1: the objective cut) as a new Problem whose last

@@ -270,6 +270,26 @@ struct Node {
 struct Cmp { bool operator()(const Node *a, const Node *b) const { return a->bound > b->bound; } };
 }  // namespace
 
+// Integer variables that violate integrality, most fractional first (setupList's second list, BonChooseVariable.cpp:357-360);
+// with priorities only those of the best (lowest) priority level stay (:330-352: a better level resets the list).
+static std::vector<std::pair<double, int>> fractional_candidates(const std::vector<double> &x, const std::vector<int> &ints,
+                                                                  const BbOptions &opt) {
+  std::vector<std::pair<double, int>> frac;
+  const bool pri = (int)opt.priorities.size() == (int)x.size();
+  int best = 0;
+  for (int j : ints) {
+    const double f = std::fabs(x[j] - std::round(x[j]));
+    if (f <= opt.integer_tolerance) continue;
+    if (pri) {
+      if (frac.empty() || opt.priorities[j] < best) { frac.clear(); best = opt.priorities[j]; }
+      else if (opt.priorities[j] > best) continue;
+    }
+    frac.push_back({-f, j});
+  }
+  std::sort(frac.begin(), frac.end());
+  return frac;
+}
+
 BbResult bb_run(TMINLP2TNLP &root, BatchSolveFn solve, const BbOptions &opt, TqpSolveFn tqp, ChildrenSolveFn children) {
   BbResult R;
   const double t0 = now_s();
@@ -307,15 +327,7 @@ BbResult bb_run(TMINLP2TNLP &root, BatchSolveFn solve, const BbOptions &opt, Tqp
     // branching children of all of them are one batch (independent relaxations sharing tape and start point)
     heap.push(first);
     dive = nullptr;
-    auto candidates_of = [&](const std::vector<double> &x) {
-      std::vector<std::pair<double, int>> frac;
-      for (int j : ints) {
-        const double f = std::fabs(x[j] - std::round(x[j]));
-        if (f > opt.integer_tolerance) frac.push_back({-f, j});
-      }
-      std::sort(frac.begin(), frac.end());
-      return frac;
-    };
+    auto candidates_of = [&](const std::vector<double> &x) { return fractional_candidates(x, ints, opt); };
     while (!heap.empty()) {
       if (R.nodes >= opt.node_limit || now_s() - t0 > opt.time_limit) { R.status = 2; break; }
       if (app.providerErrors()) break;   // a failed device call is an error, not an infeasible node
@@ -431,17 +443,12 @@ BbResult bb_run(TMINLP2TNLP &root, BatchSolveFn solve, const BbOptions &opt, Tqp
     if (obj >= cutoff) { delete nd; continue; }
     const std::vector<double> x = root.x_sol;
     // integer infeasibilities
-    std::vector<std::pair<double, int>> frac;
-    for (int j : ints) {
-      const double f = std::fabs(x[j] - std::round(x[j]));
-      if (f > opt.integer_tolerance) frac.push_back({-f, j});
-    }
+    std::vector<std::pair<double, int>> frac = fractional_candidates(x, ints, opt);
     if (frac.empty()) {   // new incumbent; Cbc's cutoff = incumbent - cutoff_decr
       if (obj < R.best_obj) { R.best_obj = obj; R.best_x = x; cutoff = obj - opt.cutoff_decr; }
       delete nd;
       continue;
     }
-    std::sort(frac.begin(), frac.end());   // most fractional first (setupList's second list, :357-360)
     // candidates needing strong branching: untrusted pseudo-costs (:633-643), at most number_strong_branch
     std::vector<int> cand;
     for (auto &f : frac) {

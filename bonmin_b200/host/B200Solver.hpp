@@ -153,6 +153,7 @@ struct BbOptions {
   int variable_selection = 0;           // 0 NLP strong branching, 1 QP strong branching (needs a TqpSolveFn)
   double time_limit = 1e10;
   int log_level = 0;
+  std::vector<int> priorities;          // empty, or n values: only the fractional integers of LOWEST value are candidates
 };
 struct BbResult {
   int status = 0;               // 0 optimal, 1 infeasible, 2 node/time limit

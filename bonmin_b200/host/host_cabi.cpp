@@ -41,6 +41,7 @@ int bnlp_bb_run_cb3(int n, int m, const int *var_type, const double *xl, const d
     opt.log_level = o->log_level;
     if (o->parallel_nodes > 0) opt.parallel_nodes = o->parallel_nodes;
     opt.variable_selection = o->variable_selection;
+    if (o->priorities) opt.priorities.assign(o->priorities, o->priorities + n);
   }
   TqpSolveFn qfn;
   if (qp_cb)
@@ -180,7 +181,11 @@ int bnlp_bb_run_engine(bnlp_engine *E, const bnlp_problem *P, const bnlp_bb_opti
                 const double *cb2, const double *X0, double *OBJ, int *ST, int *IT, double *X) {
     return bnlp_solve_children((bnlp_engine *)ctx, P, PXL, PXU, B, cp, cc, cw, cb2, X0, 0, OBJ, ST, IT, X, nullptr, nullptr);
   };
-  return bnlp_bb_run_cb3(n, m, vt.data(), xl.data(), xu.data(), gl.data(), gu.data(), x0.data(), cb, qcb, ccb, E, o, res, best_x);
+  bnlp_bb_options o2{};
+  if (o) o2 = *o;
+  std::vector<int> pri(n);
+  if (!o2.priorities && (bnlp_problem_branching_info(P, pri.data(), nullptr, nullptr, nullptr) & 1)) o2.priorities = pri.data();
+  return bnlp_bb_run_cb3(n, m, vt.data(), xl.data(), xu.data(), gl.data(), gu.data(), x0.data(), cb, qcb, ccb, E, &o2, res, best_x);
 }
 #endif
 

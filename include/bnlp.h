@@ -126,6 +126,13 @@ int bnlp_problem_info(const bnlp_problem *, int *jac_irow, int *jac_jcol, int *h
                       int *var_type, int *con_nonlinear, double *xl, double *xu, double *gl, double *gu,
                       double *x0);
 
+/* Branching information of the model = TMINLP::branchingInfo() as AmplTMINLP::read_priorities fills it from the .nl
+ * variable suffixes (src/Interfaces/Ampl/BonAmplTMINLP.cpp:215-252): priorities (9999 - suffix value: the LOWEST number is
+ * branched on first), branching directions, up / down pseudo-costs (one given: used for both).  Arrays of n or NULL.
+ * Returns a bit mask of what the model has (1 priorities, 2 directions, 4 up, 8 down), 0 for none, -1 on error. */
+int bnlp_problem_branching_info(const bnlp_problem *, int *priorities, int *directions, double *up_pseudo,
+                                double *down_pseudo);
+
 /* --- engine ------------------------------------------------------------------------------------
  * replaces the construction of an IpoptSolver (src/Interfaces/BonOsiTMINLPInterface.cpp:448-496). The tape
  * is uploaded (replicated) to every listed device. */
@@ -257,6 +264,10 @@ typedef struct bnlp_bb_options {
                                   branching (`qp-strong-branching`, src/Algorithms/BonBonminSetup.cpp:447-455): the 2K
                                   children of a node are solved on the BranchingTQP surrogate; their results rank the
                                   candidates only (trustStrongForSolution = false, never reused as node relaxations) */
+  const int *priorities;       /* n branching priorities or NULL: among the fractional integers only those with the LOWEST
+                                  value are candidates (OsiChooseVariable::setupList as kept by
+                                  BonChooseVariable::setupList, Branching/BonChooseVariable.cpp:307-584).
+                                  bnlp_bb_run_engine uses the problem's own (.nl suffix) priorities when this is NULL */
 } bnlp_bb_options;
 typedef struct bnlp_bb_result {
   int status;                 /* 0 optimal, 1 infeasible, 2 limit reached, 3 the batch-solve provider returned an error (the call returns -1) */

@@ -37,6 +37,7 @@ class NlModel:
         self.expr = {k: ("n", 0.0) for k in range(m + 1)}
         self.lin = np.zeros((m + 1, n))
         self.sense = 0
+        self.suffixes = {}
         self.defs = []      # defined variables (V segments): (linear terms, expression); index n + i
         while self._p < len(self._l):
             s = self._next()
@@ -84,8 +85,34 @@ class NlModel:
                 for _ in range(int(s[1:])):
                     v, a = self._next().split()
                     self.x0[int(v)] = float(a)
+            elif k == "S":      # suffix: "S<kind> <count> <name>", kind & 3 = 0 variables / 1 constraints / 2 objectives / 3 problem, kind & 4 = real
+                kind, cnt, name = s[1:].split()
+                tab = self.suffixes.setdefault((int(kind) & 3, name), {})
+                for _ in range(int(cnt)):
+                    v, a = self._next().split()
+                    tab[int(v)] = float(a) if int(kind) & 4 else int(float(a))
             else:
                 raise ValueError(s)
+
+    def branching_info(self):
+        """AmplTMINLP::read_priorities (src/Interfaces/Ampl/BonAmplTMINLP.cpp:215-252): variable suffixes priority (stored
+        as 9999 - value: Cbc branches on the LOWEST number first), direction, upPseudocost / downPseudocost (one given:
+        used for both).  Entries are None when the suffix is absent; unlisted variables have suffix value 0."""
+        def dense(name, dtype):
+            tab = self.suffixes.get((0, name))
+            if tab is None:
+                return None
+            a = np.zeros(self.n, dtype)
+            for i, v in tab.items():
+                a[i] = v
+            return a
+        pri = dense("priority", np.int64)
+        up, dn = dense("upPseudocost", float), dense("downPseudocost", float)
+        if up is not None and dn is None:
+            dn = up
+        elif dn is not None and up is None:
+            up = dn
+        return dict(priorities=None if pri is None else 9999 - pri, directions=dense("direction", np.int64), up=up, down=dn)
 
     def _next(self):
         s = self._l[self._p]

@@ -134,3 +134,27 @@ def test_provider_error_is_not_a_fathomed_node():
     with pytest.raises(RuntimeError):
         bb.run_callback(m, broken, number_strong_branch=4)
     assert calls["n"] >= 1
+
+
+def test_priorities_restrict_the_candidates(oracle_ipm):
+    """With branching priorities only the fractional integers of the best (lowest) level are strong-branching candidates
+    (setupList, BonChooseVariable.cpp:330-352): giving one variable the best level makes the first batch its two children."""
+    m = I.syn_miqcp(12, 6, 3, 3, 1)
+    solve = _oracle_solver(m, oracle_ipm)
+    batches = []
+
+    def rec(XL, XU, x0):
+        batches.append((XL.copy(), XU.copy()))
+        return solve(XL, XU, x0)
+    ref = bb.run_callback(m, solve, number_strong_branch=6)
+    root = solve(np.atleast_2d(m.xl), np.atleast_2d(m.xu), m.x0)["x"][0]
+    frac = [j for j in range(6) if abs(root[j] - round(root[j])) > 1e-6]
+    assert len(frac) >= 2
+    pri = np.full(12, 1000, np.int32)
+    pri[frac[-1]] = 1
+    r = bb.run_callback(m, rec, number_strong_branch=6, priorities=pri)
+    first = next(b for b in batches if b[0].shape[0] > 1)
+    assert first[0].shape[0] == 2                                  # one candidate, two children
+    changed = np.flatnonzero((first[0] != m.xl).any(0) | (first[1] != m.xu).any(0))
+    assert list(changed) == [frac[-1]]
+    assert r["status"] == 0 and r["best_obj"] == pytest.approx(ref["best_obj"], rel=1e-6)   # same optimum, other tree

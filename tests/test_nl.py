@@ -139,3 +139,22 @@ def test_defined_variables_eval_on_device(bnlp_lib):
             fd = (_defvar_values(x + e)[0] - _defvar_values(x - e)[0]) / (2 * h)
             assert r["gradf"][b, j] == pytest.approx(fd, rel=1e-6, abs=1e-7)
     eng.close()
+
+
+def test_variable_suffixes_branching_info(bnlp_lib):
+    """AmplTMINLP::read_priorities (BonAmplTMINLP.cpp:215-252): priority -> 9999 - value, direction, one pseudo-cost suffix
+    serves both ways; constraint / SOS suffixes are skipped.  tests/golden/nl_samples/mytoy_suffixes.nl = the reference's
+    mytoy.nl with hand-written S segments (the reference ships no .nl with suffixes)."""
+    txt = open(os.path.join(G, "nl_samples", "mytoy_suffixes.nl")).read()
+    p = _problem(txt)
+    b = p.branching_info()
+    assert list(b["priorities"]) == [9998, 9999, 9992, 9994]
+    assert list(b["directions"]) == [0, 0, 1, -1]
+    assert list(b["up"]) == [0, 0, 0.5, 1.25] and list(b["down"]) == [0, 0, 0.5, 1.25]
+    o = NlModel(txt).branching_info()
+    assert list(o["priorities"]) == list(b["priorities"]) and list(o["directions"]) == list(b["directions"])
+    assert list(o["up"]) == list(b["up"]) and list(o["down"]) == list(b["down"])
+    # the model itself is unchanged by the suffixes
+    q = _problem(open(os.path.join(G, "mytoy.nl")).read())
+    assert (p.n, p.m, p.nnz_jac, p.nnz_hess) == (q.n, q.m, q.nnz_jac, q.nnz_hess)
+    assert q.branching_info() == dict(priorities=None, directions=None, up=None, down=None)
