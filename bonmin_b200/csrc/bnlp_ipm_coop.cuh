@@ -350,6 +350,9 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
 
   // ---- per-child state
   int state = CS_NEED_CHILD;
+  long long seg_t0 = 0;   // (timers build) start and start state of the per-child segment between barriers 4 and 1
+  int seg_state = 0;
+  (void)seg_t0; (void)seg_state;
   int child = -1;
 #define xl (A.XL + (size_t)child * n)
 #define xu (A.XU + (size_t)child * n)
@@ -387,8 +390,8 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
   long long nfact = 0;
   // timer build: counters live in shared memory and only thread 0 touches them, so the instrumented kernel keeps the
   // register allocation (and spills) of the production one.  [0..9] phases, [10..13] barrier waits, [16..27] sub-phases
-  __shared__ long long s_tm[TIMERS ? 36 : 1];
-  if constexpr (TIMERS) { if (threadIdx.x < 36) s_tm[threadIdx.x] = 0; }
+  __shared__ long long s_tm[TIMERS ? 44 : 1];
+  if constexpr (TIMERS) { if (threadIdx.x < 44) s_tm[threadIdx.x] = 0; }
   long long dbg_t0 = 0;
 #define D2_START() do { if constexpr (TIMERS) { if (tid == 0) dbg_t0 = clock64(); } } while (0)
 #define D2_MARK(i) do { if constexpr (TIMERS) { __syncthreads(); if (tid == 0) { long long t_ = clock64(); s_tm[16 + (i)] += t_ - dbg_t0; dbg_t0 = t_; } } } while (0)
@@ -781,6 +784,15 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
     if (state != CS_ITER)
       for (int j = tid; j < ldd; j += IPM_NT) __stcg(CB.xd + (size_t)cta * ldd + j, (state == CS_INIT && j < n) ? x[j] : 0.0);
     if (tid == 0) atomicAdd(&CB.idle_cnt[step & 1], state == CS_IDLE ? 1 : 0);
+    if constexpr (TIMERS) {      // length of the per-child segment between barrier 4 and barrier 1, by the state it started in
+      if (tid == 0 && step > 0) {
+        const long long dt = clock64() - seg_t0;
+        const int bkt = seg_state == CS_INIT ? 0 : seg_state == CS_ITER ? 1 : 2;
+        s_tm[31 + 3 * bkt] += dt; s_tm[32 + 3 * bkt] += 1; if (dt > s_tm[33 + 3 * bkt]) s_tm[33 + 3 * bkt] = dt;
+        if (bkt == 1 && dt > 120000) s_tm[40] += 1;
+        if (bkt == 1 && dt > 160000) s_tm[41] += 1;
+      }
+    }
     PH_MARK(0);
     grid.sync();   // ------------------------------------------------------------------------------ barrier 1
     PH_MARKB(0);
@@ -1046,6 +1058,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
     PH_MARK(5);
     grid.sync();   // ------------------------------------------------------------------------------ barrier 4
     PH_MARKB(3);
+    if constexpr (TIMERS) { if (tid == 0) { seg_t0 = clock64(); seg_state = state; } }
 
     // =================================================================== E: initialisation tail / line search + update
     if (state == CS_INIT) {
@@ -1185,8 +1198,8 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
   }
   if constexpr (TIMERS) {
     if (tid == 0 && (cta % 37) == 0)
-      printf("[dbg cta %d] barrier waits while iterating: b1 %lld b2 %lld b3 %lld b4 %lld | top: rows %lld zeroH %lld vars %lld, chunk stage %lld J'v %lld syrk %lld | C: backsolve %lld dots %lld ftb/mu %lld dir %lld | chol3: diag0 %lld trsm %lld col8+diag %lld trailing+diag %lld (cycles, whole launch)\n",
-             cta, s_tm[10], s_tm[11], s_tm[12], s_tm[13], s_tm[16], s_tm[17], s_tm[19], s_tm[24], s_tm[25], s_tm[26], s_tm[20], s_tm[21], s_tm[22], s_tm[23], s_tm[27], s_tm[28], s_tm[29], s_tm[30]);
+      printf("[dbg cta %d] barrier waits while iterating: b1 %lld b2 %lld b3 %lld b4 %lld | top: rows %lld zeroH %lld vars %lld, chunk stage %lld J'v %lld syrk %lld | C: backsolve %lld dots %lld ftb/mu %lld dir %lld | chol3: diag0 %lld trsm %lld col8+diag %lld trailing+diag %lld (cycles, whole launch) || segment b4->b1 by start state: INIT avg %lld n %lld max %lld | ITER avg %lld n %lld max %lld (>120k: %lld, >160k: %lld) | other avg %lld n %lld max %lld\n",
+             cta, s_tm[10], s_tm[11], s_tm[12], s_tm[13], s_tm[16], s_tm[17], s_tm[19], s_tm[24], s_tm[25], s_tm[26], s_tm[20], s_tm[21], s_tm[22], s_tm[23], s_tm[27], s_tm[28], s_tm[29], s_tm[30], s_tm[31] / (s_tm[32] ? s_tm[32] : 1), s_tm[32], s_tm[33], s_tm[34] / (s_tm[35] ? s_tm[35] : 1), s_tm[35], s_tm[36], s_tm[40], s_tm[41], s_tm[37] / (s_tm[38] ? s_tm[38] : 1), s_tm[38], s_tm[39]);
     if (A.phase_cycles && tid == 0)
       for (int q = 0; q < 10; ++q) atomicAdd((unsigned long long *)&A.phase_cycles[q], (unsigned long long)s_tm[q]);
   }
