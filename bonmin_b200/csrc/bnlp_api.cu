@@ -667,6 +667,19 @@ extern "C" int bnlp_solve_batch(bnlp_engine *E, int B, const double *XL, const d
   return collect_batch(E, B, per, OBJ, STATUS, ITERS, X, G, DUALS);
 }
 
+// Page-lock a caller-owned host buffer that is passed to the batch calls again and again (cut buffers, bound arrays):
+// copies to and from it then run as DMA at PCIe speed instead of through the driver's staging buffer.
+extern "C" int bnlp_host_register(void *p, size_t bytes) {
+  if (!p || !bytes) return -1;
+  CK(cudaHostRegister(p, bytes, cudaHostRegisterDefault));
+  return 0;
+}
+extern "C" int bnlp_host_unregister(void *p) {
+  if (!p) return -1;
+  CK(cudaHostUnregister(p));
+  return 0;
+}
+
 extern "C" int bnlp_engine_stats(const bnlp_engine *E, long long *iterations, long long *factorisations, double *device_ms) {
   if (!E) return -1;
   if (iterations) *iterations = E->last_iters;

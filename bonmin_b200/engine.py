@@ -59,7 +59,17 @@ EXPORTS = ["bnlp_last_error", "bnlp_problem_from_nl", "bnlp_problem_from_tape", 
            "bnlp_resolve_cb", "bnlp_resolve_engine", "bnlp_problem_fp", "bnlp_solve_children", "bnlp_bb_run_cb3",
            "bnlp_write_node_files", "bnlp_read_bounds_file", "bnlp_read_start_file", "bnlp_write_batch_replay",
            "bnlp_read_batch_replay_header", "bnlp_read_batch_replay", "bnlp_sol_status", "bnlp_nl_header_options",
-           "bnlp_write_sol", "bnlp_write_plain_sol", "bnlp_problem_cut_strengthening", "bnlp_problem_branching_info"]
+           "bnlp_write_sol", "bnlp_write_plain_sol", "bnlp_problem_cut_strengthening", "bnlp_problem_branching_info", "bnlp_host_register", "bnlp_host_unregister"]
+
+
+def pin_array(a):
+    """Page-lock a numpy array for its lifetime (bnlp_host_register now, bnlp_host_unregister when it is collected)."""
+    import weakref
+    ptr = a.ctypes.data
+    if a.nbytes and lib().bnlp_host_register(c_void(ptr), a.nbytes) == 0:
+        weakref.finalize(a, lambda p=ptr: lib().bnlp_host_unregister(c_void(p)))
+        return True
+    return False
 
 
 def lib():
@@ -78,6 +88,8 @@ def lib():
         L.bnlp_problem_cut_strengthening.restype = c_void
         L.bnlp_problem_cut_strengthening.argtypes = [c_void, c_int, ctypes.c_char_p, ctypes.c_size_t]
         L.bnlp_problem_branching_info.argtypes = [c_void] * 5
+        L.bnlp_host_register.argtypes = [c_void, ctypes.c_size_t]
+        L.bnlp_host_unregister.argtypes = [c_void]
         L.bnlp_problem_free.argtypes = [c_void]
         L.bnlp_problem_sizes.argtypes = [c_void, P_int, P_int, P_int, P_int]
         L.bnlp_problem_info.argtypes = [c_void] + [c_void] * 11
@@ -266,20 +278,30 @@ class Engine:
         if rc != 0:
             raise BnlpError(f"engine error {rc}: {_err()}")
 
-    def solve_batch(self, XL, XU, X0, want_x=True, want_g=True, want_duals=True):
-        """B x TNLPSolver::OptimizeTNLP with host buffers (copies inside the call)."""
+    def solve_batch(self, XL, XU, X0, want_x=True, want_g=True, want_duals=True, out=None, pin=False):
+        """B x TNLPSolver::OptimizeTNLP with host buffers (copies inside the call).  `out`: the dict of an earlier call
+        with the same B and outputs, whose arrays are reused; `pin`: page-lock freshly allocated result arrays (for a
+        caller that keeps them with `out=`)."""
         n, m = self.n, self.m
         XL = _d(np.atleast_2d(XL))
         XU = _d(np.atleast_2d(XU))
         B = XL.shape[0]
         X0 = _d(X0)
         per_child = int(X0.ndim == 2)
-        OBJ = np.zeros(B)
-        ST = np.zeros(B, np.int32)
-        IT = np.zeros(B, np.int32)
-        X = np.zeros((B, n)) if want_x else None
-        G = np.zeros((B, m)) if want_g else None
-        D = np.zeros((B, 2 * n + m)) if want_duals else None
+        if (out is not None and len(out["obj"]) == B and (out["x"] is not None) == want_x and (out["g"] is not None) == want_g
+                and (out["duals"] is not None) == want_duals):
+            OBJ, ST, IT, X, G, D = (out[k] for k in ("obj", "status", "iters", "x", "g", "duals"))
+        else:
+            OBJ = np.zeros(B)
+            ST = np.zeros(B, np.int32)
+            IT = np.zeros(B, np.int32)
+            X = np.zeros((B, n)) if want_x else None
+            G = np.zeros((B, m)) if want_g else None
+            D = np.zeros((B, 2 * n + m)) if want_duals else None
+            if pin:
+                for a in (OBJ, ST, IT, X, G, D):
+                    if a is not None:
+                        pin_array(a)
         self._ck(lib().bnlp_solve_batch(self.h, B, _vp(XL), _vp(XU), _vp(X0), per_child, _vp(OBJ), _vp(ST), _vp(IT),
                                         _vp(X), _vp(G), _vp(D)))
         return dict(obj=OBJ, status=ST, iters=IT, x=X, g=G, duals=D)
@@ -336,10 +358,11 @@ class Engine:
                                        _vp(H)))
         return dict(f=F, g=G, gradf=GF, jac=J, hess=H)
 
-    def oa_batch(self, X, DUALS=None, XL=None, XU=None, X2=None, theta=0.0, get_obj=0, tols=None, out=None):
+    def oa_batch(self, X, DUALS=None, XL=None, XU=None, X2=None, theta=0.0, get_obj=0, tols=None, out=None, pin=False):
         """B x OsiTMINLPInterface::getOuterApproximation -> CSR rows (see include/bnlp.h).  `out`: a dict returned by an
         earlier call with the same B, whose arrays are reused (a caller in a loop keeps its cut buffers: allocating and
-        first-touching ~300 MB per call costs more than the whole device side)."""
+        first-touching ~300 MB per call costs more than the whole device side).  `pin`: page-lock freshly allocated cut
+        buffers (bnlp_host_register; released when the arrays are garbage-collected) — for buffers that are reused."""
         n = self.n
         X = _d(np.atleast_2d(X))
         B = X.shape[0]
@@ -356,6 +379,9 @@ class Engine:
             LB = np.zeros(nrows)
             UB = np.zeros(nrows)
             src = np.zeros(nrows, np.int32)
+            if pin:
+                for a in (col, val):
+                    pin_array(a)
         if XL is None or XU is None:
             info = self.problem.info()
         XL = _d(info["xl"] if XL is None else XL)

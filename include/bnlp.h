@@ -139,6 +139,11 @@ int bnlp_problem_branching_info(const bnlp_problem *, int *priorities, int *dire
 bnlp_engine *bnlp_engine_create(const bnlp_problem *, const int *device_ids, int ndev, const bnlp_options *);
 void bnlp_engine_free(bnlp_engine *);
 
+/* Optional: page-lock a caller-owned host buffer that is handed to the batch calls repeatedly (cudaHostRegister /
+ * cudaHostUnregister): the copies inside the calls then run as DMA.  The caller unregisters before freeing the buffer. */
+int bnlp_host_register(void *p, size_t bytes);
+int bnlp_host_unregister(void *p);
+
 /* B x {eval_f, eval_grad_f, eval_g, eval_jac_g values, eval_h values} (BonTMINLP.hpp:268-315).
  * X: B x n.  LAM: B x m or NULL (then 0), sigma = obj_factor.  Outputs (any may be NULL):
  * F: B, G: B x m, GRADF: B x n, JVAL: B x nnz_jac, HVAL: B x nnz_hess.  Host pointers. */

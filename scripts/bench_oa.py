@@ -13,8 +13,8 @@ def run(B=1024, reps=5, cpu_points=8, model=None):
     rng = np.random.default_rng(5)
     X = np.clip(m.x0 + rng.uniform(-0.3, 0.3, size=(B, m.n)), m.xl, m.xu)
     X[:, m.vtype != 0] = np.round(X[:, m.vtype != 0])
-    r = eng.oa_batch(X, None, m.xl, m.xu, get_obj=1)          # warm-up (allocations)
-    r = eng.oa_batch(X, None, m.xl, m.xu, get_obj=1)
+    r = eng.oa_batch(X, None, m.xl, m.xu, get_obj=1, pin=True)   # warm-up (allocations; the reused cut buffers are page-locked)
+    r = eng.oa_batch(X, None, m.xl, m.xu, get_obj=1, out=r)
     ts = []
     for _ in range(reps):            # the caller keeps its cut buffers (out=r), as an LP-side consumer would
         t0 = time.perf_counter()

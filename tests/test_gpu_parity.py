@@ -365,3 +365,28 @@ def test_largest_supported_model(bnlp_lib, oracle_ipm):
     with pytest.raises(BnlpError, match="512"):
         big.solve_batch(XL[:, :1].repeat(513, 1), XU[:, :1].repeat(513, 1), np.zeros(513))
     big.close()
+
+
+def test_reused_and_pinned_result_buffers(bnlp_lib):
+    """solve_batch(out=, pin=) and oa_batch(out=, pin=): reused, page-locked result arrays hold the same results."""
+    m = I.syn_miqcp(40, 20, 8, 8, 3)
+    eng = _engine(m)
+    xs = eng.solve_batch(m.xl, m.xu, m.x0)["x"][0]
+    XL, XU = I.c3_children(m, xs, 64)
+    a = eng.solve_batch(XL, XU, xs)
+    r = eng.solve_batch(XL, XU, xs, pin=True)
+    ids = {k: id(v) for k, v in r.items()}
+    r["obj"][:] = 0
+    r2 = eng.solve_batch(XL, XU, xs, out=r)
+    assert all(id(r2[k]) == ids[k] for k in ids)
+    for k in ("obj", "status", "iters", "x", "g", "duals"):
+        assert np.array_equal(a[k], r2[k]), k
+    X = np.clip(xs + 0.1, m.xl, m.xu)[None, :].repeat(8, 0)
+    c0 = eng.oa_batch(X, None, m.xl, m.xu, get_obj=1)
+    c1 = eng.oa_batch(X, None, m.xl, m.xu, get_obj=1, pin=True)
+    c2 = eng.oa_batch(X, None, m.xl, m.xu, get_obj=1, out=c1)
+    for k in ("row_start", "src_row", "lb", "ub"):
+        assert np.array_equal(c0[k], c2[k]), k
+    nnz = c0["row_start"][-1]
+    assert np.array_equal(c0["col"][:nnz], c2["col"][:nnz]) and np.array_equal(c0["val"][:nnz], c2["val"][:nnz])
+    del r, r2, c1, c2        # finalizers unregister the pages
