@@ -204,3 +204,178 @@ def run_oa(provider, integer_tolerance=1e-6, cutoff_increment=1e-5, gap_tol=1e-9
             log(f"pass {out['passes']}: master {bound:.6f} ub {ub:.6f} cuts +{new}")
     out["seconds"] = time.perf_counter() - t0
     return out
+
+
+# ------------------------------------------------------------------------------------------ single-tree generators
+def _lp_solve(ncols, rows, obj, obj_offset, lb, ub, cutoff):
+    """LP relaxation at a node (what lp->resolve() is to the generators below); (feasible, x, value)."""
+    st, x, val = _solve_master(ncols, rows, obj, obj_offset, lb, ub, np.zeros(ncols, int), 1e100)
+    return (st == 0 and val < cutoff), x, val
+
+
+def feasibility_check(provider, lp, col_lb, col_ub, x_lp, cutoff, integer_tolerance=1e-6, cutoff_increment=1e-5,
+                      add_only_violated=False, max_passes=50):
+    """OaFeasibilityChecker::performOa (src/Algorithms/OaGenerators/BonOaFeasChecker.cpp:38-135): called when the node LP
+    has an integer solution.  Loop: fix the integers at the LP values (fixIntegers), solve NLP(y) on the engine, on
+    success update incumbent and cutoff (post_nlp_solve), linearise at the NLP point (getOuterApproximation, getObj = 1;
+    against the LP point only when add_only_violated), install the cuts in the node LP, re-solve it; go on while the LP
+    stays feasible below the cutoff, integer, and different on the integers from the NLP point.
+    lp: dict(rows, obj, obj_offset, ncols) — rows is extended in place (the cuts are global).  Returns dict(cutoff,
+    incumbent (obj, x) or None, cuts, nlp_solves, fathomed = the node can be cut off, x_lp = last LP point or None)."""
+    P = provider
+    n = P.n
+    ints = np.flatnonzero(np.asarray(P.vtype) != 0)
+    out = dict(cutoff=cutoff, incumbent=None, cuts=0, nlp_solves=0, fathomed=False, x_lp=x_lp)
+    is_integer, feasible = True, True
+    passes = 0
+    while is_integer and feasible and passes < max_passes:
+        passes += 1
+        XL, XU = np.array(P.xl, float), np.array(P.xu, float)
+        XL[ints] = XU[ints] = np.round(x_lp[ints])
+        r = P.solve(XL[None, :], XU[None, :], x_lp[:n])
+        out["nlp_solves"] += 1
+        xs = r["x"][0]
+        if r["status"][0] in (1, 2) and r["obj"][0] < out["cutoff"]:
+            ub = float(r["obj"][0])
+            if out["incumbent"] is None or ub < out["incumbent"][0]:
+                out["incumbent"] = (ub, xs.copy())
+            out["cutoff"] = ub * (1 - cutoff_increment) if ub > 0 else ub * (1 + cutoff_increment)
+        cuts = P.oa(xs[None, :], X2=(x_lp[:n][None, :] if add_only_violated else None))
+        cuts = [c for c in cuts if not (c[0] == P.m and lp["ncols"] == n)]
+        lp["rows"].extend(cuts)
+        out["cuts"] += len(cuts)
+        feasible, x_new, val = _lp_solve(lp["ncols"], lp["rows"], lp["obj"], lp["obj_offset"], col_lb, col_ub, out["cutoff"])
+        is_integer = False
+        if feasible:
+            changed = np.abs(xs[ints] - x_new[ints]).max(initial=0.0) > 0.1          # isDifferentOnIntegers(.., 0.1, ..)
+            if changed:
+                is_integer = np.abs(x_new[ints] - np.round(x_new[ints])).max(initial=0.0) <= integer_tolerance
+            else:
+                out["fathomed"] = True           # same integers as the NLP point: milpBound = 1e200 (:115-119)
+            x_lp = x_new
+            out["x_lp"] = x_new
+        else:
+            out["fathomed"] = True
+            out["x_lp"] = None
+    return out
+
+
+def nlp_optim_cuts(provider, node_lb, node_ub, x_lp, add_only_violated=False):
+    """OaNlpOptim::generateCuts (src/Algorithms/OaGenerators/BonOaNlpOptim.cpp:63-173): the NLP relaxation of the NODE
+    (integer columns take the node LP's bounds), OA cuts at its solution (getObj = 1), and the solution itself when it
+    happens to be integer (1e-7).  An abandoned / iteration-limited NLP is an error, as in the reference.  Returns
+    dict(cuts, solution (obj, x) or None, status, obj)."""
+    P = provider
+    n = P.n
+    ints = np.flatnonzero(np.asarray(P.vtype) != 0)
+    XL, XU = np.array(P.xl, float), np.array(P.xu, float)
+    XL[ints], XU[ints] = np.asarray(node_lb)[ints], np.asarray(node_ub)[ints]
+    r = P.solve(XL[None, :], XU[None, :], x_lp[:n])
+    st, xs = int(r["status"][0]), r["x"][0]
+    if st in (-3, -2):            # isAbandoned() || isIterationLimitReached(): "Unsolved NLP ... exit"
+        raise RuntimeError("Unsolved NLP ... exit")
+    cuts = provider.oa(xs[None, :], X2=(x_lp[:n][None, :] if add_only_violated else None))
+    sol = None
+    if st in (1, 2) and np.abs(xs[ints] - np.floor(xs[ints] + 0.5)).max(initial=0.0) <= 1e-7:
+        sol = (float(r["obj"][0]), xs.copy())
+    return dict(cuts=cuts, solution=sol, status=st, obj=float(r["obj"][0]))
+
+
+def nlp_optim_wanted(level, solves_per_level=1.0, max_depth=10, rng=None):
+    """The depth test of OaNlpOptim::generateCuts (:84-92): never below max_depth, else with probability
+    2^-level * solves_per_level (always when solves_per_level >= 1e10)."""
+    if level > max_depth:
+        return False
+    if solves_per_level >= 1e10:
+        return True
+    rnd = (rng or np.random.default_rng()).random()
+    return 2.0 ** (-level) * solves_per_level > rnd
+
+
+def run_qg(provider, integer_tolerance=1e-6, cutoff_increment=1e-5, node_limit=100000, nlp_solves_per_level=0.0,
+           nlp_max_depth=10, seed=0, time_limit=1e10, log=None):
+    """A single-tree LP/NLP-based branch and bound in the manner of B-QG (nlp_solves_per_level = 0) and B-Hyb (> 0):
+    LP relaxation from extractLinearRelaxation at the root NLP optimum, best-bound search branching on the most
+    fractional integer, OaFeasibilityChecker at integer LP points, OaNlpOptim at nodes by the depth rule.  Host control
+    flow (the reference's is Cbc + Cgl generators, BonBonminSetup.cpp:478-620); the LPs are solved by HiGHS; NLPs, the
+    initial LP and every linearisation come from the provider (the engine in the product).  Returns dict(status 0 optimal /
+    1 infeasible / 2 limit, best_obj, best_x, nodes, nlp_solves, cuts, seconds)."""
+    import heapq
+    t0 = time.perf_counter()
+    P = provider
+    n = P.n
+    rng = np.random.default_rng(seed)
+    ints = np.flatnonzero(np.asarray(P.vtype) != 0)
+    out = dict(status=2, best_obj=1e100, best_x=None, nodes=0, nlp_solves=1, cuts=0)
+    root = P.solve(np.asarray(P.xl)[None, :], np.asarray(P.xu)[None, :], P.x0)
+    if root["status"][0] not in (1, 2):
+        out["status"] = 1 if root["status"][0] == 3 else 2
+        out["seconds"] = time.perf_counter() - t0
+        return out
+    ext = P.extract(root["x"][0], root["duals"][0])
+    ncols = n + (1 if ext["has_alpha"] else 0)
+    obj = np.zeros(ncols)
+    obj[:len(ext["obj"])] = ext["obj"]
+    lp = dict(rows=list(ext["rows"]), obj=obj, obj_offset=ext["obj_offset"], ncols=ncols)
+    lb0 = np.concatenate([P.xl, [-DMAX]])[:ncols]
+    ub0 = np.concatenate([P.xu, [DMAX]])[:ncols]
+    cutoff = 1e100
+    heap, tick = [(float(root["obj"][0]), 0, 0, lb0, ub0)], 1
+    while heap:
+        if out["nodes"] >= node_limit or time.perf_counter() - t0 > time_limit:
+            break
+        bound, _, level, lb, ub = heapq.heappop(heap)
+        if bound >= cutoff:
+            continue
+        out["nodes"] += 1
+        feas, x, val = _lp_solve(ncols, lp["rows"], lp["obj"], lp["obj_offset"], lb, ub, cutoff)
+        if not feas:
+            continue
+        if nlp_solves_per_level > 0 and nlp_optim_wanted(level, nlp_solves_per_level, nlp_max_depth, rng):
+            g = nlp_optim_cuts(P, lb, ub, x)
+            out["nlp_solves"] += 1
+            new = [c for c in g["cuts"] if not (c[0] == P.m and ncols == n)]
+            lp["rows"].extend(new)
+            out["cuts"] += len(new)
+            if g["status"] == 3:
+                continue                                   # the node's NLP relaxation is infeasible
+            if g["solution"] and g["solution"][0] < out["best_obj"]:
+                out["best_obj"], out["best_x"] = g["solution"]
+                cutoff = min(cutoff, out["best_obj"] * (1 - cutoff_increment) if out["best_obj"] > 0 else out["best_obj"] * (1 + cutoff_increment))
+            feas, x, val = _lp_solve(ncols, lp["rows"], lp["obj"], lp["obj_offset"], lb, ub, cutoff)
+            if not feas:
+                continue
+        frac = np.abs(x[ints] - np.round(x[ints]))
+        if frac.max(initial=0.0) <= integer_tolerance:
+            f = feasibility_check(P, lp, lb, ub, x, cutoff, integer_tolerance, cutoff_increment)
+            out["nlp_solves"] += f["nlp_solves"]
+            out["cuts"] += f["cuts"]
+            cutoff = min(cutoff, f["cutoff"])
+            if f["incumbent"] and f["incumbent"][0] < out["best_obj"]:
+                out["best_obj"], out["best_x"] = f["incumbent"]
+            if f["fathomed"] or f["x_lp"] is None:
+                continue
+            x = f["x_lp"]                                   # the LP moved to a fractional point: branch on it
+            feas, x, val = _lp_solve(ncols, lp["rows"], lp["obj"], lp["obj_offset"], lb, ub, cutoff)
+            if not feas:
+                continue
+            frac = np.abs(x[ints] - np.round(x[ints]))
+            if frac.max(initial=0.0) <= integer_tolerance:
+                heapq.heappush(heap, (val, tick, level, lb, ub)); tick += 1      # integer again: re-examine the node
+                continue
+        j = ints[int(np.argmax(frac))]
+        for way in (0, 1):
+            l2, u2 = lb.copy(), ub.copy()
+            if way == 0:
+                u2[j] = np.floor(x[j])
+            else:
+                l2[j] = np.ceil(x[j])
+            heapq.heappush(heap, (val, tick, level + 1, l2, u2)); tick += 1
+        if log:
+            log(f"node {out['nodes']}: lp {val:.6f} cutoff {cutoff:.6f} rows {len(lp['rows'])}")
+    else:
+        out["status"] = 0 if out["best_obj"] < 1e99 else 1
+    if not heap and out["status"] == 2 and out["nodes"] < node_limit:
+        out["status"] = 0 if out["best_obj"] < 1e99 else 1
+    out["seconds"] = time.perf_counter() - t0
+    return out

@@ -105,3 +105,41 @@ def test_ecp_engine_matches_oracle(bnlp_lib, oracle_ipm):
     assert g["rounds"] == c["rounds"] and g["cuts"] == c["cuts"]
     assert g["obj"] == pytest.approx(c["obj"], rel=1e-8) and g["violation"] == pytest.approx(c["violation"], rel=1e-6, abs=1e-9)
     eng.close()
+
+
+@pytest.mark.parametrize("mk", [lambda: I.mytoy(), lambda: I.syn_miqcp(12, 6, 3, 3, 4),
+                                lambda: I.syn_cvx_minlp(16, 6, 3, 5, 2)])
+@pytest.mark.parametrize("hyb", [0.0, 1.0])
+def test_single_tree_qg_and_hyb_reach_the_bb_optimum(oracle_ipm, mk, hyb):
+    """OaFeasibilityChecker (B-QG) and OaNlpOptim (B-Hyb, nlp_solves_per_level > 0) inside a single LP tree: the same MINLP
+    optimum as B-BB."""
+    m = mk()
+    r = oa.run_qg(OracleProvider(m, oracle_ipm), nlp_solves_per_level=hyb)
+    b = _bb_opt(m, oracle_ipm, number_strong_branch=6)
+    assert r["status"] == b["status"] == 0
+    assert r["best_obj"] == pytest.approx(b["best_obj"], rel=2e-5, abs=2e-5)
+    xi = r["best_x"][np.asarray(m.vtype) != 0]
+    assert np.abs(xi - np.round(xi)).max() <= 1e-6
+    assert r["cuts"] > 0 and r["nlp_solves"] >= 2
+
+
+def test_nlp_optim_depth_rule():
+    rng = np.random.default_rng(0)
+    assert not oa.nlp_optim_wanted(11, 1.0, 10, rng)                 # below max depth: never
+    assert oa.nlp_optim_wanted(30, 1e10, 100, rng)                    # "always"
+    assert oa.nlp_optim_wanted(0, 1.0, 10, rng)                       # 2^0 * 1 > rand in [0, 1)
+    hits = sum(oa.nlp_optim_wanted(3, 1.0, 10, rng) for _ in range(4000))
+    assert 400 < hits < 600                                           # probability 1/8
+
+
+@pytest.mark.gpu
+def test_single_tree_engine_matches_oracle(bnlp_lib, oracle_ipm):
+    from bonmin_b200.engine import Engine, Problem
+    for m in (I.mytoy(), I.syn_miqcp(12, 6, 3, 3, 4), I.syn_cvx_minlp(16, 6, 3, 5, 2)):
+        eng = Engine(Problem.from_model(m))
+        for hyb in (0.0, 1.0):
+            g = oa.run_qg(oa.EngineProvider(eng), nlp_solves_per_level=hyb)
+            c = oa.run_qg(OracleProvider(m, oracle_ipm), nlp_solves_per_level=hyb)
+            assert g["status"] == c["status"] == 0
+            assert g["best_obj"] == pytest.approx(c["best_obj"], rel=1e-6, abs=1e-8)
+        eng.close()
