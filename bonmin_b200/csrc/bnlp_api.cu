@@ -481,8 +481,11 @@ static int launch_ipm(bnlp_engine *E, Device &D, int B, const double *dXL, const
   int ctas = E->opt.ctas_per_device > 0 ? E->opt.ctas_per_device : D.sms;
   if (!E->coop_ok) ctas = std::min(ctas, B);   // the cooperative kernel keeps every SM for its shared passes
   // small models: two 256-thread CTAs per SM interleave two children's latency chains (+50 % at C2) — worth it only when
-  // there are children for all of them; a strong-branching batch of one node keeps the 512-thread CTAs
-  const bool use256 = E->coop256 && E->opt.ctas_per_device <= 0 && B >= 2 * D.sms;
+  // the batch is clearly larger than one child per SM (measured at C2, scripts/dev_256_threshold.py: 149 children 1.82 ms
+  // with 512 threads vs 2.07 ms, 200 children 2.70 vs 2.16 ms); a strong-branching batch of one node keeps the
+  // 512-thread CTAs
+  static const int min_b256 = getenv("BNLP_COOP256_MIN_B") ? atoi(getenv("BNLP_COOP256_MIN_B")) : 0;   // (tuning aid)
+  const bool use256 = E->coop256 && E->opt.ctas_per_device <= 0 && B >= (min_b256 > 0 ? min_b256 : D.sms + D.sms / 4);
   if (use256) ctas = 2 * D.sms;
   if (D.ws.reserve((size_t)ctas * E->ws_doubles)) { set_err("workspace allocation failed"); return -1; }
   CK(cudaMemsetAsync(D.queue.p, 0, sizeof(int), stream));
