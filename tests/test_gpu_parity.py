@@ -390,3 +390,28 @@ def test_reused_and_pinned_result_buffers(bnlp_lib):
     nnz = c0["row_start"][-1]
     assert np.array_equal(c0["col"][:nnz], c2["col"][:nnz]) and np.array_equal(c0["val"][:nnz], c2["val"][:nnz])
     del r, r2, c1, c2        # finalizers unregister the pages
+
+
+def test_two_devices_in_one_process_match_one_device(bnlp_lib):
+    """Engine over two devices (contiguous child shards, no data-path collective): same bits as one device, for both
+    batch forms and for a batch large enough to select the 256-thread kernel on every device (its shared-memory opt-in is
+    per device).  Skipped on a single-GPU box."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from bonmin_b200.engine import Engine, Problem
+    m = I.syn_miqcp(100, 50, 20, 20, 20261019)
+    p = Problem.from_model(m)
+    e1, e2 = Engine(p), Engine(p, devices=[0, 1])
+    xs = e1.solve_batch(m.xl, m.xu, m.x0)["x"][0]
+    for B in (64, 801):
+        XL, XU = I.c3_children(m, xs, B)
+        a, b = e1.solve_batch(XL, XU, xs), e2.solve_batch(XL, XU, xs)
+        for k in ("obj", "status", "iters", "x", "g", "duals"):
+            assert np.array_equal(a[k], b[k]), (B, k)
+    ints = np.flatnonzero(np.asarray(m.vtype) != 0)[:30]
+    cp = np.zeros(60, np.int32); cc = np.repeat(ints, 2).astype(np.int32); cw = np.tile([0, 1], 30).astype(np.int32)
+    cb = np.where(cw == 0, np.floor(xs[cc]), np.ceil(xs[cc]))
+    a = e1.solve_children(m.xl[None, :], m.xu[None, :], cp, cc, cw, cb, xs)
+    b = e2.solve_children(m.xl[None, :], m.xu[None, :], cp, cc, cw, cb, xs)
+    assert np.array_equal(a["obj"], b["obj"]) and np.array_equal(a["status"], b["status"]) and np.array_equal(a["x"], b["x"])
