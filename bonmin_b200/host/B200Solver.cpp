@@ -5,6 +5,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <fstream>
+#include <sstream>
 #include <queue>
 
 namespace Bonmin {
@@ -26,10 +28,69 @@ TNLPSolver::ReturnStatus B200Solver::OptimizeTNLP(TMINLP2TNLP &t) {
                         t.duals_sol.data());
   cpu_time_ = now_s() - t0;
   iterations_ = it;
-  if (rc != 0) { provider_errors_++; t.return_status = exception; return exception; }
+  if (rc != 0) { provider_errors_++; error_code_ = rc; t.return_status = exception; return exception; }
   t.obj_value = obj;
   t.return_status = (ReturnStatus)st;
   return (ReturnStatus)st;
+}
+
+bool B200Solver::Initialize(std::istream &is) {
+  std::string line;
+  while (std::getline(is, line)) {
+    const size_t h = line.find('#');
+    if (h != std::string::npos) line.erase(h);
+    std::istringstream ls(line);
+    std::string name, value;
+    if (!(ls >> name)) continue;
+    if (!(ls >> value)) return false;          // an option without a value is an error for Ipopt's reader too
+    if (name.rfind("bonmin.", 0) == 0) name.erase(0, 7);
+    bool found = false;
+    for (auto &kv : options_) if (kv.first == name) { kv.second = value; found = true; }
+    if (!found) options_.push_back({name, value});
+  }
+  if (const std::string *v = option("print_level")) default_log_level_ = log_level_ = atoi(v->c_str());
+  return true;
+}
+
+bool B200Solver::Initialize(std::string params_file) {
+  std::ifstream f(params_file);
+  if (!f) return true;                         // a missing options file is not an error (Ipopt: "no options file found")
+  return Initialize(f);
+}
+
+const std::string *B200Solver::option(const std::string &name) const {
+  for (auto &kv : options_) if (kv.first == name) return &kv.second;
+  return nullptr;
+}
+
+bool B200Solver::setWarmStart(const CoinWarmStart *ws, TMINLP2TNLP &tnlp) {   // BonIpoptSolver.cpp:369-401
+  if (!ws) return false;
+  if (ws->empty()) { disableWarmStart(); return true; }
+  if (ws->dualSize() > 0) { tnlp.setDualsInit(ws->dualSize(), ws->dual()); enableWarmStart(); }
+  else disableWarmStart();
+  if (ws->primalSize() != tnlp.n) return false;
+  tnlp.setxInit(ws->primalSize(), ws->primal());
+  return true;
+}
+
+CoinWarmStart *B200Solver::getUsedWarmStart(TMINLP2TNLP &tnlp) const {        // :347-356
+  if ((int)tnlp.x_init.size() < tnlp.n || tnlp.duals_init.empty()) return nullptr;
+  return new CoinWarmStart(tnlp.n, 2 * tnlp.n + tnlp.m, tnlp.x_init.data(), tnlp.duals_init.data());
+}
+
+CoinWarmStart *B200Solver::getWarmStart(TMINLP2TNLP &tnlp) const {            // :357-366: the last solution and its multipliers
+  if ((int)tnlp.x_sol.size() != tnlp.n) return new CoinWarmStart();
+  const bool have_duals = (int)tnlp.duals_sol.size() == 2 * tnlp.n + tnlp.m;
+  return new CoinWarmStart(tnlp.n, have_duals ? 2 * tnlp.n + tnlp.m : 0, tnlp.x_sol.data(), have_duals ? tnlp.duals_sol.data() : nullptr);
+}
+
+const std::string &B200Solver::UnsolvedB200Error::errorName() const {
+  static const std::string provider = "the batch-solve provider failed (see bnlp_last_error)", solver = "unrecoverable solver status";
+  return errorNum() > -100 && errorNum() < 0 ? solver : provider;
+}
+const std::string &B200Solver::UnsolvedB200Error::solverName() const {
+  static const std::string name = "B200 batched IPM";
+  return name;
 }
 
 std::shared_ptr<std::vector<double>> B200Solver::x_block(size_t cnt) {

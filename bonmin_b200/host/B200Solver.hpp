@@ -43,6 +43,37 @@ class B200Solver : public TNLPSolver {
   double CPUTime() override { return cpu_time_; }
   int IterationCount() override { return iterations_; }
   const std::string &solverName() const override { return name_; }
+  // --- the rest of the TNLPSolver contract (BonTNLPSolver.hpp:95-205)
+  // options: "name value" lines as in bonmin.opt / ipopt.opt; kept for inspection (tol and max_iter are fixed when the
+  // engine behind the BatchSolveFn is created, see bnlp_options)
+  bool Initialize(std::string params_file) override;
+  bool Initialize(std::istream &is) override;
+  const std::string *option(const std::string &name) const;
+  // warm starts as IpoptSolver handles them (Ipopt/BonIpoptSolver.cpp:345-430): the primal point becomes the start point
+  // of the next solve; the multipliers are carried in TMINLP2TNLP::duals_init and switch the warm-start flag on, but the
+  // batched IPM initialises its multipliers itself (Ipopt's warm_start_init_point = no path), which is also what the
+  // reference runs with by default (`warm_start none`)
+  bool setWarmStart(const CoinWarmStart *warm, TMINLP2TNLP &tnlp) override;
+  CoinWarmStart *getUsedWarmStart(TMINLP2TNLP &tnlp) const override;
+  CoinWarmStart *getWarmStart(TMINLP2TNLP &tnlp) const override;
+  CoinWarmStart *getEmptyWarmStart() const override { return new CoinWarmStart(); }
+  bool warmStartIsValid(const CoinWarmStart *ws) const override { return ws && !ws->empty(); }
+  void enableWarmStart() override { enable_warm_start_ = true; }
+  void disableWarmStart() override { enable_warm_start_ = false; }
+  bool warmStartEnabled() const { return enable_warm_start_; }
+  void setOutputToDefault() override { log_level_ = default_log_level_; }
+  void forceSolverOutput(int log_level) override { log_level_ = log_level; }
+  int logLevel() const { return log_level_; }
+  int errorCode() const override { return error_code_; }      // the provider's return code of the last failed call
+  class UnsolvedB200Error : public UnsolvedError {
+   public:
+    UnsolvedB200Error(int num, TMINLP2TNLP *problem, std::string name) : UnsolvedError(num, problem, std::move(name)) {}
+    const std::string &errorName() const override;
+    const std::string &solverName() const override;
+  };
+  UnsolvedError *newUnsolvedError(int num, TMINLP2TNLP *problem, std::string name) override {
+    return new UnsolvedB200Error(num, problem, std::move(name));
+  }
   // the batched sibling: children differ only in bounds; results in TMINLP2TNLP layout
   // (the primal points of one batch live in ONE shared block; a child refers to its row)
   struct Child {
@@ -76,6 +107,10 @@ class B200Solver : public TNLPSolver {
   long total_batch_iterations_ = 0;
   double solve_seconds_ = 0;
   int provider_errors_ = 0;
+  int error_code_ = 0;
+  bool enable_warm_start_ = false;
+  int log_level_ = 0, default_log_level_ = 0;
+  std::vector<std::pair<std::string, std::string>> options_;
 };
 
 // Strong-branching plugin: prefetch() solves all 2K children of a node as ONE batch; solveFromHotStart() then serves

@@ -7,12 +7,31 @@
 //                        StrongBranchingSolver src/Interfaces/BonStrongBranchingSolver.hpp:17-66
 //                        OsiTMINLPInterface    src/Interfaces/BonOsiTMINLPInterface.hpp:48-1346 (subset used here)
 #pragma once
+#include <istream>
+#include <ostream>
 #include <string>
 #include <vector>
 
 namespace Bonmin {
 
 class TMINLP2TNLP;
+
+// CoinWarmStart as IpoptWarmStart fills it (src/Interfaces/Ipopt/BonIpoptWarmStart.hpp:28-100): the primal point and the
+// [z_L | z_U | lambda] multipliers; "empty" = reset to the model's own starting point.
+class CoinWarmStart {
+ public:
+  CoinWarmStart() {}
+  CoinWarmStart(int np, int nd, const double *x, const double *duals) : primal_(x, x + np), dual_(duals ? duals : x, duals ? duals + nd : x), empty_(false) {}
+  bool empty() const { return empty_; }
+  int primalSize() const { return (int)primal_.size(); }
+  int dualSize() const { return (int)dual_.size(); }
+  const double *primal() const { return primal_.data(); }
+  const double *dual() const { return dual_.data(); }
+
+ private:
+  std::vector<double> primal_, dual_;
+  bool empty_ = true;
+};
 
 class TNLPSolver {
  public:
@@ -21,13 +40,45 @@ class TNLPSolver {
     illDefinedProblem = -4, illegalOption = -5, externalException = -6, exception = -7, solvedOptimal = 1,
     solvedOptimalTol = 2, provenInfeasible = 3, unbounded = 4, numReturnCodes
   };
+  // thrown BY POINTER by the interface when a solve ends in an unrecoverable status (:50-97, BonOsiTMINLPInterface.cpp:2639-2644)
+  class UnsolvedError {
+   public:
+    UnsolvedError(int errorNum = -10000, TMINLP2TNLP *model = nullptr, std::string name = "") : errorNum_(errorNum), model_(model), name_(std::move(name)) {}
+    virtual ~UnsolvedError() {}
+    void printError(std::ostream &os) {      // BonTNLPSolver.cpp:165-173
+      os << solverName() << " exited with error code " << errorNum_ << " " << errorName() << std::endl;
+    }
+    virtual const std::string &errorName() const = 0;
+    virtual const std::string &solverName() const = 0;
+    int errorNum() const { return errorNum_; }
+    TMINLP2TNLP *model() const { return model_; }
+    const std::string &name() const { return name_; }
+
+   private:
+    int errorNum_;
+    TMINLP2TNLP *model_;
+    std::string name_;
+  };
+  virtual UnsolvedError *newUnsolvedError(int num, TMINLP2TNLP *problem, std::string name) = 0;   // :95-97
   virtual ~TNLPSolver() {}
   virtual TNLPSolver *clone() = 0;
+  virtual bool Initialize(std::string params_file) = 0;         // :118
+  virtual bool Initialize(std::istream &is) = 0;                // :122
   virtual ReturnStatus OptimizeTNLP(TMINLP2TNLP &tnlp) = 0;     // :127
   virtual ReturnStatus ReOptimizeTNLP(TMINLP2TNLP &tnlp) = 0;   // :130
+  virtual bool setWarmStart(const CoinWarmStart *warm, TMINLP2TNLP &tnlp) = 0;     // :133-134
+  virtual CoinWarmStart *getUsedWarmStart(TMINLP2TNLP &tnlp) const = 0;            // :137
+  virtual CoinWarmStart *getWarmStart(TMINLP2TNLP &tnlp) const = 0;                // :140
+  virtual CoinWarmStart *getEmptyWarmStart() const = 0;                            // :142
+  virtual bool warmStartIsValid(const CoinWarmStart *ws) const = 0;                // :145
+  virtual void enableWarmStart() = 0;                                              // :148
+  virtual void disableWarmStart() = 0;                                             // :151
   virtual double CPUTime() = 0;
   virtual int IterationCount() = 0;
+  virtual void setOutputToDefault() = 0;                        // :174
+  virtual void forceSolverOutput(int log_level) = 0;            // :176
   virtual const std::string &solverName() const = 0;
+  virtual int errorCode() const = 0;                            // :205
   // BonTNLPSolver.cpp:253-255
   static bool isRecoverable(ReturnStatus r) {
     return !(r == illDefinedProblem || r == notEnoughFreedom || r == illegalOption || r == computationError || r == timeLimit);
@@ -42,6 +93,8 @@ class TMINLP2TNLP {
   std::vector<int> var_types;                 // 0 continuous, 1 binary, 2 integer
   std::vector<double> x_l, x_u, g_l, g_u;     // current bounds
   std::vector<double> x_init;                 // [x | z_L | z_U | lambda] when duals are set (:294-303)
+  std::vector<double> duals_init;             // [z_L | z_U | lambda] or empty (setDualsInit, .cpp:286-303)
+  void setDualsInit(int nd, const double *d) { duals_init.assign(d, d + nd); }
   std::vector<double> x_sol, g_sol, duals_sol;  // duals_sol = [z_L | z_U | lambda] (.cpp:491-498)
   double obj_value = 1e100;
   TNLPSolver::ReturnStatus return_status = TNLPSolver::exception;

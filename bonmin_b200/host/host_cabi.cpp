@@ -2,6 +2,7 @@
 // batch-solve callback.  In the product the callback is bnlp_solve_batch on a CUDA engine (bnlp_bb_run_engine in
 // bnlp_api.cu); tests may pass the CPU oracle to check that both give the same MINLP optimum.
 #include <cstring>
+#include <sstream>
 
 #include "../../include/bnlp.h"
 #include "B200Solver.hpp"
@@ -61,6 +62,67 @@ int bnlp_bb_run_cb3(int n, int m, const int *var_type, const double *xl, const d
   res->ipm_iterations = r.ipm_iterations; res->best_obj = r.best_obj; res->best_bound = r.best_bound; res->seconds = r.seconds;
   if (best_x && !r.best_x.empty()) memcpy(best_x, r.best_x.data(), sizeof(double) * n);
   return r.status == 3 ? -1 : 0;   // the arithmetic provider failed: an error, not a search result
+}
+
+// Exercises the parts of the TNLPSolver contract that have no other C entry point (options, warm starts, error objects,
+// output levels) on a stub provider; returns 0, or the source line of the first expectation that failed.
+int bnlp_host_selftest(void) {
+  using namespace Bonmin;
+#define EXPECT(c) do { if (!(c)) return __LINE__; } while (0)
+  int calls = 0, fail_next = 0;
+  BatchSolveFn stub = [&](int B, const double *XL, const double *, const double *X0, double *OBJ, int *ST, int *IT, double *X,
+                          double *G, double *D) {
+    ++calls;
+    if (fail_next) return fail_next;
+    for (int b = 0; b < B; ++b) {
+      OBJ[b] = X0[0] + XL[0]; ST[b] = 1; IT[b] = 7;
+      if (X) for (int j = 0; j < 2; ++j) X[2 * b + j] = X0[j];
+      if (G) G[b] = 0.5;
+      if (D) for (int j = 0; j < 5; ++j) D[5 * b + j] = 0.25 * (j + 1);
+    }
+    return 0;
+  };
+  B200Solver app(stub);
+  std::istringstream opts("# comment\nbonmin.tol 1e-9\nmax_iter 123 # trailing\nprint_level 3\ntol 1e-7\n");
+  EXPECT(app.Initialize(opts));
+  EXPECT(app.option("tol") && *app.option("tol") == "1e-7" && *app.option("max_iter") == "123" && !app.option("mu_init"));
+  EXPECT(app.logLevel() == 3);
+  app.forceSolverOutput(5); EXPECT(app.logLevel() == 5);
+  app.setOutputToDefault(); EXPECT(app.logLevel() == 3);
+  std::istringstream bad("tol\n");
+  EXPECT(!app.Initialize(bad));
+  EXPECT(app.Initialize(std::string("/nonexistent/bonmin.opt")));
+  TMINLP2TNLP t;
+  t.n = 2; t.m = 1; t.var_types = {0, 2}; t.x_l = {1.0, 0.0}; t.x_u = {4.0, 3.0}; t.g_l = {-1e19}; t.g_u = {1.0};
+  t.x_init = {2.0, 1.0};
+  EXPECT(app.getUsedWarmStart(t) == nullptr);                 // no duals were set
+  EXPECT(app.OptimizeTNLP(t) == TNLPSolver::solvedOptimal && t.obj_value == 3.0 && app.IterationCount() == 7);
+  CoinWarmStart *ws = app.getWarmStart(t);
+  EXPECT(ws && app.warmStartIsValid(ws) && ws->primalSize() == 2 && ws->dualSize() == 5 && ws->primal()[0] == 2.0 && ws->dual()[4] == 1.25);
+  t.x_init = {0.0, 0.0};
+  EXPECT(!app.warmStartEnabled() && app.setWarmStart(ws, t) && app.warmStartEnabled());
+  EXPECT(t.x_init[0] == 2.0 && t.duals_init.size() == 5);
+  CoinWarmStart *used = app.getUsedWarmStart(t);
+  EXPECT(used && used->primal()[1] == 1.0 && used->dualSize() == 5);
+  CoinWarmStart *empty = app.getEmptyWarmStart();
+  EXPECT(!app.warmStartIsValid(empty) && app.setWarmStart(empty, t) && !app.warmStartEnabled());
+  EXPECT(!app.setWarmStart(nullptr, t));
+  delete ws; delete used; delete empty;
+  fail_next = -17;
+  EXPECT(app.ReOptimizeTNLP(t) == TNLPSolver::exception && app.errorCode() == -17 && app.providerErrors() == 1);
+  EXPECT(TNLPSolver::isError(t.return_status) && TNLPSolver::isRecoverable(TNLPSolver::exception) &&
+         !TNLPSolver::isRecoverable(TNLPSolver::computationError));
+  TNLPSolver::UnsolvedError *e = app.newUnsolvedError(app.errorCode(), &t, "node17");
+  std::ostringstream os;
+  e->printError(os);
+  EXPECT(e->errorNum() == -17 && e->model() == &t && e->name() == "node17" && os.str().find("B200 batched IPM exited with error code -17") == 0);
+  delete e;
+  TNLPSolver *c = app.clone();
+  EXPECT(c && c->solverName() == app.solverName());
+  delete c;
+  EXPECT(calls == 2);
+#undef EXPECT
+  return 0;
 }
 
 int bnlp_resolve_cb(int mode, int n, int m, const double *xl, const double *xu, const double *x_init, double cur_obj,

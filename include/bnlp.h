@@ -346,6 +346,10 @@ int bnlp_resolve_engine(bnlp_engine *, int mode, const double *xl, const double 
                         int cur_status, int numsolve, double max_random_point_radius, unsigned seed, bnlp_retry_result *res,
                         double *obj, int *status, double *x, double *g, double *duals);
 
+/* Self-test of the host adapter's TNLPSolver contract (options, warm starts, error objects, output levels) on a stub
+ * provider; 0 = all expectations hold, otherwise the source line of the first failure (bonmin_b200/host/host_cabi.cpp). */
+int bnlp_host_selftest(void);
+
 /* --- on-disk formats either side of the path (host code; bonmin_b200/host/node_files.cpp) -------------------------
  * Failed-node dump = TMINLP2TNLP::outputDiffs (src/Interfaces/BonTMINLP2TNLP.cpp:551-615): writes <prob_name>.bounds
  * ("LO|UP\tindex\tvalue" per bound that differs from the original model, CoinRelFltEq 1e-10) and <prob_name>.start

@@ -158,3 +158,10 @@ def test_priorities_restrict_the_candidates(oracle_ipm):
     changed = np.flatnonzero((first[0] != m.xl).any(0) | (first[1] != m.xu).any(0))
     assert list(changed) == [frac[-1]]
     assert r["status"] == 0 and r["best_obj"] == pytest.approx(ref["best_obj"], rel=1e-6)   # same optimum, other tree
+
+
+def test_tnlp_solver_contract_of_the_adapter():
+    """B200Solver implements the whole TNLPSolver interface (BonTNLPSolver.hpp:95-205): Initialize from an options stream,
+    the IpoptSolver warm-start semantics (BonIpoptSolver.cpp:345-430), error code + UnsolvedError, output levels, clone.
+    The checks are C++ (bnlp_host_selftest, bonmin_b200/host/host_cabi.cpp) on a stub provider."""
+    assert bb.host_lib().bnlp_host_selftest() == 0
