@@ -2,9 +2,11 @@
 // batch-solve callback.  In the product the callback is bnlp_solve_batch on a CUDA engine (bnlp_bb_run_engine in
 // bnlp_api.cu); tests may pass the CPU oracle to check that both give the same MINLP optimum.
 #include <cstring>
+#include <vector>
 #include <sstream>
 
 #include "../../include/bnlp.h"
+#include "B200Linearizer.hpp"
 #include "B200Solver.hpp"
 
 extern "C" {
@@ -121,6 +123,51 @@ int bnlp_host_selftest(void) {
   EXPECT(c && c->solverName() == app.solverName());
   delete c;
   EXPECT(calls == 2);
+  {   // lineariser: CSR rows of the provider -> OsiRowCuts (skipped slots dropped, global flag), LP -> OsiSolverInterface
+    OaBatchFn oa = [](int B, const double *X, const double *, const double *, int getObj, double tiny, double, double, double, OaRows &o) {
+      o.rows_per_point = 2;
+      for (int b = 0; b < B; ++b) {
+        o.row_start.push_back((int)o.col.size());
+        o.col.push_back(0); o.val.push_back(X[2 * b] + tiny); o.col.push_back(1); o.val.push_back(-1.0);
+        o.src_row.push_back(0); o.lb.push_back(-1e300); o.ub.push_back(10.0 + b);
+        o.row_start.push_back((int)o.col.size());
+        if (getObj) { o.col.push_back(2); o.val.push_back(-1.0); o.src_row.push_back(1); } else o.src_row.push_back(-1);
+        o.lb.push_back(-1e300); o.ub.push_back(0.0);
+      }
+      o.row_start.push_back((int)o.col.size());
+      return 0;
+    };
+    ExtractFn ex = [](const double *, const double *xl, const double *xu, int getObj, double, double, double, double, LpRelaxation &lp) {
+      lp.n_cols = 2 + getObj; lp.has_alpha = getObj; lp.obj_offset = 1.5;
+      lp.row_start = {0, 2}; lp.col = {0, 1}; lp.val = {1.0, 2.0}; lp.row_lb = {-1e300}; lp.row_ub = {4.0};
+      lp.col_lb = {xl[0], xl[1]}; lp.col_ub = {xu[0], xu[1]}; lp.obj = {1.0, 0.0}; lp.is_integer = {0, 1};
+      if (getObj) { lp.col_lb.push_back(-1e300); lp.col_ub.push_back(1e300); lp.obj = {0.0, 0.0, 1.0}; lp.is_integer.push_back(0); }
+      return 0;
+    };
+    B200Linearizer lin(oa, ex);
+    lin.set_tols(1e-8, 1e-17, 1e-8, 1e19);
+    lin.set_model(&t);
+    OsiCuts cs;
+    const double X2[4] = {1.0, 2.0, 3.0, 4.0};
+    lin.get_oas(cs, X2, false, true);
+    EXPECT(cs.sizeRowCuts() == 1 && cs.rowCut(0).globallyValid() && cs.rowCut(0).ub() == 10.0 && cs.rowCut(0).indices().size() == 2);
+    EXPECT(cs.rowCut(0).elements()[0] == 1.0 + 1e-8);
+    lin.get_oas_batch(cs, X2, 2, true, false);
+    EXPECT(cs.sizeRowCuts() == 5 && !cs.rowCut(1).globallyValid() && cs.rowCut(3).ub() == 11.0 && cs.rowCut(4).indices()[0] == 2);
+    lin.get_refined_oa(cs);
+    EXPECT(cs.sizeRowCuts() == 5);
+    lin.set_refinement_points({1.0, 2.0, 3.0, 4.0});
+    lin.get_refined_oa(cs);
+    EXPECT(cs.sizeRowCuts() == 7 && cs.rowCut(6).globallyValid());
+    OsiSolverInterface si;
+    lin.extract(&si, X2, true);
+    EXPECT(si.getNumCols() == 3 && si.getNumRows() == 1 && si.integer_[1] == 1 && si.integer_[0] == 0 && si.obj_offset_ == 1.5 && si.colub_[1] == 3.0);
+    TMINLP2OsiLP *c2 = lin.clone();
+    OsiCuts cs2;
+    c2->get_oas(cs2, X2, true, false);
+    EXPECT(cs2.sizeRowCuts() == 2);
+    delete c2;
+  }
 #undef EXPECT
   return 0;
 }
@@ -222,6 +269,72 @@ int bnlp_dive_run_engine(bnlp_engine *E, const bnlp_problem *P, const double *xl
   };
   return bnlp_dive_run_cb(n, m, vt.data(), xl, xu, gl.data(), gu.data(), x_sol, g_sol, obj_sol, len.data(), cutoff, cb, gcb, E,
                           o, res, better_x);
+}
+
+// The lineariser with the CUDA engine behind it: B x get_oas and one extract, flattened for a C caller (tests, bench).
+int bnlp_linearizer_engine(bnlp_engine *E, const bnlp_problem *P, int B, const double *X, int getObj, int global, int *n_cuts,
+                           int *row_start, int *col, double *val, double *lb, double *ub, int *is_global, int cap_cuts,
+                           int cap_nnz, int *lp_cols, int *lp_rows, int *lp_nnz, int *lp_integers) {
+  using namespace Bonmin;
+  int n = 0, m = 0;
+  if (!E || !P || bnlp_problem_sizes(P, &n, &m, nullptr, nullptr)) return -1;
+  TMINLP2TNLP model;
+  model.n = n; model.m = m;
+  model.x_l.resize(n); model.x_u.resize(n);
+  bnlp_problem_info(P, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, model.x_l.data(), model.x_u.data(), nullptr, nullptr, nullptr);
+  OaBatchFn oa = [E](int Bp, const double *Xp, const double *xl, const double *xu, int go, double tiny, double vtiny, double relax,
+                     double infty, OaRows &o) {
+    size_t cap = 0;
+    if (bnlp_oa_capacity(E, Bp, &o.rows_per_point, &cap)) return -1;
+    const size_t slots = (size_t)Bp * o.rows_per_point;
+    o.row_start.resize(slots + 1); o.col.resize(cap); o.val.resize(cap); o.lb.resize(slots); o.ub.resize(slots); o.src_row.resize(slots);
+    bnlp_oa_tols tl{tiny, vtiny, relax, infty, 0};
+    return bnlp_oa_batch(E, Bp, Xp, nullptr, xl, xu, nullptr, 0.0, go, &tl, o.row_start.data(), o.col.data(), o.val.data(),
+                         o.lb.data(), o.ub.data(), o.src_row.data());
+  };
+  const int mm = m, nn = n;
+  ExtractFn ex = [E, mm, nn](const double *x, const double *xl, const double *xu, int go, double tiny, double vtiny, double relax,
+                             double infty, LpRelaxation &lp) {
+    bnlp_oa_tols tl{tiny, vtiny, relax, infty, 0};
+    bnlp_lp_dims d{};
+    const size_t rows = (size_t)mm + 1, nnz = rows * ((size_t)nn + 1);
+    lp.row_start.resize(rows + 1); lp.col.resize(nnz); lp.val.resize(nnz); lp.row_lb.resize(rows); lp.row_ub.resize(rows);
+    std::vector<int> src(rows);
+    lp.col_lb.resize(nn + 1); lp.col_ub.resize(nn + 1); lp.obj.resize(nn + 1); lp.is_integer.resize(nn + 1);
+    const int rc = bnlp_extract_linear_relaxation(E, x, nullptr, xl, xu, go, &tl, &d, lp.row_start.data(), lp.col.data(), lp.val.data(),
+                                                  lp.row_lb.data(), lp.row_ub.data(), src.data(), lp.col_lb.data(), lp.col_ub.data(),
+                                                  lp.obj.data(), lp.is_integer.data());
+    if (rc) return rc;
+    lp.n_cols = d.n_cols; lp.has_alpha = d.has_alpha; lp.obj_offset = d.obj_offset;
+    lp.row_start.resize(d.n_rows + 1); lp.row_lb.resize(d.n_rows); lp.row_ub.resize(d.n_rows);
+    lp.col_lb.resize(d.n_cols); lp.col_ub.resize(d.n_cols); lp.obj.resize(d.n_cols); lp.is_integer.resize(d.n_cols);
+    return 0;
+  };
+  B200Linearizer lin(oa, ex);
+  lin.set_tols(1e-8, 1e-17, 1e-8, 1e19);   // tiny_element, very_tiny_element, oa_rhs_relax, infinity (BonOsiTMINLPInterface.cpp:222-247)
+  lin.set_model(&model);
+  OsiCuts cs;
+  lin.get_oas_batch(cs, X, B, getObj != 0, global != 0);
+  if (lin.lastError()) return lin.lastError();
+  int nnz = 0;
+  if (cs.sizeRowCuts() > cap_cuts) return -2;
+  for (int k = 0; k < cs.sizeRowCuts(); ++k) {
+    const OsiRowCut &c = cs.rowCut(k);
+    if (nnz + (int)c.indices().size() > cap_nnz) return -2;
+    row_start[k] = nnz;
+    for (size_t e = 0; e < c.indices().size(); ++e) { col[nnz] = c.indices()[e]; val[nnz] = c.elements()[e]; ++nnz; }
+    lb[k] = c.lb(); ub[k] = c.ub(); is_global[k] = c.globallyValid();
+  }
+  row_start[cs.sizeRowCuts()] = nnz;
+  *n_cuts = cs.sizeRowCuts();
+  OsiSolverInterface si;
+  lin.extract(&si, X, getObj != 0);
+  if (lin.lastError()) return lin.lastError();
+  if (lp_cols) *lp_cols = si.getNumCols();
+  if (lp_rows) *lp_rows = si.getNumRows();
+  if (lp_nnz) *lp_nnz = si.start_.empty() ? 0 : si.start_.back();
+  if (lp_integers) { *lp_integers = 0; for (int v : si.integer_) *lp_integers += v; }
+  return 0;
 }
 
 // Product path: the same driver with the CUDA engine as arithmetic provider (no Python in between).

@@ -346,6 +346,12 @@ int bnlp_resolve_engine(bnlp_engine *, int mode, const double *xl, const double 
                         int cur_status, int numsolve, double max_random_point_radius, unsigned seed, bnlp_retry_result *res,
                         double *obj, int *status, double *x, double *g, double *duals);
 
+/* The host lineariser (B200Linearizer : TMINLP2OsiLP, src/Interfaces/BonTMINLP2OsiLP.hpp:73-83) with the engine behind it:
+ * get_oas at B points (cuts flattened to CSR: row_start n_cuts + 1, col/val, lb, ub, is_global) and extract at the
+ * first point (dimensions of the loaded LP).  -2 = a capacity is too small. */
+int bnlp_linearizer_engine(bnlp_engine *, const bnlp_problem *, int B, const double *X, int getObj, int global, int *n_cuts,
+                           int *row_start, int *col, double *val, double *lb, double *ub, int *is_global, int cap_cuts,
+                           int cap_nnz, int *lp_cols, int *lp_rows, int *lp_nnz, int *lp_integers);
 /* Self-test of the host adapter's TNLPSolver contract (options, warm starts, error objects, output levels) on a stub
  * provider; 0 = all expectations hold, otherwise the source line of the first failure (bonmin_b200/host/host_cabi.cpp). */
 int bnlp_host_selftest(void);

@@ -287,3 +287,37 @@ def test_fp_variant_parity(bnlp_lib):
         assert ok.all() or kw.get("cutoff") == -100.0       # the last case is infeasible under its cutoff row
         np.testing.assert_allclose(g["obj"][ok], o["obj"][ok], rtol=1e-6, atol=1e-7)
         eng.close()
+
+
+@pytest.mark.gpu
+def test_linearizer_adapter_matches_the_batch_calls(bnlp_lib):
+    """B200Linearizer (TMINLP2OsiLP: get_oas / extract) with the engine behind it returns exactly the rows of bnlp_oa_batch
+    and the LP of bnlp_extract_linear_relaxation."""
+    import ctypes
+    from bonmin_b200 import engine as E_, instances as I
+    m = I.syn_cvx_minlp(16, 6, 3, 5, 2)
+    eng = E_.Engine(E_.Problem.from_model(m))
+    rng = np.random.default_rng(1)
+    X = np.clip(m.x0 + rng.uniform(-0.3, 0.3, size=(5, m.n)), m.xl, m.xu)
+    ref = eng.oa_batch(X, None, m.xl, m.xu, get_obj=1)
+    keep = np.flatnonzero(ref["src_row"] >= 0)
+    cap_c, cap_z = len(ref["src_row"]), len(ref["val"])
+    rs = np.zeros(cap_c + 1, np.int32); col = np.zeros(cap_z, np.int32); val = np.zeros(cap_z)
+    lb = np.zeros(cap_c); ub = np.zeros(cap_c); gl = np.zeros(cap_c, np.int32)
+    nc, lc, lr, lz, li = (ctypes.c_int() for _ in range(5))
+    L = E_.lib()
+    L.bnlp_linearizer_engine.argtypes = ([ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+                                         + [ctypes.c_void_p] * 7 + [ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 4)
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)   # noqa: E731
+    rc = L.bnlp_linearizer_engine(eng.h, eng.problem.h, 5, vp(np.ascontiguousarray(X)), 1, 1, ctypes.byref(nc), vp(rs), vp(col), vp(val),
+                                  vp(lb), vp(ub), vp(gl), cap_c, cap_z, ctypes.byref(lc), ctypes.byref(lr), ctypes.byref(lz), ctypes.byref(li))
+    assert rc == 0 and nc.value == len(keep) and gl[:nc.value].all()
+    for k, slot in enumerate(keep):
+        a, b = ref["row_start"][slot], ref["row_start"][slot + 1]
+        assert np.array_equal(col[rs[k]:rs[k + 1]], ref["col"][a:b]) and np.array_equal(val[rs[k]:rs[k + 1]], ref["val"][a:b])
+        assert lb[k] == ref["lb"][slot] and ub[k] == ref["ub"][slot]
+    lp = eng.extract_linear_relaxation(X[0], None, get_obj=True)
+    assert lc.value == m.n + (1 if lp["has_alpha"] else 0) and lr.value == lp["n_rows"] and lz.value == lp["row_start"][lp["n_rows"]]
+    assert li.value == int((np.asarray(m.vtype) != 0).sum())
+    assert L.bnlp_linearizer_engine(eng.h, eng.problem.h, 5, vp(np.ascontiguousarray(X)), 1, 1, ctypes.byref(nc), vp(rs), vp(col), vp(val),
+                                    vp(lb), vp(ub), vp(gl), 2, cap_z, None, None, None, None) == -2
