@@ -28,6 +28,7 @@ class EngineProvider:
         self.xl, self.xu = info["xl"], info["xu"]
         self.vtype = info["var_type"]
         self.x0 = info["x0"]
+        self._oa_out = {}
 
     def solve(self, XL, XU, x0):
         return self.eng.solve_batch(XL, XU, x0)
@@ -46,7 +47,9 @@ class EngineProvider:
 
     def oa(self, X, X2=None, theta=0.0):
         X = np.atleast_2d(X)
-        r = self.eng.oa_batch(X, None, self.xl, self.xu, X2=X2, theta=theta, get_obj=1)
+        # the cut buffers of each batch size are kept and page-locked: every pass of a loop reuses them
+        r = self.eng.oa_batch(X, None, self.xl, self.xu, X2=X2, theta=theta, get_obj=1, out=self._oa_out.get(len(X)), pin=True)
+        self._oa_out[len(X)] = r
         out = []
         for k in range(len(r["src_row"])):
             if r["src_row"][k] < 0:
