@@ -926,7 +926,9 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
               if (dz < 0) mn[1] = fmax(mn[1], -(-tau * zU[j] / dz));
             }
           }
-          for (int r = tid; r < R; r += IPM_NT) {
+          // (rows go to the threads at the top of the CTA, variables to those at the bottom: the chain of FP64 divisions a
+          // thread runs is the critical path of this pass; a max-reduction does not care who holds what)
+          for (int r = IPM_NT - 1 - tid; r < R; r += IPM_NT) {
             const double dsr = -rc[r] - (jd0[r] + mu * jd1[r]);
             const double dvr = mu / s[r] - v[r] - Ss[r] * dsr;
             if (dsr < 0) mn[0] = fmax(mn[0], -(-tau * s[r] / dsr));
