@@ -868,7 +868,20 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
       const double of = it_of;
       // H += W  (rows < n), fixed rows/cols -> identity, diagonal += Sigma_x + delta_w
       const double *Wb = CB.Wbuf + (size_t)cta * M.ldp;
-      for (int e = tid; e < P; e += IPM_NT) H[e] += __ldcg(Wb + e);
+      {   // 16-byte requests (Wbuf rows are 128-byte aligned, H is 16-byte aligned in shared memory), four in flight per thread
+        const double2 *W2 = reinterpret_cast<const double2 *>(Wb);
+        double2 *H2 = reinterpret_cast<double2 *>(H);
+        const int P2 = P >> 1;
+        int e = tid;
+        for (; e + 3 * IPM_NT < P2; e += 4 * IPM_NT) {
+          const double2 w0 = __ldcg(W2 + e), w1 = __ldcg(W2 + e + IPM_NT), w2 = __ldcg(W2 + e + 2 * IPM_NT), w3 = __ldcg(W2 + e + 3 * IPM_NT);
+          double2 h0 = H2[e], h1 = H2[e + IPM_NT], h2 = H2[e + 2 * IPM_NT], h3 = H2[e + 3 * IPM_NT];
+          h0.x += w0.x; h0.y += w0.y; h1.x += w1.x; h1.y += w1.y; h2.x += w2.x; h2.y += w2.y; h3.x += w3.x; h3.y += w3.y;
+          H2[e] = h0; H2[e + IPM_NT] = h1; H2[e + 2 * IPM_NT] = h2; H2[e + 3 * IPM_NT] = h3;
+        }
+        for (; e < P2; e += IPM_NT) { const double2 w = __ldcg(W2 + e); double2 h = H2[e]; h.x += w.x; h.y += w.y; H2[e] = h; }
+        if ((P & 1) && tid == 0) H[P - 1] += __ldcg(Wb + P - 1);
+      }
       __syncthreads();
       const int nfix = s_nfix;
       for (int e = tid; e < nfix * N; e += IPM_NT) {
