@@ -39,6 +39,24 @@ C3 = dict(n=200, n_int=100, m_q=40, m_l=40, seed=20261020)
 WORKLOAD = "C3 SYN-MIQCP(n=200,n_int=100,m_q=40,m_l=40,seed=20261020) child relaxations, shared start point x*"
 
 
+def workload_config(batch, world):
+    """The workload both arms report (identical dicts: the driver compares them)."""
+    return {"workload": WORKLOAD, "children_per_gpu_per_step": batch, "children_per_step": batch * world,
+            "l2": "256 MiB flush write between timed steps (untimed)"}
+
+
+def measured_traffic():
+    """DRAM bytes per IPM iteration of ipm_coop_kernel from the committed ncu capture of this round
+    (profiles/r2_traffic.json, written by scripts/ncu_traffic.py from `ncu --set full`: dram__bytes_read.sum +
+    dram__bytes_write.sum of one launch / its iterations).  None when the file is absent: the bench itself cannot read
+    DRAM counters."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
 def f_iter(n, m_q, m_l, r=2, t=1):
     """Algorithmic FLOPs of one IPM iteration."""
     m = m_q + m_l
@@ -176,6 +194,50 @@ def bb_section(args, local_rank):
     return out
 
 
+def sweep_section(eng, model, xs, dev, stream):
+    """BASELINE config 3 ("1k-64k independent child NLPs") and config 2's unit of work (one node = 64 children) as
+    driver-visible numbers: device-resident batches of 1k .. 64k C3 children (relaxations/s) and the LATENCY of a
+    64-child strong-branching batch at C3 and C2 (ms per batch: what one B-BB node waits for)."""
+    import torch
+    from bonmin_b200.engine import Engine, Problem
+    out = {"c3_batch_sweep": [], "node_batch_latency": []}
+    n = model.n
+
+    def timed(e, XL, XU, x0, reps):
+        B = len(XL)
+        d = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (XL, XU, x0)]
+        O = torch.zeros(B, dtype=torch.float64, device=dev); S = torch.zeros(B, dtype=torch.int32, device=dev)
+        It = torch.zeros(B, dtype=torch.int32, device=dev); X = torch.zeros(B, XL.shape[1], dtype=torch.float64, device=dev)
+        e.solve_batch_device(d[0], d[1], d[2], O, S, It, X, None, None, stream=stream.cuda_stream)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            e.solve_batch_device(d[0], d[1], d[2], O, S, It, X, None, None, stream=stream.cuda_stream)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps, int(It.sum().item())
+
+    for B in (1024, 4096, 16384, 65536):
+        XL, XU = make_children(model, xs, B, 0)
+        ms, its = timed(eng, XL, XU, xs, 2 if B < 65536 else 1)
+        out["c3_batch_sweep"].append({"children": B, "ms": ms, "relaxations_per_s": B / (ms * 1e-3), "mean_iterations": its / B})
+    XL, XU = make_children(model, xs, 64, 0)
+    ms, _ = timed(eng, XL, XU, xs, 10)
+    out["node_batch_latency"].append({"workload": "C3 (n=200), 32 candidates = 64 children", "ms_per_batch": ms})
+    m2 = I.config_c2()
+    e2 = Engine(Problem.from_model(m2), devices=[dev.index or 0])
+    x2 = e2.solve_batch(m2.xl, m2.xu, m2.x0)["x"][0]
+    XL, XU = make_children(m2, x2, 64, 0)
+    ms, _ = timed(e2, XL, XU, x2, 10)
+    out["node_batch_latency"].append({"workload": "C2 (n=100, m=40), 32 candidates = 64 children", "ms_per_batch": ms})
+    XL, XU = make_children(m2, x2, 8192, 0)
+    ms, its = timed(e2, XL, XU, x2, 2)
+    out["c2_throughput"] = {"children": 8192, "ms": ms, "relaxations_per_s": 8192 / (ms * 1e-3), "mean_iterations": its / 8192}
+    e2.close()
+    return out
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU path for this workload.  The real Bonmin/Ipopt cannot be built or
     installed offline (no Ipopt/ASL/Osi/Cbc), so this times the CPU oracle restatement — all host
@@ -189,7 +251,10 @@ def run_reference(args, rank, world):
     root = ipm.solve_batch(model, model.xl, model.xu, model.x0, dense=dense)
     xs = root["x"][0]
     cores = cpu_cores()
-    sample = args.ref_sample
+    # the arm's step = the same children_per_step as the GPU arm (same config); bounded so that the run ends within
+    # minutes on the host cores: at most --ref-cap children of the step's sequence are solved per step
+    step_children = args.batch * world
+    sample = min(step_children, args.ref_cap)
     XL, XU = make_children(model, xs, sample, 0)
     for _ in range(args.warmup):
         ipm.solve_batch(model, XL[: max(cores, 32)], XU[: max(cores, 32)], xs, threads=cores, dense=dense)
@@ -201,10 +266,12 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": "child NLP relaxations solved/sec", "value": val, "unit": "relaxations/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "children_per_step": sample},
+            "config": workload_config(args.batch, world),
             "cpu_baseline": {"value": val, "unit": "relaxations/s", "cores": cores, "kind": "port",
-                             "sample": f"{sample} children per step (first {sample} of the C3 child sequence), "
-                                       "CPU restatement of the Bonmin/Ipopt path (Ipopt 3.13 unavailable offline)"},
+                             "sample": f"first {sample} children of the step's {step_children}-child sequence per step "
+                                       "(a rate: children/s does not depend on how many are solved), one relaxation per "
+                                       "thread; CPU restatement of the Bonmin/Ipopt path — NOT Ipopt (Ipopt 3.13 cannot be "
+                                       "built offline)"},
             "e2e": {"value": val, "unit": "relaxations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -216,8 +283,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=4096, help="children per GPU per step")
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--ref-sample", type=int, default=1024)
+    ap.add_argument("--ref-cap", type=int, default=4096, help="--impl reference: children solved per step (cap)")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the batch-size sweep / node-batch latency section")
     ap.add_argument("--cpu-sample", type=int, default=2048)
+    ap.add_argument("--parity-sample", type=int, default=512, help="children per rank checked against the CPU oracle")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-bb", action="store_true", help="skip the B-BB wall-time-to-optimum section")
     ap.add_argument("--no-oa", action="store_true", help="skip the C4 outer-approximation section")
@@ -294,39 +363,101 @@ def main():
     status = dST.cpu().numpy()
     obj_dev = dOBJ.cpu().numpy()
 
-    # ---------------- end-to-end arm through the C ABI with host buffers (pinned)
+    # ---------------- end-to-end arm through the C ABI with host buffers (pinned); the exchange step of SURVEY §8e
+    # (all-gather of every rank's per-child {objective, status}, all-reduce(min) of the incumbent bound: what a multi-rank
+    # B-BB node needs before it can branch) is INSIDE every timed step and also timed on its own with CUDA events
+    from bonmin_b200 import shard
     hXL = torch.from_numpy(XL).pin_memory().numpy()
     hXU = torch.from_numpy(XU).pin_memory().numpy()
     r = eng.solve_batch(hXL, hXU, xs, want_g=False, want_duals=False, pin=True)   # result buffers: page-locked, kept
     r = eng.solve_batch(hXL, hXU, xs, want_g=False, want_duals=False, out=r)
+    ex_obj = torch.empty(B, dtype=torch.float64, device=dev)
+    ex_st = torch.empty(B, dtype=torch.int32, device=dev)
+
+    def exchange(res):
+        """per-child results of this rank -> every rank; best feasible child objective over all ranks."""
+        ex_obj.copy_(torch.from_numpy(res["obj"]), non_blocking=True)
+        ex_st.copy_(torch.from_numpy(res["status"]), non_blocking=True)
+        all_obj, all_st = shard.gather_children(ex_obj, ex_st, B * world) if world == 1 else (
+            torch.cat(_all_gather(ex_obj, world)), torch.cat(_all_gather(ex_st, world)))
+        mine = torch.where(ex_st == 1, ex_obj, torch.full_like(ex_obj, float("inf"))).min()
+        if world > 1:
+            dist.all_reduce(mine, op=dist.ReduceOp.MIN)
+        return all_obj, all_st, mine
+
+    exchange(r)                       # warm-up (NCCL communicators)
+    torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    xev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for k in range(args.steps):
         r = eng.solve_batch(hXL, hXU, xs, want_g=False, want_duals=False, out=r)   # every step copies bounds in, results out
+        xev[k][0].record()
+        all_obj, all_st, best = exchange(r)
+        xev[k][1].record()
+    best_bound = float(best.item())   # device -> host read of the step's result
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    exchange_us = 1e3 * sum(a.elapsed_time(b) for a, b in xev) / args.steps
     clocks = sampler.stop() if rank == 0 else None
     assert np.array_equal(r["status"], status)
+    assert all_obj.numel() == B * world
     h2d = 2 * B * n * 8 + n * 8
     d2h = B * (8 + 4 + 4) + B * n * 8
 
-    # ---------------- exchange step: gather per-child results, all-reduce the incumbent bound
-    t_ms = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    # ---------------- parity of THIS rank's children against the CPU oracle (every rank checks a strided sample of its own
+    # shard; rank 0 reports the worst)
+    par = torch.zeros(3, dtype=torch.float64, device=dev)        # checked, status mismatches, max rel obj diff
+    if not args.no_cpu_baseline:
+        from oracle import ipm as _ipm
+        if rank == 0:
+            _ipm.build()
+        if world > 1:
+            dist.barrier()
+        S = min(args.parity_sample, B)
+        idx = np.unique(np.linspace(0, B - 1, S).astype(int))
+        dense_p = _ipm.dense_arrays(model)
+        o = _ipm.solve_batch(model, XL[idx], XU[idx], xs, threads=max(1, cpu_cores() // max(1, world)), dense=dense_p)
+        same = o["status"] == status[idx]
+        okk = (o["status"] == 1) & same
+        rel = np.abs(o["obj"] - obj_dev[idx]) / np.maximum(1.0, np.abs(o["obj"]))
+        par = torch.tensor([float(len(idx)), float((~same).sum()), float(rel[okk].max(initial=0.0))], dtype=torch.float64, device=dev)
+
+    t_ms = torch.tensor([dev_ms, e2e_s * 1e3, exchange_us], dtype=torch.float64, device=dev)
     tot = torch.tensor([float(iters_total), float((status == 1).sum()), float((status == 3).sum())],
                        dtype=torch.float64, device=dev)
+    par_sum = par[:2].clone()
+    par_max = par[2:].clone()
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    # every rank gets every child's {objective, status} and the best bound (what a multi-GPU B-BB node needs)
-    from bonmin_b200 import shard
-    all_obj, all_st = shard.gather_children(dOBJ, dST, B * world) if world == 1 else (
-        torch.cat([t for t in _all_gather(dOBJ, world)]), torch.cat([t for t in _all_gather(dST, world)]))
-    mine = torch.where(dST == 1, dOBJ, torch.full_like(dOBJ, float("inf"))).min().item()
-    best_bound = shard.allreduce_incumbent(mine, dev)
-    dev_ms_max, e2e_ms_max = t_ms.tolist()
+        dist.all_reduce(par_sum, op=dist.ReduceOp.SUM)
+        dist.all_reduce(par_max, op=dist.ReduceOp.MAX)
+    dev_ms_max, e2e_ms_max, exchange_us_max = t_ms.tolist()
     iters_all, n_opt, n_inf = tot.tolist()
+
+    # ---------------- strong-scaling companion (N > 1): ONE 4096-child batch split over the ranks (a single B-BB round)
+    strong = None
+    if world > 1:
+        Bs = max(2, 4096 // world)
+        sXL = dXL[:Bs].contiguous(); sXU = dXU[:Bs].contiguous()
+        sO = torch.zeros(Bs, dtype=torch.float64, device=dev); sS = torch.zeros(Bs, dtype=torch.int32, device=dev)
+        sI = torch.zeros(Bs, dtype=torch.int32, device=dev); sX = torch.zeros(Bs, n, dtype=torch.float64, device=dev)
+        for _ in range(2):
+            eng.solve_batch_device(sXL, sXU, dX0, sO, sS, sI, sX, None, None, stream=stream.cuda_stream)
+        torch.cuda.synchronize(); dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(3):
+            eng.solve_batch_device(sXL, sXU, dX0, sO, sS, sI, sX, None, None, stream=stream.cuda_stream)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        sms = torch.tensor([e0.elapsed_time(e1) / 3], dtype=torch.float64, device=dev)
+        dist.all_reduce(sms, op=dist.ReduceOp.MAX)
+        strong = {"children_total": Bs * world, "children_per_gpu": Bs, "ms": float(sms.item()),
+                  "relaxations_per_s": Bs * world / (float(sms.item()) * 1e-3)}
 
     if rank == 0:
         total = B * world
@@ -336,47 +467,48 @@ def main():
         fl_step = f_iter(C3["n"], C3["m_q"], C3["m_l"]) * iters_total      # this rank's kernel
         kern_ms = dev_ms / args.steps
         achieved = fl_step / (kern_ms * 1e-3) / 1e12
+        traffic = measured_traffic()
         line = {
             "metric": "child NLP relaxations solved/sec", "value": value, "unit": "relaxations/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "children_per_gpu_per_step": B, "children_per_step": total,
-                       "l2": "256 MiB flush write between timed steps (untimed)",
-                       "mean_ipm_iterations": iters_all / total, "optimal": int(n_opt), "infeasible": int(n_inf),
-                       "best_child_objective": best_bound},
+            "config": workload_config(B, world),
+            "results": {"mean_ipm_iterations": iters_all / total, "optimal": int(n_opt), "infeasible": int(n_inf),
+                        "best_child_objective": best_bound},
             "e2e": {"value": e2e, "unit": "relaxations/s", "h2d_bytes_per_step": h2d * world,
-                    "d2h_bytes_per_step": d2h * world},
+                    "d2h_bytes_per_step": d2h * world,
+                    "exchange_us_per_step": exchange_us_max,
+                    "exchange": "all-gather of per-child {objective, status} over all ranks + all-reduce(min) of the "
+                                "incumbent bound, inside every timed step (torch.distributed / NCCL; device copies at N=1)"},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "fp64", "kernel": "ipm_coop_kernel", "achieved": achieved, "peak": peak,
                          "unit": "TFLOP/s", "frac": achieved / peak if peak > 0 else None,
-                         # DRAM bytes per launch: ncu dram__bytes_read + write of this kernel on this workload
-                         # (profiles/r1g_traffic.csv: 12.05 GB per 52 232-iteration launch), scaled by iterations
-                         "traffic": 12.05e9 / 52232 * iters_total,
-                         "traffic_note": "exchange buffers of the cooperative passes (W, Q.dx) written through to HBM; "
-                                         "2 % of HBM bandwidth, the kernel is FP64-pipe / latency bound",
+                         "traffic": (traffic["dram_bytes_per_iteration"] * iters_total) if traffic else None,
+                         "traffic_note": (traffic or {}).get("source", "no ncu capture of this build is committed (profiles/r2_traffic.json)"),
                          "peak_source": "FP64 FMA micro-kernel measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
                          "flops_per_iteration": f_iter(C3["n"], C3["m_q"], C3["m_l"]),
                          "iterations_per_launch": iters_total, "kernel_ms": kern_ms},
+            "parity": {"checked": int(par_sum[0].item()), "status_mismatches": int(par_sum[1].item()),
+                       "max_rel_obj_diff": float(par_max[0].item()), "tolerance": 1e-6,
+                       "note": "every rank checks a strided sample of its own children against the CPU oracle"},
         }
+        if strong:
+            line["strong_scaling_4096"] = strong
         if world == 1 and not args.no_cpu_baseline:
             from oracle import ipm
-            ipm.build()
             cores = cpu_cores()
             S = min(args.cpu_sample, B)
             dense = ipm.dense_arrays(model)
             ipm.solve_batch(model, XL[:cores], XU[:cores], xs, threads=cores, dense=dense)
             t0 = time.perf_counter()
-            o = ipm.solve_batch(model, XL[:S], XU[:S], xs, threads=cores, dense=dense)
+            ipm.solve_batch(model, XL[:S], XU[:S], xs, threads=cores, dense=dense)
             dt = time.perf_counter() - t0
-            same = o["status"] == status[:S]
-            okk = o["status"] == 1
-            rel = np.abs(o["obj"] - obj_dev[:S]) / np.maximum(1.0, np.abs(o["obj"]))
             line["cpu_baseline"] = {"value": S / dt, "unit": "relaxations/s", "cores": cores, "kind": "port",
                                     "sample": f"first {S} children of the step's batch, one relaxation per thread; "
-                                              "CPU restatement of the Bonmin/Ipopt path (Ipopt 3.13 unavailable offline)"}
-            line["parity"] = {"checked": int(S), "status_mismatches": int((~same).sum()),
-                              "max_rel_obj_diff": float(rel[okk & same].max(initial=0.0)), "tolerance": 1e-6}
+                                              "CPU restatement of the Bonmin/Ipopt path — NOT Ipopt (Ipopt 3.13 cannot be built offline)"}
+        if world == 1 and not args.no_sweep:
+            line["sweep"] = sweep_section(eng, model, xs, dev, stream)
         if world == 1 and not args.no_bb:
             line["bb"] = bb_section(args, local_rank)
         if world == 1 and not args.no_oa:

@@ -12,7 +12,7 @@
 //                which is what the blocked back-substitution multiplies with
 #pragma once
 
-namespace bnlp {
+namespace BNLP_NS {
 
 // ---- H[i,k] += sign * sum_{c<K} M[c][i] M[c][k],  lo <= k <= i < hi,  lo % 8 == 0, K % 4 == 0.
 // M: K rows of length ld (ld = 4 mod 8 doubles: conflict-free fragments), zero for i in [hi, roundup8(hi)).
@@ -389,4 +389,4 @@ __device__ __forceinline__ bool chol3(double *H, int N, int Nrows, double *S, in
   return true;
 }
 
-}  // namespace bnlp
+}  // namespace BNLP_NS

@@ -14,7 +14,12 @@
 
 #include "../../include/bnlp.h"
 
-namespace bnlp {
+// The device headers are written in `namespace BNLP_NS` (default: bnlp) so that a translation unit can compile a second
+// copy of them with other compile-time parameters (bnlp_launch_coop256.cu: BNLP_NT = 256 in namespace bnlp256).
+#ifndef BNLP_NS
+#define BNLP_NS bnlp
+#endif
+namespace BNLP_NS {
 
 constexpr int EV_NT = 256;
 constexpr int TV = BNLP_MAX_TERM_VARS;                 // max variables of a term
@@ -666,4 +671,4 @@ __global__ void oa_compact_kernel(EvalModelDev M, OaArgs A, const int *row_start
 
 #endif  // BNLP_EVAL_KERNELS
 
-}  // namespace bnlp
+}  // namespace BNLP_NS

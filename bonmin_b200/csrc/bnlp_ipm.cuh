@@ -19,7 +19,7 @@
 
 #include "bnlp_eval.cuh"
 
-namespace bnlp {
+namespace BNLP_NS {
 
 #ifndef BNLP_NT
 #define BNLP_NT 512
@@ -776,7 +776,8 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
       if (phase1) {
         if (vl1 <= 0.0) to_main = true;
         else if (conv || acceptable_cnt >= o.acceptable_iter) {
-          if (viol_max > o.infeas_tol) { status = ST_provenInfeasible; done = true; break; }
+          // (an only "acceptable" phase-1 optimum proves infeasibility only beyond what its own error E0 could explain)
+          if (viol_max > (conv ? o.infeas_tol : fmax(o.infeas_tol, 10.0 * E0))) { status = ST_provenInfeasible; done = true; break; }
           to_main = true;
         }
       } else {
@@ -1299,4 +1300,4 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
   }
 }
 
-}  // namespace bnlp
+}  // namespace BNLP_NS

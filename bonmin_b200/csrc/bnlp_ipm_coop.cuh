@@ -18,7 +18,7 @@
 
 #include "bnlp_ipm.cuh"
 
-namespace bnlp {
+namespace BNLP_NS {
 namespace cg = cooperative_groups;
 
 #if defined(UEXP) && UEXP == 2
@@ -35,9 +35,9 @@ __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
                : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-}  // namespace bnlp
+}  // namespace BNLP_NS
 #include "bnlp_dense.cuh"
-namespace bnlp {
+namespace BNLP_NS {
 
 // ---- H[i,k] += sign * sum_c M[c][i] M[c][k], lo <= k <= i < hi, 8x8 tiles on the FP64 tensor pipe.
 // M: K rows (K multiple of 4) of length ld in shared memory, zero outside [lo,hi) within the touched tile range.
@@ -708,7 +708,8 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
     if (phase1) {
       if (vl1 <= 0.0) to_main = true;
       else if (conv || acceptable_cnt >= o.acceptable_iter) {
-        if (viol_max > o.infeas_tol) { status = ST_provenInfeasible; return 2; }
+        // (an only "acceptable" phase-1 optimum proves infeasibility only beyond what its own error E0 could explain)
+        if (viol_max > (conv ? o.infeas_tol : fmax(o.infeas_tol, 10.0 * E0))) { status = ST_provenInfeasible; return 2; }
         to_main = true;
       }
     } else {
@@ -1270,4 +1271,4 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
 #undef it_ad
 
 
-}  // namespace bnlp
+}  // namespace BNLP_NS

@@ -1,17 +1,17 @@
 // The cooperative IPM kernel built a second time with 256 threads per CTA, for models small enough that two CTAs fit
-// one SM (two children per SM interleave their latency chains).  The whole header set is compiled into namespace
-// bnlp256 by renaming the namespace token; the argument structs have the same layout as in namespace bnlp.
+// one SM (two children per SM interleave their latency chains).  The device headers are compiled into namespace
+// bnlp256 (BNLP_NS); the argument structs have the same layout as in namespace bnlp.
 #include <cuda_runtime.h>
 
 #include "../../include/bnlp.h"
 #define BNLP_NT 256
-#define bnlp bnlp256
+#define BNLP_NS bnlp256
 #include "bnlp_internal.h"
-namespace bnlp {
+namespace bnlp256 {
 constexpr double kInfD = 1e19;
+using bnlp::HostModel;
 }
 #include "bnlp_ipm_coop.cuh"
-#undef bnlp
 
 cudaError_t bnlp_coop256_set_smem(size_t smem) {
   cudaError_t e = cudaFuncSetAttribute(bnlp256::ipm_coop_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

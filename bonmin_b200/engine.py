@@ -52,7 +52,7 @@ class OaTols(ctypes.Structure):
 
 EXPORTS = ["bnlp_last_error", "bnlp_problem_from_nl", "bnlp_problem_from_tape", "bnlp_problem_free",
            "bnlp_problem_sizes", "bnlp_problem_info", "bnlp_engine_create", "bnlp_engine_free", "bnlp_eval_batch",
-           "bnlp_solve_batch", "bnlp_solve_batch_device", "bnlp_oa_capacity", "bnlp_oa_batch", "bnlp_engine_stats",
+           "bnlp_solve_batch", "bnlp_solve_batch_device", "bnlp_oa_capacity", "bnlp_oa_x2_width", "bnlp_oa_batch", "bnlp_engine_stats",
            "bnlp_engine_launches", "bnlp_measure_fp64_peak", "bnlp_bb_run_cb", "bnlp_bb_run_cb2", "bnlp_bb_run_engine", "bnlp_dive_run_cb", "bnlp_dive_run_engine", "bnlp_violation_batch",
            "bnlp_benders_batch", "bnlp_branching_tqp", "bnlp_tqp_solve_batch",
            "bnlp_extract_linear_relaxation", "bnlp_constraint_oa_batch", "bnlp_engine_sizes",
@@ -386,8 +386,24 @@ class Engine:
             info = self.problem.info()
         XL = _d(info["xl"] if XL is None else XL)
         XU = _d(info["xu"] if XU is None else XU)
-        Du = None if DUALS is None else _d(np.atleast_2d(DUALS))
-        X2a = None if X2 is None else _d(np.atleast_2d(X2))
+        Du = None
+        if DUALS is not None:
+            Du = np.atleast_2d(np.asarray(DUALS, float))
+            if Du.shape[0] == 1 and B > 1:       # one multiplier vector for every point (the reference's getRowPrice())
+                Du = np.repeat(Du, B, axis=0)
+            if Du.shape != (B, 2 * n + self.m):
+                raise ValueError(f"oa_batch: DUALS must be {B} x {2 * n + self.m}, got {Du.shape}")
+            Du = _d(Du)
+        X2a = None
+        if X2 is not None:
+            # the width of an X2 row depends on whether the objective cut is generated (it is tested against the LP's alpha
+            # column): a short row would be over-read by the library
+            w = lib().bnlp_oa_x2_width(self.h, int(get_obj))
+            X2a = np.atleast_2d(np.asarray(X2, float))
+            if X2a.shape[0] != B or X2a.shape[1] < w:
+                raise ValueError(f"oa_batch: X2 must be {B} x {w} for get_obj={get_obj} on this model "
+                                 f"(n = {n}; the objective cut needs the LP's alpha column), got {X2a.shape}")
+            X2a = _d(X2a[:, :w])
         t = tols or OaTols(1e-8, 1e-17, 1e-8, 1e19, 0)
         self._ck(lib().bnlp_oa_batch(self.h, B, _vp(X), _vp(Du), _vp(XL), _vp(XU), _vp(X2a), float(theta),
                                      int(get_obj), ctypes.byref(t), _vp(row_start), _vp(col), _vp(val), _vp(LB),
@@ -477,7 +493,14 @@ class Engine:
         n = self.n
         X = _d(np.atleast_2d(X))
         B = X.shape[0]
-        Du = None if DUALS is None else _d(np.atleast_2d(DUALS))
+        Du = None
+        if DUALS is not None:
+            Du = np.atleast_2d(np.asarray(DUALS, float))
+            if Du.shape[0] == 1 and B > 1:       # one multiplier vector for every point (the reference's getRowPrice())
+                Du = np.repeat(Du, B, axis=0)
+            if Du.shape != (B, 2 * n + self.m):
+                raise ValueError(f"oa_batch: DUALS must be {B} x {2 * n + self.m}, got {Du.shape}")
+            Du = _d(Du)
         xl = None if XL is None else _d(XL)
         xu = None if XU is None else _d(XU)
         rl, ci, cv = np.zeros(B, np.int32), np.zeros((B, n), np.int32), np.zeros((B, n))

@@ -373,7 +373,7 @@ BbResult bb_run(TMINLP2TNLP &root, BatchSolveFn solve, const BbOptions &opt, Tqp
   // later NLP: src/CbcBonmin/BonCbc.cpp:452,492-505)
   si.initialSolve();
   R.nlp_solves++;
-  if (!si.isProvenOptimal()) { R.status = app.providerErrors() ? 3 : si.isProvenPrimalInfeasible() ? 1 : 2; R.seconds = now_s() - t0; return R; }
+  if (!si.isProvenOptimal()) { R.status = app.providerErrors() ? 3 : si.isProvenPrimalInfeasible() ? 1 : 4; R.failed_nodes += !app.providerErrors() && !si.isProvenPrimalInfeasible(); R.seconds = now_s() - t0; return R; }
   root.setxInit(n, root.x_sol.data());
   std::priority_queue<Node *, std::vector<Node *>, Cmp> heap;
   Node *first = new Node{root.x_l, root.x_u, root.obj_value, 0};
@@ -416,13 +416,22 @@ BbResult bb_run(TMINLP2TNLP &root, BatchSolveFn solve, const BbOptions &opt, Tqp
           nd->solved = true; nd->obj = res[q].obj; nd->status = (int)res[q].status; nd->x.assign(res[q].x(), res[q].x() + n);
         }
       } 
-      // 2. fathoming, incumbents, candidate lists
+      // 2. fathoming, incumbents, candidate lists.  Only a PROVEN infeasible node is fathomed; a node whose NLP ended in an
+      // abandoned status (iteration limit, computation error: OsiTMINLPInterface::isAbandoned) is an unsolved NLP — the
+      // reference stops (nlp_failure_behavior stop) or drops it with a warning (fathom), it never reads it as infeasible
       std::vector<Node *> open;
       std::vector<BatchedStrongBranchingSolver::NodeRequest> reqs;
+      bool stop_unsolved = false;
       for (Node *nd : batch) {
         R.nodes++;
         R.served_from_sb_cache += (nd != first && need.empty());
         const bool optimal = nd->status == TNLPSolver::solvedOptimal || nd->status == TNLPSolver::solvedOptimalTol;
+        if (!optimal && nd->status != TNLPSolver::provenInfeasible) {
+          R.failed_nodes++;
+          if (opt.nlp_failure_behavior == 0) stop_unsolved = true;
+          delete nd;
+          continue;
+        }
         if (!optimal || nd->obj >= cutoff) { delete nd; continue; }
         auto frac = candidates_of(nd->x);
         if (frac.empty()) {
@@ -441,6 +450,7 @@ BbResult bb_run(TMINLP2TNLP &root, BatchSolveFn solve, const BbOptions &opt, Tqp
         open.push_back(nd);
         reqs.push_back(std::move(rq));
       }
+      if (stop_unsolved) { for (Node *nd : open) delete nd; R.status = 4; break; }
       if (open.empty()) continue;
       // 3. ONE batch for the strong-branching children of every open node of the round
       const double tp0 = now_s();
@@ -473,9 +483,13 @@ BbResult bb_run(TMINLP2TNLP &root, BatchSolveFn solve, const BbOptions &opt, Tqp
           Node *ch = new Node{nd->xl, nd->xu, nd->obj, nd->depth + 1};
           if (w == 0) ch->xu[bcol] = std::floor(nd->x[bcol]); else ch->xl[bcol] = std::ceil(nd->x[bcol]);
           const B200Solver::Child *c = fixed_any ? nullptr : sb.lookup(bcol, w == 1);
-          if (c) { ch->solved = true; ch->obj = c->obj; ch->status = (int)c->status; ch->x.assign(c->x(), c->x() + n);
-                   if (c->status == 1 || c->status == 2) ch->bound = std::max(nd->obj, c->obj); }
-          if (ch->solved && !(ch->status == 1 || ch->status == 2)) { delete ch; continue; }   // pre-solved and infeasible
+          // a strong-branching solve that did not finish (HotInfo status 2) says nothing about the child: it goes to the
+          // heap unsolved and gets its own node NLP
+          if (c && (c->status == 1 || c->status == 2 || c->status == TNLPSolver::provenInfeasible)) {
+            ch->solved = true; ch->obj = c->obj; ch->status = (int)c->status; ch->x.assign(c->x(), c->x() + n);
+            if (c->status == 1 || c->status == 2) ch->bound = std::max(nd->obj, c->obj);
+          }
+          if (ch->solved && ch->status == TNLPSolver::provenInfeasible) { delete ch; continue; }   // pre-solved and infeasible
           heap.push(ch);
         }
         delete nd;
@@ -499,7 +513,15 @@ BbResult bb_run(TMINLP2TNLP &root, BatchSolveFn solve, const BbOptions &opt, Tqp
       si.resolve();
       R.nlp_solves++;
     }
-    if (!si.isProvenOptimal()) { delete nd; continue; }           // infeasible or failed node: fathom
+    if (!si.isProvenOptimal() && !si.isProvenPrimalInfeasible()) {
+      // unsolved NLP (abandoned status): never fathomed as infeasible.  nlp_failure_behavior stop = the reference's
+      // newUnsolvedError (BonOsiTMINLPInterface.cpp:2639-2644), fathom = pretendFailIsInfeasible_
+      R.failed_nodes++;
+      delete nd;
+      if (opt.nlp_failure_behavior == 0) { R.status = 4; break; }
+      continue;
+    }
+    if (!si.isProvenOptimal()) { delete nd; continue; }           // proven infeasible node: fathom
     const double obj = root.obj_value;
     if (obj >= cutoff) { delete nd; continue; }
     const std::vector<double> x = root.x_sol;
@@ -559,8 +581,11 @@ BbResult bb_run(TMINLP2TNLP &root, BatchSolveFn solve, const BbOptions &opt, Tqp
       for (int j = 0; j < n && same; ++j)
         if (j != bcol && (nd->xl[j] != root.x_l[j] || nd->xu[j] != root.x_u[j])) same = false;
       if (same && !res.empty() && !qp_mode) c = sb.lookup(bcol, w == 1);   // QP children are surrogates, never node results
-      if (c) { ch[w]->solved = true; ch[w]->obj = c->obj; ch[w]->status = (int)c->status; ch[w]->x.assign(c->x(), c->x() + n);
-               if (c->status == 1 || c->status == 2) ch[w]->bound = std::max(obj, c->obj); }
+      // (an unfinished strong-branching solve is not a node result: that child is solved again as a node)
+      if (c && (c->status == 1 || c->status == 2 || c->status == TNLPSolver::provenInfeasible)) {
+        ch[w]->solved = true; ch[w]->obj = c->obj; ch[w]->status = (int)c->status; ch[w]->x.assign(c->x(), c->x() + n);
+        if (c->status == 1 || c->status == 2) ch[w]->bound = std::max(obj, c->obj);
+      }
     }
     // follow the preferred way first, keep the other on the heap (probed-dive flavour, BonDiver.cpp:255-316)
     dive = ch[bway];
@@ -570,6 +595,8 @@ BbResult bb_run(TMINLP2TNLP &root, BatchSolveFn solve, const BbOptions &opt, Tqp
   while (!heap.empty()) { R.best_bound = std::min(R.best_bound < -1e99 ? 1e100 : R.best_bound, heap.top()->bound); delete heap.top(); heap.pop(); }
   if (dive) delete dive;
   if (R.status == 0) { R.status = R.best_obj < 1e99 ? 0 : 1; R.best_bound = R.best_obj; }
+  if (R.failed_nodes && opt.log_level > 0)
+    fprintf(stderr, "[bb] %d node NLP(s) stayed unsolved (%s)\n", R.failed_nodes, opt.nlp_failure_behavior ? "fathomed" : "search stopped");
   if (app.providerErrors()) R.status = 3;
   R.ipm_iterations = si.totalIterations() + app.totalBatchIterations() + sb.qpIterations();
   R.seconds = now_s() - t0;

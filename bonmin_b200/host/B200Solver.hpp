@@ -189,9 +189,13 @@ struct BbOptions {
   double time_limit = 1e10;
   int log_level = 0;
   std::vector<int> priorities;          // empty, or n values: only the fractional integers of LOWEST value are candidates
+  // nlp_failure_behavior (BonOsiTMINLPInterface.cpp:233-240): 0 = stop (the reference throws newUnsolvedError when a node
+  // NLP stays unsolved, :2639-2644), 1 = fathom (pretendFailIsInfeasible_: the node is dropped with a warning)
+  int nlp_failure_behavior = 0;
 };
 struct BbResult {
-  int status = 0;               // 0 optimal, 1 infeasible, 2 node/time limit
+  int status = 0;               // 0 optimal, 1 infeasible, 2 node/time limit, 3 provider error, 4 a node NLP stayed unsolved
+  int failed_nodes = 0;         // node NLPs that ended in an abandoned status even after the re-solve
   double best_obj = 1e100, best_bound = -1e100;
   std::vector<double> best_x;
   int nodes = 0, nlp_solves = 0, sb_batches = 0, sb_children = 0, served_from_sb_cache = 0;

@@ -45,6 +45,7 @@ int bnlp_bb_run_cb3(int n, int m, const int *var_type, const double *xl, const d
     if (o->parallel_nodes > 0) opt.parallel_nodes = o->parallel_nodes;
     opt.variable_selection = o->variable_selection;
     if (o->priorities) opt.priorities.assign(o->priorities, o->priorities + n);
+    opt.nlp_failure_behavior = o->nlp_failure_behavior;
   }
   TqpSolveFn qfn;
   if (qp_cb)
@@ -60,7 +61,7 @@ int bnlp_bb_run_cb3(int n, int m, const int *var_type, const double *xl, const d
     };
   BbResult r = bb_run(root, fn, opt, qfn, cfn);
   res->status = r.status; res->nodes = r.nodes; res->nlp_solves = r.nlp_solves; res->sb_batches = r.sb_batches;
-  res->sb_children = r.sb_children; res->served_from_sb_cache = r.served_from_sb_cache;
+  res->sb_children = r.sb_children; res->served_from_sb_cache = r.served_from_sb_cache; res->failed_nodes = r.failed_nodes;
   res->ipm_iterations = r.ipm_iterations; res->best_obj = r.best_obj; res->best_bound = r.best_bound; res->seconds = r.seconds;
   if (best_x && !r.best_x.empty()) memcpy(best_x, r.best_x.data(), sizeof(double) * n);
   return r.status == 3 ? -1 : 0;   // the arithmetic provider failed: an error, not a search result

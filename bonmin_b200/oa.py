@@ -29,9 +29,14 @@ class EngineProvider:
         self.vtype = info["var_type"]
         self.x0 = info["x0"]
         self._oa_out = {}
+        # multipliers of the LAST NLP solve: the interface's getRowPrice() (all zero before the first solve, as the
+        # reference's duals_sol_: a ranged row then gets no cut side at all, :1968-1974)
+        self.duals = np.zeros(2 * self.n + self.m)
 
     def solve(self, XL, XU, x0):
-        return self.eng.solve_batch(XL, XU, x0)
+        r = self.eng.solve_batch(XL, XU, x0)
+        self.duals = np.array(r["duals"][-1])
+        return r
 
     def extract(self, x, duals):
         r = self.eng.extract_linear_relaxation(x, duals, get_obj=True)
@@ -46,9 +51,13 @@ class EngineProvider:
         return float(v[0])
 
     def oa(self, X, X2=None, theta=0.0):
+        """getOuterApproximation(cs, x, getObj = 1, x2, theta) at every row of X.  As in the reference the side of a ranged /
+        equality nonlinear row that is linearised is picked by the multipliers of the last NLP solve
+        (BonOsiTMINLPInterface.cpp:1952,1968-1974: duals = getRowPrice()): for a convex g only the binding side is a valid
+        outer approximation.  X2 rows are whole LP points (alpha column included when the objective cut exists)."""
         X = np.atleast_2d(X)
         # the cut buffers of each batch size are kept and page-locked: every pass of a loop reuses them
-        r = self.eng.oa_batch(X, None, self.xl, self.xu, X2=X2, theta=theta, get_obj=1, out=self._oa_out.get(len(X)), pin=True)
+        r = self.eng.oa_batch(X, self.duals, self.xl, self.xu, X2=X2, theta=theta, get_obj=1, out=self._oa_out.get(len(X)), pin=True)
         self._oa_out[len(X)] = r
         out = []
         for k in range(len(r["src_row"])):
@@ -57,6 +66,14 @@ class EngineProvider:
             a, b = r["row_start"][k], r["row_start"][k + 1]
             out.append((int(r["src_row"][k]), r["col"][a:b].tolist(), r["val"][a:b].tolist(), float(r["lb"][k]), float(r["ub"][k])))
         return out
+
+
+def _lp_point(x_lp, n):
+    """An LP point as getOuterApproximation's x2: the n columns plus the alpha column (0 if the LP has none)."""
+    x = np.zeros(n + 1)
+    k = min(len(x_lp), n + 1)
+    x[:k] = np.asarray(x_lp, float)[:k]
+    return x[None, :]
 
 
 def _solve_master(n_cols, rows, obj, obj_offset, col_lb, col_ub, integer, cutoff):
@@ -88,7 +105,9 @@ def ecp_rounds(provider, lp, rounds=5, abs_violation_tol=1e-6, rel_violation_tol
     """EcpCuts::generateCuts (src/Algorithms/OaGenerators/BonEcpCuts.cpp:46-143) on an LP relaxation `lp` (what
     provider.extract returns): while the LP optimum violates the nonlinear rows (getNonLinearitiesViolation), linearise
     them AT THE LP POINT (getOuterApproximation with getObj = 1), install the cuts, re-solve.  Returns dict(obj = LP
-    bound after the rounds (1e308 if the LP became infeasible), violation, rounds, cuts, rows = the enlarged row list)."""
+    bound after the rounds (1e308 if the LP became infeasible), violation, rounds, cs = every cut generated (what the
+    reference returns in its OsiCuts), cuts = len(cs), installed = those that went into the LP, rows = the enlarged row
+    list)."""
     P = provider
     n = P.n
     rows = list(lp["rows"])
@@ -98,7 +117,7 @@ def ecp_rounds(provider, lp, rounds=5, abs_violation_tol=1e-6, rel_violation_tol
     col_lb = np.concatenate([P.xl, [-DMAX]])[:ncols]
     col_ub = np.concatenate([P.xu, [DMAX]])[:ncols]
     integ = np.zeros(ncols, int) if integer is None else integer
-    out = dict(rounds=0, cuts=0, violation=0.0, obj=None)
+    out = dict(rounds=0, cuts=0, installed=0, cs=[], violation=0.0, obj=None)
 
     def lp_solve():
         st, x, val = _solve_master(ncols, rows, obj, lp["obj_offset"], col_lb, col_ub, integ, 1e100)
@@ -116,10 +135,12 @@ def ecp_rounds(provider, lp, rounds=5, abs_violation_tol=1e-6, rel_violation_tol
         if not (viol > abs_violation_tol and viol > rel_violation_tol * orig):
             break
         cuts = [c for c in P.oa(x[:n][None, :]) if not (c[0] == P.m and ncols == n)]
+        out["cs"].extend(cuts)          # EcpCuts hands the cuts of EVERY round back in `cs` — the last round's too, which
+        out["cuts"] += len(cuts)        # are generated but neither installed in the LP nor re-solved (:86)
         if not cuts or i + 1 >= rounds:
             break
         rows.extend(cuts)
-        out["cuts"] += len(cuts)
+        out["installed"] += len(cuts)
         out["rounds"] += 1
         st, x, val = lp_solve()
         if st != 0:
@@ -243,7 +264,7 @@ def feasibility_check(provider, lp, col_lb, col_ub, x_lp, cutoff, integer_tolera
             if out["incumbent"] is None or ub < out["incumbent"][0]:
                 out["incumbent"] = (ub, xs.copy())
             out["cutoff"] = ub * (1 - cutoff_increment) if ub > 0 else ub * (1 + cutoff_increment)
-        cuts = P.oa(xs[None, :], X2=(x_lp[:n][None, :] if add_only_violated else None))
+        cuts = P.oa(xs[None, :], X2=(_lp_point(x_lp, n) if add_only_violated else None))
         cuts = [c for c in cuts if not (c[0] == P.m and lp["ncols"] == n)]
         lp["rows"].extend(cuts)
         out["cuts"] += len(cuts)
@@ -277,7 +298,7 @@ def nlp_optim_cuts(provider, node_lb, node_ub, x_lp, add_only_violated=False):
     st, xs = int(r["status"][0]), r["x"][0]
     if st in (-3, -2):            # isAbandoned() || isIterationLimitReached(): "Unsolved NLP ... exit"
         raise RuntimeError("Unsolved NLP ... exit")
-    cuts = provider.oa(xs[None, :], X2=(x_lp[:n][None, :] if add_only_violated else None))
+    cuts = provider.oa(xs[None, :], X2=(_lp_point(x_lp, n) if add_only_violated else None))
     sol = None
     if st in (1, 2) and np.abs(xs[ints] - np.floor(xs[ints] + 0.5)).max(initial=0.0) <= 1e-7:
         sol = (float(r["obj"][0]), xs.copy())

@@ -178,7 +178,10 @@ int bnlp_solve_batch_device(bnlp_engine *, int dev_index, int B, const double *d
 /* Outer-approximation rows at B points = B x OsiTMINLPInterface::getOuterApproximation
  * (src/Interfaces/BonOsiTMINLPInterface.cpp:1924-2107 incl. cleanNnz :1881-1919).
  * X: B x n; DUALS: B x (2n+m) or NULL (multipliers pick the side of ranged rows); XL/XU: n column bounds used by
- * cleanNnz; X2 (B x n or NULL) + theta: violation filter; getObj as in the reference (0/1/2).
+ * cleanNnz; X2 + theta: violation filter, X2 = the LP points the cuts are tested against, B x bnlp_oa_x2_width() or
+ * NULL: the width is n + 1 whenever the objective cut is generated (getObj == 2, or getObj == 1 on a model with a
+ * nonlinear objective) because that cut is tested against the LP's alpha column x2[n] (:2077-2090), else n;
+ * getObj as in the reference (0/1/2).
  * Output is CSR with a fixed capacity of (m_nl + 1) rows per point:
  *   row_start: B*(m_nl+1)+1, col_idx/val: capacity from bnlp_oa_capacity(), LB/UB: B*(m_nl+1),
  *   src_row: B*(m_nl+1) (constraint index, m for the objective cut, -1 = row not generated). */
@@ -191,6 +194,7 @@ typedef struct bnlp_oa_tols {
                             constraint cut (BonOsiTMINLPInterface.cpp:2018-2020); 1 = drop cuts violated by < theta */
 } bnlp_oa_tols;
 int bnlp_oa_capacity(const bnlp_engine *, int B, int *rows_per_point, size_t *nnz_capacity);
+int bnlp_oa_x2_width(const bnlp_engine *, int getObj);   /* doubles per row of X2 for this getObj (n or n + 1) */
 int bnlp_oa_batch(bnlp_engine *, int B, const double *X, const double *DUALS, const double *XL, const double *XU,
                   const double *X2, double theta, int getObj, const bnlp_oa_tols *tols, int *row_start,
                   int *col_idx, double *val, double *LB, double *UB, int *src_row);
@@ -273,12 +277,18 @@ typedef struct bnlp_bb_options {
                                   value are candidates (OsiChooseVariable::setupList as kept by
                                   BonChooseVariable::setupList, Branching/BonChooseVariable.cpp:307-584).
                                   bnlp_bb_run_engine uses the problem's own (.nl suffix) priorities when this is NULL */
+  int nlp_failure_behavior;    /* a node NLP that ends in an abandoned status (iteration limit, computation error:
+                                  OsiTMINLPInterface::isAbandoned, BonOsiTMINLPInterface.cpp:2907-2920) is never read as
+                                  infeasible: 0 = stop, status 4 (the reference's `nlp_failure_behavior stop`: newUnsolvedError,
+                                  :2639-2644), 1 = fathom that node and go on (`fathom`, pretendFailIsInfeasible_) */
 } bnlp_bb_options;
 typedef struct bnlp_bb_result {
-  int status;                 /* 0 optimal, 1 infeasible, 2 limit reached, 3 the batch-solve provider returned an error (the call returns -1) */
+  int status;                 /* 0 optimal, 1 infeasible, 2 limit reached, 3 the batch-solve provider returned an error (the
+                                 call returns -1), 4 a node NLP stayed unsolved and nlp_failure_behavior = stop */
   int nodes, nlp_solves, sb_batches, sb_children, served_from_sb_cache;
   long long ipm_iterations;
   double best_obj, best_bound, seconds;
+  int failed_nodes;           /* node NLPs that ended in an abandoned status */
 } bnlp_bb_result;
 /* arithmetic provider = any batch solver with bnlp_solve_batch's meaning (tests pass the CPU oracle here) */
 int bnlp_bb_run_cb(int n, int m, const int *var_type, const double *xl, const double *xu, const double *gl,

@@ -493,7 +493,11 @@ int Solver::run(const double *xl, const double *xu, const double *x0, double *ob
       if (viol_l1() <= 0.0) { leave_phase1(); continue; }
       if (conv || acceptable_cnt >= o.acceptable_iter) {
         double vmax = viol_scaled();
-        if (vmax > o.infeas_tol) {  // Infeasible_Problem_Detected -> provenInfeasible
+        // strict convergence: the phase-1 optimum is known to tol, any violation above infeas_tol is real.  Merely
+        // "acceptable" termination leaves an error of E0 in the phase-1 optimum: a violation that this error could
+        // explain (thin or tangential feasible set) is not a proof, the child goes back to the main phase instead
+        const double vthr = conv ? o.infeas_tol : std::max(o.infeas_tol, 10.0 * E0);
+        if (vmax > vthr) {  // Infeasible_Problem_Detected -> provenInfeasible
           write_point(false);
           return finish(provenInfeasible, orig_violation());  // BonTMINLP2TNLP.cpp:503-505
         }

@@ -18,9 +18,12 @@ class OracleProvider:
         self.ev = SE.Evaluator(model)
         self.n, self.m = model.n, model.m
         self.xl, self.xu, self.vtype, self.x0 = model.xl, model.xu, model.vtype, model.x0
+        self.duals = np.zeros(2 * self.n + self.m)
 
     def solve(self, XL, XU, x0):
-        return self.ipm.solve_batch(self.model, XL, XU, x0, threads=4, dense=self.dense)
+        r = self.ipm.solve_batch(self.model, XL, XU, x0, threads=4, dense=self.dense)
+        self.duals = np.array(r["duals"][-1])       # getRowPrice() of the last solve picks the side of ranged rows
+        return r
 
     def extract(self, x, duals):
         return SE.extract_linear_relaxation(self.ev, x, duals, get_obj=True)
@@ -31,7 +34,7 @@ class OracleProvider:
     def oa(self, X, X2=None, theta=0.0):
         out = []
         for x in np.atleast_2d(X):
-            out.extend(SE.outer_approximation(self.ev, x, None, self.xl, self.xu, get_obj=1))
+            out.extend(SE.outer_approximation(self.ev, x, self.duals, self.xl, self.xu, get_obj=1))
         return out
 
 
@@ -85,7 +88,8 @@ def test_ecp_rounds_tighten_the_lp_bound(oracle_ipm):
         assert r["obj"] >= prev - 1e-9 and r["obj"] <= root["obj"][0] + 1e-6 * abs(root["obj"][0])
         prev = r["obj"]
         if rounds == 1:
-            assert r["cuts"] == 0            # numRounds 1: the cuts are generated but the LP is not re-solved (:86)
+            # numRounds 1: the cuts are generated and handed back, but not installed and the LP is not re-solved (:86)
+            assert r["installed"] == 0 and r["cuts"] == len(r["cs"]) > 0
         else:
             assert r["cuts"] > 0 and r["violation"] <= (prev_viol if prev_viol is not None else 1e300) + 1e-9
         prev_viol = r["violation"]
@@ -143,3 +147,24 @@ def test_single_tree_engine_matches_oracle(bnlp_lib, oracle_ipm):
             assert g["status"] == c["status"] == 0
             assert g["best_obj"] == pytest.approx(c["best_obj"], rel=1e-6, abs=1e-8)
         eng.close()
+
+
+def test_ranged_nonlinear_row_is_cut_on_its_binding_side_only(oracle_ipm):
+    """A ranged nonlinear row (g_l <= g(x) <= g_u, g convex): only the side that binds at the NLP optimum is a valid outer
+    approximation; the reference picks it by the sign of the row's multiplier (BonOsiTMINLPInterface.cpp:1968-1974, duals =
+    getRowPrice() of the last NLP solve).  Without multipliers both sides are linearised, and the lower-side cut
+    `grad g(xbar).(x - xbar) + g(xbar) >= g_l` is not an outer approximation of a convex g."""
+    m = I.syn_miqcp(10, 5, 3, 2, 11)
+    gl = np.array(m.gl, float)
+    gl[:3] = np.asarray(m.gu)[:3] - 400.0            # the three quadratic rows become ranged; the upper side is the near one
+    m["gl"] = gl
+    P = OracleProvider(m, oracle_ipm)
+    r = oa.run_oa(P)
+    b = _bb_opt(m, oracle_ipm, number_strong_branch=5)
+    assert r["status"] == b["status"] == 0
+    assert r["best_obj"] == pytest.approx(b["best_obj"], rel=2e-5, abs=2e-5)
+    root = P.solve(np.asarray(m.xl)[None, :], np.asarray(m.xu)[None, :], m.x0)
+    one_sided = [c for c in P.oa(root["x"][0][None, :]) if c[0] < 3]
+    assert len(one_sided) == 3 and all(lb <= -1e100 and ub < 1e100 for _, _, _, lb, ub in one_sided)
+    two_sided = [c for c in SE.outer_approximation(P.ev, root["x"][0], None, m.xl, m.xu, get_obj=1) if c[0] < 3]
+    assert all(lb > -1e100 and ub < 1e100 for _, _, _, lb, ub in two_sided)      # what a provider without duals would add
