@@ -90,7 +90,7 @@ struct Device {
   DBuf<int> e_int;   // packed integer arrays of the eval tape
   DBuf<double> e_dbl;
   // solve buffers
-  DBuf<double> dXL, dXU, dX0, dOBJ, dX, dG, dD, ws, cxw, cW, cxd;
+  DBuf<double> dXL, dXU, dX0, dOBJ, dX, dG, dD, dD0, ws, cxw, cW, cxd;
   DBuf<int> cidle;
   DBuf<int> dST, dIT, queue;
   DBuf<double> dPXL, dPXU, dCB;   // bnlp_solve_children: parent bounds and the one changed bound of each child
@@ -459,7 +459,7 @@ extern "C" void bnlp_engine_free(bnlp_engine *E) {
   for (Device &D : E->devs) {
     cudaSetDevice(D.id);
     for (auto *b : {&D.c, &D.A, &D.Qp, &D.Qf, &D.row_sgn, &D.row_bnd, &D.gl, &D.gu, &D.xl, &D.xu, &D.e_dbl, &D.dXL, &D.dXU,
-                    &D.dX0, &D.dOBJ, &D.dX, &D.dG, &D.dD, &D.ws, &D.cxw, &D.cW, &D.cxd, &D.eq_bnd, &D.eX, &D.eLAM, &D.eF, &D.eG, &D.eGF, &D.eJ, &D.eH,
+                    &D.dX0, &D.dOBJ, &D.dX, &D.dG, &D.dD, &D.dD0, &D.ws, &D.cxw, &D.cW, &D.cxd, &D.eq_bnd, &D.eX, &D.eLAM, &D.eF, &D.eG, &D.eGF, &D.eJ, &D.eH,
                     &D.eX2, &D.eDU, &D.eU, &D.oVal, &D.oLB, &D.oUB, &D.dPXL, &D.dPXU, &D.dCB})
       b->release();
     for (auto *b : {&D.qidx, &D.row_fn, &D.fn_row_up, &D.fn_row_lo, &D.e_int, &D.dST, &D.dIT, &D.queue, &D.cidle, &D.eq_fn, &D.fn_eq, &D.oRS, &D.oCI,
@@ -475,7 +475,7 @@ extern "C" void bnlp_engine_free(bnlp_engine *E) {
 
 static int launch_ipm(bnlp_engine *E, Device &D, int B, const double *dXL, const double *dXU, const double *dX0,
                       int x0_per_child, double *dOBJ, int *dST, int *dIT, double *dX, double *dG, double *dD,
-                      cudaStream_t stream) {
+                      cudaStream_t stream, const double *dDUAL0 = nullptr, int dual0_per_child = 0) {
   if (!E->ipm_supported) { set_err("bnlp_solve_batch: " + E->ipm_unsupported_why); return -2; }
   if (B <= 0) return 0;
   int ctas = E->opt.ctas_per_device > 0 ? E->opt.ctas_per_device : D.sms;
@@ -492,6 +492,7 @@ static int launch_ipm(bnlp_engine *E, Device &D, int B, const double *dXL, const
   CK(cudaMemsetAsync(D.stats.p, 0, 12 * sizeof(long long), stream));
   IpmArgs a{};
   a.B = B; a.XL = dXL; a.XU = dXU; a.X0 = dX0; a.x0_stride = x0_per_child ? E->M.n : 0;
+  a.DUAL0 = dDUAL0; a.dual0_stride = dual0_per_child ? 2 * E->M.n + E->M.m : 0;
   a.OBJ = dOBJ; a.STATUS = dST; a.ITERS = dIT; a.X = dX; a.G = dG; a.DUALS = dD;
   a.queue = D.queue.p; a.ws = D.ws.p; a.ws_stride = E->ws_doubles; a.h_in_smem = E->h_in_smem; a.stats = D.stats.p;
   a.phase_cycles = getenv("BNLP_PHASE_TIMERS") ? D.stats.p + 2 : nullptr;
@@ -639,12 +640,13 @@ extern "C" int bnlp_solve_children(bnlp_engine *E, int P, const double *parent_X
   return collect_batch(E, B, per, OBJ, STATUS, ITERS, X, G, DUALS);
 }
 
-extern "C" int bnlp_solve_batch(bnlp_engine *E, int B, const double *XL, const double *XU, const double *X0,
-                                int x0_per_child, double *OBJ, int *STATUS, int *ITERS, double *X, double *G,
-                                double *DUALS) {
+extern "C" int bnlp_solve_batch_warm(bnlp_engine *E, int B, const double *XL, const double *XU, const double *X0,
+                                     int x0_per_child, const double *DUAL0, int dual0_per_child, double *OBJ, int *STATUS,
+                                     int *ITERS, double *X, double *G, double *DUALS) {
   if (!E) { set_err("null engine"); return -1; }
   if (B <= 0) return 0;
   const int n = E->M.n, m = E->M.m, nd = (int)E->devs.size();
+  const int nmul = 2 * n + m;
   const int per = (B + nd - 1) / nd;  // contiguous child shards, one per device
   // phase 1: enqueue copies + kernels on every device
   for (int d = 0; d < nd; ++d) {
@@ -654,7 +656,8 @@ extern "C" int bnlp_solve_batch(bnlp_engine *E, int B, const double *XL, const d
     CK(cudaSetDevice(D.id));
     if (D.dXL.reserve((size_t)nb * n) || D.dXU.reserve((size_t)nb * n) || D.dX0.reserve((size_t)(x0_per_child ? nb : 1) * n) ||
         D.dOBJ.reserve(nb) || D.dST.reserve(nb) || D.dIT.reserve(nb) || D.dX.reserve((size_t)nb * n) ||
-        D.dG.reserve((size_t)nb * std::max(m, 1)) || D.dD.reserve((size_t)nb * (2 * n + m))) {
+        D.dG.reserve((size_t)nb * std::max(m, 1)) || D.dD.reserve((size_t)nb * nmul) ||
+        (DUAL0 && D.dD0.reserve((size_t)(dual0_per_child ? nb : 1) * nmul))) {
       set_err("device allocation failed");
       return -1;
     }
@@ -663,11 +666,21 @@ extern "C" int bnlp_solve_batch(bnlp_engine *E, int B, const double *XL, const d
     CK(cudaMemcpyAsync(D.dXU.p, XU + (size_t)b0 * n, (size_t)nb * n * 8, cudaMemcpyHostToDevice, D.stream));
     CK(cudaMemcpyAsync(D.dX0.p, X0 + (x0_per_child ? (size_t)b0 * n : 0), (size_t)(x0_per_child ? nb : 1) * n * 8,
                        cudaMemcpyHostToDevice, D.stream));
+    if (DUAL0)
+      CK(cudaMemcpyAsync(D.dD0.p, DUAL0 + (dual0_per_child ? (size_t)b0 * nmul : 0), (size_t)(dual0_per_child ? nb : 1) * nmul * 8,
+                         cudaMemcpyHostToDevice, D.stream));
     int rc = launch_ipm(E, D, nb, D.dXL.p, D.dXU.p, D.dX0.p, x0_per_child, D.dOBJ.p, D.dST.p, D.dIT.p,
-                        X ? D.dX.p : nullptr, G ? D.dG.p : nullptr, DUALS ? D.dD.p : nullptr, D.stream);
+                        X ? D.dX.p : nullptr, G ? D.dG.p : nullptr, DUALS ? D.dD.p : nullptr, D.stream,
+                        DUAL0 ? D.dD0.p : nullptr, dual0_per_child);
     if (rc) return rc;
   }
   return collect_batch(E, B, per, OBJ, STATUS, ITERS, X, G, DUALS);
+}
+
+extern "C" int bnlp_solve_batch(bnlp_engine *E, int B, const double *XL, const double *XU, const double *X0,
+                                int x0_per_child, double *OBJ, int *STATUS, int *ITERS, double *X, double *G,
+                                double *DUALS) {
+  return bnlp_solve_batch_warm(E, B, XL, XU, X0, x0_per_child, nullptr, 0, OBJ, STATUS, ITERS, X, G, DUALS);
 }
 
 // Page-lock a caller-owned host buffer that is passed to the batch calls again and again (cut buffers, bound arrays):

@@ -41,6 +41,7 @@ struct IpmOpt {
   int max_iter = 3000, acceptable_iter = 15;
   double dual_inf_tol = 1.0, constr_viol_tol = 1e-4, compl_inf_tol = 1e-4;
   double bound_relax = 1e-8, bound_push = 0.01, bound_frac = 0.01;
+  double warm_push = 1e-3;   // warm_start_{bound,slack_bound,mult_bound}_push / _frac of Ipopt (warm_start_init_point yes)
   double tau_min = 0.99, sigma_min = 1e-6, sigma_max = 100, mu_min = 1e-11, mu_max_fact = 1e3, mu_max = 1e5;
   double s_max = 100, kappa_sigma = 1e10;
   double gamma_theta = 1e-4, gamma_phi = 1e-8, eta_phi = 1e-8, s_phi = 2.3, s_theta = 1.1, delta = 1.0;
@@ -80,6 +81,10 @@ struct IpmArgs {
   int B;
   const double *XL, *XU, *X0;   // device: B x n, B x n, (x0_stride ? B x n : n)
   int x0_stride;
+  // warm start (IpoptSolver::ReOptimizeTNLP after setWarmStart, BonIpoptSolver.cpp:369-419): multipliers [z_L | z_U | lambda]
+  // the solve starts from, (dual0_stride ? B x (2n+m) : 2n+m), or null = cold start (unit multipliers)
+  const double *DUAL0;
+  int dual0_stride;
   double *OBJ; int *STATUS; int *ITERS;
   double *X, *G, *DUALS;        // B x n, B x m, B x (2n+m); any may be null
   int *queue;                   // work-queue counter (zeroed by the host)
@@ -501,12 +506,13 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
         else {
           if (f & F_HASL) lr = l - o.bound_relax * fmax(1.0, fabs(l));
           if (f & F_HASU) ur = u + o.bound_relax * fmax(1.0, fabs(u));
+          const double bp = A.DUAL0 ? o.warm_push : o.bound_push, bf = A.DUAL0 ? o.warm_push : o.bound_frac;   // warm start: 1e-3
           if ((f & F_HASL) && (f & F_HASU)) {
-            const double pl = fmin(o.bound_push * fmax(1.0, fabs(lr)), o.bound_frac * (ur - lr));
-            const double pu = fmin(o.bound_push * fmax(1.0, fabs(ur)), o.bound_frac * (ur - lr));
+            const double pl = fmin(bp * fmax(1.0, fabs(lr)), bf * (ur - lr));
+            const double pu = fmin(bp * fmax(1.0, fabs(ur)), bf * (ur - lr));
             xx = fmin(fmax(xx, lr + pl), ur - pu);
-          } else if (f & F_HASL) xx = fmax(xx, lr + o.bound_push * fmax(1.0, fabs(lr)));
-          else if (f & F_HASU) xx = fmin(xx, ur - o.bound_push * fmax(1.0, fabs(ur)));
+          } else if (f & F_HASL) xx = fmax(xx, lr + bp * fmax(1.0, fabs(lr)));
+          else if (f & F_HASU) xx = fmin(xx, ur - bp * fmax(1.0, fabs(ur)));
         }
         Lr[j] = lr; Ur[j] = ur;
       } else {  // elastic t: fixed at 0 outside phase 1
@@ -653,21 +659,26 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
     }
 
     // helpers (all block-uniform)
-    auto init_slacks_mults = [&]() {
+    // warm (first initialisation only): the caller's multipliers [z_L | z_U | lambda] (unscaled) start the solve, each
+    // pushed to at least warm_push, slacks pushed by warm_push; a phase switch restarts from unit multipliers
+    auto init_slacks_mults = [&](bool warm) {
+      const double *d0w = (warm && A.DUAL0) ? A.DUAL0 + (size_t)child * A.dual0_stride : nullptr;
       for (int r = tid; r < R; r += IPM_NT) {
-        const double h = fsc[r] * val[M.row_fn[r]] - (phase1 ? x[n] : 0.0);
-        s[r] = fmax(bb[r] - h, o.bound_push * fmax(1.0, fabs(bb[r])));
-        v[r] = 1.0;
+        const int fn = M.row_fn[r];
+        const double h = fsc[r] * val[fn] - (phase1 ? x[n] : 0.0);
+        s[r] = fmax(bb[r] - h, (d0w ? o.warm_push : o.bound_push) * fmax(1.0, fabs(bb[r])));
+        v[r] = d0w ? fmax(o.warm_push, fmax(0.0, (fsc[r] > 0 ? 1.0 : -1.0) * d0w[2 * n + fn - 1]) * sf / fabs(fsc[r])) : 1.0;
       }
       for (int j = tid; j < N; j += IPM_NT) {
         const int f = flg[j];
-        zL[j] = (!(f & F_FIXED) && (f & F_HASL)) ? 1.0 : 0.0;
-        zU[j] = (!(f & F_FIXED) && (f & F_HASU)) ? 1.0 : 0.0;
+        const bool w = d0w && j < n;
+        zL[j] = (!(f & F_FIXED) && (f & F_HASL)) ? (w ? fmax(o.warm_push, d0w[j] * sf) : 1.0) : 0.0;
+        zU[j] = (!(f & F_FIXED) && (f & F_HASU)) ? (w ? fmax(o.warm_push, d0w[n + j] * sf) : 1.0) : 0.0;
       }
-      for (int e = tid; e < E; e += IPM_NT) ye[e] = 0.0;
+      for (int e = tid; e < E; e += IPM_NT) ye[e] = d0w ? d0w[2 * n + M.eq_fn[e] - 1] * sf / esc[e] : 0.0;
       __syncthreads();
     };
-    if (!done) init_slacks_mults();
+    if (!done) init_slacks_mults(true);
     PH_MARK(9);
 
     while (!done) {
@@ -801,7 +812,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
         phase1 = false; iters_main = 0;
         if (tid == 0) { flg[n] |= F_FIXED; x[n] = 0.0; }
         __syncthreads();
-        init_slacks_mults();
+        init_slacks_mults(false);
         theta_init = -1; mu_max = -1; acceptable_cnt = 0;
         ++iters;
         continue;
@@ -812,7 +823,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
         const double vm = fmax(0.0, viol_max), T = fmax(1.0, vm);
         if (tid == 0) { flg[n] &= ~F_FIXED; Lr[n] = -T; x[n] = 1.1 * vm + 0.1 * T; }
         __syncthreads();
-        init_slacks_mults();
+        init_slacks_mults(false);
         theta_init = -1; mu_max = -1; acceptable_cnt = 0;
       };
       if (to_p1) { enter_phase1(); ++iters; continue; }

@@ -401,16 +401,21 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
   it_nz = 0; it_avg_compl = 0; it_cviol = 0; it_dual_inf = 0; it_s_d = 1; it_viol_max = 0; it_of = 0; it_tcur = 0;
   it_mu = 0; it_ap_max = 0; it_ad = 0;
 
-  auto init_slacks_mults = [&]() {
+  // warm (first initialisation only): the caller's multipliers [z_L | z_U | lambda] (unscaled) start the solve, each pushed
+  // to at least warm_push, slacks pushed by warm_push; a phase switch restarts from unit multipliers
+  auto init_slacks_mults = [&](bool warm) {
+    const double *d0w = (warm && A.DUAL0) ? A.DUAL0 + (size_t)child * A.dual0_stride : nullptr;
     for (int r = tid; r < R; r += IPM_NT) {
-      const double h = fsc[r] * val[M.row_fn[r]] - (phase1 ? x[n] : 0.0);
-      s[r] = fmax(bb[r] - h, o.bound_push * fmax(1.0, fabs(bb[r])));
-      v[r] = 1.0;
+      const int fn = M.row_fn[r];
+      const double h = fsc[r] * val[fn] - (phase1 ? x[n] : 0.0);
+      s[r] = fmax(bb[r] - h, (d0w ? o.warm_push : o.bound_push) * fmax(1.0, fabs(bb[r])));
+      v[r] = d0w ? fmax(o.warm_push, fmax(0.0, (fsc[r] > 0 ? 1.0 : -1.0) * d0w[2 * n + fn - 1]) * sf / fabs(fsc[r])) : 1.0;
     }
     for (int j = tid; j < N; j += IPM_NT) {
       const int f = flg[j];
-      zL[j] = (!(f & F_FIXED) && (f & F_HASL)) ? 1.0 : 0.0;
-      zU[j] = (!(f & F_FIXED) && (f & F_HASU)) ? 1.0 : 0.0;
+      const bool w = d0w && j < n;
+      zL[j] = (!(f & F_FIXED) && (f & F_HASL)) ? (w ? fmax(o.warm_push, d0w[j] * sf) : 1.0) : 0.0;
+      zU[j] = (!(f & F_FIXED) && (f & F_HASU)) ? (w ? fmax(o.warm_push, d0w[n + j] * sf) : 1.0) : 0.0;
     }
     __syncthreads();
   };
@@ -420,7 +425,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
     const double vm = fmax(0.0, it_viol_max), T = fmax(1.0, vm);
     if (tid == 0) { flg[n] &= ~F_FIXED; Lr[n] = -T; x[n] = 1.1 * vm + 0.1 * T; }
     __syncthreads();
-    init_slacks_mults();
+    init_slacks_mults(false);
     theta_init = -1; mu_cap = -1; acceptable_cnt = 0;
   };
 
@@ -452,12 +457,13 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
         else {
           if (f & F_HASL) lr = l - o.bound_relax * fmax(1.0, fabs(l));
           if (f & F_HASU) ur = u + o.bound_relax * fmax(1.0, fabs(u));
+          const double bp = A.DUAL0 ? o.warm_push : o.bound_push, bf = A.DUAL0 ? o.warm_push : o.bound_frac;   // warm start: 1e-3
           if ((f & F_HASL) && (f & F_HASU)) {
-            const double pl = fmin(o.bound_push * fmax(1.0, fabs(lr)), o.bound_frac * (ur - lr));
-            const double pu = fmin(o.bound_push * fmax(1.0, fabs(ur)), o.bound_frac * (ur - lr));
+            const double pl = fmin(bp * fmax(1.0, fabs(lr)), bf * (ur - lr));
+            const double pu = fmin(bp * fmax(1.0, fabs(ur)), bf * (ur - lr));
             xx = fmin(fmax(xx, lr + pl), ur - pu);
-          } else if (f & F_HASL) xx = fmax(xx, lr + o.bound_push * fmax(1.0, fabs(lr)));
-          else if (f & F_HASU) xx = fmin(xx, ur - o.bound_push * fmax(1.0, fabs(ur)));
+          } else if (f & F_HASL) xx = fmax(xx, lr + bp * fmax(1.0, fabs(lr)));
+          else if (f & F_HASU) xx = fmin(xx, ur - bp * fmax(1.0, fabs(ur)));
         }
         Lr[j] = lr; Ur[j] = ur;
       } else {
@@ -541,7 +547,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
       bb[r] = b + o.bound_relax * fmax(1.0, fabs(b));
     }
     __syncthreads();
-    init_slacks_mults();
+    init_slacks_mults(true);
     return false;
   };
 
@@ -739,7 +745,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
           if (flg[j] & F_FIXED) fixlist[f++] = j;
         s_nfix = f;
       }
-      init_slacks_mults();
+      init_slacks_mults(false);
       theta_init = -1; mu_cap = -1; acceptable_cnt = 0;
       ++iters;
       return 1;

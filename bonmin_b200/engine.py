@@ -52,7 +52,7 @@ class OaTols(ctypes.Structure):
 
 EXPORTS = ["bnlp_last_error", "bnlp_problem_from_nl", "bnlp_problem_from_tape", "bnlp_problem_free",
            "bnlp_problem_sizes", "bnlp_problem_info", "bnlp_engine_create", "bnlp_engine_free", "bnlp_eval_batch",
-           "bnlp_solve_batch", "bnlp_solve_batch_device", "bnlp_oa_capacity", "bnlp_oa_x2_width", "bnlp_oa_batch", "bnlp_engine_stats",
+           "bnlp_solve_batch", "bnlp_solve_batch_warm", "bnlp_solve_batch_device", "bnlp_oa_capacity", "bnlp_oa_x2_width", "bnlp_oa_batch", "bnlp_engine_stats",
            "bnlp_engine_launches", "bnlp_measure_fp64_peak", "bnlp_bb_run_cb", "bnlp_bb_run_cb2", "bnlp_bb_run_engine", "bnlp_dive_run_cb", "bnlp_dive_run_engine", "bnlp_violation_batch",
            "bnlp_benders_batch", "bnlp_branching_tqp", "bnlp_tqp_solve_batch",
            "bnlp_extract_linear_relaxation", "bnlp_constraint_oa_batch", "bnlp_engine_sizes",
@@ -98,6 +98,7 @@ def lib():
         L.bnlp_engine_free.argtypes = [c_void]
         L.bnlp_eval_batch.argtypes = [c_void, c_int, c_void, c_void, c_dbl, c_void, c_void, c_void, c_void, c_void]
         L.bnlp_solve_batch.argtypes = [c_void, c_int, c_void, c_void, c_void, c_int] + [c_void] * 6
+        L.bnlp_solve_batch_warm.argtypes = [c_void, c_int, c_void, c_void, c_void, c_int, c_void, c_int] + [c_void] * 6
         L.bnlp_solve_children.argtypes = [c_void, c_int, c_void, c_void, c_int] + [c_void] * 5 + [c_int] + [c_void] * 6
         L.bnlp_solve_batch_device.argtypes = [c_void, c_int, c_int, c_void, c_void, c_void, c_int] + [c_void] * 7
         L.bnlp_oa_capacity.argtypes = [c_void, c_int, P_int, ctypes.POINTER(ctypes.c_size_t)]
@@ -278,10 +279,11 @@ class Engine:
         if rc != 0:
             raise BnlpError(f"engine error {rc}: {_err()}")
 
-    def solve_batch(self, XL, XU, X0, want_x=True, want_g=True, want_duals=True, out=None, pin=False):
+    def solve_batch(self, XL, XU, X0, want_x=True, want_g=True, want_duals=True, out=None, pin=False, dual0=None):
         """B x TNLPSolver::OptimizeTNLP with host buffers (copies inside the call).  `out`: the dict of an earlier call
         with the same B and outputs, whose arrays are reused; `pin`: page-lock freshly allocated result arrays (for a
-        caller that keeps them with `out=`)."""
+        caller that keeps them with `out=`).  dual0: multipliers [z_L | z_U | lambda] of a warm start (2n+m values for
+        every child, or B rows): B x ReOptimizeTNLP after setWarmStart (bnlp_solve_batch_warm)."""
         n, m = self.n, self.m
         XL = _d(np.atleast_2d(XL))
         XU = _d(np.atleast_2d(XU))
@@ -302,8 +304,14 @@ class Engine:
                 for a in (OBJ, ST, IT, X, G, D):
                     if a is not None:
                         pin_array(a)
-        self._ck(lib().bnlp_solve_batch(self.h, B, _vp(XL), _vp(XU), _vp(X0), per_child, _vp(OBJ), _vp(ST), _vp(IT),
-                                        _vp(X), _vp(G), _vp(D)))
+        D0 = None
+        if dual0 is not None:
+            D0 = _d(dual0)
+            if D0.shape[-1] != 2 * n + m or (D0.ndim == 2 and D0.shape[0] != B):
+                raise ValueError(f"solve_batch: dual0 must be (2n+m,) or ({B}, 2n+m), got {D0.shape}")
+        self._ck(lib().bnlp_solve_batch_warm(self.h, B, _vp(XL), _vp(XU), _vp(X0), per_child, _vp(D0),
+                                             int(D0 is not None and D0.ndim == 2), _vp(OBJ), _vp(ST), _vp(IT),
+                                             _vp(X), _vp(G), _vp(D)))
         return dict(obj=OBJ, status=ST, iters=IT, x=X, g=G, duals=D)
 
     def solve_children(self, parent_XL, parent_XU, child_parent, child_col, child_way, child_bound, X0, want_x=True,

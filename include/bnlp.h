@@ -169,6 +169,16 @@ int bnlp_solve_children(bnlp_engine *, int P, const double *parent_XL, const dou
                         const int *child_parent, const int *child_col, const int *child_way, const double *child_bound,
                         const double *X0, int x0_per_parent, double *OBJ, int *STATUS, int *ITERS, double *X, double *G,
                         double *DUALS);
+/* Warm-started re-solve = IpoptSolver::ReOptimizeTNLP after setWarmStart (src/Interfaces/Ipopt/BonIpoptSolver.cpp:180-220,
+ * 369-419; OsiTMINLPInterface::resolve, src/Interfaces/BonOsiTMINLPInterface.cpp:2851-2874; exercised by
+ * test/InterfaceTest.cpp:165-189).  DUAL0: the multipliers [z_L | z_U | lambda] the solve starts from — one vector of
+ * 2n+m for every child (dual0_per_child = 0) or B rows — with Ipopt's warm_start_init_point = yes treatment: the start point
+ * and the slacks are pushed inside by 1e-3 (warm_start_bound_push / _bound_frac / _slack_bound_push / _slack_bound_frac)
+ * instead of 1e-2, every multiplier is taken from DUAL0 and pushed to at least 1e-3 (warm_start_mult_bound_push).
+ * DUAL0 == NULL is bnlp_solve_batch. */
+int bnlp_solve_batch_warm(bnlp_engine *, int B, const double *XL, const double *XU, const double *X0, int x0_per_child,
+                          const double *DUAL0, int dual0_per_child, double *OBJ, int *STATUS, int *ITERS, double *X,
+                          double *G, double *DUALS);
 /* Same with DEVICE pointers on device `dev_index` of the engine (inputs already resident in HBM; runs on `stream`,
  * a cudaStream_t passed as void*, no synchronisation). */
 int bnlp_solve_batch_device(bnlp_engine *, int dev_index, int B, const double *dXL, const double *dXU,

@@ -58,7 +58,8 @@ def _p(a, t=ctypes.c_double):
     return a.ctypes.data_as(ctypes.POINTER(t))
 
 
-def solve_batch(model, XL, XU, x0, threads=1, max_iter=0, dense=None):
+def solve_batch(model, XL, XU, x0, threads=1, max_iter=0, dense=None, dual0=None):
+    """dual0: multipliers [z_L | z_U | lambda] of a warm start (one vector for all children or B rows) or None."""
     n, m = model.n, model.m
     XL = np.ascontiguousarray(np.atleast_2d(XL), dtype=np.float64)
     XU = np.ascontiguousarray(np.atleast_2d(XU), dtype=np.float64)
@@ -91,8 +92,12 @@ def solve_batch(model, XL, XU, x0, threads=1, max_iter=0, dense=None):
     ti = lambda a: np.ascontiguousarray(a if len(a) else [0], dtype=np.int32)  # noqa: E731
     tfn_a, tvs_a, tv_a, tos_a, top_a, tia_a = ti(tfn), ti(tvs), ti(tv), ti(tos), ti(top), ti(tia)
     tda_a = np.ascontiguousarray(tda if len(tda) else [0.0], dtype=np.float64)
-    lib().oracle_solve_batch(ci(n), ci(m), _p(xl), _p(xu), _p(gl), _p(gu), _p(c), _p(A), _p(qidx, ci), _p(Q),
-                             ci(len(tfn)), _p(tfn_a, ci), _p(tvs_a, ci), _p(tv_a, ci), _p(tos_a, ci), _p(top_a, ci),
-                             _p(tia_a, ci), _p(tda_a), ci(B), _p(XL), _p(XU), _p(x0), ci(per_child), ci(threads), ci(max_iter),
-                             _p(OBJ), _p(STATUS, ci), _p(ITERS, ci), _p(X), _p(G), _p(D), _p(P1, ci))
+    d0 = None if dual0 is None else np.ascontiguousarray(dual0, dtype=np.float64)
+    if d0 is not None and d0.shape[-1] != 2 * n + m:
+        raise ValueError("dual0 must have 2n+m entries per row")
+    lib().oracle_solve_batch_warm(ci(n), ci(m), _p(xl), _p(xu), _p(gl), _p(gu), _p(c), _p(A), _p(qidx, ci), _p(Q),
+                                  ci(len(tfn)), _p(tfn_a, ci), _p(tvs_a, ci), _p(tv_a, ci), _p(tos_a, ci), _p(top_a, ci),
+                                  _p(tia_a, ci), _p(tda_a), ci(B), _p(XL), _p(XU), _p(x0), ci(per_child),
+                                  None if d0 is None else _p(d0), ci(int(d0 is not None and d0.ndim == 2)), ci(threads),
+                                  ci(max_iter), _p(OBJ), _p(STATUS, ci), _p(ITERS, ci), _p(X), _p(G), _p(D), _p(P1, ci))
     return dict(obj=OBJ, status=STATUS, iters=ITERS, x=X, g=G, duals=D, phase1_iters=P1)

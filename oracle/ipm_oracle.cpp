@@ -129,6 +129,9 @@ struct OOpt {
   int max_iter = 3000, acceptable_iter = 15;
   double dual_inf_tol = 1.0, constr_viol_tol = 1e-4, compl_inf_tol = 1e-4;
   double bound_relax = 1e-8, bound_push = 0.01, bound_frac = 0.01;
+  // warm_start_init_point yes (BonIpoptSolver.cpp:415-419): warm_start_bound_push / _bound_frac / _slack_bound_push /
+  // _slack_bound_frac / _mult_bound_push, all 1e-3 (options_list_ipopt_content.tex, "Warm Start")
+  double warm_push = 1e-3;
   double tau_min = 0.99, sigma_min = 1e-6, sigma_max = 100, mu_min = 1e-11, mu_max_fact = 1e3, mu_max = 1e5;
   double s_max = 100, kappa_sigma = 1e10;
   double gamma_theta = 1e-4, gamma_phi = 1e-8, eta_phi = 1e-8, s_phi = 2.3, s_theta = 1.1, delta = 1.0;
@@ -276,18 +279,24 @@ struct Solver {
     }
     return t;
   }
-  void init_slacks_mults() {
+  // warm = the caller's multipliers [z_L | z_U | lambda] (DUAL0, unscaled) start the solve, every one of them pushed to at
+  // least warm_push (warm_start_mult_bound_push), slacks pushed by warm_push instead of bound_push; used for the FIRST
+  // initialisation only (a phase switch restarts from unit multipliers as before)
+  const double *dual0 = nullptr;
+  void init_slacks_mults(bool warm = false) {
+    warm = warm && dual0;
     for (int r = 0; r < R; ++r) {
       double sl = rows[r].b - h[r];
-      double push = o.bound_push * std::max(1.0, std::fabs(rows[r].b));
+      double push = (warm ? o.warm_push : o.bound_push) * std::max(1.0, std::fabs(rows[r].b));
       s[r] = std::max(sl, push);
-      v[r] = 1.0;
+      v[r] = warm ? std::max(o.warm_push, std::max(0.0, rows[r].sgn * dual0[2 * n + rows[r].fn - 1]) * sf / rows[r].sc) : 1.0;
     }
     for (int j = 0; j < N; ++j) {
-      zL[j] = (!fixed[j] && hasL[j]) ? 1.0 : 0.0;
-      zU[j] = (!fixed[j] && hasU[j]) ? 1.0 : 0.0;
+      const bool w = warm && j < n;
+      zL[j] = (!fixed[j] && hasL[j]) ? (w ? std::max(o.warm_push, dual0[j] * sf) : 1.0) : 0.0;
+      zU[j] = (!fixed[j] && hasU[j]) ? (w ? std::max(o.warm_push, dual0[n + j] * sf) : 1.0) : 0.0;
     }
-    for (int e = 0; e < E; ++e) ye[e] = 0.0;
+    for (int e = 0; e < E; ++e) ye[e] = warm ? dual0[2 * n + eqs[e].fn - 1] * sf / eqs[e].sc : 0.0;
   }
 
   int run(const double *xl, const double *xu, const double *x0, double *obj, int *iters, double *xout,
@@ -369,14 +378,15 @@ int Solver::run(const double *xl, const double *xu, const double *x0, double *ob
     if (hasL[j]) Lr[j] = L[j] - o.bound_relax * std::max(1.0, std::fabs(L[j]));
     if (hasU[j]) Ur[j] = U[j] + o.bound_relax * std::max(1.0, std::fabs(U[j]));
     double xx = x0[j];
+    const double bp = dual0 ? o.warm_push : o.bound_push, bf = dual0 ? o.warm_push : o.bound_frac;
     if (hasL[j] && hasU[j]) {
-      double pl = std::min(o.bound_push * std::max(1.0, std::fabs(Lr[j])), o.bound_frac * (Ur[j] - Lr[j]));
-      double pu = std::min(o.bound_push * std::max(1.0, std::fabs(Ur[j])), o.bound_frac * (Ur[j] - Lr[j]));
+      double pl = std::min(bp * std::max(1.0, std::fabs(Lr[j])), bf * (Ur[j] - Lr[j]));
+      double pu = std::min(bp * std::max(1.0, std::fabs(Ur[j])), bf * (Ur[j] - Lr[j]));
       xx = std::min(std::max(xx, Lr[j] + pl), Ur[j] - pu);
     } else if (hasL[j]) {
-      xx = std::max(xx, Lr[j] + o.bound_push * std::max(1.0, std::fabs(Lr[j])));
+      xx = std::max(xx, Lr[j] + bp * std::max(1.0, std::fabs(Lr[j])));
     } else if (hasU[j]) {
-      xx = std::min(xx, Ur[j] - o.bound_push * std::max(1.0, std::fabs(Ur[j])));
+      xx = std::min(xx, Ur[j] - bp * std::max(1.0, std::fabs(Ur[j])));
     }
     x[j] = xx;
   }
@@ -402,7 +412,7 @@ int Solver::run(const double *xl, const double *xu, const double *x0, double *ob
   uq.assign((size_t)(m + 1) * n, 0); gd.assign(m + 1, 0); du.assign(m + 1, 0);
   phase1 = false;
   build_rows_values();
-  init_slacks_mults();
+  init_slacks_mults(true);
 
   std::vector<double> H((size_t)N * N), rhs0(N), rhs1(N), dx(N), ds(R), dv(R), dzL(N), dzU(N), dye(E);
   std::vector<double> Sx(N), Ss(R), rc(R), gL(N), tmpR(R), Y, S, w0(N), w1(N), de0(E), de1(E);
@@ -843,14 +853,16 @@ void oracle_set_verbose(int v) { g_verbose = v; }
 
 // Solve B child relaxations (same model, per-child bounds XL/XU [B x n], shared start point x0 [n]
 // or per-child X0 [B x n] when x0_per_child != 0) on `threads` host threads.
+// DUAL0 (optional, n-shared or per child): multipliers [z_L | z_U | lambda] of a warm start (IpoptSolver with
+// warm_start_init_point yes, BonIpoptSolver.cpp:369-419; ReOptimizeTNLP after setWarmStart).
 // Outputs follow TMINLP2TNLP's result layout (BonTMINLP2TNLP.cpp:474-509).
-int oracle_solve_batch(int n, int m, const double *xl, const double *xu, const double *gl, const double *gu,
-                       const double *c, const double *A, const int *qidx, const double *Q, int n_terms,
-                       const int *term_fn, const int *term_var_start, const int *term_var, const int *term_op_start,
-                       const int *term_op, const int *term_iarg, const double *term_darg, int B,
-                       const double *XL, const double *XU, const double *X0, int x0_per_child, int threads,
-                       int max_iter, double *OBJ, int *STATUS, int *ITERS, double *X, double *G, double *DUALS,
-                       int *P1ITERS) {
+int oracle_solve_batch_warm(int n, int m, const double *xl, const double *xu, const double *gl, const double *gu,
+                            const double *c, const double *A, const int *qidx, const double *Q, int n_terms,
+                            const int *term_fn, const int *term_var_start, const int *term_var, const int *term_op_start,
+                            const int *term_op, const int *term_iarg, const double *term_darg, int B,
+                            const double *XL, const double *XU, const double *X0, int x0_per_child, const double *DUAL0,
+                            int dual0_per_child, int threads, int max_iter, double *OBJ, int *STATUS, int *ITERS, double *X,
+                            double *G, double *DUALS, int *P1ITERS) {
   OModel M{n, m, xl, xu, gl, gu, c, A, qidx, Q};
   M.n_terms = n_terms; M.term_fn = term_fn; M.term_var_start = term_var_start; M.term_var = term_var;
   M.term_op_start = term_op_start; M.term_op = term_op; M.term_iarg = term_iarg; M.term_darg = term_darg;
@@ -863,6 +875,7 @@ int oracle_solve_batch(int n, int m, const double *xl, const double *xu, const d
       if (b >= B) break;
       Solver S(M, opt);
       const double *x0 = x0_per_child ? X0 + (size_t)b * n : X0;
+      if (DUAL0) S.dual0 = dual0_per_child ? DUAL0 + (size_t)b * (2 * n + m) : DUAL0;
       STATUS[b] = S.run(XL + (size_t)b * n, XU + (size_t)b * n, x0, &OBJ[b], &ITERS[b], X + (size_t)b * n,
                         G + (size_t)b * m, DUALS + (size_t)b * (2 * n + m));
       if (P1ITERS) P1ITERS[b] = S.st.phase1_iters;
@@ -873,6 +886,18 @@ int oracle_solve_batch(int n, int m, const double *xl, const double *xu, const d
   for (int t = 0; t < threads; ++t) th.emplace_back(work);
   for (auto &t : th) t.join();
   return 0;
+}
+
+int oracle_solve_batch(int n, int m, const double *xl, const double *xu, const double *gl, const double *gu,
+                       const double *c, const double *A, const int *qidx, const double *Q, int n_terms,
+                       const int *term_fn, const int *term_var_start, const int *term_var, const int *term_op_start,
+                       const int *term_op, const int *term_iarg, const double *term_darg, int B,
+                       const double *XL, const double *XU, const double *X0, int x0_per_child, int threads,
+                       int max_iter, double *OBJ, int *STATUS, int *ITERS, double *X, double *G, double *DUALS,
+                       int *P1ITERS) {
+  return oracle_solve_batch_warm(n, m, xl, xu, gl, gu, c, A, qidx, Q, n_terms, term_fn, term_var_start, term_var,
+                                 term_op_start, term_op, term_iarg, term_darg, B, XL, XU, X0, x0_per_child, nullptr, 0,
+                                 threads, max_iter, OBJ, STATUS, ITERS, X, G, DUALS, P1ITERS);
 }
 
 }  // extern "C"

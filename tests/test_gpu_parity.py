@@ -415,3 +415,36 @@ def test_two_devices_in_one_process_match_one_device(bnlp_lib):
     a = e1.solve_children(m.xl[None, :], m.xu[None, :], cp, cc, cw, cb, xs)
     b = e2.solve_children(m.xl[None, :], m.xu[None, :], cp, cc, cw, cb, xs)
     assert np.array_equal(a["obj"], b["obj"]) and np.array_equal(a["status"], b["status"]) and np.array_equal(a["x"], b["x"])
+
+
+@pytest.mark.gpu
+def test_warm_started_resolve_parity(bnlp_lib, oracle_ipm):
+    """bnlp_solve_batch_warm = IpoptSolver::ReOptimizeTNLP after setWarmStart (BonIpoptSolver.cpp:180-220, 369-419; the
+    sequence of test/InterfaceTest.cpp:165-189: solve, getWarmStart, change a bound, setWarmStart, resolve): primal AND
+    dual start, warm_start_init_point = yes pushes (1e-3).  Same statuses and objectives as the CPU oracle, and as the cold
+    solves of the same children (1e-6); re-solving the parent itself from its own optimum takes a few iterations."""
+    from bonmin_b200.engine import Engine, Problem
+    for m, B in ((I.syn_miqcp(40, 20, 8, 8, 3), 64), (I.config_c2(), 96), (I.mytoy(), 0)):
+        eng = Engine(Problem.from_model(m))
+        root = eng.solve_batch(m.xl, m.xu, m.x0)
+        xs, du = root["x"][0], root["duals"][0]
+        again = eng.solve_batch(m.xl, m.xu, xs, dual0=du)
+        assert again["status"][0] == 1 and again["iters"][0] < root["iters"][0]
+        assert again["obj"][0] == pytest.approx(root["obj"][0], rel=1e-7)
+        if B:
+            XL, XU = I.c3_children(m, xs, B)
+        else:                                   # mytoy: the two children of test/InterfaceTest.cpp:165-189 (x >= 1, x <= 0)
+            XL, XU = np.tile(m.xl, (2, 1)), np.tile(m.xu, (2, 1))
+            XL[0, 2] = 1.0
+            XU[1, 2] = 0.0
+        cold = eng.solve_batch(XL, XU, xs)
+        warm = eng.solve_batch(XL, XU, xs, dual0=du)
+        per_child = eng.solve_batch(XL, XU, xs, dual0=np.tile(du, (len(XL), 1)))       # the B-row form of DUAL0
+        o = oracle_ipm.solve_batch(m, XL, XU, xs, threads=4, dual0=du)
+        assert np.array_equal(warm["status"], o["status"]) and np.array_equal(warm["status"], cold["status"])
+        assert np.array_equal(per_child["status"], warm["status"]) and np.array_equal(per_child["iters"], warm["iters"])
+        ok = o["status"] == 1
+        assert np.allclose(warm["obj"][ok], o["obj"][ok], rtol=1e-9, atol=1e-9)
+        assert np.allclose(warm["obj"][ok], cold["obj"][ok], rtol=1e-6, atol=1e-8)
+        assert np.abs(warm["iters"] - o["iters"]).max() <= 1
+        eng.close()
