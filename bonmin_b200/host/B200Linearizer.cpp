@@ -5,7 +5,7 @@ namespace Bonmin {
 void B200Linearizer::get_oas_batch(OsiCuts &cs, const double *X, int B, bool getObj, bool global) const {
   if (!model_ || B <= 0) return;
   OaRows r;
-  last_rc_ = oa_(B, X, model_->x_l.data(), model_->x_u.data(), getObj ? 1 : 0, tiny_, very_tiny_, rhs_relax_, infty_, r);
+  last_rc_ = oa_(B, X, model_->x_l_.data(), model_->x_u_.data(), getObj ? 1 : 0, tiny_, very_tiny_, rhs_relax_, infty_, r);
   if (last_rc_) return;
   const int slots = B * r.rows_per_point;
   for (int k = 0; k < slots; ++k) {
@@ -28,7 +28,7 @@ void B200Linearizer::get_refined_oa(OsiCuts &cs) const {
 void B200Linearizer::extract(OsiSolverInterface *si, const double *x, bool getObj) {
   if (!model_ || !si) return;
   LpRelaxation lp;
-  last_rc_ = extract_(x, model_->x_l.data(), model_->x_u.data(), getObj ? 1 : 0, tiny_, very_tiny_, rhs_relax_, infty_, lp);
+  last_rc_ = extract_(x, model_->x_l_.data(), model_->x_u_.data(), getObj ? 1 : 0, tiny_, very_tiny_, rhs_relax_, infty_, lp);
   if (last_rc_) return;
   const int nrows = (int)lp.row_lb.size();
   si->loadProblem(lp.n_cols, nrows, lp.row_start.data(), lp.col.data(), lp.val.data(), lp.col_lb.data(), lp.col_ub.data(),

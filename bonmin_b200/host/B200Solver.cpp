@@ -15,23 +15,63 @@ static double now_s() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-// Contract of OptimizeTNLP (BonIpoptSolver.cpp:134-176, Filter/BonFilterSolver.cpp:574-645): read sizes, bounds and
-// the start point from the TNLP, solve, and finish by filling x_sol / g_sol / duals_sol / obj_value exactly as
-// TMINLP2TNLP::finalize_solution would (BonTMINLP2TNLP.cpp:474-509).  An engine error maps to TNLPSolver::exception.
-TNLPSolver::ReturnStatus B200Solver::OptimizeTNLP(TMINLP2TNLP &t) {
+// Contract of OptimizeTNLP (BonIpoptSolver.cpp:134-176, Filter/BonFilterSolver.cpp:574-645), driven purely through the
+// Ipopt::TNLP virtuals like any Bonmin NLP plugin:
+//   get_nlp_info -> get_bounds_info -> get_starting_point(init_x, init_z = init_lambda = warm start enabled)
+//   -> solve -> finalize_solution(status, n, x, z_L, z_U, m, g, lambda, obj_value, NULL, NULL)
+// (TMINLP2TNLP::finalize_solution, BonTMINLP2TNLP.cpp:474-509, stores x_sol / g_sol / duals_sol = [z_L | z_U | lambda] /
+// obj_value).  The functions themselves are not evaluated through the TNLP: they live in the tape the engine was built from,
+// so n and m must be the engine's.  The all-fixed short cut of TNLPSolver::zeroDimension (BonTNLPSolver.cpp:78-161) is taken
+// inside the batch solve (same tests, same finalize_solution arguments).  A provider error maps to TNLPSolver::exception.
+static Ipopt::SolverReturn ipopt_status_of(int st) {
+  switch (st) {   // the inverse of IpoptSolver::solverReturnStatus (BonIpoptSolver.cpp:304-343)
+    case TNLPSolver::solvedOptimal: return Ipopt::SUCCESS;
+    case TNLPSolver::solvedOptimalTol: return Ipopt::STOP_AT_ACCEPTABLE_POINT;
+    case TNLPSolver::provenInfeasible: return Ipopt::LOCAL_INFEASIBILITY;
+    case TNLPSolver::iterationLimit: return Ipopt::MAXITER_EXCEEDED;
+    case TNLPSolver::computationError: return Ipopt::ERROR_IN_STEP_COMPUTATION;
+    case TNLPSolver::notEnoughFreedom: return Ipopt::TOO_FEW_DEGREES_OF_FREEDOM;
+    case TNLPSolver::illegalOption: return Ipopt::INVALID_OPTION;
+    default: return Ipopt::INTERNAL_ERROR;
+  }
+}
+
+TNLPSolver::ReturnStatus B200Solver::solve_tnlp(const Ipopt::SmartPtr<Ipopt::TNLP> &tnlp, bool warm) {
   const double t0 = now_s();
-  const int n = t.n, m = t.m;
+  Ipopt::Index n = 0, m = 0, nnz_jac = 0, nnz_h = 0;
+  Ipopt::TNLP::IndexStyleEnum style;
+  iterations_ = 0;
+  if (!tnlp->get_nlp_info(n, m, nnz_jac, nnz_h, style)) return illDefinedProblem;
+  std::vector<double> xl(n), xu(n), gl(std::max(m, 1)), gu(std::max(m, 1)), x0(n), d0((size_t)2 * n + m, 0.0);
+  if (!tnlp->get_bounds_info(n, xl.data(), xu.data(), m, gl.data(), gu.data())) return illDefinedProblem;
+  // warm start: primal AND dual start (warm_start_init_point yes, BonIpoptSolver.cpp:415-419); a TNLP that has no
+  // multipliers to give answers false, and the solve falls back to the primal start alone
+  bool have_duals = warm && tnlp->get_starting_point(n, true, x0.data(), true, d0.data(), d0.data() + n, m, true, d0.data() + 2 * n);
+  if (!have_duals && !tnlp->get_starting_point(n, true, x0.data(), false, nullptr, nullptr, m, false, nullptr)) return illDefinedProblem;
+  std::vector<double> x(n, 0.0), g(std::max(m, 1), 0.0), du((size_t)2 * n + m, 0.0);
   double obj = 0;
-  int st = 0, it = 0;
-  t.x_sol.assign(n, 0.0); t.g_sol.assign(m, 0.0); t.duals_sol.assign(2 * n + m, 0.0);
-  const int rc = solve_(1, t.x_l.data(), t.x_u.data(), t.x_init.data(), &obj, &st, &it, t.x_sol.data(), t.g_sol.data(),
-                        t.duals_sol.data());
+  int st = 0, it = 0, rc;
+  if (have_duals && solve_warm_) rc = solve_warm_(1, xl.data(), xu.data(), x0.data(), d0.data(), &obj, &st, &it, x.data(), g.data(), du.data());
+  else rc = solve_(1, xl.data(), xu.data(), x0.data(), &obj, &st, &it, x.data(), g.data(), du.data());
+  warm_started_last_ = have_duals && (bool)solve_warm_;
   cpu_time_ = now_s() - t0;
   iterations_ = it;
-  if (rc != 0) { provider_errors_++; error_code_ = rc; t.return_status = exception; return exception; }
-  t.obj_value = obj;
-  t.return_status = (ReturnStatus)st;
+  optimized_before_ = true;
+  if (rc != 0) { provider_errors_++; error_code_ = rc; return exception; }
+  // (for an infeasible child the engine's objective is the maximal constraint violation, which is what finalize_solution
+  // computes from ip_cq in the reference, BonTMINLP2TNLP.cpp:503-505)
+  tnlp->finalize_solution(ipopt_status_of(st), n, x.data(), du.data(), du.data() + n, m, g.data(), du.data() + 2 * n, obj, nullptr, nullptr);
   return (ReturnStatus)st;
+}
+
+TNLPSolver::ReturnStatus B200Solver::OptimizeTNLP(const Ipopt::SmartPtr<Ipopt::TNLP> &tnlp) {
+  // IpoptSolver::OptimizeTNLP (:134-176): a warm start is used only when it is enabled AND the solver has optimised before
+  return solve_tnlp(tnlp, enable_warm_start_ && optimized_before_);
+}
+TNLPSolver::ReturnStatus B200Solver::ReOptimizeTNLP(const Ipopt::SmartPtr<Ipopt::TNLP> &tnlp) {
+  // IpoptSolver::ReOptimizeTNLP (:180-220): re-optimises whenever it has optimised before; whether multipliers are used is
+  // the warm_start_init_point option that enableWarmStart / disableWarmStart set (:415-427)
+  return solve_tnlp(tnlp, enable_warm_start_ && optimized_before_);
 }
 
 bool B200Solver::Initialize(std::istream &is) {
@@ -63,25 +103,31 @@ const std::string *B200Solver::option(const std::string &name) const {
   return nullptr;
 }
 
-bool B200Solver::setWarmStart(const CoinWarmStart *ws, TMINLP2TNLP &tnlp) {   // BonIpoptSolver.cpp:369-401
-  if (!ws) return false;
-  if (ws->empty()) { disableWarmStart(); return true; }
-  if (ws->dualSize() > 0) { tnlp.setDualsInit(ws->dualSize(), ws->dual()); enableWarmStart(); }
+bool B200Solver::setWarmStart(const CoinWarmStart *warmstart, Ipopt::SmartPtr<TMINLP2TNLP> tnlp) {   // BonIpoptSolver.cpp:369-401
+  if (!warmstart) return false;
+  const IpoptWarmStart *ws = dynamic_cast<const IpoptWarmStart *>(warmstart);
+  if (ws == nullptr) return false;
+  if (ws->empty()) { disableWarmStart(); return true; }   // reset initial point and leave
+  if (ws->dualSize() > 0) { tnlp->setDualsInit(ws->dualSize(), ws->dual()); enableWarmStart(); }
   else disableWarmStart();
-  if (ws->primalSize() != tnlp.n) return false;
-  tnlp.setxInit(ws->primalSize(), ws->primal());
+  if (ws->primalSize() != tnlp->num_variables()) return false;
+  tnlp->setxInit(ws->primalSize(), ws->primal());
   return true;
 }
 
-CoinWarmStart *B200Solver::getUsedWarmStart(TMINLP2TNLP &tnlp) const {        // :347-356
-  if ((int)tnlp.x_init.size() < tnlp.n || tnlp.duals_init.empty()) return nullptr;
-  return new CoinWarmStart(tnlp.n, 2 * tnlp.n + tnlp.m, tnlp.x_init.data(), tnlp.duals_init.data());
+CoinWarmStart *B200Solver::getUsedWarmStart(Ipopt::SmartPtr<TMINLP2TNLP> tnlp) const {        // :347-356
+  if (tnlp->x_init() == nullptr || tnlp->duals_init() == nullptr) return nullptr;
+  return new IpoptWarmStart(tnlp->num_variables(), 2 * tnlp->num_variables() + tnlp->num_constraints(), tnlp->x_init(),
+                            tnlp->duals_init());
 }
 
-CoinWarmStart *B200Solver::getWarmStart(TMINLP2TNLP &tnlp) const {            // :357-366: the last solution and its multipliers
-  if ((int)tnlp.x_sol.size() != tnlp.n) return new CoinWarmStart();
-  const bool have_duals = (int)tnlp.duals_sol.size() == 2 * tnlp.n + tnlp.m;
-  return new CoinWarmStart(tnlp.n, have_duals ? 2 * tnlp.n + tnlp.m : 0, tnlp.x_sol.data(), have_duals ? tnlp.duals_sol.data() : nullptr);
+CoinWarmStart *B200Solver::getWarmStart(Ipopt::SmartPtr<TMINLP2TNLP> tnlp) const {            // :357-366: the last solution and its multipliers
+  return new IpoptWarmStart(tnlp, nullptr);
+}
+
+bool B200Solver::warmStartIsValid(const CoinWarmStart *ws) const {                            // :403-410
+  const IpoptWarmStart *iws = dynamic_cast<const IpoptWarmStart *>(ws);
+  return iws && !iws->empty();
 }
 
 const std::string &B200Solver::UnsolvedB200Error::errorName() const {
@@ -119,7 +165,7 @@ int B200Solver::OptimizeBatch(const TMINLP2TNLP &p, const std::vector<double> &X
   if ((int)obj_buf_.size() < B) { obj_buf_.resize(B); st_buf_.resize(B); it_buf_.resize(B); }
   double *X = x_block((size_t)B * n)->data();
   const double ts0 = now_s();
-  const int rc = solve_(B, XL.data(), XU.data(), p.x_init.data(), obj_buf_.data(), st_buf_.data(), it_buf_.data(), X, nullptr, nullptr);
+  const int rc = solve_(B, XL.data(), XU.data(), p.x_init_.data(), obj_buf_.data(), st_buf_.data(), it_buf_.data(), X, nullptr, nullptr);
   solve_seconds_ += now_s() - ts0;
   return unpack(rc, B, n, out);
 }
@@ -133,7 +179,7 @@ int B200Solver::OptimizeChildren(const TMINLP2TNLP &p, int P, const std::vector<
   int rc;
   const double ts0 = now_s();
   if (children_) {
-    rc = children_(P, PXL.data(), PXU.data(), B, cp.data(), cc.data(), cw.data(), cb.data(), p.x_init.data(), obj_buf_.data(),
+    rc = children_(P, PXL.data(), PXU.data(), B, cp.data(), cc.data(), cw.data(), cb.data(), p.x_init_.data(), obj_buf_.data(),
                    st_buf_.data(), it_buf_.data(), X);
   } else {
     if (xl_buf_.size() < (size_t)B * n) { xl_buf_.resize((size_t)B * n); xu_buf_.resize((size_t)B * n); }
@@ -142,7 +188,7 @@ int B200Solver::OptimizeChildren(const TMINLP2TNLP &p, int P, const std::vector<
       std::copy(&PXU[(size_t)cp[b] * n], &PXU[(size_t)cp[b] * n] + n, &xu_buf_[(size_t)b * n]);
       (cw[b] == 0 ? xu_buf_ : xl_buf_)[(size_t)b * n + cc[b]] = cb[b];
     }
-    rc = solve_(B, xl_buf_.data(), xu_buf_.data(), p.x_init.data(), obj_buf_.data(), st_buf_.data(), it_buf_.data(), X, nullptr, nullptr);
+    rc = solve_(B, xl_buf_.data(), xu_buf_.data(), p.x_init_.data(), obj_buf_.data(), st_buf_.data(), it_buf_.data(), X, nullptr, nullptr);
   }
   solve_seconds_ += now_s() - ts0;
   return unpack(rc, B, n, out);
@@ -153,8 +199,8 @@ void BatchedStrongBranchingSolver::markHotStart(OsiTMINLPInterface *si) {
   xl0_.assign(si->getColLower(), si->getColLower() + n);
   xu0_.assign(si->getColUpper(), si->getColUpper() + n);
   if (qp_) {   // BranchingTQP's constructor: freeze the node optimum and its multipliers (BonBranchingTQP.cpp:41-43)
-    xsol0_ = si->problem()->x_sol;
-    duals0_ = si->problem()->duals_sol;
+    xsol0_ = si->problem()->x_sol_;
+    duals0_ = si->problem()->duals_sol_;
   }
   if (!preloaded_) cache_.clear();
 }
@@ -248,7 +294,7 @@ TNLPSolver::ReturnStatus BatchedStrongBranchingSolver::solveFromHotStart(OsiTMIN
   const B200Solver::Child *c = (ndiff == 1) ? lookup(col, way == 1) : nullptr;
   if (!c) {  // not a prefetched child: solve it on the spot (batch of one) — same answer, just not amortised
     misses_++;
-    return si->solver()->OptimizeTNLP(*si->problem());
+    return si->solver()->OptimizeTNLP(Ipopt::SmartPtr<Ipopt::TNLP>(si->problem()));
   }
   hits_++;
   si->problem()->set_obj_value(c->obj);
@@ -259,38 +305,90 @@ TNLPSolver::ReturnStatus BatchedStrongBranchingSolver::solveFromHotStart(OsiTMIN
 
 void BatchedStrongBranchingSolver::unmarkHotStart(OsiTMINLPInterface *) { preloaded_ = false; }
 
+// BonChooseVariable::doStrongBranching (BonChooseVariable.cpp:787-957) with the 2 x numberToDo solveFromHotStart calls served
+// from ONE prefetched batch.  Everything else is the reference's loop: branch down / solve / updateInformation / restore,
+// branch up / solve / updateInformation / restore; returnCode -1 when a candidate is infeasible both ways (the loop goes on,
+// :916-919), 1 when exactly one way is infeasible (:920-923), 3 and stop when the time is up (:924-929), stop early by the
+// look-ahead rule away from the root (:930-948); results_ is cut to the candidates actually evaluated (:950-952).
+int BatchedChooseVariable::doStrongBranching(OsiTMINLPInterface *solver, OsiBranchingInformation *info, int numberToDo,
+                                             int /* returnCriterion */) {
+  double bestLookAhead = -1.7976931348623157e308;
+  int trialsSinceBest = 0;
+  const bool isRoot = info->depth_ == 0;                  // isRootNode (:959-962)
+  const int numberColumns = solver->getNumCols();
+  numberToDo = std::min(numberToDo, (int)results_.size());
+  std::vector<int> cols(numberToDo);
+  std::vector<double> dn(numberToDo), up(numberToDo);
+  for (int i = 0; i < numberToDo; ++i) {
+    cols[i] = results_[i].col;
+    dn[i] = std::floor(results_[i].value); up[i] = std::ceil(results_[i].value);
+  }
+  solver->markHotStart();                                 // :799
+  if (!sb_->preloaded()) sb_->prefetch(solver, cols, dn, up);   // ONE batch of 2 x numberToDo children
+  const std::vector<double> saveLower(info->lower_, info->lower_ + numberColumns), saveUpper(info->upper_, info->upper_ + numberColumns);
+  int returnCode = 0;
+  const double timeStart = now_s();
+  int iDo = 0;
+  for (; iDo < numberToDo; ++iDo) {
+    StrongResult &r = results_[iDo];
+    int status[2];
+    for (int w = 0; w < 2; ++w) {
+      if (w == 0) solver->setColUpper(r.col, dn[iDo]); else solver->setColLower(r.col, up[iDo]);   // branch->branch(solver) :820, :866
+      solver->solveFromHotStart();                        // :822, :869
+      // HotInfo::updateInformation (:1118-1145) + OsiHotInfo: 0 finished, 1 infeasible, 2 not finished
+      const double obj = solver->getObjValue();
+      if (solver->isProvenOptimal()) status[w] = 0;
+      else if (solver->isProvenPrimalInfeasible()) status[w] = (std::fabs(obj) < 1e-6) ? 2 : 1;
+      else status[w] = 2;
+      r.status[w] = status[w];
+      r.obj[w] = obj;
+      r.change[w] = (status[w] == 0) ? std::max(0.0, obj - info->objectiveValue_) : 0.0;
+      numberStrongDone_ += (w == 1);
+      for (int j = 0; j < numberColumns; ++j) {           // restore bounds :853-858, :898-903
+        if (saveLower[j] != solver->getColLower()[j]) solver->setColLower(j, saveLower[j]);
+        if (saveUpper[j] != solver->getColUpper()[j]) solver->setColUpper(j, saveUpper[j]);
+      }
+    }
+    if (status[0] == 1 && status[1] == 1) returnCode = -1;                      // infeasible both ways (no break, :916-919)
+    else if (status[0] == 1 || status[1] == 1) { numberStrongFixed_++; returnCode = 1; }
+    const bool hitMaxTime = (now_s() - timeStart > info->timeRemaining_) || (now_s() - start_time_ > time_limit_);
+    if (hitMaxTime) { returnCode = 3; break; }
+    if (!isRoot && numberLookAhead_ && status[0] == 0 && status[1] == 0) {      // look-ahead heuristic (:930-948)
+      const double MAXMIN = (info->hasSolution_ && info->depth_ > 10) ? maxmin_crit_have_sol : maxmin_crit_no_sol;
+      const double value = MAXMIN * std::min(r.change[1], r.change[0]) + (1.0 - MAXMIN) * std::max(r.change[1], r.change[0]);
+      if (value > bestLookAhead) { bestLookAhead = value; trialsSinceBest = 0; }
+      else if (++trialsSinceBest >= numberLookAhead_) break;
+    }
+  }
+  if (iDo < numberToDo) iDo++;
+  results_.resize(iDo);
+  solver->unmarkHotStart();                               // :955
+  return returnCode;
+}
+
+// the form the host B-BB driver uses: candidates as a column list; every candidate is evaluated
 int BatchedChooseVariable::doStrongBranching(const std::vector<int> &cols, double parent_obj,
                                              std::vector<StrongResult> &results) {
-  const int K = (int)cols.size();
-  std::vector<double> xsol(si_->getColSolution(), si_->getColSolution() + si_->getNumCols());
-  std::vector<double> dn(K), up(K);
-  for (int i = 0; i < K; ++i) { dn[i] = std::floor(xsol[cols[i]]); up[i] = std::ceil(xsol[cols[i]]); }
-  si_->markHotStart();                                   // :799
-  if (!sb_->preloaded()) sb_->prefetch(si_, cols, dn, up);   // ONE batch of 2K children (Appendix C)
-  results.assign(K, StrongResult());
-  int returnCode = 0;
-  for (int iDo = 0; iDo < K; ++iDo) {                    // :807-948, unchanged control flow
-    StrongResult &r = results[iDo];
-    r.col = cols[iDo]; r.value = xsol[cols[iDo]];
-    for (int w = 0; w < 2; ++w) {
-      const double saveL = si_->getColLower()[r.col], saveU = si_->getColUpper()[r.col];
-      if (w == 0) si_->setColUpper(r.col, dn[iDo]); else si_->setColLower(r.col, up[iDo]);   // branch->branch(solver) :820
-      si_->solveFromHotStart();                          // :822
-      // HotInfo::updateInformation (:1118-1145) + OsiHotInfo: 0 feasible, 1 infeasible, 2 not finished
-      int status;
-      const double obj = si_->getObjValue();
-      if (si_->isProvenOptimal()) status = 0;
-      else if (si_->isProvenPrimalInfeasible()) status = (std::fabs(obj) < 1e-6) ? 2 : 1;
-      else status = 2;
-      r.status[w] = status;
-      r.obj[w] = obj;
-      r.change[w] = (status == 0) ? std::max(0.0, obj - parent_obj) : 0.0;
-      si_->setColLower(r.col, saveL); si_->setColUpper(r.col, saveU);   // restore bounds :853-858
-    }
-    if (r.status[0] == 1 && r.status[1] == 1) returnCode = -1;          // :916-919 (the loop continues)
+  setCandidates(cols);
+  OsiBranchingInformation info;
+  info.lower_ = si_->getColLower(); info.upper_ = si_->getColUpper(); info.solution_ = si_->getColSolution();
+  info.objectiveValue_ = parent_obj; info.depth_ = depth_; info.hasSolution_ = have_solution_;
+  info.timeRemaining_ = time_remaining_;
+  // (info.lower_ / upper_ point into the live bound arrays of the shim: take the snapshot the reference's info holds)
+  const std::vector<double> lo(info.lower_, info.lower_ + si_->getNumCols()), hi(info.upper_, info.upper_ + si_->getNumCols());
+  info.lower_ = lo.data(); info.upper_ = hi.data();
+  const int rc = doStrongBranching(si_, &info, (int)cols.size(), 0);
+  results = results_;
+  return rc;
+}
+
+void BatchedChooseVariable::setCandidates(const std::vector<int> &cols) {
+  results_.assign(cols.size(), StrongResult());
+  for (size_t i = 0; i < cols.size(); ++i) {
+    results_[i].col = cols[i];
+    results_[i].value = si_->getColSolution()[cols[i]];
+    results_[i].status[0] = results_[i].status[1] = -1;
   }
-  si_->unmarkHotStart();                                 // :955
-  return returnCode;
 }
 
 int BatchedChooseVariable::choose(const std::vector<StrongResult> &results, double parent_obj, double cutoff,
@@ -355,15 +453,18 @@ BbResult bb_run(TMINLP2TNLP &root, BatchSolveFn solve, const BbOptions &opt, Tqp
   BbResult R;
   const double t0 = now_s();
   const int n = root.n;
-  B200Solver app(solve);
+  Ipopt::SmartPtr<B200Solver> app_holder = new B200Solver(solve);   // (SmartPtr-managed objects live on the heap)
+  B200Solver &app = *app_holder;
   if (children) app.setChildrenSolver(children);
-  OsiTMINLPInterface si(&root, &app);
+  OsiTMINLPInterface si(Ipopt::SmartPtr<TMINLP2TNLP>(&root), Ipopt::SmartPtr<TNLPSolver>(GetRawPtr(app_holder)));
   BatchedStrongBranchingSolver sb(&app);
   si.SetStrongBrachingSolver(&sb);
   const bool qp_mode = opt.variable_selection == 1 && tqp;
   if (qp_mode) sb.setQpSurrogate(tqp);
   BatchedChooseVariable chooser(&si, &sb);
   chooser.integer_tolerance = opt.integer_tolerance;
+  chooser.setNumberLookAhead(opt.number_look_ahead);
+  chooser.setTimeLimit(t0, opt.time_limit);
   std::vector<int> ints;
   for (int j = 0; j < n; ++j) if (root.var_types[j] != 0) ints.push_back(j);
   std::vector<double> pc_sum[2], pc_cnt[2];   // pseudo-costs per column and direction
@@ -374,13 +475,13 @@ BbResult bb_run(TMINLP2TNLP &root, BatchSolveFn solve, const BbOptions &opt, Tqp
   si.initialSolve();
   R.nlp_solves++;
   if (!si.isProvenOptimal()) { R.status = app.providerErrors() ? 3 : si.isProvenPrimalInfeasible() ? 1 : 4; R.failed_nodes += !app.providerErrors() && !si.isProvenPrimalInfeasible(); R.seconds = now_s() - t0; return R; }
-  root.setxInit(n, root.x_sol.data());
+  root.setxInit(n, root.x_sol_.data());
   std::priority_queue<Node *, std::vector<Node *>, Cmp> heap;
-  Node *first = new Node{root.x_l, root.x_u, root.obj_value, 0};
-  first->solved = true; first->obj = root.obj_value; first->status = (int)root.return_status; first->x = root.x_sol;
+  Node *first = new Node{root.x_l_, root.x_u_, root.obj_value_, 0};
+  first->solved = true; first->obj = root.obj_value_; first->status = (int)root.return_status; first->x = root.x_sol_;
   Node *dive = first;   // node processed next without going through the heap (depth-first plunge on the better child)
   double cutoff = 1e100;
-  const std::vector<double> xl_root = root.x_l, xu_root = root.x_u;
+  const std::vector<double> xl_root = root.x_l_, xu_root = root.x_u_;
 
   double t_prefetch = 0;
   if (opt.parallel_nodes > 1 && !qp_mode) {
@@ -462,13 +563,15 @@ BbResult bb_run(TMINLP2TNLP &root, BatchSolveFn solve, const BbOptions &opt, Tqp
       for (size_t q = 0; q < open.size(); ++q) {
         Node *nd = open[q];
         if (nd->obj >= cutoff) { delete nd; continue; }
-        root.x_l = nd->xl; root.x_u = nd->xu;
-        root.obj_value = nd->obj; root.x_sol = nd->x; root.return_status = (TNLPSolver::ReturnStatus)nd->status;
+        root.x_l_ = nd->xl; root.x_u_ = nd->xu;
+        root.obj_value_ = nd->obj; root.x_sol_ = nd->x; root.return_status = (TNLPSolver::ReturnStatus)nd->status;
         si.optimizationStatus_ = (TNLPSolver::ReturnStatus)nd->status;
         sb.useNode((int)q);
         std::vector<StrongResult> res;
+        chooser.setNodeInfo(nd->depth, R.best_obj < 1e99, opt.time_limit - (now_s() - t0));
         const int rc = chooser.doStrongBranching(reqs[q].cols, nd->obj, res);
         if (rc == -1) { delete nd; continue; }
+        if (rc == 3) { R.status = 2; heap.push(nd); break; }        // time limit inside strong branching (:924-929)
         int bway = 0;
         std::vector<std::pair<int, int>> fix;
         const int bi = chooser.choose(res, nd->obj, cutoff, R.best_obj < 1e99, nd->depth, bway, fix);
@@ -504,10 +607,10 @@ BbResult bb_run(TMINLP2TNLP &root, BatchSolveFn solve, const BbOptions &opt, Tqp
     if (R.nodes >= opt.node_limit || now_s() - t0 > opt.time_limit) { R.status = 2; delete nd; break; }
     if (app.providerErrors()) { delete nd; break; }
     R.nodes++;
-    root.x_l = nd->xl; root.x_u = nd->xu;
+    root.x_l_ = nd->xl; root.x_u_ = nd->xu;
     if (nd->solved) {
       R.served_from_sb_cache += (nd != first);
-      root.obj_value = nd->obj; root.x_sol = nd->x; root.return_status = (TNLPSolver::ReturnStatus)nd->status;
+      root.obj_value_ = nd->obj; root.x_sol_ = nd->x; root.return_status = (TNLPSolver::ReturnStatus)nd->status;
       si.optimizationStatus_ = (TNLPSolver::ReturnStatus)nd->status;
     } else {
       si.resolve();
@@ -522,9 +625,9 @@ BbResult bb_run(TMINLP2TNLP &root, BatchSolveFn solve, const BbOptions &opt, Tqp
       continue;
     }
     if (!si.isProvenOptimal()) { delete nd; continue; }           // proven infeasible node: fathom
-    const double obj = root.obj_value;
+    const double obj = root.obj_value_;
     if (obj >= cutoff) { delete nd; continue; }
-    const std::vector<double> x = root.x_sol;
+    const std::vector<double> x = root.x_sol_;
     // integer infeasibilities
     std::vector<std::pair<double, int>> frac = fractional_candidates(x, ints, opt);
     if (frac.empty()) {   // new incumbent; Cbc's cutoff = incumbent - cutoff_decr
@@ -542,9 +645,11 @@ BbResult bb_run(TMINLP2TNLP &root, BatchSolveFn solve, const BbOptions &opt, Tqp
     int bcol = -1, bway = 0;
     std::vector<StrongResult> res;
     if (!cand.empty()) {
+      chooser.setNodeInfo(nd->depth, R.best_obj < 1e99, opt.time_limit - (now_s() - t0));
       const int rc = chooser.doStrongBranching(cand, obj, res);
       R.sb_batches++; R.sb_children += 2 * (int)cand.size();
       if (rc == -1) { delete nd; continue; }                       // both ways infeasible: node infeasible
+      if (rc == 3) { R.status = 2; delete nd; break; }             // time limit inside strong branching (:924-929)
       std::vector<std::pair<int, int>> fix;
       const int bi = chooser.choose(res, obj, cutoff, R.best_obj < 1e99, nd->depth, bway, fix);
       for (auto &r : res)                                           // pseudo-cost update from SB (:994-1026)
@@ -579,7 +684,7 @@ BbResult bb_run(TMINLP2TNLP &root, BatchSolveFn solve, const BbOptions &opt, Tqp
       const B200Solver::Child *c = nullptr;
       bool same = true;   // fixings applied after SB change the bounds: then the cached result is no longer this child
       for (int j = 0; j < n && same; ++j)
-        if (j != bcol && (nd->xl[j] != root.x_l[j] || nd->xu[j] != root.x_u[j])) same = false;
+        if (j != bcol && (nd->xl[j] != root.x_l_[j] || nd->xu[j] != root.x_u_[j])) same = false;
       if (same && !res.empty() && !qp_mode) c = sb.lookup(bcol, w == 1);   // QP children are surrogates, never node results
       // (an unfinished strong-branching solve is not a node result: that child is solved again as a node)
       if (c && (c->status == 1 || c->status == 2 || c->status == TNLPSolver::provenInfeasible)) {
@@ -603,7 +708,7 @@ BbResult bb_run(TMINLP2TNLP &root, BatchSolveFn solve, const BbOptions &opt, Tqp
   if (getenv("BNLP_BB_TIMERS"))
     fprintf(stderr, "[bb timers] total %.3f s, prefetchMany %.3f s, inside the batch-solve callback %.3f s\n", R.seconds, t_prefetch,
             app.solveSeconds());
-  root.x_l = xl_root; root.x_u = xu_root;
+  root.x_l_ = xl_root; root.x_u_ = xu_root;
   return R;
 }
 
@@ -616,10 +721,10 @@ static bool is_optimal(int st) { return st == TNLPSolver::solvedOptimal || st ==
 
 void random_starting_point(const TMINLP2TNLP &t, double R, unsigned long long &rng, double *sol) {
   for (int i = 0; i < t.n; ++i) {   // uniform mode (:1768-1777)
-    double lower = std::min(-R, t.x_u[i] - R);
-    lower = std::max(t.x_l[i], lower);
-    double upper = std::max(R, t.x_l[i] + R);
-    upper = std::min(t.x_u[i], upper);
+    double lower = std::min(-R, t.x_u_[i] - R);
+    lower = std::max(t.x_l_[i], lower);
+    double upper = std::max(R, t.x_l_[i] + R);
+    upper = std::min(t.x_u_[i], upper);
     lower = std::min(upper, lower);
     upper = std::max(upper, lower);
     rng = (rng * 0x5DEECE66DULL + 0xB) & ((1ULL << 48) - 1);
@@ -636,8 +741,8 @@ struct StartsBatch {
     n = t.n; m = t.m; B = (int)(X0.size() / n);
     std::vector<double> XL((size_t)B * n), XU((size_t)B * n);
     for (int b = 0; b < B; ++b) {
-      std::copy(t.x_l.begin(), t.x_l.end(), &XL[(size_t)b * n]);
-      std::copy(t.x_u.begin(), t.x_u.end(), &XU[(size_t)b * n]);
+      std::copy(t.x_l_.begin(), t.x_l_.end(), &XL[(size_t)b * n]);
+      std::copy(t.x_u_.begin(), t.x_u_.end(), &XU[(size_t)b * n]);
     }
     OBJ.assign(B, 0.0); ST.assign(B, 0); IT.assign(B, 0);
     X.assign((size_t)B * n, 0.0); G.assign((size_t)B * std::max(m, 1), 0.0); D.assign((size_t)B * (2 * n + m), 0.0);
@@ -646,10 +751,10 @@ struct StartsBatch {
     return rc;
   }
   void install(TMINLP2TNLP &t, int b) const {
-    t.x_sol.assign(X.begin() + (size_t)b * n, X.begin() + (size_t)(b + 1) * n);
-    t.g_sol.assign(G.begin() + (size_t)b * m, G.begin() + (size_t)(b + 1) * m);
-    t.duals_sol.assign(D.begin() + (size_t)b * (2 * n + m), D.begin() + (size_t)(b + 1) * (2 * n + m));
-    t.obj_value = OBJ[b];
+    t.x_sol_.assign(X.begin() + (size_t)b * n, X.begin() + (size_t)(b + 1) * n);
+    t.g_sol_.assign(G.begin() + (size_t)b * m, G.begin() + (size_t)(b + 1) * m);
+    t.duals_sol_.assign(D.begin() + (size_t)b * (2 * n + m), D.begin() + (size_t)(b + 1) * (2 * n + m));
+    t.obj_value_ = OBJ[b];
     t.return_status = (TNLPSolver::ReturnStatus)ST[b];
   }
 };
@@ -659,7 +764,7 @@ TNLPSolver::ReturnStatus resolve_for_robustness(TMINLP2TNLP &t, BatchSolveStarts
                                                 RetryResult &r) {
   const int n = t.n, B = 1 + std::max(0, numsolve);
   std::vector<double> X0((size_t)B * n);
-  std::copy(t.x_init.begin(), t.x_init.begin() + n, X0.begin());          // resetStartingPoint (:1007)
+  std::copy(t.x_init_.begin(), t.x_init_.begin() + n, X0.begin());          // resetStartingPoint (:1007)
   unsigned long long rng = 0x5DEECE66DULL ^ o.seed;
   for (int f = 1; f < B; ++f) random_starting_point(t, o.max_random_point_radius, rng, &X0[(size_t)f * n]);
   StartsBatch S;
@@ -667,25 +772,25 @@ TNLPSolver::ReturnStatus resolve_for_robustness(TMINLP2TNLP &t, BatchSolveStarts
   r = RetryResult();
   r.nlp_solves = B;
   for (int f = 0; f < B; ++f) {                                             // first attempt that is not abandoned (:1024, :1057)
-    if (!is_abandoned(S.ST[f])) { r.used = f; S.install(t, f); return t.return_status; }
+    if (!is_abandoned(S.ST[f])) { r.used = f; S.install(t, f); return (TNLPSolver::ReturnStatus)t.return_status; }
     r.num_failed++;
   }
   S.install(t, B - 1);     // all abandoned: the caller throws newUnsolvedError or pretends infeasible (:1076-1091)
-  return t.return_status;
+  return (TNLPSolver::ReturnStatus)t.return_status;
 }
 
 TNLPSolver::ReturnStatus resolve_for_cost(TMINLP2TNLP &t, BatchSolveStartsFn solve, int numsolve, const RetryOptions &o,
                                           RetryResult &r) {
   const int n = t.n, B = std::max(0, numsolve);
   r = RetryResult();
-  if (B == 0) return t.return_status;
+  if (B == 0) return (TNLPSolver::ReturnStatus)t.return_status;
   std::vector<double> X0((size_t)B * n);
   unsigned long long rng = 0x5DEECE66DULL ^ o.seed;
   for (int f = 0; f < B; ++f) random_starting_point(t, o.max_random_point_radius, rng, &X0[(size_t)f * n]);
   StartsBatch S;
   S.run(t, solve, X0);
   r.nlp_solves = B;
-  double bestBound = is_optimal(t.return_status) ? t.obj_value : 1.7976931348623157e308;   // :858
+  double bestBound = is_optimal(t.return_status) ? t.obj_value_ : 1.7976931348623157e308;   // :858
   double sum = 0;
   int nopt = 0;
   for (int f = 0; f < B; ++f) {
@@ -700,7 +805,7 @@ TNLPSolver::ReturnStatus resolve_for_cost(TMINLP2TNLP &t, BatchSolveStartsFn sol
     for (int f = 0; f < B; ++f) if (is_optimal(S.ST[f])) v += (S.OBJ[f] - r.mean) * (S.OBJ[f] - r.mean);
     r.std_dev = std::sqrt(v / nopt);
   }
-  return t.return_status;
+  return (TNLPSolver::ReturnStatus)t.return_status;
 }
 
 // ------------------------------------------------------------------------------------------------ NLP diving
@@ -711,11 +816,11 @@ DiveResult dive_run(TMINLP2TNLP &minlp, BatchSolveFn solve, GradFFn grad_f, cons
   const double integerTolerance = opt.integer_tolerance;
   double primalTolerance = 1.0e-6;
   // adjustPrimalTolerance (:335-358)
-  for (int i = 0; i < m && i < (int)minlp.g_sol.size(); ++i) {
-    if (minlp.g_sol[i] < minlp.g_l[i] - primalTolerance) primalTolerance = minlp.g_l[i] - minlp.g_sol[i];
-    else if (minlp.g_sol[i] > minlp.g_u[i] + primalTolerance) primalTolerance = minlp.g_sol[i] - minlp.g_u[i];
+  for (int i = 0; i < m && i < (int)minlp.g_sol_.size(); ++i) {
+    if (minlp.g_sol_[i] < minlp.g_l_[i] - primalTolerance) primalTolerance = minlp.g_l_[i] - minlp.g_sol_[i];
+    else if (minlp.g_sol_[i] > minlp.g_u_[i] + primalTolerance) primalTolerance = minlp.g_sol_[i] - minlp.g_u_[i];
   }
-  std::vector<double> newSolution = minlp.x_sol, new_g = minlp.g_sol;
+  std::vector<double> newSolution = minlp.x_sol_, new_g = minlp.g_sol_;
   std::vector<int> integerColumns;
   int numberFractionalVariables = 0;
   for (int j = 0; j < n; ++j)
@@ -727,10 +832,10 @@ DiveResult dive_run(TMINLP2TNLP &minlp, BatchSolveFn solve, GradFFn grad_f, cons
   const int maxNumberAtBoundToFix = (int)std::floor(opt.percentage_to_fix * numberIntegers);
   unsigned long long rng = 0x5DEECE66DULL ^ opt.seed;
   auto drand = [&]() { rng = (rng * 0x5DEECE66DULL + 0xB) & ((1ULL << 48) - 1); return (double)rng / (double)(1ULL << 48); };
-  std::vector<double> &x_l = minlp.x_l, &x_u = minlp.x_u;
+  std::vector<double> &x_l = minlp.x_l_, &x_u = minlp.x_u_;
   std::vector<double> gradient(n, 0.0);
   bool last_success = true;
-  double curObj = minlp.obj_value;   // objective of newSolution
+  double curObj = minlp.obj_value_;   // objective of newSolution
 
   auto select = [&](int &bestColumn, int &bestRound) {
     bestColumn = -1; bestRound = -1;
@@ -812,7 +917,7 @@ DiveResult dive_run(TMINLP2TNLP &minlp, BatchSolveFn solve, GradFFn grad_f, cons
         std::copy(ladder[a0 + a].xl.begin(), ladder[a0 + a].xl.end(), &XL[(size_t)a * n]);
         std::copy(ladder[a0 + a].xu.begin(), ladder[a0 + a].xu.end(), &XU[(size_t)a * n]);
       }
-      const int rc = solve(cnt, XL.data(), XU.data(), minlp.x_init.data(), &OBJ[a0], &ST[a0], &IT[a0], &X[(size_t)a0 * n],
+      const int rc = solve(cnt, XL.data(), XU.data(), minlp.x_init_.data(), &OBJ[a0], &ST[a0], &IT[a0], &X[(size_t)a0 * n],
                            &G[(size_t)a0 * std::max(m, 1)], nullptr);
       R.batches++;
       R.nlp_solves += cnt;
@@ -843,7 +948,7 @@ DiveResult dive_run(TMINLP2TNLP &minlp, BatchSolveFn solve, GradFFn grad_f, cons
     else if (minlp.var_types[j] != 0 && std::fabs(std::floor(value + 0.5) - value) > integerTolerance) feasible = false;
   }
   for (int i = 0; i < m && feasible; ++i)
-    if (new_g[i] < minlp.g_l[i] - primalTolerance || new_g[i] > minlp.g_u[i] + primalTolerance) feasible = false;
+    if (new_g[i] < minlp.g_l_[i] - primalTolerance || new_g[i] > minlp.g_u_[i] + primalTolerance) feasible = false;
   if (feasible && curObj < solutionValue) { R.found = true; R.obj = curObj; R.x = newSolution; }
   return R;
 }

@@ -34,44 +34,56 @@ using ChildrenSolveFn = std::function<int(int P, const double *PXL, const double
                                           const int *cw, const double *cb, const double *X0, double *OBJ, int *STATUS,
                                           int *ITERS, double *X)>;
 
+// B x ReOptimizeTNLP from a primal AND dual start: same argument meaning as bnlp_solve_batch_warm (include/bnlp.h),
+// DUAL0 = one vector [z_L | z_U | lambda] of 2n+m shared by the B children
+using BatchSolveWarmFn = std::function<int(int B, const double *XL, const double *XU, const double *X0, const double *DUAL0,
+                                           double *OBJ, int *STATUS, int *ITERS, double *X, double *G, double *DUALS)>;
+
 class B200Solver : public TNLPSolver {
  public:
-  explicit B200Solver(BatchSolveFn fn) : solve_(std::move(fn)) {}
-  TNLPSolver *clone() override { return new B200Solver(solve_); }
-  ReturnStatus OptimizeTNLP(TMINLP2TNLP &tnlp) override;
-  ReturnStatus ReOptimizeTNLP(TMINLP2TNLP &tnlp) override { return OptimizeTNLP(tnlp); }
+  explicit B200Solver(BatchSolveFn fn, BatchSolveWarmFn warm = nullptr) : solve_(std::move(fn)), solve_warm_(std::move(warm)) {}
+  Ipopt::SmartPtr<TNLPSolver> clone() override {
+    B200Solver *c = new B200Solver(solve_, solve_warm_);
+    c->children_ = children_; c->options_ = options_; c->enable_warm_start_ = enable_warm_start_;
+    c->log_level_ = log_level_; c->default_log_level_ = default_log_level_;
+    return Ipopt::SmartPtr<TNLPSolver>(c);
+  }
+  // the TNLP is driven through its virtuals only: get_nlp_info, get_bounds_info, get_starting_point, finalize_solution
+  ReturnStatus OptimizeTNLP(const Ipopt::SmartPtr<Ipopt::TNLP> &tnlp) override;
+  ReturnStatus ReOptimizeTNLP(const Ipopt::SmartPtr<Ipopt::TNLP> &tnlp) override;
   double CPUTime() override { return cpu_time_; }
   int IterationCount() override { return iterations_; }
-  const std::string &solverName() const override { return name_; }
+  std::string &solverName() override { return name_; }
   // --- the rest of the TNLPSolver contract (BonTNLPSolver.hpp:95-205)
   // options: "name value" lines as in bonmin.opt / ipopt.opt; kept for inspection (tol and max_iter are fixed when the
   // engine behind the BatchSolveFn is created, see bnlp_options)
   bool Initialize(std::string params_file) override;
   bool Initialize(std::istream &is) override;
   const std::string *option(const std::string &name) const;
-  // warm starts as IpoptSolver handles them (Ipopt/BonIpoptSolver.cpp:345-430): the primal point becomes the start point
-  // of the next solve; the multipliers are carried in TMINLP2TNLP::duals_init and switch the warm-start flag on, but the
-  // batched IPM initialises its multipliers itself (Ipopt's warm_start_init_point = no path), which is also what the
-  // reference runs with by default (`warm_start none`)
-  bool setWarmStart(const CoinWarmStart *warm, TMINLP2TNLP &tnlp) override;
-  CoinWarmStart *getUsedWarmStart(TMINLP2TNLP &tnlp) const override;
-  CoinWarmStart *getWarmStart(TMINLP2TNLP &tnlp) const override;
-  CoinWarmStart *getEmptyWarmStart() const override { return new CoinWarmStart(); }
-  bool warmStartIsValid(const CoinWarmStart *ws) const override { return ws && !ws->empty(); }
+  // warm starts exactly as IpoptSolver handles them (Ipopt/BonIpoptSolver.cpp:345-430): setWarmStart puts the primal point
+  // and the multipliers [z_L | z_U | lambda] into the TMINLP2TNLP (setxInit / setDualsInit) and switches the warm-start
+  // option on; the next (Re)OptimizeTNLP then asks get_starting_point for x, z_L, z_U and lambda and solves from them
+  // (bnlp_solve_batch_warm).  Without a BatchSolveWarmFn only the primal point is used.
+  bool setWarmStart(const CoinWarmStart *warm, Ipopt::SmartPtr<TMINLP2TNLP> tnlp) override;
+  CoinWarmStart *getUsedWarmStart(Ipopt::SmartPtr<TMINLP2TNLP> tnlp) const override;
+  CoinWarmStart *getWarmStart(Ipopt::SmartPtr<TMINLP2TNLP> tnlp) const override;
+  CoinWarmStart *getEmptyWarmStart() const override { return new IpoptWarmStart(true); }
+  bool warmStartIsValid(const CoinWarmStart *ws) const override;
   void enableWarmStart() override { enable_warm_start_ = true; }
   void disableWarmStart() override { enable_warm_start_ = false; }
   bool warmStartEnabled() const { return enable_warm_start_; }
+  bool lastSolveWasWarmStarted() const { return warm_started_last_; }
   void setOutputToDefault() override { log_level_ = default_log_level_; }
   void forceSolverOutput(int log_level) override { log_level_ = log_level; }
   int logLevel() const { return log_level_; }
   int errorCode() const override { return error_code_; }      // the provider's return code of the last failed call
   class UnsolvedB200Error : public UnsolvedError {
    public:
-    UnsolvedB200Error(int num, TMINLP2TNLP *problem, std::string name) : UnsolvedError(num, problem, std::move(name)) {}
+    UnsolvedB200Error(int num, Ipopt::SmartPtr<TMINLP2TNLP> problem, std::string name) : UnsolvedError(num, problem, std::move(name)) {}
     const std::string &errorName() const override;
     const std::string &solverName() const override;
   };
-  UnsolvedError *newUnsolvedError(int num, TMINLP2TNLP *problem, std::string name) override {
+  UnsolvedError *newUnsolvedError(int num, Ipopt::SmartPtr<TMINLP2TNLP> problem, std::string name) override {
     return new UnsolvedB200Error(num, problem, std::move(name));
   }
   // the batched sibling: children differ only in bounds; results in TMINLP2TNLP layout
@@ -96,8 +108,11 @@ class B200Solver : public TNLPSolver {
  private:
   int unpack(int rc, int B, int n, std::vector<Child> &out);
   std::shared_ptr<std::vector<double>> x_block(size_t cnt);
+  ReturnStatus solve_tnlp(const Ipopt::SmartPtr<Ipopt::TNLP> &tnlp, bool warm);
   BatchSolveFn solve_;
+  BatchSolveWarmFn solve_warm_;
   ChildrenSolveFn children_;
+  bool optimized_before_ = false, warm_started_last_ = false;
   std::vector<double> obj_buf_, xl_buf_, xu_buf_;   // reused between calls: no fresh pages per round
   std::vector<int> st_buf_, it_buf_;
   std::shared_ptr<std::vector<double>> x_pool_;
@@ -160,13 +175,33 @@ struct StrongResult {  // what HotInfo holds per candidate (BonChooseVariable.hp
   double obj[2];
 };
 
+// OsiBranchingInformation (Osi/OsiBranchingObject.hpp): the fields BonChooseVariable::doStrongBranching reads
+struct OsiBranchingInformation {
+  const double *lower_ = nullptr, *upper_ = nullptr, *solution_ = nullptr;   // the node's bounds and LP/NLP point
+  double objectiveValue_ = 0.0, cutoff_ = 1e100, timeRemaining_ = 1e100;
+  int depth_ = 0;
+  bool hasSolution_ = false;
+};
+
 class BatchedChooseVariable {
  public:
   BatchedChooseVariable(OsiTMINLPInterface *si, BatchedStrongBranchingSolver *sb) : si_(si), sb_(sb) {}
   double maxmin_crit_no_sol = 0.7, maxmin_crit_have_sol = 0.1;   // BonChooseVariable.cpp:170-175
   double integer_tolerance = 1e-6;                               // BonBabSetupBase.cpp:478-482
-  // doStrongBranching (BonChooseVariable.cpp:787-957): one prefetch, then the reference's sequential loop replayed
-  // against it.  Returns -1 if some candidate is infeasible both ways (node infeasible), else 0.
+  // doStrongBranching with the reference's signature and return codes (BonChooseVariable.cpp:787-957): -1 some candidate is
+  // infeasible both ways (node infeasible), 1 some candidate is infeasible one way (fix it), 3 time limit, 0 otherwise;
+  // results() is cut to the candidates evaluated (look-ahead, time limit).  The candidates are those of setCandidates().
+  int doStrongBranching(OsiTMINLPInterface *solver, OsiBranchingInformation *info, int numberToDo, int returnCriterion);
+  void setCandidates(const std::vector<int> &cols);              // setupList's strong-branching list (HotInfo per candidate)
+  const std::vector<StrongResult> &results() const { return results_; }
+  void setNumberLookAhead(int k) { numberLookAhead_ = k; }       // `number_look_ahead` (:152-158), default 0 = off
+  void setTimeLimit(double start_time, double time_limit) { start_time_ = start_time; time_limit_ = time_limit; }
+  void setNodeInfo(int depth, bool have_solution, double time_remaining = 1e100) {
+    depth_ = depth; have_solution_ = have_solution; time_remaining_ = time_remaining;
+  }
+  int numberStrongDone() const { return numberStrongDone_; }
+  int numberStrongFixed() const { return numberStrongFixed_; }
+  // the column-list form the host B-BB driver uses (every candidate evaluated unless look-ahead / time stops the loop)
   int doStrongBranching(const std::vector<int> &cols, double parent_obj, std::vector<StrongResult> &results);
   // scoring of chooseVariable (BonChooseVariable.cpp:682-747); returns the index into results (or -1) and the way
   int choose(const std::vector<StrongResult> &results, double parent_obj, double cutoff, bool have_solution, int depth,
@@ -175,6 +210,11 @@ class BatchedChooseVariable {
  private:
   OsiTMINLPInterface *si_;
   BatchedStrongBranchingSolver *sb_;
+  std::vector<StrongResult> results_;
+  int numberLookAhead_ = 0, numberStrongDone_ = 0, numberStrongFixed_ = 0;
+  int depth_ = 0;
+  bool have_solution_ = false;
+  double time_limit_ = 1e100, start_time_ = 0.0, time_remaining_ = 1e100;
 };
 
 struct BbOptions {
@@ -192,6 +232,7 @@ struct BbOptions {
   // nlp_failure_behavior (BonOsiTMINLPInterface.cpp:233-240): 0 = stop (the reference throws newUnsolvedError when a node
   // NLP stays unsolved, :2639-2644), 1 = fathom (pretendFailIsInfeasible_: the node is dropped with a warning)
   int nlp_failure_behavior = 0;
+  int number_look_ahead = 0;            // BonChooseVariable.cpp:152-158: stop strong branching after that many non-improving candidates (0 = off)
 };
 struct BbResult {
   int status = 0;               // 0 optimal, 1 infeasible, 2 node/time limit, 3 provider error, 4 a node NLP stayed unsolved

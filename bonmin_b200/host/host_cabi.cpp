@@ -27,12 +27,13 @@ int bnlp_bb_run_cb3(int n, int m, const int *var_type, const double *xl, const d
                     const double *gu, const double *x0, bnlp_batch_solve_cb cb, bnlp_tqp_solve_cb qp_cb,
                     bnlp_children_solve_cb ch_cb, void *ctx, const bnlp_bb_options *o, bnlp_bb_result *res, double *best_x) {
   using namespace Bonmin;
-  TMINLP2TNLP root;
+  Ipopt::SmartPtr<TMINLP2TNLP> root_holder = new TMINLP2TNLP();   // SmartPtr-managed objects live on the heap
+  TMINLP2TNLP &root = *root_holder;
   root.n = n; root.m = m;
   root.var_types.assign(var_type, var_type + n);
-  root.x_l.assign(xl, xl + n); root.x_u.assign(xu, xu + n);
-  root.g_l.assign(gl, gl + m); root.g_u.assign(gu, gu + m);
-  root.x_init.assign(x0, x0 + n);
+  root.x_l_.assign(xl, xl + n); root.x_u_.assign(xu, xu + n);
+  root.g_l_.assign(gl, gl + m); root.g_u_.assign(gu, gu + m);
+  root.x_init_.assign(x0, x0 + n);
   BbOptions opt;
   if (o) {
     if (o->number_strong_branch > 0) opt.number_strong_branch = o->number_strong_branch;
@@ -46,6 +47,7 @@ int bnlp_bb_run_cb3(int n, int m, const int *var_type, const double *xl, const d
     opt.variable_selection = o->variable_selection;
     if (o->priorities) opt.priorities.assign(o->priorities, o->priorities + n);
     opt.nlp_failure_behavior = o->nlp_failure_behavior;
+    opt.number_look_ahead = o->number_look_ahead;
   }
   TqpSolveFn qfn;
   if (qp_cb)
@@ -67,25 +69,82 @@ int bnlp_bb_run_cb3(int n, int m, const int *var_type, const double *xl, const d
   return r.status == 3 ? -1 : 0;   // the arithmetic provider failed: an error, not a search result
 }
 
-// Exercises the parts of the TNLPSolver contract that have no other C entry point (options, warm starts, error objects,
-// output levels) on a stub provider; returns 0, or the source line of the first expectation that failed.
+// Exercises the TNLPSolver contract on stub providers: options, output levels, error objects, and — through a MOCK
+// Ipopt::TNLP that records every call — that (Re)OptimizeTNLP drives a TNLP purely through its virtuals in the order
+// get_nlp_info -> get_bounds_info -> get_starting_point -> finalize_solution, asks for multipliers only when a warm start is
+// enabled, and that the interface sequence of test/InterfaceTest.cpp:165-189 (solve, getWarmStart, change bounds,
+// setWarmStart, resolve) reaches the warm-start provider with the saved primal and dual point.  Returns 0, or the source
+// line of the first expectation that failed.
+namespace {
+struct MockTNLP : public Ipopt::TNLP {
+  std::string log;                       // one letter per virtual call: i(nfo) b(ounds) s(tart) S(tart with duals) f(inalize)
+  int n = 2, m = 1;
+  std::vector<double> xl{1.0, 0.0}, xu{4.0, 3.0}, x0{2.0, 1.0}, duals;   // duals empty: get_starting_point(init_z) fails
+  Ipopt::SolverReturn status = Ipopt::UNASSIGNED;
+  std::vector<double> x, zl, zu, lam, g;
+  double obj = 0;
+  bool get_nlp_info(Ipopt::Index &nn, Ipopt::Index &mm, Ipopt::Index &nj, Ipopt::Index &nh, IndexStyleEnum &st) override {
+    log += 'i'; nn = n; mm = m; nj = 2; nh = 1; st = C_STYLE; return true;
+  }
+  bool get_bounds_info(Ipopt::Index nn, double *l, double *u, Ipopt::Index mm, double *gl, double *gu) override {
+    log += 'b';
+    for (int j = 0; j < nn; ++j) { l[j] = xl[j]; u[j] = xu[j]; }
+    for (int i = 0; i < mm; ++i) { gl[i] = -1e19; gu[i] = 1.0; }
+    return true;
+  }
+  bool get_starting_point(Ipopt::Index nn, bool init_x, double *xx, bool init_z, double *z_L, double *z_U, Ipopt::Index mm,
+                          bool init_lambda, double *lambda) override {
+    log += (init_z || init_lambda) ? 'S' : 's';
+    if ((init_z || init_lambda) && duals.empty()) return false;
+    if (init_x) for (int j = 0; j < nn; ++j) xx[j] = x0[j];
+    if (init_z) for (int j = 0; j < nn; ++j) { z_L[j] = duals[j]; z_U[j] = duals[nn + j]; }
+    if (init_lambda) for (int i = 0; i < mm; ++i) lambda[i] = duals[2 * nn + i];
+    return true;
+  }
+  bool eval_f(Ipopt::Index, const double *, bool, double &) override { log += 'E'; return false; }
+  bool eval_grad_f(Ipopt::Index, const double *, bool, double *) override { log += 'E'; return false; }
+  bool eval_g(Ipopt::Index, const double *, bool, Ipopt::Index, double *) override { log += 'E'; return false; }
+  bool eval_jac_g(Ipopt::Index, const double *, bool, Ipopt::Index, Ipopt::Index, Ipopt::Index *, Ipopt::Index *, double *) override {
+    log += 'E'; return false;
+  }
+  void finalize_solution(Ipopt::SolverReturn st, Ipopt::Index nn, const double *xx, const double *z_L, const double *z_U,
+                         Ipopt::Index mm, const double *gg, const double *lambda, double o, const Ipopt::IpoptData *d,
+                         Ipopt::IpoptCalculatedQuantities *q) override {
+    log += (d == nullptr && q == nullptr) ? 'f' : 'F';
+    status = st; obj = o;
+    x.assign(xx, xx + nn); zl.assign(z_L, z_L + nn); zu.assign(z_U, z_U + nn); g.assign(gg, gg + mm); lam.assign(lambda, lambda + mm);
+  }
+};
+}  // namespace
+
 int bnlp_host_selftest(void) {
   using namespace Bonmin;
 #define EXPECT(c) do { if (!(c)) return __LINE__; } while (0)
-  int calls = 0, fail_next = 0;
-  BatchSolveFn stub = [&](int B, const double *XL, const double *, const double *X0, double *OBJ, int *ST, int *IT, double *X,
+  int calls = 0, warm_calls = 0, fail_next = 0;
+  std::vector<double> seen_dual0, seen_x0, seen_xl, seen_xu;
+  BatchSolveFn stub = [&](int B, const double *XL, const double *XU, const double *X0, double *OBJ, int *ST, int *IT, double *X,
                           double *G, double *D) {
     ++calls;
     if (fail_next) return fail_next;
+    seen_x0.assign(X0, X0 + 2); seen_xl.assign(XL, XL + 2); seen_xu.assign(XU, XU + 2);
     for (int b = 0; b < B; ++b) {
       OBJ[b] = X0[0] + XL[0]; ST[b] = 1; IT[b] = 7;
-      if (X) for (int j = 0; j < 2; ++j) X[2 * b + j] = X0[j];
+      if (X) for (int j = 0; j < 2; ++j) X[2 * b + j] = std::min(std::max(X0[j], XL[2 * b + j]), XU[2 * b + j]);
       if (G) G[b] = 0.5;
       if (D) for (int j = 0; j < 5; ++j) D[5 * b + j] = 0.25 * (j + 1);
     }
     return 0;
   };
-  B200Solver app(stub);
+  BatchSolveWarmFn wstub = [&](int B, const double *XL, const double *XU, const double *X0, const double *DUAL0, double *OBJ,
+                               int *ST, int *IT, double *X, double *G, double *D) {
+    ++warm_calls;
+    seen_dual0.assign(DUAL0, DUAL0 + 5);
+    const int rc = stub(B, XL, XU, X0, OBJ, ST, IT, X, G, D);
+    for (int b = 0; b < B; ++b) IT[b] = 3;
+    return rc;
+  };
+  Ipopt::SmartPtr<B200Solver> app_holder = new B200Solver(stub, wstub);
+  B200Solver &app = *app_holder;
   std::istringstream opts("# comment\nbonmin.tol 1e-9\nmax_iter 123 # trailing\nprint_level 3\ntol 1e-7\n");
   EXPECT(app.Initialize(opts));
   EXPECT(app.option("tol") && *app.option("tol") == "1e-7" && *app.option("max_iter") == "123" && !app.option("mu_init"));
@@ -95,35 +154,75 @@ int bnlp_host_selftest(void) {
   std::istringstream bad("tol\n");
   EXPECT(!app.Initialize(bad));
   EXPECT(app.Initialize(std::string("/nonexistent/bonmin.opt")));
-  TMINLP2TNLP t;
-  t.n = 2; t.m = 1; t.var_types = {0, 2}; t.x_l = {1.0, 0.0}; t.x_u = {4.0, 3.0}; t.g_l = {-1e19}; t.g_u = {1.0};
-  t.x_init = {2.0, 1.0};
-  EXPECT(app.getUsedWarmStart(t) == nullptr);                 // no duals were set
-  EXPECT(app.OptimizeTNLP(t) == TNLPSolver::solvedOptimal && t.obj_value == 3.0 && app.IterationCount() == 7);
-  CoinWarmStart *ws = app.getWarmStart(t);
-  EXPECT(ws && app.warmStartIsValid(ws) && ws->primalSize() == 2 && ws->dualSize() == 5 && ws->primal()[0] == 2.0 && ws->dual()[4] == 1.25);
-  t.x_init = {0.0, 0.0};
-  EXPECT(!app.warmStartEnabled() && app.setWarmStart(ws, t) && app.warmStartEnabled());
-  EXPECT(t.x_init[0] == 2.0 && t.duals_init.size() == 5);
-  CoinWarmStart *used = app.getUsedWarmStart(t);
-  EXPECT(used && used->primal()[1] == 1.0 && used->dualSize() == 5);
+
+  // ---- a TNLP that is NOT a TMINLP2TNLP: only the Ipopt::TNLP virtuals can be used, and they are, in Ipopt's order
+  Ipopt::SmartPtr<MockTNLP> mock = new MockTNLP();
+  EXPECT(app.OptimizeTNLP(Ipopt::SmartPtr<Ipopt::TNLP>(GetRawPtr(mock))) == TNLPSolver::solvedOptimal);
+  EXPECT(mock->log == "ibsf" && mock->status == Ipopt::SUCCESS && mock->obj == 3.0 && app.IterationCount() == 7);
+  EXPECT(mock->x.size() == 2 && mock->x[0] == 2.0 && mock->zl[0] == 0.25 && mock->zu[1] == 1.0 && mock->lam[0] == 1.25 && mock->g[0] == 0.5);
+  EXPECT(seen_xl[0] == 1.0 && seen_xu[1] == 3.0 && seen_x0[1] == 1.0 && warm_calls == 0);
+  // warm start enabled, but this TNLP has no multipliers to give: asked for them ('S'), then for the primal start alone ('s')
+  mock->log.clear();
+  app.enableWarmStart();
+  EXPECT(app.ReOptimizeTNLP(Ipopt::SmartPtr<Ipopt::TNLP>(GetRawPtr(mock))) == TNLPSolver::solvedOptimal);
+  EXPECT(mock->log == "ibSsf" && warm_calls == 0 && !app.lastSolveWasWarmStarted());
+  // ... and now it has: one get_starting_point call with init_z = init_lambda = true, the warm provider gets [z_L | z_U | lambda]
+  mock->log.clear();
+  mock->duals = {0.1, 0.2, 0.3, 0.4, 0.5};
+  EXPECT(app.ReOptimizeTNLP(Ipopt::SmartPtr<Ipopt::TNLP>(GetRawPtr(mock))) == TNLPSolver::solvedOptimal);
+  EXPECT(mock->log == "ibSf" && warm_calls == 1 && app.lastSolveWasWarmStarted() && app.IterationCount() == 3);
+  EXPECT(seen_dual0.size() == 5 && seen_dual0[0] == 0.1 && seen_dual0[3] == 0.4 && seen_dual0[4] == 0.5);
+  app.disableWarmStart();
+
+  // ---- TMINLP2TNLP + OsiTMINLPInterface: the sequence of InterfaceTest::testSetMethods (test/InterfaceTest.cpp:165-189)
+  Ipopt::SmartPtr<TMINLP2TNLP> tp = new TMINLP2TNLP();
+  TMINLP2TNLP &t = *tp;
+  t.n = 2; t.m = 1; t.var_types = {0, 2}; t.x_l_ = {1.0, 0.0}; t.x_u_ = {4.0, 3.0}; t.g_l_ = {-1e19}; t.g_u_ = {1.0};
+  t.x_init_ = {2.0, 1.0};
+  EXPECT(app.getUsedWarmStart(tp) == nullptr);                 // no duals were set
+  {
+    OsiTMINLPInterface si(tp, Ipopt::SmartPtr<TNLPSolver>(GetRawPtr(app_holder)));
+    const int warm_before = warm_calls;
+    si.setColLower(1, 1.0);
+    EXPECT(si.getColLower()[1] == 1.0);
+    si.initialSolve();
+    EXPECT(si.isProvenOptimal() && si.getColSolution()[1] == 1.0 && warm_calls == warm_before);   // cold solve
+    CoinWarmStart *ws = si.getWarmStart();
+    const IpoptWarmStart *iws = dynamic_cast<const IpoptWarmStart *>(ws);
+    EXPECT(iws && app.warmStartIsValid(ws) && iws->primalSize() == 2 && iws->dualSize() == 5 && iws->primal()[1] == 1.0 && iws->dual()[4] == 1.25);
+    si.setColLower(1, 0.0);
+    si.setColUpper(1, 0.0);
+    EXPECT(si.getColUpper()[1] == 0.0);
+    si.setWarmStart(ws);
+    si.resolve();                                               // setWarmStart -> enableWarmStart -> ReOptimizeTNLP
+    EXPECT(si.isProvenOptimal() && si.getColSolution()[1] == 0.0);
+    EXPECT(warm_calls == warm_before + 1 && app.lastSolveWasWarmStarted());
+    EXPECT(seen_x0[0] == 2.0 && seen_x0[1] == 1.0 && seen_dual0[4] == 1.25 && seen_xu[1] == 0.0);   // the saved point and multipliers
+    CoinWarmStart *used = app.getUsedWarmStart(tp);
+    const IpoptWarmStart *iu = dynamic_cast<const IpoptWarmStart *>(used);
+    EXPECT(iu && iu->primal()[1] == 1.0 && iu->dualSize() == 5);
+    si.setColUpper(1, 3.0);                                     // (the model's own bound again)
+    delete ws; delete used;
+  }
   CoinWarmStart *empty = app.getEmptyWarmStart();
-  EXPECT(!app.warmStartIsValid(empty) && app.setWarmStart(empty, t) && !app.warmStartEnabled());
-  EXPECT(!app.setWarmStart(nullptr, t));
-  delete ws; delete used; delete empty;
+  EXPECT(!app.warmStartIsValid(empty) && app.setWarmStart(empty, tp) && !app.warmStartEnabled());
+  EXPECT(!app.setWarmStart(nullptr, tp));
+  delete empty;
+  const int calls_before = calls;
   fail_next = -17;
-  EXPECT(app.ReOptimizeTNLP(t) == TNLPSolver::exception && app.errorCode() == -17 && app.providerErrors() == 1);
-  EXPECT(TNLPSolver::isError(t.return_status) && TNLPSolver::isRecoverable(TNLPSolver::exception) &&
-         !TNLPSolver::isRecoverable(TNLPSolver::computationError));
-  TNLPSolver::UnsolvedError *e = app.newUnsolvedError(app.errorCode(), &t, "node17");
+  EXPECT(app.ReOptimizeTNLP(Ipopt::SmartPtr<Ipopt::TNLP>(GetRawPtr(tp))) == TNLPSolver::exception && app.errorCode() == -17 && app.providerErrors() == 1);
+  fail_next = 0;
+  TNLPSolver::ReturnStatus st_exc = TNLPSolver::exception, st_ce = TNLPSolver::computationError;
+  EXPECT(app.isError(st_exc) && app.isRecoverable(st_exc) && !app.isRecoverable(st_ce));
+  TNLPSolver::UnsolvedError *e = app.newUnsolvedError(app.errorCode(), tp, "node17");
   std::ostringstream os;
   e->printError(os);
-  EXPECT(e->errorNum() == -17 && e->model() == &t && e->name() == "node17" && os.str().find("B200 batched IPM exited with error code -17") == 0);
+  EXPECT(e->errorNum() == -17 && GetRawPtr(e->model()) == GetRawPtr(tp) && e->name() == "node17" &&
+         os.str().find("B200 batched IPM exited with error code -17") == 0);
   delete e;
-  TNLPSolver *c = app.clone();
-  EXPECT(c && c->solverName() == app.solverName());
-  delete c;
-  EXPECT(calls == 2);
+  Ipopt::SmartPtr<TNLPSolver> c = app.clone();
+  EXPECT(IsValid(c) && c->solverName() == app.solverName() && GetRawPtr(c) != static_cast<TNLPSolver *>(&app));
+  EXPECT(calls == calls_before + 1);
   {   // lineariser: CSR rows of the provider -> OsiRowCuts (skipped slots dropped, global flag), LP -> OsiSolverInterface
     OaBatchFn oa = [](int B, const double *X, const double *, const double *, int getObj, double tiny, double, double, double, OaRows &o) {
       o.rows_per_point = 2;
@@ -178,12 +277,13 @@ int bnlp_resolve_cb(int mode, int n, int m, const double *xl, const double *xu, 
                     bnlp_batch_solve_cb cb, void *ctx, bnlp_retry_result *res, double *obj, int *status, double *x,
                     double *g, double *duals) {
   using namespace Bonmin;
-  TMINLP2TNLP t;
+  Ipopt::SmartPtr<TMINLP2TNLP> t_holder = new TMINLP2TNLP();   // SmartPtr-managed objects live on the heap
+  TMINLP2TNLP &t = *t_holder;
   t.n = n; t.m = m;
-  t.x_l.assign(xl, xl + n); t.x_u.assign(xu, xu + n);
-  t.x_init.assign(x_init, x_init + n);
-  t.x_sol.assign(n, 0.0); t.g_sol.assign(m, 0.0); t.duals_sol.assign(2 * n + m, 0.0);
-  t.obj_value = cur_obj;
+  t.x_l_.assign(xl, xl + n); t.x_u_.assign(xu, xu + n);
+  t.x_init_.assign(x_init, x_init + n);
+  t.x_sol_.assign(n, 0.0); t.g_sol_.assign(m, 0.0); t.duals_sol_.assign(2 * n + m, 0.0);
+  t.obj_value_ = cur_obj;
   t.return_status = (TNLPSolver::ReturnStatus)cur_status;
   RetryOptions o;
   if (max_random_point_radius > 0) o.max_random_point_radius = max_random_point_radius;
@@ -194,11 +294,11 @@ int bnlp_resolve_cb(int mode, int n, int m, const double *xl, const double *xu, 
   const TNLPSolver::ReturnStatus st = mode == 0 ? resolve_for_robustness(t, fn, numsolve, o, r) : resolve_for_cost(t, fn, numsolve, o, r);
   if (res) { res->used = r.used; res->num_failed = r.num_failed; res->num_infeasible = r.num_infeasible;
              res->nlp_solves = r.nlp_solves; res->mean = r.mean; res->std_dev = r.std_dev; }
-  if (obj) *obj = t.obj_value;
+  if (obj) *obj = t.obj_value_;
   if (status) *status = (int)st;
-  if (x) memcpy(x, t.x_sol.data(), sizeof(double) * n);
-  if (g && m) memcpy(g, t.g_sol.data(), sizeof(double) * m);
-  if (duals) memcpy(duals, t.duals_sol.data(), sizeof(double) * (2 * n + m));
+  if (x) memcpy(x, t.x_sol_.data(), sizeof(double) * n);
+  if (g && m) memcpy(g, t.g_sol_.data(), sizeof(double) * m);
+  if (duals) memcpy(duals, t.duals_sol_.data(), sizeof(double) * (2 * n + m));
   return 0;
 }
 
@@ -207,15 +307,16 @@ int bnlp_dive_run_cb(int n, int m, const int *var_type, const double *xl, const 
                      double cutoff, bnlp_batch_solve_cb cb, bnlp_grad_f_cb grad_cb, void *ctx, const bnlp_dive_options *o,
                      bnlp_dive_result *res, double *better_x) {
   using namespace Bonmin;
-  TMINLP2TNLP node;
+  Ipopt::SmartPtr<TMINLP2TNLP> node_holder = new TMINLP2TNLP();   // SmartPtr-managed objects live on the heap
+  TMINLP2TNLP &node = *node_holder;
   node.n = n; node.m = m;
   node.var_types.assign(var_type, var_type + n);
-  node.x_l.assign(xl, xl + n); node.x_u.assign(xu, xu + n);
-  node.g_l.assign(gl, gl + m); node.g_u.assign(gu, gu + m);
-  node.x_init.assign(x_sol, x_sol + n);
-  node.x_sol.assign(x_sol, x_sol + n);
-  node.g_sol.assign(g_sol, g_sol + m);
-  node.obj_value = obj_sol;
+  node.x_l_.assign(xl, xl + n); node.x_u_.assign(xu, xu + n);
+  node.g_l_.assign(gl, gl + m); node.g_u_.assign(gu, gu + m);
+  node.x_init_.assign(x_sol, x_sol + n);
+  node.x_sol_.assign(x_sol, x_sol + n);
+  node.g_sol_.assign(g_sol, g_sol + m);
+  node.obj_value_ = obj_sol;
   DiveOptions opt;
   if (o) {
     opt.rule = o->rule; opt.speculate = o->speculate != 0; opt.seed = o->seed;
@@ -279,10 +380,11 @@ int bnlp_linearizer_engine(bnlp_engine *E, const bnlp_problem *P, int B, const d
   using namespace Bonmin;
   int n = 0, m = 0;
   if (!E || !P || bnlp_problem_sizes(P, &n, &m, nullptr, nullptr)) return -1;
-  TMINLP2TNLP model;
+  Ipopt::SmartPtr<TMINLP2TNLP> model_holder = new TMINLP2TNLP();   // SmartPtr-managed objects live on the heap
+  TMINLP2TNLP &model = *model_holder;
   model.n = n; model.m = m;
-  model.x_l.resize(n); model.x_u.resize(n);
-  bnlp_problem_info(P, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, model.x_l.data(), model.x_u.data(), nullptr, nullptr, nullptr);
+  model.x_l_.resize(n); model.x_u_.resize(n);
+  bnlp_problem_info(P, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, model.x_l_.data(), model.x_u_.data(), nullptr, nullptr, nullptr);
   OaBatchFn oa = [E](int Bp, const double *Xp, const double *xl, const double *xu, int go, double tiny, double vtiny, double relax,
                      double infty, OaRows &o) {
     size_t cap = 0;

@@ -291,6 +291,9 @@ typedef struct bnlp_bb_options {
                                   OsiTMINLPInterface::isAbandoned, BonOsiTMINLPInterface.cpp:2907-2920) is never read as
                                   infeasible: 0 = stop, status 4 (the reference's `nlp_failure_behavior stop`: newUnsolvedError,
                                   :2639-2644), 1 = fathom that node and go on (`fathom`, pretendFailIsInfeasible_) */
+  int number_look_ahead;       /* `number_look_ahead` (BonChooseVariable.cpp:152-158, 930-948): away from the root, stop the
+                                  strong-branching loop after that many candidates in a row that did not improve the best
+                                  score; 0 = off (the default) */
 } bnlp_bb_options;
 typedef struct bnlp_bb_result {
   int status;                 /* 0 optimal, 1 infeasible, 2 limit reached, 3 the batch-solve provider returned an error (the
