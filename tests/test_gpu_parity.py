@@ -448,3 +448,75 @@ def test_warm_started_resolve_parity(bnlp_lib, oracle_ipm):
         assert np.allclose(warm["obj"][ok], cold["obj"][ok], rtol=1e-6, atol=1e-8)
         assert np.abs(warm["iters"] - o["iters"]).max() <= 1
         eng.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B", [4096, 65536])
+def test_c3_baseline_batches_against_the_oracle_on_a_strided_sample(bnlp_lib, oracle_ipm, B):
+    """BASELINE config 3 at its own sizes ("1k-64k independent child NLPs", n = 200): the whole batch is solved on the GPU
+    and a strided sample of 512 children — the same relaxations, solved alone — is checked against the CPU oracle: same
+    status, objective within 1e-6 relative (north_star), same iteration count (the two run the same algorithm)."""
+    m = I.config_c3()
+    eng = _engine(m)
+    root = eng.solve_batch(m.xl, m.xu, m.x0)
+    xs = root["x"][0]
+    XL, XU = I.c3_children(m, xs, B)
+    r = eng.solve_batch(XL, XU, xs, want_g=False, want_duals=False)
+    assert set(np.unique(r["status"])) <= {1, 2, 3}
+    idx = np.unique(np.linspace(0, B - 1, 512).astype(int))
+    o = oracle_ipm.solve_batch(m, XL[idx], XU[idx], xs, threads=16)
+    assert np.array_equal(r["status"][idx], o["status"])
+    ok = o["status"] == 1
+    rel = np.abs(r["obj"][idx] - o["obj"]) / np.maximum(1.0, np.abs(o["obj"]))
+    assert rel[ok].max() <= 1e-6
+    assert np.abs(r["iters"][idx] - o["iters"]).max() <= 1
+    np.testing.assert_allclose(r["x"][idx][ok], o["x"][ok], rtol=0, atol=1e-6 * 10.0)
+    # the same child gives the same bits wherever it sits in a batch (a sample re-solved as a small batch)
+    again = eng.solve_batch(XL[idx[:64]], XU[idx[:64]], xs, want_g=False, want_duals=False)
+    assert np.array_equal(again["obj"], r["obj"][idx[:64]]) and np.array_equal(again["status"], r["status"][idx[:64]])
+    eng.close()
+
+
+@pytest.mark.gpu
+def test_c4_full_size_children_and_oa_rows(bnlp_lib, oracle_ipm):
+    """BASELINE config 4 at full size (SYN-CVX-MINLP n = 500: 100 dense quadratic rows + 1000 exp element terms): the NLP(y)
+    and node relaxations that B-OA / B-QG solve, and the outer-approximation rows of all nonlinear constraints at their
+    solutions, against the CPU oracle."""
+    from oracle.struct_eval import Evaluator, outer_approximation
+    m = I.config_c4()
+    assert m.n == 500
+    eng = _engine(m)
+    root = eng.solve_batch(m.xl, m.xu, m.x0)
+    oroot = oracle_ipm.solve_batch(m, m.xl, m.xu, m.x0)
+    _compare(root, oroot)
+    assert root["status"][0] == 1
+    xs = root["x"][0]
+    B = 24
+    XL, XU = I.c3_children(m, xs, B)
+    nb = int((np.asarray(m.vtype) != 0).sum())
+    ints = np.flatnonzero(np.asarray(m.vtype) != 0)
+    XL[:6, ints] = XU[:6, ints] = np.round(xs[ints])            # NLP(y): every integer fixed (OACutGenerator2::performOa)
+    r = eng.solve_batch(XL, XU, xs)
+    o = oracle_ipm.solve_batch(m, XL, XU, xs, threads=16)
+    ok = _compare(r, o)
+    assert ok.sum() >= 6 and nb > 0
+    # OA rows at the optimal points, cut sides from the NLP multipliers (getOuterApproximation, getObj = 1)
+    ev = Evaluator(m)
+    pts = np.flatnonzero(ok)[:4]
+    out = eng.oa_batch(r["x"][pts], DUALS=r["duals"][pts], get_obj=1)
+    rpp = out["rows_per_point"]
+    for q, b in enumerate(pts):
+        ref = outer_approximation(ev, r["x"][b], duals=r["duals"][b], get_obj=1)
+        got = []
+        for srow in range(rpp):
+            k = q * rpp + srow
+            if out["src_row"][k] < 0:
+                continue
+            a, e = out["row_start"][k], out["row_start"][k + 1]
+            got.append((int(out["src_row"][k]), out["col"][a:e].tolist(), out["val"][a:e], out["lb"][k], out["ub"][k]))
+        assert [c[0] for c in got] == [c[0] for c in ref]
+        for gc, rc in zip(got, ref):
+            assert gc[1] == rc[1]
+            np.testing.assert_allclose(gc[2], rc[2], rtol=1e-11, atol=1e-13)
+            assert gc[4] == pytest.approx(rc[4], rel=1e-11, abs=1e-11)
+    eng.close()
