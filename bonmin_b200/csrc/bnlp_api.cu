@@ -228,6 +228,7 @@ static size_t ipm_smem_doubles(int n, int m, int R, int E, int h_in_smem) {
   const int Rp = (R + 1) & ~1, Kp = (m + 2) & ~1;
   d += (size_t)10 * Rp + (size_t)8 * Kp + (size_t)IPM_NW * 12;
   d += (size_t)(((N + 1) & ~1) * 2 + 2 * Kp) / 2 + 2;   // flg, fixlist, qblk, qfn (ints)
+  if (!h_in_smem) d += 2 * (size_t)((N + 7) & ~7) + 2;  // tile-major H in global memory: the two right-hand sides live here
   return d;
 }
 
@@ -394,7 +395,7 @@ extern "C" bnlp_engine *bnlp_engine_create(const bnlp_problem *prob, const int *
       E->h_in_smem = need + 1024 <= D.smem_optin ? 1 : 0;
       E->smem_bytes = ipm_smem_doubles(n, m, E->R, E->E, E->h_in_smem) * sizeof(double);
       if (E->smem_bytes + 1024 > D.smem_optin) { E->ipm_supported = false; E->ipm_unsupported_why = "iterate vectors do not fit shared memory"; }
-      E->ws_doubles = (size_t)2 * (m + 1) * n + (size_t)M.terms.size() * (2 + TV + TH) + (E->h_in_smem ? 0 : (size_t)(n + 3 + E->E) * (n + 4 + E->E) / 2 + 2);
+      E->ws_doubles = (size_t)2 * (m + 1) * n + (size_t)M.terms.size() * (2 + TV + TH) + (E->h_in_smem ? 0 : (size_t)tm_size(tm_layout(n + 3 + E->E)) + 2);   // tile-major H (bnlp_dense_tm.cuh)
       E->ws_doubles = (E->ws_doubles + 1) & ~(size_t)1;
       // cooperative DMMA kernel: needs H in shared memory, n <= 256 and the group weights to fit the staging area
       E->nqpad = (std::max(E->nq, 1) + 3) & ~3;

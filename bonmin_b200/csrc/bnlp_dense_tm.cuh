@@ -586,27 +586,34 @@ __device__ __forceinline__ bool chol_tm_ll(double *H, const TmLayout &L, int N, 
 // Straight-line (addresses clamped instead of branches), so the JN independent FMA chains interleave.
 template <int JN>
 __device__ __forceinline__ void bs_update(const double *H, const TmLayout &L, int bi, int i0, int nb, int lane, const double (&x)[8],
-                                          double (&v)[8], double &keep) {
+                                          double (&v)[16], double &keep) {
   const double *Trow = H + tm_tile(L, bi, 0);
   const int tstride = (bi == L.nt - 1) ? 8 * L.last_h : 64;
-  double t[JN][8];
 #pragma unroll
-  for (int j = 0; j < JN; ++j) {
-    const int k = min(lane + 32 * j, i0 - 1);
-    const double *T = Trow + (k >> 3) * tstride;
-    const int kc = k & 7;
+  for (int j0 = 0; j0 < JN; j0 += 4) {      // four columns per lane in flight (32 loads, then four independent FMA chains)
+    double t[4][8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) t[j][q] = (q < nb) ? T[(q << 3) + (kc ^ tm_swz(q))] : 0.0;
-  }
+    for (int jj = 0; jj < 4; ++jj) {
+      if (j0 + jj < JN) {
+        const int k = min(lane + 32 * (j0 + jj), i0 - 1);
+        const double *T = Trow + (k >> 3) * tstride;
+        const int kc = k & 7;
 #pragma unroll
-  for (int j = 0; j < JN; ++j) {
-    double a = v[j];
+        for (int q = 0; q < 8; ++q) t[jj][q] = (q < nb) ? T[(q << 3) + (kc ^ tm_swz(q))] : 0.0;
+      }
+    }
 #pragma unroll
-    for (int q = 0; q < 8; ++q) a = fma(-t[j][q], x[q], a);
-    const int k = lane + 32 * j;
-    if (k < i0) {
-      v[j] = a;
-      if (k >= i0 - 8) keep = a;
+    for (int jj = 0; jj < 4; ++jj) {
+      if (j0 + jj < JN) {
+        double a = v[j0 + jj];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) a = fma(-t[jj][q], x[q], a);
+        const int k = lane + 32 * (j0 + jj);
+        if (k < i0) {
+          v[j0 + jj] = a;
+          if (k >= i0 - 8) keep = a;
+        }
+      }
     }
   }
 }
@@ -626,7 +633,7 @@ __device__ __forceinline__ void backsolve_tm(const double *H, const TmLayout &L,
     // lane l keeps entries l, l + 32, ... of its right-hand side in registers; per block the eight solved entries go
     // through shared memory, everything else is independent FMA chains (nothing in the loop is stored to and re-read)
     double *b = w ? b1 : b0;
-    constexpr int J = 8;                      // N <= 256
+    constexpr int J = 16;                     // N <= 512
     double v[J];
 #pragma unroll
     for (int j = 0; j < J; ++j) v[j] = (lane + 32 * j < 8 * ntN) ? b[lane + 32 * j] : 0.0;
@@ -656,6 +663,14 @@ __device__ __forceinline__ void backsolve_tm(const double *H, const TmLayout &L,
         case 6: bs_update<6>(H, L, bi, i0, nb, lane, x, v, keep); break;
         case 7: bs_update<7>(H, L, bi, i0, nb, lane, x, v, keep); break;
         case 8: bs_update<8>(H, L, bi, i0, nb, lane, x, v, keep); break;
+        case 9: bs_update<9>(H, L, bi, i0, nb, lane, x, v, keep); break;
+        case 10: bs_update<10>(H, L, bi, i0, nb, lane, x, v, keep); break;
+        case 11: bs_update<11>(H, L, bi, i0, nb, lane, x, v, keep); break;
+        case 12: bs_update<12>(H, L, bi, i0, nb, lane, x, v, keep); break;
+        case 13: bs_update<13>(H, L, bi, i0, nb, lane, x, v, keep); break;
+        case 14: bs_update<14>(H, L, bi, i0, nb, lane, x, v, keep); break;
+        case 15: bs_update<15>(H, L, bi, i0, nb, lane, x, v, keep); break;
+        case 16: bs_update<16>(H, L, bi, i0, nb, lane, x, v, keep); break;
         default: break;
       }
       // the next block's entries go back to shared memory (one store, after the loop: a store inside it would order

@@ -97,6 +97,13 @@ struct IpmArgs {
 
 __device__ __forceinline__ int tri(int i) { return (i * (i + 1)) >> 1; }
 
+// FP64 tensor-core MMA (SASS DMMA.8x8x4): C[8x8] += A[8x4] B[4x8]; lane (lr = lane / 4, lc = lane % 4) holds A[lr][lc],
+// B[lc][lr], C[lr][2 lc], C[lr][2 lc + 1]
+__device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
 // streaming read of shared read-only model data (no L1 allocation: one CTA per SM never re-reads it from L1)
 __device__ __forceinline__ double ld_stream(const double *p) {
   double v;
@@ -397,6 +404,18 @@ __device__ __forceinline__ void dots_grad(const DevModel &M, const double *grad,
 
 enum { F_FIXED = 1, F_HASL = 2, F_HASU = 4 };
 
+}  // namespace BNLP_NS
+#include "bnlp_dense_tm.cuh"
+namespace BNLP_NS {
+
+// packed lower-triangular index e = tri(i) + k  ->  (i, k)
+__device__ __forceinline__ void packed_ik(int e, int &i, int &k) {
+  i = (int)((sqrt(8.0 * (double)e + 1.0) - 1.0) * 0.5);
+  while (tri(i + 1) <= e) ++i;
+  while (tri(i) > e) --i;
+  k = e - tri(i);
+}
+
 // optional per-phase cycle counters (IpmArgs::phase_cycles != nullptr): 0 residuals 1 W pass 2 J'SJ 3 Cholesky
 // 4 back-substitution 5 direction/mu 6 U pass 7 line search 8 update 9 init
 #define PH_MARK(idx)                                               \
@@ -424,7 +443,14 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
   double *uq = grad + (size_t)(m + 1) * n;        // (m+1) x n
   const int NTm = M.n_terms;
   double *tgl = uq + (size_t)(m + 1) * n;          // per term: value, local gradient (TV), packed local Hessian (TH)
-  if (A.h_in_smem) { H = sp; sp += (Haug + 1) & ~1; } else { H = tgl + (size_t)NTm * TREC; }
+  // Large models (H does not fit shared memory): H lives in this CTA's global workspace (L2 / L1 resident) in the TILE-MAJOR
+  // layout of bnlp_dense_tm.cuh and is assembled, factorised and solved with the DMMA routines there (left-looking
+  // Cholesky: every tile is read-modify-written once; the packed scalar path re-read the whole trailing matrix from L2 per
+  // 8-column panel and ran at ~2 % of the FP64 peak).  The two right-hand sides then live in their own shared-memory vectors.
+  const bool TM = !A.h_in_smem;
+  const TmLayout TL = tm_layout(N + 2 + E);
+  const int nb8 = (N + 7) & ~7, lds_tm = nb8 + 4;
+  if (A.h_in_smem) { H = sp; sp += (Haug + 1) & ~1; } else { H = tgl + (((size_t)NTm * TREC + 1) & ~(size_t)1); }   // 16-byte aligned tiles
   double *stage = sp; sp += (IPM_KC + 1) * npad;
   double *x = sp; sp += npad;
   double *zL = sp; sp += npad;
@@ -464,7 +490,13 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
   int *qfn = qblk + Kp;                    // m+1 ints: functions that own a quadratic block
   double *qwt = wq + Kp;                   // m+1 weights of the compact list
   __shared__ int s_child, s_nqa, s_nfix, s_fail;
-  double *d0 = H + tri(N), *d1 = H + tri(N + 1);   // solutions live in the augmented rows
+  __shared__ int s_ctr[2];
+  // the two right-hand sides / solutions: the augmented rows N, N+1 of the packed H, or (tile-major H) their own vectors
+  double *d0 = H + tri(N), *d1 = H + tri(N + 1);
+  if (TM) {
+    double *dv2 = reinterpret_cast<double *>(qfn + Kp + (Kp & 1));
+    d0 = dv2; d1 = dv2 + nb8;
+  }
   __shared__ int s_nqf;
   if (tid == 0) {
     int c = 0;
@@ -888,11 +920,21 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               const int e = base + u * IPM_NT + tid;
-              if (e < P) H[e] = acc[u];
+              if (e < P) {
+                if (TM) { int i_, k_; packed_ik(e, i_, k_); H[tm_idx(TL, i_, k_)] = acc[u]; }
+                else H[e] = acc[u];
+              }
             }
           }
-          // elastic row
-          for (int k = tid; k <= n; k += IPM_NT) H[tri(n) + k] = 0.0;
+          // elastic row (tile-major: also the corner of the carried rows, so that nothing uninitialised is ever loaded)
+          if (TM) {
+            for (int k = tid; k <= n; k += IPM_NT) H[tm_idx(TL, n, k)] = 0.0;
+            const int nx = 2 + E;
+            for (int q = tid; q < nx * nx; q += IPM_NT)
+              if (q % nx <= q / nx) H[tm_idx(TL, N + q / nx, N + q % nx)] = 0.0;
+          } else {
+            for (int k = tid; k <= n; k += IPM_NT) H[tri(n) + k] = 0.0;
+          }
         }
         __syncthreads();
         if (NTm > 0) {   // + sum_t w_fn(t) * Hessian of term t (stored at the last evaluation); one thread per target entry
@@ -902,24 +944,52 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
               const int t = M.hent_term[e];
               acc = fma(wq[M.term_fn[t]], tgl[(size_t)t * TREC + 1 + TV + M.hent_lidx[e]], acc);
             }
-            H[M.hseg_target[sg]] += acc;
+            if (TM) { int i_, k_; packed_ik(M.hseg_target[sg], i_, k_); H[tm_idx(TL, i_, k_)] += acc; }
+            else H[M.hseg_target[sg]] += acc;
           }
           __syncthreads();
         }
         // fixed variables: identity rows/columns; then the diagonal Sigma_x + delta_w
         for (int e = tid; e < nfix * N; e += IPM_NT) {
           const int j = fixlist[e / N], t = e % N;
-          if (t < j) H[tri(j) + t] = 0.0;
-          else if (t > j) H[tri(t) + j] = 0.0;
+          if (t < j) H[TM ? tm_idx(TL, j, t) : tri(j) + t] = 0.0;
+          else if (t > j) H[TM ? tm_idx(TL, t, j) : tri(t) + j] = 0.0;
         }
         __syncthreads();
         for (int j = tid; j < N; j += IPM_NT) {
-          if (flg[j] & F_FIXED) H[tri(j) + j] = 1.0;
-          else H[tri(j) + j] += Sx[j] + delta_w;
+          double *hjj = H + (TM ? tm_idx(TL, j, j) : tri(j) + j);
+          if (flg[j] & F_FIXED) *hjj = 1.0;
+          else *hjj += Sx[j] + delta_w;
         }
         __syncthreads();
         PH_MARK(1);
         // J' Sigma_s J through staged rank-KC updates: stage[c][j] = sqrt(Ss_r) J[r][j]
+        if (TM) {
+          // rank-16 DMMA updates of the tile-major H from staged rows (row stride lds_tm = 4 mod 8: conflict-free fragments)
+          for (int r0 = 0; r0 < R; r0 += IPM_KC) {
+            const int kc = min(IPM_KC, R - r0);
+            for (int c = tid >> 5; c < IPM_KC; c += IPM_NW) {
+              const int r = min(r0 + c, R - 1);
+              const double sq = (c < kc) ? sqrt(Ss[r]) : 0.0, f = sq * fsc[r];
+              const double *g = grad + (size_t)M.row_fn[r] * n;
+              for (int j = tid & 31; j < lds_tm; j += 32) {
+                double vv = 0.0;
+                if (c < kc && j < N && !(flg[j] & F_FIXED)) vv = (j < n) ? f * g[j] : -sq;
+                stage[c * lds_tm + j] = vv;
+              }
+            }
+            if (tid == 0) s_ctr[0] = 0;
+            __syncthreads();
+            tm_syrk_stage<false>(H, TL, (N + 7) >> 3, stage, lds_tm, IPM_KC, s_ctr);
+            __syncthreads();
+          }
+          // the carried rows: the two right-hand sides and the equality rows A_e (after the factorisation Y_e = L^-1 A_e')
+          for (int j = tid; j < N; j += IPM_NT) { H[tm_idx(TL, N, j)] = d0[j]; H[tm_idx(TL, N + 1, j)] = d1[j]; }
+          for (int e = 0; e < E; ++e) {
+            const double *g = grad + (size_t)M.eq_fn[e] * n;
+            for (int j = tid; j < N; j += IPM_NT) H[tm_idx(TL, N + 2 + e, j)] = (j < n && !(flg[j] & F_FIXED)) ? esc[e] * g[j] : 0.0;
+          }
+        } else {
         for (int r0 = 0; r0 < R; r0 += IPM_KC) {
           const int kc = min(IPM_KC, R - r0);
           for (int c = tid >> 5; c < kc; c += IPM_NW) {   // one warp per staged row
@@ -942,9 +1012,10 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
           const double *g = grad + (size_t)M.eq_fn[e] * n;
           for (int j = tid; j < N; j += IPM_NT) Ye[j] = (j < n && !(flg[j] & F_FIXED)) ? esc[e] * g[j] : 0.0;
         }
+        }
         ++nfact;
         PH_MARK(2);
-        if (chol_packed(H, N, N + 2 + E, stage, npad, &s_fail)) { fact_ok = true; break; }
+        if (TM ? chol_tm_ll(H, TL, N, N + 2 + E, &s_fail) : chol_packed(H, N, N + 2 + E, stage, npad, &s_fail)) { fact_ok = true; break; }
         // inertia correction (first_hessian_perturbation 1e-4, x100 then x8, /3 between iterations)
         if (delta_w == 0.0) delta_w = (delta_w_last == 0.0) ? 1e-4 : fmax(1e-20, delta_w_last / 3.0);
         else delta_w *= (delta_w_last == 0.0 ? 100.0 : 8.0);
@@ -984,9 +1055,13 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
         const int w = tid >> 5, lane = tid & 31;
         for (int p = w; p < E * E + 2 * E; p += IPM_NW) {
           const double *ra, *rb;
-          if (p < E * E) { ra = H + tri(N + 2 + p / E); rb = H + tri(N + 2 + p % E); }
-          else { const int q = p - E * E; ra = H + tri(N + 2 + (q >> 1)); rb = (q & 1) ? d1 : d0; }
+          int ia, ib;     // rows of the carried block: Y_a, and Y_b or a forward-substituted right-hand side
+          if (p < E * E) { ia = N + 2 + p / E; ib = N + 2 + p % E; }
+          else { const int q = p - E * E; ia = N + 2 + (q >> 1); ib = N + (q & 1); }
+          ra = H + tri(ia); rb = (ib >= N + 2) ? H + tri(ib) : (ib == N ? d0 : d1);
           double acc = 0.0;
+          if (TM) { for (int j = lane; j < N; j += 32) acc = fma(H[tm_idx(TL, ia, j)], H[tm_idx(TL, ib, j)], acc); }
+          else
           for (int j = lane; j < N; j += 32) acc = fma(ra[j], rb[j], acc);
 #pragma unroll
           for (int q = 16; q > 0; q >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, q);
@@ -1023,13 +1098,15 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
         __syncthreads();
         if (s_fail) { status = ST_computationError; objv = val[0]; with_duals = true; done = true; break; }
         for (int j = tid; j < N; j += IPM_NT) {
-          double w0 = d0[j], w1 = d1[j];
-          for (int e = 0; e < E; ++e) { const double yv = H[tri(N + 2 + e) + j]; w0 = fma(-yv, de0[e], w0); w1 = fma(-yv, de1[e], w1); }
-          d0[j] = w0; d1[j] = w1;
+          double *p0 = TM ? H + tm_idx(TL, N, j) : d0 + j, *p1 = TM ? H + tm_idx(TL, N + 1, j) : d1 + j;
+          double w0 = *p0, w1 = *p1;
+          for (int e = 0; e < E; ++e) { const double yv = H[TM ? tm_idx(TL, N + 2 + e, j) : tri(N + 2 + e) + j]; w0 = fma(-yv, de0[e], w0); w1 = fma(-yv, de1[e], w1); }
+          *p0 = w0; *p1 = w1;
         }
         __syncthreads();
       }
-      backsolve2(H, N);   // d0 = H^-1 rhs0, d1 = H^-1 rhs1
+      if (TM) backsolve_tm(H, TL, N, d0, d1);   // rows N, N+1 of H -> d0, d1 = H^-1 rhs0, H^-1 rhs1
+      else backsolve2(H, N);   // d0 = H^-1 rhs0, d1 = H^-1 rhs1
       PH_MARK(4);
 
       // ---------------------------------------------------------------- J d0, J d1 per row

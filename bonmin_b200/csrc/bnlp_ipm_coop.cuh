@@ -30,11 +30,6 @@ __device__ unsigned long long g_dbg_cycles[4];
 constexpr int COOP_RB = 32;   // children per cooperative group (four m8 tiles): every block element crosses L2->SM once per 32 children
 constexpr int COOP_NP = COOP_RB / 8;
 
-__device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b) {
-  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
-}
-
 }  // namespace BNLP_NS
 #include "bnlp_dense.cuh"
 namespace BNLP_NS {

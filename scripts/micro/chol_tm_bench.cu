@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 namespace bnlp { constexpr double kInfD = 1e19; }
 #include "../../bonmin_b200/csrc/bnlp_ipm_coop.cuh"
+#include "../../bonmin_b200/csrc/bnlp_dense_tm.cuh"
 using namespace bnlp;
 
 __global__ void __launch_bounds__(IPM_NT, 1) bench_tm(int N, const double *H0, const double *M0, double *Hout, double *Xout,
@@ -129,6 +130,43 @@ __global__ void __launch_bounds__(IPM_NT, 1) bench_ll(int N, const double *H0, l
   }
 }
 
+// the same routines with H in GLOBAL memory (one block of P doubles per CTA, L2/L1 resident): the large-n path
+__global__ void __launch_bounds__(IPM_NT, 1) bench_ll_global(int N, const double *H0, double *Hg, const double *M0, double *Hout,
+                                                             double *Xout, long long *out) {
+  extern __shared__ double sm[];
+  const int Nrows = N + 2;
+  const TmLayout L = tm_layout(Nrows);
+  const int lds = ((N + 2 + 7) & ~7) + 4;
+  const int P = tm_size(L);
+  double *H = Hg + (size_t)blockIdx.x * P, *stage = sm;
+  __shared__ int fail;
+  __shared__ int ctr[2];
+  for (int rep = 0; rep < 2; ++rep) {
+    for (int e = threadIdx.x; e < P; e += IPM_NT) H[e] = H0[e];
+    __syncthreads();
+    long long t0 = clock64();
+    const bool ok = chol_tm_ll(H, L, N, Nrows, &fail);
+    __syncthreads();
+    long long t1 = clock64();
+    if (blockIdx.x == 0 && rep == 1) for (int e = threadIdx.x; e < P; e += IPM_NT) Hout[e] = H[e];
+    __syncthreads();
+    long long t2 = clock64();
+    backsolve_tm(H, L, N, stage, stage + lds);
+    __syncthreads();
+    long long t3 = clock64();
+    if (blockIdx.x == 0 && rep == 1) for (int e = threadIdx.x; e < 2 * N; e += IPM_NT) Xout[e] = stage[(e / N) * lds + e % N];
+    __syncthreads();
+    for (int e = threadIdx.x; e < 16 * lds; e += IPM_NT) stage[e] = M0[e];
+    if (threadIdx.x == 0) ctr[0] = 0;
+    __syncthreads();
+    long long t4 = clock64();
+    tm_syrk_stage<false>(H, L, (N + 7) >> 3, stage, lds, 16, ctr);
+    __syncthreads();
+    long long t5 = clock64();
+    if (threadIdx.x == 0 && blockIdx.x == 0) { out[0] = t1 - t0; out[1] = ok ? 1 : 0; out[2] = t3 - t2; out[3] = t5 - t4; }
+  }
+}
+
 int main(int argc, char **argv) {
   const int N = argc > 1 ? atoi(argv[1]) : 201;
   const int NB = argc > 2 ? atoi(argv[2]) : 1;
@@ -185,6 +223,25 @@ int main(int argc, char **argv) {
   const size_t smem_tm = (size_t)(P + 16 * lds) * 8, smem_p = (size_t)(((Pp + 1) & ~1) + 17 * lds) * 8;
   cudaFuncSetAttribute(bench_tm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tm);
   cudaFuncSetAttribute(bench_packed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p);
+  if (argc > 3 && argv[3][0] == 'g') {
+    double *Hg; cudaMalloc(&Hg, (size_t)NB * P * 8);
+    const size_t smem_g = (size_t)17 * lds * 8;
+    cudaFuncSetAttribute(bench_ll_global, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g);
+    long long h2[8];
+    for (int rep = 0; rep < 2; ++rep) { bench_ll_global<<<NB, IPM_NT, smem_g>>>(N, dHt, Hg, dM0, dHo, dXo, dout); cudaDeviceSynchronize(); }
+    cudaMemcpy(h2, dout, 64, cudaMemcpyDeviceToHost);
+    std::vector<double> Ho(P), Xo(2 * N);
+    cudaMemcpy(Ho.data(), dHo, P * 8, cudaMemcpyDeviceToHost);
+    cudaMemcpy(Xo.data(), dXo, 2 * N * 8, cudaMemcpyDeviceToHost);
+    double errl = 0, errx = 0;
+    for (int i = 0; i < Nrows; ++i)
+      for (int k = 0; k < (i & ~7) && k < N; ++k) errl = fmax(errl, fabs(Ho[tm_idx(L, i, k)] - Lh[(size_t)i * Nrows + k]));
+    for (int r = 0; r < 2; ++r)
+      for (int i = 0; i < N; ++i) errx = fmax(errx, fabs(Xo[r * N + i] - X[r * N + i]) / (1e-300 + fabs(X[r * N + i])));
+    printf("H in GLOBAL memory, N=%d, %d CTAs: chol_tm_ll %lld cycles (ok=%lld), backsolve_tm %lld, rank-16 syrk (add) %lld | max|L err| %.2e max rel x err %.2e (%s)\n",
+           N, NB, h2[0], h2[1], h2[2], h2[3], errl, errx, cudaGetErrorString(cudaGetLastError()));
+    return 0;
+  }
   if (argc > 3) {
     cudaFuncSetAttribute(bench_ll, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tm);
     long long h2[8];

@@ -37,6 +37,9 @@ def test_mytoy_goldens(bnlp_lib, oracle_ipm):
     assert r["duals"][0][8] == pytest.approx(sq5, rel=1e-6)               # :155-159
     assert r["duals"][0][9] == pytest.approx(1.0, rel=1e-6)
     assert r["x"][1][2] == 1.0 and r["x"][2][2] == 0.0                    # :165-189
+    # the x >= 1 child at what Ipopt's 1e-8 relaxations predict analytically (tests/test_oracle_golden.py::test_mytoy_children)
+    assert r["obj"][1] == pytest.approx(-(2.5 - 1e-8 + (2e-8 - 1e-16) ** 0.5), abs=2e-9)
+    assert r["obj"][2] == pytest.approx(-(1 + 2 ** -0.5), rel=1e-6)
     assert list(r["status"]) == [1, 1, 1]
     np.testing.assert_allclose(r["x"], o["x"], atol=1e-6)
     np.testing.assert_allclose(r["duals"], o["duals"], atol=1e-5)

@@ -37,10 +37,18 @@ def test_mytoy_children(oracle_ipm):
     r = oracle_ipm.solve_batch(m, XL, XU, m.x0)
     assert list(r["status"]) == [1, 1]
     assert r["x"][0][2] == 1.0 and r["x"][1][2] == 0.0
-    # analytic objectives -2.5 and -(1+1/sqrt2); the x>=1 child is only reachable thanks to the 1e-8 bound
-    # relaxation, which moves its optimum by O(sqrt(1e-8))
-    assert r["obj"][0] == pytest.approx(-2.5, abs=5e-4)
+    # x <= 0 child: analytic optimum -(1 + 1/sqrt2).
     assert r["obj"][1] == pytest.approx(-(1 + 2 ** -0.5), rel=1e-6)
+    # x >= 1 child: the exact feasible set is the single point (x, y1, y2) = (1, 1, 1/2), objective -2.5, and an interior-
+    # point method only gets there through Ipopt's bound_relax_factor 1e-8.  What the relaxation predicts, exactly: x is
+    # FIXED (xl = xu: eliminated, not relaxed); the row x - y1 <= 0 becomes <= 1e-8, so y1 >= 1 - 1e-8; the circle
+    # (y1-1/2)^2 + (y2-1/2)^2 <= 1/4 becomes <= 1/4 + 1e-8.  Maximising x + y1 + y2 puts y1 on its bound and y2 on the circle:
+    #   (y2 - 1/2)^2 = 1/4 + 1e-8 - (1/2 - 1e-8)^2 = 2e-8 - 1e-16,   objective = -(2.5 - 1e-8 + sqrt(2e-8 - 1e-16)).
+    # The optimum is sqrt-sensitive to the relaxation (d obj / d eps = 3.5e3), so this pins the treatment of all three
+    # relaxations, not just "about -2.5" (SURVEY.md §8c item 3).
+    predicted = -(2.5 - 1e-8 + (2e-8 - 1e-16) ** 0.5)
+    assert r["obj"][0] == pytest.approx(predicted, abs=2e-9)
+    assert r["x"][0][0] == pytest.approx(1 - 1e-8, abs=2e-9) and r["x"][0][1] == pytest.approx(0.5 + (2e-8 - 1e-16) ** 0.5, abs=1e-8)
 
 
 def test_all_fixed_shortcut(oracle_ipm):
