@@ -84,7 +84,8 @@ struct Device {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // model
   DBuf<double> c, A, Qp, Qf, row_sgn, row_bnd, gl, gu, xl, xu;
-  DBuf<int> qidx, row_fn, fn_row_up, fn_row_lo, eq_fn, fn_eq;
+  DBuf<int> qidx, row_fn, fn_row_up, fn_row_lo, eq_fn, fn_eq, dense_rows, sp_seg_start, sp_seg_i, sp_seg_k, sp_ent_row;
+  DBuf<double> sp_ent_p;
   DBuf<double> eq_bnd;
   EvalModelDev ev;   // eval / OA view of the tape
   DBuf<int> e_int;   // packed integer arrays of the eval tape
@@ -262,6 +263,9 @@ struct IpmView {
   std::vector<int> qidx, row_fn, fn_up, fn_lo, eq_fn, fn_eq;
   int nq = 0, nE = 0;
   size_t ldp = 0, ldq = 0;
+  // sparse linear rows of J' Sigma J (DevModel::sp_*): everything else is in dense_rows
+  std::vector<int> dense_rows, sp_seg_start, sp_seg_i, sp_seg_k, sp_ent_row;
+  std::vector<double> sp_ent_p;
 };
 void build_ipm_view(const HostModel &M, IpmView &V) {
   const int n = M.n, m = M.m;
@@ -306,6 +310,34 @@ void build_ipm_view(const HostModel &M, IpmView &V) {
     if (hi) { V.fn_up[i + 1] = (int)V.row_fn.size(); V.row_fn.push_back(i + 1); V.row_sgn.push_back(1.0); V.row_bnd.push_back(M.gu[i]); }
     if (lo) { V.fn_lo[i + 1] = (int)V.row_fn.size(); V.row_fn.push_back(i + 1); V.row_sgn.push_back(-1.0); V.row_bnd.push_back(-M.gl[i]); }
   }
+  // ---- sparse linear rows: a function without quadratic part and element terms whose row of A has few nonzeros
+  std::vector<char> has_term(m + 1, 0);
+  for (const Term &t : M.terms) has_term[t.fn] = 1;
+  struct Ent { int i, k, row; double p; };
+  std::vector<Ent> ents;
+  for (int r = 0; r < (int)V.row_fn.size(); ++r) {
+    const int fn = V.row_fn[r];
+    std::vector<int> cols;
+    for (int j = 0; j < n; ++j) if (V.A[(size_t)fn * n + j] != 0.0) cols.push_back(j);
+    const bool sparse = V.qidx[fn] < 0 && !has_term[fn] && (int)cols.size() <= IPM_SPARSE_ROW && n > 64;
+    if (!sparse) { V.dense_rows.push_back(r); continue; }
+    for (size_t a = 0; a < cols.size(); ++a) {
+      const double va = V.A[(size_t)fn * n + cols[a]];
+      for (size_t b = 0; b <= a; ++b) ents.push_back({cols[a], cols[b], r, va * V.A[(size_t)fn * n + cols[b]]});   // kind 0
+      ents.push_back({n, cols[a], r | (1 << 28), va});                                                           // kind 1
+    }
+    ents.push_back({n, n, r | (2 << 28), 1.0});                                                                   // kind 2
+  }
+  std::stable_sort(ents.begin(), ents.end(), [](const Ent &a, const Ent &b) { return a.i != b.i ? a.i < b.i : a.k < b.k; });
+  V.sp_seg_start.push_back(0);
+  for (size_t e = 0; e < ents.size(); ++e) {
+    if (e == 0 || ents[e].i != ents[e - 1].i || ents[e].k != ents[e - 1].k) {
+      if (e) V.sp_seg_start.push_back((int)e);
+      V.sp_seg_i.push_back(ents[e].i); V.sp_seg_k.push_back(ents[e].k);
+    }
+    V.sp_ent_row.push_back(ents[e].row); V.sp_ent_p.push_back(ents[e].p);
+  }
+  if (!ents.empty()) V.sp_seg_start.push_back((int)ents.size());
 }
 }  // namespace
 
@@ -373,6 +405,8 @@ extern "C" bnlp_engine *bnlp_engine_create(const bnlp_problem *prob, const int *
     bad |= upload(D.row_fn, row_fn); bad |= upload(D.row_sgn, row_sgn); bad |= upload(D.row_bnd, row_bnd);
     bad |= upload(D.fn_row_up, fn_up); bad |= upload(D.fn_row_lo, fn_lo);
     bad |= upload(D.eq_fn, eq_fn); bad |= upload(D.fn_eq, fn_eq); bad |= upload(D.eq_bnd, eq_bnd);
+    bad |= upload(D.dense_rows, V.dense_rows); bad |= upload(D.sp_seg_start, V.sp_seg_start); bad |= upload(D.sp_seg_i, V.sp_seg_i);
+    bad |= upload(D.sp_seg_k, V.sp_seg_k); bad |= upload(D.sp_ent_row, V.sp_ent_row); bad |= upload(D.sp_ent_p, V.sp_ent_p);
     bad |= upload(D.gl, M.gl); bad |= upload(D.gu, M.gu); bad |= upload(D.xl, M.xl); bad |= upload(D.xu, M.xu);
     bad |= upload(D.e_int, e_ints); bad |= upload(D.e_dbl, e_dbls);
     if (bad) { set_err("device upload failed"); delete E; return nullptr; }
@@ -390,6 +424,9 @@ extern "C" bnlp_engine *bnlp_engine_create(const bnlp_problem *prob, const int *
     dm.hseg_target = D.ev.hseg_target; dm.hent_term = D.ev.hent_term; dm.hent_lidx = D.ev.hent_lidx; dm.n_hseg = D.ev.n_hseg;
     dm.term_op_start = D.ev.term_op_start; dm.term_op = D.ev.term_op; dm.term_iarg = D.ev.term_iarg; dm.term_darg = D.ev.term_darg;
     dm.E = E->E; dm.eq_fn = D.eq_fn.p; dm.eq_bnd = D.eq_bnd.p; dm.fn_eq = D.fn_eq.p;
+    dm.Rd = (int)V.dense_rows.size(); dm.dense_rows = D.dense_rows.p;
+    dm.sp_nseg = (int)V.sp_seg_i.size(); dm.sp_seg_start = D.sp_seg_start.p; dm.sp_seg_i = D.sp_seg_i.p; dm.sp_seg_k = D.sp_seg_k.p;
+    dm.sp_ent_row = D.sp_ent_row.p; dm.sp_ent_p = D.sp_ent_p.p;
     if (d == 0) {
       const size_t need = ipm_smem_doubles(n, m, E->R, E->E, 1) * sizeof(double);
       E->h_in_smem = need + 1024 <= D.smem_optin ? 1 : 0;
@@ -448,7 +485,15 @@ int engine_reload_values(bnlp_engine *Q, const HostModel &M) {
     bad |= upload(D.c, M.c); bad |= upload(D.A, V.A); bad |= upload(D.Qp, V.QpD); bad |= upload(D.Qf, V.Qf);
     bad |= upload(D.row_bnd, V.row_bnd); bad |= upload(D.eq_bnd, V.eq_bnd);
     bad |= upload(D.gl, M.gl); bad |= upload(D.gu, M.gu); bad |= upload(D.xl, M.xl); bad |= upload(D.xu, M.xu);
+    // the sparse-row lists depend on which coefficients of A are non-zero: they follow the new numbers
+    bad |= upload(D.dense_rows, V.dense_rows); bad |= upload(D.sp_seg_start, V.sp_seg_start); bad |= upload(D.sp_seg_i, V.sp_seg_i);
+    bad |= upload(D.sp_seg_k, V.sp_seg_k); bad |= upload(D.sp_ent_row, V.sp_ent_row); bad |= upload(D.sp_ent_p, V.sp_ent_p);
     if (bad) return 0;
+    D.dm.A = D.A.p; D.dm.Qp = D.Qp.p; D.dm.Qf = D.Qf.p; D.dm.c = D.c.p; D.dm.row_bnd = D.row_bnd.p; D.dm.eq_bnd = D.eq_bnd.p;
+    D.dm.gl = D.gl.p; D.dm.gu = D.gu.p;
+    D.dm.Rd = (int)V.dense_rows.size(); D.dm.dense_rows = D.dense_rows.p;
+    D.dm.sp_nseg = (int)V.sp_seg_i.size(); D.dm.sp_seg_start = D.sp_seg_start.p; D.dm.sp_seg_i = D.sp_seg_i.p; D.dm.sp_seg_k = D.sp_seg_k.p;
+    D.dm.sp_ent_row = D.sp_ent_row.p; D.dm.sp_ent_p = D.sp_ent_p.p;
   }
   Q->M = M;
   return 1;
@@ -464,9 +509,10 @@ extern "C" void bnlp_engine_free(bnlp_engine *E) {
                     &D.eX2, &D.eDU, &D.eU, &D.oVal, &D.oLB, &D.oUB, &D.dPXL, &D.dPXU, &D.dCB})
       b->release();
     for (auto *b : {&D.qidx, &D.row_fn, &D.fn_row_up, &D.fn_row_lo, &D.e_int, &D.dST, &D.dIT, &D.queue, &D.cidle, &D.eq_fn, &D.fn_eq, &D.oRS, &D.oCI,
-                    &D.oSR, &D.dCP, &D.dCC, &D.dCW})
+                    &D.oSR, &D.dCP, &D.dCC, &D.dCW, &D.dense_rows, &D.sp_seg_start, &D.sp_seg_i, &D.sp_seg_k, &D.sp_ent_row})
       b->release();
     D.stats.release();
+    D.sp_ent_p.release();
     if (D.stream) cudaStreamDestroy(D.stream);
     if (D.ev0) cudaEventDestroy(D.ev0);
     if (D.ev1) cudaEventDestroy(D.ev1);

@@ -75,7 +75,16 @@ struct DevModel {
   const int *fn_term_start, *fn_term_list, *hseg_start, *hseg_target, *hent_term, *hent_lidx;
   int n_hseg;
   const double *gl, *gu;        // m
+  // J' Sigma J of SPARSE linear rows (a linear function with <= IPM_SPARSE_ROW nonzeros, e.g. the linking rows w_j <= z_j of
+  // C5): instead of a dense rank-1 update per row, the few entries of H they touch are listed per TARGET entry (i, k), so
+  // one thread sums a target's contributions in a fixed order (no atomics).  Entry e of target s: row sp_ent_row[e] & 0xfffffff,
+  // kind sp_ent_row[e] >> 28 (0: p = a_i a_k, both columns < n; 1: p = a_k, i = the phase-1 elastic; 2: i = k = the elastic).
+  // Only the rows of dense_rows[0 .. Rd) go through the staged DMMA updates.
+  int Rd, sp_nseg;
+  const int *dense_rows, *sp_seg_start, *sp_seg_i, *sp_seg_k, *sp_ent_row;
+  const double *sp_ent_p;
 };
+constexpr int IPM_SPARSE_ROW = 8;
 
 struct IpmArgs {
   int B;
@@ -380,12 +389,22 @@ __device__ __forceinline__ void pass_U(const DevModel &M, const double *d, doubl
   __syncthreads();
 }
 
+// A function without a quadratic part and without element terms is LINEAR: its gradient is the constant row of M.A, which
+// every CTA shares.  Reading it there instead of from a per-CTA copy keeps the copies of the linear rows out of L2 (C5: 201
+// of 204 functions are linear; the per-CTA gradient block is 650 KB, and 148 of them plus the H blocks do not fit L2).
+__device__ __forceinline__ bool fn_is_linear(const DevModel &M, int k) {
+  return M.qidx[k] < 0 && (M.n_terms == 0 || M.fn_term_start[k + 1] == M.fn_term_start[k]);
+}
+__device__ __forceinline__ const double *grow(const DevModel &M, const double *grad, int k) {
+  return fn_is_linear(M, k) ? M.A + (size_t)k * M.n : grad + (size_t)k * M.n;
+}
+
 // out[k] = base_k . d  for k = 0..m  (base = raw gradients, one warp per function)
 __device__ __forceinline__ void dots_grad(const DevModel &M, const double *grad, const double *d0, const double *d1,
                                           double *g0, double *g1) {
   const int n = M.n, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int k = w; k <= M.m; k += IPM_NW) {
-    const double *g = grad + (size_t)k * n;
+    const double *g = grow(M, grad, k);
     double a = 0.0, b = 0.0;
     for (int j = lane; j < n; j += 32) {
       const double gv = g[j];
@@ -577,11 +596,12 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
         const double *a = M.A + (size_t)k * n;
         double *g = grad + (size_t)k * n;
         const bool hq = M.qidx[k] >= 0;
+        const bool lin = fn_is_linear(M, k);      // gradient = the shared row of M.A: no per-CTA copy is written
         const double *u = uq + (size_t)k * n;
         double acc = 0.0;
         for (int j = lane; j < n; j += 32) {
           const double aj = a[j], uj = hq ? u[j] : 0.0;
-          g[j] = aj + uj;
+          if (!lin) g[j] = aj + uj;
           acc = fma(x[j], aj + 0.5 * uj, acc);
         }
 #pragma unroll
@@ -668,7 +688,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
       {
         const int w = tid >> 5, lane = tid & 31;
         for (int k = w; k <= m; k += IPM_NW) {
-          const double *g = grad + (size_t)k * n;
+          const double *g = grow(M, grad, k);
           double gm = 0.0;
           for (int j = lane; j < n; j += 32)
             if (!(flg[j] & F_FIXED)) gm = fmax(gm, fabs(g[j]));
@@ -752,13 +772,13 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
         const int f = flg[j];
         double r0 = 0.0, r1 = 0.0, sx = 0.0;
         if (!(f & F_FIXED)) {
-          double g0 = (j < n) ? of * grad[j] : (phase1 ? 1.0 : 0.0);
+          double g0 = (j < n) ? of * grow(M, grad, 0)[j] : (phase1 ? 1.0 : 0.0);
           if (j < n)
-            for (int e = 0; e < E; ++e) g0 = fma(esc[e] * grad[(size_t)M.eq_fn[e] * n + j], ye[e], g0);
+            for (int e = 0; e < E; ++e) g0 = fma(esc[e] * grow(M, grad, M.eq_fn[e])[j], ye[e], g0);
           double jv = 0.0, a0 = 0.0, a1 = 0.0;
           if (j < n) {
             for (int r = 0; r < R; ++r) {
-              const double Jrj = fsc[r] * grad[(size_t)M.row_fn[r] * n + j];
+              const double Jrj = fsc[r] * grow(M, grad, M.row_fn[r])[j];
               jv = fma(Jrj, v[r], jv);
               a0 = fma(Jrj, Ss[r] * rc[r], a0);
               a1 += Jrj / s[r];
@@ -966,12 +986,12 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
         // J' Sigma_s J through staged rank-KC updates: stage[c][j] = sqrt(Ss_r) J[r][j]
         if (TM) {
           // rank-16 DMMA updates of the tile-major H from staged rows (row stride lds_tm = 4 mod 8: conflict-free fragments)
-          for (int r0 = 0; r0 < R; r0 += IPM_KC) {
-            const int kc = min(IPM_KC, R - r0);
+          for (int r0 = 0; r0 < M.Rd; r0 += IPM_KC) {
+            const int kc = min(IPM_KC, M.Rd - r0);
             for (int c = tid >> 5; c < IPM_KC; c += IPM_NW) {
-              const int r = min(r0 + c, R - 1);
+              const int r = M.dense_rows[min(r0 + c, M.Rd - 1)];
               const double sq = (c < kc) ? sqrt(Ss[r]) : 0.0, f = sq * fsc[r];
-              const double *g = grad + (size_t)M.row_fn[r] * n;
+              const double *g = grow(M, grad, M.row_fn[r]);
               for (int j = tid & 31; j < lds_tm; j += 32) {
                 double vv = 0.0;
                 if (c < kc && j < N && !(flg[j] & F_FIXED)) vv = (j < n) ? f * g[j] : -sq;
@@ -986,16 +1006,16 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
           // the carried rows: the two right-hand sides and the equality rows A_e (after the factorisation Y_e = L^-1 A_e')
           for (int j = tid; j < N; j += IPM_NT) { H[tm_idx(TL, N, j)] = d0[j]; H[tm_idx(TL, N + 1, j)] = d1[j]; }
           for (int e = 0; e < E; ++e) {
-            const double *g = grad + (size_t)M.eq_fn[e] * n;
+            const double *g = grow(M, grad, M.eq_fn[e]);
             for (int j = tid; j < N; j += IPM_NT) H[tm_idx(TL, N + 2 + e, j)] = (j < n && !(flg[j] & F_FIXED)) ? esc[e] * g[j] : 0.0;
           }
         } else {
-        for (int r0 = 0; r0 < R; r0 += IPM_KC) {
-          const int kc = min(IPM_KC, R - r0);
+        for (int r0 = 0; r0 < M.Rd; r0 += IPM_KC) {
+          const int kc = min(IPM_KC, M.Rd - r0);
           for (int c = tid >> 5; c < kc; c += IPM_NW) {   // one warp per staged row
-            const int r = r0 + c;
+            const int r = M.dense_rows[r0 + c];
             const double sq = sqrt(Ss[r]), f = sq * fsc[r];
-            const double *g = grad + (size_t)M.row_fn[r] * n;
+            const double *g = grow(M, grad, M.row_fn[r]);
             for (int j = tid & 31; j < npad; j += 32) {
               double vv = 0.0;
               if (j < N && !(flg[j] & F_FIXED)) vv = (j < n) ? f * g[j] : -sq;
@@ -1009,10 +1029,23 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
         // equality rows A_e ride along as extra rows: after the factorisation they hold Y_e = L^-1 A_e'
         for (int e = 0; e < E; ++e) {
           double *Ye = H + tri(N + 2 + e);
-          const double *g = grad + (size_t)M.eq_fn[e] * n;
+          const double *g = grow(M, grad, M.eq_fn[e]);
           for (int j = tid; j < N; j += IPM_NT) Ye[j] = (j < n && !(flg[j] & F_FIXED)) ? esc[e] * g[j] : 0.0;
         }
         }
+        // sparse linear rows: one thread per touched entry of H (fixed summation order)
+        for (int sg = tid; sg < M.sp_nseg; sg += IPM_NT) {
+          const int i = M.sp_seg_i[sg], k = M.sp_seg_k[sg];
+          if ((flg[i] | flg[k]) & F_FIXED) continue;
+          double acc = 0.0;
+          for (int e = M.sp_seg_start[sg]; e < M.sp_seg_start[sg + 1]; ++e) {
+            const int r = M.sp_ent_row[e] & 0xfffffff, kind = M.sp_ent_row[e] >> 28;
+            const double t = (kind == 0) ? Ss[r] * fsc[r] * fsc[r] : (kind == 1) ? -Ss[r] * fsc[r] : Ss[r];
+            acc = fma(t, M.sp_ent_p[e], acc);
+          }
+          H[TM ? tm_idx(TL, i, k) : tri(i) + k] += acc;
+        }
+        __syncthreads();
         ++nfact;
         PH_MARK(2);
         if (TM ? chol_tm_ll(H, TL, N, N + 2 + E, &s_fail) : chol_packed(H, N, N + 2 + E, stage, npad, &s_fail)) { fact_ok = true; break; }
@@ -1026,13 +1059,13 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
           const int f = flg[j];
           double r0 = 0.0, r1 = 0.0;
           if (!(f & F_FIXED)) {
-            double g0 = (j < n) ? of * grad[j] : (phase1 ? 1.0 : 0.0);
+            double g0 = (j < n) ? of * grow(M, grad, 0)[j] : (phase1 ? 1.0 : 0.0);
             if (j < n)
-              for (int e = 0; e < E; ++e) g0 = fma(esc[e] * grad[(size_t)M.eq_fn[e] * n + j], ye[e], g0);
+              for (int e = 0; e < E; ++e) g0 = fma(esc[e] * grow(M, grad, M.eq_fn[e])[j], ye[e], g0);
             double a0 = 0.0, a1 = 0.0;
             if (j < n) {
               for (int r = 0; r < R; ++r) {
-                const double Jrj = fsc[r] * grad[(size_t)M.row_fn[r] * n + j];
+                const double Jrj = fsc[r] * grow(M, grad, M.row_fn[r])[j];
                 a0 = fma(Jrj, Ss[r] * rc[r], a0);
                 a1 += Jrj / s[r];
               }

@@ -30,6 +30,8 @@ def _init(which):
 def _solve(args):
     from scipy.optimize import Bounds, NonlinearConstraint, minimize
     xl, xu, x0 = args
+    if (xu < xl).any():            # crossed bounds: infeasible before any solver is asked (status -1 = not solved)
+        return 0.0, float(np.max(xl - xu)), -1, 0.0, 0
     m, c, A, qidx, Q = (_G[k] for k in ("m", "c", "A", "qidx", "Q"))
     n, mm = m.n, m.m
     Qk = [Q[qidx[k]] if qidx[k] >= 0 else None for k in range(mm + 1)]
