@@ -85,13 +85,16 @@ struct Device {
   // model
   DBuf<double> c, A, Qp, Qf, row_sgn, row_bnd, gl, gu, xl, xu;
   DBuf<int> qidx, row_fn, fn_row_up, fn_row_lo, eq_fn, fn_eq, dense_rows, sp_seg_start, sp_seg_i, sp_seg_k, sp_ent_row;
-  DBuf<double> sp_ent_p;
+  DBuf<double> sp_ent_p, lrV;
+  DBuf<int> fn_lr_start;
   DBuf<double> eq_bnd;
   EvalModelDev ev;   // eval / OA view of the tape
   DBuf<int> e_int;   // packed integer arrays of the eval tape
   DBuf<double> e_dbl;
   // solve buffers
   DBuf<double> dXL, dXU, dX0, dOBJ, dX, dG, dD, dD0, ws, cxw, cW, cxd;
+  DBuf<double> xch;          // cooperative kernel: [ws | Wbuf | xd | xw] in ONE allocation (one L2 access-policy window covers it)
+  size_t l2_persist_max = 0, l2_window_max = 0;
   DBuf<int> cidle;
   DBuf<int> dST, dIT, queue;
   DBuf<double> dPXL, dPXU, dCB;   // bnlp_solve_children: parent bounds and the one changed bound of each child
@@ -123,6 +126,7 @@ struct bnlp_engine {
   bool coop256 = false;   // small model: 256-thread CTAs, two per SM
   size_t coop_smem_bytes = 0;
   int nqpad = 0, ldd = 0;
+  size_t l2_set_aside = 0;   // bytes of L2 reserved for persisting lines (cudaLimitPersistingL2CacheSize), device 0's view
   size_t ws_doubles = 0;
   int nnz_jac = 0, nnz_hes = 0, m_nl = 0;
   bnlp_engine *tqp_engine = nullptr;   // cached engine of the QP strong-branching surrogate (same shape at every node)
@@ -219,7 +223,7 @@ extern "C" int bnlp_problem_info(const bnlp_problem *p, int *jac_irow, int *jac_
   return 0;
 }
 
-static size_t ipm_smem_doubles(int n, int m, int R, int E, int h_in_smem) {
+static size_t ipm_smem_doubles(int n, int m, int R, int E, int h_in_smem, int n_lr = 0) {
   const int N = n + 1;
   const int npad = (N + 2 + 3) & ~3;
   size_t d = 5 * IPM_MAXE + IPM_MAXE * IPM_MAXE;
@@ -229,7 +233,7 @@ static size_t ipm_smem_doubles(int n, int m, int R, int E, int h_in_smem) {
   const int Rp = (R + 1) & ~1, Kp = (m + 2) & ~1;
   d += (size_t)10 * Rp + (size_t)8 * Kp + (size_t)IPM_NW * 12;
   d += (size_t)(((N + 1) & ~1) * 2 + 2 * Kp) / 2 + 2;   // flg, fixlist, qblk, qfn (ints)
-  if (!h_in_smem) d += 2 * (size_t)((N + 7) & ~7) + 2;  // tile-major H in global memory: the two right-hand sides live here
+  if (!h_in_smem) d += 2 * (size_t)((N + 7) & ~7) + 2 + IPM_KC + (size_t)n_lr;  // tile-major H in global memory: the two right-hand sides live here (+ chunk signs, low-rank products)
   return d;
 }
 
@@ -266,7 +270,43 @@ struct IpmView {
   // sparse linear rows of J' Sigma J (DevModel::sp_*): everything else is in dense_rows
   std::vector<int> dense_rows, sp_seg_start, sp_seg_i, sp_seg_k, sp_ent_row;
   std::vector<double> sp_ent_p;
+  // low-rank quadratic blocks (DevModel::lrV): factor rows per function, CSR over functions 0 .. m
+  std::vector<int> fn_lr_start;
+  std::vector<double> lrV;
+  int n_lr = 0;
 };
+
+// Pivoted Cholesky of a symmetric block given as packed lower triangle: Q ~= sum_r v_r v_r' with at most max_rank rows.
+// Returns the rank, or -1 if the block is not positive semidefinite of rank <= max_rank to the relative tolerance.
+int pivoted_cholesky(const double *Qp, int n, int max_rank, double rel_tol, std::vector<double> &rows) {
+  auto q = [&](int i, int j) { return i >= j ? Qp[(size_t)i * (i + 1) / 2 + j] : Qp[(size_t)j * (j + 1) / 2 + i]; };
+  std::vector<double> d(n);
+  double dmax0 = 0.0;
+  for (int i = 0; i < n; ++i) { d[i] = q(i, i); dmax0 = std::max(dmax0, std::fabs(d[i])); }
+  rows.clear();
+  if (dmax0 == 0.0) return 0;
+  int rank = 0;
+  for (;;) {
+    int piv = 0;
+    double dm = -1e300, dmin = 1e300;
+    for (int i = 0; i < n; ++i) { if (d[i] > dm) { dm = d[i]; piv = i; } dmin = std::min(dmin, d[i]); }
+    if (dmin < -rel_tol * dmax0 * 10) return -1;          // indefinite
+    if (dm <= rel_tol * dmax0) break;                      // residual diagonal gone: done (a PSD residual is then gone everywhere)
+    if (rank == max_rank) return -1;
+    rows.resize((size_t)(rank + 1) * n);
+    double *v = rows.data() + (size_t)rank * n;
+    const double inv = 1.0 / std::sqrt(dm);
+    for (int i = 0; i < n; ++i) {
+      double a = q(i, piv);
+      for (int r = 0; r < rank; ++r) a -= rows[(size_t)r * n + i] * rows[(size_t)r * n + piv];
+      v[i] = a * inv;
+    }
+    for (int i = 0; i < n; ++i) d[i] -= v[i] * v[i];
+    d[piv] = 0.0;
+    ++rank;
+  }
+  return rank;
+}
 void build_ipm_view(const HostModel &M, IpmView &V) {
   const int n = M.n, m = M.m;
   const size_t P = (size_t)n * (n + 1) / 2;
@@ -338,6 +378,22 @@ void build_ipm_view(const HostModel &M, IpmView &V) {
     V.sp_ent_row.push_back(ents[e].row); V.sp_ent_p.push_back(ents[e].p);
   }
   if (!ents.empty()) V.sp_seg_start.push_back((int)ents.size());
+  // ---- low-rank quadratic blocks (used by the large-model path only; the dense copies stay for evaluation / OA)
+  V.fn_lr_start.assign(m + 2, 0);
+  V.n_lr = 0;
+  if (n > 256 && !getenv("BNLP_NO_LOWRANK")) {
+    std::vector<double> rows;
+    for (int k = 0; k <= m; ++k) {
+      V.fn_lr_start[k] = V.n_lr;
+      if (V.qidx[k] < 0) continue;
+      const int rk = pivoted_cholesky(Qp.data() + (size_t)V.qidx[k] * P, n, IPM_LR_MAX, 1e-14, rows);
+      if (rk <= 0) continue;
+      V.lrV.insert(V.lrV.end(), rows.begin(), rows.begin() + (size_t)rk * n);
+      V.n_lr += rk;
+    }
+  }
+  V.fn_lr_start[m + 1] = V.n_lr;
+  for (int k = m; k >= 0; --k) if (V.fn_lr_start[k] > V.fn_lr_start[k + 1]) V.fn_lr_start[k] = V.fn_lr_start[k + 1];
 }
 }  // namespace
 
@@ -397,6 +453,8 @@ extern "C" bnlp_engine *bnlp_engine_create(const bnlp_problem *prob, const int *
     cudaGetDeviceProperties(&prop, D.id);
     D.sms = prop.multiProcessorCount;
     D.smem_optin = prop.sharedMemPerBlockOptin;
+    D.l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
+    D.l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
     cudaStreamCreateWithFlags(&D.stream, cudaStreamNonBlocking);
     cudaEventCreate(&D.ev0);
     cudaEventCreate(&D.ev1);
@@ -407,6 +465,7 @@ extern "C" bnlp_engine *bnlp_engine_create(const bnlp_problem *prob, const int *
     bad |= upload(D.eq_fn, eq_fn); bad |= upload(D.fn_eq, fn_eq); bad |= upload(D.eq_bnd, eq_bnd);
     bad |= upload(D.dense_rows, V.dense_rows); bad |= upload(D.sp_seg_start, V.sp_seg_start); bad |= upload(D.sp_seg_i, V.sp_seg_i);
     bad |= upload(D.sp_seg_k, V.sp_seg_k); bad |= upload(D.sp_ent_row, V.sp_ent_row); bad |= upload(D.sp_ent_p, V.sp_ent_p);
+    bad |= upload(D.fn_lr_start, V.fn_lr_start); bad |= upload(D.lrV, V.lrV);
     bad |= upload(D.gl, M.gl); bad |= upload(D.gu, M.gu); bad |= upload(D.xl, M.xl); bad |= upload(D.xu, M.xu);
     bad |= upload(D.e_int, e_ints); bad |= upload(D.e_dbl, e_dbls);
     if (bad) { set_err("device upload failed"); delete E; return nullptr; }
@@ -427,10 +486,11 @@ extern "C" bnlp_engine *bnlp_engine_create(const bnlp_problem *prob, const int *
     dm.Rd = (int)V.dense_rows.size(); dm.dense_rows = D.dense_rows.p;
     dm.sp_nseg = (int)V.sp_seg_i.size(); dm.sp_seg_start = D.sp_seg_start.p; dm.sp_seg_i = D.sp_seg_i.p; dm.sp_seg_k = D.sp_seg_k.p;
     dm.sp_ent_row = D.sp_ent_row.p; dm.sp_ent_p = D.sp_ent_p.p;
+    dm.n_lr = V.n_lr; dm.fn_lr_start = D.fn_lr_start.p; dm.lrV = D.lrV.p;
     if (d == 0) {
       const size_t need = ipm_smem_doubles(n, m, E->R, E->E, 1) * sizeof(double);
       E->h_in_smem = need + 1024 <= D.smem_optin ? 1 : 0;
-      E->smem_bytes = ipm_smem_doubles(n, m, E->R, E->E, E->h_in_smem) * sizeof(double);
+      E->smem_bytes = ipm_smem_doubles(n, m, E->R, E->E, E->h_in_smem, V.n_lr) * sizeof(double);
       if (E->smem_bytes + 1024 > D.smem_optin) { E->ipm_supported = false; E->ipm_unsupported_why = "iterate vectors do not fit shared memory"; }
       E->ws_doubles = (size_t)2 * (m + 1) * n + (size_t)M.terms.size() * (2 + TV + TH) + (E->h_in_smem ? 0 : (size_t)tm_size(tm_layout(n + 3 + E->E)) + 2);   // tile-major H (bnlp_dense_tm.cuh)
       E->ws_doubles = (E->ws_doubles + 1) & ~(size_t)1;
@@ -494,6 +554,8 @@ int engine_reload_values(bnlp_engine *Q, const HostModel &M) {
     D.dm.Rd = (int)V.dense_rows.size(); D.dm.dense_rows = D.dense_rows.p;
     D.dm.sp_nseg = (int)V.sp_seg_i.size(); D.dm.sp_seg_start = D.sp_seg_start.p; D.dm.sp_seg_i = D.sp_seg_i.p; D.dm.sp_seg_k = D.sp_seg_k.p;
     D.dm.sp_ent_row = D.sp_ent_row.p; D.dm.sp_ent_p = D.sp_ent_p.p;
+    if (upload(D.fn_lr_start, V.fn_lr_start) || upload(D.lrV, V.lrV)) return 0;
+    D.dm.n_lr = V.n_lr; D.dm.fn_lr_start = D.fn_lr_start.p; D.dm.lrV = D.lrV.p;
   }
   Q->M = M;
   return 1;
@@ -505,14 +567,14 @@ extern "C" void bnlp_engine_free(bnlp_engine *E) {
   for (Device &D : E->devs) {
     cudaSetDevice(D.id);
     for (auto *b : {&D.c, &D.A, &D.Qp, &D.Qf, &D.row_sgn, &D.row_bnd, &D.gl, &D.gu, &D.xl, &D.xu, &D.e_dbl, &D.dXL, &D.dXU,
-                    &D.dX0, &D.dOBJ, &D.dX, &D.dG, &D.dD, &D.dD0, &D.ws, &D.cxw, &D.cW, &D.cxd, &D.eq_bnd, &D.eX, &D.eLAM, &D.eF, &D.eG, &D.eGF, &D.eJ, &D.eH,
+                    &D.dX0, &D.dOBJ, &D.dX, &D.dG, &D.dD, &D.dD0, &D.ws, &D.cxw, &D.cW, &D.cxd, &D.xch, &D.eq_bnd, &D.eX, &D.eLAM, &D.eF, &D.eG, &D.eGF, &D.eJ, &D.eH,
                     &D.eX2, &D.eDU, &D.eU, &D.oVal, &D.oLB, &D.oUB, &D.dPXL, &D.dPXU, &D.dCB})
       b->release();
     for (auto *b : {&D.qidx, &D.row_fn, &D.fn_row_up, &D.fn_row_lo, &D.e_int, &D.dST, &D.dIT, &D.queue, &D.cidle, &D.eq_fn, &D.fn_eq, &D.oRS, &D.oCI,
                     &D.oSR, &D.dCP, &D.dCC, &D.dCW, &D.dense_rows, &D.sp_seg_start, &D.sp_seg_i, &D.sp_seg_k, &D.sp_ent_row})
       b->release();
     D.stats.release();
-    D.sp_ent_p.release();
+    D.sp_ent_p.release(); D.lrV.release(); D.fn_lr_start.release();
     if (D.stream) cudaStreamDestroy(D.stream);
     if (D.ev0) cudaEventDestroy(D.ev0);
     if (D.ev1) cudaEventDestroy(D.ev1);
@@ -534,26 +596,58 @@ static int launch_ipm(bnlp_engine *E, Device &D, int B, const double *dXL, const
   static const int min_b256 = getenv("BNLP_COOP256_MIN_B") ? atoi(getenv("BNLP_COOP256_MIN_B")) : 0;   // (tuning aid)
   const bool use256 = E->coop256 && E->opt.ctas_per_device <= 0 && B >= (min_b256 > 0 ? min_b256 : D.sms + D.sms / 4);
   if (use256) ctas = 2 * D.sms;
-  if (D.ws.reserve((size_t)ctas * E->ws_doubles)) { set_err("workspace allocation failed"); return -1; }
+  // cooperative kernel: the per-CTA workspace and the three exchange buffers of the shared passes are carved from ONE block,
+  // which is marked PERSISTING in L2 for this launch: they are rewritten every iteration (W_b 162 KB + Q.dx 65 KB + gradients
+  // per child and step at C3) and round 1's ncu showed half of that traffic going out to HBM (12 GB per 4096-child launch
+  // against 36 MB of algorithmic bytes) although the whole working set is smaller than L2.
+  const size_t ws_cnt = (size_t)ctas * E->ws_doubles;
+  size_t w_off = 0, xd_off = 0, xw_off = 0, xch_cnt = 0;
+  if (E->coop_ok) {
+    auto up = [](size_t v) { return (v + 31) & ~(size_t)31; };   // 256-byte aligned pieces
+    w_off = up(ws_cnt); xd_off = w_off + up((size_t)ctas * D.dm.ldp); xw_off = xd_off + up((size_t)ctas * E->ldd);
+    xch_cnt = xw_off + up((size_t)ctas * E->nqpad);
+    if (D.xch.reserve(xch_cnt) || D.cidle.reserve(2)) { set_err("cooperative buffers: allocation failed"); return -1; }
+  } else if (D.ws.reserve(ws_cnt)) { set_err("workspace allocation failed"); return -1; }
   CK(cudaMemsetAsync(D.queue.p, 0, sizeof(int), stream));
   CK(cudaMemsetAsync(D.stats.p, 0, 12 * sizeof(long long), stream));
   IpmArgs a{};
   a.B = B; a.XL = dXL; a.XU = dXU; a.X0 = dX0; a.x0_stride = x0_per_child ? E->M.n : 0;
   a.DUAL0 = dDUAL0; a.dual0_stride = dual0_per_child ? 2 * E->M.n + E->M.m : 0;
   a.OBJ = dOBJ; a.STATUS = dST; a.ITERS = dIT; a.X = dX; a.G = dG; a.DUALS = dD;
-  a.queue = D.queue.p; a.ws = D.ws.p; a.ws_stride = E->ws_doubles; a.h_in_smem = E->h_in_smem; a.stats = D.stats.p;
+  a.queue = D.queue.p; a.ws = E->coop_ok ? D.xch.p : D.ws.p; a.ws_stride = E->ws_doubles; a.h_in_smem = E->h_in_smem; a.stats = D.stats.p;
   a.phase_cycles = getenv("BNLP_PHASE_TIMERS") ? D.stats.p + 2 : nullptr;
   a.o = IpmOpt();
   a.o.tol = E->opt.tol; a.o.max_iter = E->opt.max_iter;
   if (E->coop_ok) {
     CoopBufs cb{};
-    const size_t P = (size_t)D.dm.P;
-    if (D.cxw.reserve((size_t)ctas * E->nqpad) || D.cW.reserve((size_t)ctas * D.dm.ldp) || D.cxd.reserve((size_t)ctas * E->ldd) ||
-        D.cidle.reserve(2)) { set_err("cooperative buffers: allocation failed"); return -1; }
     CK(cudaMemsetAsync(D.cidle.p, 0, 2 * sizeof(int), stream));
-    cb.xw = D.cxw.p; cb.Wbuf = D.cW.p; cb.xd = D.cxd.p; cb.idle_cnt = D.cidle.p; cb.nqpad = E->nqpad; cb.ldd = E->ldd;
-    if (use256) CK(bnlp_coop256_launch(a.phase_cycles != nullptr, ctas, E->coop_smem_bytes, stream, &D.dm, &a, &cb));
-    else CK(ipm_coop_launch(a.phase_cycles != nullptr, ctas, E->coop_smem_bytes, stream, D.dm, a, cb));
+    cb.xw = D.xch.p + xw_off; cb.Wbuf = D.xch.p + w_off; cb.xd = D.xch.p + xd_off; cb.idle_cnt = D.cidle.p; cb.nqpad = E->nqpad; cb.ldd = E->ldd;
+    static const bool no_persist = getenv("BNLP_NO_L2_PERSIST") != nullptr;
+    const size_t xbytes = xch_cnt * sizeof(double);
+    bool windowed = false;
+    if (!no_persist && D.l2_persist_max > 0 && D.l2_window_max > 0) {
+      // (the set-aside is a device limit; the window is an attribute of the launching stream and is cleared right after the
+      // launch has been enqueued, so a caller's stream is left as it was)
+      const size_t want = std::min(xbytes, D.l2_persist_max);
+      if (E->l2_set_aside < want && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) E->l2_set_aside = want;
+      cudaStreamAttrValue av{};
+      av.accessPolicyWindow.base_ptr = D.xch.p;
+      av.accessPolicyWindow.num_bytes = std::min(xbytes, D.l2_window_max);
+      av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)E->l2_set_aside / (double)std::max<size_t>(av.accessPolicyWindow.num_bytes, 1));
+      av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      windowed = E->l2_set_aside > 0 && cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &av) == cudaSuccess;
+      cudaGetLastError();
+    }
+    cudaError_t le;
+    if (use256) le = bnlp_coop256_launch(a.phase_cycles != nullptr, ctas, E->coop_smem_bytes, stream, &D.dm, &a, &cb);
+    else le = ipm_coop_launch(a.phase_cycles != nullptr, ctas, E->coop_smem_bytes, stream, D.dm, a, cb);
+    if (windowed) {
+      cudaStreamAttrValue av{};
+      av.accessPolicyWindow.num_bytes = 0;
+      cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &av);
+    }
+    CK(le);
   } else CK(ipm_general_launch(E->M.n > 256, ctas, E->smem_bytes, stream, D.dm, a));
   E->launches++;
   CK(cudaGetLastError());

@@ -81,8 +81,10 @@ __device__ __forceinline__ void tm_unit_decode(int m, int u, int &r2, int &cq) {
 
 // ---- H(tile rows < ntr) (+)= M' M.  M: K staged rows of length ld (ld = 4 mod 8 doubles: conflict-free fragments), zero
 // beyond the last real column.  Units are taken from *ctr (shared memory, zeroed by the caller before a CTA barrier).
+// sgn (optional, K values of +-1 in shared memory): staged row c enters as sgn[c] * m_c m_c' (the A fragments are scaled).
 template <bool FIRST>
-__device__ __forceinline__ void tm_syrk_stage(double *H, const TmLayout &L, int ntr, const double *M, int ld, int K, int *ctr) {
+__device__ __forceinline__ void tm_syrk_stage(double *H, const TmLayout &L, int ntr, const double *M, int ld, int K, int *ctr,
+                                              const double *sgn = nullptr) {
   const int lane = threadIdx.x & 31;
   const int lr = lane >> 2, lc = lane & 3;
   const int nunits = tm_units(ntr);
@@ -113,7 +115,8 @@ __device__ __forceinline__ void tm_syrk_stage(double *H, const TmLayout &L, int 
     if (ntc == 4 && has1 && bk0 + 3 <= bi0) {          // all eight tiles on or below the diagonal
 #pragma unroll 2
       for (int k = 0; k < K; k += 4) {
-        const double a0 = Ma[k * ld], a1 = Ma[k * ld + 8];
+        const double sg = sgn ? sgn[k + lc] : 1.0;
+        const double a0 = sg * Ma[k * ld], a1 = sg * Ma[k * ld + 8];
         const double v0 = Mb[k * ld], v1 = Mb[k * ld + 8], v2 = Mb[k * ld + 16], v3 = Mb[k * ld + 24];
         dmma(acc[0][0][0], acc[0][0][1], a0, v0);
         dmma(acc[1][0][0], acc[1][0][1], a1, v0);
@@ -126,7 +129,8 @@ __device__ __forceinline__ void tm_syrk_stage(double *H, const TmLayout &L, int 
       }
     } else {
       for (int k = 0; k < K; k += 4) {
-        const double a0 = Ma[k * ld], a1 = has1 ? Ma[k * ld + 8] : 0.0;
+        const double sg = sgn ? sgn[k + lc] : 1.0;
+        const double a0 = sg * Ma[k * ld], a1 = has1 ? sg * Ma[k * ld + 8] : 0.0;
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           if (t < ntc) {

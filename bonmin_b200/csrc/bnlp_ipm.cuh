@@ -83,8 +83,17 @@ struct DevModel {
   int Rd, sp_nseg;
   const int *dense_rows, *sp_seg_start, *sp_seg_i, *sp_seg_k, *sp_ent_row;
   const double *sp_ent_p;
+  // LOW-RANK quadratic parts (large-model path only): Q_k = sum_r v_r v_r' over the factor rows fn_lr_start[k] ..
+  // fn_lr_start[k+1] of lrV (n_lr x n), found by a pivoted Cholesky when the model is loaded (a sum of squares of linear forms
+  // arrives as a dense n x n block from the tape builder).  u_k = Q_k d costs 2 r n FMAs instead of n^2 and no block is
+  // streamed (C4: 100 blocks of 500 x 500 = 200 MB per pass and CTA); their part of the Hessian, sum_k w_k Q_k, is a
+  // rank-(sum r) update done with the staged DMMA rows of J' Sigma J.  n_lr = 0: every block is dense.
+  int n_lr;
+  const int *fn_lr_start;       // m+2
+  const double *lrV;
 };
 constexpr int IPM_SPARSE_ROW = 8;
+constexpr int IPM_LR_MAX = 16;     // a quadratic block of rank <= 16 is kept as factor rows in the large-model path
 
 struct IpmArgs {
   int B;
@@ -395,6 +404,36 @@ __device__ __forceinline__ void pass_U(const DevModel &M, const double *d, doubl
 __device__ __forceinline__ bool fn_is_linear(const DevModel &M, int k) {
   return M.qidx[k] < 0 && (M.n_terms == 0 || M.fn_term_start[k + 1] == M.fn_term_start[k]);
 }
+__device__ __forceinline__ bool fn_is_lowrank(const DevModel &M, int k, bool large_path) {
+  return large_path && M.n_lr > 0 && M.fn_lr_start[k + 1] > M.fn_lr_start[k];
+}
+// u_k = Q_k d and du[k] = d'Q_k d for the low-rank blocks: s_r = v_r . d (one warp per factor row, kept in lrs), then
+// u_k[j] = sum_r s_r v_r[j]
+__device__ __forceinline__ void pass_U_lowrank(const DevModel &M, const double *d, double *uq, double *du, double *lrs) {
+  const int n = M.n, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = w; r < M.n_lr; r += IPM_NW) {
+    const double *vr = M.lrV + (size_t)r * n;
+    double acc = 0.0;
+    for (int j = lane; j < n; j += 32) acc = fma(vr[j], d[j], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) lrs[r] = acc;
+  }
+  __syncthreads();
+  for (int k = w; k <= M.m; k += IPM_NW) {
+    const int r0 = M.fn_lr_start[k], r1 = M.fn_lr_start[k + 1];
+    if (r1 <= r0) continue;
+    double dd = 0.0;
+    for (int r = r0; r < r1; ++r) dd = fma(lrs[r], lrs[r], dd);
+    for (int j = lane; j < n; j += 32) {
+      double u = 0.0;
+      for (int r = r0; r < r1; ++r) u = fma(lrs[r], M.lrV[(size_t)r * n + j], u);
+      uq[(size_t)k * n + j] = u;
+    }
+    if (lane == 0) du[k] = dd;
+  }
+  __syncthreads();
+}
 __device__ __forceinline__ const double *grow(const DevModel &M, const double *grad, int k) {
   return fn_is_linear(M, k) ? M.A + (size_t)k * M.n : grad + (size_t)k * M.n;
 }
@@ -512,15 +551,18 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
   __shared__ int s_ctr[2];
   // the two right-hand sides / solutions: the augmented rows N, N+1 of the packed H, or (tile-major H) their own vectors
   double *d0 = H + tri(N), *d1 = H + tri(N + 1);
+  double *lrs = nullptr, *sgn16 = nullptr;      // low-rank path: s_r = v_r . d per factor row; signs of a staged chunk
   if (TM) {
     double *dv2 = reinterpret_cast<double *>(qfn + Kp + (Kp & 1));
     d0 = dv2; d1 = dv2 + nb8;
+    sgn16 = d1 + nb8;
+    lrs = sgn16 + IPM_KC;
   }
   __shared__ int s_nqf;
   if (tid == 0) {
     int c = 0;
     for (int k = 0; k <= m; ++k)
-      if (M.qidx[k] >= 0) qfn[c++] = k;
+      if (M.qidx[k] >= 0 && !fn_is_lowrank(M, k, TM)) qfn[c++] = k;
     s_nqf = c;
   }
   for (int k = tid; k <= m; k += IPM_NT) du[k] = 0.0;
@@ -590,6 +632,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
 
     // ------------------------------------------------------------------ full evaluation at x: grad_k = a_k + Q_k x
     pass_U<MAXC>(M, x, uq, du, qfn, nqf);
+    if (TM && M.n_lr > 0) pass_U_lowrank(M, x, uq, du, lrs);
     {
       const int w = tid >> 5, lane = tid & 31;
       for (int k = w; k <= m; k += IPM_NW) {
@@ -895,7 +938,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
       if (tid == 0) {  // compact list of quadratic blocks with a non-zero weight
         int c = 0;
         for (int k = 0; k <= m; ++k)
-          if (M.qidx[k] >= 0 && wq[k] != 0.0) { qblk[c] = M.qidx[k]; qwt[c] = wq[k]; ++c; }
+          if (M.qidx[k] >= 0 && wq[k] != 0.0 && !fn_is_lowrank(M, k, TM)) { qblk[c] = M.qidx[k]; qwt[c] = wq[k]; ++c; }
         s_nqa = c;
         int f = 0;
         for (int j = 0; j < N; ++j)
@@ -1001,6 +1044,27 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
             if (tid == 0) s_ctr[0] = 0;
             __syncthreads();
             tm_syrk_stage<false>(H, TL, (N + 7) >> 3, stage, lds_tm, IPM_KC, s_ctr);
+            __syncthreads();
+          }
+          // low-rank quadratic parts: sum_k w_k sum_r v_r v_r' as staged rows sqrt|w_k| v_r with the sign of w_k
+          for (int r0 = 0; r0 < M.n_lr; r0 += IPM_KC) {
+            const int kc = min(IPM_KC, M.n_lr - r0);
+            for (int c = tid >> 5; c < IPM_KC; c += IPM_NW) {
+              const int r = min(r0 + c, M.n_lr - 1);
+              // owner function of factor row r (fn_lr_start is monotone: a short scan from the previous owner would do; rows
+              // per function are few, so a binary search over m+1 functions is cheap enough)
+              int lo = 0, hi = m + 1;
+              while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (M.fn_lr_start[mid] <= r) lo = mid; else hi = mid; }
+              const double wk = (c < kc) ? wq[lo] : 0.0;
+              const double sw = sqrt(fabs(wk));
+              const double *vr = M.lrV + (size_t)r * n;
+              if ((tid & 31) == 0) sgn16[c] = wk < 0.0 ? -1.0 : 1.0;
+              for (int j = tid & 31; j < lds_tm; j += 32)
+                stage[c * lds_tm + j] = (j < n && !(flg[j] & F_FIXED)) ? sw * vr[j] : 0.0;
+            }
+            if (tid == 0) s_ctr[0] = 0;
+            __syncthreads();
+            tm_syrk_stage<false>(H, TL, (N + 7) >> 3, stage, lds_tm, IPM_KC, s_ctr, sgn16);
             __syncthreads();
           }
           // the carried rows: the two right-hand sides and the equality rows A_e (after the factorisation Y_e = L^-1 A_e')
@@ -1243,6 +1307,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
       PH_MARK(5);
       // ---------------------------------------------------------------- u_k = Q_k dx, du_k = dx.u_k
       pass_U<MAXC>(M, dx, uq, du, qfn, nqf);
+      if (TM && M.n_lr > 0) pass_U_lowrank(M, dx, uq, du, lrs);
 
       PH_MARK(6);
       // ---------------------------------------------------------------- filter line search

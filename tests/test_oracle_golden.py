@@ -149,3 +149,31 @@ def test_oracle_terms_and_equalities_against_scipy(oracle_ipm):
     resp = minimize(lambda x: evp.dense(x)[0][0], p.x0, bounds=list(zip(p.xl, p.xu)), constraints=consp,
                     method="SLSQP", options={"ftol": 1e-12, "maxiter": 300})
     assert abs(resp.fun - rp["obj"][0]) <= 1e-6 * max(1.0, abs(resp.fun))
+
+
+@pytest.mark.parametrize("which", ["c2", "c3"])
+def test_oracle_matches_scipy_fixture(oracle_ipm, which):
+    """200 random children of each BASELINE shape (C2: n = 100, m = 40; C3: n = 200, m = 80) solved by an
+    INDEPENDENT method — scipy's trust-constr with exact derivatives, results committed as tests/golden/scipy_children_*.npz
+    by tests/golden/make_scipy_children.py (minutes of CPU, not run here) — against the oracle on the same children:
+    the same feasible / infeasible verdict for every child, the objective within 1e-6 relative (north_star's tolerance)
+    wherever trust-constr itself converged, and never worse than its last iterate where it ran out of iterations."""
+    import os
+    path = os.path.join(os.path.dirname(__file__), "golden", f"scipy_children_{which}.npz")
+    if not os.path.exists(path):
+        pytest.skip(f"{path} has not been generated")
+    d = np.load(path)
+    m = I.config_c2() if which == "c2" else I.config_c3()
+    assert str(d["model"]) == m.name
+    B = int(d["children"])
+    XL, XU = I.c3_children(m, d["x_start"], B)
+    o = oracle_ipm.solve_batch(m, XL, XU, d["x_start"], threads=8, dense=oracle_ipm.dense_arrays(m))
+    feasible = (d["viol"] < 1e-6) & (d["status"] != -1)            # -1: crossed bounds, no solver was asked
+    assert set(np.unique(o["status"])) <= {1, 3}
+    assert np.array_equal(o["status"] == 1, feasible)
+    assert feasible.sum() >= B // 2 and (~feasible).sum() >= 5
+    rel = (o["obj"] - d["fun"]) / np.maximum(1.0, np.abs(d["fun"]))
+    conv = feasible & (d["status"] > 0)
+    assert conv.sum() >= 20 and np.abs(rel[conv]).max() <= 1e-6
+    unfinished = feasible & (d["status"] == 0)                      # maxiter: a feasible upper bound, a little above the optimum
+    assert rel[unfinished].max(initial=-1.0) <= 1e-6 and rel[unfinished].min(initial=0.0) >= -1e-4
