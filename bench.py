@@ -238,6 +238,45 @@ def sweep_section(eng, model, xs, dev, stream):
     return out
 
 
+def large_models_section(dev, stream, peak):
+    """BASELINE configs 4 and 5 at full size on the large-model path (H in global memory, tile-major, DMMA): child / NLP(y)
+    relaxations per second, device-resident, with the FP64 roofline from the same SURVEY.md §8d formula (dense counts: the
+    algorithmic FLOPs are a property of the problem, the sparse / low-rank short cuts the engine takes are not credited)."""
+    import torch
+    from bonmin_b200.engine import Engine, Problem
+    out = []
+    for name, mk, B, (mq, ml) in (("C5 SYN-PORTFOLIO(N=200): n=400, m=203 (1 quadratic row, 1 equality)", I.config_c5, 592, (1, 202)),
+                                  ("C4 SYN-CVX-MINLP(n=500, m=200: 100 quadratic+exp rows)", I.config_c4, 296, (100, 100))):
+        m = mk()
+        eng = Engine(Problem.from_model(m), devices=[dev.index or 0])
+        root = eng.solve_batch(m.xl, m.xu, m.x0)
+        xs = root["x"][0]
+        XL, XU = make_children(m, xs, B, 0)
+        d = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (XL, XU, xs)]
+        O = torch.zeros(B, dtype=torch.float64, device=dev); S = torch.zeros(B, dtype=torch.int32, device=dev)
+        It = torch.zeros(B, dtype=torch.int32, device=dev); X = torch.zeros(B, m.n, dtype=torch.float64, device=dev)
+        for _ in range(2):
+            eng.solve_batch_device(d[0], d[1], d[2], O, S, It, X, None, None, stream=stream.cuda_stream)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(3):
+            eng.solve_batch_device(d[0], d[1], d[2], O, S, It, X, None, None, stream=stream.cuda_stream)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        its = int(It.sum().item())
+        fl = f_iter(m.n, mq, ml) * its
+        ach = fl / (ms * 1e-3) / 1e12
+        out.append({"workload": name, "children": B, "ms": ms, "relaxations_per_s": B / (ms * 1e-3), "mean_iterations": its / B,
+                    "optimal": int((S == 1).sum().item()), "infeasible": int((S == 3).sum().item()),
+                    "roofline": {"bound": "fp64", "kernel": "ipm_kernel (tile-major large path)", "achieved": ach, "peak": peak,
+                                 "unit": "TFLOP/s", "frac": ach / peak if peak > 0 else None,
+                                 "flops_per_iteration": f_iter(m.n, mq, ml)}})
+        eng.close()
+    return out
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU path for this workload.  The real Bonmin/Ipopt cannot be built or
     installed offline (no Ipopt/ASL/Osi/Cbc), so this times the CPU oracle restatement — all host
@@ -509,6 +548,7 @@ def main():
                                               "CPU restatement of the Bonmin/Ipopt path — NOT Ipopt (Ipopt 3.13 cannot be built offline)"}
         if world == 1 and not args.no_sweep:
             line["sweep"] = sweep_section(eng, model, xs, dev, stream)
+            line["large_models"] = large_models_section(dev, stream, peak)
         if world == 1 and not args.no_bb:
             line["bb"] = bb_section(args, local_rank)
         if world == 1 and not args.no_oa:

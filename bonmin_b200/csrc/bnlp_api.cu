@@ -121,6 +121,7 @@ struct bnlp_engine {
   bool ipm_supported = true;
   std::string ipm_unsupported_why;
   int h_in_smem = 1;
+  int tm_kc = 16;
   size_t smem_bytes = 0;
   bool coop_ok = false;
   bool coop256 = false;   // small model: 256-thread CTAs, two per SM
@@ -223,17 +224,17 @@ extern "C" int bnlp_problem_info(const bnlp_problem *p, int *jac_irow, int *jac_
   return 0;
 }
 
-static size_t ipm_smem_doubles(int n, int m, int R, int E, int h_in_smem, int n_lr = 0) {
+static size_t ipm_smem_doubles(int n, int m, int R, int E, int h_in_smem, int n_lr = 0, int tm_kc = IPM_KC) {
   const int N = n + 1;
   const int npad = (N + 2 + 3) & ~3;
   size_t d = 5 * IPM_MAXE + IPM_MAXE * IPM_MAXE;
   if (h_in_smem) d += (size_t)(((N + 2 + E) * (N + 3 + E) / 2) + 1) & ~(size_t)1;
-  d += (size_t)(IPM_KC + 1) * npad;
+  d += std::max((size_t)(IPM_KC + 1) * npad, h_in_smem ? (size_t)0 : (size_t)tm_kc * ((((size_t)N + 7) & ~(size_t)7) + 4));
   d += (size_t)7 * npad;
   const int Rp = (R + 1) & ~1, Kp = (m + 2) & ~1;
   d += (size_t)10 * Rp + (size_t)8 * Kp + (size_t)IPM_NW * 12;
   d += (size_t)(((N + 1) & ~1) * 2 + 2 * Kp) / 2 + 2;   // flg, fixlist, qblk, qfn (ints)
-  if (!h_in_smem) d += 2 * (size_t)((N + 7) & ~7) + 2 + IPM_KC + (size_t)n_lr;  // tile-major H in global memory: the two right-hand sides live here (+ chunk signs, low-rank products)
+  if (!h_in_smem) d += 2 * (size_t)((N + 7) & ~7) + 2 + 32 + (size_t)n_lr;  // tile-major H in global memory: the two right-hand sides live here (+ chunk signs, low-rank products)
   return d;
 }
 
@@ -490,7 +491,9 @@ extern "C" bnlp_engine *bnlp_engine_create(const bnlp_problem *prob, const int *
     if (d == 0) {
       const size_t need = ipm_smem_doubles(n, m, E->R, E->E, 1) * sizeof(double);
       E->h_in_smem = need + 1024 <= D.smem_optin ? 1 : 0;
-      E->smem_bytes = ipm_smem_doubles(n, m, E->R, E->E, E->h_in_smem, V.n_lr) * sizeof(double);
+      E->tm_kc = IPM_KC;
+      if (!E->h_in_smem && ipm_smem_doubles(n, m, E->R, E->E, 0, V.n_lr, 32) * sizeof(double) + 1024 <= D.smem_optin && !getenv("BNLP_TM_KC16")) E->tm_kc = 32;
+      E->smem_bytes = ipm_smem_doubles(n, m, E->R, E->E, E->h_in_smem, V.n_lr, E->tm_kc) * sizeof(double);
       if (E->smem_bytes + 1024 > D.smem_optin) { E->ipm_supported = false; E->ipm_unsupported_why = "iterate vectors do not fit shared memory"; }
       E->ws_doubles = (size_t)2 * (m + 1) * n + (size_t)M.terms.size() * (2 + TV + TH) + (E->h_in_smem ? 0 : (size_t)tm_size(tm_layout(n + 3 + E->E)) + 2);   // tile-major H (bnlp_dense_tm.cuh)
       E->ws_doubles = (E->ws_doubles + 1) & ~(size_t)1;
@@ -614,7 +617,7 @@ static int launch_ipm(bnlp_engine *E, Device &D, int B, const double *dXL, const
   a.B = B; a.XL = dXL; a.XU = dXU; a.X0 = dX0; a.x0_stride = x0_per_child ? E->M.n : 0;
   a.DUAL0 = dDUAL0; a.dual0_stride = dual0_per_child ? 2 * E->M.n + E->M.m : 0;
   a.OBJ = dOBJ; a.STATUS = dST; a.ITERS = dIT; a.X = dX; a.G = dG; a.DUALS = dD;
-  a.queue = D.queue.p; a.ws = E->coop_ok ? D.xch.p : D.ws.p; a.ws_stride = E->ws_doubles; a.h_in_smem = E->h_in_smem; a.stats = D.stats.p;
+  a.queue = D.queue.p; a.ws = E->coop_ok ? D.xch.p : D.ws.p; a.ws_stride = E->ws_doubles; a.h_in_smem = E->h_in_smem; a.tm_kc = E->tm_kc; a.stats = D.stats.p;
   a.phase_cycles = getenv("BNLP_PHASE_TIMERS") ? D.stats.p + 2 : nullptr;
   a.o = IpmOpt();
   a.o.tol = E->opt.tol; a.o.max_iter = E->opt.max_iter;

@@ -625,6 +625,9 @@ __device__ __forceinline__ void bs_update(const double *H, const TmLayout &L, in
 // ---- backward substitution L' x = w for the two right-hand sides carried in rows N and N + 1 (after chol_tm they hold
 // L^-1 rhs).  The rows are copied to the contiguous vectors b0 / b1 (shared memory, >= 8 * ceil(N / 8) doubles each),
 // which hold the solutions on exit.  One warp per right-hand side, no CTA barrier inside the block loop.
+// GLOBAL_H: H lives in global memory — the tile rows the next two blocks will read are prefetched into L2 (a block's chain
+// otherwise starts with a DRAM-latency load when the per-CTA blocks of a large model do not fit L2).
+template <bool GLOBAL_H = false>
 __device__ __forceinline__ void backsolve_tm(const double *H, const TmLayout &L, int N, double *b0, double *b1) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int ntN = (N + 7) >> 3;
@@ -644,6 +647,11 @@ __device__ __forceinline__ void backsolve_tm(const double *H, const TmLayout &L,
     for (int bi = ntN - 1; bi >= 0; --bi) {
       const int i0 = bi << 3, nb = min(8, N - i0);
       const double *X = H + tm_tile(L, bi, bi);
+      if (GLOBAL_H && w == 0 && bi >= 2) {
+        const char *row = reinterpret_cast<const char *>(H + tm_tile(L, bi - 2, 0));
+        const int bytes = ((bi - 1) * 64 + bi * 64) * 8;       // tile rows bi-2 and bi-1 are contiguous
+        for (int off = lane * 128; off < bytes; off += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + off));
+      }
       // b[i0 .. i0 + 7] is current in shared memory (initially, then written back by the previous block's update)
       double xc = 0.0;
       if (lane < nb) {

@@ -108,6 +108,7 @@ struct IpmArgs {
   int *queue;                   // work-queue counter (zeroed by the host)
   double *ws; size_t ws_stride; // per-CTA global workspace (doubles)
   int h_in_smem;
+  int tm_kc;                    // tile-major path: staged rows per rank-K update of H (16 or 32: the host picks what shared memory allows)
   long long *stats;             // [0] total iterations, [1] factorisations (optional)
   long long *phase_cycles;      // 10 counters or null
   IpmOpt o;
@@ -509,7 +510,8 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
   const TmLayout TL = tm_layout(N + 2 + E);
   const int nb8 = (N + 7) & ~7, lds_tm = nb8 + 4;
   if (A.h_in_smem) { H = sp; sp += (Haug + 1) & ~1; } else { H = tgl + (((size_t)NTm * TREC + 1) & ~(size_t)1); }   // 16-byte aligned tiles
-  double *stage = sp; sp += (IPM_KC + 1) * npad;
+  const int KT = TM ? A.tm_kc : IPM_KC;       // rows per staged update (tile-major path: 32 halves the read-modify-writes of H)
+  double *stage = sp; sp += max((IPM_KC + 1) * npad, TM ? KT * lds_tm : 0);
   double *x = sp; sp += npad;
   double *zL = sp; sp += npad;
   double *zU = sp; sp += npad;
@@ -556,7 +558,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
     double *dv2 = reinterpret_cast<double *>(qfn + Kp + (Kp & 1));
     d0 = dv2; d1 = dv2 + nb8;
     sgn16 = d1 + nb8;
-    lrs = sgn16 + IPM_KC;
+    lrs = sgn16 + 32;
   }
   __shared__ int s_nqf;
   if (tid == 0) {
@@ -1028,10 +1030,10 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
         PH_MARK(1);
         // J' Sigma_s J through staged rank-KC updates: stage[c][j] = sqrt(Ss_r) J[r][j]
         if (TM) {
-          // rank-16 DMMA updates of the tile-major H from staged rows (row stride lds_tm = 4 mod 8: conflict-free fragments)
-          for (int r0 = 0; r0 < M.Rd; r0 += IPM_KC) {
-            const int kc = min(IPM_KC, M.Rd - r0);
-            for (int c = tid >> 5; c < IPM_KC; c += IPM_NW) {
+          // rank-KT DMMA updates of the tile-major H from staged rows (row stride lds_tm = 4 mod 8: conflict-free fragments)
+          for (int r0 = 0; r0 < M.Rd; r0 += KT) {
+            const int kc = min(KT, M.Rd - r0);
+            for (int c = tid >> 5; c < KT; c += IPM_NW) {
               const int r = M.dense_rows[min(r0 + c, M.Rd - 1)];
               const double sq = (c < kc) ? sqrt(Ss[r]) : 0.0, f = sq * fsc[r];
               const double *g = grow(M, grad, M.row_fn[r]);
@@ -1043,13 +1045,13 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
             }
             if (tid == 0) s_ctr[0] = 0;
             __syncthreads();
-            tm_syrk_stage<false>(H, TL, (N + 7) >> 3, stage, lds_tm, IPM_KC, s_ctr);
+            tm_syrk_stage<false>(H, TL, (N + 7) >> 3, stage, lds_tm, KT, s_ctr);
             __syncthreads();
           }
           // low-rank quadratic parts: sum_k w_k sum_r v_r v_r' as staged rows sqrt|w_k| v_r with the sign of w_k
-          for (int r0 = 0; r0 < M.n_lr; r0 += IPM_KC) {
-            const int kc = min(IPM_KC, M.n_lr - r0);
-            for (int c = tid >> 5; c < IPM_KC; c += IPM_NW) {
+          for (int r0 = 0; r0 < M.n_lr; r0 += KT) {
+            const int kc = min(KT, M.n_lr - r0);
+            for (int c = tid >> 5; c < KT; c += IPM_NW) {
               const int r = min(r0 + c, M.n_lr - 1);
               // owner function of factor row r (fn_lr_start is monotone: a short scan from the previous owner would do; rows
               // per function are few, so a binary search over m+1 functions is cheap enough)
@@ -1064,7 +1066,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
             }
             if (tid == 0) s_ctr[0] = 0;
             __syncthreads();
-            tm_syrk_stage<false>(H, TL, (N + 7) >> 3, stage, lds_tm, IPM_KC, s_ctr, sgn16);
+            tm_syrk_stage<false>(H, TL, (N + 7) >> 3, stage, lds_tm, KT, s_ctr, sgn16);
             __syncthreads();
           }
           // the carried rows: the two right-hand sides and the equality rows A_e (after the factorisation Y_e = L^-1 A_e')
@@ -1202,7 +1204,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
         }
         __syncthreads();
       }
-      if (TM) backsolve_tm(H, TL, N, d0, d1);   // rows N, N+1 of H -> d0, d1 = H^-1 rhs0, H^-1 rhs1
+      if (TM) backsolve_tm<true>(H, TL, N, d0, d1);   // rows N, N+1 of H -> d0, d1 = H^-1 rhs0, H^-1 rhs1
       else backsolve2(H, N);   // d0 = H^-1 rhs0, d1 = H^-1 rhs1
       PH_MARK(4);
 
