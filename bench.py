@@ -477,6 +477,48 @@ def main():
     dev_ms_max, e2e_ms_max, exchange_us_max = t_ms.tolist()
     iters_all, n_opt, n_inf = tot.tolist()
 
+    # ---------------- the same step through the ENGINE's own multi-rank call (N > 1): every rank hands the whole B x N batch
+    # to bnlp_solve_batch_sharded (host buffers), solves its block and receives every child's {objective, status, iterations}
+    # through ncclAllGather issued by libbnlp; then the incumbent bound through ncclAllReduce(min) (bnlp_comm_allreduce_min)
+    sharded = None
+    if world > 1:
+        from bonmin_b200.engine import Comm
+        comm = Comm.from_torch(eng, dev)
+        XLa, XUa = make_children(model, xs, B * world, first=0)
+        comm.solve_batch(XLa, XUa, xs, want_x=False)
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            rs = comm.solve_batch(XLa, XUa, xs, want_x=False)
+            inc = comm.allreduce_min(float(np.where(rs["status"] == 1, rs["obj"], np.inf).min()))
+        torch.cuda.synchronize()
+        ts = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        mine_ok = bool(np.array_equal(rs["status"][rank * B:(rank + 1) * B], status) and np.array_equal(rs["obj"][rank * B:(rank + 1) * B], obj_dev))
+        agree = torch.tensor([1.0 if mine_ok else 0.0], device=dev)
+        dist.all_reduce(agree, op=dist.ReduceOp.MIN)
+        sharded = {"value": B * world * args.steps / float(ts.item()), "unit": "relaxations/s", "children_per_step": B * world,
+                   "exchange_us_per_step": comm.stats()["exchange_ms"] * 1e3, "nccl_collectives": comm.stats()["collectives"],
+                   "incumbent": inc, "every_rank_sees_its_own_block_bit_for_bit": bool(agree.item() == 1.0),
+                   "what": "bnlp_solve_batch_sharded + bnlp_comm_allreduce_min (NCCL inside libbnlp), host buffers, no primal points"}
+        # config 2's tree search with the children of every round sharded over the ranks (bnlp_bb_run_engine_sharded)
+        from bonmin_b200 import bb
+        from bonmin_b200.engine import Engine, Problem
+        m2 = I.config_c2()
+        e2 = Engine(Problem.from_model(m2), devices=[local_rank])
+        c2 = Comm.from_torch(e2, dev)
+        kw = dict(number_strong_branch=32, number_before_trust=1000000, node_limit=5000000, time_limit=60.0, parallel_nodes=128)
+        bb.run_engine_sharded(c2, **dict(kw, node_limit=200))
+        dist.barrier()
+        g = bb.run_engine_sharded(c2, **kw)
+        tb = torch.tensor([g["seconds"]], dtype=torch.float64, device=dev)
+        dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+        sharded["c2_bb_sharded"] = {"instance": m2.name + ", B-BB, 32 candidates/node, 128 nodes per round, children sharded over the ranks",
+                                    "wall_s": float(tb.item()), "status": g["status"], "optimum": g["best_obj"], "nodes": g["nodes"],
+                                    "child_nlps": g["sb_children"], "nccl_collectives": c2.stats()["collectives"]}
+        c2.close(); e2.close(); comm.close()
+
     # ---------------- strong-scaling companion (N > 1): ONE 4096-child batch split over the ranks (a single B-BB round)
     strong = None
     if world > 1:
@@ -534,6 +576,8 @@ def main():
         }
         if strong:
             line["strong_scaling_4096"] = strong
+        if sharded:
+            line["e2e_engine_sharded"] = sharded
         if world == 1 and not args.no_cpu_baseline:
             from oracle import ipm
             cores = cpu_cores()

@@ -75,6 +75,22 @@ def run_engine(eng: "_e.Engine", **kw):
     return d
 
 
+def run_engine_sharded(comm: "_e.Comm", **kw):
+    """bnlp_bb_run_engine_sharded: the same search on every rank, every batch of children split over the ranks (NCCL)."""
+    eng = comm.engine
+    res = BbResult()
+    x = np.zeros(eng.n)
+    L = _e.lib()
+    L.bnlp_bb_run_engine_sharded.argtypes = [c_void, c_void, ctypes.POINTER(BbOptions), ctypes.POINTER(BbResult), c_void]
+    o = _opts(**kw)
+    rc = L.bnlp_bb_run_engine_sharded(comm.h, eng.problem.h, ctypes.byref(o), ctypes.byref(res), x.ctypes.data_as(c_void))
+    if rc:
+        raise _e.BnlpError("bnlp_bb_run_engine_sharded failed: " + L.bnlp_last_error().decode())
+    d = res.as_dict()
+    d["best_x"] = x
+    return d
+
+
 def run_callback(model, solve_batch, tqp_solve=None, **kw):
     """solve_batch(XL, XU, x0) -> dict(obj, status, iters, x) with the meaning of Engine.solve_batch.
     tqp_solve(x_sol, duals_sol, XL, XU) -> dict(obj, status, iters, x) with the meaning of Engine.tqp_solve_batch

@@ -17,13 +17,13 @@ SOURCES = ["bnlp_launch_ipm.cu", "bnlp_launch_coop.cu", "bnlp_launch_coop256.cu"
            "../host/B200Solver.cpp", "../host/host_cabi.cpp", "../host/node_files.cpp", "../host/B200Linearizer.cpp"]
 HOST_LIB = os.path.join(HERE, "libbnlp_host.so")
 HEADERS = ["../host/B200Solver.hpp", "../host/B200Linearizer.hpp", "../host/bonmin_shim.hpp", "bnlp_internal.h", "bnlp_ipm.cuh", "bnlp_ipm_coop.cuh",
-           "bnlp_dense.cuh", "bnlp_eval.cuh", "bnlp_api_eval.inc", "../../include/bnlp.h"]
+           "bnlp_dense.cuh", "bnlp_dense_tm.cuh", "bnlp_eval.cuh", "bnlp_api_eval.inc", "bnlp_api_comm.inc", "../../include/bnlp.h"]
 # headers each source depends on (None = all)
 DEPS = {
-    "bnlp_launch_ipm.cu": ["bnlp_internal.h", "bnlp_ipm.cuh", "bnlp_eval.cuh", "../../include/bnlp.h"],
-    "bnlp_launch_coop.cu": ["bnlp_internal.h", "bnlp_ipm.cuh", "bnlp_ipm_coop.cuh", "bnlp_dense.cuh", "bnlp_eval.cuh",
+    "bnlp_launch_ipm.cu": ["bnlp_internal.h", "bnlp_ipm.cuh", "bnlp_dense_tm.cuh", "bnlp_eval.cuh", "../../include/bnlp.h"],
+    "bnlp_launch_coop.cu": ["bnlp_internal.h", "bnlp_ipm.cuh", "bnlp_ipm_coop.cuh", "bnlp_dense.cuh", "bnlp_dense_tm.cuh", "bnlp_eval.cuh",
                             "../../include/bnlp.h"],
-    "bnlp_launch_coop256.cu": ["bnlp_internal.h", "bnlp_ipm.cuh", "bnlp_ipm_coop.cuh", "bnlp_dense.cuh", "bnlp_eval.cuh",
+    "bnlp_launch_coop256.cu": ["bnlp_internal.h", "bnlp_ipm.cuh", "bnlp_ipm_coop.cuh", "bnlp_dense.cuh", "bnlp_dense_tm.cuh", "bnlp_eval.cuh",
                                "../../include/bnlp.h"],
 }
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
@@ -68,7 +68,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if bad:
         raise RuntimeError(f"nvcc failed for {bad}")
     subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] +
-                          [_obj_of(s) for s in SOURCES])
+                          [_obj_of(s) for s in SOURCES] + ["-ldl"])
     build_host()
     return LIB
 

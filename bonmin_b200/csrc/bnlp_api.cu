@@ -893,3 +893,4 @@ extern "C" double bnlp_measure_fp64_peak(bnlp_engine *E, int dev_index) {
 }
 
 #include "bnlp_api_eval.inc"
+#include "bnlp_api_comm.inc"

@@ -59,7 +59,9 @@ EXPORTS = ["bnlp_last_error", "bnlp_problem_from_nl", "bnlp_problem_from_tape", 
            "bnlp_resolve_cb", "bnlp_resolve_engine", "bnlp_problem_fp", "bnlp_solve_children", "bnlp_bb_run_cb3",
            "bnlp_write_node_files", "bnlp_read_bounds_file", "bnlp_read_start_file", "bnlp_write_batch_replay",
            "bnlp_read_batch_replay_header", "bnlp_read_batch_replay", "bnlp_sol_status", "bnlp_nl_header_options",
-           "bnlp_write_sol", "bnlp_write_plain_sol", "bnlp_problem_cut_strengthening", "bnlp_problem_branching_info", "bnlp_host_register", "bnlp_host_unregister", "bnlp_host_selftest", "bnlp_linearizer_engine"]
+           "bnlp_write_sol", "bnlp_write_plain_sol", "bnlp_problem_cut_strengthening", "bnlp_problem_branching_info", "bnlp_host_register", "bnlp_host_unregister", "bnlp_host_selftest", "bnlp_linearizer_engine",
+           "bnlp_comm_unique_id", "bnlp_comm_create", "bnlp_comm_free", "bnlp_comm_stats", "bnlp_comm_allreduce_min",
+           "bnlp_solve_batch_sharded", "bnlp_bb_run_engine_sharded"]
 
 
 def pin_array(a):
@@ -539,3 +541,70 @@ class Engine:
             self.close()
         except Exception:
             pass
+
+
+class Comm:
+    """Multi-rank exchange of the engine (`bnlp_comm`, NCCL inside libbnlp): one process per GPU.  `broadcast_id(buf)` must
+    hand rank 0's 128-byte id to every rank (e.g. torch.distributed.broadcast of a uint8 tensor); `Comm.from_torch` does that."""
+
+    def __init__(self, engine: "Engine", rank: int, world: int, uid: bytes):
+        L = lib()
+        L.bnlp_comm_create.restype = c_void
+        L.bnlp_comm_create.argtypes = [c_void, c_int, c_int, ctypes.c_char_p]
+        self.engine, self.rank, self.world = engine, rank, world
+        self.h = L.bnlp_comm_create(engine.h, rank, world, uid)
+        if not self.h:
+            raise BnlpError(L.bnlp_last_error().decode())
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = ctypes.create_string_buffer(128)
+        if lib().bnlp_comm_unique_id(buf):
+            raise BnlpError(lib().bnlp_last_error().decode())
+        return buf.raw
+
+    @classmethod
+    def from_torch(cls, engine, device):
+        """The id travels through the existing torch.distributed process group (NCCL or gloo)."""
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(), dist.get_world_size()
+        t = torch.zeros(128, dtype=torch.uint8, device=device if dist.get_backend() == "nccl" else "cpu")
+        if rank == 0:
+            t.copy_(torch.frombuffer(bytearray(cls.unique_id()), dtype=torch.uint8))
+        dist.broadcast(t, 0)
+        return cls(engine, rank, world, bytes(t.cpu().numpy().tobytes()))
+
+    def solve_batch(self, XL, XU, X0, want_x=True):
+        """B children, the same arrays on every rank; rank r solves its block and every rank gets every result."""
+        e = self.engine
+        XL = _d(np.atleast_2d(XL)); XU = _d(np.atleast_2d(XU)); X0 = _d(X0)
+        B = XL.shape[0]
+        OBJ = np.zeros(B); ST = np.zeros(B, np.int32); IT = np.zeros(B, np.int32)
+        X = np.zeros((B, e.n)) if want_x else None
+        L = lib()
+        L.bnlp_solve_batch_sharded.argtypes = [c_void, c_int, c_void, c_void, c_void, c_int] + [c_void] * 4
+        if L.bnlp_solve_batch_sharded(self.h, B, _vp(XL), _vp(XU), _vp(X0), int(X0.ndim == 2), _vp(OBJ), _vp(ST), _vp(IT), _vp(X)):
+            raise BnlpError(L.bnlp_last_error().decode())
+        return dict(obj=OBJ, status=ST, iters=IT, x=X)
+
+    def allreduce_min(self, value: float) -> float:
+        v = ctypes.c_double(value)
+        L = lib()
+        L.bnlp_comm_allreduce_min.argtypes = [c_void, ctypes.POINTER(ctypes.c_double)]
+        if L.bnlp_comm_allreduce_min(self.h, ctypes.byref(v)):
+            raise BnlpError(L.bnlp_last_error().decode())
+        return v.value
+
+    def stats(self):
+        n = ctypes.c_longlong(); ms = ctypes.c_double()
+        L = lib()
+        L.bnlp_comm_stats.argtypes = [c_void, ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_double)]
+        L.bnlp_comm_stats(self.h, ctypes.byref(n), ctypes.byref(ms))
+        return dict(collectives=n.value, exchange_ms=ms.value)
+
+    def close(self):
+        if self.h:
+            lib().bnlp_comm_free.argtypes = [c_void]
+            lib().bnlp_comm_free(self.h)
+            self.h = None

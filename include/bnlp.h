@@ -327,6 +327,27 @@ int bnlp_bb_run_cb3(int n, int m, const int *var_type, const double *xl, const d
 int bnlp_bb_run_engine(bnlp_engine *, const bnlp_problem *, const bnlp_bb_options *o, bnlp_bb_result *res,
                        double *best_x);
 
+/* --- Multi-rank exchange inside the engine (one process per GPU) --------------------------------------
+ * The children of a batch are independent: ranks solve contiguous blocks of the child index space and the only
+ * communication is an ncclAllGather of per-child {objective, status, iterations} (+ primal point) and an ncclAllReduce(min)
+ * of the incumbent bound (what BM_lp_branch.cpp:445-535,746-811 does by message passing in the reference's experimental
+ * BCP code).  NCCL is bound at run time (dlopen libnccl.so.2).
+ *   bnlp_comm_unique_id        rank 0: 128 bytes to hand to every rank (the host broadcasts them, e.g. torch.distributed)
+ *   bnlp_comm_create           collective over the ranks (ncclCommInitRank); the engine must own exactly one device
+ *   bnlp_solve_batch_sharded   SAME input arrays on every rank; every rank receives all B results
+ *   bnlp_comm_allreduce_min    incumbent bound
+ *   bnlp_bb_run_engine_sharded bnlp_bb_run_engine with every batch of children sharded: all ranks run the same search on
+ *                              identical results and return the same optimum (checked with the all-reduce) */
+typedef struct bnlp_comm bnlp_comm;
+int bnlp_comm_unique_id(unsigned char *id128);
+bnlp_comm *bnlp_comm_create(bnlp_engine *, int rank, int world, const unsigned char *id128);
+void bnlp_comm_free(bnlp_comm *);
+int bnlp_comm_stats(const bnlp_comm *, long long *collectives, double *exchange_ms);
+int bnlp_comm_allreduce_min(bnlp_comm *, double *value);
+int bnlp_solve_batch_sharded(bnlp_comm *, int B, const double *XL, const double *XU, const double *X0, int x0_per_child,
+                             double *OBJ, int *STATUS, int *ITERS, double *X);
+int bnlp_bb_run_engine_sharded(bnlp_comm *, const bnlp_problem *, const bnlp_bb_options *o, bnlp_bb_result *res, double *best_x);
+
 /* --- NLP diving heuristics (host control flow; the NLPs of a step are one batch) --------------------------------
  * Restates HeuristicDive::solution (src/CbcBonmin/Heuristics/BonHeuristicDive.cpp:67-302) with the selection rules of
  * HeuristicDiveFractional (BonHeuristicDiveFractional.cpp:55-108, rule 0) and HeuristicDiveVectorLength
