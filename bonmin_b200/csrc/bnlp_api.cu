@@ -82,6 +82,11 @@ struct Device {
   size_t smem_optin = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // outer-approximation pipeline: copy stream, per-buffer-set events, double-buffered cut buffers
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t oa_comp[2] = {nullptr, nullptr}, oa_copy[2] = {nullptr, nullptr}, oa_k0[2] = {nullptr, nullptr};
+  DBuf<double> oaVal[2], oaLB[2], oaUB[2];
+  DBuf<int> oaCI[2], oaSR[2], oaRS[2];
   // model
   DBuf<double> c, A, Qp, Qf, row_sgn, row_bnd, gl, gu, xl, xu;
   DBuf<int> qidx, row_fn, fn_row_up, fn_row_lo, eq_fn, fn_eq, dense_rows, sp_seg_start, sp_seg_i, sp_seg_k, sp_ent_row;
@@ -577,6 +582,9 @@ extern "C" void bnlp_engine_free(bnlp_engine *E) {
                     &D.oSR, &D.dCP, &D.dCC, &D.dCW, &D.dense_rows, &D.sp_seg_start, &D.sp_seg_i, &D.sp_seg_k, &D.sp_ent_row})
       b->release();
     D.stats.release();
+    for (int p = 0; p < 2; ++p) { D.oaVal[p].release(); D.oaLB[p].release(); D.oaUB[p].release(); D.oaCI[p].release(); D.oaSR[p].release(); D.oaRS[p].release();
+      if (D.oa_comp[p]) cudaEventDestroy(D.oa_comp[p]); if (D.oa_copy[p]) cudaEventDestroy(D.oa_copy[p]); if (D.oa_k0[p]) cudaEventDestroy(D.oa_k0[p]); }
+    if (D.stream2) cudaStreamDestroy(D.stream2);
     D.sp_ent_p.release(); D.lrV.release(); D.fn_lr_start.release();
     if (D.stream) cudaStreamDestroy(D.stream);
     if (D.ev0) cudaEventDestroy(D.ev0);

@@ -44,6 +44,9 @@ def run(B=1024, reps=5, cpu_points=8, model=None):
         for b in range(cpu_points):
             SE.outer_approximation(ev, X[b], None, m.xl, m.xu, get_obj=1)
         out["cpu_oracle_points_per_s"] = cpu_points / (time.perf_counter() - t0)
+        out["cpu_oracle_note"] = ("single-threaded numpy restatement (oracle/struct_eval.py), the parity checker — NOT a tuned CPU "
+                                  "baseline and not to be quoted as one")
+    out["pipeline"] = "chunks of ~48 MB of cuts; kernels of chunk k+1 overlap the device-to-host copy of chunk k (two streams)"
     eng.close()
     return out
 
