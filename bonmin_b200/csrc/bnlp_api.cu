@@ -626,6 +626,7 @@ static int launch_ipm(bnlp_engine *E, Device &D, int B, const double *dXL, const
   a.DUAL0 = dDUAL0; a.dual0_stride = dual0_per_child ? 2 * E->M.n + E->M.m : 0;
   a.OBJ = dOBJ; a.STATUS = dST; a.ITERS = dIT; a.X = dX; a.G = dG; a.DUALS = dD;
   a.queue = D.queue.p; a.ws = E->coop_ok ? D.xch.p : D.ws.p; a.ws_stride = E->ws_doubles; a.h_in_smem = E->h_in_smem; a.tm_kc = E->tm_kc; a.stats = D.stats.p;
+  { static const int tma = getenv("BNLP_COOP_TMA") ? atoi(getenv("BNLP_COOP_TMA")) : 0; a.coop_tma = tma; }
   a.phase_cycles = getenv("BNLP_PHASE_TIMERS") ? D.stats.p + 2 : nullptr;
   a.o = IpmOpt();
   a.o.tol = E->opt.tol; a.o.max_iter = E->opt.max_iter;

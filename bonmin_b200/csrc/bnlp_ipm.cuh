@@ -108,6 +108,7 @@ struct IpmArgs {
   int *queue;                   // work-queue counter (zeroed by the host)
   double *ws; size_t ws_stride; // per-CTA global workspace (doubles)
   int h_in_smem;
+  int coop_tma;                 // cooperative kernel: stage the Jacobian rows with bulk copies (TMA); measured slower, off by default
   int tm_kc;                    // tile-major path: staged rows per rank-K update of H (16 or 32: the host picks what shared memory allows)
   long long *stats;             // [0] total iterations, [1] factorisations (optional)
   long long *phase_cycles;      // 10 counters or null

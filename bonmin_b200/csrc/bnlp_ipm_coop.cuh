@@ -250,6 +250,33 @@ __device__ __forceinline__ void backsolve_inv(double *H, int N, double *xs /* 16
   }
 }
 
+// ---- bulk asynchronous copies (TMA, cp.async.bulk) global -> shared memory, completion on an mbarrier
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// orders earlier generic-proxy accesses (ordinary loads / stores) before later async-proxy ones (bulk copies)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
 struct CoopBufs {
   double *xw;       // G x nqpad : Hessian weights published by every CTA
   double *Wbuf;     // G x P     : W_b produced by the cooperative W pass
@@ -313,6 +340,19 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
 #define qblk (flg + 2 * ((N + 1) & ~1))
 #define qfn (flg + 2 * ((N + 1) & ~1) + Kp)
   __shared__ int s_child, s_nfix, s_fail, s_nqf;
+  // The scaled Jacobian rows of a J' Sigma J chunk are staged by BULK COPIES (TMA): thread 0 issues one cp.async.bulk per
+  // raw gradient row (n doubles from this CTA's workspace in L2 into the staging area), every warp then scales its row in
+  // place.  The copies of the first chunk are issued at the very top of the iteration and land under the residual loops; the
+  // register path (eight loads in flight per lane) cost 4.3 k cycles per chunk, all of it exposed.  Needs 16-byte aligned
+  // rows: even n (otherwise the register path below is used).
+  __shared__ __align__(8) unsigned long long s_mbar;
+  // MEASURED (round 2, C3, 4096 children): 41.8 k relaxations/s with the bulk copies against 43.0 k with the register path —
+  // staging itself drops from 7.8 M to 5.8 M cycles per launch and CTA, but issuing sixteen copies per chunk from one
+  // thread after the SYRK barrier, the extra in-place pass and the proxy fences behind the gradient updates cost more than
+  // that.  The path is therefore OFF unless BNLP_COOP_TMA=1 (IpmArgs::coop_tma); profiles/r2_coop_tma_staging.txt.
+  const bool use_tma = A.coop_tma && (n & 1) == 0 && ((A.ws_stride & 1) == 0);
+  unsigned tma_parity = 0;
+  if (tid == 0) mbar_init(&s_mbar, 1);
 #define grad (A.ws + (size_t)cta * A.ws_stride)
 #define uq (A.ws + (size_t)cta * A.ws_stride + (size_t)(m + 1) * n)
 #define d0 (H + tri(N))
@@ -504,6 +544,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
         g[j] = aj + uj;
         acc = fma(x[j], aj + 0.5 * uj, acc);
       }
+      if (use_tma) fence_proxy_async();     // these rows are read by bulk copies (async proxy) at the top of the next iteration
 #pragma unroll
       for (int q = 16; q > 0; q >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, q);
       if (lane == 0) val[k] = M.c[k] + acc;
@@ -591,6 +632,16 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
     const double of = phase1 ? 0.0 : sf;
     const double tcur = phase1 ? x[n] : 0.0;
     it_of = of; it_tcur = tcur;
+    auto tma_issue = [&](int r0) {     // raw gradient rows r0 .. r0 + kc of the chunk -> staging rows (thread 0)
+      if (tid == 0) {
+        const int kc = min(IPM_KC, R - r0);
+        // (write-after-read on the staging area needs no proxy fence: the generic-proxy reads of the previous chunk were
+        // complete at the CTA barrier this thread has just left)
+        mbar_expect_tx(&s_mbar, (unsigned)(kc * n * 8));
+        for (int c = 0; c < kc; ++c) tma_load_1d(stage + c * lds, grad + (size_t)M.row_fn[r0 + c] * n, (unsigned)(n * 8), &s_mbar);
+      }
+    };
+    if (use_tma && R > 0) tma_issue(0);
     D2_START();
     double th_p = 0, sumv_p = 0, cs_p = 0, vl1_p = 0, ci_p = 0, cv_p = 0, cvu_p = 0, vmax_p = 0, viol_p = -1e300;
     for (int r = tid; r < R; r += IPM_NT) {
@@ -625,6 +676,23 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
     };
     for (int r0 = 0; r0 < R; r0 += IPM_KC) {
       const int kc = min(IPM_KC, R - r0), kc4 = (kc + 3) & ~3;
+      if (use_tma) {
+        mbar_wait(&s_mbar, tma_parity);
+        tma_parity ^= 1u;
+        for (int c = wid; c < kc4; c += IPM_NW) {   // scale / mask the landed row in place
+          if (c < kc) {
+            const int r = r0 + c;
+            const double sq = sqrt(Ss[r]), f = sq * fsc[r];
+            for (int j = lane; j < lds; j += 32) {
+              double vv = 0.0;
+              if (j < N && !(flg[j] & F_FIXED)) vv = (j < n) ? f * stage[c * lds + j] : -sq;
+              stage[c * lds + j] = vv;
+            }
+          } else {
+            for (int j = lane; j < lds; j += 32) stage[c * lds + j] = 0.0;
+          }
+        }
+      } else
       for (int c = wid; c < kc4; c += IPM_NW) {   // one staged row per warp (two with the 8-warp build)
         const int r = r0 + c;
         if (c < kc) prefetch_row(r);       // eight loads in flight per lane; a prefetch one chunk ahead only spilled
@@ -657,6 +725,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
       if (kc4 == IPM_KC) syrk_dmma(H, 0, N, stage, lds, IPM_KC, 1.0);   // compile-time rank: the k loop unrolls
       else syrk_dmma(H, 0, N, stage, lds, kc4, 1.0);
       __syncthreads();
+      if (use_tma && r0 + IPM_KC < R) tma_issue(r0 + IPM_KC);   // (single staging buffer: the next chunk can only start now)
       D2_MARK(10);
     }
     D2_MARK(2);
@@ -1208,6 +1277,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
         const int qi = e / n, j = e - qi * n, k = qfn[qi];
         grad[(size_t)k * n + j] += alpha * __ldcg(uq + (size_t)k * n + j);
       }
+      if (use_tma) fence_proxy_async();     // (see finish_init)
       __syncthreads();
       ++iters;
       PH_MARK(7);
