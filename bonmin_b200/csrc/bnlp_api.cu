@@ -89,8 +89,8 @@ struct Device {
   DBuf<int> oaCI[2], oaSR[2], oaRS[2];
   // model
   DBuf<double> c, A, Qp, Qf, row_sgn, row_bnd, gl, gu, xl, xu;
-  DBuf<int> qidx, row_fn, fn_row_up, fn_row_lo, eq_fn, fn_eq, dense_rows, sp_seg_start, sp_seg_i, sp_seg_k, sp_ent_row;
-  DBuf<double> sp_ent_p, lrV;
+  DBuf<int> qidx, row_fn, fn_row_up, fn_row_lo, eq_fn, fn_eq, dense_rows, sp_seg_start, sp_seg_i, sp_seg_k, sp_ent_row, sp_rows, spc_row;
+  DBuf<double> sp_ent_p, lrV, spc_val, sph_rec;
   DBuf<int> fn_lr_start;
   DBuf<double> eq_bnd;
   EvalModelDev ev;   // eval / OA view of the tape
@@ -252,7 +252,7 @@ static size_t ipm_smem_doubles_coop(int n, int m, int R) {
   d += (size_t)7 * npad;
   const int Rp = (R + 1) & ~1, Kp = (m + 2) & ~1;
   d += (size_t)10 * Rp + (size_t)6 * Kp + (size_t)IPM_NW * 12;
-  d += (size_t)(((N + 1) & ~1) * 2 + 2 * Kp) / 2 + 2;
+  d += (size_t)(((N + 1) & ~1) * 2 + 2 * Kp + Rp) / 2 + 2;   // flg, fixlist, qblk, qfn, drow (ints)
   return d;
 }
 
@@ -276,6 +276,10 @@ struct IpmView {
   // sparse linear rows of J' Sigma J (DevModel::sp_*): everything else is in dense_rows
   std::vector<int> dense_rows, sp_seg_start, sp_seg_i, sp_seg_k, sp_ent_row;
   std::vector<double> sp_ent_p;
+  // the same sparse rows in the layout the cooperative kernel reads (DevModel::spc_* / sph_*)
+  std::vector<int> sp_rows, spc_row;
+  std::vector<double> spc_val, sph_rec;
+  int spc_slots = 0, spc_ld = 0, sph_slots = 0;
   // low-rank quadratic blocks (DevModel::lrV): factor rows per function, CSR over functions 0 .. m
   std::vector<int> fn_lr_start;
   std::vector<double> lrV;
@@ -361,11 +365,18 @@ void build_ipm_view(const HostModel &M, IpmView &V) {
   for (const Term &t : M.terms) has_term[t.fn] = 1;
   struct Ent { int i, k, row; double p; };
   std::vector<Ent> ents;
+  // Which rows are worth it: a staged dense row costs ~1.2 k cycles of its rank-16 DMMA update at n = 200 (cooperative kernel,
+  // H in shared memory), a sparse row ~1 cycle per touched entry (z (z + 1) / 2 of them for z nonzeros), so models that
+  // qualify for the cooperative kernel take rows of up to n / 5 nonzeros (C3: the 40 linear rows with ~20 of 200).  The
+  // general kernel, whose H may live in global memory, keeps the short-row limit.
+  const bool coop_candidate = n <= 256 && M.terms.empty() && V.nE == 0 && V.nq > 0;
+  int sparse_max = coop_candidate ? std::max(IPM_SPARSE_ROW, n / 5) : IPM_SPARSE_ROW;
+  if (const char *e = getenv("BNLP_SPARSE_ROW_MAX")) sparse_max = atoi(e);
   for (int r = 0; r < (int)V.row_fn.size(); ++r) {
     const int fn = V.row_fn[r];
     std::vector<int> cols;
     for (int j = 0; j < n; ++j) if (V.A[(size_t)fn * n + j] != 0.0) cols.push_back(j);
-    const bool sparse = V.qidx[fn] < 0 && !has_term[fn] && (int)cols.size() <= IPM_SPARSE_ROW && n > 64;
+    const bool sparse = V.qidx[fn] < 0 && !has_term[fn] && (int)cols.size() <= sparse_max && n > 64;
     if (!sparse) { V.dense_rows.push_back(r); continue; }
     for (size_t a = 0; a < cols.size(); ++a) {
       const double va = V.A[(size_t)fn * n + cols[a]];
@@ -384,6 +395,68 @@ void build_ipm_view(const HostModel &M, IpmView &V) {
     V.sp_ent_row.push_back(ents[e].row); V.sp_ent_p.push_back(ents[e].p);
   }
   if (!ents.empty()) V.sp_seg_start.push_back((int)ents.size());
+  // ---- the cooperative kernel's view of the same rows.  Walking the segment lists above costs three DEPENDENT L2 round
+  // trips per touched entry (segment -> entry -> row data); measured at C3 that was 84 k cycles per iteration, twice what
+  // the two staged chunks it replaced had cost.  So: (1) the transposed lists are slot-major arrays (slot s of column j at
+  // [s * spc_ld + j]: consecutive threads read consecutive addresses, the loads of all slots are independent); (2) the
+  // touched entries of H are dealt to 512 virtual threads as self-contained 16-byte records {packed index, row | last
+  // << 30, a_i a_k}, slot-major again ([s * 512 + v]): a thread streams its records with several loads in flight and adds
+  // a run of records that share a target in a fixed order before it touches H once.  The elastic's row is not listed:
+  // its entries are sums the column pass forms on the side.
+  V.sp_rows.clear(); V.spc_row.clear(); V.spc_val.clear(); V.sph_rec.clear();
+  V.spc_slots = V.spc_ld = V.sph_slots = 0;
+  {
+    std::vector<char> is_dense(V.row_fn.size(), 0);
+    for (int r : V.dense_rows) is_dense[r] = 1;
+    for (int r = 0; r < (int)V.row_fn.size(); ++r) if (!is_dense[r]) V.sp_rows.push_back(r);
+  }
+  if (!V.sp_rows.empty()) {
+    std::vector<std::vector<std::pair<int, double>>> col(n);
+    for (int r : V.sp_rows) {
+      const int fn = V.row_fn[r];
+      for (int j = 0; j < n; ++j) if (V.A[(size_t)fn * n + j] != 0.0) col[j].push_back({r, V.A[(size_t)fn * n + j]});
+    }
+    for (int j = 0; j < n; ++j) V.spc_slots = std::max(V.spc_slots, (int)col[j].size());
+    V.spc_ld = (n + 31) & ~31;
+    V.spc_row.assign((size_t)V.spc_slots * V.spc_ld, -1);
+    V.spc_val.assign((size_t)V.spc_slots * V.spc_ld, 0.0);
+    for (int j = 0; j < n; ++j)
+      for (size_t e = 0; e < col[j].size(); ++e) { V.spc_row[e * V.spc_ld + j] = col[j][e].first; V.spc_val[e * V.spc_ld + j] = col[j][e].second; }
+    // records: whole segments (kind 0 only) to the least loaded virtual thread, longest first
+    const int VT = 512;
+    struct Seg { int start, len, tgt; };
+    std::vector<Seg> segs;
+    for (size_t sgi = 0; sgi < V.sp_seg_i.size(); ++sgi) {
+      if (V.sp_seg_i[sgi] >= n) continue;
+      segs.push_back({V.sp_seg_start[sgi], V.sp_seg_start[sgi + 1] - V.sp_seg_start[sgi], V.sp_seg_i[sgi] * (V.sp_seg_i[sgi] + 1) / 2 + V.sp_seg_k[sgi]});
+    }
+    std::stable_sort(segs.begin(), segs.end(), [](const Seg &a, const Seg &b) { return a.len > b.len; });
+    std::vector<std::vector<std::pair<long long, double>>> th(VT);   // (tgt | row << 32 | last << 62, p)
+    size_t nxt = 0;
+    for (const Seg &sg : segs) {
+      // longest first + round robin over threads sorted by load: with the lengths sorted a plain cyclic deal is balanced to
+      // within one segment
+      std::vector<std::pair<long long, double>> &T = th[nxt];
+      nxt = (nxt + 1) % VT;
+      for (int e = 0; e < sg.len; ++e) {
+        const long long row = V.sp_ent_row[sg.start + e] & 0xfffffff;
+        const long long last = (e == sg.len - 1) ? 1 : 0;
+        T.push_back({(long long)sg.tgt | (row << 32) | (last << 62), V.sp_ent_p[sg.start + e]});
+      }
+    }
+    for (int v = 0; v < VT; ++v) V.sph_slots = std::max(V.sph_slots, (int)th[v].size());
+    V.sph_rec.assign((size_t)V.sph_slots * VT * 2, 0.0);
+    for (int v = 0; v < VT; ++v)
+      for (int sl = 0; sl < V.sph_slots; ++sl) {
+        long long key = 0;            // padding: target 0, row 0, coefficient 0, not last: adds nothing and is never flushed
+        double pv = 0.0;
+        if (sl < (int)th[v].size()) { key = th[v][sl].first; pv = th[v][sl].second; }
+        double kd;
+        std::memcpy(&kd, &key, 8);
+        V.sph_rec[((size_t)sl * VT + v) * 2] = kd;
+        V.sph_rec[((size_t)sl * VT + v) * 2 + 1] = pv;
+      }
+  }
   // ---- low-rank quadratic blocks (used by the large-model path only; the dense copies stay for evaluation / OA)
   V.fn_lr_start.assign(m + 2, 0);
   V.n_lr = 0;
@@ -471,6 +544,7 @@ extern "C" bnlp_engine *bnlp_engine_create(const bnlp_problem *prob, const int *
     bad |= upload(D.eq_fn, eq_fn); bad |= upload(D.fn_eq, fn_eq); bad |= upload(D.eq_bnd, eq_bnd);
     bad |= upload(D.dense_rows, V.dense_rows); bad |= upload(D.sp_seg_start, V.sp_seg_start); bad |= upload(D.sp_seg_i, V.sp_seg_i);
     bad |= upload(D.sp_seg_k, V.sp_seg_k); bad |= upload(D.sp_ent_row, V.sp_ent_row); bad |= upload(D.sp_ent_p, V.sp_ent_p);
+    bad |= upload(D.sp_rows, V.sp_rows); bad |= upload(D.spc_row, V.spc_row); bad |= upload(D.spc_val, V.spc_val); bad |= upload(D.sph_rec, V.sph_rec);
     bad |= upload(D.fn_lr_start, V.fn_lr_start); bad |= upload(D.lrV, V.lrV);
     bad |= upload(D.gl, M.gl); bad |= upload(D.gu, M.gu); bad |= upload(D.xl, M.xl); bad |= upload(D.xu, M.xu);
     bad |= upload(D.e_int, e_ints); bad |= upload(D.e_dbl, e_dbls);
@@ -492,6 +566,8 @@ extern "C" bnlp_engine *bnlp_engine_create(const bnlp_problem *prob, const int *
     dm.Rd = (int)V.dense_rows.size(); dm.dense_rows = D.dense_rows.p;
     dm.sp_nseg = (int)V.sp_seg_i.size(); dm.sp_seg_start = D.sp_seg_start.p; dm.sp_seg_i = D.sp_seg_i.p; dm.sp_seg_k = D.sp_seg_k.p;
     dm.sp_ent_row = D.sp_ent_row.p; dm.sp_ent_p = D.sp_ent_p.p;
+    dm.Rs = (int)V.sp_rows.size(); dm.sp_rows = D.sp_rows.p; dm.spc_slots = V.spc_slots; dm.spc_ld = V.spc_ld; dm.spc_row = D.spc_row.p;
+    dm.spc_val = D.spc_val.p; dm.sph_slots = V.sph_slots; dm.sph_rec = D.sph_rec.p;
     dm.n_lr = V.n_lr; dm.fn_lr_start = D.fn_lr_start.p; dm.lrV = D.lrV.p;
     if (d == 0) {
       const size_t need = ipm_smem_doubles(n, m, E->R, E->E, 1) * sizeof(double);
@@ -556,12 +632,15 @@ int engine_reload_values(bnlp_engine *Q, const HostModel &M) {
     // the sparse-row lists depend on which coefficients of A are non-zero: they follow the new numbers
     bad |= upload(D.dense_rows, V.dense_rows); bad |= upload(D.sp_seg_start, V.sp_seg_start); bad |= upload(D.sp_seg_i, V.sp_seg_i);
     bad |= upload(D.sp_seg_k, V.sp_seg_k); bad |= upload(D.sp_ent_row, V.sp_ent_row); bad |= upload(D.sp_ent_p, V.sp_ent_p);
+    bad |= upload(D.sp_rows, V.sp_rows); bad |= upload(D.spc_row, V.spc_row); bad |= upload(D.spc_val, V.spc_val); bad |= upload(D.sph_rec, V.sph_rec);
     if (bad) return 0;
     D.dm.A = D.A.p; D.dm.Qp = D.Qp.p; D.dm.Qf = D.Qf.p; D.dm.c = D.c.p; D.dm.row_bnd = D.row_bnd.p; D.dm.eq_bnd = D.eq_bnd.p;
     D.dm.gl = D.gl.p; D.dm.gu = D.gu.p;
     D.dm.Rd = (int)V.dense_rows.size(); D.dm.dense_rows = D.dense_rows.p;
     D.dm.sp_nseg = (int)V.sp_seg_i.size(); D.dm.sp_seg_start = D.sp_seg_start.p; D.dm.sp_seg_i = D.sp_seg_i.p; D.dm.sp_seg_k = D.sp_seg_k.p;
     D.dm.sp_ent_row = D.sp_ent_row.p; D.dm.sp_ent_p = D.sp_ent_p.p;
+    D.dm.Rs = (int)V.sp_rows.size(); D.dm.sp_rows = D.sp_rows.p; D.dm.spc_slots = V.spc_slots; D.dm.spc_ld = V.spc_ld; D.dm.spc_row = D.spc_row.p;
+    D.dm.spc_val = D.spc_val.p; D.dm.sph_slots = V.sph_slots; D.dm.sph_rec = D.sph_rec.p;
     if (upload(D.fn_lr_start, V.fn_lr_start) || upload(D.lrV, V.lrV)) return 0;
     D.dm.n_lr = V.n_lr; D.dm.fn_lr_start = D.fn_lr_start.p; D.dm.lrV = D.lrV.p;
   }
@@ -579,13 +658,13 @@ extern "C" void bnlp_engine_free(bnlp_engine *E) {
                     &D.eX2, &D.eDU, &D.eU, &D.oVal, &D.oLB, &D.oUB, &D.dPXL, &D.dPXU, &D.dCB})
       b->release();
     for (auto *b : {&D.qidx, &D.row_fn, &D.fn_row_up, &D.fn_row_lo, &D.e_int, &D.dST, &D.dIT, &D.queue, &D.cidle, &D.eq_fn, &D.fn_eq, &D.oRS, &D.oCI,
-                    &D.oSR, &D.dCP, &D.dCC, &D.dCW, &D.dense_rows, &D.sp_seg_start, &D.sp_seg_i, &D.sp_seg_k, &D.sp_ent_row})
+                    &D.oSR, &D.dCP, &D.dCC, &D.dCW, &D.dense_rows, &D.sp_seg_start, &D.sp_seg_i, &D.sp_seg_k, &D.sp_ent_row, &D.sp_rows, &D.spc_row})
       b->release();
     D.stats.release();
     for (int p = 0; p < 2; ++p) { D.oaVal[p].release(); D.oaLB[p].release(); D.oaUB[p].release(); D.oaCI[p].release(); D.oaSR[p].release(); D.oaRS[p].release();
       if (D.oa_comp[p]) cudaEventDestroy(D.oa_comp[p]); if (D.oa_copy[p]) cudaEventDestroy(D.oa_copy[p]); if (D.oa_k0[p]) cudaEventDestroy(D.oa_k0[p]); }
     if (D.stream2) cudaStreamDestroy(D.stream2);
-    D.sp_ent_p.release(); D.lrV.release(); D.fn_lr_start.release();
+    D.sp_ent_p.release(); D.lrV.release(); D.fn_lr_start.release(); D.spc_val.release(); D.sph_rec.release();
     if (D.stream) cudaStreamDestroy(D.stream);
     if (D.ev0) cudaEventDestroy(D.ev0);
     if (D.ev1) cudaEventDestroy(D.ev1);

@@ -344,16 +344,20 @@ __device__ __forceinline__ void trsm_dmma8(double *H, int j0, int nb, int lo, in
   }
 }
 
-// ---- chol2 with in-register block inverses and DMMA panel solves (no separate inversion pass)
-__device__ __forceinline__ bool chol3(double *H, int N, int Nrows, double *S, int ld, int *fail, long long *dbg = nullptr) {
+// ---- chol2 with in-register block inverses and DMMA panel solves (no separate inversion pass).
+// jstart > 0: the columns before jstart are final and the diagonal block at jstart is already factored and inverted.
+__device__ __forceinline__ bool chol3(double *H, int N, int Nrows, double *S, int ld, int *fail, long long *dbg = nullptr,
+                                      int jstart = 0) {
   const int w = threadIdx.x >> 5;
   long long t0 = dbg ? clock64() : 0;
-  __syncthreads();
-  if (w == 0) chol_diag8_inv(H, 0, min(8, N), fail);
-  __syncthreads();
-  if (*fail) return false;
+  if (jstart == 0) {
+    __syncthreads();
+    if (w == 0) chol_diag8_inv(H, 0, min(8, N), fail);
+    __syncthreads();
+    if (*fail) return false;
+  }
   C2_MARK(0);
-  for (int j0 = 0; j0 < N; j0 += 16) {
+  for (int j0 = jstart; j0 < N; j0 += 16) {
     const int nb0 = min(8, N - j0), j1 = j0 + 8;
     trsm_dmma8(H, j0, nb0, j0 + nb0, Nrows, S, ld);
     __syncthreads();
@@ -387,6 +391,169 @@ __device__ __forceinline__ bool chol3(double *H, int N, int Nrows, double *S, in
     if (*fail) return false;
   }
   return true;
+}
+
+// =====================================================================================================================
+// chol4: 16-column panels with the WHOLE 16 x 16 diagonal block factored one panel ahead.
+//
+// chol3 runs four CTA-wide phases per 16 columns (solve | 8-column update + diagonal block | solve | trailing update +
+// diagonal block) and in two of them everybody waits for the pivot chain of an 8 x 8 diagonal block (~2 k cycles of one
+// thread).  Here a panel is two phases:
+//   panel phase     every warp takes row tiles below the diagonal block and does, for its own eight rows and without any
+//                   CTA barrier in between, solve against X(j0) -> 8-column update of the second sub-panel -> solve
+//                   against X(j1) (all three are row-local), leaving the sixteen solved columns transposed in S;
+//   trailing phase  warps 1 .. NW-1 apply the rank-16 update; warp 0 updates the NEXT 16 x 16 diagonal block first and
+//                   factors it completely under that update: diagonal tile, the tile below it, second diagonal tile.
+// The pivot chain is thereby hidden as long as the trailing update is longer than it, and there are two CTA barriers
+// per 16 columns instead of four.  Ragged ends (N not a multiple of 16; the carried right-hand-side rows share the last
+// tile row with the last diagonal block) are left to chol3's loop, entered at the first panel that is not full.
+
+// 8 x 8 diagonal block at j0 (full: 8 valid rows): Cholesky + inverse by ONE WARP.  Every lane runs the factorisation
+// redundantly in registers (same values, no communication); lane c < 8 forms column c of X = L^-1 alongside, so the
+// instruction stream of the warp holds the factorisation plus ONE column of the inverse instead of all eight (the
+// one-thread version issues ~250 dependent-ish FP64 instructions; this one ~150).  A non-positive pivot SETS *fail
+// (never clears it).
+static __device__ __noinline__ void chol_diag8_invw(double *H, int j0, int *fail) {
+  const int lane = threadIdx.x & 31, c = lane & 7;
+  double a[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int k = 0; k <= i; ++k) a[i][k] = H[tri(j0 + i) + j0 + k];
+  __syncwarp();
+  bool ok = true;
+  double x[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const double d = a[j][j];
+    if (!(d > 0.0) || !isfinite(d)) ok = false;
+    const double rs = rsqrt(d);
+    double t = (c == j) ? 1.0 : 0.0;            // row j of X, column c: [c == j] - sum_{k<j} L_jk X_kc
+#pragma unroll
+    for (int k = 0; k < j; ++k) t = fma(-a[j][k], x[k], t);
+    x[j] = t * rs;
+#pragma unroll
+    for (int i = j + 1; i < 8; ++i) a[i][j] *= rs;
+#pragma unroll
+    for (int i = j + 1; i < 8; ++i)
+#pragma unroll
+      for (int k = j + 1; k <= i; ++k) a[i][k] = fma(-a[i][j], a[k][j], a[i][k]);
+  }
+  if (lane < 8) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i >= c) H[tri(j0 + i) + j0 + c] = x[i];
+  }
+  if (lane == 0 && !ok) *fail = 1;
+  __syncwarp();
+}
+
+// the rest of the 16 x 16 diagonal block at la (both 8 x 8 diagonal tiles full), given its first diagonal tile factored and
+// inverted: tile (lb, la) := tile X(la)', tile (lb, lb) -= L(lb, la) L(lb, la)', factor + invert (lb, lb).  One whole warp.
+__device__ __forceinline__ void chol_diag16_rest(double *H, int la, int *fail) {
+  const int lane = threadIdx.x & 31, lr = lane >> 2, lc = lane & 3;
+  const int lb = la + 8, cc = 2 * lc;
+  double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+    const int kk = 4 * ks + lc;
+    const double av = H[tri(lb + lr) + la + kk];
+    const double bv = (kk <= lr) ? H[tri(la + lr) + la + kk] : 0.0;     // B[k][c] = X[c][k]
+    dmma(c0, c1, av, bv);
+  }
+  double *Tl = H + tri(lb + lr) + la;
+  __syncwarp();
+  Tl[cc] = c0; Tl[cc + 1] = c1;
+  __syncwarp();
+  const double a0 = Tl[lc], a1 = Tl[4 + lc];      // A[m][k] = L[lb+m][la+k] and B[k][n] = L[lb+n][la+k]: the same fragment
+  double *Td = H + tri(lb + lr) + lb;
+  double d0 = (cc <= lr) ? Td[cc] : 0.0, d1 = (cc + 1 <= lr) ? Td[cc + 1] : 0.0;
+  dmma(d0, d1, -a0, a0);
+  dmma(d0, d1, -a1, a1);
+  if (cc <= lr) Td[cc] = d0;
+  if (cc + 1 <= lr) Td[cc + 1] = d1;
+  __syncwarp();
+  chol_diag8_invw(H, lb, fail);
+}
+
+// panel phase of a full panel (16 columns from j0, diagonal block factored): rows [lo2, Nrows), lo2 = j0 + 16, one row
+// tile per warp at a time; the solved columns go to H and, transposed, to S[0 .. 15][i] (zero for i >= Nrows).
+__device__ __forceinline__ void panel16_rows(double *H, int j0, int Nrows, double *S, int ld) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int lr = lane >> 2, lc = lane & 3, cc = 2 * lc;
+  const int j1 = j0 + 8, lo2 = j0 + 16, hi8 = (Nrows + 7) & ~7;
+  double bx0[2], bx1[2], bl[2];
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+    const int kk = 4 * ks + lc;
+    bx0[ks] = (kk <= lr) ? H[tri(j0 + lr) + j0 + kk] : 0.0;
+    bx1[ks] = (kk <= lr) ? H[tri(j1 + lr) + j1 + kk] : 0.0;
+    bl[ks] = H[tri(j1 + lr) + j0 + kk];            // B[k][n] = L[j1 + n][j0 + k]
+  }
+  for (int i0 = lo2 + 8 * w; i0 < hi8; i0 += 8 * IPM_NW) {
+    const int i = i0 + lr;
+    const bool iv = i < Nrows;
+    double *Hi = H + tri(min(i, Nrows - 1));
+    // (a) columns j0 .. j0+7: L = A X(j0)'
+    double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) dmma(c0, c1, iv ? Hi[j0 + 4 * ks + lc] : 0.0, bx0[ks]);
+    __syncwarp();
+    if (iv) { Hi[j0 + cc] = c0; Hi[j0 + cc + 1] = c1; }
+    S[cc * ld + i] = iv ? c0 : 0.0;
+    S[(cc + 1) * ld + i] = iv ? c1 : 0.0;
+    // the tile of the second sub-panel, as accumulator
+    double d0 = iv ? Hi[j1 + cc] : 0.0, d1 = iv ? Hi[j1 + cc + 1] : 0.0;
+    __syncwarp();
+    // (b) columns j1 .. j1+7 -= L(i, j0..) L(j1.., j0..)'
+    dmma(d0, d1, -S[lc * ld + i], bl[0]);
+    dmma(d0, d1, -S[(4 + lc) * ld + i], bl[1]);
+    if (iv) { Hi[j1 + cc] = d0; Hi[j1 + cc + 1] = d1; }
+    __syncwarp();
+    // (c) L = (updated tile) X(j1)'
+    double e0 = 0.0, e1 = 0.0;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) dmma(e0, e1, iv ? Hi[j1 + 4 * ks + lc] : 0.0, bx1[ks]);
+    __syncwarp();
+    if (iv) { Hi[j1 + cc] = e0; Hi[j1 + cc + 1] = e1; }
+    S[(8 + cc) * ld + i] = iv ? e0 : 0.0;
+    S[(9 + cc) * ld + i] = iv ? e1 : 0.0;
+  }
+}
+
+__device__ __forceinline__ bool chol4(double *H, int N, int Nrows, double *S, int ld, int *fail, long long *dbg = nullptr) {
+  const int w = threadIdx.x >> 5;
+  if (N < 32) return chol3(H, N, Nrows, S, ld, fail, dbg);
+  long long t0 = dbg ? clock64() : 0;
+  if (threadIdx.x == 0) *fail = 0;
+  __syncthreads();
+  if (w == 0) { chol_diag8_invw(H, 0, fail); chol_diag16_rest(H, 0, fail); }
+  __syncthreads();
+  if (*fail) return false;
+  C2_MARK(0);
+  int j0 = 0;
+  for (;;) {                                  // invariant: j0 + 16 <= N and the 16 x 16 diagonal block at j0 is factored
+    panel16_rows(H, j0, Nrows, S, ld);
+    __syncthreads();
+    C2_MARK(1);
+    const int lo = j0 + 16;
+    if (lo >= N) return true;                 // (N a multiple of 16: only carried rows were left)
+    const bool next_full = lo + 16 <= N;
+    if (w == 0) {
+      syrk_rt(H, lo, Nrows, S, ld, 16, -1.0, 0, 1 << 20);
+      __syncwarp();
+      if (next_full) { chol_diag8_invw(H, lo, fail); chol_diag16_rest(H, lo, fail); }
+      else chol_diag8_inv(H, lo, min(8, N - lo), fail);   // (*fail is 0 here: it was checked after the last barrier)
+    } else {
+      syrk_rt(H, lo, Nrows, S, ld, 16, -1.0, w, IPM_NW - 1);
+    }
+    __syncthreads();
+    C2_MARK(3);
+    if (*fail) return false;
+    j0 = lo;
+    if (!next_full) break;
+  }
+  return chol3(H, N, Nrows, S, ld, fail, dbg, j0);
 }
 
 }  // namespace BNLP_NS

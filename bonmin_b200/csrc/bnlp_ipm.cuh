@@ -83,6 +83,12 @@ struct DevModel {
   int Rd, sp_nseg;
   const int *dense_rows, *sp_seg_start, *sp_seg_i, *sp_seg_k, *sp_ent_row;
   const double *sp_ent_p;
+  // the same rows as the cooperative kernel reads them (built in build_ipm_view, explained there): sp_rows[0 .. Rs) = the
+  // sparse rows; column lists, slot-major: slot s of column j at [s * spc_ld + j] (row or -1, coefficient); touched entries
+  // of H as 16-byte records {packed index | row << 32 | last << 62, a_i a_k} dealt to 512 virtual threads: [s * 512 + v]
+  int Rs, spc_slots, spc_ld, sph_slots;
+  const int *sp_rows, *spc_row;
+  const double *spc_val, *sph_rec;
   // LOW-RANK quadratic parts (large-model path only): Q_k = sum_r v_r v_r' over the factor rows fn_lr_start[k] ..
   // fn_lr_start[k+1] of lrV (n_lr x n), found by a pivoted Cholesky when the model is loaded (a sum of squares of linear forms
   // arrives as a dense n x n block from the tape builder).  u_k = Q_k d costs 2 r n FMAs instead of n^2 and no block is

@@ -339,6 +339,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
 #define fixlist (flg + ((N + 1) & ~1))
 #define qblk (flg + 2 * ((N + 1) & ~1))
 #define qfn (flg + 2 * ((N + 1) & ~1) + Kp)
+#define drow (flg + 2 * ((N + 1) & ~1) + 2 * Kp)
   __shared__ int s_child, s_nfix, s_fail, s_nqf;
   // The scaled Jacobian rows of a J' Sigma J chunk are staged by BULK COPIES (TMA): thread 0 issues one cp.async.bulk per
   // raw gradient row (n doubles from this CTA's workspace in L2 into the staging area), every warp then scales its row in
@@ -361,6 +362,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
 #define pv ds
 #define p0 dv
 #define p1 jd0
+#define psq jd1
 
   if (tid == 0) {
     int c = 0;
@@ -369,6 +371,10 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
     s_nqf = c;
   }
   for (int k = tid; k <= m; k += IPM_NT) du[k] = 0.0;
+  // rows that go through the staged DMMA updates of J' Sigma J (the sparse linear rows are scattered entry by entry)
+  const int Rd = M.Rd;
+  for (int r = tid; r < Rd; r += IPM_NT) drow[r] = M.dense_rows[r];
+  for (int r = tid; r < M.Rs; r += IPM_NT) drow[Rd + r] = M.sp_rows[r];
   __syncthreads();
   const int nqf = s_nqf;
   const int nqpad = CB.nqpad, ldd = CB.ldd;
@@ -634,14 +640,14 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
     it_of = of; it_tcur = tcur;
     auto tma_issue = [&](int r0) {     // raw gradient rows r0 .. r0 + kc of the chunk -> staging rows (thread 0)
       if (tid == 0) {
-        const int kc = min(IPM_KC, R - r0);
+        const int kc = min(IPM_KC, Rd - r0);
         // (write-after-read on the staging area needs no proxy fence: the generic-proxy reads of the previous chunk were
         // complete at the CTA barrier this thread has just left)
         mbar_expect_tx(&s_mbar, (unsigned)(kc * n * 8));
-        for (int c = 0; c < kc; ++c) tma_load_1d(stage + c * lds, grad + (size_t)M.row_fn[r0 + c] * n, (unsigned)(n * 8), &s_mbar);
+        for (int c = 0; c < kc; ++c) tma_load_1d(stage + c * lds, grad + (size_t)M.row_fn[drow[r0 + c]] * n, (unsigned)(n * 8), &s_mbar);
       }
     };
-    if (use_tma && R > 0) tma_issue(0);
+    if (use_tma && Rd > 0) tma_issue(0);
     D2_START();
     double th_p = 0, sumv_p = 0, cs_p = 0, vl1_p = 0, ci_p = 0, cv_p = 0, cvu_p = 0, vmax_p = 0, viol_p = -1e300;
     for (int r = tid; r < R; r += IPM_NT) {
@@ -650,7 +656,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
       rc[r] = res;
       const double ss = v[r] / s[r], sq = sqrt(ss);
       Ss[r] = ss;
-      pv[r] = v[r] / sq; p0[r] = sq * res; p1[r] = 1.0 / (sq * s[r]);
+      pv[r] = v[r] / sq; p0[r] = sq * res; p1[r] = 1.0 / (sq * s[r]); psq[r] = sq;
       th_p += fabs(res);
       sumv_p += v[r];
       cs_p += s[r] * v[r];
@@ -670,19 +676,19 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
     // warp c stages row c of a chunk; its raw gradient row is prefetched into registers one chunk ahead
     double gpre[8];
     auto prefetch_row = [&](int r) {
-      const double *g = grad + (size_t)M.row_fn[min(r, R - 1)] * n;
+      const double *g = grad + (size_t)M.row_fn[r] * n;
 #pragma unroll
       for (int u = 0; u < 8; ++u) gpre[u] = g[min(lane + 32 * u, n - 1)];
     };
-    for (int r0 = 0; r0 < R; r0 += IPM_KC) {
-      const int kc = min(IPM_KC, R - r0), kc4 = (kc + 3) & ~3;
+    for (int r0 = 0; r0 < Rd; r0 += IPM_KC) {
+      const int kc = min(IPM_KC, Rd - r0), kc4 = (kc + 3) & ~3;
       if (use_tma) {
         mbar_wait(&s_mbar, tma_parity);
         tma_parity ^= 1u;
         for (int c = wid; c < kc4; c += IPM_NW) {   // scale / mask the landed row in place
           if (c < kc) {
-            const int r = r0 + c;
-            const double sq = sqrt(Ss[r]), f = sq * fsc[r];
+            const int r = drow[r0 + c];
+            const double sq = psq[r], f = sq * fsc[r];
             for (int j = lane; j < lds; j += 32) {
               double vv = 0.0;
               if (j < N && !(flg[j] & F_FIXED)) vv = (j < n) ? f * stage[c * lds + j] : -sq;
@@ -694,10 +700,10 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
         }
       } else
       for (int c = wid; c < kc4; c += IPM_NW) {   // one staged row per warp (two with the 8-warp build)
-        const int r = r0 + c;
+        const int r = drow[min(r0 + c, Rd - 1)];
         if (c < kc) prefetch_row(r);       // eight loads in flight per lane; a prefetch one chunk ahead only spilled
         if (c < kc) {
-          const double sq = sqrt(Ss[r]), f = sq * fsc[r];
+          const double sq = psq[r], f = sq * fsc[r];
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             const int j = lane + 32 * u;
@@ -716,17 +722,81 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
       if (tid < N) {
         for (int c = 0; c < kc; ++c) {
           const double sv = stage[c * lds + tid];
-          jv = fma(sv, pv[r0 + c], jv);
-          a0 = fma(sv, p0[r0 + c], a0);
-          a1 = fma(sv, p1[r0 + c], a1);
+          const int r = drow[r0 + c];
+          jv = fma(sv, pv[r], jv);
+          a0 = fma(sv, p0[r], a0);
+          a1 = fma(sv, p1[r], a1);
         }
       }
       D2_MARK(9);
       if (kc4 == IPM_KC) syrk_dmma(H, 0, N, stage, lds, IPM_KC, 1.0);   // compile-time rank: the k loop unrolls
       else syrk_dmma(H, 0, N, stage, lds, kc4, 1.0);
       __syncthreads();
-      if (use_tma && r0 + IPM_KC < R) tma_issue(r0 + IPM_KC);   // (single staging buffer: the next chunk can only start now)
+      if (use_tma && r0 + IPM_KC < Rd) tma_issue(r0 + IPM_KC);   // (single staging buffer: the next chunk can only start now)
       D2_MARK(10);
+    }
+    // ---- sparse linear rows (DevModel::spc_* / sph_*, layouts explained in build_ipm_view): no staged rank-1 updates.
+    // Same values as a staged row would give (sv = (sqrt(Ss_r) fsc_r) a_rk, -sqrt(Ss_r) in the phase-1 elastic's column),
+    // summed in a fixed order; every load of the lists is independent of the arithmetic, several are kept in flight.
+    if (M.Rs > 0) {
+      const bool el_free = !(flg[n] & F_FIXED);       // phase 1: the elastic's row / column of H is live
+      double a2 = 0.0;
+      if (tid < n && !(flg[tid] & F_FIXED)) {
+        const int S2 = M.spc_slots, ldc = M.spc_ld;
+        for (int s0 = 0; s0 < S2; s0 += 4) {
+          int rr[4];
+          double av[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int sl = min(s0 + u, S2 - 1);
+            rr[u] = __ldg(M.spc_row + sl * ldc + tid);
+            av[u] = __ldg(M.spc_val + sl * ldc + tid);
+            if (s0 + u >= S2) rr[u] = -1;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (rr[u] >= 0) {
+              const int r = rr[u];
+              const double sv = (psq[r] * fsc[r]) * av[u];
+              jv = fma(sv, pv[r], jv);
+              a0 = fma(sv, p0[r], a0);
+              a1 = fma(sv, p1[r], a1);
+              a2 = fma(Ss[r] * fsc[r], av[u], a2);
+            }
+          }
+        }
+        if (el_free) H[tri(n) + tid] -= a2;
+      } else if (tid == n && el_free) {
+        double hnn = 0.0;
+        for (int q = 0; q < M.Rs; ++q) {
+          const int r = drow[Rd + q];
+          const double sv = -psq[r];
+          jv = fma(sv, pv[r], jv);
+          a0 = fma(sv, p0[r], a0);
+          a1 = fma(sv, p1[r], a1);
+          hnn += Ss[r];
+        }
+        H[tri(n) + n] += hnn;
+      }
+      const int SH = M.sph_slots;
+      const double2 *rec = reinterpret_cast<const double2 *>(M.sph_rec);
+      for (int vt = tid; vt < 512; vt += IPM_NT) {
+        double acc = 0.0;
+        for (int s0 = 0; s0 < SH; s0 += 8) {
+          double2 q[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) q[u] = __ldg(rec + (size_t)min(s0 + u, SH - 1) * 512 + vt);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            if (s0 + u < SH) {
+              const long long key = __double_as_longlong(q[u].x);
+              const int r = (int)(key >> 32) & 0xfffffff;
+              acc = fma(Ss[r] * fsc[r] * fsc[r], q[u].y, acc);
+              if ((key >> 62) & 1) { H[(int)(key & 0x7fffffff)] += acc; acc = 0.0; }
+            }
+          }
+        }
+      }
     }
     D2_MARK(2);
     // sweep over variables: Lagrangian gradient, right-hand sides (into the augmented rows), Sigma_x
@@ -968,7 +1038,11 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
       ++nfact;
       retry = false;
       PH_MARK(8);
+#ifdef BNLP_COOP_CHOL3
       if (!chol3(H, N, N + 2, stage, lds, &s_fail, TIMERS ? &s_tm[27] : nullptr)) {
+#else
+      if (!chol4(H, N, N + 2, stage, lds, &s_fail, TIMERS ? &s_tm[27] : nullptr)) {
+#endif
         // inertia correction: retry the whole step with a larger delta_w (first 1e-4, x100 then x8, /3 between iterations)
         if (delta_w == 0.0) delta_w = (delta_w_last == 0.0) ? 1e-4 : fmax(1e-20, delta_w_last / 3.0);
         else delta_w *= (delta_w_last == 0.0 ? 100.0 : 8.0);
@@ -983,6 +1057,8 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
         D2_START();
         backsolve_inv(H, N, red);
         D2_MARK(4);
+        // (requesting two whole rows per warp up front — sixteen loads in flight per lane — was measured: the phase itself gets
+        // shorter, the kernel 4 % slower; the register arrays cost more elsewhere than the exposed L2 round trips do here)
         dots_grad(M, grad, d0, d1, gd0, gd1);
         D2_MARK(5);
         for (int r = tid; r < R; r += IPM_NT) {
@@ -1273,9 +1349,18 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
         v[r] = fmin(fmax(v[r] + ad * dv[r], mu / (o.kappa_sigma * sn)), o.kappa_sigma * mu / sn);
       }
       for (int k = tid; k <= m; k += IPM_NT) val[k] += alpha * gd0[k] + 0.5 * alpha * alpha * du[k];
-      for (int e = tid; e < nqf * n; e += IPM_NT) {
-        const int qi = e / n, j = e - qi * n, k = qfn[qi];
-        grad[(size_t)k * n + j] += alpha * __ldcg(uq + (size_t)k * n + j);
+      for (int qi = wid; qi < nqf; qi += IPM_NW) {        // one row per warp, sixteen loads in flight per lane
+        const int k = qfn[qi];
+        double *gk = grad + (size_t)k * n;
+        const double *uk = uq + (size_t)k * n;
+        double gv[8], uv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int j = min(lane + 32 * u, n - 1); gv[u] = gk[j]; uv[u] = __ldcg(uk + j); }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int j = lane + 32 * u;
+          if (j < n) gk[j] = gv[u] + alpha * uv[u];
+        }
       }
       if (use_tma) fence_proxy_async();     // (see finish_init)
       __syncthreads();
@@ -1318,6 +1403,8 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
 #undef pv
 #undef p0
 #undef p1
+#undef psq
+#undef drow
 #undef xl
 #undef xu
 #undef x0

@@ -9,6 +9,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIBPATH = os.path.join(_HERE, "libbnlp.so")
+if os.environ.get("BNLP_LIB"):      # development aid: A/B runs of two builds of the same source on one GPU box (scripts/dev_variants.py)
+    _LIBPATH = os.path.abspath(os.environ["BNLP_LIB"])
 _lib = None
 
 c_int, c_dbl, c_void = ctypes.c_int, ctypes.c_double, ctypes.c_void_p

@@ -27,6 +27,7 @@ __global__ void __launch_bounds__(512, 1) bench(int N, const double *H0, double 
   if (which == 1) ok = chol2<false>(H, N, Nrows, stage, lds, &fail, dbg);
   else if (which == 2) ok = chol2<true>(H, N, Nrows, stage, lds, &fail, dbg);
   else if (which == 3) ok = chol3(H, N, Nrows, stage, lds, &fail, dbg);
+  else if (which == 4) ok = chol4(H, N, Nrows, stage, lds, &fail, dbg);
   if (threadIdx.x == 0 && blockIdx.x == 0) for (int q = 0; q < 5; ++q) out[8 + q] = dbgl[q];
   __syncthreads();
   long long t1 = clock64();
@@ -58,6 +59,22 @@ __global__ void __launch_bounds__(512, 1) bench(int N, const double *H0, double 
   long long q6 = clock64(); __syncthreads(); long long q7 = clock64();
   trsm_rows8(H, 8, 8, 16, Nrows, stage + 8 * lds, lds);
   long long q8 = clock64(); __syncthreads(); long long q9 = clock64();
+  // chol4 pieces, one warp alone: diagonal tile by a whole warp, rest of the 16 x 16 block, warp 0's trailing unit
+  for (int e = threadIdx.x; e < P; e += 512) H[e] = H0[e];
+  __syncthreads();
+  long long r0 = clock64();
+  if (threadIdx.x < 32) chol_diag8_invw(H, 0, &fail);
+  long long r1 = clock64();
+  if (threadIdx.x < 32) chol_diag16_rest(H, 0, &fail);
+  long long r2 = clock64();
+  if (threadIdx.x < 32) syrk_rt(H, 16, Nrows, stage, lds, 16, -1.0, 0, 1 << 20);
+  long long r3 = clock64();
+  __syncthreads();
+  long long r4 = clock64();
+  panel16_rows(H, 0, Nrows, stage, lds);
+  long long r5 = clock64();
+  __syncthreads();
+  if (threadIdx.x == 0 && blockIdx.x == 0) { out[19] = r1 - r0; out[20] = r2 - r1; out[21] = r3 - r2; out[22] = r5 - r4; }
   if (threadIdx.x == 0 && blockIdx.x == 0) { out[5] = q1 - q0; out[6] = q2 - q1; out[7] = q3 - q2; out[13] = q4 - q3; out[14] = q5 - q4; out[15] = q6 - q5; out[16] = q7 - q6; out[17] = q8 - q7; out[18] = q9 - q8; }
 }
 
@@ -105,9 +122,9 @@ int main(int argc, char **argv) {
   const int lds = ((N + 2 + 7) & ~7) + 4;
   size_t smem = (size_t)(((P + 1) & ~1) + 17 * lds) * 8;
   cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  const char *nm[4] = {"chol_dmma (old)", "chol2", "chol2 look-ahead", "chol3"};
+  const char *nm[5] = {"chol_dmma (old)", "chol2", "chol2 look-ahead", "chol3", "chol4"};
   for (int usedbg = 0; usedbg < 2; ++usedbg)
-  for (int which = 0; which < 4; ++which) {
+  for (int which = 0; which < 5; ++which) {
     long long h[32];
     for (int rep = 0; rep < 3; ++rep) { bench<<<NB, 512, smem>>>(N, dH0, dHo, dout, which, usedbg); cudaDeviceSynchronize(); }
     cudaError_t e = cudaGetLastError();
@@ -124,6 +141,7 @@ int main(int argc, char **argv) {
     printf("%-18s N=%d: factor %lld cycles (ok=%lld), backsolve %lld cycles, max|L err| %.2e, max rel x err %.2e | syrk16 old %lld new %lld\n",
            nm[which], N, h[0], h[1], h[2], errl, errx, h[3], h[4]);
     if (!which && !usedbg) printf("  probes (thread 0): sync %lld | diag8_inv %lld +sync %lld | trsm_dmma8 %lld +sync %lld | col8 %lld +sync %lld | trsm_rows8 %lld +sync %lld\n", h[5], h[6], h[7], h[13], h[14], h[15], h[16], h[17], h[18]);
+    if (!which && !usedbg) printf("  chol4 probes (warp 0 alone): diag8_invw %lld | diag16_rest (incl. second diag8_invw) %lld | trailing unit 0 %lld | panel16_rows (thread 0) %lld\n", h[19], h[20], h[21], h[22]);
     if (which) printf("    diag %lld trsm %lld col8 %lld trailing %lld invert %lld\n", h[8], h[9], h[10], h[11], h[12]);
   }
   return 0;
