@@ -18,7 +18,8 @@ class BbOptions(ctypes.Structure):
     _fields_ = [("number_strong_branch", c_int), ("number_before_trust", c_int), ("node_limit", c_int),
                 ("log_level", c_int), ("integer_tolerance", c_dbl), ("cutoff_decr", c_dbl), ("time_limit", c_dbl),
                 ("parallel_nodes", c_int), ("variable_selection", c_int), ("priorities", ctypes.POINTER(c_int)),
-                ("nlp_failure_behavior", c_int), ("number_look_ahead", c_int)]
+                ("nlp_failure_behavior", c_int), ("number_look_ahead", c_int), ("incumbent_x", ctypes.POINTER(c_dbl)),
+                ("incumbent_obj", c_dbl)]
 
 
 class BbResult(ctypes.Structure):
@@ -50,11 +51,16 @@ VARIABLE_SELECTION = {"strong-branching": 0, "qp-strong-branching": 1}
 
 
 def _opts(number_strong_branch=0, number_before_trust=0, node_limit=0, time_limit=0.0, parallel_nodes=0,
-          variable_selection="strong-branching", priorities=None, nlp_failure_behavior="stop", number_look_ahead=0):
+          variable_selection="strong-branching", priorities=None, nlp_failure_behavior="stop", number_look_ahead=0,
+          incumbent=None):
     o = BbOptions(number_strong_branch, number_before_trust, node_limit, 0, 0.0, 0.0, time_limit, parallel_nodes,
                   VARIABLE_SELECTION[variable_selection])
     o.nlp_failure_behavior = {"stop": 0, "fathom": 1}[nlp_failure_behavior]
     o.number_look_ahead = int(number_look_ahead)
+    if incumbent is not None:       # (objective, x) of a heuristic's solution: the search starts from its cutoff
+        o._inc = np.ascontiguousarray(incumbent[1], float)
+        o.incumbent_x = o._inc.ctypes.data_as(ctypes.POINTER(c_dbl))
+        o.incumbent_obj = float(incumbent[0])
     if priorities is not None:      # n ints, the LOWEST value is branched on first (kept alive on the struct)
         o._pri = np.ascontiguousarray(priorities, np.int32)
         o.priorities = o._pri.ctypes.data_as(ctypes.POINTER(c_int))

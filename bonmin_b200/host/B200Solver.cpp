@@ -481,6 +481,9 @@ BbResult bb_run(TMINLP2TNLP &root, BatchSolveFn solve, const BbOptions &opt, Tqp
   first->solved = true; first->obj = root.obj_value_; first->status = (int)root.return_status; first->x = root.x_sol_;
   Node *dive = first;   // node processed next without going through the heap (depth-first plunge on the better child)
   double cutoff = 1e100;
+  if (!opt.incumbent_x.empty() && opt.incumbent_obj < 1e99) {   // a heuristic's solution: CbcModel::setBestSolution before the tree
+    R.best_obj = opt.incumbent_obj; R.best_x = opt.incumbent_x; cutoff = opt.incumbent_obj - opt.cutoff_decr;
+  }
   const std::vector<double> xl_root = root.x_l_, xu_root = root.x_u_;
 
   double t_prefetch = 0;

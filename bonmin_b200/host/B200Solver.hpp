@@ -233,6 +233,8 @@ struct BbOptions {
   // NLP stays unsolved, :2639-2644), 1 = fathom (pretendFailIsInfeasible_: the node is dropped with a warning)
   int nlp_failure_behavior = 0;
   int number_look_ahead = 0;            // BonChooseVariable.cpp:152-158: stop strong branching after that many non-improving candidates (0 = off)
+  std::vector<double> incumbent_x;      // empty, or an integer-feasible point found before the search (heuristics) ...
+  double incumbent_obj = 1e100;         // ... and its objective: the search starts with cutoff = incumbent_obj - cutoff_decr
 };
 struct BbResult {
   int status = 0;               // 0 optimal, 1 infeasible, 2 node/time limit, 3 provider error, 4 a node NLP stayed unsolved

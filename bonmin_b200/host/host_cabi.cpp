@@ -48,6 +48,7 @@ int bnlp_bb_run_cb3(int n, int m, const int *var_type, const double *xl, const d
     if (o->priorities) opt.priorities.assign(o->priorities, o->priorities + n);
     opt.nlp_failure_behavior = o->nlp_failure_behavior;
     opt.number_look_ahead = o->number_look_ahead;
+    if (o->incumbent_x) { opt.incumbent_x.assign(o->incumbent_x, o->incumbent_x + n); opt.incumbent_obj = o->incumbent_obj; }
   }
   TqpSolveFn qfn;
   if (qp_cb)

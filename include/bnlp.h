@@ -294,6 +294,12 @@ typedef struct bnlp_bb_options {
   int number_look_ahead;       /* `number_look_ahead` (BonChooseVariable.cpp:152-158, 930-948): away from the root, stop the
                                   strong-branching loop after that many candidates in a row that did not improve the best
                                   score; 0 = off (the default) */
+  const double *incumbent_x;   /* n values or NULL: a known integer-feasible point with objective incumbent_obj (what a primal
+                                  heuristic found before the tree search starts: B-Hyb's HeuristicDive*,
+                                  src/CbcBonmin/Heuristics/BonHeuristicDive.cpp:67-302, registered in
+                                  BonBonminSetup.cpp:300-330).  The search starts with cutoff = incumbent_obj - cutoff_decr,
+                                  as CbcModel::setBestSolution does */
+  double incumbent_obj;
 } bnlp_bb_options;
 typedef struct bnlp_bb_result {
   int status;                 /* 0 optimal, 1 infeasible, 2 limit reached, 3 the batch-solve provider returned an error (the

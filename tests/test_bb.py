@@ -166,3 +166,18 @@ def test_tnlp_solver_contract_of_the_adapter():
     the IpoptSolver warm-start semantics (BonIpoptSolver.cpp:345-430), error code + UnsolvedError, output levels, clone.
     The checks are C++ (bnlp_host_selftest, bonmin_b200/host/host_cabi.cpp) on a stub provider."""
     assert bb.host_lib().bnlp_host_selftest() == 0
+
+
+def test_incumbent_from_a_heuristic_seeds_the_cutoff(oracle_ipm):
+    """B-Hyb runs its primal heuristics (HeuristicDive*, BonHeuristicDive.cpp:67-302) before the tree: the search then starts
+    from cutoff = incumbent - cutoff_decr.  Seeded with the optimum itself the tree proves it (same value, no more nodes than
+    the unseeded search) and hands the seeded point back; seeded with a worse feasible point it still finds the optimum."""
+    m = I.syn_miqcp(12, 6, 3, 3, 4)
+    s = _oracle_solver(m, oracle_ipm)
+    a = bb.run_callback(m, s, number_strong_branch=6)
+    assert a["status"] == 0
+    b = bb.run_callback(m, s, number_strong_branch=6, incumbent=(a["best_obj"], a["best_x"]))
+    assert b["status"] == 0 and b["best_obj"] == a["best_obj"] and b["nodes"] <= a["nodes"]
+    assert np.array_equal(b["best_x"], a["best_x"])
+    c = bb.run_callback(m, s, number_strong_branch=6, incumbent=(a["best_obj"] + 5.0, a["best_x"]))
+    assert c["status"] == 0 and c["best_obj"] == pytest.approx(a["best_obj"], rel=1e-9)
