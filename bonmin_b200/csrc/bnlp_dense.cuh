@@ -89,6 +89,13 @@ __device__ __forceinline__ void syrk_rt(double *H, int lo, int hi, const double 
   }
 }
 
+// the factorisations call the rank-16 trailing update from several places (warp 0's look-ahead unit, the other warps,
+// chol3's tail behind chol4): ONE out-of-line copy, so that every warp runs the same instructions (the inlined copies were
+// 3 000 of the cooperative kernel's instructions, and instruction fetch is what its warps wait for most after barriers)
+static __device__ __noinline__ void syrk_rt16_sub(double *H, int lo, int hi, const double *M, int ld, int u0, int ustride) {
+  syrk_rt(H, lo, hi, M, ld, 16, -1.0, u0, ustride);
+}
+
 // ---- rank-8 update of ONE 8-column block jc: H[i, jc .. jc+7] -= sum_{c<8} M[c][i] M[c][jc+k] for the tile rows from
 // row0 (jc % 8 == row0 % 8 == 0, row0 >= jc) up to hi, dealt to warps: the calling warp is number wi of nw.
 __device__ __forceinline__ void syrk_col8(double *H, int row0, int hi, const double *M, int ld, int wi, int nw, int jc = -1) {
@@ -380,11 +387,11 @@ __device__ __forceinline__ bool chol3(double *H, int N, int Nrows, double *S, in
     C2_MARK(1);
     if (lo >= N) break;
     if (w == 0) {
-      syrk_rt(H, lo, Nrows, S, ld, 16, -1.0, 0, 1 << 20);
+      syrk_rt16_sub(H, lo, Nrows, S, ld, 0, 1 << 20);
       __syncwarp();
       chol_diag8_inv(H, lo, min(8, N - lo), fail);
     } else {
-      syrk_rt(H, lo, Nrows, S, ld, 16, -1.0, w, IPM_NW - 1);
+      syrk_rt16_sub(H, lo, Nrows, S, ld, w, IPM_NW - 1);
     }
     __syncthreads();
     C2_MARK(3);
@@ -540,12 +547,12 @@ __device__ __forceinline__ bool chol4(double *H, int N, int Nrows, double *S, in
     if (lo >= N) return true;                 // (N a multiple of 16: only carried rows were left)
     const bool next_full = lo + 16 <= N;
     if (w == 0) {
-      syrk_rt(H, lo, Nrows, S, ld, 16, -1.0, 0, 1 << 20);
+      syrk_rt16_sub(H, lo, Nrows, S, ld, 0, 1 << 20);
       __syncwarp();
       if (next_full) { chol_diag8_invw(H, lo, fail); chol_diag16_rest(H, lo, fail); }
       else chol_diag8_inv(H, lo, min(8, N - lo), fail);   // (*fail is 0 here: it was checked after the last barrier)
     } else {
-      syrk_rt(H, lo, Nrows, S, ld, 16, -1.0, w, IPM_NW - 1);
+      syrk_rt16_sub(H, lo, Nrows, S, ld, w, IPM_NW - 1);
     }
     __syncthreads();
     C2_MARK(3);

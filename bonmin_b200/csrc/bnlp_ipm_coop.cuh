@@ -250,6 +250,131 @@ __device__ __forceinline__ void backsolve_inv(double *H, int N, double *xs /* 16
   }
 }
 
+// =====================================================================================================================
+// Back-substitution with 32 x 32 INVERSE diagonal blocks.
+//
+// backsolve_inv walks the factor in 8-row blocks: 26 blocks at n = 200, two CTA barriers and two dependent 8-FMA chains
+// per block, 23-25 k cycles for 0.08 MFLOP.  Here the diagonal 32 x 32 blocks of L that are made of four FULL tiles are
+// first replaced by their inverses (one warp per block, all blocks at once: Inv_pq = -X_p sum_{r=q}^{p-1} L_pr Inv_rq
+// over 8 x 8 tiles on DMMA, in place column by column — L_pq is last needed when Inv_pq is formed), then a 32-row block is
+// ONE dot-product stage (x_B = Inv_B' w_B) and one update stage.  Ragged tail tiles keep the 8-row procedure.
+
+// C (8 x 8, accumulator layout) += sgn * A(tile at rows ia.., cols ka..) * B(tile at rows ib.., cols kb..); lower-triangular
+// operand tiles (diagonal tiles of X / Inv) are masked by a_lo / b_lo (entries above the diagonal do not exist in the packed
+// storage).
+__device__ __forceinline__ void tile_mm(const double *H, int ia, int ka, bool a_lo, int ib, int kb, bool b_lo, double sgn,
+                                        double &c0, double &c1) {
+  const int lane = threadIdx.x & 31, lr = lane >> 2, lc = lane & 3;
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+    const int kk = 4 * ks + lc;
+    // A[m = lr][k = kk] = tile_a(lr, kk);  B[k = kk][n = lr] = tile_b(kk, lr)
+    const double av = (!a_lo || kk <= lr) ? H[tri(ia + lr) + ka + kk] : 0.0;
+    const double bv = (!b_lo || lr <= kk) ? H[tri(ib + kk) + kb + lr] : 0.0;
+    dmma(c0, c1, sgn * av, bv);
+  }
+}
+__device__ __forceinline__ void tile_store(double *H, int i0, int k0, double c0, double c1) {
+  const int lane = threadIdx.x & 31, lr = lane >> 2, lc = lane & 3;
+  double *p = H + tri(i0 + lr) + k0 + 2 * lc;
+  p[0] = c0; p[1] = c1;
+}
+
+// in-place inverse of the 32 x 32 lower-triangular diagonal block at i0 (four full tiles; diagonal tiles already hold the
+// inverses X_p of the 8 x 8 diagonal blocks).  One whole warp.
+__device__ __forceinline__ void invert_block32(double *H, int i0) {
+  for (int q = 0; q < 3; ++q) {
+    for (int p = q + 1; p < 4; ++p) {
+      // S = sum_{r=q}^{p-1} L_pr Inv_rq   (Inv_qq = X_q is lower triangular; Inv_rq, r > q, full)
+      double s0 = 0.0, s1 = 0.0;
+      for (int r = q; r < p; ++r) tile_mm(H, i0 + 8 * p, i0 + 8 * r, false, i0 + 8 * r, i0 + 8 * q, r == q, 1.0, s0, s1);
+      __syncwarp();
+      tile_store(H, i0 + 8 * p, i0 + 8 * q, s0, s1);        // L_pq is dead: its place takes S, then Inv_pq
+      __syncwarp();
+      double c0 = 0.0, c1 = 0.0;
+      tile_mm(H, i0 + 8 * p, i0 + 8 * p, true, i0 + 8 * p, i0 + 8 * q, false, -1.0, c0, c1);   // -X_p S
+      __syncwarp();
+      tile_store(H, i0 + 8 * p, i0 + 8 * q, c0, c1);
+      __syncwarp();
+    }
+  }
+}
+
+// L' x = w for the two right-hand sides in rows N and N + 1 (same contract as backsolve_inv; xs: 64 doubles of scratch).
+__device__ __forceinline__ void backsolve32(double *H, int N, double *xs) {
+  const int tid = threadIdx.x, w = tid >> 5;
+  const int nfull = N >> 5;                      // 32-row blocks made of full tiles
+  for (int b = w; b < nfull; b += IPM_NW) invert_block32(H, 32 * b);
+  __syncthreads();
+  double *b0 = H + tri(N), *b1 = H + tri(N + 1);
+  const int half = tid / (IPM_NT / 2), kk = tid % (IPM_NT / 2);
+  double *bh = half ? b1 : b0;
+  // ragged tail: 8-row blocks above the last full 32-block
+  const int nblk = (N + 7) >> 3;
+  for (int blk = nblk - 1; blk >= 4 * nfull; --blk) {
+    const int i0 = blk << 3, nb = min(8, N - i0);
+    if (tid < 16) {
+      const int rhs = tid >> 3, c = tid & 7;
+      const double *bb_ = rhs ? b1 : b0;
+      double xc = 0.0;
+      if (c < nb) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (k < nb && k >= c) xc = fma(H[tri(i0 + k) + i0 + c], bb_[i0 + k], xc);
+      }
+      xs[tid] = xc;
+    }
+    __syncthreads();
+    if (kk < i0) {
+      double v = bh[kk];
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        if (c < nb) v = fma(-H[tri(i0 + c) + kk], xs[half * 8 + c], v);
+      bh[kk] = v;
+    } else if (kk < i0 + nb) {
+      bh[kk] = xs[half * 8 + (kk - i0)];
+    }
+    __syncthreads();
+  }
+  // full blocks: LPD lanes per dot product (64 dot products: 32 entries x 2 right-hand sides)
+  // (four lanes per dot product in BOTH builds of the kernel: the 256- and the 512-thread variant must sum in the same order,
+  // results are bit-identical whichever one a launch picks)
+  constexpr int LPD = 4;
+  const int dot = tid / LPD, part = tid % LPD;   // dot = rhs * 32 + c
+  const int drhs = (dot >> 5) & 1, dc = dot & 31;
+  for (int b = nfull - 1; b >= 0; --b) {
+    const int i0 = 32 * b;
+    if (tid < 64 * LPD) {
+      const double *wv = drhs ? b1 : b0;
+      double a = 0.0;
+#pragma unroll
+      for (int u = 0; u < 32 / LPD; ++u) {
+        const int k = part + LPD * u;            // x[c] = sum_{k >= c} Inv[k][c] w[k]
+        if (k >= dc) a = fma(H[tri(i0 + k) + i0 + dc], wv[i0 + k], a);
+      }
+#pragma unroll
+      for (int o = LPD / 2; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if (part == 0) xs[dot] = a;
+    }
+    __syncthreads();
+    if (kk < i0) {
+      double v0 = bh[kk], v1 = 0.0, v2 = 0.0, v3 = 0.0;
+      const double *xv = xs + half * 32;
+#pragma unroll
+      for (int c = 0; c < 32; c += 4) {
+        v0 = fma(-H[tri(i0 + c) + kk], xv[c], v0);
+        v1 = fma(-H[tri(i0 + c + 1) + kk], xv[c + 1], v1);
+        v2 = fma(-H[tri(i0 + c + 2) + kk], xv[c + 2], v2);
+        v3 = fma(-H[tri(i0 + c + 3) + kk], xv[c + 3], v3);
+      }
+      bh[kk] = (v0 + v1) + (v2 + v3);
+    } else if (kk < i0 + 32) {
+      bh[kk] = xs[half * 32 + (kk - i0)];
+    }
+    __syncthreads();
+  }
+}
+
 // ---- bulk asynchronous copies (TMA, cp.async.bulk) global -> shared memory, completion on an mbarrier
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
@@ -370,10 +495,13 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
       if (M.qidx[k] >= 0) { qfn[c] = k; qblk[c] = M.qidx[k]; ++c; }
     s_nqf = c;
   }
+#pragma unroll 1
   for (int k = tid; k <= m; k += IPM_NT) du[k] = 0.0;
   // rows that go through the staged DMMA updates of J' Sigma J (the sparse linear rows are scattered entry by entry)
   const int Rd = M.Rd;
+#pragma unroll 1
   for (int r = tid; r < Rd; r += IPM_NT) drow[r] = M.dense_rows[r];
+#pragma unroll 1
   for (int r = tid; r < M.Rs; r += IPM_NT) drow[Rd + r] = M.sp_rows[r];
   __syncthreads();
   const int nqf = s_nqf;
@@ -446,12 +574,14 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
   // to at least warm_push, slacks pushed by warm_push; a phase switch restarts from unit multipliers
   auto init_slacks_mults = [&](bool warm) {
     const double *d0w = (warm && A.DUAL0) ? A.DUAL0 + (size_t)child * A.dual0_stride : nullptr;
+#pragma unroll 1
     for (int r = tid; r < R; r += IPM_NT) {
       const int fn = M.row_fn[r];
       const double h = fsc[r] * val[fn] - (phase1 ? x[n] : 0.0);
       s[r] = fmax(bb[r] - h, (d0w ? o.warm_push : o.bound_push) * fmax(1.0, fabs(bb[r])));
       v[r] = d0w ? fmax(o.warm_push, fmax(0.0, (fsc[r] > 0 ? 1.0 : -1.0) * d0w[2 * n + fn - 1]) * sf / fabs(fsc[r])) : 1.0;
     }
+#pragma unroll 1
     for (int j = tid; j < N; j += IPM_NT) {
       const int f = flg[j];
       const bool w = d0w && j < n;
@@ -482,6 +612,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
     theta_init = -1.0; mu_cap = -1.0; delta_w_last = 0.0; delta_w = 0.0;
     th_hist[0] = th_hist[1] = th_hist[2] = th_hist[3] = 0.0; a_last0 = a_last1 = 1.0; nfact = 0;
     double acc0 = 0.0, acc1 = 0.0, bw = 0.0;
+#pragma unroll 1
     for (int j = tid; j < N; j += IPM_NT) {
       int f = 0;
       double xx;
@@ -518,11 +649,13 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
     all_fixed = !inconsistent && r3[1] <= 1e-5;
     badw = r3[2];
     if (inconsistent) {
+#pragma unroll 1
       for (int j = tid; j < n; j += IPM_NT) {
         const double lo = fmin(xl[j], xu[j]), hi = fmax(xl[j], xu[j]);
         x[j] = fmin(fmax(x0[j], lo), hi);
       }
     } else if (all_fixed) {
+#pragma unroll 1
       for (int j = tid; j < n; j += IPM_NT) x[j] = xl[j];
     }
     __syncthreads();
@@ -558,6 +691,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
     __syncthreads();
     if (inconsistent || all_fixed) {
       double t = 0.0, infe = 0.0;
+#pragma unroll 1
       for (int i = tid; i < m; i += IPM_NT) {
         const double g = val[i + 1];
         if (M.gu[i] < kInfD) t = fmax(t, g - M.gu[i]);
@@ -581,6 +715,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
     }
     __syncthreads();
     sf = wq[0];
+#pragma unroll 1
     for (int r = tid; r < R; r += IPM_NT) {
       const int fn = M.row_fn[r];
       const double sc = wq[fn], sg = M.row_sgn[r];
@@ -597,6 +732,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
     __syncthreads();
     if (status == ST_provenInfeasible && !(inconsistent || all_fixed)) {
       double t[1] = {0.0};
+#pragma unroll 1
       for (int i = tid; i < m; i += IPM_NT) {
         const double g = val[i + 1];
         if (M.gu[i] < kInfD) t[0] = fmax(t[0], g - M.gu[i]);
@@ -612,13 +748,18 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
     }
     if (A.X) for (int j = tid; j < n; j += IPM_NT)
       A.X[(size_t)child * n + j] = all_fixed ? xl[j] : fmin(fmax(x[j], fmin(xl[j], xu[j])), fmax(xl[j], xu[j]));
-    if (A.G) for (int i = tid; i < m; i += IPM_NT) A.G[(size_t)child * m + i] = val[i + 1];
+    if (A.G) {
+#pragma unroll 1
+      for (int i = tid; i < m; i += IPM_NT) A.G[(size_t)child * m + i] = val[i + 1];
+    }
     if (A.DUALS) {
       double *D = A.DUALS + (size_t)child * (2 * n + m);
+#pragma unroll 1
       for (int j = tid; j < n; j += IPM_NT) {
         D[j] = with_duals ? zL[j] / sf : 0.0;
         D[n + j] = with_duals ? zU[j] / sf : 0.0;
       }
+#pragma unroll 1
       for (int i = tid; i < m; i += IPM_NT) {
         double lam = 0.0;
         if (with_duals) {
@@ -650,6 +791,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
     if (use_tma && Rd > 0) tma_issue(0);
     D2_START();
     double th_p = 0, sumv_p = 0, cs_p = 0, vl1_p = 0, ci_p = 0, cv_p = 0, cvu_p = 0, vmax_p = 0, viol_p = -1e300;
+#pragma unroll 1
     for (int r = tid; r < R; r += IPM_NT) {
       const double hraw = fsc[r] * val[M.row_fn[r]];
       const double res = hraw - tcur + s[r] - bb[r];
@@ -801,6 +943,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
     D2_MARK(2);
     // sweep over variables: Lagrangian gradient, right-hand sides (into the augmented rows), Sigma_x
     double di_p = 0, sumz_p = 0, nz_p = 0;
+#pragma unroll 1
     for (int j = tid; j < N; j += IPM_NT) {   // N <= IPM_NT: one variable per thread, jv/a0/a1 belong to j = tid
       const int f = flg[j];
       double r0v = 0.0, r1v = 0.0, sx = 0.0;
@@ -911,6 +1054,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
     }
     if (state == CS_NEED_CHILD) state = (cta < Gc && setup_child()) ? CS_INIT : CS_IDLE;
     // publish the Hessian weights (zero unless iterating) and, when initialising, the point to evaluate
+#pragma unroll 1
     for (int qi = tid; qi < nqpad; qi += IPM_NT) {
       double w = 0.0;
       if (state == CS_ITER && qi < nqf) {
@@ -923,6 +1067,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
       __stcg(CB.xw + (size_t)cta * nqpad + qi, w);
     }
     if (state != CS_ITER)
+#pragma unroll 1
       for (int j = tid; j < ldd; j += IPM_NT) __stcg(CB.xd + (size_t)cta * ldd + j, (state == CS_INIT && j < n) ? x[j] : 0.0);
     if (tid == 0) atomicAdd(&CB.idle_cnt[step & 1], state == CS_IDLE ? 1 : 0);
     if constexpr (TIMERS) {      // length of the per-child segment between barrier 4 and barrier 1, by the state it started in
@@ -1004,6 +1149,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
     if (state == CS_FINISH) {
       write_results();
       state = setup_child() ? CS_INIT : CS_IDLE;   // (only CTAs below Gc ever get here)
+#pragma unroll 1
       for (int j = tid; j < ldd; j += IPM_NT) __stcg(CB.xd + (size_t)cta * ldd + j, (state == CS_INIT && j < n) ? x[j] : 0.0);
     } else if (state == CS_ITER) {
       const double of = it_of;
@@ -1031,6 +1177,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
         else if (t > j) H[tri(t) + j] = 0.0;
       }
       __syncthreads();
+#pragma unroll 1
       for (int j = tid; j < N; j += IPM_NT) {
         if (flg[j] & F_FIXED) H[tri(j) + j] = 1.0;
         else H[tri(j) + j] += Sx[j] + delta_w;
@@ -1048,6 +1195,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
         else delta_w *= (delta_w_last == 0.0 ? 100.0 : 8.0);
         retry = true;
         if (delta_w > 1e20 || ++fact_attempts > 45) { status = ST_computationError; objv = val[0]; with_duals = true; }
+#pragma unroll 1
         for (int j = tid; j < N; j += IPM_NT) dx[j] = 0.0;
         __syncthreads();
       } else {
@@ -1055,12 +1203,17 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
         delta_w = 0.0; fact_attempts = 0;
         PH_MARK(3);
         D2_START();
+#ifdef BNLP_OLD_BACKSOLVE
         backsolve_inv(H, N, red);
+#else
+        backsolve32(H, N, red);
+#endif
         D2_MARK(4);
         // (requesting two whole rows per warp up front — sixteen loads in flight per lane — was measured: the phase itself gets
         // shorter, the kernel 4 % slower; the register arrays cost more elsewhere than the exposed L2 round trips do here)
         dots_grad(M, grad, d0, d1, gd0, gd1);
         D2_MARK(5);
+#pragma unroll 1
         for (int r = tid; r < R; r += IPM_NT) {
           const int fn = M.row_fn[r];
           jd0[r] = fsc[r] * gd0[fn] - d0[n];
@@ -1069,6 +1222,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
         __syncthreads();
         auto ftb = [&](double mu, double tau, double &ap, double &ad) {
           double mn[2] = {-1.0, -1.0};
+#pragma unroll 1
           for (int j = tid; j < N; j += IPM_NT) {
             const int f = flg[j];
             if (f & F_FIXED) continue;
@@ -1088,6 +1242,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
           }
           // (rows go to the threads at the top of the CTA, variables to those at the bottom: the chain of FP64 divisions a
           // thread runs is the critical path of this pass; a max-reduction does not care who holds what)
+#pragma unroll 1
           for (int r = IPM_NT - 1 - tid; r < R; r += IPM_NT) {
             const double dsr = -rc[r] - (jd0[r] + mu * jd1[r]);
             const double dvr = mu / s[r] - v[r] - Ss[r] * dsr;
@@ -1097,11 +1252,16 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
           block_reduce<0, 2>(mn, red);
           ap = fmin(1.0, -mn[0]); ad = fmin(1.0, -mn[1]);
         };
-        double mu;
-        {
-          double ap, ad;
-          ftb(0.0, 1.0, ap, ad);
+        // the fraction-to-the-boundary pass is instantiated ONCE and run twice (affine step: mu = 0, tau = 1; then the real
+        // step): every inlined copy of these loops is instructions the SM has to fetch again each iteration
+        double mu = 0.0, tau = 1.0, ap_max = 1.0, ad = 1.0;
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+          double ap;
+          ftb(mu, tau, ap, ad);
+          if (pass == 1) { ap_max = ap; break; }
           double t[1] = {0.0};
+#pragma unroll 1
           for (int j = tid; j < N; j += IPM_NT) {
             const int f = flg[j];
             if (f & F_FIXED) continue;
@@ -1117,6 +1277,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
               t[0] += (su - ap * dxj) * (zU[j] + ad * dz);
             }
           }
+#pragma unroll 1
           for (int r = tid; r < R; r += IPM_NT) {
             const double dsr = -rc[r] - jd0[r];
             const double dvr = -v[r] - Ss[r] * dsr;
@@ -1128,22 +1289,24 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
           sigma = fmin(fmax(sigma, o.sigma_min), o.sigma_max);
           mu = fmin(fmax(sigma * it_avg_compl, o.mu_min), mu_cap);
           mu = fmax(mu, fmin(it_avg_compl, o.mu_safeguard * fmax(it_cviol, it_dual_inf / it_s_d)));
+          tau = fmax(o.tau_min, 1.0 - mu);
         }
-        const double tau = fmax(o.tau_min, 1.0 - mu);
-        double ap_max, ad;
-        ftb(mu, tau, ap_max, ad);
         it_mu = mu; it_ap_max = ap_max; it_ad = ad;
         D2_MARK(6);
+#pragma unroll 1
         for (int j = tid; j < N; j += IPM_NT) dx[j] = (flg[j] & F_FIXED) ? 0.0 : d0[j] + mu * d1[j];
+#pragma unroll 1
         for (int r = tid; r < R; r += IPM_NT) {
           ds[r] = -rc[r] - (jd0[r] + mu * jd1[r]);
           dv[r] = mu / s[r] - v[r] - Ss[r] * ds[r];
         }
+#pragma unroll 1
         for (int k = tid; k <= m; k += IPM_NT) gd0[k] = gd0[k] + mu * gd1[k];
         __syncthreads();
         D2_MARK(7);
       }
       (void)of;
+#pragma unroll 1
       for (int j = tid; j < ldd; j += IPM_NT) __stcg(CB.xd + (size_t)cta * ldd + j, j < n ? dx[j] : 0.0);
     }
     PH_MARK(4);
@@ -1246,6 +1409,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
       auto merit = [&](double a, double &theta, double &phi) {
         double t2[2] = {0.0, 0.0};
         const double t = tcur + a * dxt;
+#pragma unroll 1
         for (int r = tid; r < R; r += IPM_NT) {
           const int fn = M.row_fn[r];
           const double hv = fsc[r] * (val[fn] + a * gd0[fn] + 0.5 * a * a * du[fn]) - t;
@@ -1253,6 +1417,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
           t2[0] += fabs(hv + sv - bb[r]);
           t2[1] -= mu * log(sv);
         }
+#pragma unroll 1
         for (int j = tid; j < N; j += IPM_NT) {
           const int f = flg[j];
           if (f & F_FIXED) continue;
@@ -1264,12 +1429,12 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
         theta = t2[0];
         phi = t2[1] + (phase1 ? t : sf * (val[0] + a * gd0[0] + 0.5 * a * a * du[0]));
       };
-      double theta0, phi0;
-      merit(0.0, theta0, phi0);
       double dphi;
       {
         double t[1] = {0.0};
+#pragma unroll 1
         for (int r = tid; r < R; r += IPM_NT) t[0] -= mu * ds[r] / s[r];
+#pragma unroll 1
         for (int j = tid; j < N; j += IPM_NT) {
           const int f = flg[j];
           if (f & F_FIXED) continue;
@@ -1281,17 +1446,22 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
       }
       const double theta_min = o.theta_min_fact * fmax(1.0, theta_init);
       const double theta_max = o.theta_max_fact * fmax(1.0, theta_init);
-      double amin = o.gamma_theta;
-      if (dphi < 0) {
-        amin = fmin(amin, o.gamma_phi * theta0 / (-dphi));
-        if (theta0 <= theta_min) amin = fmin(amin, o.delta * pow(theta0, o.s_theta) / pow(-dphi, o.s_phi));
-      }
-      amin *= o.alpha_min_frac;
+      double amin = o.gamma_theta, theta0 = 0.0, phi0 = 0.0;
       double alpha = ap_max;
       bool accepted = false;
-      for (int bt = 0; bt < 60; ++bt) {
+#pragma unroll 1
+      for (int bt = -1; bt < 60; ++bt) {       // bt = -1: the merit function at the current point (ONE inlined copy of merit)
         double th_t, ph_t;
-        merit(alpha, th_t, ph_t);
+        merit(bt < 0 ? 0.0 : alpha, th_t, ph_t);
+        if (bt < 0) {
+          theta0 = th_t; phi0 = ph_t;
+          if (dphi < 0) {
+            amin = fmin(amin, o.gamma_phi * theta0 / (-dphi));
+            if (theta0 <= theta_min) amin = fmin(amin, o.delta * pow(theta0, o.s_theta) / pow(-dphi, o.s_phi));
+          }
+          amin *= o.alpha_min_frac;
+          continue;
+        }
         const double fuzz = 10.0 * 2.220446049250313e-16 * fabs(phi0);
         const bool sw = dphi < 0 && theta0 <= theta_min && alpha * pow(-dphi, o.s_phi) > o.delta * pow(theta0, o.s_theta);
         bool ok;
@@ -1323,6 +1493,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
       a_last1 = a_last0; a_last0 = alpha;
       PH_MARK(6);
       __syncthreads();
+#pragma unroll 1
       for (int j = tid; j < N; j += IPM_NT) {
         const int f = flg[j];
         if (f & F_FIXED) continue;
@@ -1343,11 +1514,13 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_coop_kernel(DevModel
         }
         x[j] = xn;
       }
+#pragma unroll 1
       for (int r = tid; r < R; r += IPM_NT) {
         const double sn = s[r] + alpha * ds[r];
         s[r] = sn;
         v[r] = fmin(fmax(v[r] + ad * dv[r], mu / (o.kappa_sigma * sn)), o.kappa_sigma * mu / sn);
       }
+#pragma unroll 1
       for (int k = tid; k <= m; k += IPM_NT) val[k] += alpha * gd0[k] + 0.5 * alpha * alpha * du[k];
       for (int qi = wid; qi < nqf; qi += IPM_NW) {        // one row per warp, sixteen loads in flight per lane
         const int k = qfn[qi];
