@@ -574,6 +574,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
       if (M.qidx[k] >= 0 && !fn_is_lowrank(M, k, TM)) qfn[c++] = k;
     s_nqf = c;
   }
+#pragma unroll 1
   for (int k = tid; k <= m; k += IPM_NT) du[k] = 0.0;
   __syncthreads();
   const int nqf = s_nqf;
@@ -592,6 +593,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
     // ------------------------------------------------------------------ bounds, fixed variables, start point
     double acc2[2] = {0.0, 0.0};  // [0] sum inconsistent, [1] max width
     double badw = 0.0;
+#pragma unroll 1
     for (int j = tid; j < N; j += IPM_NT) {
       int f = 0;
       double l, u, xx;
@@ -630,11 +632,13 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
     const bool inconsistent = acc2[0] > 0.0;
     const bool all_fixed = !inconsistent && acc2[1] <= 1e-5;
     if (inconsistent) {  // evaluate at the start point clipped into the (crossed) box
+#pragma unroll 1
       for (int j = tid; j < n; j += IPM_NT) {
         const double lo = fmin(xl[j], xu[j]), hi = fmax(xl[j], xu[j]);
         x[j] = fmin(fmax(x0[j], lo), hi);
       }
     } else if (all_fixed) {
+#pragma unroll 1
       for (int j = tid; j < n; j += IPM_NT) x[j] = xl[j];
     }
     __syncthreads();
@@ -667,6 +671,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
     // Accumulation order is fixed: thread k walks the terms of function k in tape order (M.fn_term_list).
     auto terms_remove = [&]() {
       if (NTm == 0) return;
+#pragma unroll 1
       for (int k = tid; k <= m; k += IPM_NT) {
         for (int e = M.fn_term_start[k]; e < M.fn_term_start[k + 1]; ++e) {
           const int t = M.fn_term_list[e], v0 = M.term_var_start[t], nv = M.term_var_start[t + 1] - v0;
@@ -690,6 +695,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
         for (int a = 0; a < nv * (nv + 1) / 2; ++a) rec[1 + TV + a] = r.h[a];
       }
       __syncthreads();
+#pragma unroll 1
       for (int k = tid; k <= m; k += IPM_NT) {
         double tv = 0.0;
         for (int e = M.fn_term_start[k]; e < M.fn_term_start[k + 1]; ++e) {
@@ -716,6 +722,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
       // all-variables-fixed short cut (BonTNLPSolver.cpp:78-161) / trivially infeasible crossed bounds
       double t[1] = {0.0};
       double infe = 0.0;
+#pragma unroll 1
       for (int i = tid; i < m; i += IPM_NT) {
         const double g = val[i + 1];
         if (M.gu[i] < kInfD) t[0] = fmax(t[0], g - M.gu[i]);
@@ -751,6 +758,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
       }
       __syncthreads();
       sf = wq[0];
+#pragma unroll 1
       for (int r = tid; r < R; r += IPM_NT) {
         const int fn = M.row_fn[r];
         const double sc = wq[fn], sg = M.row_sgn[r];
@@ -758,6 +766,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
         fsc[r] = sc * sg;
         bb[r] = b + o.bound_relax * fmax(1.0, fabs(b));
       }
+#pragma unroll 1
       for (int e = tid; e < E; e += IPM_NT) esc[e] = wq[M.eq_fn[e]];
       __syncthreads();
     }
@@ -767,18 +776,21 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
     // pushed to at least warm_push, slacks pushed by warm_push; a phase switch restarts from unit multipliers
     auto init_slacks_mults = [&](bool warm) {
       const double *d0w = (warm && A.DUAL0) ? A.DUAL0 + (size_t)child * A.dual0_stride : nullptr;
+#pragma unroll 1
       for (int r = tid; r < R; r += IPM_NT) {
         const int fn = M.row_fn[r];
         const double h = fsc[r] * val[fn] - (phase1 ? x[n] : 0.0);
         s[r] = fmax(bb[r] - h, (d0w ? o.warm_push : o.bound_push) * fmax(1.0, fabs(bb[r])));
         v[r] = d0w ? fmax(o.warm_push, fmax(0.0, (fsc[r] > 0 ? 1.0 : -1.0) * d0w[2 * n + fn - 1]) * sf / fabs(fsc[r])) : 1.0;
       }
+#pragma unroll 1
       for (int j = tid; j < N; j += IPM_NT) {
         const int f = flg[j];
         const bool w = d0w && j < n;
         zL[j] = (!(f & F_FIXED) && (f & F_HASL)) ? (w ? fmax(o.warm_push, d0w[j] * sf) : 1.0) : 0.0;
         zU[j] = (!(f & F_FIXED) && (f & F_HASU)) ? (w ? fmax(o.warm_push, d0w[n + j] * sf) : 1.0) : 0.0;
       }
+#pragma unroll 1
       for (int e = tid; e < E; e += IPM_NT) ye[e] = d0w ? d0w[2 * n + M.eq_fn[e] - 1] * sf / esc[e] : 0.0;
       __syncthreads();
     };
@@ -792,6 +804,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
       // sweep 1 over rows: rc, Ss, sums
       double a9[9];  // sums: th, sum_v, compl_sum(rows); max: compl_inf, cviol, cviol_unsc, vmax, viol_max ; sum viol_l1
       double th_p = 0, sumv_p = 0, cs_p = 0, vl1_p = 0, ci_p = 0, cv_p = 0, cvu_p = 0, vmax_p = 0, viol_p = -1e300;
+#pragma unroll 1
       for (int r = tid; r < R; r += IPM_NT) {
         const double hraw = fsc[r] * val[M.row_fn[r]];
         const double res = hraw - tcur + s[r] - bb[r];
@@ -808,6 +821,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
         viol_p = fmax(viol_p, hraw - bb[r]);
       }
       double sumye_p = 0.0;
+#pragma unroll 1
       for (int e = tid; e < E; e += IPM_NT) {
         const double res = esc[e] * (val[M.eq_fn[e]] - M.eq_bnd[e]);
         ce[e] = res;
@@ -820,6 +834,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
       __syncthreads();
       // sweep 2 over variables: gradient of the Lagrangian (J' v), rhs vectors, Sigma_x
       double di_p = 0, sumz_p = 0, nz_p = 0;
+#pragma unroll 1
       for (int j = tid; j < N; j += IPM_NT) {
         const int f = flg[j];
         double r0 = 0.0, r1 = 0.0, sx = 0.0;
@@ -934,6 +949,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
 
       PH_MARK(0);
       // ---------------------------------------------------------------- condensed matrix + factorisation
+#pragma unroll 1
       for (int k = tid; k <= m; k += IPM_NT) {
         double w = (k == 0) ? of : 0.0;
         const int ru = M.fn_row_up[k], rl = M.fn_row_lo[k];
@@ -1000,11 +1016,13 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
           }
           // elastic row (tile-major: also the corner of the carried rows, so that nothing uninitialised is ever loaded)
           if (TM) {
+#pragma unroll 1
             for (int k = tid; k <= n; k += IPM_NT) H[tm_idx(TL, n, k)] = 0.0;
             const int nx = 2 + E;
             for (int q = tid; q < nx * nx; q += IPM_NT)
               if (q % nx <= q / nx) H[tm_idx(TL, N + q / nx, N + q % nx)] = 0.0;
           } else {
+#pragma unroll 1
             for (int k = tid; k <= n; k += IPM_NT) H[tri(n) + k] = 0.0;
           }
         }
@@ -1028,6 +1046,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
           else if (t > j) H[TM ? tm_idx(TL, t, j) : tri(t) + j] = 0.0;
         }
         __syncthreads();
+#pragma unroll 1
         for (int j = tid; j < N; j += IPM_NT) {
           double *hjj = H + (TM ? tm_idx(TL, j, j) : tri(j) + j);
           if (flg[j] & F_FIXED) *hjj = 1.0;
@@ -1077,9 +1096,11 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
             __syncthreads();
           }
           // the carried rows: the two right-hand sides and the equality rows A_e (after the factorisation Y_e = L^-1 A_e')
+#pragma unroll 1
           for (int j = tid; j < N; j += IPM_NT) { H[tm_idx(TL, N, j)] = d0[j]; H[tm_idx(TL, N + 1, j)] = d1[j]; }
           for (int e = 0; e < E; ++e) {
             const double *g = grow(M, grad, M.eq_fn[e]);
+#pragma unroll 1
             for (int j = tid; j < N; j += IPM_NT) H[tm_idx(TL, N + 2 + e, j)] = (j < n && !(flg[j] & F_FIXED)) ? esc[e] * g[j] : 0.0;
           }
         } else {
@@ -1103,6 +1124,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
         for (int e = 0; e < E; ++e) {
           double *Ye = H + tri(N + 2 + e);
           const double *g = grow(M, grad, M.eq_fn[e]);
+#pragma unroll 1
           for (int j = tid; j < N; j += IPM_NT) Ye[j] = (j < n && !(flg[j] & F_FIXED)) ? esc[e] * g[j] : 0.0;
         }
         }
@@ -1128,6 +1150,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
         if (delta_w > 1e20) break;
         __syncthreads();
         // the failed factorisation destroyed the right-hand sides: rebuild them
+#pragma unroll 1
         for (int j = tid; j < N; j += IPM_NT) {
           const int f = flg[j];
           double r0 = 0.0, r1 = 0.0;
@@ -1203,6 +1226,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
         }
         __syncthreads();
         if (s_fail) { status = ST_computationError; objv = val[0]; with_duals = true; done = true; break; }
+#pragma unroll 1
         for (int j = tid; j < N; j += IPM_NT) {
           double *p0 = TM ? H + tm_idx(TL, N, j) : d0 + j, *p1 = TM ? H + tm_idx(TL, N + 1, j) : d1 + j;
           double w0 = *p0, w1 = *p1;
@@ -1217,6 +1241,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
 
       // ---------------------------------------------------------------- J d0, J d1 per row
       dots_grad(M, grad, d0, d1, gd0, gd1);
+#pragma unroll 1
       for (int r = tid; r < R; r += IPM_NT) {
         const int fn = M.row_fn[r];
         jd0[r] = fsc[r] * gd0[fn] - d0[n];
@@ -1228,6 +1253,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
       // fraction-to-the-boundary + (optional) complementarity at the trial point
       auto ftb = [&](double mu, double tau, double &ap, double &ad) {
         double mn[2] = {-1.0, -1.0};  // max of -alpha  => min alpha
+#pragma unroll 1
         for (int j = tid; j < N; j += IPM_NT) {
           const int f = flg[j];
           if (f & F_FIXED) continue;
@@ -1245,6 +1271,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
             if (dz < 0) mn[1] = fmax(mn[1], -(-tau * zU[j] / dz));
           }
         }
+#pragma unroll 1
         for (int r = tid; r < R; r += IPM_NT) {
           const double dsr = -rc[r] - (jd0[r] + mu * jd1[r]);
           const double dvr = mu / s[r] - v[r] - Ss[r] * dsr;
@@ -1260,6 +1287,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
         double ap, ad;
         ftb(0.0, 1.0, ap, ad);
         double t[1] = {0.0};
+#pragma unroll 1
         for (int j = tid; j < N; j += IPM_NT) {
           const int f = flg[j];
           if (f & F_FIXED) continue;
@@ -1275,6 +1303,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
             t[0] += (su - ap * dxj) * (zU[j] + ad * dz);
           }
         }
+#pragma unroll 1
         for (int r = tid; r < R; r += IPM_NT) {
           const double dsr = -rc[r] - jd0[r];
           const double dvr = -v[r] - Ss[r] * dsr;
@@ -1291,16 +1320,20 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
       double ap_max, ad;
       ftb(mu, tau, ap_max, ad);
       // final direction
+#pragma unroll 1
       for (int j = tid; j < N; j += IPM_NT) dx[j] = (flg[j] & F_FIXED) ? 0.0 : d0[j] + mu * d1[j];
+#pragma unroll 1
       for (int r = tid; r < R; r += IPM_NT) {
         ds[r] = -rc[r] - (jd0[r] + mu * jd1[r]);
         dv[r] = mu / s[r] - v[r] - Ss[r] * ds[r];
       }
+#pragma unroll 1
       for (int k = tid; k <= m; k += IPM_NT) gd0[k] = gd0[k] + mu * gd1[k];   // gd = grad_k . dx
       __syncthreads();
       const double gd_obj_total = gd0[0];   // directional derivative of f uses the total gradient
       if (NTm > 0) {   // the closed-form trial values use the quadratic part only: remove the terms' share of grad.dx
         __syncthreads();
+#pragma unroll 1
         for (int kf = tid; kf <= m; kf += IPM_NT) {
           double acc = 0.0;
           for (int e = M.fn_term_start[kf]; e < M.fn_term_start[kf + 1]; ++e) {
@@ -1325,6 +1358,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
         double t2[2] = {0.0, 0.0};
         const double t = tcur + a * dxt;
         if (NTm > 0) {   // element terms at the trial point (values only); Sx is free here and holds x + a dx
+#pragma unroll 1
           for (int j = tid; j < n; j += IPM_NT) Sx[j] = x[j] + a * dx[j];
           __syncthreads();
           HDual st[TS];
@@ -1334,6 +1368,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
             tgl[(size_t)tt * TREC + TREC - 1] = r.v;       // trial value, summed per function in tape order below
           }
           __syncthreads();
+#pragma unroll 1
           for (int k = tid; k <= m; k += IPM_NT) {
             double tv = -tval[k];
             for (int e = M.fn_term_start[k]; e < M.fn_term_start[k + 1]; ++e) tv += tgl[(size_t)M.fn_term_list[e] * TREC + TREC - 1];
@@ -1341,6 +1376,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
           }
           __syncthreads();
         }
+#pragma unroll 1
         for (int r = tid; r < R; r += IPM_NT) {
           const int fn = M.row_fn[r];
           const double hv = fsc[r] * (val[fn] + a * gd0[fn] + 0.5 * a * a * du[fn] + (NTm > 0 ? tvt[fn] : 0.0)) - t;
@@ -1348,10 +1384,12 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
           t2[0] += fabs(hv + sv - bb[r]);
           t2[1] -= mu * log(sv);
         }
+#pragma unroll 1
         for (int e = tid; e < E; e += IPM_NT) {
           const int fn = M.eq_fn[e];
           t2[0] += fabs(esc[e] * (val[fn] + a * gd0[fn] + 0.5 * a * a * du[fn] + (NTm > 0 ? tvt[fn] : 0.0) - M.eq_bnd[e]));
         }
+#pragma unroll 1
         for (int j = tid; j < N; j += IPM_NT) {
           const int f = flg[j];
           if (f & F_FIXED) continue;
@@ -1368,7 +1406,9 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
       double dphi;
       {
         double t[1] = {0.0};
+#pragma unroll 1
         for (int r = tid; r < R; r += IPM_NT) t[0] -= mu * ds[r] / s[r];
+#pragma unroll 1
         for (int j = tid; j < N; j += IPM_NT) {
           const int f = flg[j];
           if (f & F_FIXED) continue;
@@ -1414,6 +1454,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
       // ---------------------------------------------------------------- accept the step
       __syncthreads();
       terms_remove();
+#pragma unroll 1
       for (int j = tid; j < N; j += IPM_NT) {
         const int f = flg[j];
         if (f & F_FIXED) continue;
@@ -1434,17 +1475,21 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
         }
         x[j] = xn;
       }
+#pragma unroll 1
       for (int r = tid; r < R; r += IPM_NT) {
         const double sn = s[r] + alpha * ds[r];
         s[r] = sn;
         v[r] = fmin(fmax(v[r] + ad * dv[r], mu / (o.kappa_sigma * sn)), o.kappa_sigma * mu / sn);
       }
+#pragma unroll 1
       for (int e = tid; e < E; e += IPM_NT) ye[e] += alpha * (de0[e] + mu * de1[e]);
+#pragma unroll 1
       for (int k = tid; k <= m; k += IPM_NT) val[k] += alpha * gd0[k] + 0.5 * alpha * alpha * du[k];
       for (int k = 0; k <= m; ++k) {
         if (M.qidx[k] < 0) continue;
         double *g = grad + (size_t)k * n;
         const double *u = uq + (size_t)k * n;
+#pragma unroll 1
         for (int j = tid; j < n; j += IPM_NT) g[j] += alpha * u[j];
       }
       __syncthreads();
@@ -1457,6 +1502,7 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
     __syncthreads();
     if (status == ST_provenInfeasible && !(inconsistent || all_fixed)) {
       double t[1] = {0.0};
+#pragma unroll 1
       for (int i = tid; i < m; i += IPM_NT) {
         const double g = val[i + 1];
         if (M.gu[i] < kInfD) t[0] = fmax(t[0], g - M.gu[i]);
@@ -1476,10 +1522,12 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
     if (A.G) for (int i = tid; i < m; i += IPM_NT) A.G[(size_t)child * m + i] = val[i + 1];
     if (A.DUALS) {
       double *D = A.DUALS + (size_t)child * (2 * n + m);
+#pragma unroll 1
       for (int j = tid; j < n; j += IPM_NT) {
         D[j] = with_duals ? zL[j] / sf : 0.0;
         D[n + j] = with_duals ? zU[j] / sf : 0.0;
       }
+#pragma unroll 1
       for (int i = tid; i < m; i += IPM_NT) {
         double lam = 0.0;
         if (with_duals) {

@@ -1,10 +1,13 @@
 """Development aid: build variants of libbnlp.so that differ only in -D flags of the two cooperative-kernel translation
-units, for A/B measurements inside ONE gpurun call (box-to-box noise is ~4 %, larger than most single changes).
+units (and of the general kernel's), for A/B measurements inside ONE gpurun call (box-to-box noise is ~4 %, larger than most single changes).
   python scripts/dev_variants.py name1:-DFOO=1,-DBAR name2: ...      -> bonmin_b200/_ab/libbnlp_<name>.so
 Run a variant with BNLP_LIB=bonmin_b200/_ab/libbnlp_<name>.so."""
 import os, subprocess, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from bonmin_b200 import build as b
+
+VAR_SRC = ("bnlp_launch_coop.cu", "bnlp_launch_coop256.cu", "bnlp_launch_ipm.cu")   # the kernels' translation units
+
 
 def main():
     b.build()
@@ -15,11 +18,11 @@ def main():
         name, _, flags = spec.partition(":")
         flags = [f for f in flags.split(",") if f]
         objs = []
-        for src in ("bnlp_launch_coop.cu", "bnlp_launch_coop256.cu"):
+        for src in VAR_SRC:
             o = os.path.join(out, f"{name}_{src[:-3]}.o")
             objs.append(o)
             procs.append(subprocess.Popen(["nvcc"] + b.NVCC_FLAGS + flags + ["-c", os.path.join(b.CSRC, src), "-o", o]))
-        others = [b._obj_of(s) for s in b.SOURCES if s not in ("bnlp_launch_coop.cu", "bnlp_launch_coop256.cu")]
+        others = [b._obj_of(s) for s in b.SOURCES if s not in VAR_SRC]
         procs.append((name, objs + others))
     for p in procs:
         if isinstance(p, subprocess.Popen) and p.wait() != 0:
