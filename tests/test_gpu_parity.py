@@ -523,3 +523,53 @@ def test_c4_full_size_children_and_oa_rows(bnlp_lib, oracle_ipm):
             np.testing.assert_allclose(gc[2], rc[2], rtol=1e-11, atol=1e-13)
             assert gc[4] == pytest.approx(rc[4], rel=1e-11, abs=1e-11)
     eng.close()
+
+
+def test_sparse_linear_rows_in_the_cooperative_kernel(bnlp_lib, oracle_ipm, monkeypatch):
+    """Round 2: linear rows with few coefficients leave the staged rank-16 updates of the cooperative kernel (entries of
+    J' Sigma J scattered from slot-major lists, bnlp_api.cu build_ipm_view).  The model puts them where the lists are
+    stressed: sparse linear rows BEFORE the quadratic ones, ranged (two one-sided rows each), some that share columns, one
+    empty of structure but for a single coefficient; half of the children are infeasible, so the phase-1 elastic's row
+    and column are live.  Against the oracle, and against the same engine with every row staged (BNLP_SPARSE_ROW_MAX=0)."""
+    n, m_l, m_q = 120, 24, 10
+    rng = np.random.default_rng(6)
+    base = I.syn_miqcp(n, 40, m_q, 0, 99)
+    A = np.zeros((1 + m_l + m_q, n))
+    A[0] = base.A[0]
+    gl = np.full(m_l + m_q, -I.INF)
+    gu = np.zeros(m_l + m_q)
+    x0 = np.asarray(base.x0)
+    for i in range(m_l):                      # sparse linear rows first: 1 .. 14 coefficients, clustered columns
+        k = 1 if i == 0 else int(rng.integers(2, 15))
+        cols = rng.choice(30 if i % 3 == 0 else n, k, replace=False)
+        A[1 + i, cols] = rng.standard_normal(k)
+        act = A[1 + i] @ x0
+        gu[i] = act + rng.uniform(0.5, 1.5)
+        if i % 2 == 0:
+            gl[i] = act - rng.uniform(2.0, 4.0)                  # ranged
+    A[1 + m_l:] = base.A[1:]
+    gu[m_l:] = base.gu
+    mdl = I.StructuredModel(dict(base))
+    mdl.update(m=m_l + m_q, A=A, c=np.zeros(1 + m_l + m_q), gl=gl, gu=gu,
+               qd_fn=np.array([0] + [1 + m_l + i for i in range(m_q)], np.int32), name="sparse rows first, ranged")
+    eng = _engine(mdl)
+    root = eng.solve_batch(mdl.xl, mdl.xu, mdl.x0)
+    oroot = oracle_ipm.solve_batch(mdl, mdl.xl, mdl.xu, mdl.x0)
+    _compare(root, oroot)
+    xs = root["x"][0]
+    XL, XU = I.c3_children(mdl, xs, 320)
+    XL[::2, 40:60] = np.minimum(XL[::2, 40:60] + 3.0, XU[::2, 40:60])       # squeeze every other child: many infeasible
+    r = eng.solve_batch(XL, XU, xs)
+    o = oracle_ipm.solve_batch(mdl, XL, XU, xs, threads=8)
+    ok = _compare(r, o)
+    assert ok.sum() >= 40 and (o["status"] == 3).sum() >= 10
+    assert np.abs(r["iters"] - o["iters"]).max() <= 2
+    eng.close()
+    monkeypatch.setenv("BNLP_SPARSE_ROW_MAX", "0")
+    dense = _engine(mdl)
+    d = dense.solve_batch(XL, XU, xs)
+    monkeypatch.delenv("BNLP_SPARSE_ROW_MAX")
+    _compare(d, o)
+    rel = np.abs(d["obj"] - r["obj"]) / np.maximum(1.0, np.abs(r["obj"]))
+    assert rel[ok].max() <= 1e-9 and (d["status"] == r["status"]).all()
+    dense.close()
