@@ -98,7 +98,9 @@ struct Device {
   DBuf<double> e_dbl;
   // solve buffers
   DBuf<double> dXL, dXU, dX0, dOBJ, dX, dG, dD, dD0, ws, cxw, cW, cxd;
-  DBuf<double> xch;          // cooperative kernel: [ws | Wbuf | xd | xw] in ONE allocation (one L2 access-policy window covers it)
+  DBuf<double> xch;          // cooperative kernel: [ws | Wbuf | xd | xw | Qp | Qf] in ONE allocation (one L2 access-policy window covers it)
+  size_t xch_q_off = 0;
+  const double *xch_q_for = nullptr;   // xch.p the copies of the quadratic blocks behind the exchange buffers were made for (null: stale)
   size_t l2_persist_max = 0, l2_window_max = 0;
   DBuf<int> cidle;
   DBuf<int> dST, dIT, queue;
@@ -627,6 +629,7 @@ int engine_reload_values(bnlp_engine *Q, const HostModel &M) {
     if (old_q != V.qidx || old_r != V.row_fn) return 0;
     int bad = 0;
     bad |= upload(D.c, M.c); bad |= upload(D.A, V.A); bad |= upload(D.Qp, V.QpD); bad |= upload(D.Qf, V.Qf);
+    D.xch_q_for = nullptr;      // the copies behind the exchange buffers are stale
     bad |= upload(D.row_bnd, V.row_bnd); bad |= upload(D.eq_bnd, V.eq_bnd);
     bad |= upload(D.gl, M.gl); bad |= upload(D.gu, M.gu); bad |= upload(D.xl, M.xl); bad |= upload(D.xu, M.xu);
     // the sparse-row lists depend on which coefficients of A are non-zero: they follow the new numbers
@@ -691,12 +694,25 @@ static int launch_ipm(bnlp_engine *E, Device &D, int B, const double *dXL, const
   // per child and step at C3) and round 1's ncu showed half of that traffic going out to HBM (12 GB per 4096-child launch
   // against 36 MB of algorithmic bytes) although the whole working set is smaller than L2.
   const size_t ws_cnt = (size_t)ctas * E->ws_doubles;
-  size_t w_off = 0, xd_off = 0, xw_off = 0, xch_cnt = 0;
+  size_t w_off = 0, xd_off = 0, xw_off = 0, xch_cnt = 0, qp_off = 0, qf_off = 0;
   if (E->coop_ok) {
     auto up = [](size_t v) { return (v + 31) & ~(size_t)31; };   // 256-byte aligned pieces
     w_off = up(ws_cnt); xd_off = w_off + up((size_t)ctas * D.dm.ldp); xw_off = xd_off + up((size_t)ctas * E->ldd);
     xch_cnt = xw_off + up((size_t)ctas * E->nqpad);
+    // the quadratic blocks ride behind the exchange buffers (copies of D.Qp / D.Qf, which the evaluation kernels keep using):
+    // every step re-reads all of them, and beside 62 MB of persisting lines they were what the rest of L2 kept evicting
+    // (4.7 GB of DRAM reads per 4096-child launch against 20 MB of blocks)
+    static const bool q_in_window = getenv("BNLP_NO_Q_IN_WINDOW") == nullptr;
+    if (q_in_window) {
+      qp_off = xch_cnt; qf_off = qp_off + up((size_t)E->nq * D.dm.ldp);
+      xch_cnt = qf_off + up((size_t)E->nq * E->M.n * D.dm.ldq);
+    }
     if (D.xch.reserve(xch_cnt) || D.cidle.reserve(2)) { set_err("cooperative buffers: allocation failed"); return -1; }
+    if (q_in_window && (D.xch_q_for != D.xch.p || D.xch_q_off != qp_off)) {
+      CK(cudaMemcpyAsync(D.xch.p + qp_off, D.Qp.p, (size_t)E->nq * D.dm.ldp * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+      CK(cudaMemcpyAsync(D.xch.p + qf_off, D.Qf.p, (size_t)E->nq * E->M.n * D.dm.ldq * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+      D.xch_q_for = D.xch.p; D.xch_q_off = qp_off;
+    }
   } else if (D.ws.reserve(ws_cnt)) { set_err("workspace allocation failed"); return -1; }
   CK(cudaMemsetAsync(D.queue.p, 0, sizeof(int), stream));
   CK(cudaMemsetAsync(D.stats.p, 0, 12 * sizeof(long long), stream));
@@ -728,11 +744,17 @@ static int launch_ipm(bnlp_engine *E, Device &D, int B, const double *dXL, const
       av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
       av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
       windowed = E->l2_set_aside > 0 && cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &av) == cudaSuccess;
+      if (getenv("BNLP_L2_INFO"))
+        fprintf(stderr, "[bnlp] L2 window %.1f MB (exchange %.1f MB + quadratic blocks %.1f MB), set-aside %.1f MB of max %.1f MB, max window %.1f MB, hit ratio %.2f, %s\n",
+                av.accessPolicyWindow.num_bytes / 1e6, (qp_off ? qp_off : xch_cnt) * 8 / 1e6, qp_off ? (xch_cnt - qp_off) * 8 / 1e6 : 0.0,
+                E->l2_set_aside / 1e6, D.l2_persist_max / 1e6, D.l2_window_max / 1e6, av.accessPolicyWindow.hitRatio, windowed ? "on" : "off");
       cudaGetLastError();
     }
     cudaError_t le;
-    if (use256) le = bnlp_coop256_launch(a.phase_cycles != nullptr, ctas, E->coop_smem_bytes, stream, &D.dm, &a, &cb);
-    else le = ipm_coop_launch(a.phase_cycles != nullptr, ctas, E->coop_smem_bytes, stream, D.dm, a, cb);
+    DevModel dmc = D.dm;
+    if (qp_off) { dmc.Qp = D.xch.p + qp_off; dmc.Qf = D.xch.p + qf_off; }
+    if (use256) le = bnlp_coop256_launch(a.phase_cycles != nullptr, ctas, E->coop_smem_bytes, stream, &dmc, &a, &cb);
+    else le = ipm_coop_launch(a.phase_cycles != nullptr, ctas, E->coop_smem_bytes, stream, dmc, a, cb);
     if (windowed) {
       cudaStreamAttrValue av{};
       av.accessPolicyWindow.num_bytes = 0;
