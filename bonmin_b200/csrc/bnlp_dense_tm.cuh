@@ -695,4 +695,137 @@ __device__ __forceinline__ void backsolve_tm(const double *H, const TmLayout &L,
   __syncthreads();
 }
 
+// =====================================================================================================================
+// Back-substitution with 32 x 32 INVERSE diagonal blocks on the tile-major matrix (the large-model path: H in global memory).
+//
+// backsolve_tm above keeps one warp per right-hand side busy and everything else idle: at n = 400 its 51 block steps are 51
+// chains of L2 round trips, 544 k cycles per iteration (23 % of the C5 iteration, profiles/r2c notes).  Here the diagonal
+// 32 x 32 blocks made of full tiles are inverted in place first (one warp per block, all blocks at once, 8 x 8 tile products
+// on DMMA: Inv_pq = -X_p sum_{r=q}^{p-1} L_pr Inv_rq, column by column), and a block step is then one dot-product stage
+// (64 dot products, eight lanes each) and one update stage in which EVERY thread owns an entry of both right-hand sides
+// and requests its 32 coefficients in batches of eight: 13 block steps at n = 400, all 512 threads loading.
+
+// C += sgn * A B for 8 x 8 tiles of the tile-major matrix (a_lo / b_lo: the operand is lower triangular)
+__device__ __forceinline__ void tm_tile_mm(const double *Ta, bool a_lo, const double *Tb, bool b_lo, double sgn, double &c0, double &c1) {
+  const int lane = threadIdx.x & 31, lr = lane >> 2, lc = lane & 3;
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+    const int kk = 4 * ks + lc;
+    const double av = (!a_lo || kk <= lr) ? Ta[(lr << 3) + (kk ^ tm_swz(lr))] : 0.0;      // A[m = lr][k = kk]
+    const double bv = (!b_lo || lr <= kk) ? Tb[(kk << 3) + (lr ^ tm_swz(kk))] : 0.0;      // B[k = kk][n = lr]
+    dmma(c0, c1, sgn * av, bv);
+  }
+}
+
+// in-place inverse of the 32 x 32 diagonal block at tile row 4 b (four full tile rows; diagonal tiles hold X_p).  One warp.
+__device__ __forceinline__ void tm_invert_block32(double *H, const TmLayout &L, int b) {
+  const int lane = threadIdx.x & 31, lr = lane >> 2, lc = lane & 3;
+  const int t0 = 4 * b;
+  for (int q = 0; q < 3; ++q) {
+    for (int p = q + 1; p < 4; ++p) {
+      double s0 = 0.0, s1 = 0.0;
+      for (int r = q; r < p; ++r)
+        tm_tile_mm(H + tm_tile(L, t0 + p, t0 + r), false, H + tm_tile(L, t0 + r, t0 + q), r == q, 1.0, s0, s1);
+      double *T = H + tm_tile(L, t0 + p, t0 + q);
+      __syncwarp();
+      *tm_acc(T, lr, lc) = make_double2(s0, s1);
+      __syncwarp();
+      double c0 = 0.0, c1 = 0.0;
+      tm_tile_mm(H + tm_tile(L, t0 + p, t0 + p), true, T, false, -1.0, c0, c1);
+      __syncwarp();
+      *tm_acc(T, lr, lc) = make_double2(c0, c1);
+      __syncwarp();
+    }
+  }
+}
+
+// L' x = w for the two right-hand sides carried in rows N and N + 1; b0 / b1 (shared memory, >= 8 ceil(N / 8) doubles each)
+// hold the solutions on exit; xs: 64 doubles of shared scratch.  Same contract as backsolve_tm.
+__device__ __forceinline__ void backsolve32_tm(double *H, const TmLayout &L, int N, double *b0, double *b1, double *xs) {
+  const int tid = threadIdx.x, w = tid >> 5;
+  const int ntN = (N + 7) >> 3, nfull = N >> 5;
+  for (int b = w; b < nfull; b += IPM_NW) tm_invert_block32(H, L, b);
+  for (int e = tid; e < 2 * 8 * ntN; e += IPM_NT) {
+    const int r = e / (8 * ntN), k = e - r * 8 * ntN;
+    (r ? b1 : b0)[k] = (k < N) ? H[tm_idx(L, N + r, k)] : 0.0;
+  }
+  __syncthreads();
+  // ragged tail above the last full block: 8-row steps
+  for (int bi = ntN - 1; bi >= 4 * nfull; --bi) {
+    const int i0 = bi << 3, nb = min(8, N - i0);
+    if (tid < 16) {
+      const int rhs = tid >> 3, c = tid & 7;
+      const double *bv = rhs ? b1 : b0;
+      const double *X = H + tm_tile(L, bi, bi);
+      double xc = 0.0;
+      if (c < nb) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (k < nb && k >= c) xc = fma(X[(k << 3) + (c ^ tm_swz(k))], bv[i0 + k], xc);
+      }
+      xs[tid] = xc;
+    }
+    __syncthreads();
+    for (int kk = tid; kk < i0 + 8; kk += IPM_NT) {
+      if (kk < i0) {
+        const double *T = H + tm_tile(L, bi, kk >> 3);
+        const int kc = kk & 7;
+        double v0 = b0[kk], v1 = b1[kk];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          if (c < nb) {
+            const double l = T[(c << 3) + (kc ^ tm_swz(c))];
+            v0 = fma(-l, xs[c], v0);
+            v1 = fma(-l, xs[8 + c], v1);
+          }
+        }
+        b0[kk] = v0; b1[kk] = v1;
+      } else if (kk < i0 + nb) {
+        b0[kk] = xs[kk - i0]; b1[kk] = xs[8 + kk - i0];
+      }
+    }
+    __syncthreads();
+  }
+  constexpr int LPD = IPM_NT / 64;                 // lanes per dot product (64 dot products: 32 entries x 2 right-hand sides)
+  const int dot = tid / LPD, part = tid % LPD, drhs = dot >> 5, dc = dot & 31;
+  for (int b = nfull - 1; b >= 0; --b) {
+    const int i0 = 32 * b, t0 = 4 * b;
+    {
+      const double *wv = drhs ? b1 : b0;
+      double a = 0.0;
+#pragma unroll
+      for (int u = 0; u < 32 / LPD; ++u) {
+        const int k = part + LPD * u;                // x[c] = sum_{k >= c} Inv[k][c] w[k]
+        if (k >= dc) {
+          const double *T = H + tm_tile(L, t0 + (k >> 3), t0 + (dc >> 3));
+          a = fma(T[((k & 7) << 3) + ((dc & 7) ^ tm_swz(k & 7))], wv[i0 + k], a);
+        }
+      }
+#pragma unroll
+      for (int o = LPD / 2; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if (part == 0) xs[dot] = a;
+    }
+    __syncthreads();
+    for (int kk = tid; kk < i0 + 32; kk += IPM_NT) {
+      if (kk < i0) {
+        const int kt = kk >> 3, kc = kk & 7;
+        double v0 = b0[kk], v1 = b1[kk];
+#pragma unroll
+        for (int c0 = 0; c0 < 32; c0 += 8) {        // eight coefficients requested before the first FMA
+          const double *T = H + tm_tile(L, t0 + (c0 >> 3), kt);
+          double l[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) l[c] = T[(c << 3) + (kc ^ tm_swz(c))];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) { v0 = fma(-l[c], xs[c0 + c], v0); v1 = fma(-l[c], xs[32 + c0 + c], v1); }
+        }
+        b0[kk] = v0; b1[kk] = v1;
+      } else {
+        b0[kk] = xs[kk - i0]; b1[kk] = xs[32 + kk - i0];
+      }
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace BNLP_NS

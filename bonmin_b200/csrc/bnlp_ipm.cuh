@@ -1235,7 +1235,11 @@ __global__ void __launch_bounds__(IPM_NT, 512 / IPM_NT) ipm_kernel(DevModel M, I
         }
         __syncthreads();
       }
+#ifdef BNLP_OLD_BACKSOLVE_TM
       if (TM) backsolve_tm<true>(H, TL, N, d0, d1);   // rows N, N+1 of H -> d0, d1 = H^-1 rhs0, H^-1 rhs1
+#else
+      if (TM) backsolve32_tm(H, TL, N, d0, d1, red);  // rows N, N+1 of H -> d0, d1 = H^-1 rhs0, H^-1 rhs1
+#endif
       else backsolve2(H, N);   // d0 = H^-1 rhs0, d1 = H^-1 rhs1
       PH_MARK(4);
 
