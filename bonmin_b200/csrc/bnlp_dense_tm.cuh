@@ -552,6 +552,69 @@ __device__ __forceinline__ void tm_ll_update(double *H, const TmLayout &L, int j
   }
 }
 
+// ---- the same update for k in [k0, k1) and for NC block columns j .. j + NC - 1 alongside (the caller passes only rows
+// i >= j + NC - 1, so every tile written exists): T(i, j + c) -= sum_k T(i, k) T(j + c, k)'.  Every A tile T(i, k) that crosses
+// L2 -> SM then feeds the DMMAs of NC block columns: the left-looking factorisation of a large model is bound by exactly that traffic
+// (11 MB per factorisation and CTA at n = 400, 148 CTAs at once).
+template <int R, int NC>
+__device__ __forceinline__ void tm_ll_update2(double *H, const TmLayout &L, int j, int i0, int st, int k0, int k1) {
+  const int lane = threadIdx.x & 31;
+  const int lr = lane >> 2, lc = lane & 3;
+  const int nt = L.nt;
+  const int fo = (lr << 3) + (lc ^ tm_swz(lr)), f1 = ((4 + lc) ^ tm_swz(lr)) - (lc ^ tm_swz(lr)), ao = (lr << 3) + ((2 * lc) ^ tm_swz(lr));
+  const bool thin_ok = lr < L.last_h;
+  const double *Brow[NC];
+  int bst[NC];
+  bool bv[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    Brow[c] = H + tm_tile(L, j + c, 0) + fo;
+    bst[c] = (j + c == nt - 1) ? 8 * L.last_h : 64;
+    bv[c] = j + c != nt - 1 || thin_ok;
+  }
+  const double *Arow[R];
+  int ast[R];
+  bool rv[R];
+  double s0[R][NC][2], s1[R][NC][2];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int i = i0 + r * st;
+    const int ii = min(i, nt - 1);
+    rv[r] = i < nt && (ii != nt - 1 || thin_ok);
+    Arow[r] = H + tm_tile(L, ii, 0) + fo;
+    ast[r] = (ii == nt - 1) ? 8 * L.last_h : 64;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) s0[r][c][0] = s0[r][c][1] = s1[r][c][0] = s1[r][c][1] = 0.0;
+  }
+#pragma unroll 4
+  for (int k = k0; k < k1; ++k) {
+    double b0[NC], b1[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) { b0[c] = bv[c] ? Brow[c][k * bst[c]] : 0.0; b1[c] = bv[c] ? Brow[c][k * bst[c] + f1] : 0.0; }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const double a0 = rv[r] ? Arow[r][k * ast[r]] : 0.0, a1 = rv[r] ? Arow[r][k * ast[r] + f1] : 0.0;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        dmma(s0[r][c][0], s0[r][c][1], a0, b0[c]);
+        dmma(s1[r][c][0], s1[r][c][1], a1, b1[c]);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    if (rv[r]) {
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        double2 *C = reinterpret_cast<double2 *>(H + tm_tile(L, i0 + r * st, j + c) + ao);
+        double2 h = *C;
+        h.x -= s0[r][c][0] + s1[r][c][0]; h.y -= s0[r][c][1] + s1[r][c][1];
+        *C = h;
+      }
+    }
+  }
+}
+
 // ---- left-looking blocked Cholesky, same contract as chol_tm (rows [N, Nrows) carried, diagonal tiles end up as the
 // inverses of the diagonal blocks of L).  Per block column j: warp 0 updates and factors the diagonal tile (the pivot
 // chain), warps 1 .. NW-1 update the tiles below it; CTA barrier; every warp solves its tiles against the new diagonal
@@ -565,14 +628,20 @@ __device__ __forceinline__ bool chol_tm_ll(double *H, const TmLayout &L, int N, 
   __syncthreads();
   for (int j = 0; j < ntN; ++j) {
     if (j < 8) LL_STAMP(8 * j);
+    // block columns in PAIRS: an even column applies its terms k < j and, alongside (same A tiles), the terms k < j of
+    // column j + 1; the odd column that follows only has the term k = j left.  Measured at C5 / C4 (relaxations/s): one
+    // column at a time 6.3 k / 1.80 k, pairs 7.2 k / 1.99 k, groups of four (one row per warp) 6.15 k / 1.77 k.
+    const bool even = (j & 1) == 0;
+    const int k0 = even ? 0 : j - 1, k1 = j;
+    const bool two = even && j + 1 < ntN;
     if (w == 0) {
-      if (j > 0) { tm_ll_update<1>(H, L, j, j, 0); __syncwarp(); }
-      if (dbg && j < 8 && threadIdx.x == 0) { const int f_ = *(volatile int *)fail; dbg[8 * j + 6] = clock64() + (f_ & 0); }
+      if (k1 > k0) { tm_ll_update2<1, 1>(H, L, j, j, 0, k0, k1); __syncwarp(); }
       tm_potrf(H + tm_tile(L, j, j), min(8, N - 8 * j), min(8, Nrows - 8 * j), fail);
-    } else if (j > 0) {
+    } else if (k1 > k0) {
       for (int i = j + w; i < nt; i += 2 * (IPM_NW - 1)) {
-        if (i + (IPM_NW - 1) < nt) tm_ll_update<2>(H, L, j, i, IPM_NW - 1);
-        else tm_ll_update<1>(H, L, j, i, 0);
+        const bool pair = i + (IPM_NW - 1) < nt;
+        if (two) { if (pair) tm_ll_update2<2, 2>(H, L, j, i, IPM_NW - 1, k0, k1); else tm_ll_update2<1, 2>(H, L, j, i, 0, k0, k1); }
+        else { if (pair) tm_ll_update2<2, 1>(H, L, j, i, IPM_NW - 1, k0, k1); else tm_ll_update2<1, 1>(H, L, j, i, 0, k0, k1); }
       }
     }
     if (j < 8) LL_STAMP(8 * j + 2);
