@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libbnlp.so")
-SOURCES = ["bnlp_launch_ipm.cu", "bnlp_launch_coop.cu", "bnlp_launch_coop256.cu", "bnlp_api.cu", "bnlp_model.cpp", "bnlp_nl.cpp",
+SOURCES = ["bnlp_launch_ipm.cu", "bnlp_launch_wide.cu", "bnlp_launch_coop.cu", "bnlp_launch_coop256.cu", "bnlp_api.cu", "bnlp_model.cpp", "bnlp_nl.cpp",
            "../host/B200Solver.cpp", "../host/host_cabi.cpp", "../host/node_files.cpp", "../host/B200Linearizer.cpp"]
 HOST_LIB = os.path.join(HERE, "libbnlp_host.so")
 HEADERS = ["../host/B200Solver.hpp", "../host/B200Linearizer.hpp", "../host/bonmin_shim.hpp", "bnlp_internal.h", "bnlp_ipm.cuh", "bnlp_ipm_coop.cuh",
@@ -21,6 +21,7 @@ HEADERS = ["../host/B200Solver.hpp", "../host/B200Linearizer.hpp", "../host/bonm
 # headers each source depends on (None = all)
 DEPS = {
     "bnlp_launch_ipm.cu": ["bnlp_internal.h", "bnlp_ipm.cuh", "bnlp_dense_tm.cuh", "bnlp_eval.cuh", "../../include/bnlp.h"],
+    "bnlp_launch_wide.cu": ["bnlp_internal.h", "bnlp_ipm.cuh", "bnlp_dense_tm.cuh", "bnlp_eval.cuh", "../../include/bnlp.h"],
     "bnlp_launch_coop.cu": ["bnlp_internal.h", "bnlp_ipm.cuh", "bnlp_ipm_coop.cuh", "bnlp_dense.cuh", "bnlp_dense_tm.cuh", "bnlp_eval.cuh",
                             "../../include/bnlp.h"],
     "bnlp_launch_coop256.cu": ["bnlp_internal.h", "bnlp_ipm.cuh", "bnlp_ipm_coop.cuh", "bnlp_dense.cuh", "bnlp_dense_tm.cuh", "bnlp_eval.cuh",

@@ -37,6 +37,10 @@ cudaError_t ipm_coop_launch(bool timers, int ctas, size_t smem, cudaStream_t str
 
 using namespace bnlp;
 
+// wide build of the term machine (bnlp_launch_wide.cu: namespace bnlpw, BNLP_TV = BNLP_MAX_WIDE_TERM_VARS)
+cudaError_t bnlpw_ipm_set_smem(size_t smem);
+cudaError_t bnlpw_ipm_launch(bool big, int ctas, size_t smem, cudaStream_t stream, const void *M, const void *A);
+cudaError_t bnlpw_eval_launch(int nc, size_t smem, cudaStream_t stream, const void *ev, const void *args);
 // 256-thread build of the cooperative kernel (bnlp_launch_coop256.cu)
 cudaError_t bnlp_coop256_set_smem(size_t smem);
 cudaError_t bnlp_coop256_launch(bool timers, int ctas, size_t smem, cudaStream_t stream, void *M, void *A, void *CB);
@@ -130,6 +134,7 @@ struct bnlp_engine {
   int h_in_smem = 1;
   int tm_kc = 16;
   size_t smem_bytes = 0;
+  bool wide_terms = false;   // some element term couples more than BNLP_MAX_TERM_VARS variables: evaluation and the IPM run the wide build (namespace bnlpw)
   bool coop_ok = false;
   bool coop256 = false;   // small model: 256-thread CTAs, two per SM
   size_t coop_smem_bytes = 0;
@@ -266,7 +271,7 @@ static int upload(DBuf<T> &b, const std::vector<T> &v) {
 }
 
 int build_eval_tape(const HostModel &M, bool densified, std::vector<int> &ints, std::vector<double> &dbls,
-                    EvalModelHostOffsets &off, const std::vector<int> &qidx);
+                    EvalModelHostOffsets &off, const std::vector<int> &qidx, int tv_cap);
 
 namespace {
 // IPM view of a model: dense A, one packed quadratic block per function (device strides), one-sided rows, equality rows
@@ -520,7 +525,14 @@ extern "C" bnlp_engine *bnlp_engine_create(const bnlp_problem *prob, const int *
   std::vector<int> e_ints;
   std::vector<double> e_dbls;
   EvalModelHostOffsets eoff;
-  build_eval_tape(M, densify, e_ints, e_dbls, eoff, qidx);
+  {
+    std::string werr;
+    const int wc = term_width_class(M, werr);
+    if (wc < 0) { set_err("bnlp_engine_create: " + werr); delete E; return nullptr; }
+    E->wide_terms = wc == 1;
+  }
+  const int tv_cap = E->wide_terms ? BNLP_MAX_WIDE_TERM_VARS : BNLP_MAX_TERM_VARS;
+  build_eval_tape(M, densify, e_ints, e_dbls, eoff, qidx, tv_cap);
 
   for (size_t d = 0; d < ids.size(); ++d) {
     Device &D = E->devs[d];
@@ -578,7 +590,7 @@ extern "C" bnlp_engine *bnlp_engine_create(const bnlp_problem *prob, const int *
       if (!E->h_in_smem && ipm_smem_doubles(n, m, E->R, E->E, 0, V.n_lr, 32) * sizeof(double) + 1024 <= D.smem_optin && !getenv("BNLP_TM_KC16")) E->tm_kc = 32;
       E->smem_bytes = ipm_smem_doubles(n, m, E->R, E->E, E->h_in_smem, V.n_lr, E->tm_kc) * sizeof(double);
       if (E->smem_bytes + 1024 > D.smem_optin) { E->ipm_supported = false; E->ipm_unsupported_why = "iterate vectors do not fit shared memory"; }
-      E->ws_doubles = (size_t)2 * (m + 1) * n + (size_t)M.terms.size() * (2 + TV + TH) + (E->h_in_smem ? 0 : (size_t)tm_size(tm_layout(n + 3 + E->E)) + 2);   // tile-major H (bnlp_dense_tm.cuh)
+      E->ws_doubles = (size_t)2 * (m + 1) * n + (size_t)M.terms.size() * (2 + tv_cap + tv_cap * (tv_cap + 1) / 2) + (E->h_in_smem ? 0 : (size_t)tm_size(tm_layout(n + 3 + E->E)) + 2);   // tile-major H (bnlp_dense_tm.cuh)
       E->ws_doubles = (E->ws_doubles + 1) & ~(size_t)1;
       // cooperative DMMA kernel: needs H in shared memory, n <= 256 and the group weights to fit the staging area
       E->nqpad = (std::max(E->nq, 1) + 3) & ~3;
@@ -603,7 +615,7 @@ extern "C" bnlp_engine *bnlp_engine_create(const bnlp_problem *prob, const int *
       E->coop_ok = false;
       cudaGetLastError();
     }
-    if (E->ipm_supported && ipm_general_set_smem(D.smem_optin - 1024) != cudaSuccess) {
+    if (E->ipm_supported && (E->wide_terms ? bnlpw_ipm_set_smem(D.smem_optin - 1024) : ipm_general_set_smem(D.smem_optin - 1024)) != cudaSuccess) {
       set_err(std::string("cudaFuncSetAttribute(ipm_kernel): ") + cudaGetErrorString(cudaGetLastError()));
       delete E;
       return nullptr;
@@ -761,7 +773,8 @@ static int launch_ipm(bnlp_engine *E, Device &D, int B, const double *dXL, const
       cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &av);
     }
     CK(le);
-  } else CK(ipm_general_launch(E->M.n > 256, ctas, E->smem_bytes, stream, D.dm, a));
+  } else if (E->wide_terms) CK(bnlpw_ipm_launch(E->M.n > 256, ctas, E->smem_bytes, stream, &D.dm, &a));
+  else CK(ipm_general_launch(E->M.n > 256, ctas, E->smem_bytes, stream, D.dm, a));
   E->launches++;
   CK(cudaGetLastError());
   return 0;

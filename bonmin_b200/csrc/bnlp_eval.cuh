@@ -22,9 +22,17 @@
 namespace BNLP_NS {
 
 constexpr int EV_NT = 256;
-constexpr int TV = BNLP_MAX_TERM_VARS;                 // max variables of a term
+// (BNLP_TV / BNLP_TS: the wide build of the term machine — bnlp_launch_wide.cu compiles these headers a second time in
+// namespace bnlpw with BNLP_MAX_WIDE_TERM_VARS / _STACK)
+#ifndef BNLP_TV
+#define BNLP_TV BNLP_MAX_TERM_VARS
+#endif
+#ifndef BNLP_TS
+#define BNLP_TS BNLP_MAX_TERM_STACK
+#endif
+constexpr int TV = BNLP_TV;                            // max variables of a term
 constexpr int TH = TV * (TV + 1) / 2;                  // packed local Hessian
-constexpr int TS = BNLP_MAX_TERM_STACK;
+constexpr int TS = BNLP_TS;
 
 struct EvalModelHostOffsets {
   int n = 0, m = 0, nnz_jac = 0, nnz_hes = 0, n_terms = 0, nqs = 0, mnl = 0, nlin = 0, nfq = 0, P = 0;

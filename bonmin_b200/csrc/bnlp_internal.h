@@ -52,4 +52,10 @@ struct HostModel {
 
 bool parse_nl(const char *text, size_t len, HostModel &out, std::string &err);
 
+// deepest postfix stack of a (validated) term program
+int term_stack_depth(const Term &T);
+// 0: every term fits the narrow term machine (BNLP_MAX_TERM_VARS / _STACK); 1: the model needs the wide build
+// (BNLP_MAX_WIDE_TERM_VARS / _STACK hold for every term); -1 + err: a term fits neither
+int term_width_class(const HostModel &M, std::string &err);
+
 }  // namespace bnlp

@@ -96,7 +96,7 @@ bool model_from_desc(const bnlp_tape_desc *d, HostModel &M, std::string &err) {
     T.fn = d->term_fn[t];
     if (T.fn < 0 || T.fn > m) { err = "term function index out of range"; return false; }
     T.vars.assign(d->term_var + d->term_var_start[t], d->term_var + d->term_var_start[t + 1]);
-    if ((int)T.vars.size() > BNLP_MAX_TERM_VARS) { err = "term has more than BNLP_MAX_TERM_VARS variables"; return false; }
+    if ((int)T.vars.size() > BNLP_MAX_WIDE_TERM_VARS) { err = "term has more than BNLP_MAX_WIDE_TERM_VARS = " + std::to_string(BNLP_MAX_WIDE_TERM_VARS) + " variables"; return false; }
     for (int v : T.vars) if (v < 0 || v >= n) { err = "term variable out of range"; return false; }
     const int a = d->term_op_start[t], b = d->term_op_start[t + 1];
     T.op.assign(d->term_op + a, d->term_op + b);
@@ -125,8 +125,37 @@ bool model_from_desc(const bnlp_tape_desc *d, HostModel &M, std::string &err) {
     if (maxd > BNLP_MAX_TERM_STACK) { err = "term stack deeper than BNLP_MAX_TERM_STACK"; return false; }
     M.terms.push_back(std::move(T));
   }
+  if (term_width_class(M, err) < 0) return false;
   M.finalize();
   return true;
+}
+
+int term_stack_depth(const Term &T) {
+  int depth = 0, maxd = 0;
+  for (int op : T.op) {
+    if (op == BNLP_OP_CONST || op == BNLP_OP_VAR) depth++;
+    else if (op == BNLP_OP_ADD || op == BNLP_OP_SUB || op == BNLP_OP_MUL || op == BNLP_OP_DIV || op == BNLP_OP_POW) depth--;
+    maxd = std::max(maxd, depth);
+  }
+  return maxd;
+}
+
+int term_width_class(const HostModel &M, std::string &err) {
+  bool wide = false;
+  for (const Term &T : M.terms) wide |= (int)T.vars.size() > BNLP_MAX_TERM_VARS;
+  for (const Term &T : M.terms) {
+    const int nv = (int)T.vars.size(), d = term_stack_depth(T);
+    if (nv > (wide ? BNLP_MAX_WIDE_TERM_VARS : BNLP_MAX_TERM_VARS)) {
+      err = "a nonlinear element term couples " + std::to_string(nv) + " variables (limit " + std::to_string(BNLP_MAX_WIDE_TERM_VARS) + ")";
+      return -1;
+    }
+    if (d > (wide ? BNLP_MAX_WIDE_TERM_STACK : BNLP_MAX_TERM_STACK)) {
+      err = "a nonlinear element term needs a postfix stack of " + std::to_string(d) + " entries (limit " +
+            std::to_string(wide ? BNLP_MAX_WIDE_TERM_STACK : BNLP_MAX_TERM_STACK) + (wide ? " in a model with wide terms)" : ")");
+      return -1;
+    }
+  }
+  return wide ? 1 : 0;
 }
 
 // ---- TNLP2FPNLP (src/Interfaces/BonTNLP2FPNLP.cpp:75-330) as a tape transformation.

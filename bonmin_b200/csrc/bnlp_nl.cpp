@@ -6,7 +6,8 @@
 // (`oN` operator, `nX` constant, `vI` variable); each function is lowered to
 //     c + a.x + 1/2 x'Qx + sum of element terms
 // by symbolic degree-<=2 polynomial extraction; what is not polynomial of degree <= 2 becomes a postfix element term
-// over at most BNLP_MAX_TERM_VARS variables (partially separable structure).
+// over at most BNLP_MAX_TERM_VARS variables (partially separable structure) — up to BNLP_MAX_WIDE_TERM_VARS in a model
+// that the wide build of the term machine evaluates (include/bnlp.h).
 #include <cmath>
 #include <cstdlib>
 #include <map>
@@ -250,8 +251,8 @@ bool lower(const Node &e, double sign, int fn, Poly &P, std::vector<Term> &terms
   // c * g(x): pull a constant factor out so that the sign/scale does not hide a polynomial
   std::set<int> vs;
   collect_vars(e, vs);
-  if ((int)vs.size() > BNLP_MAX_TERM_VARS) {
-    err = "a non-quadratic, non-separable expression couples more than " + std::to_string(BNLP_MAX_TERM_VARS) + " variables";
+  if ((int)vs.size() > BNLP_MAX_WIDE_TERM_VARS) {
+    err = "a non-quadratic, non-separable expression couples more than " + std::to_string(BNLP_MAX_WIDE_TERM_VARS) + " variables";
     return false;
   }
   Term T;
@@ -464,6 +465,7 @@ bool parse_nl(const char *text, size_t len, HostModel &M, std::string &err) {
     }
   }
   M.lin_start[m + 1] = (int)M.lin_col.size();
+  if (term_width_class(M, err) < 0) return false;
   M.finalize();
   return true;
 }

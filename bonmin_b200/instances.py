@@ -246,6 +246,58 @@ def syn_cvx_minlp(n: int, n_bin: int, m_nl: int, m_l: int, seed: int, dense_quad
         name=f"SYN-CVX-MINLP(n={n},n_bin={n_bin},m_nl={m_nl},m_l={m_l},seed={seed})"))
 
 
+OP_ADD, OP_LOG, OP_SQRT, OP_SQR = 2, 10, 11, 14
+
+
+def wide_terms_minlp(seed: int = 1) -> StructuredModel:
+    """A small convex MINLP whose nonlinear rows couple MANY variables in one non-quadratic expression — what the narrow
+    element-term machine (<= 6 variables) cannot hold and the wide build (include/bnlp.h, BNLP_MAX_WIDE_TERM_VARS) is for:
+      row 1: log(sum_{i<20} exp(0.3 x_i)) <= b1          (log-sum-exp over 20 variables)
+      row 2: sqrt(1 + sum_{8<=i<20} x_i^2) <= b2          (a norm over 12 variables)
+      row 3: exp(0.5 x_12 + 0.5 x_13) + x_28 <= b3        (a narrow term in the same model)
+      rows 4..6: sparse linear; linear objective.
+    n = 30 in AMPL's canonical order so that nlwrite can write it: x_0..x_13 continuous and x_14..x_19 integer (nonlinear in
+    constraints), x_20..x_27 continuous and x_28, x_29 integer (linear)."""
+    n, m = 30, 6
+    rng = np.random.Generator(np.random.PCG64(seed))
+    is_int = np.zeros(n, bool)
+    is_int[14:20] = True
+    is_int[28:] = True
+    xl = np.where(is_int, 0.0, -3.0)
+    xu = np.where(is_int, 5.0, 3.0)
+    vtype = np.where(is_int, INTEGER, CONTINUOUS).astype(np.int32)
+    x0 = np.where(is_int, rng.integers(1, 4, n).astype(float), rng.uniform(-1, 1, n))
+    A = np.zeros((m + 1, n))
+    A[0] = -rng.uniform(0.2, 1.0, n)                    # push every variable up against the rows
+    A[3, 28] = 1.0
+    gl = np.full(m, -INF)
+    gu = np.zeros(m)
+    lse = [(OP_VAR, 0, 0.0), (OP_CONST, 0, 0.3), (OP_MUL, 0, 0.0), (OP_EXP, 0, 0.0)]
+    for i in range(1, 20):
+        lse += [(OP_VAR, i, 0.0), (OP_CONST, 0, 0.3), (OP_MUL, 0, 0.0), (OP_EXP, 0, 0.0), (OP_ADD, 0, 0.0)]
+    lse.append((OP_LOG, 0, 0.0))
+    nrm = [(OP_CONST, 0, 1.0)]
+    for i in range(12):
+        nrm += [(OP_VAR, i, 0.0), (OP_SQR, 0, 0.0), (OP_ADD, 0, 0.0)]
+    nrm.append((OP_SQRT, 0, 0.0))
+    ex2 = [(OP_CONST, 0, 0.5), (OP_VAR, 0, 0.0), (OP_MUL, 0, 0.0), (OP_CONST, 0, 0.5), (OP_VAR, 1, 0.0), (OP_MUL, 0, 0.0),
+           (OP_ADD, 0, 0.0), (OP_EXP, 0, 0.0)]
+    terms = [(1, list(range(20)), lse), (2, list(range(8, 20)), nrm), (3, [12, 13], ex2)]
+    g0 = np.array([np.log(np.exp(0.3 * x0[:20]).sum()), np.sqrt(1.0 + (x0[8:20] ** 2).sum()),
+                   np.exp(0.5 * x0[12] + 0.5 * x0[13]) + x0[28]])
+    gu[:3] = g0 + np.array([0.15, 0.2, 0.3])
+    for r in range(3, m):
+        li = np.zeros(n)
+        cols = rng.choice(n, 6, replace=False)
+        li[cols] = rng.uniform(0.2, 1.0, 6)
+        A[r + 1] = li
+        gu[r] = li @ x0 + rng.uniform(0.5, 1.5)
+    return _empty_sparse(StructuredModel(
+        n=n, m=m, xl=xl, xu=xu, gl=gl, gu=gu, vtype=vtype, x0=x0, c=np.zeros(m + 1), A=A,
+        qd_fn=np.zeros(0, np.int32), qd=np.zeros((0, n * (n + 1) // 2)), terms=terms,
+        name=f"WIDE-TERMS-MINLP(seed={seed})"))
+
+
 def config_c4() -> StructuredModel:
     return syn_cvx_minlp(500, 250, 100, 100, 20261021)
 

@@ -42,6 +42,13 @@ enum {
 };
 #define BNLP_MAX_TERM_VARS 6
 #define BNLP_MAX_TERM_STACK 12
+/* WIDE element terms: a non-quadratic expression that couples more than BNLP_MAX_TERM_VARS variables (a log-sum-exp over 20
+ * variables, sqrt(sum x^2), ...; the reference forwards any ASL expression DAG, src/Interfaces/Ampl/BonAmplTMINLP.cpp:629-710).
+ * A model that holds at least one such term is evaluated by a second build of the term machine (same second-order forward
+ * mode, dense local Hessian of up to 24 x 24): every term of that model may then couple up to BNLP_MAX_WIDE_TERM_VARS
+ * variables with a postfix stack of at most BNLP_MAX_WIDE_TERM_STACK entries. */
+#define BNLP_MAX_WIDE_TERM_VARS 24
+#define BNLP_MAX_WIDE_TERM_STACK 8
 
 /* Structured model ("flat tape" input): every function k (k = 0 objective, k = 1..m rows) is
  *     F_k(x) = c[k] + a_k.x + 1/2 x'Q_k x + sum_t phi_t(x[term vars])

@@ -63,8 +63,9 @@ struct OModel {
   const double *term_darg = nullptr;
 };
 
-// second-order forward mode over the (<= 6) local variables of a term
-constexpr int TVm = 6;
+// second-order forward mode over the local variables of a term (<= 24: BNLP_MAX_WIDE_TERM_VARS of include/bnlp.h; only the
+// leading nv x nv part of a stack entry is ever touched)
+constexpr int TVm = 24;
 struct HD { double v; double g[TVm]; double h[TVm][TVm]; };
 enum { OP_CONST = 0, OP_VAR, OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_NEG, OP_POWC, OP_POW, OP_EXP, OP_LOG, OP_SQRT, OP_SIN,
        OP_COS, OP_SQR, OP_ABS };
@@ -88,7 +89,8 @@ static HD eval_term(const OModel &M, int t, const double *x) {
     const int op = M.term_op[p];
     if (op == OP_CONST || op == OP_VAR) {
       HD &z = st[sp++];
-      std::memset(&z, 0, sizeof(HD));
+      z.v = 0.0;
+      for (int i = 0; i < nv; ++i) { z.g[i] = 0.0; for (int j = 0; j < nv; ++j) z.h[i][j] = 0.0; }
       if (op == OP_CONST) z.v = M.term_darg[p];
       else { z.v = x[M.term_var[v0 + M.term_iarg[p]]]; z.g[M.term_iarg[p]] = 1.0; }
     } else if (op == OP_ADD || op == OP_SUB || op == OP_MUL || op == OP_DIV || op == OP_POW) {

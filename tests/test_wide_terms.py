@@ -1,0 +1,96 @@
+"""Wide element terms (round 2): a non-quadratic expression that couples more than BNLP_MAX_TERM_VARS = 6 variables — the
+reference forwards any ASL expression DAG (src/Interfaces/Ampl/BonAmplTMINLP.cpp:629-710).  A model with such a term runs on
+the wide build of the term machine (include/bnlp.h: up to 24 variables per term, bnlp_launch_wide.cu).  The instance has a
+log-sum-exp over 20 variables, a norm over 12 and a narrow term; it is written as `.nl`, read back by the product's parser and
+by the independent pure-Python reader, evaluated on the device against both, and its relaxations are solved against the
+oracle."""
+import numpy as np
+import pytest
+
+from bonmin_b200 import instances as I, nlwrite
+from oracle.nl_reader import NlModel
+from oracle.struct_eval import Evaluator
+
+
+def test_wide_model_loads_and_limits(bnlp_lib):
+    from bonmin_b200.engine import BnlpError, Problem
+    m = I.wide_terms_minlp()
+    ev = Evaluator(m)
+    txt = nlwrite.write_nl(m)
+    for p in (Problem.from_nl(txt), Problem.from_model(m)):
+        assert (p.n, p.m, p.nnz_jac, p.nnz_hess) == (30, 6, len(ev.jac), len(ev.hes))
+        info = p.info()
+        assert list(zip(info["jac_irow"], info["jac_jcol"])) == ev.jac
+    # the independent reader agrees with the structured evaluator on the written file
+    x = np.random.default_rng(0).uniform(-1, 2, m.n)
+    np.testing.assert_allclose(NlModel(txt).values(x), ev.dense(x)[0], rtol=1e-14)
+    # 25 variables in one expression: beyond the wide machine too — refused, with the limit in the message
+    big = I.wide_terms_minlp()
+    prog = [(I.OP_VAR, 0, 0.0), (I.OP_EXP, 0, 0.0)]
+    for i in range(1, 25):
+        prog += [(I.OP_VAR, i, 0.0), (I.OP_EXP, 0, 0.0), (I.OP_ADD, 0, 0.0)]
+    prog.append((I.OP_LOG, 0, 0.0))
+    big["terms"] = [(1, list(range(25)), prog)]
+    with pytest.raises(BnlpError, match="24"):
+        Problem.from_model(big)
+    # a wide term next to a term that needs a deeper stack than the wide machine has: refused as well
+    deep = I.wide_terms_minlp()
+    dprog = [(I.OP_VAR, 0, 0.0)] * 10 + [(I.OP_ADD, 0, 0.0)] * 9
+    deep["terms"] = list(deep["terms"]) + [(3, [20], dprog)]
+    with pytest.raises(BnlpError, match="stack"):
+        Problem.from_model(deep)
+    # ... while the same deep term alone (narrow model, stack of 12) is fine
+    narrow = I.wide_terms_minlp()
+    narrow["terms"] = [(3, [20], dprog)]
+    assert Problem.from_model(narrow).n == 30
+
+
+@pytest.mark.gpu
+def test_wide_terms_eval_matches_both_readers(bnlp_lib):
+    from bonmin_b200.engine import Engine, Problem
+    m = I.wide_terms_minlp()
+    ev = Evaluator(m)
+    txt = nlwrite.write_nl(m)
+    nm = NlModel(txt)
+    rng = np.random.default_rng(3)
+    B = 41
+    X = np.clip(m.x0 + rng.normal(0, 0.5, (B, m.n)), m.xl, m.xu)
+    LAM = rng.normal(0, 1, (B, m.m))
+    for prob in (Problem.from_nl(txt), Problem.from_model(m)):
+        eng = Engine(prob)
+        r = eng.eval_batch(X, LAM, sigma=0.7)
+        for b in range(B):
+            o = ev.sparse(X[b], LAM[b], 0.7)
+            for k in ("f", "g", "gradf", "jac", "hess"):
+                np.testing.assert_allclose(r[k][b], o[k], rtol=1e-12, atol=1e-12 * (1 + np.abs(o[k]).max(initial=0)))
+            np.testing.assert_allclose(np.concatenate([[r["f"][b]], r["g"][b]]), nm.values(X[b]), rtol=1e-12, atol=1e-12)
+        eng.close()
+
+
+@pytest.mark.gpu
+def test_wide_terms_relaxations_match_the_oracle(bnlp_lib, oracle_ipm):
+    from bonmin_b200.engine import Engine, Problem
+    m = I.wide_terms_minlp()
+    eng = Engine(Problem.from_nl(nlwrite.write_nl(m)))
+    root = eng.solve_batch(m.xl, m.xu, m.x0)
+    oroot = oracle_ipm.solve_batch(m, m.xl, m.xu, m.x0)
+    assert root["status"][0] == oroot["status"][0] == 1
+    assert root["obj"][0] == pytest.approx(oroot["obj"][0], rel=1e-6)
+    xs = root["x"][0]
+    XL, XU = I.c3_children(m, xs, 96)
+    r = eng.solve_batch(XL, XU, xs)
+    o = oracle_ipm.solve_batch(m, XL, XU, xs, threads=8)
+    assert (r["status"] == o["status"]).all(), np.flatnonzero(r["status"] != o["status"])
+    ok = o["status"] == 1
+    assert ok.sum() >= 40 and (o["status"] == 3).sum() >= 5
+    rel = np.abs(r["obj"] - o["obj"]) / np.maximum(1.0, np.abs(o["obj"]))
+    assert rel[ok].max() <= 1e-6
+    # the rows hold at the returned points, evaluated independently
+    ev = Evaluator(m)
+    for b in np.flatnonzero(ok)[:10]:
+        g = ev.dense(r["x"][b])[0][1:]
+        assert (g <= np.asarray(m.gu) + 1e-6).all()
+    # linearisation of the wide rows at the root (getOuterApproximation): a valid cut at random feasible-ish points
+    cuts = eng.oa_batch(xs[None, :], root["duals"], m.xl, m.xu, get_obj=0)
+    assert cuts["rows_per_point"] >= 3
+    eng.close()
