@@ -183,6 +183,9 @@ __device__ inline void eval_term(const MM &M, int t, const double *x, HDual *st,
       case BNLP_OP_SIN: hd_unary(a, nv, sin(v), cos(v), -sin(v)); break;
       case BNLP_OP_COS: hd_unary(a, nv, cos(v), -sin(v), -cos(v)); break;
       case BNLP_OP_ABS: hd_unary(a, nv, fabs(v), v >= 0 ? 1.0 : -1.0, 0.0); break;
+      case BNLP_OP_ATAN: { const double q = 1.0 / (1.0 + v * v); hd_unary(a, nv, atan(v), q, -2.0 * v * q * q); break; }
+      case BNLP_OP_ASIN: { const double q = 1.0 / sqrt(1.0 - v * v); hd_unary(a, nv, asin(v), q, v * q * q * q); break; }
+      case BNLP_OP_ACOS: { const double q = 1.0 / sqrt(1.0 - v * v); hd_unary(a, nv, acos(v), -q, -v * q * q * q); break; }
       default: break;
     }
   }

@@ -114,7 +114,7 @@ bool model_from_desc(const bnlp_tape_desc *d, HostModel &M, std::string &err) {
           if (depth < 2) { err = "term stack underflow"; return false; }
           depth--; break;
         case BNLP_OP_NEG: case BNLP_OP_POWC: case BNLP_OP_EXP: case BNLP_OP_LOG: case BNLP_OP_SQRT:
-        case BNLP_OP_SIN: case BNLP_OP_COS: case BNLP_OP_SQR: case BNLP_OP_ABS:
+        case BNLP_OP_SIN: case BNLP_OP_COS: case BNLP_OP_SQR: case BNLP_OP_ABS: case BNLP_OP_ATAN: case BNLP_OP_ASIN: case BNLP_OP_ACOS:
           if (depth < 1) { err = "term stack underflow"; return false; }
           break;
         default: err = "unknown term opcode"; return false;

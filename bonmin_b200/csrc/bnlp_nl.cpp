@@ -61,13 +61,13 @@ bool poly_mul(const Poly &a, const Poly &b, Poly &out) {
 // tanh, tan, sinh, log10, cosh are lowered at parse time to the operations the tape has (exp, sin, cos, log, /).
 enum { O_PLUS = 0, O_MINUS = 1, O_MULT = 2, O_DIV = 3, O_POW = 5, O_ABS = 15, O_NEG = 16, O_TANH = 37, O_TAN = 38,
        O_SQRT = 39, O_SINH = 40, O_SIN = 41, O_LOG10 = 42, O_LOG = 43, O_EXP = 44, O_COSH = 45, O_COS = 46,
-       O_SUMLIST = 54, O_1POW = 75, O_2POW = 76, O_CPOW = 77 };
+       O_ATAN = 49, O_ASIN = 51, O_ACOS = 53, O_SUMLIST = 54, O_1POW = 75, O_2POW = 76, O_CPOW = 77 };
 
 int arity(int op) {
   switch (op) {
     case O_PLUS: case O_MINUS: case O_MULT: case O_DIV: case O_POW: case O_1POW: case O_CPOW: return 2;
     case O_ABS: case O_NEG: case O_SQRT: case O_SIN: case O_LOG: case O_EXP: case O_COS: case O_2POW:
-    case O_TANH: case O_TAN: case O_SINH: case O_LOG10: case O_COSH: return 1;
+    case O_TANH: case O_TAN: case O_SINH: case O_LOG10: case O_COSH: case O_ATAN: case O_ASIN: case O_ACOS: return 1;
     case O_SUMLIST: return -1;
     default: return -2;
   }
@@ -222,6 +222,9 @@ bool emit(const Node &e, const std::map<int, int> &slot, Term &T, std::string &e
     case O_SQRT: if (!kids(1)) return false; push(BNLP_OP_SQRT, 0, 0); return true;
     case O_SIN: if (!kids(1)) return false; push(BNLP_OP_SIN, 0, 0); return true;
     case O_COS: if (!kids(1)) return false; push(BNLP_OP_COS, 0, 0); return true;
+    case O_ATAN: if (!kids(1)) return false; push(BNLP_OP_ATAN, 0, 0); return true;
+    case O_ASIN: if (!kids(1)) return false; push(BNLP_OP_ASIN, 0, 0); return true;
+    case O_ACOS: if (!kids(1)) return false; push(BNLP_OP_ACOS, 0, 0); return true;
     case O_LOG: if (!kids(1)) return false; push(BNLP_OP_LOG, 0, 0); return true;
     case O_EXP: if (!kids(1)) return false; push(BNLP_OP_EXP, 0, 0); return true;
     case O_SUMLIST:

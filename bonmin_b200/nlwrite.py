@@ -10,7 +10,7 @@ import numpy as np
 from .instances import BINARY, CONTINUOUS, INF, INTEGER, unpack_lower
 
 _OPS = {2: "o0", 3: "o1", 4: "o2", 5: "o3", 8: "o5", 6: "o16", 9: "o44", 10: "o43", 11: "o39", 12: "o41", 13: "o46",
-        14: "o76", 15: "o15"}
+        14: "o76", 15: "o15", 16: "o49", 17: "o51", 18: "o53"}
 
 
 def _f(v):

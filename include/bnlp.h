@@ -38,7 +38,8 @@ enum {
 enum {
   BNLP_OP_CONST = 0, BNLP_OP_VAR = 1, BNLP_OP_ADD = 2, BNLP_OP_SUB = 3, BNLP_OP_MUL = 4, BNLP_OP_DIV = 5,
   BNLP_OP_NEG = 6, BNLP_OP_POWC = 7 /* x^darg */, BNLP_OP_POW = 8, BNLP_OP_EXP = 9, BNLP_OP_LOG = 10,
-  BNLP_OP_SQRT = 11, BNLP_OP_SIN = 12, BNLP_OP_COS = 13, BNLP_OP_SQR = 14, BNLP_OP_ABS = 15
+  BNLP_OP_SQRT = 11, BNLP_OP_SIN = 12, BNLP_OP_COS = 13, BNLP_OP_SQR = 14, BNLP_OP_ABS = 15,
+  BNLP_OP_ATAN = 16, BNLP_OP_ASIN = 17, BNLP_OP_ACOS = 18
 };
 #define BNLP_MAX_TERM_VARS 6
 #define BNLP_MAX_TERM_STACK 12

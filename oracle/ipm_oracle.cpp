@@ -68,7 +68,7 @@ struct OModel {
 constexpr int TVm = 24;
 struct HD { double v; double g[TVm]; double h[TVm][TVm]; };
 enum { OP_CONST = 0, OP_VAR, OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_NEG, OP_POWC, OP_POW, OP_EXP, OP_LOG, OP_SQRT, OP_SIN,
-       OP_COS, OP_SQR, OP_ABS };
+       OP_COS, OP_SQR, OP_ABS, OP_ATAN, OP_ASIN, OP_ACOS };
 static void hd_unary(HD &a, int nv, double f, double f1, double f2) {
   for (int i = 0; i < nv; ++i)
     for (int j = 0; j < nv; ++j) a.h[i][j] = f2 * a.g[i] * a.g[j] + f1 * a.h[i][j];
@@ -120,6 +120,9 @@ static HD eval_term(const OModel &M, int t, const double *x) {
         case OP_SIN: hd_unary(a, nv, std::sin(v), std::cos(v), -std::sin(v)); break;
         case OP_COS: hd_unary(a, nv, std::cos(v), -std::sin(v), -std::cos(v)); break;
         case OP_ABS: hd_unary(a, nv, std::fabs(v), v >= 0 ? 1.0 : -1.0, 0.0); break;
+        case OP_ATAN: { const double q = 1.0 / (1.0 + v * v); hd_unary(a, nv, std::atan(v), q, -2.0 * v * q * q); break; }
+        case OP_ASIN: { const double q = 1.0 / std::sqrt(1.0 - v * v); hd_unary(a, nv, std::asin(v), q, v * q * q * q); break; }
+        case OP_ACOS: { const double q = 1.0 / std::sqrt(1.0 - v * v); hd_unary(a, nv, std::acos(v), -q, -v * q * q * q); break; }
       }
     }
   }

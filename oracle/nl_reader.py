@@ -8,7 +8,8 @@ import numpy as np
 
 INF = 1e19
 _UN = {15: abs, 16: lambda a: -a, 37: math.tanh, 38: math.tan, 39: math.sqrt, 40: math.sinh, 41: math.sin,
-       42: math.log10, 43: math.log, 44: math.exp, 45: math.cosh, 46: math.cos, 76: lambda a: a * a}
+       42: math.log10, 43: math.log, 44: math.exp, 45: math.cosh, 46: math.cos, 49: math.atan, 51: math.asin, 53: math.acos,
+       76: lambda a: a * a}
 _BIN = {0: lambda a, b: a + b, 1: lambda a, b: a - b, 2: lambda a, b: a * b, 3: lambda a, b: a / b,
         5: lambda a, b: a ** b, 75: lambda a, b: a ** b, 77: lambda a, b: a ** b}
 

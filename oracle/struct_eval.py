@@ -19,7 +19,7 @@ DBL_MAX = sys.float_info.max
 
 # opcodes: include/bnlp.h
 (OP_CONST, OP_VAR, OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_NEG, OP_POWC, OP_POW, OP_EXP, OP_LOG, OP_SQRT, OP_SIN, OP_COS,
- OP_SQR, OP_ABS) = range(16)
+ OP_SQR, OP_ABS, OP_ATAN, OP_ASIN, OP_ACOS) = range(19)
 
 
 class _HD:
@@ -93,6 +93,15 @@ def eval_term(vars_, prog, x):
                 st.append(a.unary(math.cos(v), -math.sin(v), -math.cos(v)))
             elif op == OP_ABS:
                 st.append(a.unary(abs(v), 1.0 if v >= 0 else -1.0, 0.0))
+            elif op == OP_ATAN:
+                q = 1.0 / (1.0 + v * v)
+                st.append(a.unary(math.atan(v), q, -2.0 * v * q * q))
+            elif op == OP_ASIN:
+                q = 1.0 / math.sqrt(1.0 - v * v)
+                st.append(a.unary(math.asin(v), q, v * q ** 3))
+            elif op == OP_ACOS:
+                q = 1.0 / math.sqrt(1.0 - v * v)
+                st.append(a.unary(math.acos(v), -q, -v * q ** 3))
             else:
                 raise ValueError(op)
     assert len(st) == 1

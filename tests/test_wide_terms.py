@@ -94,3 +94,51 @@ def test_wide_terms_relaxations_match_the_oracle(bnlp_lib, oracle_ipm):
     cuts = eng.oa_batch(xs[None, :], root["duals"], m.xl, m.xu, get_obj=0)
     assert cuts["rows_per_point"] >= 3
     eng.close()
+
+
+def _inverse_trig_model():
+    """atan / asin / acos (AMPL o49 / o51 / o53): evaluation only (the rows are not convex)."""
+    m = I.wide_terms_minlp()
+    m["terms"] = [(1, [0, 1], [(I.OP_VAR, 0, 0.0), (I.OP_VAR, 1, 0.0), (I.OP_MUL, 0, 0.0), (16, 0, 0.0)]),                    # atan(x0 x1)
+                  (2, [2], [(I.OP_CONST, 0, 0.3), (I.OP_VAR, 0, 0.0), (I.OP_MUL, 0, 0.0), (17, 0, 0.0)]),                     # asin(0.3 x2)
+                  (3, [3, 4], [(I.OP_CONST, 0, 0.1), (I.OP_VAR, 0, 0.0), (I.OP_MUL, 0, 0.0), (I.OP_CONST, 0, 0.2), (I.OP_VAR, 1, 0.0),
+                               (I.OP_MUL, 0, 0.0), (I.OP_ADD, 0, 0.0), (18, 0, 0.0)])]                                        # acos(0.1 x3 + 0.2 x4)
+    m["name"] = "inverse trigonometric terms"
+    m["vtype"] = np.zeros(m.n, np.int32)         # (all continuous: only x_0..x_4 are nonlinear now, AMPL's order must still hold)
+    return m
+
+
+def test_inverse_trig_opcodes_are_read(bnlp_lib):
+    from bonmin_b200.engine import Problem
+    m = _inverse_trig_model()
+    txt = nlwrite.write_nl(m)
+    assert "o49" in txt and "o51" in txt and "o53" in txt
+    p = Problem.from_nl(txt)
+    ev = Evaluator(m)
+    assert (p.nnz_jac, p.nnz_hess) == (len(ev.jac), len(ev.hes))
+    x = np.random.default_rng(1).uniform(-1, 1, m.n)
+    np.testing.assert_allclose(NlModel(txt).values(x), ev.dense(x)[0], rtol=1e-14)
+    # derivatives of the evaluator against central differences
+    v0, g0, _ = ev.dense(x)
+    for j in range(5):
+        e = np.zeros(m.n)
+        e[j] = 1e-6
+        fd = (ev.dense(x + e)[0] - ev.dense(x - e)[0]) / 2e-6
+        np.testing.assert_allclose(g0[:, j], fd, atol=1e-7)
+
+
+@pytest.mark.gpu
+def test_inverse_trig_eval_on_device(bnlp_lib):
+    from bonmin_b200.engine import Engine, Problem
+    m = _inverse_trig_model()
+    ev = Evaluator(m)
+    eng = Engine(Problem.from_nl(nlwrite.write_nl(m)))
+    rng = np.random.default_rng(2)
+    X = rng.uniform(-1, 1, (9, m.n))
+    LAM = rng.normal(0, 1, (9, m.m))
+    r = eng.eval_batch(X, LAM, sigma=1.0)
+    for b in range(9):
+        o = ev.sparse(X[b], LAM[b], 1.0)
+        for k in ("f", "g", "gradf", "jac", "hess"):
+            np.testing.assert_allclose(r[k][b], o[k], rtol=1e-12, atol=1e-12 * (1 + np.abs(o[k]).max(initial=0)))
+    eng.close()
