@@ -213,6 +213,50 @@ extern "C" int bnlp_problem_branching_info(const bnlp_problem *p, int *prioritie
   return mask;
 }
 
+extern "C" int bnlp_problem_sos_info(const bnlp_problem *p, int *num, int *num_nz, char *types, int *priorities, int *starts,
+                                     int *indices, double *weights) {
+  if (!p || !num || !num_nz) return -1;
+  const HostModel &M = p->M;
+  *num = 0; *num_nz = 0;
+  if (M.sos_no.empty()) return 0;
+  // sets = the distinct non-zero .sosno values, in increasing order of the value; members by increasing .ref (ties and
+  // a missing .ref: by variable index)
+  std::vector<std::tuple<int, double, int>> mem;     // (set number, weight, variable)
+  for (int j = 0; j < M.n; ++j)
+    if (M.sos_no[j] != 0) mem.push_back({M.sos_no[j], M.sos_ref.empty() ? (double)j : M.sos_ref[j], j});
+  std::sort(mem.begin(), mem.end());
+  int ns = 0;
+  for (size_t e = 0; e < mem.size(); ++e) {
+    const bool first = e == 0 || std::get<0>(mem[e]) != std::get<0>(mem[e - 1]);
+    if (first) {
+      if (starts) starts[ns] = (int)e;
+      if (types) types[ns] = std::get<0>(mem[e]) > 0 ? 1 : 2;
+      if (priorities) priorities[ns] = 0;
+      ++ns;
+    }
+    if (indices) indices[e] = std::get<2>(mem[e]);
+    if (weights) weights[e] = std::get<1>(mem[e]);
+    // a set inherits the best (largest) .priority of its members, stored like the variables' (9999 - value)
+    if (priorities && !M.br_priority.empty()) priorities[ns - 1] = std::max(priorities[ns - 1], M.br_priority[std::get<2>(mem[e])]);
+  }
+  if (starts) starts[ns] = (int)mem.size();
+  if (priorities) for (int s = 0; s < ns; ++s) priorities[s] = 9999 - priorities[s];
+  if (weights && starts) {
+    // ampl_utils::sos_kludge (src/Interfaces/Ampl/sos_kludge.cpp:29-45): reference weights made strictly increasing
+    for (int s = 0; s < ns; ++s) {
+      double t = weights[starts[s]];
+      for (int e = starts[s] + 1; e < starts[s + 1]; ++e) {
+        double t1 = weights[e];
+        t += 1e-10;
+        if (t1 <= t) weights[e] = t1 = t + 1e-10;
+        t = t1;
+      }
+    }
+  }
+  *num = ns; *num_nz = (int)mem.size();
+  return 0;
+}
+
 extern "C" void bnlp_problem_free(bnlp_problem *p) { delete p; }
 
 extern "C" int bnlp_problem_sizes(const bnlp_problem *p, int *n, int *m, int *nnz_jac, int *nnz_hess) {

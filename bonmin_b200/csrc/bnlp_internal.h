@@ -40,6 +40,10 @@ struct HostModel {
   // empty = suffix absent
   std::vector<int> br_priority, br_direction;
   std::vector<double> br_up_ps, br_down_ps;
+  // SOS suffixes of the variables (AmplTMINLP::read_sos, BonAmplTMINLP.cpp:254-296): .sosno (set number: > 0 type 1, < 0
+  // type 2, 0 = in no set) and .ref (reference weight); empty = suffix absent
+  std::vector<int> sos_no;
+  std::vector<double> sos_ref;
   // derived structures (TMINLP::eval_jac_g / eval_h sparsity, BonTMINLP.hpp:286-315), 0-based
   std::vector<int> jac_row, jac_col;       // rows 0..m-1 (constraints only), row-major sorted
   std::vector<int> jac_start;              // m+1

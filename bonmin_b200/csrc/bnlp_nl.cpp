@@ -420,8 +420,8 @@ bool parse_nl(const char *text, size_t len, HostModel &M, std::string &err) {
       for (int i = 0; i < cnt; ++i) L.next(s);
     } else if (k == 'S') {
       // suffix "S<kind> <count> <name>": kind & 3 = 0 variables, 1 constraints, 2 objectives, 3 problem; kind & 4 = real values.
-      // The variable suffixes AmplTMINLP::read_priorities uses are kept (BonAmplTMINLP.cpp:215-252); SOS suffixes
-      // (sosno / ref, read_sos :254-296) and the rest are skipped.
+      // The variable suffixes AmplTMINLP::read_priorities (BonAmplTMINLP.cpp:215-252) and read_sos (:254-296: sosno, ref) use
+      // are kept; the rest are skipped.
       std::stringstream ss(s.substr(1));
       int kind = 0, cnt = 0;
       std::string name;
@@ -433,6 +433,8 @@ bool parse_nl(const char *text, size_t len, HostModel &M, std::string &err) {
         else if (name == "direction") ti = &M.br_direction;
         else if (name == "upPseudocost") td = &M.br_up_ps;
         else if (name == "downPseudocost") td = &M.br_down_ps;
+        else if (name == "sosno") ti = &M.sos_no;
+        else if (name == "ref") td = &M.sos_ref;
       }
       if (ti) ti->assign(n, 0);
       if (td) td->assign(n, 0.0);

@@ -61,7 +61,7 @@ EXPORTS = ["bnlp_last_error", "bnlp_problem_from_nl", "bnlp_problem_from_tape", 
            "bnlp_resolve_cb", "bnlp_resolve_engine", "bnlp_problem_fp", "bnlp_solve_children", "bnlp_bb_run_cb3",
            "bnlp_write_node_files", "bnlp_read_bounds_file", "bnlp_read_start_file", "bnlp_write_batch_replay",
            "bnlp_read_batch_replay_header", "bnlp_read_batch_replay", "bnlp_sol_status", "bnlp_nl_header_options",
-           "bnlp_write_sol", "bnlp_write_plain_sol", "bnlp_problem_cut_strengthening", "bnlp_problem_branching_info", "bnlp_host_register", "bnlp_host_unregister", "bnlp_host_selftest", "bnlp_linearizer_engine",
+           "bnlp_write_sol", "bnlp_write_plain_sol", "bnlp_problem_cut_strengthening", "bnlp_problem_branching_info", "bnlp_problem_sos_info", "bnlp_host_register", "bnlp_host_unregister", "bnlp_host_selftest", "bnlp_linearizer_engine",
            "bnlp_comm_unique_id", "bnlp_comm_create", "bnlp_comm_free", "bnlp_comm_stats", "bnlp_comm_allreduce_min",
            "bnlp_solve_batch_sharded", "bnlp_bb_run_engine_sharded"]
 
@@ -237,6 +237,21 @@ class Problem:
             raise BnlpError("bnlp_problem_branching_info failed")
         return dict(priorities=pri if mask & 1 else None, directions=dr if mask & 2 else None,
                     up=up if mask & 4 else None, down=dn if mask & 8 else None)
+
+    def sos_info(self):
+        """TMINLP::sosConstraints(): None, or dict(types, priorities, starts, indices, weights) from the .sosno / .ref suffixes."""
+        L = lib()
+        L.bnlp_problem_sos_info.argtypes = [c_void] * 8
+        num, nz = c_int(), c_int()
+        if L.bnlp_problem_sos_info(self.h, ctypes.byref(num), ctypes.byref(nz), None, None, None, None, None):
+            raise BnlpError("bnlp_problem_sos_info failed")
+        if num.value == 0:
+            return None
+        types = np.zeros(num.value, np.int8)
+        pri, starts = np.zeros(num.value, np.int32), np.zeros(num.value + 1, np.int32)
+        idx, wts = np.zeros(nz.value, np.int32), np.zeros(nz.value)
+        L.bnlp_problem_sos_info(self.h, ctypes.byref(num), ctypes.byref(nz), _vp(types), _vp(pri), _vp(starts), _vp(idx), _vp(wts))
+        return dict(types=types, priorities=pri, starts=starts, indices=idx, weights=wts)
 
     def cs_variant(self, constr_index):
         """CutStrengthener::StrengtheningTNLP for row `constr_index` (-1: the objective cut) as a new Problem whose last

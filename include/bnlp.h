@@ -138,6 +138,14 @@ int bnlp_problem_info(const bnlp_problem *, int *jac_irow, int *jac_jcol, int *h
  * variable suffixes (src/Interfaces/Ampl/BonAmplTMINLP.cpp:215-252): priorities (9999 - suffix value: the LOWEST number is
  * branched on first), branching directions, up / down pseudo-costs (one given: used for both).  Arrays of n or NULL.
  * Returns a bit mask of what the model has (1 priorities, 2 directions, 4 up, 8 down), 0 for none, -1 on error. */
+/* TMINLP::sosConstraints() (src/Interfaces/BonTMINLP.hpp:114-150 SosInfo) as AmplTMINLP::read_sos fills it from the .nl
+ * variable suffixes .sosno / .ref (src/Interfaces/Ampl/BonAmplTMINLP.cpp:254-296): num sets, num_nz members; per set its type
+ * (1 or 2: sign of .sosno), priority (9999 - the largest .priority of its members) and starts[num + 1] into indices /
+ * weights (members by increasing .ref, made strictly increasing as ampl_utils::sos_kludge does, sos_kludge.cpp:29-45).
+ * Call once with null arrays for the sizes.  The grouping itself is ASL's suf_sos, which is not in the reference tree: restated
+ * from its documented meaning (parity-unpinned).  The engine does not branch on the sets (SOS branching objects are Cbc's). */
+int bnlp_problem_sos_info(const bnlp_problem *, int *num, int *num_nz, char *types, int *priorities, int *starts, int *indices,
+                          double *weights);
 int bnlp_problem_branching_info(const bnlp_problem *, int *priorities, int *directions, double *up_pseudo,
                                 double *down_pseudo);
 

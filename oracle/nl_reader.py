@@ -115,6 +115,36 @@ class NlModel:
             up = dn
         return dict(priorities=None if pri is None else 9999 - pri, directions=dense("direction", np.int64), up=up, down=dn)
 
+    def sos_info(self):
+        """AmplTMINLP::read_sos (BonAmplTMINLP.cpp:254-296) from the .sosno / .ref variable suffixes: sets by increasing set
+        number, type 1 for a positive number and 2 for a negative one, members by increasing reference weight, weights made
+        strictly increasing (sos_kludge.cpp:29-45), priority 9999 - the largest member priority."""
+        no = self.suffixes.get((0, "sosno"))
+        if not no:
+            return None
+        ref = self.suffixes.get((0, "ref")) or {}
+        pri = self.suffixes.get((0, "priority")) or {}
+        mem = sorted((int(s), float(ref.get(j, 0.0)) if ref else float(j), j) for j, s in no.items() if int(s) != 0)
+        types, prios, starts, idx, wts = [], [], [], [], []
+        for e, (s, w, j) in enumerate(mem):
+            if e == 0 or s != mem[e - 1][0]:
+                starts.append(e)
+                types.append(1 if s > 0 else 2)
+                prios.append(0)
+            idx.append(j)
+            wts.append(w)
+            prios[-1] = max(prios[-1], int(pri.get(j, 0)))
+        starts.append(len(mem))
+        for k in range(len(types)):
+            t = wts[starts[k]]
+            for e in range(starts[k] + 1, starts[k + 1]):
+                t += 1e-10
+                if wts[e] <= t:
+                    wts[e] = t + 1e-10
+                t = wts[e]
+        return dict(types=np.array(types), priorities=9999 - np.array(prios), starts=np.array(starts), indices=np.array(idx),
+                    weights=np.array(wts))
+
     def _next(self):
         s = self._l[self._p]
         self._p += 1

@@ -158,3 +158,31 @@ def test_variable_suffixes_branching_info(bnlp_lib):
     q = _problem(open(os.path.join(G, "mytoy.nl")).read())
     assert (p.n, p.m, p.nnz_jac, p.nnz_hess) == (q.n, q.m, q.nnz_jac, q.nnz_hess)
     assert q.branching_info() == dict(priorities=None, directions=None, up=None, down=None)
+
+
+def test_sos_suffixes(bnlp_lib):
+    """AmplTMINLP::read_sos (BonAmplTMINLP.cpp:254-296): the .sosno / .ref variable suffixes become TMINLP::SosInfo — sets by
+    set number, type from its sign, members by reference weight (made strictly increasing, sos_kludge.cpp:29-45), set priority
+    from the members' .priority.  The fixture has one set {y1, y2} (sosno 1); a second file adds a type-2 set with equal
+    reference weights."""
+    txt = open(os.path.join(G, "nl_samples", "mytoy_suffixes.nl")).read()
+    p = _problem(txt)
+    s = p.sos_info()
+    assert list(s["types"]) == [1] and list(s["starts"]) == [0, 2] and list(s["indices"]) == [0, 1]
+    assert list(s["priorities"]) == [9998]                     # y1 has priority 1, y2 none
+    assert s["weights"][1] > s["weights"][0]
+    o = NlModel(txt).sos_info()
+    for k in ("types", "priorities", "starts", "indices"):
+        assert list(o[k]) == list(s[k])
+    np.testing.assert_allclose(o["weights"], s["weights"])
+    txt2 = txt.replace("S0 2 sosno\n0 1\n1 1", "S0 4 sosno\n0 1\n1 1\n2 -3\n3 -3\nS4 4 ref\n0 2.5\n1 1.5\n2 4\n3 4")
+    s2 = _problem(txt2).sos_info()
+    assert list(s2["types"]) == [2, 1] and list(s2["starts"]) == [0, 2, 4]          # set -3 first, then set 1
+    assert list(s2["indices"]) == [2, 3, 1, 0]                                        # set 1 ordered by its weights 1.5 < 2.5
+    assert s2["weights"][1] == pytest.approx(4.0 + 2e-10, abs=1e-12) and list(s2["weights"][2:]) == [1.5, 2.5]
+    assert list(s2["priorities"]) == [9992, 9998]                                      # x has priority 7, z 5; y1 1
+    o2 = NlModel(txt2).sos_info()
+    for k in ("types", "priorities", "starts", "indices"):
+        assert list(o2[k]) == list(s2[k])
+    np.testing.assert_allclose(o2["weights"], s2["weights"], rtol=0, atol=1e-15)
+    assert _problem(open(os.path.join(G, "mytoy.nl")).read()).sos_info() is None
