@@ -101,3 +101,70 @@ def solve_batch(model, XL, XU, x0, threads=1, max_iter=0, dense=None, dual0=None
                                   None if d0 is None else _p(d0), ci(int(d0 is not None and d0.ndim == 2)), ci(threads),
                                   ci(max_iter), _p(OBJ), _p(STATUS, ci), _p(ITERS, ci), _p(X), _p(G), _p(D), _p(P1, ci))
     return dict(obj=OBJ, status=STATUS, iters=ITERS, x=X, g=G, duals=D, phase1_iters=P1)
+
+
+def oa_batch(model, ev, X, duals=None, get_obj=1, threads=1, dense=None, as_cuts=True):
+    """B x getOuterApproximation on host threads (oracle_oa_batch, the C++ restatement beside struct_eval.outer_approximation).
+    ev: oracle.struct_eval.Evaluator of the model (Jacobian structure).  Returns per point the list of cuts
+    (src_row, cols, vals, lb, ub) — or, with as_cuts=False, the raw fixed-capacity arrays (the timing baseline of bench.py)."""
+    n, m = model.n, model.m
+    X = np.ascontiguousarray(np.atleast_2d(X), dtype=np.float64)
+    B = X.shape[0]
+    c, A, qidx, Q = dense if dense is not None else dense_arrays(model)
+    arr = lambda a: np.ascontiguousarray(a, dtype=np.float64)  # noqa: E731
+    xl, xu, gl, gu = arr(model.xl), arr(model.xu), arr(model.gl), arr(model.gu)
+    ci = ctypes.c_int
+    tfn, tvs, tv, tos, top, tia, tda = [], [0], [], [0], [], [], []
+    for fn, vars_, prog in model.get("terms", []):
+        tfn.append(fn)
+        tv.extend(vars_)
+        tvs.append(len(tv))
+        for op, ia, da in prog:
+            top.append(op)
+            tia.append(ia)
+            tda.append(da)
+        tos.append(len(top))
+    ti = lambda a: np.ascontiguousarray(a if len(a) else [0], dtype=np.int32)  # noqa: E731
+    tfn_a, tvs_a, tv_a, tos_a, top_a, tia_a = ti(tfn), ti(tvs), ti(tv), ti(tos), ti(top), ti(tia)
+    tda_a = np.ascontiguousarray(tda if len(tda) else [0.0], dtype=np.float64)
+    jac_start = np.zeros(m + 1, np.int32)
+    for i, _ in ev.jac:
+        jac_start[i + 1] += 1
+    jac_start = np.cumsum(jac_start).astype(np.int32)
+    jac_col = ti([j for _, j in ev.jac])
+    nl_rows = ti([i for i in range(m) if ev.con_nonlinear[i]])
+    mnl = int(sum(1 for i in range(m) if ev.con_nonlinear[i]))
+    cap = [0]
+    for s in range(mnl):
+        i = int(nl_rows[s])
+        cap.append(cap[-1] + int(jac_start[i + 1] - jac_start[i]))
+    cap.append(cap[-1] + n + 1)
+    cap_start = ti(cap)
+    slots = mnl + 1
+    CNT = np.zeros(B * slots, np.int32)
+    COLS = np.zeros(B * cap[-1], np.int32)
+    VALS = np.zeros(B * cap[-1])
+    LB, UB = np.zeros(B * slots), np.zeros(B * slots)
+    D = None if duals is None else np.ascontiguousarray(np.atleast_2d(duals), dtype=np.float64)
+    if D is not None and D.shape[0] == 1 and B > 1:
+        D = np.ascontiguousarray(np.tile(D, (B, 1)))
+    L = lib()
+    L.oracle_oa_batch.restype = ci
+    L.oracle_oa_batch(ci(n), ci(m), _p(xl), _p(xu), _p(gl), _p(gu), _p(c), _p(A), _p(qidx, ci), _p(Q), ci(len(tfn)), _p(tfn_a, ci),
+                      _p(tvs_a, ci), _p(tv_a, ci), _p(tos_a, ci), _p(top_a, ci), _p(tia_a, ci), _p(tda_a), _p(jac_start, ci),
+                      _p(jac_col, ci), ci(mnl), _p(nl_rows, ci), ci(int(ev.obj_nonlinear)), _p(cap_start, ci), ci(B), _p(X),
+                      None if D is None else _p(D), ci(get_obj), ci(threads), _p(CNT, ci), _p(COLS, ci), _p(VALS), _p(LB), _p(UB))
+    if not as_cuts:
+        return dict(cnt=CNT, cols=COLS, vals=VALS, lb=LB, ub=UB, slots=slots, cap=cap[-1], cap_start=cap_start)
+    out = []
+    for b in range(B):
+        cuts = []
+        for s in range(slots):
+            k = int(CNT[b * slots + s])
+            if k < 0:
+                continue
+            o = b * cap[-1] + cap[s]
+            src = int(nl_rows[s]) if s < mnl else m
+            cuts.append((src, COLS[o:o + k].tolist(), VALS[o:o + k].tolist(), float(LB[b * slots + s]), float(UB[b * slots + s])))
+        out.append(cuts)
+    return out

@@ -905,4 +905,123 @@ int oracle_solve_batch(int n, int m, const double *xl, const double *xu, const d
                                  threads, max_iter, OBJ, STATUS, ITERS, X, G, DUALS, P1ITERS);
 }
 
+// ---- B x OsiTMINLPInterface::getOuterApproximation (src/Interfaces/BonOsiTMINLPInterface.cpp:1924-2107, cleanNnz :1881-1919)
+// on `threads` host threads, one point per thread at a time: the CPU baseline of the batched OA kernels (bench.py) and a second
+// checker beside oracle/struct_eval.py (same semantics, restated line by line from the same reference lines).
+// jac_start / jac_col: structural columns of every row (m + 1 entries / nnz), obj_cols: structural columns of the objective
+// gradient are all n (the reference loops over every column, :2063).  Slot s < mnl = the s-th nonlinear row (nl_rows[s]),
+// slot mnl = the objective cut.  Fixed-capacity output: slot s of point b writes at cap_start[s] of its block of `cap` entries.
+// DUALS (B x (2n+m)) may be null.  get_obj as in the reference (0 none, 1 if the objective is nonlinear, 2 always).
+int oracle_oa_batch(int n, int m, const double *xl, const double *xu, const double *gl, const double *gu, const double *c,
+                    const double *A, const int *qidx, const double *Q, int n_terms, const int *term_fn,
+                    const int *term_var_start, const int *term_var, const int *term_op_start, const int *term_op,
+                    const int *term_iarg, const double *term_darg, const int *jac_start, const int *jac_col, int mnl,
+                    const int *nl_rows, int obj_nonlinear, const int *cap_start, int B, const double *X, const double *DUALS,
+                    int get_obj, int threads, int *CNT, int *COLS, double *VALS, double *LB, double *UB) {
+  OModel M{n, m, xl, xu, gl, gu, c, A, qidx, Q};
+  M.n_terms = n_terms; M.term_fn = term_fn; M.term_var_start = term_var_start; M.term_var = term_var;
+  M.term_op_start = term_op_start; M.term_op = term_op; M.term_iarg = term_iarg; M.term_darg = term_darg;
+  const double DMAX = 1.7976931348623157e308, tiny = 1e-8, very_tiny = 1e-17, rhs_relax = 1e-8, infty_ = 1e19;
+  const int slots = mnl + 1, cap = cap_start[slots];
+  const bool want_obj = get_obj == 2 || (get_obj && obj_nonlinear);
+  auto clean_nnz = [&](double value, double colLower, double colUpper, double rowLower, double rowUpper, double colsol,
+                       double &lb, double &ub, double vtiny) {
+    if (std::fabs(value) >= tiny) return true;
+    if (std::fabs(value) < vtiny) return false;
+    const bool colUpBounded = colUpper < infty_, colLoBounded = colLower > -infty_;
+    const bool rowNotLoBounded = rowLower <= -infty_, rowNotUpBounded = rowUpper >= infty_;
+    const bool pos = value > 0;
+    if (colUpBounded && pos && rowNotUpBounded) { lb += value * (colsol - colUpper); return false; }
+    if (colUpBounded && !pos && rowNotLoBounded) { ub += value * (colsol - colUpper); return false; }
+    if (colLoBounded && !pos && rowNotUpBounded) { lb += value * (colsol - colLower); return false; }
+    if (colLoBounded && pos && rowNotLoBounded) { ub += value * (colsol - colLower); return false; }
+    return true;
+  };
+  std::atomic<int> next(0);
+  auto work = [&]() {
+    std::vector<double> grad(n), u(n);
+    for (;;) {
+      const int b = next.fetch_add(1);
+      if (b >= B) break;
+      const double *x = X + (size_t)b * n;
+      // value and dense gradient of function k at x
+      auto eval_fn = [&](int k, double &val) {
+        val = c[k];
+        const double *a = A + (size_t)k * n;
+        for (int j = 0; j < n; ++j) { grad[j] = a[j]; val += a[j] * x[j]; }
+        if (qidx[k] >= 0) {
+          const double *Qk = Q + (size_t)qidx[k] * n * n;
+          double q = 0.0;
+          for (int i = 0; i < n; ++i) {
+            const double *row = Qk + (size_t)i * n;
+            double acc = 0.0;
+            for (int j = 0; j < n; ++j) acc += row[j] * x[j];
+            grad[i] += acc;
+            q += x[i] * acc;
+          }
+          val += 0.5 * q;
+        }
+        for (int t = 0; t < n_terms; ++t) {
+          if (term_fn[t] != k) continue;
+          const HD r = eval_term(M, t, x);
+          const int v0 = term_var_start[t], nv = term_var_start[t + 1] - v0;
+          val += r.v;
+          for (int q2 = 0; q2 < nv; ++q2) grad[term_var[v0 + q2]] += r.g[q2];
+        }
+      };
+      for (int s = 0; s < mnl; ++s) {
+        const int i = nl_rows[s], o = b * slots + s;
+        double g;
+        eval_fn(i + 1, g);
+        double lb = gl[i] > -infty_ ? gl[i] - g : -DMAX, ub = gu[i] < infty_ ? gu[i] - g : DMAX;
+        if (DUALS && gl[i] > -DMAX && gu[i] < DMAX) {                              // :1968-1974
+          const double d = DUALS[(size_t)b * (2 * n + m) + 2 * n + i];
+          if (d >= 0) lb = -DMAX;
+          if (d <= 0) ub = DMAX;
+        }
+        int cnt = 0;
+        int *cols = COLS + (size_t)b * cap + cap_start[s];
+        double *vals = VALS + (size_t)b * cap + cap_start[s];
+        for (int e = jac_start[i]; e < jac_start[i + 1]; ++e) {                    // :1981-1999
+          const int j = jac_col[e];
+          const double v = grad[j];
+          if (clean_nnz(v, xl[j], xu[j], gl[i], gu[i], x[j], lb, ub, very_tiny)) {
+            cols[cnt] = j; vals[cnt] = v; ++cnt;
+            if (lb > -DMAX) lb += v * x[j];
+            if (ub < DMAX) ub += v * x[j];
+          }
+        }
+        if (lb > DMAX) lb -= rhs_relax * std::max(std::fabs(lb), 1.0);             // dead code in the reference (:2043)
+        if (ub < DMAX) ub += rhs_relax * std::max(std::fabs(ub), 1.0);
+        CNT[o] = cnt; LB[o] = lb; UB[o] = ub;
+      }
+      {
+        const int o = b * slots + mnl;
+        CNT[o] = -1; LB[o] = -DMAX; UB[o] = DMAX;
+        if (want_obj) {                                                            // :2053-2105
+          double f;
+          eval_fn(0, f);
+          double lb = -f, ub = -f;
+          int cnt = 0;
+          int *cols = COLS + (size_t)b * cap + cap_start[mnl];
+          double *vals = VALS + (size_t)b * cap + cap_start[mnl];
+          for (int j = 0; j < n; ++j) {
+            if (clean_nnz(grad[j], xl[j], xu[j], -DMAX, 0.0, x[j], lb, ub, 1e-15)) {
+              cols[cnt] = j; vals[cnt] = grad[j]; ++cnt;
+              lb += grad[j] * x[j]; ub += grad[j] * x[j];
+            }
+          }
+          cols[cnt] = n; vals[cnt] = -1.0; ++cnt;
+          CNT[o] = cnt; LB[o] = -DMAX; UB[o] = ub;
+        }
+      }
+    }
+  };
+  if (threads <= 1) { work(); return 0; }
+  std::vector<std::thread> th;
+  for (int t = 0; t < threads; ++t) th.emplace_back(work);
+  for (auto &t : th) t.join();
+  return 0;
+}
+
 }  // extern "C"

@@ -109,3 +109,28 @@ def _toy_point(m, s5):
             if abs(x[j] - target) < 1e-5:
                 x[j] = target
     return x
+
+
+def test_cpp_outer_approximation_matches_the_numpy_restatement(oracle_ipm):
+    """oracle_oa_batch (C++, one point per host thread: the CPU baseline of the OA kernels in bench.py) against
+    struct_eval.outer_approximation (numpy), both restated from BonOsiTMINLPInterface.cpp:1881-2107: same kept columns,
+    coefficients, sides, with and without multipliers, for every getObj mode."""
+    from bonmin_b200 import instances as I
+    from oracle import struct_eval as SE
+    for m in (I.mytoy(), I.syn_cvx_minlp(14, 4, 3, 4, 2), I.syn_miqcp(20, 8, 4, 4, 3), I.wide_terms_minlp()):
+        ev = SE.Evaluator(m)
+        rng = np.random.default_rng(1)
+        X = np.clip(m.x0 + rng.normal(0, 0.3, (5, m.n)), np.maximum(m.xl, -20), np.minimum(m.xu, 20))
+        X[0, : min(3, m.n)] = np.asarray(m.xl)[: min(3, m.n)] + 1e-12           # tiny gradients exercise cleanNnz
+        D = rng.normal(0, 1, (5, 2 * m.n + m.m))
+        for du in (None, D):
+            for go in (0, 1, 2):
+                got = oracle_ipm.oa_batch(m, ev, X, du, get_obj=go, threads=3)
+                for b in range(5):
+                    want = SE.outer_approximation(ev, X[b], None if du is None else du[b], m.xl, m.xu, get_obj=go)
+                    assert [g[0] for g in got[b]] == [w[0] for w in want]
+                    for g, w in zip(got[b], want):
+                        assert g[1] == list(w[1])
+                        np.testing.assert_allclose(g[2], w[2], rtol=1e-13, atol=1e-14)
+                        sc = 1 + 20 * np.abs(np.array(w[2])).sum()
+                        assert all(a == b_ or abs(a - b_) <= 1e-12 * sc for a, b_ in ((g[3], w[3]), (g[4], w[4])))
