@@ -112,7 +112,7 @@ struct Device {
   DBuf<int> dCP, dCC, dCW;
   DBuf<long long> stats;
   // eval buffers
-  DBuf<double> eX, eLAM, eF, eG, eGF, eJ, eH, eX2, eDU, eU, oVal, oLB, oUB;
+  DBuf<double> eX, eLAM, eF, eG, eGF, eJ, eH, eX2, eDU, eU, eTH, oVal, oLB, oUB;
   DBuf<int> oRS, oCI, oSR;
   DevModel dm{};
 };
@@ -714,7 +714,7 @@ extern "C" void bnlp_engine_free(bnlp_engine *E) {
     cudaSetDevice(D.id);
     for (auto *b : {&D.c, &D.A, &D.Qp, &D.Qf, &D.row_sgn, &D.row_bnd, &D.gl, &D.gu, &D.xl, &D.xu, &D.e_dbl, &D.dXL, &D.dXU,
                     &D.dX0, &D.dOBJ, &D.dX, &D.dG, &D.dD, &D.dD0, &D.ws, &D.cxw, &D.cW, &D.cxd, &D.xch, &D.eq_bnd, &D.eX, &D.eLAM, &D.eF, &D.eG, &D.eGF, &D.eJ, &D.eH,
-                    &D.eX2, &D.eDU, &D.eU, &D.oVal, &D.oLB, &D.oUB, &D.dPXL, &D.dPXU, &D.dCB})
+                    &D.eX2, &D.eDU, &D.eU, &D.eTH, &D.oVal, &D.oLB, &D.oUB, &D.dPXL, &D.dPXU, &D.dCB})
       b->release();
     for (auto *b : {&D.qidx, &D.row_fn, &D.fn_row_up, &D.fn_row_lo, &D.e_int, &D.dST, &D.dIT, &D.queue, &D.cidle, &D.eq_fn, &D.fn_eq, &D.oRS, &D.oCI,
                     &D.oSR, &D.dCP, &D.dCC, &D.dCW, &D.dense_rows, &D.sp_seg_start, &D.sp_seg_i, &D.sp_seg_k, &D.sp_ent_row, &D.sp_rows, &D.spc_row})

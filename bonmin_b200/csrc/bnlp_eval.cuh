@@ -43,6 +43,7 @@ struct EvalModelHostOffsets {
       row_cap_start = 0;
   // fixed-order accumulation of element terms (IPM kernel): terms grouped by function, Hessian entries grouped by target
   int fn_term_start = 0, fn_term_list = 0, hseg_start = 0, hseg_target = 0, hent_term = 0, hent_lidx = 0, n_hseg = 0;
+  int hseg_hpos = 0;     // position of every Hessian-entry group in the sparse Hessian structure (eval_kernel)
   // offsets into the packed double buffer
   int c = 0, lin_val = 0, qs_v = 0, term_darg = 0;
 };
@@ -58,6 +59,7 @@ struct EvalModelDev {
   const int *row_cap_start;  // mnl+2 : fixed-capacity offsets of the OA rows of one point
   const int *fn_term_start, *fn_term_list;                       // m+2, n_terms : terms of each function, in tape order
   const int *hseg_start, *hseg_target, *hent_term, *hent_lidx;   // Hessian entries grouped by packed target tri(i)+j
+  const int *hseg_hpos;    // n_hseg : position of the group's target in the sparse Hessian structure
   int n_hseg;
   const double *c, *lin_val, *qs_v, *term_darg;
   const double *gl, *gu;
@@ -82,6 +84,7 @@ inline EvalModelDev make_eval_model_dev(const EvalModelHostOffsets &o, const int
   e.nl_rows = I + o.nl_rows; e.fq_fn = I + o.fq_fn; e.fq_dense = I + o.fq_dense; e.row_cap_start = I + o.row_cap_start;
   e.fn_term_start = I + o.fn_term_start; e.fn_term_list = I + o.fn_term_list; e.hseg_start = I + o.hseg_start;
   e.hseg_target = I + o.hseg_target; e.hent_term = I + o.hent_term; e.hent_lidx = I + o.hent_lidx; e.n_hseg = o.n_hseg;
+  e.hseg_hpos = I + o.hseg_hpos;
   e.c = D + o.c; e.lin_val = D + o.lin_val; e.qs_v = D + o.qs_v; e.term_darg = D + o.term_darg;
   e.gl = gl; e.gu = gu;
   return e;
@@ -199,6 +202,7 @@ struct EvalArgs {
   double sigma;
   double *F, *G, *GRADF, *JVAL, *HVAL;   // any may be null
   const double *U;      // B x nfq x n : u = Q x of every dense quadratic block, from quad_batch_kernel (null if nfq == 0)
+  double *TH_scratch;   // B x n_terms x TH : local Hessians of the element terms (needed when HVAL is asked for and the model has terms)
 };
 
 __device__ inline int jac_pos(const EvalModelDev &M, int fn, int col, int dense) {
@@ -362,8 +366,7 @@ __global__ void __launch_bounds__(EV_NT) eval_kernel(EvalModelDev M, EvalArgs A)
   }
   __syncthreads();
   // ---- general nonlinear element terms: one thread per FUNCTION walks its terms in tape order, so values, gradients and
-  // Jacobian entries are accumulated in a fixed order (only the optional Hessian values still use atomics: entries of
-  // different functions meet in the same position)
+  // Jacobian entries are accumulated in a fixed order; the Hessian values go through per-position lists (second pass)
   if (M.n_terms > 0) {
     HDual st[TS];
     HDual r;
@@ -379,12 +382,26 @@ __global__ void __launch_bounds__(EV_NT) eval_kernel(EvalModelDev M, EvalArgs A)
           if (k == 0) { if (gf) gf[M.term_var[v0 + a]] += r.g[a]; }
           else if (jv) jv[M.term_jpos[v0 + a]] += r.g[a];
         }
-        if (hv && wgt != 0.0)
-          for (int a = 0; a < nv; ++a)
-            for (int c = 0; c <= a; ++c)
-              atomicAdd(&hv[M.term_hpos[(size_t)t * TV * TV + a * TV + c]], wgt * r.h[a * (a + 1) / 2 + c]);
+        if (hv) {      // the local Hessian is kept; the entries of different functions that meet in one position are summed below
+          double *th = A.TH_scratch + ((size_t)b * M.n_terms + t) * TH;
+          for (int a = 0; a < nv * (nv + 1) / 2; ++a) th[a] = r.h[a];
+        }
       }
       fv[k] += fk;
+    }
+    if (hv) {
+      // one thread per touched position of the Hessian, contributions in the fixed order of the host-built lists: the
+      // values are bit-reproducible (round 1 used FP64 atomics here)
+      __syncthreads();
+      for (int sg = tid; sg < M.n_hseg; sg += EV_NT) {
+        double acc = 0.0;
+        for (int e = M.hseg_start[sg]; e < M.hseg_start[sg + 1]; ++e) {
+          const int t = M.hent_term[e], k = M.term_fn[t];
+          const double wgt = (k == 0) ? A.sigma : (lam ? lam[k - 1] : 0.0);
+          if (wgt != 0.0) acc = fma(wgt, A.TH_scratch[((size_t)b * M.n_terms + t) * TH + M.hent_lidx[e]], acc);
+        }
+        hv[M.hseg_hpos[sg]] += acc;
+      }
     }
   }
   __syncthreads();

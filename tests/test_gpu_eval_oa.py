@@ -321,3 +321,17 @@ def test_linearizer_adapter_matches_the_batch_calls(bnlp_lib):
     assert li.value == int((np.asarray(m.vtype) != 0).sum())
     assert L.bnlp_linearizer_engine(eng.h, eng.problem.h, 5, vp(np.ascontiguousarray(X)), 1, 1, ctypes.byref(nc), vp(rs), vp(col), vp(val),
                                     vp(lb), vp(ub), vp(gl), 2, cap_z, None, None, None, None) == -2
+
+
+def test_hessian_values_are_bit_reproducible(bnlp_lib):
+    """eval_h with element terms: entries of different functions that meet in one position of the Hessian are summed in a
+    fixed order (per-position lists), not with floating-point atomics: two evaluations give the same bits."""
+    m = I.syn_cvx_minlp(40, 10, 12, 6, 9)
+    eng = _engine(m)
+    rng = np.random.default_rng(4)
+    X = np.clip(m.x0 + rng.normal(0, 0.3, (64, m.n)), m.xl, m.xu)
+    LAM = rng.normal(0, 1, (64, m.m))
+    a = eng.eval_batch(X, LAM, sigma=0.9, want=("hess",))["hess"]
+    for _ in range(3):
+        assert np.array_equal(a, eng.eval_batch(X, LAM, sigma=0.9, want=("hess",))["hess"])
+    eng.close()
