@@ -796,7 +796,13 @@ static int launch_ipm(bnlp_engine *E, Device &D, int B, const double *dXL, const
       cudaStreamAttrValue av{};
       av.accessPolicyWindow.base_ptr = D.xch.p;
       av.accessPolicyWindow.num_bytes = std::min(xbytes, D.l2_window_max);
-      av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)E->l2_set_aside / (double)std::max<size_t>(av.accessPolicyWindow.num_bytes, 1));
+      // Hit ratio: with EVERY access of the window persisting (ratio 1: 82.7 MB of the 126 MB L2 at C3) the DRAM traffic of a
+      // 4096-child launch is lowest (2.4 GB) but the kernel is 5 % SLOWER than with no window at all — what is left of L2 for
+      // everything else (code, spills, inputs) is then too small; 0.4 - 0.7 is the fastest setting measured (49.0 - 50.1 k against
+      // 47.3 - 47.5 k relaxations/s at ratio 1 and 47.9 - 48.6 k without a window; 7.6 GB of DRAM traffic, 1.4 % of the HBM
+      // bandwidth).  BNLP_L2_HIT_RATIO overrides.
+      static const double hit_cap = getenv("BNLP_L2_HIT_RATIO") ? atof(getenv("BNLP_L2_HIT_RATIO")) : 0.6;
+      av.accessPolicyWindow.hitRatio = (float)std::min(hit_cap, (double)E->l2_set_aside / (double)std::max<size_t>(av.accessPolicyWindow.num_bytes, 1));
       av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
       av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
       windowed = E->l2_set_aside > 0 && cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &av) == cudaSuccess;
