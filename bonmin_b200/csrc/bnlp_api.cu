@@ -804,7 +804,7 @@ static int launch_ipm(bnlp_engine *E, Device &D, int B, const double *dXL, const
       static const double hit_cap = getenv("BNLP_L2_HIT_RATIO") ? atof(getenv("BNLP_L2_HIT_RATIO")) : 0.6;
       av.accessPolicyWindow.hitRatio = (float)std::min(hit_cap, (double)E->l2_set_aside / (double)std::max<size_t>(av.accessPolicyWindow.num_bytes, 1));
       av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-      av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      av.accessPolicyWindow.missProp = getenv("BNLP_L2_MISS_NORMAL") ? cudaAccessPropertyNormal : cudaAccessPropertyStreaming;
       windowed = E->l2_set_aside > 0 && cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &av) == cudaSuccess;
       if (getenv("BNLP_L2_INFO"))
         fprintf(stderr, "[bnlp] L2 window %.1f MB (exchange %.1f MB + quadratic blocks %.1f MB), set-aside %.1f MB of max %.1f MB, max window %.1f MB, hit ratio %.2f, %s\n",
