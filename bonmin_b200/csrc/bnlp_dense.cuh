@@ -485,8 +485,9 @@ __device__ __forceinline__ void chol_diag16_rest(double *H, int la, int *fail) {
 
 // panel phase of a full panel (16 columns from j0, diagonal block factored): rows [lo2, Nrows), lo2 = j0 + 16, one row
 // tile per warp at a time; the solved columns go to H and, transposed, to S[0 .. 15][i] (zero for i >= Nrows).
-__device__ __forceinline__ void panel16_rows(double *H, int j0, int Nrows, double *S, int ld) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+// (t0, tstride: the calling warp takes the row tiles t0, t0 + tstride, ... counted from row lo2)
+__device__ __forceinline__ void panel16_rows(double *H, int j0, int Nrows, double *S, int ld, int t0 = -1, int tstride = IPM_NW) {
+  const int lane = threadIdx.x & 31, w = t0 >= 0 ? t0 : (int)(threadIdx.x >> 5);
   const int lr = lane >> 2, lc = lane & 3, cc = 2 * lc;
   const int j1 = j0 + 8, lo2 = j0 + 16, hi8 = (Nrows + 7) & ~7;
   double bx0[2], bx1[2], bl[2];
@@ -497,7 +498,7 @@ __device__ __forceinline__ void panel16_rows(double *H, int j0, int Nrows, doubl
     bx1[ks] = (kk <= lr) ? H[tri(j1 + lr) + j1 + kk] : 0.0;
     bl[ks] = H[tri(j1 + lr) + j0 + kk];            // B[k][n] = L[j1 + n][j0 + k]
   }
-  for (int i0 = lo2 + 8 * w; i0 < hi8; i0 += 8 * IPM_NW) {
+  for (int i0 = lo2 + 8 * w; i0 < hi8; i0 += 8 * tstride) {
     const int i = i0 + lr;
     const bool iv = i < Nrows;
     double *Hi = H + tri(min(i, Nrows - 1));
@@ -540,12 +541,39 @@ __device__ __forceinline__ bool chol4(double *H, int N, int Nrows, double *S, in
   C2_MARK(0);
   int j0 = 0;
   for (;;) {                                  // invariant: j0 + 16 <= N and the 16 x 16 diagonal block at j0 is factored
+    const int lo = j0 + 16;
+    const bool next_full = lo + 16 <= N;
+#ifndef BNLP_CHOL4_NO_EARLY_CHAIN
+    if (next_full) {
+      // Warp 0 solves the two row tiles of the NEXT diagonal block itself and goes straight on to that block's update and
+      // pivot chain; it only ARRIVES at the barrier that separates the other warps' panel rows from their trailing update
+      // (named barrier 1: 15 warps wait, warp 0 does not), so in the late panels — where the chain is longer than the
+      // trailing update — the chain no longer starts behind everybody's panel phase.
+      if (w == 0) {
+        panel16_rows(H, j0, Nrows, S, ld, 0, 1 << 20);
+        panel16_rows(H, j0, Nrows, S, ld, 1, 1 << 20);
+        __syncwarp();
+        asm volatile("bar.arrive 1, %0;" ::"r"(IPM_NT) : "memory");
+        syrk_rt16_sub(H, lo, Nrows, S, ld, 0, 1 << 20);
+        __syncwarp();
+        chol_diag8_invw(H, lo, fail);
+        chol_diag16_rest(H, lo, fail);
+      } else {
+        panel16_rows(H, j0, Nrows, S, ld, 1 + w, IPM_NW - 1);        // tiles 2, 3, ... over warps 1 .. NW-1
+        asm volatile("bar.sync 1, %0;" ::"r"(IPM_NT) : "memory");
+        syrk_rt16_sub(H, lo, Nrows, S, ld, w, IPM_NW - 1);
+      }
+      __syncthreads();
+      C2_MARK(3);
+      if (*fail) return false;
+      j0 = lo;
+      continue;
+    }
+#endif
     panel16_rows(H, j0, Nrows, S, ld);
     __syncthreads();
     C2_MARK(1);
-    const int lo = j0 + 16;
     if (lo >= N) return true;                 // (N a multiple of 16: only carried rows were left)
-    const bool next_full = lo + 16 <= N;
     if (w == 0) {
       syrk_rt16_sub(H, lo, Nrows, S, ld, 0, 1 << 20);
       __syncwarp();
