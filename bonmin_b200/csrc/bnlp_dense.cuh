@@ -559,9 +559,16 @@ __device__ __forceinline__ bool chol4(double *H, int N, int Nrows, double *S, in
         chol_diag8_invw(H, lo, fail);
         chol_diag16_rest(H, lo, fail);
       } else {
-        panel16_rows(H, j0, Nrows, S, ld, 1 + w, IPM_NW - 1);        // tiles 2, 3, ... over warps 1 .. NW-1
+#ifndef BNLP_CHOL4_PLAIN_ORDER
+        // work goes first to the warps that do NOT share warp 0's SM sub-partition (warps 4, 8, 12 do): in the late panels,
+        // where there are fewer units than warps, the pivot chain then has its FP64 pipe to itself
+        const int rk = (w & 3) ? w - (w >> 2) : (IPM_NW - IPM_NW / 4) + (w >> 2);       // 1 .. NW-1, a permutation
+#else
+        const int rk = w;
+#endif
+        panel16_rows(H, j0, Nrows, S, ld, 1 + rk, IPM_NW - 1);       // tiles 2, 3, ... over warps 1 .. NW-1
         asm volatile("bar.sync 1, %0;" ::"r"(IPM_NT) : "memory");
-        syrk_rt16_sub(H, lo, Nrows, S, ld, w, IPM_NW - 1);
+        syrk_rt16_sub(H, lo, Nrows, S, ld, rk, IPM_NW - 1);
       }
       __syncthreads();
       C2_MARK(3);
