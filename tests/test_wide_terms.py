@@ -142,3 +142,40 @@ def test_inverse_trig_eval_on_device(bnlp_lib):
         for k in ("f", "g", "gradf", "jac", "hess"):
             np.testing.assert_allclose(r[k][b], o[k], rtol=1e-12, atol=1e-12 * (1 + np.abs(o[k]).max(initial=0)))
     eng.close()
+
+
+def test_oracle_on_wide_terms_against_scipy(oracle_ipm):
+    """The oracle's wide-term path (24-variable second-order forward mode in ipm_oracle.cpp) pinned independently: root and
+    children of the wide model against scipy SLSQP on the numpy evaluator (objective 1e-6 relative, same feasibility verdict)."""
+    from scipy.optimize import minimize
+    m = I.wide_terms_minlp()
+    ev = Evaluator(m)
+    root = oracle_ipm.solve_batch(m, m.xl, m.xu, m.x0)
+    assert root["status"][0] == 1
+    xs = root["x"][0]
+    XL, XU = I.c3_children(m, xs, 12)
+    XL = np.vstack([m.xl, XL])
+    XU = np.vstack([m.xu, XU])
+    r = oracle_ipm.solve_batch(m, XL, XU, xs, threads=4)
+    gu = np.asarray(m.gu)
+
+    def fg(x):
+        v, g, _ = ev.dense(x)
+        return v, g
+
+    n_feas = 0
+    for b in range(len(XL)):
+        fixed = XL[b] >= XU[b]
+        if (XL[b] > XU[b]).any():
+            assert r["status"][b] == 3
+            continue
+        cons = [dict(type="ineq", fun=lambda x: gu - fg(x)[0][1:], jac=lambda x: -fg(x)[1][1:])]
+        res = minimize(lambda x: fg(x)[0][0], np.clip(xs, XL[b], XU[b]), jac=lambda x: fg(x)[1][0], method="SLSQP",
+                       bounds=list(zip(XL[b], np.where(fixed, XL[b], XU[b]))), constraints=cons, options=dict(maxiter=500, ftol=1e-12))
+        viol = max(0.0, float((fg(res.x)[0][1:] - gu).max()))
+        if r["status"][b] == 1:
+            assert viol < 1e-6 and abs(res.fun - r["obj"][b]) <= 1e-6 * max(1.0, abs(res.fun)), (b, res.fun, r["obj"][b], viol)
+            n_feas += 1
+        else:
+            assert r["status"][b] == 3 and (viol > 1e-7 or not res.success), (b, viol, res.message)
+    assert n_feas >= 6
