@@ -554,7 +554,10 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(B, world),
-            "results": {"mean_ipm_iterations": iters_all / total, "optimal": int(n_opt), "infeasible": int(n_inf),
+            "results": {"mean_ipm_iterations": iters_all / total,
+                        "ipm_iterations_p50_p99_max_rank0": [float(v) for v in torch.quantile(
+                            dIT.double().flatten(), torch.tensor([0.5, 0.99, 1.0], dtype=torch.float64, device=dIT.device)).tolist()],
+                        "optimal": int(n_opt), "infeasible": int(n_inf),
                         "best_child_objective": best_bound},
             "e2e": {"value": e2e, "unit": "relaxations/s", "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": d2h * world,
@@ -596,7 +599,12 @@ def main():
             t0 = time.perf_counter()
             ipm.solve_batch(model, XL[:S], XU[:S], xs, threads=cores, dense=dense)
             dt = time.perf_counter() - t0
+            S1 = min(48, S)                     # the same port on ONE thread beside the all-cores figure
+            t1 = time.perf_counter()
+            ipm.solve_batch(model, XL[:S1], XU[:S1], xs, threads=1, dense=dense)
+            dt1 = time.perf_counter() - t1
             line["cpu_baseline"] = {"value": S / dt, "unit": "relaxations/s", "cores": cores, "kind": "port",
+                                    "one_thread": {"value": S1 / dt1, "unit": "relaxations/s", "sample": f"first {S1} children"},
                                     "sample": f"first {S} children of the step's batch, one relaxation per thread; "
                                               "CPU restatement of the Bonmin/Ipopt path — NOT Ipopt (Ipopt 3.13 cannot be built offline)"}
         if world == 1 and not args.no_sweep:
