@@ -14,9 +14,9 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libbnlp.so")
 SOURCES = ["bnlp_launch_ipm.cu", "bnlp_launch_wide.cu", "bnlp_launch_coop.cu", "bnlp_launch_coop256.cu", "bnlp_api.cu", "bnlp_model.cpp", "bnlp_nl.cpp",
-           "../host/B200Solver.cpp", "../host/host_cabi.cpp", "../host/node_files.cpp", "../host/B200Linearizer.cpp"]
+           "../host/B200Solver.cpp", "../host/host_cabi.cpp", "../host/node_files.cpp", "../host/B200Linearizer.cpp", "../host/B200Oa.cpp"]
 HOST_LIB = os.path.join(HERE, "libbnlp_host.so")
-HEADERS = ["../host/B200Solver.hpp", "../host/B200Linearizer.hpp", "../host/bonmin_shim.hpp", "bnlp_internal.h", "bnlp_ipm.cuh", "bnlp_ipm_coop.cuh",
+HEADERS = ["../host/B200Solver.hpp", "../host/B200Linearizer.hpp", "../host/B200Oa.hpp", "../host/bonmin_shim.hpp", "bnlp_internal.h", "bnlp_ipm.cuh", "bnlp_ipm_coop.cuh",
            "bnlp_dense.cuh", "bnlp_dense_tm.cuh", "bnlp_eval.cuh", "bnlp_api_eval.inc", "bnlp_api_comm.inc", "../../include/bnlp.h"]
 # headers each source depends on (None = all)
 DEPS = {
@@ -79,7 +79,8 @@ def build_host() -> str:
     host = os.path.join(HERE, "host")
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", HOST_LIB,
                            os.path.join(host, "B200Solver.cpp"), os.path.join(host, "host_cabi.cpp"),
-                           os.path.join(host, "node_files.cpp"), os.path.join(host, "B200Linearizer.cpp")])
+                           os.path.join(host, "node_files.cpp"), os.path.join(host, "B200Linearizer.cpp"),
+                           os.path.join(host, "B200Oa.cpp")])
     return HOST_LIB
 
 

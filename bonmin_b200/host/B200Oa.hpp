@@ -1,0 +1,56 @@
+// B-OA on the host side of the boundary, in C++: the outer-approximation decomposition loop of
+// OACutGenerator2::performOa (src/Algorithms/OaGenerators/BonOACutGenerator2.cpp:121-268; helpers fixIntegers /
+// isDifferentOnIntegers / installCuts in BonSolverHelp.cpp:49-174, cutoff handling post_nlp_solve in
+// BonOaDecBase.cpp:237-400) around the batched engine.  The reference holds the master MILP behind a SubMipSolver
+// (src/Algorithms/OaGenerators/BonSubMipSolver.hpp: optimize(cutoff, loglevel, maxTime), getLastSolution(), lowBound())
+// built over an OsiSolverInterface; Cbc / Osi are absent from this image, so the master is the one thing that stays a
+// callback: MasterMipFn receives the whole LP (initial relaxation + every cut installed so far, CSR by rows) and the
+// cutoff, and returns a point and a bound.  Everything else — the NLP relaxation, every NLP(y), the initial LP and the
+// linearisations at SEVERAL points per pass — is served by the arithmetic providers below, which in the product are
+// bnlp_solve_batch, bnlp_extract_linear_relaxation and bnlp_oa_batch on the CUDA engine (bnlp_oa_run_engine).
+#pragma once
+#include <functional>
+#include <vector>
+
+#include "B200Linearizer.hpp"
+#include "B200Solver.hpp"
+
+namespace Bonmin {
+
+// cuts of one getOuterApproximation call over B points: CSR rows, the source row of each (m = the objective cut)
+struct CutRows { std::vector<int> row_start{0}, col, src_row; std::vector<double> val, lb, ub;
+                 int size() const { return (int)lb.size(); } };
+
+// B x getOuterApproximation(cs, x, getObj = 1) with the side of ranged rows picked by `duals` = the multipliers of the
+// last NLP solve (getRowPrice, BonOsiTMINLPInterface.cpp:1952,1968-1974); rows that are not generated are left out
+using OaCutsFn = std::function<int(int B, const double *X, const double *duals, CutRows &out)>;
+// extractLinearRelaxation + addObjectiveFunction at (x, duals)
+using OaExtractFn = std::function<int(const double *x, const double *duals, LpRelaxation &out)>;
+// the SubMipSolver: min obj.x + obj_offset over the rows, integer columns integral, objective below `cutoff`
+// (OsiDualObjectiveLimit, BonOACutGenerator2.cpp:150).  Returns 0 solved (x: n_cols, bound), 1 infeasible / cut off,
+// < 0 error.
+using MasterMipFn = std::function<int(int n_cols, int n_rows, const int *row_start, const int *col, const double *val,
+                                      const double *row_lb, const double *row_ub, const double *col_lb, const double *col_ub,
+                                      const double *obj, double obj_offset, const int *is_integer, double cutoff,
+                                      double max_seconds, double *x, double *bound)>;
+
+struct OaOptions {
+  double cutoff_increment = 1e-5;    // relative, as the Python driver (oa.py) and B-BB's cutoff_decr
+  double gap_tol = 1e-9;
+  double time_limit = 1e10;
+  int max_passes = 200;
+  int add_master_point = 1;          // also linearise at the master point (ECP style), one engine call for both points
+};
+
+struct OaResult {
+  int status = 2;                    // 0 optimal, 1 infeasible, 2 limit reached, < 0 provider error
+  double best_obj = 1e100, lower_bound = -1e200;
+  int passes = 0, nlp_solves = 0, cuts = 0, oa_points = 0;
+  double seconds = 0, master_seconds = 0;
+  std::vector<double> best_x;
+};
+
+OaResult oa_run(const TMINLP2TNLP &root, const BatchSolveFn &solve, const OaCutsFn &oa, const OaExtractFn &extract,
+                const MasterMipFn &master, const OaOptions &opt);
+
+}  // namespace Bonmin

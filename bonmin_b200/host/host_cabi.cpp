@@ -7,6 +7,7 @@
 
 #include "../../include/bnlp.h"
 #include "B200Linearizer.hpp"
+#include "B200Oa.hpp"
 #include "B200Solver.hpp"
 
 extern "C" {
@@ -117,6 +118,68 @@ struct MockTNLP : public Ipopt::TNLP {
   }
 };
 }  // namespace
+
+// B-OA (B200Oa.cpp) over caller-supplied arithmetic and master
+int bnlp_oa_run_cb(int n, int m, const int *var_type, const double *xl, const double *xu, const double *x0,
+                   bnlp_batch_solve_cb solve, bnlp_oa_cuts_cb cuts, bnlp_oa_extract_cb extract, bnlp_master_mip_cb master,
+                   void *ctx, const bnlp_oa_run_options *o, bnlp_oa_run_result *res, double *best_x) {
+  using namespace Bonmin;
+  if (!solve || !cuts || !extract || !master || !res || n <= 0 || m < 0) return -1;
+  Ipopt::SmartPtr<TMINLP2TNLP> holder = new TMINLP2TNLP();
+  TMINLP2TNLP &root = *holder;
+  root.n = n; root.m = m;
+  root.var_types.assign(var_type, var_type + n);
+  root.x_l_.assign(xl, xl + n); root.x_u_.assign(xu, xu + n);
+  if (x0) root.x_init_.assign(x0, x0 + n);
+  OaOptions opt;
+  if (o) {
+    if (o->cutoff_increment > 0) opt.cutoff_increment = o->cutoff_increment;
+    if (o->gap_tol > 0) opt.gap_tol = o->gap_tol;
+    if (o->time_limit > 0) opt.time_limit = o->time_limit;
+    if (o->max_passes > 0) opt.max_passes = o->max_passes;
+    opt.add_master_point = o->no_master_point ? 0 : 1;
+  }
+  BatchSolveFn sf = [solve, ctx](int B, const double *XL, const double *XU, const double *X0, double *OBJ, int *STATUS,
+                                 int *ITERS, double *X, double *G, double *DUALS) {
+    return solve(ctx, B, XL, XU, X0, OBJ, STATUS, ITERS, X, G, DUALS);
+  };
+  const size_t rows_cap = (size_t)m + 1, nnz_row = (size_t)n + 1;
+  OaCutsFn cf = [cuts, ctx, rows_cap, nnz_row](int B, const double *X, const double *duals, CutRows &out) {
+    const int cap_cuts = (int)(B * rows_cap), cap_nnz = (int)(B * rows_cap * nnz_row);
+    out.row_start.assign(cap_cuts + 1, 0); out.col.resize(cap_nnz); out.val.resize(cap_nnz);
+    out.lb.resize(cap_cuts); out.ub.resize(cap_cuts); out.src_row.resize(cap_cuts);
+    int nc = 0;
+    const int rc = cuts(ctx, B, X, duals, &nc, out.row_start.data(), out.col.data(), out.val.data(), out.lb.data(), out.ub.data(),
+                        out.src_row.data(), cap_cuts, cap_nnz);
+    if (rc) return rc;
+    if (nc < 0 || nc > cap_cuts) return -2;
+    out.row_start.resize(nc + 1); out.lb.resize(nc); out.ub.resize(nc); out.src_row.resize(nc);
+    return 0;
+  };
+  OaExtractFn ef = [extract, ctx, rows_cap, nnz_row, n](const double *x, const double *duals, LpRelaxation &lp) {
+    const int cap_rows = (int)rows_cap, cap_nnz = (int)(rows_cap * nnz_row);
+    lp.row_start.assign(cap_rows + 1, 0); lp.col.resize(cap_nnz); lp.val.resize(cap_nnz);
+    lp.row_lb.resize(cap_rows); lp.row_ub.resize(cap_rows); lp.obj.assign(n + 1, 0.0);
+    int nr = 0;
+    const int rc = extract(ctx, x, duals, &nr, &lp.has_alpha, &lp.obj_offset, lp.row_start.data(), lp.col.data(), lp.val.data(),
+                           lp.row_lb.data(), lp.row_ub.data(), lp.obj.data(), cap_rows, cap_nnz);
+    if (rc) return rc;
+    if (nr < 0 || nr > cap_rows) return -2;
+    lp.n_cols = n + (lp.has_alpha ? 1 : 0);
+    lp.row_start.resize(nr + 1); lp.row_lb.resize(nr); lp.row_ub.resize(nr); lp.obj.resize(lp.n_cols);
+    return 0;
+  };
+  MasterMipFn mf = [master, ctx](int nc, int nr, const int *rs, const int *cl, const double *vl, const double *rlb,
+                                 const double *rub, const double *clb, const double *cub, const double *ob, double off,
+                                 const int *isint, double cutoff, double maxs, double *x, double *bound) {
+    return master(ctx, nc, nr, rs, cl, vl, rlb, rub, clb, cub, ob, off, isint, cutoff, maxs, x, bound);
+  };
+  OaResult R = oa_run(root, sf, cf, ef, mf, opt);
+  res->status = R.status; res->passes = R.passes; res->nlp_solves = R.nlp_solves; res->cuts = R.cuts; res->oa_points = R.oa_points;
+  res->best_obj = R.best_obj; res->lower_bound = R.lower_bound; res->seconds = R.seconds; res->master_seconds = R.master_seconds;
+  if (best_x && !R.best_x.empty()) std::memcpy(best_x, R.best_x.data(), sizeof(double) * n);
+  return R.status < 0 ? R.status : 0;
+}
 
 int bnlp_host_selftest(void) {
   using namespace Bonmin;
@@ -439,6 +502,71 @@ int bnlp_linearizer_engine(bnlp_engine *E, const bnlp_problem *P, int B, const d
   if (lp_nnz) *lp_nnz = si.start_.empty() ? 0 : si.start_.back();
   if (lp_integers) { *lp_integers = 0; for (int v : si.integer_) *lp_integers += v; }
   return 0;
+}
+
+// Product path of B-OA: the engine is the arithmetic provider of every step, only the master MILP is the caller's.
+namespace {
+struct OaEngineCtx { bnlp_engine *E; int n, m; std::vector<double> xl, xu; };
+}
+int bnlp_oa_run_engine(bnlp_engine *E, const bnlp_problem *P, bnlp_master_mip_cb master, void *ctx, const bnlp_oa_run_options *o,
+                       bnlp_oa_run_result *res, double *best_x) {
+  int n = 0, m = 0;
+  if (!E || !P || !master || !res || bnlp_problem_sizes(P, &n, &m, nullptr, nullptr)) return -1;
+  std::vector<int> vt(n);
+  std::vector<double> x0(n);
+  OaEngineCtx C{E, n, m, std::vector<double>(n), std::vector<double>(n)};
+  bnlp_problem_info(P, nullptr, nullptr, nullptr, nullptr, vt.data(), nullptr, C.xl.data(), C.xu.data(), nullptr, nullptr, x0.data());
+  struct Both { OaEngineCtx *c; bnlp_master_mip_cb master; void *mctx; } both{&C, master, ctx};
+  auto solve = [](void *p, int B, const double *XL, const double *XU, const double *X0, double *OBJ, int *STATUS, int *ITERS,
+                  double *X, double *G, double *DUALS) {
+    return bnlp_solve_batch(((Both *)p)->c->E, B, XL, XU, X0, 0, OBJ, STATUS, ITERS, X, G, DUALS);
+  };
+  auto cuts = [](void *p, int B, const double *X, const double *duals, int *n_cuts, int *row_start, int *col, double *val,
+                 double *lb, double *ub, int *src_row, int cap_cuts, int cap_nnz) {
+    OaEngineCtx &c = *((Both *)p)->c;
+    int rpp = 0;
+    size_t cap = 0;
+    if (bnlp_oa_capacity(c.E, B, &rpp, &cap)) return -1;
+    const size_t slots = (size_t)B * rpp;
+    std::vector<int> rs(slots + 1), ci(cap), src(slots);
+    std::vector<double> cv(cap), LB(slots), UB(slots);
+    bnlp_oa_tols tl{1e-8, 1e-17, 1e-8, 1e19, 0};   // tiny_element, very_tiny_element, oa_rhs_relax, infinity
+    if (int rc = bnlp_oa_batch(c.E, B, X, duals, c.xl.data(), c.xu.data(), nullptr, 0.0, 1, &tl, rs.data(), ci.data(), cv.data(),
+                               LB.data(), UB.data(), src.data()))
+      return rc;
+    int nc = 0, nnz = 0;
+    row_start[0] = 0;
+    for (size_t k = 0; k < slots; ++k) {
+      if (src[k] < 0) continue;                      // row not generated
+      if (nc >= cap_cuts || nnz + (rs[k + 1] - rs[k]) > cap_nnz) return -2;
+      for (int e = rs[k]; e < rs[k + 1]; ++e) { col[nnz] = ci[e]; val[nnz] = cv[e]; ++nnz; }
+      lb[nc] = LB[k]; ub[nc] = UB[k]; src_row[nc] = src[k];
+      row_start[++nc] = nnz;
+    }
+    *n_cuts = nc;
+    return 0;
+  };
+  auto extract = [](void *p, const double *x, const double *duals, int *n_rows, int *has_alpha, double *obj_offset, int *row_start,
+                    int *col, double *val, double *row_lb, double *row_ub, double *obj, int cap_rows, int cap_nnz) {
+    OaEngineCtx &c = *((Both *)p)->c;
+    if (cap_rows < c.m + 1 || (size_t)cap_nnz < ((size_t)c.m + 1) * ((size_t)c.n + 1)) return -2;
+    bnlp_oa_tols tl{1e-8, 1e-17, 1e-8, 1e19, 0};
+    bnlp_lp_dims d{};
+    std::vector<int> src(c.m + 1), isint(c.n + 1);
+    std::vector<double> clb(c.n + 1), cub(c.n + 1);
+    if (int rc = bnlp_extract_linear_relaxation(c.E, x, duals, nullptr, nullptr, 1, &tl, &d, row_start, col, val, row_lb, row_ub,
+                                                src.data(), clb.data(), cub.data(), obj, isint.data()))
+      return rc;
+    *n_rows = d.n_rows; *has_alpha = d.has_alpha; *obj_offset = d.obj_offset;
+    return 0;
+  };
+  auto mast = [](void *p, int nc, int nr, const int *rs, const int *cl, const double *vl, const double *rlb, const double *rub,
+                 const double *clb, const double *cub, const double *ob, double off, const int *isint, double cutoff, double maxs,
+                 double *x, double *bound) {
+    Both *b = (Both *)p;
+    return b->master(b->mctx, nc, nr, rs, cl, vl, rlb, rub, clb, cub, ob, off, isint, cutoff, maxs, x, bound);
+  };
+  return bnlp_oa_run_cb(n, m, vt.data(), C.xl.data(), C.xu.data(), x0.data(), solve, cuts, extract, mast, &both, o, res, best_x);
 }
 
 // Product path: the same driver with the CUDA engine as arithmetic provider (no Python in between).

@@ -403,3 +403,166 @@ def run_qg(provider, integer_tolerance=1e-6, cutoff_increment=1e-5, node_limit=1
         out["status"] = 0 if out["best_obj"] < 1e99 else 1
     out["seconds"] = time.perf_counter() - t0
     return out
+
+
+# ------------------------------------------------------------------------------------------ the C++ B-OA loop
+# bonmin_b200/host/B200Oa.cpp (bnlp_oa_run_engine / bnlp_oa_run_cb, include/bnlp.h): the same decomposition loop as run_oa
+# in C++, engine calls made directly from the driver; only the master MILP (the reference's SubMipSolver — Cbc there,
+# HiGHS here) is a callback.  run_oa above stays as the readable statement of the loop and as its cross-check.
+import ctypes as _ct
+
+_c_int, _c_dbl, _c_void = _ct.c_int, _ct.c_double, _ct.c_void_p
+_P_int, _P_dbl = _ct.POINTER(_c_int), _ct.POINTER(_c_dbl)
+MASTER_CB = _ct.CFUNCTYPE(_c_int, _c_void, _c_int, _c_int, _P_int, _P_int, _P_dbl, _P_dbl, _P_dbl, _P_dbl, _P_dbl, _P_dbl, _c_dbl,
+                          _P_int, _c_dbl, _c_dbl, _P_dbl, _P_dbl)
+CUTS_CB = _ct.CFUNCTYPE(_c_int, _c_void, _c_int, _P_dbl, _P_dbl, _P_int, _P_int, _P_int, _P_dbl, _P_dbl, _P_dbl, _P_int, _c_int, _c_int)
+EXTRACT_CB = _ct.CFUNCTYPE(_c_int, _c_void, _P_dbl, _P_dbl, _P_int, _P_int, _P_dbl, _P_int, _P_int, _P_dbl, _P_dbl, _P_dbl, _P_dbl,
+                           _c_int, _c_int)
+
+
+class OaRunOptions(_ct.Structure):
+    _fields_ = [("cutoff_increment", _c_dbl), ("gap_tol", _c_dbl), ("time_limit", _c_dbl), ("max_passes", _c_int),
+                ("no_master_point", _c_int)]
+
+
+class OaRunResult(_ct.Structure):
+    _fields_ = [("status", _c_int), ("passes", _c_int), ("nlp_solves", _c_int), ("cuts", _c_int), ("oa_points", _c_int),
+                ("best_obj", _c_dbl), ("lower_bound", _c_dbl), ("seconds", _c_dbl), ("master_seconds", _c_dbl)]
+
+
+def _as(p, shape):
+    return np.ctypeslib.as_array(p, shape)
+
+
+def highs_master(failure=None):
+    """The master MILP as a bnlp_master_mip_cb: HiGHS through _solve_master (the same call run_oa makes)."""
+    def cb(ctx, ncols, nrows, RS, COL, VAL, RLB, RUB, CLB, CUB, OBJ, off, ISINT, cutoff, max_s, X, BOUND):
+        try:
+            rs = _as(RS, (nrows + 1,))
+            nnz = int(rs[nrows])
+            col, val = _as(COL, (max(nnz, 1),)), _as(VAL, (max(nnz, 1),))
+            lb, ub = _as(RLB, (max(nrows, 1),)), _as(RUB, (max(nrows, 1),))
+            rows = [(-1, col[rs[k]:rs[k + 1]].tolist(), val[rs[k]:rs[k + 1]].tolist(), float(lb[k]), float(ub[k]))
+                    for k in range(nrows)]
+            st, x, bound = _solve_master(ncols, rows, _as(OBJ, (ncols,)).copy(), off, _as(CLB, (ncols,)).copy(),
+                                         _as(CUB, (ncols,)).copy(), _as(ISINT, (ncols,)).copy(), cutoff)
+            if st != 0:
+                return 1
+            _as(X, (ncols,))[:] = x
+            BOUND[0] = bound
+            return 0
+        except Exception as e:      # a master failure reaches the driver as an error code and the caller as an exception
+            if failure is not None:
+                failure.append(e)
+            return -1
+    return MASTER_CB(cb)
+
+
+def _run_opts(cutoff_increment=1e-5, gap_tol=1e-9, max_passes=200, time_limit=1e10, add_master_point=True):
+    return OaRunOptions(cutoff_increment, gap_tol, time_limit, max_passes, 0 if add_master_point else 1)
+
+
+def _run_result(res, x, n, failure):
+    if failure:
+        raise failure[0]
+    out = {k: getattr(res, k) for k, _ in res._fields_}
+    out["best_x"] = x.copy() if res.best_obj < 1e99 else None
+    return out
+
+
+def run_oa_engine(eng, **kw):
+    """B-OA with the C++ loop calling the CUDA engine directly (bnlp_oa_run_engine).  Same result keys as run_oa, plus
+    master_seconds (time inside the master callback)."""
+    from . import engine as _e
+    L = _e.lib()
+    L.bnlp_oa_run_engine.argtypes = [_c_void, _c_void, MASTER_CB, _c_void, _ct.POINTER(OaRunOptions), _ct.POINTER(OaRunResult), _c_void]
+    failure = []
+    master = highs_master(failure)
+    res, x, o = OaRunResult(), np.zeros(eng.n), _run_opts(**kw)
+    rc = L.bnlp_oa_run_engine(eng.h, eng.problem.h, master, None, _ct.byref(o), _ct.byref(res), x.ctypes.data_as(_c_void))
+    if rc and not failure:
+        raise _e.BnlpError(f"bnlp_oa_run_engine failed ({rc}): " + L.bnlp_last_error().decode())
+    return _run_result(res, x, eng.n, failure)
+
+
+def run_oa_callback(provider, **kw):
+    """The C++ loop (bnlp_oa_run_cb, libbnlp_host.so: no CUDA needed) over any arithmetic provider with solve / oa / extract
+    (tests: the CPU oracle)."""
+    from . import bb as _bb
+    P = provider
+    n, m = P.n, P.m
+    failure = []
+
+    def solve(ctx, B, XL, XU, X0, OBJ, ST, IT, X, G, D):
+        try:
+            r = P.solve(_as(XL, (B, n)).copy(), _as(XU, (B, n)).copy(), _as(X0, (n,)).copy())
+            _as(OBJ, (B,))[:] = r["obj"]
+            _as(ST, (B,))[:] = r["status"]
+            _as(IT, (B,))[:] = r["iters"]
+            if X:
+                _as(X, (B, n))[:] = r["x"]
+            if D:
+                _as(D, (B, 2 * n + m))[:] = r["duals"]
+            return 0
+        except Exception as e:
+            failure.append(e)
+            return -1
+
+    def cuts(ctx, B, X, DU, NC, RS, COL, VAL, LB, UB, SRC, cap_cuts, cap_nnz):
+        try:
+            P.duals = _as(DU, (2 * n + m,)).copy()
+            cs = P.oa(_as(X, (B, n)).copy())
+            nnz = sum(len(c[1]) for c in cs)
+            if len(cs) > cap_cuts or nnz > cap_nnz:
+                return -2
+            rs = _as(RS, (cap_cuts + 1,))
+            rs[0] = 0
+            e = 0
+            for k, (src, cols, vals, lb, ub) in enumerate(cs):
+                _as(COL, (cap_nnz,))[e:e + len(cols)] = cols
+                _as(VAL, (cap_nnz,))[e:e + len(cols)] = vals
+                e += len(cols)
+                rs[k + 1] = e
+                LB[k], UB[k], SRC[k] = lb, ub, src
+            NC[0] = len(cs)
+            return 0
+        except Exception as ex:
+            failure.append(ex)
+            return -1
+
+    def extract(ctx, X, DU, NR, HA, OFF, RS, COL, VAL, RLB, RUB, OBJ, cap_rows, cap_nnz):
+        try:
+            lp = P.extract(_as(X, (n,)).copy(), _as(DU, (2 * n + m,)).copy())
+            rows = lp["rows"]
+            nnz = sum(len(r[1]) for r in rows)
+            if len(rows) > cap_rows or nnz > cap_nnz:
+                return -2
+            RS[0] = 0
+            e = 0
+            for k, (_, cols, vals, lb, ub) in enumerate(rows):
+                for c, v in zip(cols, vals):
+                    COL[e], VAL[e] = c, v
+                    e += 1
+                RS[k + 1] = e
+                RLB[k], RUB[k] = lb, ub
+            ob = np.zeros(n + 1)
+            ob[:len(lp["obj"])] = lp["obj"]
+            _as(OBJ, (n + 1,))[:] = ob
+            NR[0], HA[0], OFF[0] = len(rows), int(bool(lp["has_alpha"])), float(lp["obj_offset"])
+            return 0
+        except Exception as ex:
+            failure.append(ex)
+            return -1
+
+    L = _bb.host_lib()
+    L.bnlp_oa_run_cb.argtypes = [_c_int, _c_int, _c_void, _c_void, _c_void, _c_void, _bb.CB, CUTS_CB, EXTRACT_CB, MASTER_CB, _c_void,
+                                 _ct.POINTER(OaRunOptions), _ct.POINTER(OaRunResult), _c_void]
+    keep = (_bb.CB(solve), CUTS_CB(cuts), EXTRACT_CB(extract), highs_master(failure))
+    vt = np.ascontiguousarray(P.vtype, np.int32)
+    xl, xu, x0 = (np.ascontiguousarray(a, float) for a in (P.xl, P.xu, P.x0))
+    res, x, o = OaRunResult(), np.zeros(n), _run_opts(**kw)
+    rc = L.bnlp_oa_run_cb(n, m, vt.ctypes.data_as(_c_void), xl.ctypes.data_as(_c_void), xu.ctypes.data_as(_c_void),
+                          x0.ctypes.data_as(_c_void), *keep, None, _ct.byref(o), _ct.byref(res), x.ctypes.data_as(_c_void))
+    if rc and not failure:
+        raise RuntimeError(f"bnlp_oa_run_cb failed ({rc})")
+    return _run_result(res, x, n, failure)

@@ -418,6 +418,39 @@ int bnlp_resolve_engine(bnlp_engine *, int mode, const double *xl, const double 
 int bnlp_linearizer_engine(bnlp_engine *, const bnlp_problem *, int B, const double *X, int getObj, int global, int *n_cuts,
                            int *row_start, int *col, double *val, double *lb, double *ub, int *is_global, int cap_cuts,
                            int cap_nnz, int *lp_cols, int *lp_rows, int *lp_nnz, int *lp_integers);
+/* --- B-OA in the host layer (bonmin_b200/host/B200Oa.cpp): the decomposition loop of OACutGenerator2::performOa
+ * (src/Algorithms/OaGenerators/BonOACutGenerator2.cpp:121-268; fixIntegers / installCuts, src/Algorithms/BonSolverHelp.cpp:49-174;
+ * post_nlp_solve, src/Algorithms/OaGenerators/BonOaDecBase.cpp:237-400) in C++ around the batched engine.  The master MILP
+ * is the reference's SubMipSolver (src/Algorithms/OaGenerators/BonSubMipSolver.hpp: optimize(cutoff, loglevel, maxTime),
+ * getLastSolution, lowBound) — Cbc there, a callback here: it receives the whole master (initial relaxation + every cut
+ * installed so far, CSR by rows, +-DBL_MAX = free side) and the cutoff on the objective, returns 0 with a point (n_cols)
+ * and its bound, 1 when the master is infeasible / cut off, < 0 on error.
+ * bnlp_oa_run_engine: relaxation, every NLP(y), the initial LP and the linearisations (at the NLP(y) point and, when
+ * add_master_point, at the master point: one bnlp_oa_batch call per pass) run on the CUDA engine.
+ * bnlp_oa_run_cb: the same loop over caller-supplied arithmetic (tests: the CPU oracle).  cuts callback = B x
+ * getOuterApproximation(getObj = 1) with `duals` = the multipliers of the last NLP solve, generated rows only, CSR;
+ * extract callback = extractLinearRelaxation + addObjectiveFunction (obj: n + 1 entries, the last one alpha's);
+ * both return -2 when a capacity is too small.  0 in an option field means its default (1e-5, 1e-9, 1e10, 200). */
+typedef int (*bnlp_master_mip_cb)(void *ctx, int n_cols, int n_rows, const int *row_start, const int *col, const double *val,
+                                  const double *row_lb, const double *row_ub, const double *col_lb, const double *col_ub,
+                                  const double *obj, double obj_offset, const int *is_integer, double cutoff,
+                                  double max_seconds, double *x, double *bound);
+typedef int (*bnlp_oa_cuts_cb)(void *ctx, int B, const double *X, const double *duals, int *n_cuts, int *row_start, int *col,
+                               double *val, double *lb, double *ub, int *src_row, int cap_cuts, int cap_nnz);
+typedef int (*bnlp_oa_extract_cb)(void *ctx, const double *x, const double *duals, int *n_rows, int *has_alpha,
+                                  double *obj_offset, int *row_start, int *col, double *val, double *row_lb, double *row_ub,
+                                  double *obj, int cap_rows, int cap_nnz);
+typedef struct bnlp_oa_run_options { double cutoff_increment, gap_tol, time_limit; int max_passes, no_master_point; } bnlp_oa_run_options;
+typedef struct bnlp_oa_run_result {
+  int status;                 /* 0 optimal, 1 infeasible, 2 limit reached */
+  int passes, nlp_solves, cuts, oa_points;
+  double best_obj, lower_bound, seconds, master_seconds;
+} bnlp_oa_run_result;
+int bnlp_oa_run_cb(int n, int m, const int *var_type, const double *xl, const double *xu, const double *x0,
+                   bnlp_batch_solve_cb solve, bnlp_oa_cuts_cb cuts, bnlp_oa_extract_cb extract, bnlp_master_mip_cb master,
+                   void *ctx, const bnlp_oa_run_options *o, bnlp_oa_run_result *res, double *best_x);
+int bnlp_oa_run_engine(bnlp_engine *, const bnlp_problem *, bnlp_master_mip_cb master, void *ctx, const bnlp_oa_run_options *o,
+                       bnlp_oa_run_result *res, double *best_x);
 /* Self-test of the host adapter's TNLPSolver contract (options, warm starts, error objects, output levels) on a stub
  * provider; 0 = all expectations hold, otherwise the source line of the first failure (bonmin_b200/host/host_cabi.cpp). */
 int bnlp_host_selftest(void);

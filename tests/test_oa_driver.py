@@ -168,3 +168,54 @@ def test_ranged_nonlinear_row_is_cut_on_its_binding_side_only(oracle_ipm):
     assert len(one_sided) == 3 and all(lb <= -1e100 and ub < 1e100 for _, _, _, lb, ub in one_sided)
     two_sided = [c for c in SE.outer_approximation(P.ev, root["x"][0], None, m.xl, m.xu, get_obj=1) if c[0] < 3]
     assert all(lb > -1e100 and ub < 1e100 for _, _, _, lb, ub in two_sided)      # what a provider without duals would add
+
+
+_KEYS = ("status", "best_obj", "lower_bound", "passes", "nlp_solves", "cuts", "oa_points")
+
+
+@pytest.mark.parametrize("mk", [lambda: I.mytoy(), lambda: I.syn_miqcp(12, 6, 3, 3, 4),
+                                lambda: I.syn_cvx_minlp(16, 6, 3, 5, 2)])
+def test_cpp_oa_loop_reproduces_the_python_loop(oracle_ipm, mk):
+    # bonmin_b200/host/B200Oa.cpp (bnlp_oa_run_cb) against oa.run_oa on the same provider and the same master: the two
+    # statements of OACutGenerator2::performOa must take the same passes, install the same cuts and end at the same point
+    m = mk()
+    p = oa.run_oa(OracleProvider(m, oracle_ipm))
+    c = oa.run_oa_callback(OracleProvider(m, oracle_ipm))
+    assert {k: c[k] for k in _KEYS} == {k: p[k] for k in _KEYS}
+    assert np.array_equal(c["best_x"], p["best_x"])
+    # without the master point (the reference's plain performOa): still the same optimum
+    c1 = oa.run_oa_callback(OracleProvider(m, oracle_ipm), add_master_point=False)
+    p1 = oa.run_oa(OracleProvider(m, oracle_ipm), add_master_point=False)
+    assert {k: c1[k] for k in _KEYS} == {k: p1[k] for k in _KEYS}
+    assert c1["best_obj"] == pytest.approx(p["best_obj"], rel=2e-5, abs=2e-5)
+
+
+def test_cpp_oa_loop_limits_and_provider_failure(oracle_ipm):
+    m = I.syn_miqcp(12, 6, 3, 3, 4)
+    r = oa.run_oa_callback(OracleProvider(m, oracle_ipm), max_passes=3)
+    assert r["status"] == 2 and r["passes"] == 3 and r["lower_bound"] <= r["best_obj"]
+
+    class Broken(OracleProvider):
+        def oa(self, X, X2=None, theta=0.0):
+            raise RuntimeError("provider down")
+    with pytest.raises(RuntimeError, match="provider down"):
+        oa.run_oa_callback(Broken(m, oracle_ipm))
+
+
+@pytest.mark.gpu
+def test_cpp_oa_loop_on_the_engine(bnlp_lib, oracle_ipm):
+    # product path: bnlp_oa_run_engine (C++ loop -> bnlp_solve_batch / bnlp_extract_linear_relaxation / bnlp_oa_batch,
+    # HiGHS master behind the callback) against the Python loop on the same engine and against the CPU oracle
+    from bonmin_b200.engine import Engine, Problem
+    for m in (I.mytoy(), I.syn_miqcp(12, 6, 3, 3, 4), I.syn_cvx_minlp(16, 6, 3, 5, 2), I.syn_cvx_minlp(60, 24, 10, 10, 5)):
+        eng = Engine(Problem.from_model(m))
+        l0 = eng.launches()
+        g = oa.run_oa_engine(eng)
+        assert eng.launches() > l0
+        p = oa.run_oa(oa.EngineProvider(eng))
+        assert {k: g[k] for k in _KEYS} == {k: p[k] for k in _KEYS}
+        assert np.array_equal(g["best_x"], p["best_x"])
+        c = oa.run_oa(OracleProvider(m, oracle_ipm))
+        assert g["status"] == c["status"] == 0
+        assert g["best_obj"] == pytest.approx(c["best_obj"], rel=1e-6, abs=1e-8)
+        eng.close()
