@@ -112,4 +112,67 @@ OaResult oa_run(const TMINLP2TNLP &root, const BatchSolveFn &solve, const OaCuts
   return finish();
 }
 
+OaFeasResult oa_feas_check(const TMINLP2TNLP &root, OaLp &lp, const double *x_lp_in, double cutoff, const BatchSolveFn &solve,
+                           const OaCutsFn &oa, const MasterMipFn &lp_solve, const OaFeasOptions &opt) {
+  OaFeasResult R;
+  const int n = root.n, m = root.m, ncols = lp.n_cols;
+  std::vector<int> ints;
+  for (int j = 0; j < n; ++j)
+    if (root.var_types[j] != 0) ints.push_back(j);
+  R.cutoff = cutoff;
+  R.x_lp.assign(x_lp_in, x_lp_in + ncols);
+  std::vector<double> xs(n), duals(2 * (size_t)n + m, 0.0), XL(root.x_l_), XU(root.x_u_), x_new(ncols);
+  const std::vector<int> no_integer(ncols, 0);
+  double nlp_obj = 0;
+  int nlp_status = 0, nlp_iters = 0, passes = 0;
+  bool is_integer = true, feasible = true;
+  while (is_integer && feasible && passes < opt.max_passes) {
+    ++passes;
+    for (int j : ints) XL[j] = XU[j] = std::nearbyint(R.x_lp[j]);            // fixIntegers
+    if (int rc = solve(1, XL.data(), XU.data(), R.x_lp.data(), &nlp_obj, &nlp_status, &nlp_iters, xs.data(), nullptr, duals.data())) {
+      R.status = rc < 0 ? rc : -1;
+      return R;
+    }
+    ++R.nlp_solves;
+    if ((nlp_status == 1 || nlp_status == 2) && nlp_obj < R.cutoff) {         // post_nlp_solve
+      if (!R.has_incumbent || nlp_obj < R.incumbent_obj) { R.has_incumbent = true; R.incumbent_obj = nlp_obj; R.incumbent_x = xs; }
+      R.cutoff = nlp_obj > 0 ? nlp_obj * (1 - opt.cutoff_increment) : nlp_obj * (1 + opt.cutoff_increment);
+    }
+    CutRows cuts;
+    if (int rc = oa(1, xs.data(), duals.data(), cuts)) { R.status = rc < 0 ? rc : -1; return R; }
+    for (int k = 0; k < cuts.size(); ++k) {
+      if (cuts.src_row[k] == m && ncols == n) continue;
+      for (int e = cuts.row_start[k]; e < cuts.row_start[k + 1]; ++e) {
+        lp.col.push_back(cuts.col[e]); lp.val.push_back(cuts.val[e]);
+        R.new_rows.col.push_back(cuts.col[e]); R.new_rows.val.push_back(cuts.val[e]);
+      }
+      lp.row_start.push_back((int)lp.col.size()); lp.row_lb.push_back(cuts.lb[k]); lp.row_ub.push_back(cuts.ub[k]);
+      R.new_rows.row_start.push_back((int)R.new_rows.col.size());
+      R.new_rows.lb.push_back(cuts.lb[k]); R.new_rows.ub.push_back(cuts.ub[k]); R.new_rows.src_row.push_back(cuts.src_row[k]);
+      ++R.cuts;
+    }
+    double val = 1e200;
+    const int st = lp_solve(ncols, (int)lp.row_lb.size(), lp.row_start.data(), lp.col.data(), lp.val.data(), lp.row_lb.data(),
+                            lp.row_ub.data(), lp.col_lb.data(), lp.col_ub.data(), lp.obj.data(), lp.obj_offset, no_integer.data(),
+                            1e100, 1e10, x_new.data(), &val);                 // lp->resolve()
+    if (st < 0) { R.status = st; return R; }
+    feasible = st == 0 && val < R.cutoff;
+    is_integer = false;
+    if (feasible) {
+      double diff = 0, frac = 0;
+      for (int j : ints) {
+        diff = std::max(diff, std::fabs(xs[j] - x_new[j]));
+        frac = std::max(frac, std::fabs(x_new[j] - std::nearbyint(x_new[j])));
+      }
+      if (diff > 0.1) is_integer = frac <= opt.integer_tolerance;            // isDifferentOnIntegers(.., 0.1, ..)
+      else R.fathomed = true;                                                // same integers as the NLP point (:115-119)
+      R.x_lp = x_new;
+    } else {
+      R.fathomed = true;
+      R.has_x_lp = false;
+    }
+  }
+  return R;
+}
+
 }  // namespace Bonmin

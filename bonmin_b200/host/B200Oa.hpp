@@ -53,4 +53,25 @@ struct OaResult {
 OaResult oa_run(const TMINLP2TNLP &root, const BatchSolveFn &solve, const OaCutsFn &oa, const OaExtractFn &extract,
                 const MasterMipFn &master, const OaOptions &opt);
 
+// OaFeasibilityChecker::performOa (src/Algorithms/OaGenerators/BonOaFeasChecker.cpp:38-135), the generator B-QG / B-Hyb call
+// when a node LP has an integer solution: fix the integers at the LP values, solve NLP(y), update incumbent and cutoff,
+// linearise at the NLP point, install the cuts in the node LP and re-solve it (MasterMipFn with no integer column); go on
+// while the LP stays feasible below the cutoff, integer, and different on the integers from the NLP point.
+// (add_only_violated_oa, default "no" in the reference, is not offered here: OaCutsFn carries no second point.)
+struct OaLp {                       // the node LP: CSR rows, columns, objective
+  int n_cols = 0; double obj_offset = 0;
+  std::vector<int> row_start{0}, col; std::vector<double> val, row_lb, row_ub, col_lb, col_ub, obj;
+};
+struct OaFeasOptions { double integer_tolerance = 1e-6, cutoff_increment = 1e-5; int max_passes = 50; };
+struct OaFeasResult {
+  int status = 0;                   // < 0: provider error
+  double cutoff = 1e100, incumbent_obj = 1e100;
+  bool has_incumbent = false, fathomed = false, has_x_lp = true;
+  int cuts = 0, nlp_solves = 0;
+  std::vector<double> incumbent_x, x_lp;
+  CutRows new_rows;                 // the cuts installed (they are global: the caller keeps them)
+};
+OaFeasResult oa_feas_check(const TMINLP2TNLP &root, OaLp &lp /* rows are appended */, const double *x_lp, double cutoff,
+                           const BatchSolveFn &solve, const OaCutsFn &oa, const MasterMipFn &lp_solve, const OaFeasOptions &opt);
+
 }  // namespace Bonmin

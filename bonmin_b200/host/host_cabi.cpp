@@ -1,6 +1,7 @@
 // C entry points of the host layer (used by bench.py, tests and the `bnlp_bb` command): the B-BB driver with a
 // batch-solve callback.  In the product the callback is bnlp_solve_batch on a CUDA engine (bnlp_bb_run_engine in
 // bnlp_api.cu); tests may pass the CPU oracle to check that both give the same MINLP optimum.
+#include <algorithm>
 #include <cstring>
 #include <vector>
 #include <sstream>
@@ -179,6 +180,74 @@ int bnlp_oa_run_cb(int n, int m, const int *var_type, const double *xl, const do
   res->best_obj = R.best_obj; res->lower_bound = R.lower_bound; res->seconds = R.seconds; res->master_seconds = R.master_seconds;
   if (best_x && !R.best_x.empty()) std::memcpy(best_x, R.best_x.data(), sizeof(double) * n);
   return R.status < 0 ? R.status : 0;
+}
+
+// OaFeasibilityChecker::performOa (B200Oa.cpp: oa_feas_check) over caller-supplied arithmetic and LP solver
+int bnlp_oa_feas_check_cb(int n, int m, const int *var_type, const double *xl, const double *xu, int n_cols, int n_rows,
+                          const int *row_start, const int *col, const double *val, const double *row_lb, const double *row_ub,
+                          const double *col_lb, const double *col_ub, const double *obj, double obj_offset, const double *x_lp,
+                          double cutoff, const bnlp_oa_feas_options *o, bnlp_batch_solve_cb solve, bnlp_oa_cuts_cb cuts,
+                          bnlp_master_mip_cb lp_solve, void *ctx, bnlp_oa_feas_result *res, double *incumbent_x, double *x_lp_out,
+                          int *new_row_start, int *new_col, double *new_val, double *new_lb, double *new_ub, int *new_src,
+                          int cap_cuts, int cap_nnz) {
+  using namespace Bonmin;
+  if (!solve || !cuts || !lp_solve || !res || n <= 0 || m < 0 || n_cols < n || n_rows < 0) return -1;
+  Ipopt::SmartPtr<TMINLP2TNLP> holder = new TMINLP2TNLP();
+  TMINLP2TNLP &root = *holder;
+  root.n = n; root.m = m;
+  root.var_types.assign(var_type, var_type + n);
+  root.x_l_.assign(xl, xl + n); root.x_u_.assign(xu, xu + n);
+  OaLp lp;
+  lp.n_cols = n_cols; lp.obj_offset = obj_offset;
+  lp.row_start.assign(row_start, row_start + n_rows + 1);
+  lp.col.assign(col, col + row_start[n_rows]); lp.val.assign(val, val + row_start[n_rows]);
+  lp.row_lb.assign(row_lb, row_lb + n_rows); lp.row_ub.assign(row_ub, row_ub + n_rows);
+  lp.col_lb.assign(col_lb, col_lb + n_cols); lp.col_ub.assign(col_ub, col_ub + n_cols); lp.obj.assign(obj, obj + n_cols);
+  OaFeasOptions opt;
+  if (o) {
+    if (o->integer_tolerance > 0) opt.integer_tolerance = o->integer_tolerance;
+    if (o->cutoff_increment > 0) opt.cutoff_increment = o->cutoff_increment;
+    if (o->max_passes > 0) opt.max_passes = o->max_passes;
+  }
+  BatchSolveFn sf = [solve, ctx](int B, const double *XL, const double *XU, const double *X0, double *OBJ, int *STATUS,
+                                 int *ITERS, double *X, double *G, double *DUALS) {
+    return solve(ctx, B, XL, XU, X0, OBJ, STATUS, ITERS, X, G, DUALS);
+  };
+  const size_t rows_cap = (size_t)m + 1, nnz_row = (size_t)n + 1;
+  OaCutsFn cf = [cuts, ctx, rows_cap, nnz_row](int B, const double *X, const double *duals, CutRows &out) {
+    const int cc = (int)(B * rows_cap), cn = (int)(B * rows_cap * nnz_row);
+    out.row_start.assign(cc + 1, 0); out.col.resize(cn); out.val.resize(cn);
+    out.lb.resize(cc); out.ub.resize(cc); out.src_row.resize(cc);
+    int nc = 0;
+    const int rc = cuts(ctx, B, X, duals, &nc, out.row_start.data(), out.col.data(), out.val.data(), out.lb.data(), out.ub.data(),
+                        out.src_row.data(), cc, cn);
+    if (rc) return rc;
+    if (nc < 0 || nc > cc) return -2;
+    out.row_start.resize(nc + 1); out.lb.resize(nc); out.ub.resize(nc); out.src_row.resize(nc);
+    return 0;
+  };
+  MasterMipFn mf = [lp_solve, ctx](int nc, int nr, const int *rs, const int *cl, const double *vl, const double *rlb,
+                                   const double *rub, const double *clb, const double *cub, const double *ob, double off,
+                                   const int *isint, double co, double maxs, double *x, double *bound) {
+    return lp_solve(ctx, nc, nr, rs, cl, vl, rlb, rub, clb, cub, ob, off, isint, co, maxs, x, bound);
+  };
+  OaFeasResult R = oa_feas_check(root, lp, x_lp, cutoff, sf, cf, mf, opt);
+  res->status = R.status; res->cuts = R.cuts; res->nlp_solves = R.nlp_solves; res->fathomed = R.fathomed;
+  res->has_incumbent = R.has_incumbent; res->has_x_lp = R.has_x_lp; res->cutoff = R.cutoff; res->incumbent_obj = R.incumbent_obj;
+  res->new_nnz = (int)R.new_rows.col.size();
+  if (R.status < 0) return R.status;
+  if (R.cuts > cap_cuts || res->new_nnz > cap_nnz) return -2;
+  if (incumbent_x && R.has_incumbent) std::memcpy(incumbent_x, R.incumbent_x.data(), sizeof(double) * n);
+  if (x_lp_out && R.has_x_lp) std::memcpy(x_lp_out, R.x_lp.data(), sizeof(double) * n_cols);
+  if (new_row_start) std::memcpy(new_row_start, R.new_rows.row_start.data(), sizeof(int) * (R.cuts + 1));
+  if (R.cuts) {
+    std::memcpy(new_col, R.new_rows.col.data(), sizeof(int) * res->new_nnz);
+    std::memcpy(new_val, R.new_rows.val.data(), sizeof(double) * res->new_nnz);
+    std::memcpy(new_lb, R.new_rows.lb.data(), sizeof(double) * R.cuts);
+    std::memcpy(new_ub, R.new_rows.ub.data(), sizeof(double) * R.cuts);
+    if (new_src) std::memcpy(new_src, R.new_rows.src_row.data(), sizeof(int) * R.cuts);
+  }
+  return 0;
 }
 
 int bnlp_host_selftest(void) {
@@ -506,67 +575,86 @@ int bnlp_linearizer_engine(bnlp_engine *E, const bnlp_problem *P, int B, const d
 
 // Product path of B-OA: the engine is the arithmetic provider of every step, only the master MILP is the caller's.
 namespace {
-struct OaEngineCtx { bnlp_engine *E; int n, m; std::vector<double> xl, xu; };
+struct OaEngineCtx { bnlp_engine *E; int n, m; std::vector<double> xl, xu; bnlp_master_mip_cb master; void *mctx; };
+int oa_eng_solve(void *p, int B, const double *XL, const double *XU, const double *X0, double *OBJ, int *STATUS, int *ITERS,
+                 double *X, double *G, double *DUALS) {
+  return bnlp_solve_batch(((OaEngineCtx *)p)->E, B, XL, XU, X0, 0, OBJ, STATUS, ITERS, X, G, DUALS);
 }
+int oa_eng_cuts(void *p, int B, const double *X, const double *duals, int *n_cuts, int *row_start, int *col, double *val,
+                double *lb, double *ub, int *src_row, int cap_cuts, int cap_nnz) {
+  OaEngineCtx &c = *(OaEngineCtx *)p;
+  int rpp = 0;
+  size_t cap = 0;
+  if (bnlp_oa_capacity(c.E, B, &rpp, &cap)) return -1;
+  const size_t slots = (size_t)B * rpp;
+  std::vector<int> rs(slots + 1), ci(cap), src(slots);
+  std::vector<double> cv(cap), LB(slots), UB(slots);
+  bnlp_oa_tols tl{1e-8, 1e-17, 1e-8, 1e19, 0};   // tiny_element, very_tiny_element, oa_rhs_relax, infinity
+  // bnlp_oa_batch takes one multiplier vector PER POINT; the loop has one for all of them (the interface's getRowPrice())
+  const size_t nmul = 2 * (size_t)c.n + c.m;
+  std::vector<double> du((size_t)B * nmul);
+  for (int b = 0; b < B; ++b) std::copy(duals, duals + nmul, du.begin() + (size_t)b * nmul);
+  if (int rc = bnlp_oa_batch(c.E, B, X, du.data(), c.xl.data(), c.xu.data(), nullptr, 0.0, 1, &tl, rs.data(), ci.data(), cv.data(),
+                             LB.data(), UB.data(), src.data()))
+    return rc;
+  int nc = 0, nnz = 0;
+  row_start[0] = 0;
+  for (size_t k = 0; k < slots; ++k) {
+    if (src[k] < 0) continue;                      // row not generated
+    if (nc >= cap_cuts || nnz + (rs[k + 1] - rs[k]) > cap_nnz) return -2;
+    for (int e = rs[k]; e < rs[k + 1]; ++e) { col[nnz] = ci[e]; val[nnz] = cv[e]; ++nnz; }
+    lb[nc] = LB[k]; ub[nc] = UB[k]; src_row[nc] = src[k];
+    row_start[++nc] = nnz;
+  }
+  *n_cuts = nc;
+  return 0;
+}
+int oa_eng_extract(void *p, const double *x, const double *duals, int *n_rows, int *has_alpha, double *obj_offset, int *row_start,
+                   int *col, double *val, double *row_lb, double *row_ub, double *obj, int cap_rows, int cap_nnz) {
+  OaEngineCtx &c = *(OaEngineCtx *)p;
+  if (cap_rows < c.m + 1 || (size_t)cap_nnz < ((size_t)c.m + 1) * ((size_t)c.n + 1)) return -2;
+  bnlp_oa_tols tl{1e-8, 1e-17, 1e-8, 1e19, 0};
+  bnlp_lp_dims d{};
+  std::vector<int> src(c.m + 1), isint(c.n + 1);
+  std::vector<double> clb(c.n + 1), cub(c.n + 1);
+  if (int rc = bnlp_extract_linear_relaxation(c.E, x, duals, nullptr, nullptr, 1, &tl, &d, row_start, col, val, row_lb, row_ub,
+                                              src.data(), clb.data(), cub.data(), obj, isint.data()))
+    return rc;
+  *n_rows = d.n_rows; *has_alpha = d.has_alpha; *obj_offset = d.obj_offset;
+  return 0;
+}
+int oa_eng_master(void *p, int nc, int nr, const int *rs, const int *cl, const double *vl, const double *rlb, const double *rub,
+                  const double *clb, const double *cub, const double *ob, double off, const int *isint, double cutoff, double maxs,
+                  double *x, double *bound) {
+  OaEngineCtx *c = (OaEngineCtx *)p;
+  return c->master(c->mctx, nc, nr, rs, cl, vl, rlb, rub, clb, cub, ob, off, isint, cutoff, maxs, x, bound);
+}
+}  // namespace
 int bnlp_oa_run_engine(bnlp_engine *E, const bnlp_problem *P, bnlp_master_mip_cb master, void *ctx, const bnlp_oa_run_options *o,
                        bnlp_oa_run_result *res, double *best_x) {
   int n = 0, m = 0;
   if (!E || !P || !master || !res || bnlp_problem_sizes(P, &n, &m, nullptr, nullptr)) return -1;
   std::vector<int> vt(n);
   std::vector<double> x0(n);
-  OaEngineCtx C{E, n, m, std::vector<double>(n), std::vector<double>(n)};
+  OaEngineCtx C{E, n, m, std::vector<double>(n), std::vector<double>(n), master, ctx};
   bnlp_problem_info(P, nullptr, nullptr, nullptr, nullptr, vt.data(), nullptr, C.xl.data(), C.xu.data(), nullptr, nullptr, x0.data());
-  struct Both { OaEngineCtx *c; bnlp_master_mip_cb master; void *mctx; } both{&C, master, ctx};
-  auto solve = [](void *p, int B, const double *XL, const double *XU, const double *X0, double *OBJ, int *STATUS, int *ITERS,
-                  double *X, double *G, double *DUALS) {
-    return bnlp_solve_batch(((Both *)p)->c->E, B, XL, XU, X0, 0, OBJ, STATUS, ITERS, X, G, DUALS);
-  };
-  auto cuts = [](void *p, int B, const double *X, const double *duals, int *n_cuts, int *row_start, int *col, double *val,
-                 double *lb, double *ub, int *src_row, int cap_cuts, int cap_nnz) {
-    OaEngineCtx &c = *((Both *)p)->c;
-    int rpp = 0;
-    size_t cap = 0;
-    if (bnlp_oa_capacity(c.E, B, &rpp, &cap)) return -1;
-    const size_t slots = (size_t)B * rpp;
-    std::vector<int> rs(slots + 1), ci(cap), src(slots);
-    std::vector<double> cv(cap), LB(slots), UB(slots);
-    bnlp_oa_tols tl{1e-8, 1e-17, 1e-8, 1e19, 0};   // tiny_element, very_tiny_element, oa_rhs_relax, infinity
-    if (int rc = bnlp_oa_batch(c.E, B, X, duals, c.xl.data(), c.xu.data(), nullptr, 0.0, 1, &tl, rs.data(), ci.data(), cv.data(),
-                               LB.data(), UB.data(), src.data()))
-      return rc;
-    int nc = 0, nnz = 0;
-    row_start[0] = 0;
-    for (size_t k = 0; k < slots; ++k) {
-      if (src[k] < 0) continue;                      // row not generated
-      if (nc >= cap_cuts || nnz + (rs[k + 1] - rs[k]) > cap_nnz) return -2;
-      for (int e = rs[k]; e < rs[k + 1]; ++e) { col[nnz] = ci[e]; val[nnz] = cv[e]; ++nnz; }
-      lb[nc] = LB[k]; ub[nc] = UB[k]; src_row[nc] = src[k];
-      row_start[++nc] = nnz;
-    }
-    *n_cuts = nc;
-    return 0;
-  };
-  auto extract = [](void *p, const double *x, const double *duals, int *n_rows, int *has_alpha, double *obj_offset, int *row_start,
-                    int *col, double *val, double *row_lb, double *row_ub, double *obj, int cap_rows, int cap_nnz) {
-    OaEngineCtx &c = *((Both *)p)->c;
-    if (cap_rows < c.m + 1 || (size_t)cap_nnz < ((size_t)c.m + 1) * ((size_t)c.n + 1)) return -2;
-    bnlp_oa_tols tl{1e-8, 1e-17, 1e-8, 1e19, 0};
-    bnlp_lp_dims d{};
-    std::vector<int> src(c.m + 1), isint(c.n + 1);
-    std::vector<double> clb(c.n + 1), cub(c.n + 1);
-    if (int rc = bnlp_extract_linear_relaxation(c.E, x, duals, nullptr, nullptr, 1, &tl, &d, row_start, col, val, row_lb, row_ub,
-                                                src.data(), clb.data(), cub.data(), obj, isint.data()))
-      return rc;
-    *n_rows = d.n_rows; *has_alpha = d.has_alpha; *obj_offset = d.obj_offset;
-    return 0;
-  };
-  auto mast = [](void *p, int nc, int nr, const int *rs, const int *cl, const double *vl, const double *rlb, const double *rub,
-                 const double *clb, const double *cub, const double *ob, double off, const int *isint, double cutoff, double maxs,
-                 double *x, double *bound) {
-    Both *b = (Both *)p;
-    return b->master(b->mctx, nc, nr, rs, cl, vl, rlb, rub, clb, cub, ob, off, isint, cutoff, maxs, x, bound);
-  };
-  return bnlp_oa_run_cb(n, m, vt.data(), C.xl.data(), C.xu.data(), x0.data(), solve, cuts, extract, mast, &both, o, res, best_x);
+  return bnlp_oa_run_cb(n, m, vt.data(), C.xl.data(), C.xu.data(), x0.data(), oa_eng_solve, oa_eng_cuts, oa_eng_extract,
+                        oa_eng_master, &C, o, res, best_x);
+}
+int bnlp_oa_feas_check_engine(bnlp_engine *E, const bnlp_problem *P, int n_cols, int n_rows, const int *row_start, const int *col,
+                              const double *val, const double *row_lb, const double *row_ub, const double *col_lb,
+                              const double *col_ub, const double *obj, double obj_offset, const double *x_lp, double cutoff,
+                              const bnlp_oa_feas_options *o, bnlp_master_mip_cb lp_solve, void *ctx, bnlp_oa_feas_result *res,
+                              double *incumbent_x, double *x_lp_out, int *new_row_start, int *new_col, double *new_val,
+                              double *new_lb, double *new_ub, int *new_src, int cap_cuts, int cap_nnz) {
+  int n = 0, m = 0;
+  if (!E || !P || !lp_solve || !res || bnlp_problem_sizes(P, &n, &m, nullptr, nullptr)) return -1;
+  std::vector<int> vt(n);
+  OaEngineCtx C{E, n, m, std::vector<double>(n), std::vector<double>(n), lp_solve, ctx};
+  bnlp_problem_info(P, nullptr, nullptr, nullptr, nullptr, vt.data(), nullptr, C.xl.data(), C.xu.data(), nullptr, nullptr, nullptr);
+  return bnlp_oa_feas_check_cb(n, m, vt.data(), C.xl.data(), C.xu.data(), n_cols, n_rows, row_start, col, val, row_lb, row_ub, col_lb,
+                               col_ub, obj, obj_offset, x_lp, cutoff, o, oa_eng_solve, oa_eng_cuts, oa_eng_master, &C, res,
+                               incumbent_x, x_lp_out, new_row_start, new_col, new_val, new_lb, new_ub, new_src, cap_cuts, cap_nnz);
 }
 
 // Product path: the same driver with the CUDA engine as arithmetic provider (no Python in between).

@@ -317,7 +317,7 @@ def nlp_optim_wanted(level, solves_per_level=1.0, max_depth=10, rng=None):
 
 
 def run_qg(provider, integer_tolerance=1e-6, cutoff_increment=1e-5, node_limit=100000, nlp_solves_per_level=0.0,
-           nlp_max_depth=10, seed=0, time_limit=1e10, log=None):
+           nlp_max_depth=10, seed=0, time_limit=1e10, log=None, feas_check=None):
     """A single-tree LP/NLP-based branch and bound in the manner of B-QG (nlp_solves_per_level = 0) and B-Hyb (> 0):
     LP relaxation from extractLinearRelaxation at the root NLP optimum, best-bound search branching on the most
     fractional integer, OaFeasibilityChecker at integer LP points, OaNlpOptim at nodes by the depth rule.  Host control
@@ -371,7 +371,8 @@ def run_qg(provider, integer_tolerance=1e-6, cutoff_increment=1e-5, node_limit=1
                 continue
         frac = np.abs(x[ints] - np.round(x[ints]))
         if frac.max(initial=0.0) <= integer_tolerance:
-            f = feasibility_check(P, lp, lb, ub, x, cutoff, integer_tolerance, cutoff_increment)
+            # feas_check: feasibility_check (default) or the C++ loop behind the same signature (feasibility_check_native)
+            f = (feas_check or feasibility_check)(P, lp, lb, ub, x, cutoff, integer_tolerance, cutoff_increment)
             out["nlp_solves"] += f["nlp_solves"]
             out["cuts"] += f["cuts"]
             cutoff = min(cutoff, f["cutoff"])
@@ -566,3 +567,109 @@ def run_oa_callback(provider, **kw):
     if rc and not failure:
         raise RuntimeError(f"bnlp_oa_run_cb failed ({rc})")
     return _run_result(res, x, n, failure)
+
+
+class OaFeasOptions(_ct.Structure):
+    _fields_ = [("integer_tolerance", _c_dbl), ("cutoff_increment", _c_dbl), ("max_passes", _c_int)]
+
+
+class OaFeasResult(_ct.Structure):
+    _fields_ = [("status", _c_int), ("cuts", _c_int), ("nlp_solves", _c_int), ("fathomed", _c_int), ("has_incumbent", _c_int),
+                ("has_x_lp", _c_int), ("new_nnz", _c_int), ("cutoff", _c_dbl), ("incumbent_obj", _c_dbl)]
+
+
+def _lp_csr(lp, col_lb, col_ub):
+    rows = lp["rows"]
+    rs = np.zeros(len(rows) + 1, np.int32)
+    rs[1:] = np.cumsum([len(r[1]) for r in rows])
+    col = np.ascontiguousarray(np.concatenate([np.asarray(r[1], np.int32) for r in rows]) if rows else np.zeros(1), np.int32)
+    val = np.ascontiguousarray(np.concatenate([np.asarray(r[2], float) for r in rows]) if rows else np.zeros(1), float)
+    lb = np.ascontiguousarray([r[3] for r in rows] or [0.0], float)
+    ub = np.ascontiguousarray([r[4] for r in rows] or [0.0], float)
+    nc = lp["ncols"]
+    obj = np.zeros(nc)
+    obj[:min(nc, len(lp["obj"]))] = np.asarray(lp["obj"], float)[:nc]
+    return rs, col, val, lb, ub, np.ascontiguousarray(col_lb, float), np.ascontiguousarray(col_ub, float), obj
+
+
+def feasibility_check_native(target, lp, col_lb, col_ub, x_lp, cutoff, integer_tolerance=1e-6, cutoff_increment=1e-5, max_passes=50):
+    """feasibility_check through the C++ loop (B200Oa.cpp: oa_feas_check).  target: an Engine (bnlp_oa_feas_check_engine, the
+    product path) or an arithmetic provider (bnlp_oa_feas_check_cb; tests pass the CPU oracle).  Same arguments and result
+    as feasibility_check (add_only_violated is not offered); lp["rows"] is extended in place."""
+    from . import bb as _bb, engine as _e
+    is_engine = isinstance(target, _e.Engine)
+    n, m = target.n, target.m
+    nc = lp["ncols"]
+    rs, col, val, lb, ub, clb, cub, obj = _lp_csr(lp, col_lb, col_ub)
+    xlp = np.ascontiguousarray(np.asarray(x_lp, float)[:nc])
+    cap_cuts, cap_nnz = max_passes * (m + 1), max_passes * (m + 1) * (n + 1)
+    nrs, ncol, nval = np.zeros(cap_cuts + 1, np.int32), np.zeros(cap_nnz, np.int32), np.zeros(cap_nnz)
+    nlb, nub, nsrc = np.zeros(cap_cuts), np.zeros(cap_cuts), np.zeros(cap_cuts, np.int32)
+    inc_x, x_out = np.zeros(n), np.zeros(nc)
+    res, o = OaFeasResult(), OaFeasOptions(integer_tolerance, cutoff_increment, max_passes)
+    failure = []
+    master = highs_master(failure)
+    vp = lambda a: a.ctypes.data_as(_c_void)
+    lp_args = [nc, len(lp["rows"]), vp(rs), vp(col), vp(val), vp(lb), vp(ub), vp(clb), vp(cub), vp(obj), float(lp["obj_offset"]),
+               vp(xlp), float(cutoff), _ct.byref(o)]
+    out_args = [_ct.byref(res), vp(inc_x), vp(x_out), vp(nrs), vp(ncol), vp(nval), vp(nlb), vp(nub), vp(nsrc), cap_cuts, cap_nnz]
+    lp_types = [_c_int, _c_int] + [_c_void] * 8 + [_c_dbl, _c_void, _c_dbl, _ct.POINTER(OaFeasOptions)]
+    out_types = [_ct.POINTER(OaFeasResult)] + [_c_void] * 8 + [_c_int, _c_int]
+    if is_engine:
+        L = _e.lib()
+        L.bnlp_oa_feas_check_engine.argtypes = [_c_void, _c_void] + lp_types + [MASTER_CB, _c_void] + out_types
+        rc = L.bnlp_oa_feas_check_engine(target.h, target.problem.h, *lp_args, master, None, *out_args)
+    else:
+        P = target
+
+        def solve(ctx, B, XL, XU, X0, OBJ, ST, IT, X, G, D):
+            try:
+                r = P.solve(_as(XL, (B, n)).copy(), _as(XU, (B, n)).copy(), _as(X0, (n,)).copy())
+                _as(OBJ, (B,))[:] = r["obj"]
+                _as(ST, (B,))[:] = r["status"]
+                _as(IT, (B,))[:] = r["iters"]
+                if X:
+                    _as(X, (B, n))[:] = r["x"]
+                if D:
+                    _as(D, (B, 2 * n + m))[:] = r["duals"]
+                return 0
+            except Exception as e:
+                failure.append(e)
+                return -1
+
+        def cuts(ctx, B, X, DU, NC, RS, COL, VAL, LB, UB, SRC, cc, cn):
+            try:
+                P.duals = _as(DU, (2 * n + m,)).copy()
+                cs = P.oa(_as(X, (B, n)).copy())
+                if len(cs) > cc or sum(len(c[1]) for c in cs) > cn:
+                    return -2
+                RS[0] = 0
+                e = 0
+                for k, (src, cols, vals, l, u) in enumerate(cs):
+                    _as(COL, (cn,))[e:e + len(cols)] = cols
+                    _as(VAL, (cn,))[e:e + len(cols)] = vals
+                    e += len(cols)
+                    RS[k + 1] = e
+                    LB[k], UB[k], SRC[k] = l, u, src
+                NC[0] = len(cs)
+                return 0
+            except Exception as ex:
+                failure.append(ex)
+                return -1
+
+        L = _bb.host_lib()
+        L.bnlp_oa_feas_check_cb.argtypes = ([_c_int, _c_int, _c_void, _c_void, _c_void] + lp_types +
+                                            [_bb.CB, CUTS_CB, MASTER_CB, _c_void] + out_types)
+        vt = np.ascontiguousarray(P.vtype, np.int32)
+        xl, xu = np.ascontiguousarray(P.xl, float), np.ascontiguousarray(P.xu, float)
+        keep = (_bb.CB(solve), CUTS_CB(cuts))
+        rc = L.bnlp_oa_feas_check_cb(n, m, vp(vt), vp(xl), vp(xu), *lp_args, keep[0], keep[1], master, None, *out_args)
+    if failure:
+        raise failure[0]
+    if rc:
+        raise RuntimeError(f"bnlp_oa_feas_check failed ({rc})")
+    for k in range(res.cuts):
+        a, b = nrs[k], nrs[k + 1]
+        lp["rows"].append((int(nsrc[k]), ncol[a:b].tolist(), nval[a:b].tolist(), float(nlb[k]), float(nub[k])))
+    return dict(cutoff=res.cutoff, incumbent=(res.incumbent_obj, inc_x.copy()) if res.has_incumbent else None, cuts=res.cuts,
+                nlp_solves=res.nlp_solves, fathomed=bool(res.fathomed), x_lp=x_out.copy() if res.has_x_lp else None)

@@ -451,6 +451,31 @@ int bnlp_oa_run_cb(int n, int m, const int *var_type, const double *xl, const do
                    void *ctx, const bnlp_oa_run_options *o, bnlp_oa_run_result *res, double *best_x);
 int bnlp_oa_run_engine(bnlp_engine *, const bnlp_problem *, bnlp_master_mip_cb master, void *ctx, const bnlp_oa_run_options *o,
                        bnlp_oa_run_result *res, double *best_x);
+/* OaFeasibilityChecker::performOa (src/Algorithms/OaGenerators/BonOaFeasChecker.cpp:38-135), the generator B-QG / B-Hyb call
+ * when a node LP has an integer solution x_lp (n_cols): fix the integers, solve NLP(y), update incumbent and cutoff, linearise
+ * at the NLP point, install the cuts in the node LP (given as CSR rows + columns + objective) and re-solve it through
+ * lp_solve (a bnlp_master_mip_cb called with no integer column and no cutoff); repeated while the LP stays feasible below
+ * the cutoff, integer, and different on the integers from the NLP point.  Outputs: the installed cuts (CSR, global), the new
+ * cutoff, the incumbent if one was found, the last LP point, fathomed = the node can be cut off.  -2: a capacity is too
+ * small (res->cuts / res->new_nnz say what is needed).  add_only_violated_oa (reference default "no") is not offered. */
+typedef struct bnlp_oa_feas_options { double integer_tolerance, cutoff_increment; int max_passes; } bnlp_oa_feas_options;
+typedef struct bnlp_oa_feas_result {
+  int status, cuts, nlp_solves, fathomed, has_incumbent, has_x_lp, new_nnz;
+  double cutoff, incumbent_obj;
+} bnlp_oa_feas_result;
+int bnlp_oa_feas_check_cb(int n, int m, const int *var_type, const double *xl, const double *xu, int n_cols, int n_rows,
+                          const int *row_start, const int *col, const double *val, const double *row_lb, const double *row_ub,
+                          const double *col_lb, const double *col_ub, const double *obj, double obj_offset, const double *x_lp,
+                          double cutoff, const bnlp_oa_feas_options *o, bnlp_batch_solve_cb solve, bnlp_oa_cuts_cb cuts,
+                          bnlp_master_mip_cb lp_solve, void *ctx, bnlp_oa_feas_result *res, double *incumbent_x, double *x_lp_out,
+                          int *new_row_start, int *new_col, double *new_val, double *new_lb, double *new_ub, int *new_src,
+                          int cap_cuts, int cap_nnz);
+int bnlp_oa_feas_check_engine(bnlp_engine *, const bnlp_problem *, int n_cols, int n_rows, const int *row_start, const int *col,
+                              const double *val, const double *row_lb, const double *row_ub, const double *col_lb,
+                              const double *col_ub, const double *obj, double obj_offset, const double *x_lp, double cutoff,
+                              const bnlp_oa_feas_options *o, bnlp_master_mip_cb lp_solve, void *ctx, bnlp_oa_feas_result *res,
+                              double *incumbent_x, double *x_lp_out, int *new_row_start, int *new_col, double *new_val,
+                              double *new_lb, double *new_ub, int *new_src, int cap_cuts, int cap_nnz);
 /* Self-test of the host adapter's TNLPSolver contract (options, warm starts, error objects, output levels) on a stub
  * provider; 0 = all expectations hold, otherwise the source line of the first failure (bonmin_b200/host/host_cabi.cpp). */
 int bnlp_host_selftest(void);

@@ -217,5 +217,38 @@ def test_cpp_oa_loop_on_the_engine(bnlp_lib, oracle_ipm):
         assert np.array_equal(g["best_x"], p["best_x"])
         c = oa.run_oa(OracleProvider(m, oracle_ipm))
         assert g["status"] == c["status"] == 0
+        # both loops stop on the relative cutoff increment (1e-5): two arithmetic providers may end on different incumbents
+        # inside that band
+        assert g["best_obj"] == pytest.approx(c["best_obj"], rel=2e-5, abs=2e-5)
+        eng.close()
+
+
+_QG_KEYS = ("status", "best_obj", "nodes", "nlp_solves", "cuts")
+
+
+@pytest.mark.parametrize("mk", [lambda: I.mytoy(), lambda: I.syn_miqcp(12, 6, 3, 3, 4),
+                                lambda: I.syn_cvx_minlp(16, 6, 3, 5, 2)])
+def test_cpp_feasibility_checker_inside_the_single_tree(oracle_ipm, mk):
+    # OaFeasibilityChecker::performOa in C++ (B200Oa.cpp: oa_feas_check, bnlp_oa_feas_check_cb) in the place of the Python
+    # feasibility_check inside B-QG: the tree must be the same tree (nodes, NLP solves, cuts, optimum)
+    m = mk()
+    p = oa.run_qg(OracleProvider(m, oracle_ipm))
+    P = OracleProvider(m, oracle_ipm)
+    c = oa.run_qg(P, feas_check=lambda _, lp, lb, ub, x, cutoff, it, ci: oa.feasibility_check_native(P, lp, lb, ub, x, cutoff, it, ci))
+    assert {k: c[k] for k in _QG_KEYS} == {k: p[k] for k in _QG_KEYS}
+    assert np.array_equal(c["best_x"], p["best_x"])
+
+
+@pytest.mark.gpu
+def test_cpp_feasibility_checker_on_the_engine(bnlp_lib, oracle_ipm):
+    from bonmin_b200.engine import Engine, Problem
+    for m in (I.mytoy(), I.syn_miqcp(12, 6, 3, 3, 4), I.syn_cvx_minlp(16, 6, 3, 5, 2)):
+        eng = Engine(Problem.from_model(m))
+        p = oa.run_qg(oa.EngineProvider(eng))
+        g = oa.run_qg(oa.EngineProvider(eng),
+                      feas_check=lambda _, lp, lb, ub, x, cutoff, it, ci: oa.feasibility_check_native(eng, lp, lb, ub, x, cutoff, it, ci))
+        assert {k: g[k] for k in _QG_KEYS} == {k: p[k] for k in _QG_KEYS}
+        c = oa.run_qg(OracleProvider(m, oracle_ipm))
+        assert g["status"] == c["status"] == 0
         assert g["best_obj"] == pytest.approx(c["best_obj"], rel=1e-6, abs=1e-8)
         eng.close()
