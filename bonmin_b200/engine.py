@@ -63,7 +63,8 @@ EXPORTS = ["bnlp_last_error", "bnlp_problem_from_nl", "bnlp_problem_from_tape", 
            "bnlp_read_batch_replay_header", "bnlp_read_batch_replay", "bnlp_sol_status", "bnlp_nl_header_options",
            "bnlp_write_sol", "bnlp_write_plain_sol", "bnlp_problem_cut_strengthening", "bnlp_problem_branching_info", "bnlp_problem_sos_info", "bnlp_host_register", "bnlp_host_unregister", "bnlp_host_selftest", "bnlp_linearizer_engine",
            "bnlp_comm_unique_id", "bnlp_comm_create", "bnlp_comm_free", "bnlp_comm_stats", "bnlp_comm_allreduce_min",
-           "bnlp_solve_batch_sharded", "bnlp_bb_run_engine_sharded", "bnlp_oa_run_cb", "bnlp_oa_run_engine", "bnlp_oa_feas_check_cb", "bnlp_oa_feas_check_engine"]
+           "bnlp_solve_batch_sharded", "bnlp_bb_run_engine_sharded", "bnlp_oa_run_cb", "bnlp_oa_run_engine", "bnlp_oa_feas_check_cb", "bnlp_oa_feas_check_engine", "bnlp_oa_nlp_optim_cb", "bnlp_oa_nlp_optim_engine",
+           "bnlp_ecp_rounds_cb", "bnlp_ecp_rounds_engine"]
 
 
 def pin_array(a):

@@ -175,4 +175,80 @@ OaFeasResult oa_feas_check(const TMINLP2TNLP &root, OaLp &lp, const double *x_lp
   return R;
 }
 
+OaNlpOptimResult oa_nlp_optim(const TMINLP2TNLP &root, const double *node_lb, const double *node_ub, const double *x_lp,
+                              const BatchSolveFn &solve, const OaCutsFn &oa) {
+  OaNlpOptimResult R;
+  const int n = root.n, m = root.m;
+  std::vector<double> XL(root.x_l_), XU(root.x_u_);
+  for (int j = 0; j < n; ++j)
+    if (root.var_types[j] != 0) { XL[j] = node_lb[j]; XU[j] = node_ub[j]; }
+  R.x.assign(n, 0.0); R.duals.assign(2 * (size_t)n + m, 0.0);
+  int iters = 0;
+  if (int rc = solve(1, XL.data(), XU.data(), x_lp, &R.obj, &R.nlp_status, &iters, R.x.data(), nullptr, R.duals.data())) {
+    R.rc = rc < 0 ? rc : -1;
+    return R;
+  }
+  if (R.nlp_status == -3 || R.nlp_status == -2) { R.rc = -3; return R; }   // isAbandoned() || isIterationLimitReached()
+  if (int rc = oa(1, R.x.data(), R.duals.data(), R.cuts)) { R.rc = rc < 0 ? rc : -1; return R; }
+  if (R.nlp_status == 1 || R.nlp_status == 2) {
+    double frac = 0;
+    for (int j = 0; j < n; ++j)
+      if (root.var_types[j] != 0) frac = std::max(frac, std::fabs(R.x[j] - std::floor(R.x[j] + 0.5)));
+    R.has_solution = frac <= 1e-7;
+  }
+  return R;
+}
+
+OaEcpResult oa_ecp_rounds(int n, int m, OaLp &lp, const int *is_integer, const double *duals, int rounds, double abs_tol,
+                          double rel_tol, const OaCutsFn &oa, const OaViolationFn &violation, const MasterMipFn &lp_solve) {
+  OaEcpResult R;
+  const int ncols = lp.n_cols;
+  const std::vector<int> no_integer(ncols, 0);
+  const std::vector<double> zero_duals(2 * (size_t)n + m, 0.0);
+  if (!duals) duals = zero_duals.data();
+  R.x.assign(ncols, 0.0);
+  double val = 0;
+  auto solve_lp = [&]() {
+    return lp_solve(ncols, (int)lp.row_lb.size(), lp.row_start.data(), lp.col.data(), lp.val.data(), lp.row_lb.data(),
+                    lp.row_ub.data(), lp.col_lb.data(), lp.col_ub.data(), lp.obj.data(), lp.obj_offset,
+                    is_integer ? is_integer : no_integer.data(), 1e100, 1e10, R.x.data(), &val);
+  };
+  int st = solve_lp();
+  if (st < 0) { R.rc = st; return R; }
+  if (st != 0) { R.lp_infeasible = true; R.obj = DBL_MAX; return R; }
+  auto alpha = [&]() { return ncols > n ? R.x[n] : val; };     // the LP's value of the objective (alpha column)
+  double orig = 0;
+  if (int rc = violation(R.x.data(), alpha(), &orig)) { R.rc = rc < 0 ? rc : -1; return R; }
+  R.violation = orig;
+  double viol = orig;
+  for (int i = 0; i < rounds; ++i) {
+    if (!(viol > abs_tol && viol > rel_tol * orig)) break;
+    CutRows cuts;
+    if (int rc = oa(1, R.x.data(), duals, cuts)) { R.rc = rc < 0 ? rc : -1; return R; }
+    int kept = 0;
+    const int first = R.cs.size();
+    for (int k = 0; k < cuts.size(); ++k) {
+      if (cuts.src_row[k] == m && ncols == n) continue;
+      for (int e = cuts.row_start[k]; e < cuts.row_start[k + 1]; ++e) { R.cs.col.push_back(cuts.col[e]); R.cs.val.push_back(cuts.val[e]); }
+      R.cs.row_start.push_back((int)R.cs.col.size());
+      R.cs.lb.push_back(cuts.lb[k]); R.cs.ub.push_back(cuts.ub[k]); R.cs.src_row.push_back(cuts.src_row[k]);
+      ++kept;
+    }
+    if (!kept || i + 1 >= rounds) break;
+    for (int k = first; k < first + kept; ++k) {               // installCuts
+      for (int e = R.cs.row_start[k]; e < R.cs.row_start[k + 1]; ++e) { lp.col.push_back(R.cs.col[e]); lp.val.push_back(R.cs.val[e]); }
+      lp.row_start.push_back((int)lp.col.size()); lp.row_lb.push_back(R.cs.lb[k]); lp.row_ub.push_back(R.cs.ub[k]);
+    }
+    R.installed += kept;
+    ++R.rounds;
+    st = solve_lp();
+    if (st < 0) { R.rc = st; return R; }
+    if (st != 0) { R.lp_infeasible = true; R.obj = DBL_MAX; return R; }
+    if (int rc = violation(R.x.data(), alpha(), &viol)) { R.rc = rc < 0 ? rc : -1; return R; }
+  }
+  R.violation = viol;
+  R.obj = val;
+  return R;
+}
+
 }  // namespace Bonmin

@@ -74,4 +74,22 @@ struct OaFeasResult {
 OaFeasResult oa_feas_check(const TMINLP2TNLP &root, OaLp &lp /* rows are appended */, const double *x_lp, double cutoff,
                            const BatchSolveFn &solve, const OaCutsFn &oa, const MasterMipFn &lp_solve, const OaFeasOptions &opt);
 
+// OaNlpOptim::generateCuts (src/Algorithms/OaGenerators/BonOaNlpOptim.cpp:63-173): the NLP relaxation of the NODE (integer
+// columns take the node LP's bounds), OA cuts at its solution (getObj = 1), and the solution itself when it happens to be
+// integer (1e-7).  status -3 / -2 of the NLP (abandoned, iteration limit) is the reference's "Unsolved NLP ... exit": rc -3.
+struct OaNlpOptimResult { int rc = 0, nlp_status = 0; double obj = 0; bool has_solution = false;
+                          std::vector<double> x, duals; CutRows cuts; };
+OaNlpOptimResult oa_nlp_optim(const TMINLP2TNLP &root, const double *node_lb, const double *node_ub, const double *x_lp,
+                              const BatchSolveFn &solve, const OaCutsFn &oa);
+
+// EcpCuts::generateCuts (src/Algorithms/OaGenerators/BonEcpCuts.cpp:46-143) on an LP: while the LP optimum violates the
+// nonlinear rows (getNonLinearitiesViolation), linearise them AT THE LP POINT, install the cuts, re-solve.  `cs` collects the
+// cuts of EVERY round — the last round's too, which are generated but neither installed nor re-solved (:86).
+using OaViolationFn = std::function<int(const double *x, double obj, double *viol)>;
+struct OaEcpResult { int rc = 0, rounds = 0, installed = 0; bool lp_infeasible = false; double violation = 0, obj = 0;
+                     CutRows cs; std::vector<double> x; };
+OaEcpResult oa_ecp_rounds(int n, int m, OaLp &lp /* installed cuts are appended */, const int *is_integer, const double *duals,
+                          int rounds, double abs_violation_tol, double rel_violation_tol, const OaCutsFn &oa,
+                          const OaViolationFn &violation, const MasterMipFn &lp_solve);
+
 }  // namespace Bonmin

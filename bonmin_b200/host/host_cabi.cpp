@@ -182,6 +182,97 @@ int bnlp_oa_run_cb(int n, int m, const int *var_type, const double *xl, const do
   return R.status < 0 ? R.status : 0;
 }
 
+namespace {
+// shared by the OA entry points: C callbacks -> the std::function providers of B200Oa.hpp, cut rows -> flat CSR outputs
+Bonmin::BatchSolveFn oa_wrap_solve(bnlp_batch_solve_cb solve, void *ctx) {
+  return [solve, ctx](int B, const double *XL, const double *XU, const double *X0, double *OBJ, int *STATUS, int *ITERS, double *X,
+                      double *G, double *DUALS) { return solve(ctx, B, XL, XU, X0, OBJ, STATUS, ITERS, X, G, DUALS); };
+}
+Bonmin::OaCutsFn oa_wrap_cuts(bnlp_oa_cuts_cb cuts, void *ctx, int n, int m) {
+  const size_t rows_cap = (size_t)m + 1, nnz_row = (size_t)n + 1;
+  return [cuts, ctx, rows_cap, nnz_row](int B, const double *X, const double *duals, Bonmin::CutRows &out) {
+    const int cc = (int)(B * rows_cap), cn = (int)(B * rows_cap * nnz_row);
+    out.row_start.assign(cc + 1, 0); out.col.resize(cn); out.val.resize(cn);
+    out.lb.resize(cc); out.ub.resize(cc); out.src_row.resize(cc);
+    int nc = 0;
+    const int rc = cuts(ctx, B, X, duals, &nc, out.row_start.data(), out.col.data(), out.val.data(), out.lb.data(), out.ub.data(),
+                        out.src_row.data(), cc, cn);
+    if (rc) return rc;
+    if (nc < 0 || nc > cc) return -2;
+    out.row_start.resize(nc + 1); out.lb.resize(nc); out.ub.resize(nc); out.src_row.resize(nc);
+    return 0;
+  };
+}
+Bonmin::MasterMipFn oa_wrap_master(bnlp_master_mip_cb f, void *ctx) {
+  return [f, ctx](int nc, int nr, const int *rs, const int *cl, const double *vl, const double *rlb, const double *rub,
+                  const double *clb, const double *cub, const double *ob, double off, const int *isint, double co, double maxs,
+                  double *x, double *bound) { return f(ctx, nc, nr, rs, cl, vl, rlb, rub, clb, cub, ob, off, isint, co, maxs, x, bound); };
+}
+int oa_rows_out(const Bonmin::CutRows &R, int *new_row_start, int *new_col, double *new_val, double *new_lb, double *new_ub,
+                int *new_src, int cap_cuts, int cap_nnz) {
+  const int nc = R.size(), nnz = (int)R.col.size();
+  if (nc > cap_cuts || nnz > cap_nnz) return -2;
+  if (new_row_start) std::memcpy(new_row_start, R.row_start.data(), sizeof(int) * (nc + 1));
+  if (nc) {
+    std::memcpy(new_col, R.col.data(), sizeof(int) * nnz); std::memcpy(new_val, R.val.data(), sizeof(double) * nnz);
+    std::memcpy(new_lb, R.lb.data(), sizeof(double) * nc); std::memcpy(new_ub, R.ub.data(), sizeof(double) * nc);
+    if (new_src) std::memcpy(new_src, R.src_row.data(), sizeof(int) * nc);
+  }
+  return 0;
+}
+Bonmin::OaLp oa_lp_in(int n_cols, int n_rows, const int *row_start, const int *col, const double *val, const double *row_lb,
+                      const double *row_ub, const double *col_lb, const double *col_ub, const double *obj, double obj_offset) {
+  Bonmin::OaLp lp;
+  lp.n_cols = n_cols; lp.obj_offset = obj_offset;
+  lp.row_start.assign(row_start, row_start + n_rows + 1);
+  lp.col.assign(col, col + row_start[n_rows]); lp.val.assign(val, val + row_start[n_rows]);
+  lp.row_lb.assign(row_lb, row_lb + n_rows); lp.row_ub.assign(row_ub, row_ub + n_rows);
+  lp.col_lb.assign(col_lb, col_lb + n_cols); lp.col_ub.assign(col_ub, col_ub + n_cols); lp.obj.assign(obj, obj + n_cols);
+  return lp;
+}
+}  // namespace
+
+// OaNlpOptim::generateCuts (B200Oa.cpp: oa_nlp_optim) over caller-supplied arithmetic
+int bnlp_oa_nlp_optim_cb(int n, int m, const int *var_type, const double *xl, const double *xu, const double *node_lb,
+                         const double *node_ub, const double *x_lp, bnlp_batch_solve_cb solve, bnlp_oa_cuts_cb cuts, void *ctx,
+                         bnlp_nlp_optim_result *res, double *x_nlp, double *duals_out, int *new_row_start, int *new_col,
+                         double *new_val, double *new_lb, double *new_ub, int *new_src, int cap_cuts, int cap_nnz) {
+  using namespace Bonmin;
+  if (!solve || !cuts || !res || n <= 0 || m < 0) return -1;
+  Ipopt::SmartPtr<TMINLP2TNLP> holder = new TMINLP2TNLP();
+  TMINLP2TNLP &root = *holder;
+  root.n = n; root.m = m;
+  root.var_types.assign(var_type, var_type + n);
+  root.x_l_.assign(xl, xl + n); root.x_u_.assign(xu, xu + n);
+  OaNlpOptimResult R = oa_nlp_optim(root, node_lb, node_ub, x_lp, oa_wrap_solve(solve, ctx), oa_wrap_cuts(cuts, ctx, n, m));
+  res->nlp_status = R.nlp_status; res->cuts = R.cuts.size(); res->new_nnz = (int)R.cuts.col.size();
+  res->has_solution = R.has_solution; res->obj = R.obj;
+  if (R.rc) return R.rc;
+  if (x_nlp) std::memcpy(x_nlp, R.x.data(), sizeof(double) * n);
+  if (duals_out) std::memcpy(duals_out, R.duals.data(), sizeof(double) * (2 * (size_t)n + m));
+  return oa_rows_out(R.cuts, new_row_start, new_col, new_val, new_lb, new_ub, new_src, cap_cuts, cap_nnz);
+}
+
+// EcpCuts::generateCuts (B200Oa.cpp: oa_ecp_rounds) over caller-supplied arithmetic and LP solver
+int bnlp_ecp_rounds_cb(int n, int m, int n_cols, int n_rows, const int *row_start, const int *col, const double *val,
+                       const double *row_lb, const double *row_ub, const double *col_lb, const double *col_ub, const double *obj,
+                       double obj_offset, const int *is_integer, const double *duals, int rounds, double abs_tol, double rel_tol,
+                       bnlp_oa_cuts_cb cuts, bnlp_violation_cb violation, bnlp_master_mip_cb lp_solve, void *ctx,
+                       bnlp_ecp_result *res, double *x_out, int *new_row_start, int *new_col, double *new_val, double *new_lb,
+                       double *new_ub, int *new_src, int cap_cuts, int cap_nnz) {
+  using namespace Bonmin;
+  if (!cuts || !violation || !lp_solve || !res || n <= 0 || m < 0 || n_cols < n || n_rows < 0) return -1;
+  OaLp lp = oa_lp_in(n_cols, n_rows, row_start, col, val, row_lb, row_ub, col_lb, col_ub, obj, obj_offset);
+  OaViolationFn vf = [violation, ctx](const double *x, double o, double *v) { return violation(ctx, x, o, v); };
+  OaEcpResult R = oa_ecp_rounds(n, m, lp, is_integer, duals, rounds, abs_tol, rel_tol, oa_wrap_cuts(cuts, ctx, n, m), vf,
+                                oa_wrap_master(lp_solve, ctx));
+  res->rounds = R.rounds; res->cuts = R.cs.size(); res->installed = R.installed; res->new_nnz = (int)R.cs.col.size();
+  res->lp_infeasible = R.lp_infeasible; res->violation = R.violation; res->obj = R.obj;
+  if (R.rc) return R.rc;
+  if (x_out) std::memcpy(x_out, R.x.data(), sizeof(double) * n_cols);
+  return oa_rows_out(R.cs, new_row_start, new_col, new_val, new_lb, new_ub, new_src, cap_cuts, cap_nnz);
+}
+
 // OaFeasibilityChecker::performOa (B200Oa.cpp: oa_feas_check) over caller-supplied arithmetic and LP solver
 int bnlp_oa_feas_check_cb(int n, int m, const int *var_type, const double *xl, const double *xu, int n_cols, int n_rows,
                           const int *row_start, const int *col, const double *val, const double *row_lb, const double *row_ub,
@@ -640,6 +731,34 @@ int bnlp_oa_run_engine(bnlp_engine *E, const bnlp_problem *P, bnlp_master_mip_cb
   bnlp_problem_info(P, nullptr, nullptr, nullptr, nullptr, vt.data(), nullptr, C.xl.data(), C.xu.data(), nullptr, nullptr, x0.data());
   return bnlp_oa_run_cb(n, m, vt.data(), C.xl.data(), C.xu.data(), x0.data(), oa_eng_solve, oa_eng_cuts, oa_eng_extract,
                         oa_eng_master, &C, o, res, best_x);
+}
+int bnlp_oa_nlp_optim_engine(bnlp_engine *E, const bnlp_problem *P, const double *node_lb, const double *node_ub, const double *x_lp,
+                             bnlp_nlp_optim_result *res, double *x_nlp, double *duals_out, int *new_row_start, int *new_col,
+                             double *new_val, double *new_lb, double *new_ub, int *new_src, int cap_cuts, int cap_nnz) {
+  int n = 0, m = 0;
+  if (!E || !P || !res || bnlp_problem_sizes(P, &n, &m, nullptr, nullptr)) return -1;
+  std::vector<int> vt(n);
+  OaEngineCtx C{E, n, m, std::vector<double>(n), std::vector<double>(n), nullptr, nullptr};
+  bnlp_problem_info(P, nullptr, nullptr, nullptr, nullptr, vt.data(), nullptr, C.xl.data(), C.xu.data(), nullptr, nullptr, nullptr);
+  return bnlp_oa_nlp_optim_cb(n, m, vt.data(), C.xl.data(), C.xu.data(), node_lb, node_ub, x_lp, oa_eng_solve, oa_eng_cuts, &C, res,
+                              x_nlp, duals_out, new_row_start, new_col, new_val, new_lb, new_ub, new_src, cap_cuts, cap_nnz);
+}
+int bnlp_ecp_rounds_engine(bnlp_engine *E, const bnlp_problem *P, int n_cols, int n_rows, const int *row_start, const int *col,
+                           const double *val, const double *row_lb, const double *row_ub, const double *col_lb,
+                           const double *col_ub, const double *obj, double obj_offset, const int *is_integer, const double *duals,
+                           int rounds, double abs_tol, double rel_tol, bnlp_master_mip_cb lp_solve, void *ctx,
+                           bnlp_ecp_result *res, double *x_out, int *new_row_start, int *new_col, double *new_val, double *new_lb,
+                           double *new_ub, int *new_src, int cap_cuts, int cap_nnz) {
+  int n = 0, m = 0;
+  if (!E || !P || !lp_solve || !res || bnlp_problem_sizes(P, &n, &m, nullptr, nullptr)) return -1;
+  OaEngineCtx C{E, n, m, std::vector<double>(n), std::vector<double>(n), lp_solve, ctx};
+  bnlp_problem_info(P, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, C.xl.data(), C.xu.data(), nullptr, nullptr, nullptr);
+  auto viol = [](void *p, const double *x, double o, double *v) {    // getNonLinearitiesViolation(x, obj)
+    return bnlp_violation_batch(((OaEngineCtx *)p)->E, 1, x, &o, v, nullptr);
+  };
+  return bnlp_ecp_rounds_cb(n, m, n_cols, n_rows, row_start, col, val, row_lb, row_ub, col_lb, col_ub, obj, obj_offset, is_integer,
+                            duals, rounds, abs_tol, rel_tol, oa_eng_cuts, viol, oa_eng_master, &C, res, x_out, new_row_start, new_col,
+                            new_val, new_lb, new_ub, new_src, cap_cuts, cap_nnz);
 }
 int bnlp_oa_feas_check_engine(bnlp_engine *E, const bnlp_problem *P, int n_cols, int n_rows, const int *row_start, const int *col,
                               const double *val, const double *row_lb, const double *row_ub, const double *col_lb,

@@ -317,7 +317,7 @@ def nlp_optim_wanted(level, solves_per_level=1.0, max_depth=10, rng=None):
 
 
 def run_qg(provider, integer_tolerance=1e-6, cutoff_increment=1e-5, node_limit=100000, nlp_solves_per_level=0.0,
-           nlp_max_depth=10, seed=0, time_limit=1e10, log=None, feas_check=None):
+           nlp_max_depth=10, seed=0, time_limit=1e10, log=None, feas_check=None, nlp_optim=None):
     """A single-tree LP/NLP-based branch and bound in the manner of B-QG (nlp_solves_per_level = 0) and B-Hyb (> 0):
     LP relaxation from extractLinearRelaxation at the root NLP optimum, best-bound search branching on the most
     fractional integer, OaFeasibilityChecker at integer LP points, OaNlpOptim at nodes by the depth rule.  Host control
@@ -356,7 +356,7 @@ def run_qg(provider, integer_tolerance=1e-6, cutoff_increment=1e-5, node_limit=1
         if not feas:
             continue
         if nlp_solves_per_level > 0 and nlp_optim_wanted(level, nlp_solves_per_level, nlp_max_depth, rng):
-            g = nlp_optim_cuts(P, lb, ub, x)
+            g = (nlp_optim or nlp_optim_cuts)(P, lb, ub, x)      # or the C++ generator (nlp_optim_cuts_native)
             out["nlp_solves"] += 1
             new = [c for c in g["cuts"] if not (c[0] == P.m and ncols == n)]
             lp["rows"].extend(new)
@@ -673,3 +673,163 @@ def feasibility_check_native(target, lp, col_lb, col_ub, x_lp, cutoff, integer_t
         lp["rows"].append((int(nsrc[k]), ncol[a:b].tolist(), nval[a:b].tolist(), float(nlb[k]), float(nub[k])))
     return dict(cutoff=res.cutoff, incumbent=(res.incumbent_obj, inc_x.copy()) if res.has_incumbent else None, cuts=res.cuts,
                 nlp_solves=res.nlp_solves, fathomed=bool(res.fathomed), x_lp=x_out.copy() if res.has_x_lp else None)
+
+
+class NlpOptimResult(_ct.Structure):
+    _fields_ = [("nlp_status", _c_int), ("cuts", _c_int), ("new_nnz", _c_int), ("has_solution", _c_int), ("obj", _c_dbl)]
+
+
+class EcpResult(_ct.Structure):
+    _fields_ = [("rounds", _c_int), ("cuts", _c_int), ("installed", _c_int), ("new_nnz", _c_int), ("lp_infeasible", _c_int),
+                ("violation", _c_dbl), ("obj", _c_dbl)]
+
+
+VIOL_CB = _ct.CFUNCTYPE(_c_int, _c_void, _P_dbl, _c_dbl, _P_dbl)
+
+
+def _provider_callbacks(P, failure):
+    """ctypes callbacks (solve, cuts, violation) over an arithmetic provider."""
+    n, m = P.n, P.m
+
+    def solve(ctx, B, XL, XU, X0, OBJ, ST, IT, X, G, D):
+        try:
+            r = P.solve(_as(XL, (B, n)).copy(), _as(XU, (B, n)).copy(), _as(X0, (n,)).copy())
+            _as(OBJ, (B,))[:] = r["obj"]
+            _as(ST, (B,))[:] = r["status"]
+            _as(IT, (B,))[:] = r["iters"]
+            if X:
+                _as(X, (B, n))[:] = r["x"]
+            if D:
+                _as(D, (B, 2 * n + m))[:] = r["duals"]
+            return 0
+        except Exception as e:
+            failure.append(e)
+            return -1
+
+    def cuts(ctx, B, X, DU, NC, RS, COL, VAL, LB, UB, SRC, cc, cn):
+        try:
+            P.duals = _as(DU, (2 * n + m,)).copy()
+            cs = P.oa(_as(X, (B, n)).copy())
+            if len(cs) > cc or sum(len(c[1]) for c in cs) > cn:
+                return -2
+            RS[0] = 0
+            e = 0
+            for k, (src, cols, vals, l, u) in enumerate(cs):
+                _as(COL, (cn,))[e:e + len(cols)] = cols
+                _as(VAL, (cn,))[e:e + len(cols)] = vals
+                e += len(cols)
+                RS[k + 1] = e
+                LB[k], UB[k], SRC[k] = l, u, src
+            NC[0] = len(cs)
+            return 0
+        except Exception as ex:
+            failure.append(ex)
+            return -1
+
+    def viol(ctx, X, obj, V):
+        try:
+            V[0] = P.violation(_as(X, (n,)).copy(), obj)
+            return 0
+        except Exception as ex:
+            failure.append(ex)
+            return -1
+
+    from . import bb as _bb
+    return _bb.CB(solve), CUTS_CB(cuts), VIOL_CB(viol)
+
+
+def _cut_outs(cap_cuts, cap_nnz):
+    return (np.zeros(cap_cuts + 1, np.int32), np.zeros(max(cap_nnz, 1), np.int32), np.zeros(max(cap_nnz, 1)), np.zeros(max(cap_cuts, 1)),
+            np.zeros(max(cap_cuts, 1)), np.zeros(max(cap_cuts, 1), np.int32))
+
+
+def _cuts_list(k_cuts, outs):
+    nrs, ncol, nval, nlb, nub, nsrc = outs
+    return [(int(nsrc[k]), ncol[nrs[k]:nrs[k + 1]].tolist(), nval[nrs[k]:nrs[k + 1]].tolist(), float(nlb[k]), float(nub[k]))
+            for k in range(k_cuts)]
+
+
+def nlp_optim_cuts_native(target, node_lb, node_ub, x_lp):
+    """nlp_optim_cuts through the C++ generator (B200Oa.cpp: oa_nlp_optim); target: an Engine (bnlp_oa_nlp_optim_engine) or a
+    provider (bnlp_oa_nlp_optim_cb).  Same result dict as nlp_optim_cuts, plus duals."""
+    from . import bb as _bb, engine as _e
+    n, m = target.n, target.m
+    vp = lambda a: a.ctypes.data_as(_c_void)
+    lb, ub = np.ascontiguousarray(np.asarray(node_lb, float)[:n]), np.ascontiguousarray(np.asarray(node_ub, float)[:n])
+    xlp = np.ascontiguousarray(np.asarray(x_lp, float)[:n])
+    outs = _cut_outs(m + 1, (m + 1) * (n + 1))
+    res, x, du = NlpOptimResult(), np.zeros(n), np.zeros(2 * n + m)
+    tail = [_ct.byref(res), vp(x), vp(du)] + [vp(a) for a in outs] + [m + 1, (m + 1) * (n + 1)]
+    tail_t = [_ct.POINTER(NlpOptimResult)] + [_c_void] * 8 + [_c_int, _c_int]
+    failure = []
+    if isinstance(target, _e.Engine):
+        L = _e.lib()
+        L.bnlp_oa_nlp_optim_engine.argtypes = [_c_void] * 5 + tail_t
+        rc = L.bnlp_oa_nlp_optim_engine(target.h, target.problem.h, vp(lb), vp(ub), vp(xlp), *tail)
+    else:
+        P = target
+        cbs = _provider_callbacks(P, failure)
+        L = _bb.host_lib()
+        L.bnlp_oa_nlp_optim_cb.argtypes = [_c_int, _c_int] + [_c_void] * 6 + [_bb.CB, CUTS_CB, _c_void] + tail_t
+        vt = np.ascontiguousarray(P.vtype, np.int32)
+        xl, xu = np.ascontiguousarray(P.xl, float), np.ascontiguousarray(P.xu, float)
+        rc = L.bnlp_oa_nlp_optim_cb(n, m, vp(vt), vp(xl), vp(xu), vp(lb), vp(ub), vp(xlp), cbs[0], cbs[1], None, *tail)
+    if failure:
+        raise failure[0]
+    if rc == -3:
+        raise RuntimeError("Unsolved NLP ... exit")
+    if rc:
+        raise RuntimeError(f"bnlp_oa_nlp_optim failed ({rc})")
+    return dict(cuts=_cuts_list(res.cuts, outs), solution=(res.obj, x.copy()) if res.has_solution else None, status=res.nlp_status,
+                obj=res.obj, duals=du)
+
+
+def ecp_rounds_native(target, lp, rounds=5, abs_violation_tol=1e-6, rel_violation_tol=1e-4, integer=None, duals=None):
+    """ecp_rounds through the C++ generator (B200Oa.cpp: oa_ecp_rounds); target: an Engine (bnlp_ecp_rounds_engine) or a provider
+    (bnlp_ecp_rounds_cb).  lp: what provider.extract returns.  Same result keys as ecp_rounds."""
+    from . import bb as _bb, engine as _e
+    is_engine = isinstance(target, _e.Engine)
+    n, m = target.n, target.m
+    info = target.problem.info() if is_engine else None
+    xl, xu = (info["xl"], info["xu"]) if is_engine else (target.xl, target.xu)
+    ncols = n + (1 if lp["has_alpha"] else 0)
+    lpd = dict(rows=list(lp["rows"]), obj=lp["obj"], obj_offset=lp["obj_offset"], ncols=ncols)
+    rs, col, val, lb, ub, clb, cub, obj = _lp_csr(lpd, np.concatenate([xl, [-DMAX]])[:ncols], np.concatenate([xu, [DMAX]])[:ncols])
+    vp = lambda a: None if a is None else a.ctypes.data_as(_c_void)
+    integ = None if integer is None else np.ascontiguousarray(integer, np.int32)
+    du = None if duals is None else np.ascontiguousarray(duals, float)
+    cap_cuts, cap_nnz = rounds * (m + 1), rounds * (m + 1) * (n + 1)
+    outs = _cut_outs(cap_cuts, cap_nnz)
+    res, x = EcpResult(), np.zeros(ncols)
+    failure = []
+    master = highs_master(failure)
+    head = [ncols, len(lpd["rows"]), vp(rs), vp(col), vp(val), vp(lb), vp(ub), vp(clb), vp(cub), vp(obj), float(lp["obj_offset"]),
+            vp(integ), vp(du), int(rounds), float(abs_violation_tol), float(rel_violation_tol)]
+    head_t = [_c_int, _c_int] + [_c_void] * 8 + [_c_dbl, _c_void, _c_void, _c_int, _c_dbl, _c_dbl]
+    tail = [_ct.byref(res), vp(x)] + [vp(a) for a in outs] + [cap_cuts, cap_nnz]
+    tail_t = [_ct.POINTER(EcpResult)] + [_c_void] * 7 + [_c_int, _c_int]
+    if is_engine:
+        L = _e.lib()
+        L.bnlp_ecp_rounds_engine.argtypes = [_c_void, _c_void] + head_t + [MASTER_CB, _c_void] + tail_t
+        rc = L.bnlp_ecp_rounds_engine(target.h, target.problem.h, *head, master, None, *tail)
+    else:
+        cbs = _provider_callbacks(target, failure)
+        if du is not None:
+            target.duals = du
+        L = _bb.host_lib()
+        L.bnlp_ecp_rounds_cb.argtypes = [_c_int, _c_int] + head_t + [CUTS_CB, VIOL_CB, MASTER_CB, _c_void] + tail_t
+        if du is None:
+            head[12] = vp(np.ascontiguousarray(target.duals, float))
+        rc = L.bnlp_ecp_rounds_cb(n, m, *head, cbs[1], cbs[2], master, None, *tail)
+    if failure:
+        raise failure[0]
+    if rc:
+        raise RuntimeError(f"bnlp_ecp_rounds failed ({rc})")
+    cs = _cuts_list(res.cuts, outs)
+    out = dict(rounds=res.rounds, cuts=res.cuts, installed=res.installed, cs=cs, violation=res.violation,
+               obj=1.7976931348623157e308 if res.lp_infeasible else res.obj)
+    if not res.lp_infeasible or res.installed:
+        out["rows"] = lpd["rows"] + cs[:res.installed]
+    if not res.lp_infeasible:
+        out["x"] = x.copy()
+    return out

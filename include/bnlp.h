@@ -476,6 +476,38 @@ int bnlp_oa_feas_check_engine(bnlp_engine *, const bnlp_problem *, int n_cols, i
                               const bnlp_oa_feas_options *o, bnlp_master_mip_cb lp_solve, void *ctx, bnlp_oa_feas_result *res,
                               double *incumbent_x, double *x_lp_out, int *new_row_start, int *new_col, double *new_val,
                               double *new_lb, double *new_ub, int *new_src, int cap_cuts, int cap_nnz);
+/* OaNlpOptim::generateCuts (src/Algorithms/OaGenerators/BonOaNlpOptim.cpp:63-173): the NLP relaxation of a NODE (integer
+ * columns take node_lb / node_ub, n values each), started from x_lp; OA cuts at its solution (CSR out, getObj = 1); x_nlp (n)
+ * and duals_out (2n+m) of the solve; has_solution = the NLP point is integer (1e-7).  Returns -3 for the reference's "Unsolved
+ * NLP ... exit" (abandoned / iteration limit), -2 when a capacity is too small. */
+typedef struct bnlp_nlp_optim_result { int nlp_status, cuts, new_nnz, has_solution; double obj; } bnlp_nlp_optim_result;
+int bnlp_oa_nlp_optim_cb(int n, int m, const int *var_type, const double *xl, const double *xu, const double *node_lb,
+                         const double *node_ub, const double *x_lp, bnlp_batch_solve_cb solve, bnlp_oa_cuts_cb cuts, void *ctx,
+                         bnlp_nlp_optim_result *res, double *x_nlp, double *duals_out, int *new_row_start, int *new_col,
+                         double *new_val, double *new_lb, double *new_ub, int *new_src, int cap_cuts, int cap_nnz);
+int bnlp_oa_nlp_optim_engine(bnlp_engine *, const bnlp_problem *, const double *node_lb, const double *node_ub, const double *x_lp,
+                             bnlp_nlp_optim_result *res, double *x_nlp, double *duals_out, int *new_row_start, int *new_col,
+                             double *new_val, double *new_lb, double *new_ub, int *new_src, int cap_cuts, int cap_nnz);
+/* EcpCuts::generateCuts (src/Algorithms/OaGenerators/BonEcpCuts.cpp:46-143) on an LP (CSR rows + columns + objective;
+ * is_integer NULL = pure LP): while the LP optimum violates the nonlinear rows (getNonLinearitiesViolation) by more than
+ * abs_tol and rel_tol x the first violation, linearise them AT THE LP POINT (duals: the multipliers that pick the side of
+ * ranged rows, NULL = zeros), install the cuts, re-solve; at most `rounds` rounds.  Out: every cut generated (CSR; the first
+ * res->installed of them went into the LP — the last round's are generated but not installed, :86), the last LP point x_out
+ * (n_cols), res->obj = the LP value after the rounds (DBL_MAX and lp_infeasible when the LP became infeasible). */
+typedef int (*bnlp_violation_cb)(void *ctx, const double *x, double obj, double *viol);
+typedef struct bnlp_ecp_result { int rounds, cuts, installed, new_nnz, lp_infeasible; double violation, obj; } bnlp_ecp_result;
+int bnlp_ecp_rounds_cb(int n, int m, int n_cols, int n_rows, const int *row_start, const int *col, const double *val,
+                       const double *row_lb, const double *row_ub, const double *col_lb, const double *col_ub, const double *obj,
+                       double obj_offset, const int *is_integer, const double *duals, int rounds, double abs_tol, double rel_tol,
+                       bnlp_oa_cuts_cb cuts, bnlp_violation_cb violation, bnlp_master_mip_cb lp_solve, void *ctx,
+                       bnlp_ecp_result *res, double *x_out, int *new_row_start, int *new_col, double *new_val, double *new_lb,
+                       double *new_ub, int *new_src, int cap_cuts, int cap_nnz);
+int bnlp_ecp_rounds_engine(bnlp_engine *, const bnlp_problem *, int n_cols, int n_rows, const int *row_start, const int *col,
+                           const double *val, const double *row_lb, const double *row_ub, const double *col_lb,
+                           const double *col_ub, const double *obj, double obj_offset, const int *is_integer, const double *duals,
+                           int rounds, double abs_tol, double rel_tol, bnlp_master_mip_cb lp_solve, void *ctx,
+                           bnlp_ecp_result *res, double *x_out, int *new_row_start, int *new_col, double *new_val, double *new_lb,
+                           double *new_ub, int *new_src, int cap_cuts, int cap_nnz);
 /* Self-test of the host adapter's TNLPSolver contract (options, warm starts, error objects, output levels) on a stub
  * provider; 0 = all expectations hold, otherwise the source line of the first failure (bonmin_b200/host/host_cabi.cpp). */
 int bnlp_host_selftest(void);

@@ -252,3 +252,55 @@ def test_cpp_feasibility_checker_on_the_engine(bnlp_lib, oracle_ipm):
         assert g["status"] == c["status"] == 0
         assert g["best_obj"] == pytest.approx(c["best_obj"], rel=1e-6, abs=1e-8)
         eng.close()
+
+
+def _native(target):
+    return dict(feas_check=lambda _, lp, lb, ub, x, cutoff, it, ci: oa.feasibility_check_native(target, lp, lb, ub, x, cutoff, it, ci),
+                nlp_optim=lambda _, lb, ub, x: oa.nlp_optim_cuts_native(target, lb, ub, x))
+
+
+@pytest.mark.parametrize("mk", [lambda: I.syn_miqcp(12, 6, 3, 3, 4), lambda: I.syn_cvx_minlp(16, 6, 3, 5, 2)])
+def test_cpp_generators_inside_b_hyb(oracle_ipm, mk):
+    # OaNlpOptim::generateCuts and OaFeasibilityChecker::performOa in C++ (B200Oa.cpp) in the places of the Python ones inside
+    # the single-tree B-Hyb: same tree, same cuts, same optimum
+    m = mk()
+    p = oa.run_qg(OracleProvider(m, oracle_ipm), nlp_solves_per_level=1.0, seed=3)
+    P = OracleProvider(m, oracle_ipm)
+    c = oa.run_qg(P, nlp_solves_per_level=1.0, seed=3, **_native(P))
+    assert {k: c[k] for k in _QG_KEYS} == {k: p[k] for k in _QG_KEYS}
+    assert np.array_equal(c["best_x"], p["best_x"])
+
+
+def test_cpp_ecp_rounds_reproduce_the_python_rounds(oracle_ipm):
+    m = I.syn_miqcp(12, 6, 3, 3, 4)
+    P = OracleProvider(m, oracle_ipm)
+    P.solve(m.xl[None, :], m.xu[None, :], m.x0)
+    lp = P.extract(np.clip(m.x0, m.xl, m.xu), None)
+    for rounds in (1, 3, 8):
+        p = oa.ecp_rounds(P, lp, rounds=rounds)
+        c = oa.ecp_rounds_native(P, lp, rounds=rounds)
+        assert (c["rounds"], c["cuts"], c["installed"]) == (p["rounds"], p["cuts"], p["installed"])
+        assert c["obj"] == p["obj"] and c["violation"] == p["violation"]
+        assert c["cs"] == [(int(a), list(b), list(v), float(l), float(u)) for a, b, v, l, u in p["cs"]]
+
+
+@pytest.mark.gpu
+def test_cpp_generators_on_the_engine(bnlp_lib, oracle_ipm):
+    from bonmin_b200.engine import Engine, Problem
+    for m in (I.syn_miqcp(12, 6, 3, 3, 4), I.syn_cvx_minlp(16, 6, 3, 5, 2)):
+        eng = Engine(Problem.from_model(m))
+        p = oa.run_qg(oa.EngineProvider(eng), nlp_solves_per_level=1.0, seed=3)
+        g = oa.run_qg(oa.EngineProvider(eng), nlp_solves_per_level=1.0, seed=3, **_native(eng))
+        assert {k: g[k] for k in _QG_KEYS} == {k: p[k] for k in _QG_KEYS}
+        c = oa.run_qg(OracleProvider(m, oracle_ipm), nlp_solves_per_level=1.0, seed=3)
+        assert g["status"] == c["status"] == 0 and g["best_obj"] == pytest.approx(c["best_obj"], rel=2e-5, abs=2e-5)
+        # ECP rounds: the C++ generator on the engine against the Python rounds on the engine
+        P = oa.EngineProvider(eng)
+        root = P.solve(m.xl[None, :], m.xu[None, :], m.x0)
+        lp = P.extract(np.clip(m.x0, m.xl, m.xu), None)
+        for rounds in (1, 4):
+            pe = oa.ecp_rounds(P, lp, rounds=rounds)
+            ce = oa.ecp_rounds_native(eng, lp, rounds=rounds, duals=root["duals"][0])
+            assert (ce["rounds"], ce["cuts"], ce["installed"]) == (pe["rounds"], pe["cuts"], pe["installed"])
+            assert ce["obj"] == pe["obj"] and ce["violation"] == pe["violation"]
+        eng.close()
