@@ -617,6 +617,7 @@ def main():
             import bench_oa
             eng.close()
             line["oa"] = bench_oa.run(B=512, reps=3, cpu_points=4)
+            line["oa"]["b_oa"] = bench_oa.run_b_oa()
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
