@@ -2,6 +2,7 @@
 // batch-solve callback.  In the product the callback is bnlp_solve_batch on a CUDA engine (bnlp_bb_run_engine in
 // bnlp_api.cu); tests may pass the CPU oracle to check that both give the same MINLP optimum.
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <vector>
 #include <sstream>
@@ -491,6 +492,64 @@ int bnlp_host_selftest(void) {
     c2->get_oas(cs2, X2, true, false);
     EXPECT(cs2.sizeRowCuts() == 2);
     delete c2;
+  }
+  {  // B-OA loop (B200Oa.cpp: oa_run) on closed-form providers, no Python and no engine: min (x - 1.4)^2, x integer in [0, 3].
+     // Objective cuts alpha >= f(xk) + f'(xk)(x - xk); the master is solved by enumeration.  Expected: x = 1, f = 0.16.
+    Ipopt::SmartPtr<TMINLP2TNLP> toy_holder = new TMINLP2TNLP();
+    TMINLP2TNLP &toy = *toy_holder;
+    toy.n = 1; toy.m = 0;
+    toy.var_types = {2}; toy.x_l_ = {0.0}; toy.x_u_ = {3.0}; toy.x_init_ = {3.0};
+    auto f = [](double x) { return (x - 1.4) * (x - 1.4); };
+    BatchSolveFn nlp = [&](int B, const double *XL, const double *XU, const double *, double *OBJ, int *ST, int *IT, double *X, double *,
+                           double *D) {
+      for (int b = 0; b < B; ++b) {
+        const double x = std::min(std::max(1.4, XL[b]), XU[b]);
+        OBJ[b] = f(x); ST[b] = 1; IT[b] = 1;
+        if (X) X[b] = x;
+        if (D) D[2 * b] = D[2 * b + 1] = 0.0;
+      }
+      return 0;
+    };
+    auto cut_at = [&](double xk, CutRows &o) {          // 2(xk-1.4) x - alpha <= 2(xk-1.4) xk - f(xk)
+      const double s = 2 * (xk - 1.4);
+      o.col.push_back(0); o.val.push_back(s); o.col.push_back(1); o.val.push_back(-1.0);
+      o.row_start.push_back((int)o.col.size()); o.lb.push_back(-1.7976931348623157e308); o.ub.push_back(s * xk - f(xk));
+      o.src_row.push_back(0);
+    };
+    OaCutsFn cuts = [&](int B, const double *X, const double *, CutRows &o) { for (int b = 0; b < B; ++b) cut_at(X[b], o); return 0; };
+    OaExtractFn ext = [&](const double *x, const double *, LpRelaxation &lp) {
+      CutRows o; cut_at(x[0], o);
+      lp.n_cols = 2; lp.has_alpha = 1; lp.obj_offset = 0; lp.row_start = o.row_start; lp.col = o.col; lp.val = o.val;
+      lp.row_lb = o.lb; lp.row_ub = o.ub; lp.obj = {0.0, 1.0};
+      return 0;
+    };
+    int master_calls = 0;
+    MasterMipFn master = [&](int nc, int nr, const int *rs, const int *cl, const double *vl, const double *, const double *rub,
+                             const double *clb, const double *cub, const double *, double, const int *isint, double cutoff, double,
+                             double *x, double *bound) {
+      ++master_calls;
+      if (nc != 2 || !isint[0] || isint[1]) return -1;
+      double best = 1e300; int arg = -1;
+      for (int xi = (int)clb[0]; xi <= (int)cub[0]; ++xi) {
+        double alpha = -1e300;
+        for (int r = 0; r < nr; ++r) {
+          double a = 0;
+          for (int e = rs[r]; e < rs[r + 1]; ++e) if (cl[e] == 0) a = vl[e];
+          alpha = std::max(alpha, a * xi - rub[r]);
+        }
+        if (alpha < cutoff && alpha < best) { best = alpha; arg = xi; }
+      }
+      if (arg < 0) return 1;
+      x[0] = arg; x[1] = best; *bound = best;
+      return 0;
+    };
+    OaResult R = oa_run(toy, nlp, cuts, ext, master, OaOptions());
+    EXPECT(R.status == 0 && R.best_x.size() == 1 && R.best_x[0] == 1.0);
+    EXPECT(std::fabs(R.best_obj - 0.16) < 1e-12 && R.nlp_solves == R.passes + 1 && master_calls == R.passes + 1);
+    EXPECT(R.cuts == 2 * R.passes && R.oa_points == 2 * R.passes && R.lower_bound <= R.best_obj + 1e-12);
+    OaOptions one; one.max_passes = 1;
+    R = oa_run(toy, nlp, cuts, ext, master, one);
+    EXPECT(R.status == 2 && R.passes == 1);
   }
 #undef EXPECT
   return 0;
