@@ -603,7 +603,8 @@ def feasibility_check_native(target, lp, col_lb, col_ub, x_lp, cutoff, integer_t
     rs, col, val, lb, ub, clb, cub, obj = _lp_csr(lp, col_lb, col_ub)
     xlp = np.ascontiguousarray(np.asarray(x_lp, float)[:nc])
     cap_cuts, cap_nnz = max_passes * (m + 1), max_passes * (m + 1) * (n + 1)
-    nrs, ncol, nval = np.zeros(cap_cuts + 1, np.int32), np.zeros(cap_nnz, np.int32), np.zeros(cap_nnz)
+    # (np.empty: the capacity is the worst case of max_passes full rounds; untouched pages are never committed)
+    nrs, ncol, nval = np.zeros(cap_cuts + 1, np.int32), np.empty(cap_nnz, np.int32), np.empty(cap_nnz)
     nlb, nub, nsrc = np.zeros(cap_cuts), np.zeros(cap_cuts), np.zeros(cap_cuts, np.int32)
     inc_x, x_out = np.zeros(n), np.zeros(nc)
     res, o = OaFeasResult(), OaFeasOptions(integer_tolerance, cutoff_increment, max_passes)
@@ -739,7 +740,7 @@ def _provider_callbacks(P, failure):
 
 
 def _cut_outs(cap_cuts, cap_nnz):
-    return (np.zeros(cap_cuts + 1, np.int32), np.zeros(max(cap_nnz, 1), np.int32), np.zeros(max(cap_nnz, 1)), np.zeros(max(cap_cuts, 1)),
+    return (np.zeros(cap_cuts + 1, np.int32), np.empty(max(cap_nnz, 1), np.int32), np.empty(max(cap_nnz, 1)), np.zeros(max(cap_cuts, 1)),
             np.zeros(max(cap_cuts, 1)), np.zeros(max(cap_cuts, 1), np.int32))
 
 
